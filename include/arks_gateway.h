@@ -1,0 +1,238 @@
+/*
+ * arks_gateway.h — C ABI of the B200-native arks-gateway-plugins hot path.
+ *
+ * One object (`arks_ctx`, one per GPU) replaces, together, the three plugin seams the reference
+ * ext_proc server calls per request (all paths relative to the reference tree):
+ *
+ *   ratelimiter.RateLimterInterface   pkg/gateway/ratelimiter/rate_limiter.go:21-28
+ *   quota.QuotaService                pkg/gateway/quota/types.go:24-28
+ *   qosconfig.ConfigProvider          pkg/gateway/qosconfig/provider.go:29-37
+ *
+ * plus the per-byte work of the four phase handlers
+ *
+ *   HandleRequestBody                 pkg/gateway/handle_request.go:83-249
+ *   HandleResponseBody                pkg/gateway/handle_response.go:80-268
+ *
+ * The Go host keeps the ext_proc gRPC server (pkg/gateway/gateway.go:77-138) and calls these entry
+ * points through cgo from one OS-thread-locked batcher goroutine per GPU.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every buffer is caller-owned HOST memory unless the name ends
+ *     in `_dev`; the library owns all device memory.
+ *   - the clock is never read inside: every batch carries `now_unix` (seconds). Batches are applied
+ *     in call order; within a batch, requests are applied in index order (the linearisation the
+ *     oracle shares). `now_unix` must not move to an earlier rate-limit window.
+ *   - return value: 0 ok, negative `arks_status`. Per-request outcomes only via the result arrays.
+ *   - there is no CPU fallback: without a CUDA device `arks_create` fails with ARKS_E_NO_DEVICE.
+ */
+#ifndef ARKS_GATEWAY_H
+#define ARKS_GATEWAY_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARKS_ABI_VERSION 1
+
+/* ---- status codes (library-level errors; Go `error` in the reference) ---- */
+enum arks_status {
+  ARKS_S_OK = 0,
+  ARKS_E_INVALID_ARG = -1,
+  ARKS_E_NO_DEVICE = -2,
+  ARKS_E_CUDA = -3,
+  ARKS_E_TIME_WENT_BACK = -4, /* now_unix fell into an earlier window than a previous batch */
+  ARKS_E_BAD_TABLE = -5,      /* unknown rate-limit rule / quota type (reference: 500 / panic,
+                                 pkg/gateway/check.go:112-121, ratelimiter/types.go:46) */
+  ARKS_E_CAPACITY = -6,
+  ARKS_E_NOT_LOADED = -7,
+};
+
+/* ---- rate-limit rules: compiled in, pkg/gateway/ratelimiter/rate_limiter.go:31-68 ---- */
+enum arks_rule {
+  ARKS_RULE_RPM = 0, /* request, 1 minute */
+  ARKS_RULE_RPD = 1, /* request, 1 day    */
+  ARKS_RULE_TPM = 2, /* token,   1 minute */
+  ARKS_RULE_TPD = 3, /* token,   1 day    */
+  ARKS_N_RULES = 4,
+};
+/* quota item types: api/v1/arksquota_types.go:28-33 */
+enum arks_quota_type {
+  ARKS_QT_PROMPT = 0,
+  ARKS_QT_RESPONSE = 1,
+  ARKS_QT_TOTAL = 2,
+  ARKS_N_QT = 3,
+};
+#define ARKS_QUOTA_NONE (-1)    /* qos.quota.name == ""           handle_request.go:185 */
+#define ARKS_QUOTA_MISSING (-2) /* named ArksQuota does not exist check.go:76-84 -> 500 */
+
+/* ---- per-request outcome: (http status, x-error-* header) of SURVEY §8a / pkg/gateway/types.go:24-56 ---- */
+enum arks_reason {
+  ARKS_R_OK = 0,
+  ARKS_R_NO_TOKEN = 1,             /* 401 x-error-token                         handle_request.go:48-56   */
+  ARKS_R_REQUEST_BODY = 2,         /* 400 x-error-request-body-processing       handle_request.go:97-104  */
+  ARKS_R_NO_MODEL = 3,             /* 400 x-error-no-model-in-request           handle_request.go:108-115 */
+  ARKS_R_TOKEN_NOT_FOUND = 4,      /* 500 x-error-token "token not found"       arks_impl.go:313-315      */
+  ARKS_R_MODEL_NOT_IN_TOKEN = 5,   /* 500 x-error-token "model not found"       arks_impl.go:337          */
+  ARKS_R_NO_MODEL_BACKENDS = 6,    /* 400 x-error-no-model-backends             handle_request.go:147-154 */
+  ARKS_R_STREAM_OPTIONS = 7,       /* 400 x-error-no-stream-options-include-usage  :160-171               */
+  ARKS_R_RATE_LIMIT = 8,           /* 429 x-error-rate-limit  (detail = index in qos.RateLimits) check.go:140-152 */
+  ARKS_R_QUOTA = 9,                /* 429 x-error-quota       (detail = index in quota items)   check.go:95-104  */
+  ARKS_R_QUOTA_CONFIG = 10,        /* 500 x-error-quota       (ArksQuota missing)               check.go:76-84   */
+  ARKS_R_STREAMING = 11,           /* 500 x-error-streaming                     handle_response.go:125-133 */
+  ARKS_R_RESPONSE_UNMARSHAL = 12,  /* 500 x-error-response-unmarshal            handle_response.go:157-166 */
+  ARKS_R_RESPONSE_UNKNOWN = 13,    /* 500 x-error-response-unknown              handle_response.go:167-181 */
+  ARKS_R_QUOTA_CONFIG_RESP = 14,   /* 500 x-error-quota at response time        handle_response.go:215-223 */
+  ARKS_R_PENDING = 15,             /* non-stream chunk without end_of_stream: empty CommonResponse :141-149 */
+};
+
+/* ---- config tables: a flat snapshot of the ArksToken / ArksQuota / ArksEndpoint informer cache ----
+ * (qosconfig/arks_impl.go:303-397). Strings live in one pool; string i = str_bytes[str_off[i]..str_off[i+1]).
+ * Equal strings need not share an id; the library resolves names by content. */
+typedef struct arks_tables {
+  const uint8_t* str_bytes;
+  const uint32_t* str_off; /* n_str + 1 */
+  uint32_t n_str;
+
+  /* ArksToken objects, api/v1/arkstoken_types.go:55-61. If two objects carry the same spec.token the
+   * first one in this array wins (reference: Items[0] of an unordered index, arks_impl.go:317). */
+  uint32_t n_tokens;
+  const uint32_t* tok_token_str; /* spec.token                         */
+  const uint32_t* tok_ns_str;    /* metadata.namespace                 */
+  const uint32_t* tok_name_str;  /* metadata.name == UserQos.User      */
+  const uint32_t* tok_qos_off;   /* n_tokens + 1, CSR into qos entries */
+
+  /* spec.qos[] entries, api/v1/arkstoken_types.go:46-52 */
+  uint32_t n_qos;
+  const uint32_t* qos_model_str; /* arksEndpoint.name                                  */
+  const int32_t* qos_quota;      /* index into quotas, ARKS_QUOTA_NONE, ARKS_QUOTA_MISSING */
+  const uint32_t* qos_rl_off;    /* n_qos + 1, CSR into rate limits                    */
+  uint32_t n_rl;
+  const uint8_t* rl_rule;   /* enum arks_rule, in spec order */
+  const int64_t* rl_value;  /* limit                          */
+
+  /* ArksQuota objects, api/v1/arksquota_types.go:36-53 */
+  uint32_t n_quotas;
+  const uint32_t* quota_ns_str;
+  const uint32_t* quota_name_str;
+  const uint32_t* quota_item_off; /* n_quotas + 1 */
+  uint32_t n_qitems;
+  const uint8_t* qitem_type;   /* enum arks_quota_type, in spec order */
+  const int64_t* qitem_value;  /* limit                                */
+
+  /* ArksEndpoint objects, api/v1/arksendpoint_types.go:28-48; backends in the order the controller
+   * emits HTTPRoute backendRefs (internal/controller/arksendpoint_controller.go:283-347): static
+   * routeConfigs first, then ready application Services at defaultWeight. */
+  uint32_t n_endpoints;
+  const uint32_t* ep_ns_str;
+  const uint32_t* ep_name_str;    /* == model name */
+  const uint32_t* ep_backend_off; /* n_endpoints + 1 */
+  uint32_t n_backends;
+  const int32_t* backend_weight;  /* >= 0 */
+} arks_tables;
+
+/* ---- request phase (ProcessingRequest_RequestBody, handle_request.go:83-249) ---- */
+typedef struct arks_request_batch {
+  uint32_t n;
+  const uint8_t* bodies;      /* concatenated request bodies; each body starts 16-byte aligned  */
+  const uint32_t* body_off;   /* n: byte offset of body i (multiple of 16)                      */
+  const uint32_t* body_len;   /* n: exact length                                                */
+  uint64_t bodies_bytes;      /* total size of `bodies` (last body padded up to 16)             */
+  const uint8_t* tokens;      /* concatenated bearer tokens (output of arks_extract_bearer)     */
+  const uint32_t* token_off;  /* n + 1                                                          */
+  const uint64_t* pick_rand;  /* n or NULL: per-request random for the weighted pick (A12)      */
+  int64_t now_unix;
+} arks_request_batch;
+
+typedef struct arks_request_result {
+  uint8_t* reason;      /* n: enum arks_reason; ARKS_R_OK == continue (BodyResponse + 3 headers)            */
+  uint8_t* detail;      /* n: rule / quota-item index for 429s, else 0                                       */
+  uint8_t* flags;       /* n: bit0 = stream                                                                  */
+  int32_t* qos;         /* n: qos-entry index carried into the response phase, -1 if not resolved            */
+  int32_t* token;       /* n: ArksToken index (namespace / username headers), -1 if not found                */
+  int32_t* pick;        /* n: backend index within the endpoint, -1 none / not admitted                      */
+  int64_t* cur_usage;   /* n: RateLimitResponse.currentUsage / QuotaResult.currentUsage for 429s, else 0     */
+  int64_t* limit_max;   /* n: limitMax for 429s, else 0                                                      */
+} arks_request_result;
+
+/* ---- response phase (ProcessingRequest_ResponseBody with :status 200, handle_response.go:80-268) ---- */
+#define ARKS_RESP_STREAM 1u        /* the request had stream:true  -> body is one SSE chunk, decoded in isolation */
+#define ARKS_RESP_END_OF_STREAM 2u /* non-stream: `body` is the complete concatenated response body               */
+typedef struct arks_response_batch {
+  uint32_t n;
+  const uint8_t* bodies;
+  const uint32_t* body_off; /* n, multiples of 16 */
+  const uint32_t* body_len; /* n */
+  uint64_t bodies_bytes;
+  const int32_t* qos;    /* n: from arks_request_result.qos */
+  const uint8_t* flags;  /* n: ARKS_RESP_* */
+  int64_t now_unix;
+} arks_response_batch;
+
+typedef struct arks_response_result {
+  uint8_t* reason;   /* n: ARKS_R_OK / STREAMING / RESPONSE_UNMARSHAL / RESPONSE_UNKNOWN / QUOTA_CONFIG_RESP / PENDING */
+  uint8_t* counted;  /* n: 1 iff usage.total_tokens != 0 (counters were incremented, `complete = true`)               */
+  int64_t* usage;    /* 3n: prompt_tokens, completion_tokens, total_tokens                                           */
+} arks_response_result;
+
+typedef struct arks_ctx arks_ctx;
+
+/* lifecycle */
+int arks_abi_version(void);
+int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_ctx** out);
+void arks_destroy(arks_ctx* ctx);
+const char* arks_last_error(const arks_ctx* ctx);
+
+/* config plane: replaces the informer cache behind qosconfig.ConfigProvider (arks_impl.go:104-189).
+ * A load between batches swaps the whole snapshot; counters are carried over by key
+ * ((namespace,user,model) and (namespace,quotaName)), like Redis keys survive a CRD edit. */
+int arks_load_tables(arks_ctx* ctx, const arks_tables* t);
+/* routing churn (BASELINE config 5): replace the weights of one endpoint's backends in place */
+int arks_update_endpoint_weights(arks_ctx* ctx, uint32_t endpoint, uint32_t n, const int32_t* weights);
+
+/* A2: HandleRequestHeaders bearer extraction (handle_request.go:38-46). Pure host function.
+ * keys/values: n_headers (ptr,len) pairs. Returns token length (>0) and sets *token to point into
+ * the value, 0 when no usable token (-> 401 ARKS_R_NO_TOKEN). */
+size_t arks_extract_bearer(const uint8_t* const* keys, const size_t* key_lens,
+                           const uint8_t* const* values, const size_t* value_lens, size_t n_headers,
+                           const uint8_t** token);
+
+/* request phase: H2D + scan_request + limit_admit (+ pick) + D2H */
+int arks_submit_request_batch(arks_ctx* ctx, const arks_request_batch* b, arks_request_result* r);
+/* response phase: H2D + scan_response + apply_usage + D2H */
+int arks_submit_response_batch(arks_ctx* ctx, const arks_response_batch* b, arks_response_result* r);
+
+/* split form of the two calls above (bench: kernel-only timing with inputs resident in HBM) */
+int arks_stage_request_batch(arks_ctx* ctx, const arks_request_batch* b);  /* H2D only          */
+int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix);               /* kernels only      */
+int arks_fetch_request_result(arks_ctx* ctx, arks_request_result* r);      /* D2H + stream sync */
+int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b);
+int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix);
+int arks_fetch_response_result(arks_ctx* ctx, arks_response_result* r);
+/* CUDA stream handle (cudaStream_t) the kernels are launched on, for event timing by the caller */
+void* arks_stream(arks_ctx* ctx);
+/* number of kernel launches issued by this context so far */
+uint64_t arks_launch_count(const arks_ctx* ctx);
+
+/* quota.QuotaService surface (quota/redis_impl.go:38-107) and A14 snapshot/restore (arks_impl.go:217-300) */
+int arks_snapshot_quota(arks_ctx* ctx, int64_t* usage /* 3 * n_quotas: prompt,response,total */);
+int arks_set_quota_usage(arks_ctx* ctx, uint32_t quota, const int64_t usage[3]); /* SetUsage */
+int arks_incr_quota_usage(arks_ctx* ctx, uint32_t quota, const int64_t delta[3]); /* IncrUsage */
+/* rate counters of the CURRENT windows (value 0 if the stored window is older than now_unix's) */
+int arks_snapshot_rate(arks_ctx* ctx, int64_t now_unix, int64_t* counters /* 4 * n_qos */);
+
+/* multi-GPU: fold per-GPU deltas of quotas shared across GPUs. `delta_out` receives this
+ * GPU's not-yet-folded deltas (3*n_quotas) and zeroes them; `arks_apply_quota_delta` adds the reduced
+ * remote part. The reduction itself is the caller's (NCCL all-reduce of int64). */
+int arks_take_quota_delta(arks_ctx* ctx, int64_t* delta_out);
+int arks_apply_quota_delta(arks_ctx* ctx, const int64_t* remote_delta);
+/* device pointer of the delta vector (3*n_quotas int64) for an in-place ncclAllReduce */
+void* arks_quota_delta_dev(arks_ctx* ctx);
+int arks_fold_quota_delta_dev(arks_ctx* ctx, const void* reduced_dev, const void* own_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARKS_GATEWAY_H */
