@@ -1,0 +1,769 @@
+// json_machine.cuh — per-lane byte state machines for the gateway hot path (device code, sm_100a).
+//
+// One lane == one body. The machine is a pushdown automaton that consumes one byte per step and never
+// looks back, so the kernels can feed it from shared-memory tiles staged with cp.async while 31
+// neighbouring lanes parse 31 other bodies in lock step.
+//
+// Three configurations of the same engine (reference call sites, paths relative to the reference tree):
+//   K_REQ   request body   -> {model, stream, stream_options.include_usage}   pkg/gateway/handle_request.go:87-104
+//   K_RESP  response body  -> {model, usage{prompt,completion,total}}         pkg/gateway/handle_response.go:89-93,157
+//   K_EVT   one SSE event's data -> {error?, len(choices)==0, usage}          pkg/gateway/handle_response.go:113-124
+// K_REQ/K_RESP follow json-iterator v1.1.12 (ConfigFastest: case-insensitive field hash, strict skip,
+// last duplicate wins); K_EVT follows encoding/json validation + gjson/apijson extraction. The grammar and
+// its documented divergences are the ones the oracle states (oracle/ork_json.c header).
+//
+// The file is host+device so that tests/ can compile it with g++ and fuzz it against the oracle on CPU
+// (tests/test_machine_vs_oracle.py); the shipped library only instantiates it inside CUDA kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ARKS_HD __host__ __device__ __forceinline__
+#else
+#define ARKS_HD inline
+#endif
+
+namespace arks {
+
+enum : uint8_t { K_REQ = 0, K_RESP = 1, K_EVT = 2 };
+
+// token-level states first (they share the whitespace skip), then in-token states
+enum : uint8_t {
+  S_TOP = 0,       // jsoniter readObjectStart at depth 0 (K_REQ / K_RESP)
+  S_VAL,           // expecting a value
+  S_ARR_FIRST,     // after '[': value or ']'
+  S_OBJ_FIRST,     // after '{' (ReadObjectCB / encoding/json): key string or '}'
+  S_OBJ_KEY,       // after ',' in such an object: key string (jsoniter also accepts the literal null)
+  S_STRUCT_FIRST,  // after '{' in a jsoniter struct decoder: '}' or key
+  S_STRUCT_KEY,    // after ',' in a struct decoder (readFieldHash): key
+  S_COLON,         // expecting ':'
+  S_AFTER,         // after a value inside a container: ',' or closer
+  S_FINISH,        // top-level value complete: only whitespace may follow
+  S_TOKEN_STATES,  // ---- marker
+  S_STR,           // in string, no backslash seen yet
+  S_STR_E,         // in string, a backslash has been seen
+  S_ESC,           // byte after a backslash
+  S_U,             // \uXXXX hex digits
+  S_LIT,           // rest of null / true / false
+  S_NUM,           // number
+  S_STOP,          // jsoniter Unmarshal met a NUL byte after the value: accepted, rest ignored
+};
+
+// what a string is (decides what happens at its closing quote)
+enum : uint8_t { SK_VALUE_SKIP = 0, SK_VALUE_MODEL, SK_VALUE_UINT, SK_KEY_SKIP, SK_KEY_STRUCT, SK_KEY_EXACT };
+// how the next value is consumed
+enum : uint8_t { VM_SKIP = 0, VM_MODEL, VM_BOOL_STREAM, VM_BOOL_IU, VM_SO, VM_USAGE, VM_UINT, VM_ECHOICES };
+// special object one level below the top-level object
+enum : uint8_t { L2_NONE = 0, L2_SO, L2_USAGE };
+// RFC 8259 number DFA
+enum : uint8_t { F_MINUS = 0, F_ZERO, F_INT, F_DOT, F_FRAC, F_E, F_ESIGN, F_EXP, F_DEAD };
+
+static constexpr uint32_t kMaxDepth = 10000;  // jsoniter maxDepth == encoding/json maxNestingDepth
+
+// jsoniter readFieldHash: int64 0x811c9dc5, ^= lower(byte), *= 0x1000193 (iter_object.go)
+ARKS_HD constexpr uint64_t fhash_step(uint64_t h, uint8_t b) {
+  return (h ^ (uint64_t)((b >= 'A' && b <= 'Z') ? b + 32 : b)) * 0x1000193ull;
+}
+ARKS_HD constexpr uint64_t fhash_lit(const char* s, int n) {
+  uint64_t h = 0x811c9dc5ull;
+  for (int i = 0; i < n; i++) h = fhash_step(h, (uint8_t)s[i]);
+  return h;
+}
+static constexpr uint64_t H_MODEL = fhash_lit("model", 5);
+static constexpr uint64_t H_STREAM = fhash_lit("stream", 6);
+static constexpr uint64_t H_SO = fhash_lit("stream_options", 14);
+static constexpr uint64_t H_IU = fhash_lit("include_usage", 13);
+static constexpr uint64_t H_USAGE = fhash_lit("usage", 5);
+
+// exact-key candidates (gjson Map(): case-sensitive, unescaped)
+ARKS_HD constexpr uint64_t xhash_step(uint64_t h, uint8_t b) { return (h ^ (uint64_t)b) * 0x100000001b3ull; }
+ARKS_HD constexpr uint64_t xhash_lit(const char* s, int n) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (int i = 0; i < n; i++) h = xhash_step(h, (uint8_t)s[i]);
+  return h;
+}
+// ids: 0 prompt_tokens 1 completion_tokens 2 total_tokens 3 error 4 choices 5 usage
+ARKS_HD const char* xkey_str(int id) {
+  switch (id) {
+    case 0: return "prompt_tokens";
+    case 1: return "completion_tokens";
+    case 2: return "total_tokens";
+    case 3: return "error";
+    case 4: return "choices";
+    default: return "usage";
+  }
+}
+ARKS_HD constexpr int xkey_len(int id) { return id == 0 ? 13 : id == 1 ? 17 : id == 2 ? 12 : id == 3 ? 5 : id == 4 ? 7 : 5; }
+static constexpr uint64_t X_PROMPT = xhash_lit("prompt_tokens", 13);
+static constexpr uint64_t X_COMPL = xhash_lit("completion_tokens", 17);
+static constexpr uint64_t X_TOTAL = xhash_lit("total_tokens", 12);
+static constexpr uint64_t X_ERROR = xhash_lit("error", 5);
+static constexpr uint64_t X_CHOICES = xhash_lit("choices", 7);
+static constexpr uint64_t X_USAGE = xhash_lit("usage", 5);
+
+ARKS_HD bool is_ws(uint8_t c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r'; }
+ARKS_HD bool is_digit(uint8_t c) { return (uint8_t)(c - '0') <= 9; }
+ARKS_HD int hexval(uint8_t c) {
+  if (is_digit(c)) return c - '0';
+  uint8_t l = c | 0x20;
+  if (l >= 'a' && l <= 'f') return l - 'a' + 10;
+  return -1;
+}
+
+// ---- slow paths over an already validated raw string span (only when the span contains a backslash) ----
+// Decodes jsoniter-style (readEscapedChar: surrogate pairing, lone surrogates -> U+FFFD) and feeds every
+// output byte to `f`. The span is known to be well-formed.
+template <class F>
+ARKS_HD void decode_span(const uint8_t* p, uint32_t n, F&& f) {
+  auto put_rune = [&](uint32_t r) {
+    if (r <= 0x7F) {
+      f((uint8_t)r);
+    } else if (r <= 0x7FF) {
+      f((uint8_t)(0xC0 | (r >> 6)));
+      f((uint8_t)(0x80 | (r & 0x3F)));
+    } else {
+      if (r > 0x10FFFF || (r >= 0xD800 && r <= 0xDFFF)) r = 0xFFFD;
+      if (r <= 0xFFFF) {
+        f((uint8_t)(0xE0 | (r >> 12)));
+        f((uint8_t)(0x80 | ((r >> 6) & 0x3F)));
+        f((uint8_t)(0x80 | (r & 0x3F)));
+      } else {
+        f((uint8_t)(0xF0 | (r >> 18)));
+        f((uint8_t)(0x80 | ((r >> 12) & 0x3F)));
+        f((uint8_t)(0x80 | ((r >> 6) & 0x3F)));
+        f((uint8_t)(0x80 | (r & 0x3F)));
+      }
+    }
+  };
+  auto u4 = [&](uint32_t i) {
+    return (uint32_t)((hexval(p[i]) << 12) | (hexval(p[i + 1]) << 8) | (hexval(p[i + 2]) << 4) | hexval(p[i + 3]));
+  };
+  uint32_t i = 0;
+  while (i < n) {
+    uint8_t c = p[i++];
+    if (c != '\\') {
+      f(c);
+      continue;
+    }
+    uint8_t e = p[i++];
+    for (;;) {  // readEscapedChar, with its tail call unrolled into this loop
+      if (e == 'u') {
+        uint32_t r = u4(i);
+        i += 4;
+        if (r >= 0xD800 && r <= 0xDFFF) {
+          if (i >= n || p[i] != '\\') {
+            put_rune(r);
+            break;
+          }
+          i++;  // the backslash
+          e = p[i++];
+          if (e != 'u') {
+            put_rune(r);
+            continue;  // readEscapedChar(e)
+          }
+          uint32_t r2 = u4(i);
+          i += 4;
+          if (r < 0xDC00 && r2 >= 0xDC00 && r2 < 0xE000) {
+            put_rune((((r - 0xD800) << 10) | (r2 - 0xDC00)) + 0x10000);
+          } else {
+            put_rune(r);
+            put_rune(r2);
+          }
+        } else {
+          put_rune(r);
+        }
+        break;
+      }
+      uint8_t o = e;  // " \ / stay themselves
+      if (e == 'b') o = '\b';
+      else if (e == 'f') o = '\f';
+      else if (e == 'n') o = '\n';
+      else if (e == 'r') o = '\r';
+      else if (e == 't') o = '\t';
+      f(o);
+      break;
+    }
+  }
+}
+
+struct JsonM {
+  // ---- configuration ----
+  const uint8_t* base;  // body bytes (global memory): only slow paths and key verification read it
+  uint8_t kind;
+  // ---- automaton ----
+  uint8_t st, err, vm, skind, s_esc, ucnt, lit_is_key;
+  uint8_t nf, tsn, tsn_any, tsn_dot, tsn_need, ncap;  // number sub-machines
+  uint8_t l2, in_choices, ufield;
+  uint32_t lit;      // remaining literal bytes, low byte first
+  uint32_t depth;
+  uint32_t sstart;   // offset of the first content byte of the current string
+  uint64_t khash;
+  uint32_t cur_word; // cached word of the container-type stack (bit = 1 object, 0 array)
+  // number capture (usage counters; gjson Result.Int)
+  uint64_t nacc;     // wrapping decimal accumulation of all digits of the mantissa
+  uint8_t nneg, nplain, novf, sval_ok, sval_any, ncphase;
+  int32_t nfrac, nexp;
+  uint8_t nexpneg;
+  // ---- outputs ----
+  uint32_t m_start, m_rawlen;  // model string raw span
+  uint8_t m_esc;               // raw span contains a backslash
+  uint8_t stream3, so_present, iu3;
+  int64_t usage[3];
+  int64_t cand[3];
+  uint8_t cand_set, cand_nonnull;
+  uint8_t has_error_key, n_choices;
+  uint32_t stk[(kMaxDepth + 31) / 32 + 1];
+
+  ARKS_HD void init(uint8_t k, const uint8_t* b) {
+    base = b;
+    kind = k;
+    st = (k == K_EVT) ? S_VAL : S_TOP;
+    err = 0;
+    vm = VM_SKIP;
+    skind = 0; s_esc = 0; ucnt = 0; lit_is_key = 0;
+    nf = 0; tsn = 0; tsn_any = 0; tsn_dot = 0; tsn_need = 0; ncap = 0;
+    l2 = L2_NONE; in_choices = 0; ufield = 255;
+    lit = 0; depth = 0; sstart = 0; khash = 0; cur_word = 0;
+    nacc = 0; nneg = 0; nplain = 1; novf = 0; sval_ok = 0; sval_any = 0; nfrac = 0; nexp = 0; nexpneg = 0; ncphase = 0;
+    m_start = 0; m_rawlen = 0; m_esc = 0;
+    stream3 = 0; so_present = 0; iu3 = 0;
+    usage[0] = usage[1] = usage[2] = 0;
+    cand[0] = cand[1] = cand[2] = 0;
+    cand_set = 0; cand_nonnull = 0;
+    has_error_key = 0; n_choices = 0;
+  }
+  // restart for the next SSE event (fresh ChatCompletionChunk per event)
+  ARKS_HD void reset_event() {
+    const uint8_t* b = base;
+    init(K_EVT, b);
+  }
+
+  ARKS_HD bool top_is_object() const { return (cur_word >> ((depth - 1) & 31)) & 1u; }
+  ARKS_HD void push(bool is_obj) {
+    if (depth >= kMaxDepth) {
+      err = 1;
+      return;
+    }
+    uint32_t nd = depth + 1;
+    if (depth > 0 && ((nd - 1) >> 5) != ((depth - 1) >> 5)) {
+      stk[(depth - 1) >> 5] = cur_word;
+      cur_word = 0;
+    }
+    uint32_t bit = 1u << ((nd - 1) & 31);
+    cur_word = is_obj ? (cur_word | bit) : (cur_word & ~bit);
+    depth = nd;
+  }
+  ARKS_HD void pop() {
+    uint32_t nd = depth - 1;
+    if (nd > 0 && ((nd - 1) >> 5) != ((depth - 1) >> 5)) cur_word = stk[(nd - 1) >> 5];
+    depth = nd;
+  }
+  ARKS_HD void value_done() { st = depth == 0 ? S_FINISH : S_AFTER; }
+
+  ARKS_HD void commit_usage_cands() {
+    // apijson struct decoder over node.Map(): last duplicate wins; null leaves the field untouched
+    for (int f = 0; f < 3; f++)
+      if ((cand_set >> f) & (cand_nonnull >> f) & 1) usage[f] = cand[f];
+  }
+  ARKS_HD void close_container(uint8_t c) {
+    bool obj = top_is_object();
+    if ((c == '}') != obj) {
+      err = 1;
+      return;
+    }
+    if (depth == 2) {
+      if (l2 == L2_USAGE) commit_usage_cands();
+      l2 = L2_NONE;
+      in_choices = 0;
+    }
+    pop();
+    value_done();
+  }
+
+  ARKS_HD void begin_string(uint8_t kindv, uint32_t pos) {
+    skind = kindv;
+    s_esc = 0;
+    sstart = pos + 1;
+    st = S_STR;
+    khash = (kindv == SK_KEY_STRUCT) ? 0x811c9dc5ull : 0xcbf29ce484222325ull;
+    if (kindv == SK_VALUE_UINT) {
+      nacc = 0; nneg = 0; sval_ok = 1; sval_any = 0;
+    }
+  }
+  ARKS_HD void begin_key(uint32_t pos) {
+    uint8_t k = SK_KEY_SKIP;
+    if (kind != K_EVT) {
+      if (depth == 1 || (depth == 2 && l2 == L2_SO)) k = SK_KEY_STRUCT;
+      else if (depth == 2 && l2 == L2_USAGE) k = SK_KEY_EXACT;
+    } else {
+      if (depth == 1 || (depth == 2 && l2 == L2_USAGE)) k = SK_KEY_EXACT;
+    }
+    begin_string(k, pos);
+  }
+  ARKS_HD void begin_literal(uint8_t c, bool as_key) {
+    // remaining bytes, low byte first
+    lit = c == 'n' ? 0x006c6c75u /*ull*/ : c == 't' ? 0x00657572u /*rue*/ : 0x65736c61u /*alse*/;
+    lit_is_key = as_key;
+    st = S_LIT;
+  }
+  ARKS_HD void begin_number(uint8_t c) {
+    st = S_NUM;
+    tsn = (kind != K_EVT) && c != '0';  // jsoniter: '0' goes straight to ReadFloat32, others trySkipNumber first
+    tsn_any = 0; tsn_dot = 0; tsn_need = 0;
+    nf = c == '-' ? F_MINUS : c == '0' ? F_ZERO : F_INT;
+    if (ncap) {
+      nneg = c == '-';
+      nacc = c == '-' ? 0 : (uint64_t)(c - '0');
+      nplain = 1; novf = 0; nfrac = 0; nexp = 0; nexpneg = 0; ncphase = 0;
+    }
+  }
+  // value start byte (whitespace already skipped)
+  ARKS_HD void begin_value(uint8_t c, uint32_t pos) {
+    uint8_t m = vm;
+    vm = VM_SKIP;
+    ncap = 0;
+    switch (m) {
+      case VM_MODEL:  // stringCodec -> ReadString: string or null
+        if (c == '"') begin_string(SK_VALUE_MODEL, pos);
+        else if (c == 'n') { m_start = 0; m_rawlen = 0; m_esc = 0; begin_literal(c, false); }
+        else err = 1;
+        return;
+      case VM_BOOL_STREAM:
+      case VM_BOOL_IU: {  // OptionalDecoder{boolCodec}: ReadNil / ReadBool
+        uint8_t v;
+        if (c == 'n') v = 0; else if (c == 'f') v = 1; else if (c == 't') v = 2;
+        else { err = 1; return; }
+        if (m == VM_BOOL_STREAM) stream3 = v; else iu3 = v;
+        begin_literal(c, false);
+        return;
+      }
+      case VM_SO:  // OptionalDecoder{oneFieldStructDecoder}
+        if (c == 'n') { so_present = 0; iu3 = 0; begin_literal(c, false); }
+        else if (c == '{') { so_present = 1; push(true); l2 = L2_SO; st = S_STRUCT_FIRST; }
+        else err = 1;
+        return;
+      case VM_UINT:  // a usage counter: gjson Result.Int by JSON type
+        cand_set |= (uint8_t)(1u << ufield);
+        cand_nonnull |= (uint8_t)(1u << ufield);
+        cand[ufield] = 0;
+        if (c == '"') { begin_string(SK_VALUE_UINT, pos); return; }
+        if (c == 't') cand[ufield] = 1;
+        if (c == 'n') cand_nonnull &= (uint8_t)~(1u << ufield);
+        ncap = 1;
+        break;  // generic dispatch below (ncap only matters for numbers)
+      case VM_USAGE:
+        if (kind == K_EVT) { usage[0] = usage[1] = usage[2] = 0; }  // Map(): the last "usage" member wins outright
+        cand_set = 0; cand_nonnull = 0;
+        if (c == '{') { push(true); l2 = L2_USAGE; st = S_OBJ_FIRST; return; }
+        break;
+      case VM_ECHOICES:
+        n_choices = 0;
+        if (c == '[') { push(false); in_choices = 1; st = S_ARR_FIRST; return; }
+        break;
+      default: break;
+    }
+    // Iterator.Skip / encoding/json value
+    if (c == '"') begin_string(SK_VALUE_SKIP, pos);
+    else if (c == 'n' || c == 't' || c == 'f') begin_literal(c, false);
+    else if (c == '-' || is_digit(c)) begin_number(c);
+    else if (c == '[') { push(false); st = S_ARR_FIRST; }
+    else if (c == '{') { push(true); st = S_OBJ_FIRST; }
+    else err = 1;
+  }
+
+  // ---- key dispatch at the closing quote ----
+  ARKS_HD void struct_key_end(uint32_t pos) {
+    uint64_t h = khash;
+    if (s_esc) {  // readFieldHash slow path: hash continues over the decoded remainder
+      // bytes before the first backslash were hashed incrementally; find it again
+      const uint8_t* p = base + sstart;
+      uint32_t n = pos - sstart, i = 0;
+      h = 0x811c9dc5ull;
+      while (p[i] != '\\') h = fhash_step(h, p[i++]);
+      decode_span(p + i, n - i, [&](uint8_t b) { h = fhash_step(h, b); });
+    }
+    if (depth == 1) {
+      if (h == H_MODEL) vm = VM_MODEL;
+      else if (kind == K_REQ && h == H_STREAM) vm = VM_BOOL_STREAM;
+      else if (kind == K_REQ && h == H_SO) vm = VM_SO;
+      else if (kind == K_RESP && h == H_USAGE) vm = VM_USAGE;
+    } else {
+      if (h == H_IU) vm = VM_BOOL_IU;
+    }
+  }
+  ARKS_HD bool exact_verify(int id, uint32_t pos) const {
+    const char* s = xkey_str(id);
+    int L = xkey_len(id);
+    const uint8_t* p = base + sstart;
+    uint32_t n = pos - sstart;
+    if (!s_esc) {
+      if ((int)n != L) return false;
+      for (int i = 0; i < L; i++)
+        if (p[i] != (uint8_t)s[i]) return false;
+      return true;
+    }
+    int k = 0;
+    bool ok = true;
+    decode_span(p, n, [&](uint8_t b) {
+      if (k >= L || (uint8_t)s[k] != b) ok = false;
+      k++;
+    });
+    return ok && k == L;
+  }
+  ARKS_HD void exact_key_end(uint32_t pos) {
+    int lo, hi;
+    if (depth == 2) { lo = 0; hi = 3; } else { lo = 3; hi = 6; }
+    int hit = -1;
+    if (!s_esc) {
+      uint64_t h = khash;
+      for (int id = lo; id < hi; id++) {
+        uint64_t want = id == 0 ? X_PROMPT : id == 1 ? X_COMPL : id == 2 ? X_TOTAL : id == 3 ? X_ERROR : id == 4 ? X_CHOICES : X_USAGE;
+        if (h == want && exact_verify(id, pos)) hit = id;
+      }
+    } else {
+      for (int id = lo; id < hi; id++)
+        if (exact_verify(id, pos)) hit = id;
+    }
+    if (hit < 0) return;
+    if (hit < 3) { ufield = (uint8_t)hit; vm = VM_UINT; }
+    else if (hit == 3) has_error_key = 1;
+    else if (hit == 4) vm = VM_ECHOICES;
+    else vm = VM_USAGE;
+  }
+
+  ARKS_HD void end_string(uint32_t pos) {
+    switch (skind) {
+      case SK_VALUE_SKIP: value_done(); break;
+      case SK_VALUE_MODEL:
+        m_start = sstart; m_rawlen = pos - sstart; m_esc = s_esc;
+        value_done();
+        break;
+      case SK_VALUE_UINT: {  // gjson String -> parseInt(t.Str)
+        int64_t v = 0;
+        if (!s_esc && sval_ok && sval_any) v = nneg ? (int64_t)(0 - nacc) : (int64_t)nacc;
+        cand[ufield] = v;
+        value_done();
+        break;
+      }
+      case SK_KEY_SKIP: st = S_COLON; break;
+      case SK_KEY_STRUCT: struct_key_end(pos); st = S_COLON; break;
+      default: exact_key_end(pos); st = S_COLON; break;
+    }
+  }
+
+  // gjson Result.Int for a Number token; called when the number ends
+  ARKS_HD void finish_number_capture() {
+    if (!ncap) return;
+    ncap = 0;
+    int64_t v;
+    if (nplain) {
+      v = nneg ? (int64_t)(0 - nacc) : (int64_t)nacc;  // safeInt / parseInt agree with a wrapping parse
+    } else {
+      // mantissa * 10^(exp - frac) truncated toward zero; exact for the documented domain (<= 18 digits)
+      int64_t e10 = (int64_t)(nexpneg ? -nexp : nexp) - (int64_t)nfrac;
+      uint64_t m = nacc;
+      bool ovf = novf;
+      if (m == 0) { v = 0; }
+      else {
+        while (e10 < 0 && m) { m /= 10; e10++; }
+        while (e10 > 0 && !ovf) {
+          if (m > 0xFFFFFFFFFFFFFFFFull / 10) ovf = true; else m *= 10;
+          e10--;
+        }
+        if (ovf || m > 0x7FFFFFFFFFFFFFFFull) v = INT64_MIN;
+        else v = nneg ? -(int64_t)m : (int64_t)m;
+      }
+    }
+    cand[ufield] = v;
+  }
+
+  // returns true when `c` was consumed, false when the number ended before `c` (reprocess it)
+  ARKS_HD bool step_number(uint8_t c) {
+    const bool numbyte = is_digit(c) || c == '.' || c == 'e' || c == 'E' || c == '+' || c == '-';
+    if (tsn) {  // jsoniter trySkipNumber (iter_skip_strict.go)
+      if (tsn_need) {
+        if (!is_digit(c)) { err = 1; return true; }  // "missing digit after dot"
+        tsn_need = 0;
+      } else if (is_digit(c)) {
+      } else if (c == '.') {
+        if (tsn_dot) { err = 1; return true; }  // "more than one dot found in number"
+        tsn_dot = 1;
+        tsn_need = 1;
+      } else if (c == ',' || c == ']' || c == '}' || c == ' ' || c == '\t' || c == '\n' || c == '\r') {
+        if (tsn_any) {  // accepted without further validation
+          finish_number_capture();
+          value_done();
+          return false;
+        }
+        tsn = 0;  // lone first char: defer to the float reader
+      } else {
+        tsn = 0;
+      }
+      tsn_any = 1;
+    }
+    // RFC 8259 number DFA, tracked from the first byte (divergence D1 when reached from jsoniter's fallback)
+    if (!numbyte) {  // the token ends before c
+      if (nf == F_ZERO || nf == F_INT || nf == F_FRAC || nf == F_EXP) {
+        finish_number_capture();
+        value_done();
+        return false;
+      }
+      err = 1;
+      return true;
+    }
+    uint8_t f = nf, nx = F_DEAD;
+    if (is_digit(c)) {
+      if (f == F_MINUS) nx = c == '0' ? F_ZERO : F_INT;
+      else if (f == F_INT) nx = F_INT;
+      else if (f == F_DOT || f == F_FRAC) nx = F_FRAC;
+      else if (f == F_E || f == F_ESIGN || f == F_EXP) nx = F_EXP;
+    } else if (c == '.') {
+      if (f == F_ZERO || f == F_INT) nx = F_DOT;
+    } else if (c == 'e' || c == 'E') {
+      if (f == F_ZERO || f == F_INT || f == F_FRAC) nx = F_E;
+    } else {
+      if (f == F_E) nx = F_ESIGN;
+    }
+    nf = nx;
+    if (nx == F_DEAD && !tsn) {  // readNumberAsString would swallow this byte and the parse would fail
+      err = 1;
+      return true;
+    }
+    if (ncap) {
+      if (is_digit(c)) {
+        if (ncphase == 2) {
+          if (nexp < 100000) nexp = nexp * 10 + (c - '0');
+        } else {
+          if (nacc > (0xFFFFFFFFFFFFFFFFull - 9) / 10) novf = 1;
+          nacc = nacc * 10 + (uint64_t)(c - '0');
+          if (ncphase == 1) nfrac++;
+        }
+      } else {
+        nplain = 0;
+        if (c == '.') ncphase = 1;
+        else if (c == 'e' || c == 'E') ncphase = 2;
+        else if (c == '-' && ncphase == 2) nexpneg = 1;
+      }
+    }
+    return true;
+  }
+
+  ARKS_HD void step(uint8_t c, uint32_t pos) {
+    for (;;) {
+      if (err | (st == S_STOP)) return;
+      if (st < S_TOKEN_STATES) {
+        if (is_ws(c)) return;
+        switch (st) {
+          case S_TOP:  // readObjectStart
+            if (c == '{') { push(true); st = S_STRUCT_FIRST; }
+            else if (c == 'n') begin_literal(c, false);
+            else err = 1;
+            return;
+          case S_VAL: begin_value(c, pos); return;
+          case S_ARR_FIRST:
+            if (c == ']') { close_container(c); return; }
+            if (in_choices && depth == 2) n_choices = 1;
+            begin_value(c, pos);
+            return;
+          case S_OBJ_FIRST:
+            if (c == '"') begin_key(pos);
+            else if (c == '}') close_container(c);
+            else err = 1;
+            return;
+          case S_OBJ_KEY:
+            if (c == '"') begin_key(pos);
+            else if (c == 'n' && kind != K_EVT) begin_literal(c, true);  // ReadString() accepts null as a key
+            else err = 1;
+            return;
+          case S_STRUCT_FIRST:
+            if (c == '}') close_container(c);
+            else if (c == '"') begin_key(pos);
+            else err = 1;
+            return;
+          case S_STRUCT_KEY:
+            if (c == '"') begin_key(pos);
+            else err = 1;
+            return;
+          case S_COLON:
+            if (c == ':') st = S_VAL;
+            else err = 1;
+            return;
+          case S_AFTER:
+            if (c == ',') {
+              if (top_is_object()) {
+                bool strct = kind != K_EVT && (depth == 1 || (depth == 2 && l2 == L2_SO));
+                st = strct ? S_STRUCT_KEY : S_OBJ_KEY;
+                vm = VM_SKIP;
+              } else {
+                st = S_VAL;
+                vm = VM_SKIP;
+              }
+            } else if (c == '}' || c == ']') {
+              close_container(c);
+            } else {
+              err = 1;
+            }
+            return;
+          default:  // S_FINISH
+            if (c == 0 && kind != K_EVT) st = S_STOP;  // frozenConfig.Unmarshal: `if c == 0` also matches a NUL byte
+            else err = 1;
+            return;
+        }
+      }
+      switch (st) {
+        case S_STR:
+          if (c == '"') { end_string(pos); return; }
+          if (c == '\\') { s_esc = 1; st = S_ESC; return; }
+          if (c < 0x20 && skind != SK_KEY_STRUCT) { err = 1; return; }  // readFieldHash has no such check
+          if (skind >= SK_KEY_STRUCT) khash = skind == SK_KEY_STRUCT ? fhash_step(khash, c) : xhash_step(khash, c);
+          else if (skind == SK_VALUE_UINT) {
+            if (c == '-' && !sval_any && !nneg && pos == sstart) nneg = 1;
+            else if (is_digit(c)) { nacc = nacc * 10 + (uint64_t)(c - '0'); sval_any = 1; }
+            else sval_ok = 0;
+          }
+          return;
+        case S_STR_E:
+          if (c == '"') { end_string(pos); return; }
+          if (c == '\\') { st = S_ESC; return; }
+          if (c < 0x20 && kind == K_EVT) err = 1;  // jsoniter's slow path does not check control characters
+          return;
+        case S_ESC:
+          if (c == 'u') { ucnt = 4; st = S_U; }
+          else if (c == '"' || c == '\\' || c == '/' || c == 'b' || c == 'f' || c == 'n' || c == 'r' || c == 't') st = S_STR_E;
+          else err = 1;
+          return;
+        case S_U:
+          if (hexval(c) < 0) { err = 1; return; }
+          if (--ucnt == 0) st = S_STR_E;
+          return;
+        case S_LIT:
+          if (c != (uint8_t)(lit & 0xff)) { err = 1; return; }
+          lit >>= 8;
+          if (lit == 0) {
+            if (lit_is_key) st = S_COLON; else value_done();
+          }
+          return;
+        default:  // S_NUM
+          if (step_number(c)) return;
+          break;  // reprocess c in the new state
+      }
+    }
+  }
+
+  // end of input: jsoniter Unmarshal / encoding/json checkValid verdict
+  ARKS_HD bool ok_at_end() const { return !err && (st == S_FINISH || st == S_STOP); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// SSE chunk machine: bufio.Scanner(ScanLines) + eventStreamDecoder.Next + Stream.Next
+// (openai-go packages/ssestream, restated in oracle/ork_json.c: ork_sse_chunk / sse_event)
+// ---------------------------------------------------------------------------------------------
+struct SseM {
+  JsonM ev;
+  int64_t usage[3];
+  uint32_t line_len;   // raw bytes of the current line (CR included)
+  uint32_t name_len;   // bytes of the field name seen so far
+  uint64_t name_acc;   // first 8 name bytes, little endian
+  uint32_t data_pos;   // bytes of event data fed so far
+  uint64_t data_head;  // first 8 bytes of the event data (the [DONE] probe)
+  uint32_t ev_match;   // progress of matching the event type against "thread."
+  uint8_t phase;       // 0 name, 1 just after ':', 2 value
+  uint8_t field;       // 0 other, 1 data, 2 event
+  uint8_t pending_cr, done, fail, thread_evt, ev_len_any;
+
+  ARKS_HD void init(const uint8_t* base) {
+    ev.init(K_EVT, base);
+    usage[0] = usage[1] = usage[2] = 0;
+    line_len = 0; name_len = 0; name_acc = 0; data_pos = 0; data_head = 0; ev_match = 0;
+    phase = 0; field = 0; pending_cr = 0; done = 0; fail = 0; thread_evt = 0; ev_len_any = 0;
+  }
+  ARKS_HD void feed_data(uint8_t c, uint32_t pos) {
+    if (data_pos < 8) data_head |= (uint64_t)c << (8 * data_pos);
+    data_pos++;
+    if (!done) ev.step(c, pos);
+  }
+  ARKS_HD void classify_name() {
+    if (name_len == 4 && (uint32_t)name_acc == 0x61746164u /*data*/) field = 1;
+    else if (name_len == 5 && (name_acc & 0xFFFFFFFFFFull) == 0x746e657665ull /*event*/) field = 2;
+    else field = 0;
+    if (field == 2) { ev_match = 0; thread_evt = 0; }  // `event = string(value)`: the last event line wins
+  }
+  ARKS_HD void line_byte(uint8_t c, uint32_t pos) {
+    if (phase == 0) {
+      if (c == ':') { classify_name(); phase = 1; return; }
+      if (name_len < 8) name_acc |= (uint64_t)c << (8 * name_len);
+      name_len++;
+      return;
+    }
+    if (phase == 1) {
+      phase = 2;
+      if (c == ' ') return;  // one optional space after the colon
+    }
+    if (field == 1) feed_data(c, pos);
+    else if (field == 2) {
+      static const char T[8] = {'t', 'h', 'r', 'e', 'a', 'd', '.', 0};
+      if (ev_match < 7) {
+        if (ev_match != 0xFFu && (uint8_t)T[ev_match] == c) { if (++ev_match == 7) thread_evt = 1; }
+        else ev_match = 0xFF;
+      }
+    }
+  }
+  ARKS_HD void dispatch() {
+    // Stream.Next for one event
+    if (!done) {
+      bool is_done = data_pos >= 6 && (data_head & 0xFFFFFFFFFFFFull) == 0x5d454e4f445bull;  // "[DONE]"
+      if (is_done) done = 1;
+      else if (!ev.ok_at_end() || ev.has_error_key) fail = 1;
+      else {
+        bool wrapped = thread_evt;
+        uint8_t nc = wrapped ? 0 : ev.n_choices;
+        if (nc == 0) {  // handle_response.go:119-123
+          usage[0] = wrapped ? 0 : ev.usage[0];
+          usage[1] = wrapped ? 0 : ev.usage[1];
+          usage[2] = wrapped ? 0 : ev.usage[2];
+        }
+      }
+    }
+    ev.reset_event();
+    data_pos = 0; data_head = 0; thread_evt = 0; ev_match = 0;
+  }
+  ARKS_HD void end_line(uint32_t pos) {
+    // line content complete (CR already dropped)
+    uint32_t content = line_len - (pending_cr ? 1 : 0);
+    if (content == 0) {
+      dispatch();
+    } else {
+      if (phase == 0) classify_name();  // no colon: the whole line is the field name
+      if (field == 1) feed_data('\n', pos);
+    }
+    line_len = 0; name_len = 0; name_acc = 0; phase = 0; field = 0; pending_cr = 0;
+  }
+  ARKS_HD void step(uint8_t c, uint32_t pos) {
+    if (fail) return;
+    if (c == '\n') {
+      end_line(pos);
+      return;
+    }
+    line_len++;
+    if (line_len >= 65536) {  // bufio.Scanner: token too long
+      fail = 1;
+      return;
+    }
+    if (pending_cr) {  // the held CR was not the last byte of its line
+      pending_cr = 0;
+      line_byte('\r', pos);
+    }
+    if (c == '\r') {
+      pending_cr = 1;
+      return;
+    }
+    line_byte(c, pos);
+  }
+  // end of chunk: an unterminated last line is still a token; a pending event is dropped
+  ARKS_HD bool finish(uint32_t pos) {
+    if (!fail && line_len > 0) end_line(pos);
+    return !fail;
+  }
+};
+
+}  // namespace arks

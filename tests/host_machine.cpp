@@ -1,0 +1,50 @@
+// host_machine.cpp — TEST-ONLY build of arks_b200/csrc/json_machine.cuh with g++ so the device state
+// machines can be fuzzed against the oracle on CPU (tests/test_machine_vs_oracle.py). Not shipped.
+#include <stddef.h>
+#include <string.h>
+
+#include "../arks_b200/csrc/json_machine.cuh"
+
+using namespace arks;
+
+extern "C" {
+int hm_parse_request(const uint8_t* body, size_t len, uint8_t* model_out, size_t cap, size_t* model_len, int* stream,
+                     int* so_present, int* iu) {
+  static thread_local JsonM m;
+  m.init(K_REQ, body);
+  for (size_t i = 0; i < len; i++) m.step(body[i], (uint32_t)i);
+  *stream = m.stream3;
+  *so_present = m.so_present;
+  *iu = m.iu3;
+  size_t k = 0;
+  if (m.ok_at_end()) {
+    if (m.m_esc)
+      decode_span(body + m.m_start, m.m_rawlen, [&](uint8_t b) {
+        if (k < cap) model_out[k] = b;
+        k++;
+      });
+    else {
+      k = m.m_rawlen;
+      memcpy(model_out, body + m.m_start, k < cap ? k : cap);
+    }
+  }
+  *model_len = k;
+  return m.ok_at_end() ? 0 : 1;
+}
+int hm_parse_response(const uint8_t* body, size_t len, size_t* model_nonempty, int64_t usage[3]) {
+  static thread_local JsonM m;
+  m.init(K_RESP, body);
+  for (size_t i = 0; i < len; i++) m.step(body[i], (uint32_t)i);
+  *model_nonempty = m.m_rawlen > 0;
+  for (int k = 0; k < 3; k++) usage[k] = m.usage[k];
+  return m.ok_at_end() ? 0 : 1;
+}
+int hm_parse_sse(const uint8_t* body, size_t len, int64_t usage[3]) {
+  static thread_local SseM m;
+  m.init(body);
+  for (size_t i = 0; i < len; i++) m.step(body[i], (uint32_t)i);
+  bool ok = m.finish((uint32_t)len);
+  for (int k = 0; k < 3; k++) usage[k] = m.usage[k];
+  return ok ? 0 : 1;
+}
+}

@@ -1,0 +1,48 @@
+"""ctypes wrapper around the TEST-ONLY host build of the device state machines (tests/host_machine.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host_machine.cpp")
+HDR = os.path.join(ROOT, "arks_b200", "csrc", "json_machine.cuh")
+OUT = os.path.join(ROOT, "tests", "_build", "libhost_machine.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        if not os.path.exists(OUT) or max(os.path.getmtime(SRC), os.path.getmtime(HDR)) > os.path.getmtime(OUT):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", OUT, SRC])
+        L = C.CDLL(OUT)
+        i64p = C.POINTER(C.c_int64)
+        L.hm_parse_request.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.hm_parse_response.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), i64p]
+        L.hm_parse_sse.argtypes = [C.c_char_p, C.c_size_t, i64p]
+        _lib = L
+    return _lib
+
+
+def parse_request_body(body: bytes):
+    buf = C.create_string_buffer(4096)
+    ml, st, so, iu = C.c_size_t(), C.c_int(), C.c_int(), C.c_int()
+    rc = lib().hm_parse_request(body, len(body), buf, 4096, C.byref(ml), C.byref(st), C.byref(so), C.byref(iu))
+    return rc, buf.raw[:min(ml.value, 4096)], st.value, so.value, iu.value
+
+
+def parse_response_body(body: bytes):
+    ne = C.c_size_t()
+    u = np.zeros(3, np.int64)
+    rc = lib().hm_parse_response(body, len(body), C.byref(ne), u.ctypes.data_as(C.POINTER(C.c_int64)))
+    return rc, ne.value, tuple(int(x) for x in u)
+
+
+def parse_sse_chunk(body: bytes):
+    u = np.zeros(3, np.int64)
+    rc = lib().hm_parse_sse(body, len(body), u.ctypes.data_as(C.POINTER(C.c_int64)))
+    return rc, tuple(int(x) for x in u)

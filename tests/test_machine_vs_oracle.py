@@ -1,0 +1,100 @@
+"""Differential fuzz on CPU: the device byte state machines (arks_b200/csrc/json_machine.cuh, compiled for the host
+by tests/host_machine.cpp) against the oracle's function-by-function restatement of jsoniter / ssestream / gjson
+(oracle/ork_json.c). Any disagreement on (error?, model bytes, stream flags, usage ints) fails.
+
+Documents containing a usage-shaped number with a fraction/exponent and more than 15 significant digits are outside
+the documented exact domain (divergence D2) and are skipped."""
+import re
+
+import pytest
+
+import hostmachine as hm
+import orklib
+from jsonfuzz import Gen
+
+D2 = re.compile(rb"[0-9.]{17,}|[eE][+-]?[0-9]{2,}")
+
+
+def d2(b):
+    return bool(D2.search(b))
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_request_body_machine(seed):
+    g = Gen(seed)
+    for _ in range(30000):
+        b = g.request()
+        a, c = orklib.parse_request_body(b), hm.parse_request_body(b)
+        assert a[0] == c[0] and (a[0] == 1 or a == c), (b, a, c)
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_response_body_machine(seed):
+    g = Gen(seed)
+    for _ in range(30000):
+        b = g.response()
+        if d2(b):
+            continue
+        a, c = orklib.parse_response_body(b), hm.parse_response_body(b)
+        assert a[0] == c[0], (b, a, c)
+        if a[0] == 0:
+            assert (a[1] > 0, a[2]) == (c[1] > 0, c[2]), (b, a, c)
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_sse_chunk_machine(seed):
+    g = Gen(seed)
+    for _ in range(30000):
+        b = g.sse_chunk()
+        if d2(b):
+            continue
+        a, c = orklib.parse_sse_chunk(b), hm.parse_sse_chunk(b)
+        assert a[0] == c[0] and (a[0] == 1 or a == c), (b, a, c)
+
+
+CASES_REQ = [
+    (b'{"model":"a","model":null}', (0, b"", 0, 0, 0)),                      # last duplicate wins, null -> ""
+    (b'{"MODEL":"a"}', (0, b"a", 0, 0, 0)),                                  # case-insensitive field hash
+    (b'{"stream_options":{"include_usage":true},"stream_options":{}}', (0, b"", 0, 1, 2)),   # pointer reuse
+    (b'{"stream_options":{"include_usage":true},"stream_options":null}', (0, b"", 0, 0, 0)),
+    (b'null', (0, b"", 0, 0, 0)),                                            # readObjectStart accepts null
+    (b'{"model":"a"}\x00garbage', (0, b"a", 0, 0, 0)),                       # Unmarshal's `c == 0` quirk
+    (b'{"model":"a"} x', (1,)),
+    (b'{"a":{"b":1,null:2},"model":"m"}', (0, b"m", 0, 0, 0)),               # ReadObjectCB reads keys with ReadString
+    (b'{"a":-01,"model":"m"}', (0, b"m", 0, 0, 0)),                          # trySkipNumber leniency
+    (b'{"a":01,"model":"m"}', (1,)),
+    (b'{"a":"x\x01","model":"m"}', (1,)),                                    # control char before any backslash
+    (b'{"a":"\\n\x01","model":"m"}', (0, b"m", 0, 0, 0)),                    # ... not checked on the slow path
+    (b'{"model":"\\ud83d\\ude00"}', (0, "\U0001F600".encode(), 0, 0, 0)),
+    (b'{"model":"\\ud800x"}', (0, "\ufffdx".encode(), 0, 0, 0)),
+    (b'{"model":"a",}', (1,)),
+    (b'', (1,)),
+    (b'[]', (1,)),
+    (b'{"stream":"true"}', (1,)),
+]
+
+
+@pytest.mark.parametrize("body,want", CASES_REQ)
+def test_request_known_answers(body, want):
+    for impl in (orklib, hm):
+        got = impl.parse_request_body(body)
+        if want[0] == 1:
+            assert got[0] == 1, (impl.__name__, body, got)
+        else:
+            assert got == want, (impl.__name__, body, got)
+
+
+def test_depth_limit_10000():
+    deep_ok = b'{"a":' + b"[" * 9999 + b"]" * 9999 + b',"model":"m"}'
+    deep_bad = b'{"a":' + b"[" * 10000 + b"]" * 10000 + b',"model":"m"}'
+    for impl in (orklib, hm):
+        assert impl.parse_request_body(deep_ok)[0] == 0
+        assert impl.parse_request_body(deep_bad)[0] == 1
+
+
+def test_sse_line_limit_64k():
+    ok = b"data: " + b'{"a":"' + b"x" * 65000 + b'"}\n\n'
+    bad = b"data: " + b'{"a":"' + b"x" * 65600 + b'"}\n\n'
+    for impl in (orklib, hm):
+        assert impl.parse_sse_chunk(ok)[0] == 0
+        assert impl.parse_sse_chunk(bad)[0] == 1
