@@ -1,0 +1,1077 @@
+// arks_gateway.cu — libarksgw.so: the B200 (sm_100a) implementation behind include/arks_gateway.h.
+//
+// Data layout in HBM
+//   config (replaces the controller-runtime informer cache, pkg/gateway/qosconfig/arks_impl.go):
+//     token hash table (open addressing, 64-bit FNV-1a of spec.token -> token index, bytes verified),
+//     per token: namespace id, qos CSR; per qos entry: model-name span, quota index, endpoint index,
+//     rate-limit CSR (rule, limit); per quota: item CSR (type, limit); per endpoint: backend-weight CSR.
+//   state (replaces Redis, pkg/gateway/ratelimiter/redis_impl.go + pkg/gateway/quota/redis_impl.go):
+//     rate[rule][qos]   int64   counter of the CURRENT fixed window of `rule` (cache_key.go:73-80); the host
+//                               zeroes rate[rule][*] when floor(now/W) advances, which is what a new Redis key is
+//     quota[quota][3]   int64   cumulative usage, never reset (quota/redis_impl.go:38-48)
+//   per batch: bodies (16-byte aligned spans), tokens, a batch-local group table (qos -> arrivals), results.
+//
+// Kernels
+//   scan_request_kernel    one lane per request: JSON machine over the body, token lookup, qos/endpoint match,
+//                          static decision, and registration in the batch-local group table
+//   limit_admit_kernel     one lane per request: closed-form fixed-window admission in arrival order
+//                          (SURVEY.md §8a A6), quota check, one commit per group, weighted pick (A12)
+//   scan_response_kernel   one lane per response: JSON / SSE machine, usage extraction and the unconditional
+//                          counter increments (check.go:47-72) as warp-aggregated 64-bit atomics
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/arks_gateway.h"
+#include "json_machine.cuh"
+
+using namespace arks;
+
+// ------------------------------------------------------------------------------------------------
+// device-side views
+// ------------------------------------------------------------------------------------------------
+struct TokSlot {
+  unsigned long long hash;
+  int tok;  // -1 empty
+  int pad;
+};
+
+struct DevTables {
+  const uint8_t* pool;  // string bytes
+  // tokens
+  const TokSlot* tok_slots;
+  uint32_t tok_mask;
+  const uint32_t* tok_str_off;  // n_tokens: offset of spec.token in pool
+  const uint32_t* tok_str_len;
+  const uint32_t* tok_qos_off;  // n_tokens + 1
+  // qos entries
+  const uint32_t* qos_model_off;
+  const uint32_t* qos_model_len;
+  const int32_t* qos_quota;
+  const int32_t* qos_ep;  // endpoint index for (token namespace, model) or -1
+  const uint32_t* qos_rl_off;
+  const uint8_t* rl_rule;
+  const int64_t* rl_value;
+  // quotas
+  const uint32_t* quota_item_off;
+  const uint8_t* qitem_type;
+  const int64_t* qitem_value;
+  // endpoints
+  const uint32_t* ep_backend_off;
+  const int32_t* backend_weight;
+  // state
+  long long* rate;   // [4][n_qos]
+  long long* quota;  // [n_quotas][3]
+  uint32_t n_qos;
+};
+
+struct ReqDev {  // request batch, device resident
+  const uint8_t* bodies;
+  const uint32_t* body_off;
+  const uint32_t* body_len;
+  const uint8_t* tokens;
+  const uint32_t* token_off;
+  const unsigned long long* pick_rand;  // may be null
+  uint32_t n;
+  // intermediates
+  uint8_t* st_reason;  // static reason after scan (ARKS_R_OK == reached the limiter)
+  uint8_t* st_flags;
+  int32_t* st_qos;
+  int32_t* st_tok;
+  int32_t* gslot;  // group slot per request or -1
+  // group table
+  int32_t* gkey;
+  int32_t* gcnt;
+  int32_t* gdone;
+  uint32_t gmask;
+  // results (SoA, packed in one buffer for a single D2H)
+  uint8_t* reason;
+  uint8_t* detail;
+  uint8_t* flags;
+  int32_t* qos;
+  int32_t* token;
+  int32_t* pick;
+  long long* cur_usage;
+  long long* limit_max;
+};
+
+struct RespDev {
+  const uint8_t* bodies;
+  const uint32_t* body_off;
+  const uint32_t* body_len;
+  const int32_t* qos;
+  const uint8_t* flags;
+  uint32_t n;
+  uint8_t* reason;
+  uint8_t* counted;
+  long long* usage;  // 3n
+};
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// feed a whole body to a machine, 16 bytes per global load (bodies start 16-byte aligned and are padded)
+template <class M>
+__device__ __forceinline__ void feed_body(M& m, const uint8_t* body, uint32_t len) {
+  const uint4* p = reinterpret_cast<const uint4*>(body);
+  uint32_t pos = 0;
+  while (pos < len) {
+    uint4 v = ld_nc_v4(p++);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t x = w[k];
+#pragma unroll 1
+      for (int b = 0; b < 4; b++) {
+        if (pos < len) m.step((uint8_t)(x & 0xff), pos);
+        x >>= 8;
+        pos++;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long fnv1a64(const uint8_t* p, uint32_t n) {
+  unsigned long long h = 0xcbf29ce484222325ull;
+  for (uint32_t i = 0; i < n; i++) h = (h ^ p[i]) * 0x100000001b3ull;
+  return h;
+}
+
+// compare the (possibly escaped) model span of a body with a pool string
+__device__ bool model_equals(const uint8_t* body, const JsonM& m, const uint8_t* name, uint32_t nlen) {
+  const uint8_t* p = body + m.m_start;
+  if (!m.m_esc) {
+    if (m.m_rawlen != nlen) return false;
+    for (uint32_t i = 0; i < nlen; i++)
+      if (p[i] != name[i]) return false;
+    return true;
+  }
+  uint32_t k = 0;
+  bool ok = true;
+  decode_span(p, m.m_rawlen, [&](uint8_t b) {
+    if (k >= nlen || name[k] != b) ok = false;
+    k++;
+  });
+  return ok && k == nlen;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1: scan_request — A3 (body parse), A4 (GetQosByToken), A5 (GetModelList) of SURVEY.md §8a
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) scan_request_kernel(DevTables T, ReqDev B) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n) return;
+  const uint8_t* body = B.bodies + B.body_off[i];
+  uint32_t len = B.body_len[i];
+
+  JsonM m;
+  m.init(K_REQ, body);
+  feed_body(m, body, len);
+
+  uint8_t reason = ARKS_R_OK, flags = 0;
+  int32_t tok = -1, qos = -1, slot = -1;
+  do {
+    if (!m.ok_at_end()) { reason = ARKS_R_REQUEST_BODY; break; }           // handle_request.go:97-104
+    if (m.m_rawlen == 0) { reason = ARKS_R_NO_MODEL; break; }              // :106-115
+    // GetQosByToken: first ArksToken whose spec.token equals the bearer      arks_impl.go:303-338
+    const uint8_t* tk = B.tokens + B.token_off[i];
+    uint32_t tkl = B.token_off[i + 1] - B.token_off[i];
+    unsigned long long h = fnv1a64(tk, tkl);
+    uint32_t s = (uint32_t)h & T.tok_mask;
+    for (;;) {
+      TokSlot e = T.tok_slots[s];
+      if (e.tok < 0) break;
+      if (e.hash == h && T.tok_str_len[e.tok] == tkl) {
+        const uint8_t* q = T.pool + T.tok_str_off[e.tok];
+        bool eq = true;
+        for (uint32_t k = 0; k < tkl; k++) eq &= q[k] == tk[k];
+        if (eq) { tok = e.tok; break; }
+      }
+      s = (s + 1) & T.tok_mask;
+    }
+    if (tok < 0) { reason = ARKS_R_TOKEN_NOT_FOUND; break; }
+    for (uint32_t q = T.tok_qos_off[tok]; q < T.tok_qos_off[tok + 1]; q++)
+      if (model_equals(body, m, T.pool + T.qos_model_off[q], T.qos_model_len[q])) { qos = (int32_t)q; break; }
+    if (qos < 0) { reason = ARKS_R_MODEL_NOT_IN_TOKEN; break; }
+    if (T.qos_ep[qos] < 0) { reason = ARKS_R_NO_MODEL_BACKENDS; break; }   // handle_request.go:137-154
+    bool stream = m.stream3 == 2;
+    if (stream && !(m.so_present && m.iu3 == 2)) { reason = ARKS_R_STREAM_OPTIONS; break; }  // :156-171
+    flags = stream ? 1 : 0;
+    // register in the batch-local group table: qos -> dense slot, count arrivals
+    uint32_t g = ((uint32_t)qos * 2654435761u) & B.gmask;
+    for (;;) {
+      int32_t prev = atomicCAS(&B.gkey[g], -1, qos);
+      if (prev == -1 || prev == qos) break;
+      g = (g + 1) & B.gmask;
+    }
+    atomicAdd(&B.gcnt[g], 1);
+    slot = (int32_t)g;
+  } while (0);
+  B.st_reason[i] = reason;
+  B.st_flags[i] = flags;
+  B.st_qos[i] = qos;
+  B.st_tok[i] = tok;
+  B.gslot[i] = slot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2: limit_admit — A6 (checkRateLimit + doRequestRateLimit), A8 (checkTokenQuotaLimit), A12 (pick)
+//
+// Serial semantics being reproduced (oracle/ork_core.c handle_request): requests are applied in index order;
+// a request is denied by the first over-limit entry of qos.RateLimits, then by the first over-limit quota item;
+// an admitted request adds 1 to every request-type entry's counter. Within one batch only request-type counters
+// of the request's own qos entry change, so for the n_g arrivals of a group the first
+//     k = min over request-type entries j of  max(0, floor((limit_j - cur_rule(j) - 1) / cnt_rule(j)) + 1)
+// are admitted (k = 0 if any token-type entry or quota item is already over) and every later one is denied by
+// the first entry that is over with `k` admissions applied.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n) return;
+  uint8_t reason = B.st_reason[i], detail = 0;
+  int32_t qos = B.st_qos[i], slot = B.gslot[i], pick = -1;
+  long long cur_out = 0, lim_out = 0;
+  if (slot >= 0) {
+    const uint32_t rl0 = T.qos_rl_off[qos], rl1 = T.qos_rl_off[qos + 1];
+    const long long n_g = B.gcnt[slot];
+    long long cur[4], cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 4; r++) cur[r] = T.rate[(size_t)r * T.n_qos + qos];
+    for (uint32_t j = rl0; j < rl1; j++) cnt[T.rl_rule[j]]++;
+    // how many of this group can be admitted
+    long long k = n_g;
+    for (uint32_t j = rl0; j < rl1; j++) {
+      int rule = T.rl_rule[j];
+      long long lim = T.rl_value[j];
+      if (rule < 2) {
+        long long room = lim - cur[rule] - 1;  // cur + a*cnt + 1 <= lim  <=>  a <= room / cnt
+        long long kj = room < 0 ? 0 : room / cnt[rule] + 1;
+        k = kj < k ? kj : k;
+      } else if (cur[rule] > lim) {
+        k = 0;  // "token is not caculated in request": cur + 0 > limit (check.go:124-126)
+      }
+    }
+    int32_t qt = T.qos_quota[qos];
+    int quota_fail = -1;  // first over-limit item
+    long long q_cur = 0, q_lim = 0;
+    if (qt >= 0) {
+      uint32_t i0 = T.quota_item_off[qt], i1 = T.quota_item_off[qt + 1];
+      for (uint32_t j = i0; j < i1; j++) {
+        long long c = T.quota[(size_t)qt * 3 + T.qitem_type[j]];
+        if (c > T.qitem_value[j]) { quota_fail = (int)(j - i0); q_cur = c; q_lim = T.qitem_value[j]; break; }
+      }
+    }
+    if (qt == ARKS_QUOTA_MISSING || quota_fail >= 0) k = 0;
+    // arrival rank inside the group, only needed when the group straddles its limit
+    bool admitted;
+    if (k >= n_g) admitted = true;
+    else if (k <= 0) admitted = false;
+    else {
+      long long rank = 0;
+      for (uint32_t j = 0; j < i; j++) rank += B.gslot[j] == slot;
+      admitted = rank < k;
+    }
+    if (!admitted) {
+      // first entry over its limit once k admissions are applied (RateLimitResponse.currentUsage = cur + k*cnt)
+      reason = 0;
+      for (uint32_t j = rl0; j < rl1 && !reason; j++) {
+        int rule = T.rl_rule[j];
+        long long lim = T.rl_value[j];
+        long long c = rule < 2 ? cur[rule] + k * cnt[rule] : cur[rule];
+        long long req = rule < 2 ? 1 : 0;
+        if (c + req > lim) { reason = ARKS_R_RATE_LIMIT; detail = (uint8_t)(j - rl0); cur_out = c; lim_out = lim; }
+      }
+      if (!reason) {
+        if (qt == ARKS_QUOTA_MISSING) reason = ARKS_R_QUOTA_CONFIG;
+        else { reason = ARKS_R_QUOTA; detail = (uint8_t)quota_fail; cur_out = q_cur; lim_out = q_lim; }
+      }
+    } else if (B.pick_rand) {
+      // Envoy's weighted choice over the HTTPRoute backendRefs order (arksendpoint_controller.go:283-347)
+      int32_t ep = T.qos_ep[qos];
+      uint32_t b0 = T.ep_backend_off[ep], b1 = T.ep_backend_off[ep + 1];
+      unsigned long long sum = 0;
+      for (uint32_t b = b0; b < b1; b++) sum += (unsigned long long)max(T.backend_weight[b], 0);
+      if (sum) {
+        unsigned long long x = B.pick_rand[i] % sum, acc = 0;
+        for (uint32_t b = b0; b < b1; b++) {
+          acc += (unsigned long long)max(T.backend_weight[b], 0);
+          if (x < acc) { pick = (int32_t)(b - b0); break; }
+        }
+      }
+    }
+    // the last lane of the group to finish reading commits the group's increments (DoLimit INCRBY 1 x admitted)
+    __threadfence();
+    int done = atomicAdd(&B.gdone[slot], 1);
+    if (done == (int)n_g - 1) {
+      __threadfence();
+      long long adm = k < n_g ? (k < 0 ? 0 : k) : n_g;
+      if (adm > 0) {
+        if (cnt[0]) T.rate[(size_t)0 * T.n_qos + qos] = cur[0] + adm * cnt[0];
+        if (cnt[1]) T.rate[(size_t)1 * T.n_qos + qos] = cur[1] + adm * cnt[1];
+      }
+    }
+  }
+  B.reason[i] = reason;
+  B.detail[i] = detail;
+  B.flags[i] = reason == ARKS_R_OK ? B.st_flags[i] : 0;
+  B.qos[i] = qos;
+  B.token[i] = B.st_tok[i];
+  B.pick[i] = pick;
+  B.cur_usage[i] = cur_out;
+  B.limit_max[i] = lim_out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 3: scan_response — A10 (HandleResponseBody) + A11 (doTokenRateLimit / doTokenQuotaLimit)
+// ------------------------------------------------------------------------------------------------
+// 64-bit add aggregated over the lanes of a warp that target the same address
+__device__ __forceinline__ void warp_agg_add(long long* addr, long long v, bool active) {
+  unsigned mask = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  unsigned peers = __match_any_sync(mask, (unsigned long long)addr);
+  int leader = __ffs(peers) - 1;
+  long long sum = 0;
+  // reduce over the peer set (peers differ per lane group; iterate set bits)
+  for (unsigned p = peers; p; p &= p - 1) {
+    int src = __ffs(p) - 1;
+    sum += __shfl_sync(peers, v, src);
+  }
+  if ((int)(threadIdx.x & 31) == leader) atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)sum);
+}
+
+__global__ void __launch_bounds__(128) scan_response_kernel(DevTables T, RespDev B) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = i < B.n;
+  uint8_t reason = ARKS_R_OK, counted = 0;
+  long long u0 = 0, u1 = 0, u2 = 0;
+  int32_t qos = 0;
+  if (live) {
+    const uint8_t* body = B.bodies + B.body_off[i];
+    uint32_t len = B.body_len[i];
+    uint8_t fl = B.flags[i];
+    qos = B.qos[i];
+    SseM s;
+    if (fl & ARKS_RESP_STREAM) {  // handle_response.go:113-133, every chunk in isolation
+      s.init(body);
+      feed_body(s, body, len);
+      if (!s.finish(len)) reason = ARKS_R_STREAMING;
+      else { u0 = s.usage[0]; u1 = s.usage[1]; u2 = s.usage[2]; }
+    } else if (!(fl & ARKS_RESP_END_OF_STREAM)) {  // :141-149
+      reason = ARKS_R_PENDING;
+    } else {
+      s.ev.init(K_RESP, body);
+      feed_body(s.ev, body, len);
+      if (!s.ev.ok_at_end()) reason = ARKS_R_RESPONSE_UNMARSHAL;  // :157-166
+      else if (s.ev.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // :167-181
+      else { u0 = s.ev.usage[0]; u1 = s.ev.usage[1]; u2 = s.ev.usage[2]; }
+    }
+    if (reason != ARKS_R_OK) { u0 = u1 = u2 = 0; }
+    counted = reason == ARKS_R_OK && u2 != 0;  // :186
+  }
+  // doTokenRateLimit: += total on every token-type entry (check.go:47-59). Warp-aggregated per address.
+  int32_t qt = ARKS_QUOTA_NONE;
+  uint32_t nt[2] = {0, 0};
+  if (counted) {
+    for (uint32_t j = T.qos_rl_off[qos]; j < T.qos_rl_off[qos + 1]; j++) {
+      int rule = T.rl_rule[j];
+      if (rule >= 2) nt[rule - 2]++;
+    }
+    qt = T.qos_quota[qos];
+  }
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+    warp_agg_add(T.rate + (size_t)(2 + r) * T.n_qos + qos, u2 * (long long)nt[r], counted && nt[r]);
+  // doTokenQuotaLimit: QosToQuotaRequests + IncrUsage (check.go:62-72, qosconfig/types.go:45-72)
+  long long add[3] = {0, 0, 0};
+  if (counted && qt == ARKS_QUOTA_MISSING) reason = ARKS_R_QUOTA_CONFIG_RESP;
+  if (counted && qt >= 0) {
+    for (uint32_t j = T.quota_item_off[qt]; j < T.quota_item_off[qt + 1]; j++) {
+      int ty = T.qitem_type[j];
+      add[ty] += ty == 0 ? u0 : ty == 1 ? u1 : u2;
+    }
+  }
+#pragma unroll
+  for (int ty = 0; ty < 3; ty++)
+    warp_agg_add(T.quota + (size_t)(qt >= 0 ? qt : 0) * 3 + ty, add[ty], counted && qt >= 0 && add[ty] != 0);
+  if (live) {
+    B.reason[i] = reason;
+    B.counted[i] = counted;
+    B.usage[3 * (size_t)i + 0] = u0;
+    B.usage[3 * (size_t)i + 1] = u1;
+    B.usage[3 * (size_t)i + 2] = u2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct HostTables {  // what we need to remember for reloads, snapshots and validation
+  std::vector<std::string> qos_key;    // namespace \0 user \0 model
+  std::vector<std::string> quota_key;  // namespace \0 name
+  std::vector<uint32_t> ep_backend_off;
+  uint32_t n_tokens = 0, n_qos = 0, n_quotas = 0, n_endpoints = 0, n_backends = 0;
+};
+
+struct arks_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  char err[512] = {0};
+  uint32_t max_batch = 0;
+  uint64_t max_bytes = 0;
+  uint64_t launches = 0;
+  bool loaded = false;
+  HostTables ht;
+  std::vector<void*> table_allocs;
+  DevTables dt{};
+  long long* d_rate = nullptr;
+  long long* d_quota = nullptr;
+  int32_t* d_backend_weight = nullptr;
+  int64_t last_win[4];
+  // batch buffers: kSlots independent staging slots so several batches can be resident in HBM at once
+  struct Slot {
+    uint8_t* d_req_bodies = nullptr;   // max_bytes
+    uint8_t* d_req_meta = nullptr;     // offsets/lens/token_off/pick_rand/tokens packed
+    uint8_t* d_resp_bodies = nullptr;
+    uint8_t* d_resp_meta = nullptr;    // offsets/lens/qos/flags packed
+    uint8_t* h_req_meta = nullptr;     // pinned staging for the meta blocks
+    uint8_t* h_resp_meta = nullptr;
+    cudaEvent_t req_copied = nullptr, resp_copied = nullptr;
+    ReqDev rq{};
+    RespDev rp{};
+    uint32_t req_n = 0, resp_n = 0;
+    bool req_staged = false, resp_staged = false;
+  };
+  static constexpr int kSlots = 4;
+  Slot slots[kSlots];
+  int cur = 0;
+  size_t meta_cap = 0;
+  uint32_t fetch_n = 0;          // batch size of the last run_* call (what fetch_* copies back)
+  // optional per-kernel timing (bench roofline): events around each launch of the last run_* call
+  bool prof = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int ev_n = 0;
+  uint8_t* d_inter = nullptr;    // intermediates + group table
+  uint8_t* d_result = nullptr;   // packed results
+  uint8_t* h_result = nullptr;   // pinned
+  size_t result_cap = 0;
+  uint32_t gsize = 0;
+};
+
+static int fail(arks_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof c->err, fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return fail(ctx, ARKS_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static const int64_t kRuleWindow[4] = {60, 86400, 60, 86400};  // ratelimiter/rate_limiter.go:31-68
+static int64_t window_start(int64_t now, int rule) {            // ratelimiter/cache_key.go:73-80
+  int64_t w = kRuleWindow[rule];
+  int64_t r = (now + 62135596800LL) % w;
+  if (r < 0) r += w;
+  return now - r;
+}
+
+template <class Tv>
+static int upload(arks_ctx* ctx, const std::vector<Tv>& v, const Tv** out) {
+  void* p = nullptr;
+  size_t bytes = (v.size() + 1) * sizeof(Tv);
+  CK(cudaMalloc(&p, bytes));
+  ctx->table_allocs.push_back(p);
+  if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(Tv), cudaMemcpyHostToDevice, ctx->stream));
+  *out = (const Tv*)p;
+  return 0;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" {
+
+int arks_abi_version(void) { return ARKS_ABI_VERSION; }
+
+const char* arks_last_error(const arks_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+size_t arks_extract_bearer(const uint8_t* const* keys, const size_t* key_lens, const uint8_t* const* values,
+                           const size_t* value_lens, size_t n_headers, const uint8_t** token) {
+  // handle_request.go:38-46 — strings.ToLower(key) == "authorization" && HasPrefix(value, "Bearer ")
+  static const char A[] = "authorization";
+  *token = nullptr;
+  for (size_t i = 0; i < n_headers; i++) {
+    if (key_lens[i] != 13) continue;
+    bool ok = true;
+    for (int k = 0; k < 13; k++) {
+      uint8_t c = keys[i][k];
+      if (c >= 'A' && c <= 'Z') c += 32;
+      ok &= c == (uint8_t)A[k];
+    }
+    if (!ok) continue;
+    if (value_lens[i] >= 7 && memcmp(values[i], "Bearer ", 7) == 0) {
+      *token = values[i] + 7;
+      return value_lens[i] - 7;
+    }
+  }
+  return 0;
+}
+
+int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_ctx** out) {
+  if (!out || max_batch == 0) return ARKS_E_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return ARKS_E_NO_DEVICE;
+  arks_ctx* ctx = new arks_ctx();
+  ctx->device = device;
+  ctx->max_batch = max_batch;
+  ctx->max_bytes = align_up(max_batch_bytes + 16, 256);
+  for (int r = 0; r < 4; r++) ctx->last_win[r] = INT64_MIN;
+  *out = ctx;
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  size_t n = max_batch;
+  // meta: body_off, body_len, token_off(n+1), pick_rand, qos, flags + token bytes (256 B per request budget)
+  ctx->meta_cap = align_up(n * 4, 256) * 4 + align_up(n * 8, 256) + align_up(n, 256) + align_up(n * 256, 256);
+  for (int k = 0; k < 4; k++) CK(cudaEventCreate(&ctx->ev[k]));
+  uint32_t g = 64;
+  while (g < 2 * n) g <<= 1;
+  ctx->gsize = g;
+  size_t inter = align_up(n, 256) * 2 + align_up(n * 4, 256) * 3 + align_up((size_t)g * 4, 256) * 3;
+  CK(cudaMalloc(&ctx->d_inter, inter));
+  ctx->result_cap = align_up(n, 256) * 3 + align_up(n * 4, 256) * 3 + align_up(n * 8, 256) * 3;
+  CK(cudaMalloc(&ctx->d_result, ctx->result_cap));
+  CK(cudaMallocHost(&ctx->h_result, ctx->result_cap));
+  return 0;
+}
+
+static void free_tables(arks_ctx* ctx) {
+  for (void* p : ctx->table_allocs) cudaFree(p);
+  ctx->table_allocs.clear();
+}
+
+void arks_destroy(arks_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_tables(ctx);
+  cudaFree(ctx->d_rate);
+  cudaFree(ctx->d_quota);
+  for (auto& sl : ctx->slots) {
+    cudaFree(sl.d_req_bodies);
+    cudaFree(sl.d_req_meta);
+    cudaFree(sl.d_resp_bodies);
+    cudaFree(sl.d_resp_meta);
+    cudaFreeHost(sl.h_req_meta);
+    cudaFreeHost(sl.h_resp_meta);
+    if (sl.req_copied) cudaEventDestroy(sl.req_copied);
+    if (sl.resp_copied) cudaEventDestroy(sl.resp_copied);
+  }
+  for (int k = 0; k < 4; k++)
+    if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+  cudaFree(ctx->d_inter);
+  cudaFree(ctx->d_result);
+  cudaFreeHost(ctx->h_result);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+void* arks_stream(arks_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t arks_launch_count(const arks_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- config plane -------------------------------------------------------------------------------
+int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
+  if (!ctx || !t) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  auto S = [&](uint32_t id) {
+    return std::string((const char*)t->str_bytes + t->str_off[id], t->str_off[id + 1] - t->str_off[id]);
+  };
+  for (uint32_t i = 0; i < t->n_rl; i++)
+    if (t->rl_rule[i] >= ARKS_N_RULES) return fail(ctx, ARKS_E_BAD_TABLE, "unknown rate-limit rule %u", t->rl_rule[i]);
+  for (uint32_t i = 0; i < t->n_qitems; i++)
+    if (t->qitem_type[i] >= ARKS_N_QT) return fail(ctx, ARKS_E_BAD_TABLE, "unknown quota type %u", t->qitem_type[i]);
+  for (uint32_t q = 0; q < t->n_qos; q++) {
+    if (t->qos_rl_off[q + 1] - t->qos_rl_off[q] > 255) return fail(ctx, ARKS_E_BAD_TABLE, "more than 255 rate limits");
+    if (t->qos_quota[q] >= (int32_t)t->n_quotas || t->qos_quota[q] < ARKS_QUOTA_MISSING)
+      return fail(ctx, ARKS_E_BAD_TABLE, "qos %u: bad quota index", q);
+  }
+  for (uint32_t q = 0; q < t->n_quotas; q++)
+    if (t->quota_item_off[q + 1] - t->quota_item_off[q] > 255) return fail(ctx, ARKS_E_BAD_TABLE, "more than 255 quota items");
+
+  // string pool on the device: token strings and model names, deduplicated by content
+  std::vector<uint8_t> pool;
+  std::unordered_map<std::string, uint32_t> pool_at;
+  auto intern = [&](const std::string& s) {
+    auto it = pool_at.find(s);
+    if (it != pool_at.end()) return it->second;
+    uint32_t off = (uint32_t)pool.size();
+    pool.insert(pool.end(), s.begin(), s.end());
+    pool_at.emplace(s, off);
+    return off;
+  };
+  // endpoints by (namespace, name); first object wins on duplicates
+  std::unordered_map<std::string, int32_t> ep_by_key;
+  for (uint32_t e = 0; e < t->n_endpoints; e++) ep_by_key.emplace(S(t->ep_ns_str[e]) + '\0' + S(t->ep_name_str[e]), (int32_t)e);
+
+  HostTables ht;
+  ht.n_tokens = t->n_tokens; ht.n_qos = t->n_qos; ht.n_quotas = t->n_quotas; ht.n_endpoints = t->n_endpoints;
+  ht.n_backends = t->n_backends;
+  ht.ep_backend_off.assign(t->ep_backend_off, t->ep_backend_off + t->n_endpoints + 1);
+  std::vector<uint32_t> tok_off(t->n_tokens), tok_len(t->n_tokens), qmodel_off(t->n_qos), qmodel_len(t->n_qos);
+  std::vector<int32_t> qos_ep(t->n_qos);
+  uint32_t cap = 16;
+  while (cap < 2 * t->n_tokens + 2) cap <<= 1;
+  std::vector<TokSlot> slots(cap, TokSlot{0, -1, 0});
+  ht.qos_key.resize(t->n_qos);
+  for (uint32_t k = 0; k < t->n_tokens; k++) {
+    std::string tk = S(t->tok_token_str[k]), ns = S(t->tok_ns_str[k]), nm = S(t->tok_name_str[k]);
+    tok_off[k] = intern(tk);
+    tok_len[k] = (uint32_t)tk.size();
+    unsigned long long h = 0xcbf29ce484222325ull;
+    for (unsigned char c : tk) h = (h ^ c) * 0x100000001b3ull;
+    uint32_t s = (uint32_t)h & (cap - 1);
+    bool dup = false;
+    while (slots[s].tok >= 0) {
+      if (slots[s].hash == h && S(t->tok_token_str[slots[s].tok]) == tk) { dup = true; break; }  // first object wins
+      s = (s + 1) & (cap - 1);
+    }
+    if (!dup) slots[s] = TokSlot{h, (int)k, 0};
+    for (uint32_t q = t->tok_qos_off[k]; q < t->tok_qos_off[k + 1]; q++) {
+      std::string model = S(t->qos_model_str[q]);
+      qmodel_off[q] = intern(model);
+      qmodel_len[q] = (uint32_t)model.size();
+      auto it = ep_by_key.find(ns + '\0' + model);
+      qos_ep[q] = it == ep_by_key.end() ? -1 : it->second;
+      ht.qos_key[q] = ns + '\0' + nm + '\0' + model;
+      int32_t qt = t->qos_quota[q];
+      if (qt >= 0 && S(t->quota_ns_str[qt]) != ns)
+        return fail(ctx, ARKS_E_BAD_TABLE, "qos %u references a quota of another namespace", q);
+    }
+  }
+  ht.quota_key.resize(t->n_quotas);
+  for (uint32_t q = 0; q < t->n_quotas; q++) ht.quota_key[q] = S(t->quota_ns_str[q]) + '\0' + S(t->quota_name_str[q]);
+
+  // carry counters over by key (Redis keys survive a CRD edit)
+  std::vector<long long> new_rate((size_t)4 * t->n_qos + 1, 0), new_quota((size_t)3 * t->n_quotas + 1, 0);
+  if (ctx->loaded) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<long long> old_rate((size_t)4 * ctx->ht.n_qos + 1), old_quota((size_t)3 * ctx->ht.n_quotas + 1);
+    if (ctx->ht.n_qos) CK(cudaMemcpy(old_rate.data(), ctx->d_rate, (size_t)32 * ctx->ht.n_qos, cudaMemcpyDeviceToHost));
+    if (ctx->ht.n_quotas) CK(cudaMemcpy(old_quota.data(), ctx->d_quota, (size_t)24 * ctx->ht.n_quotas, cudaMemcpyDeviceToHost));
+    std::unordered_map<std::string, uint32_t> oq, ou;
+    for (uint32_t q = 0; q < ctx->ht.n_qos; q++) oq.emplace(ctx->ht.qos_key[q], q);
+    for (uint32_t q = 0; q < ctx->ht.n_quotas; q++) ou.emplace(ctx->ht.quota_key[q], q);
+    for (uint32_t q = 0; q < t->n_qos; q++) {
+      auto it = oq.find(ht.qos_key[q]);
+      if (it != oq.end())
+        for (int r = 0; r < 4; r++) new_rate[(size_t)r * t->n_qos + q] = old_rate[(size_t)r * ctx->ht.n_qos + it->second];
+    }
+    for (uint32_t q = 0; q < t->n_quotas; q++) {
+      auto it = ou.find(ht.quota_key[q]);
+      if (it != ou.end())
+        for (int k = 0; k < 3; k++) new_quota[(size_t)3 * q + k] = old_quota[(size_t)3 * it->second + k];
+    }
+  }
+  free_tables(ctx);
+  cudaFree(ctx->d_rate);
+  cudaFree(ctx->d_quota);
+  ctx->d_rate = ctx->d_quota = nullptr;
+  CK(cudaMalloc(&ctx->d_rate, (size_t)32 * t->n_qos + 64));
+  CK(cudaMalloc(&ctx->d_quota, (size_t)24 * t->n_quotas + 64));
+  CK(cudaMemcpyAsync(ctx->d_rate, new_rate.data(), (size_t)32 * t->n_qos, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_quota, new_quota.data(), (size_t)24 * t->n_quotas, cudaMemcpyHostToDevice, ctx->stream));
+
+  DevTables d{};
+  int rc;
+  std::vector<uint32_t> v_tok_qos_off(t->tok_qos_off, t->tok_qos_off + t->n_tokens + 1);
+  std::vector<int32_t> v_qos_quota(t->qos_quota, t->qos_quota + t->n_qos);
+  std::vector<uint32_t> v_qos_rl_off(t->qos_rl_off, t->qos_rl_off + t->n_qos + 1);
+  std::vector<uint8_t> v_rl_rule(t->rl_rule, t->rl_rule + t->n_rl);
+  std::vector<int64_t> v_rl_value(t->rl_value, t->rl_value + t->n_rl);
+  std::vector<uint32_t> v_qi_off(t->quota_item_off, t->quota_item_off + t->n_quotas + 1);
+  std::vector<uint8_t> v_qi_type(t->qitem_type, t->qitem_type + t->n_qitems);
+  std::vector<int64_t> v_qi_val(t->qitem_value, t->qitem_value + t->n_qitems);
+  std::vector<uint32_t> v_ep_off(t->ep_backend_off, t->ep_backend_off + t->n_endpoints + 1);
+  std::vector<int32_t> v_bw(t->backend_weight, t->backend_weight + t->n_backends);
+  if ((rc = upload(ctx, pool, &d.pool))) return rc;
+  if ((rc = upload(ctx, slots, &d.tok_slots))) return rc;
+  d.tok_mask = cap - 1;
+  if ((rc = upload(ctx, tok_off, &d.tok_str_off))) return rc;
+  if ((rc = upload(ctx, tok_len, &d.tok_str_len))) return rc;
+  if ((rc = upload(ctx, v_tok_qos_off, &d.tok_qos_off))) return rc;
+  if ((rc = upload(ctx, qmodel_off, &d.qos_model_off))) return rc;
+  if ((rc = upload(ctx, qmodel_len, &d.qos_model_len))) return rc;
+  if ((rc = upload(ctx, v_qos_quota, &d.qos_quota))) return rc;
+  if ((rc = upload(ctx, qos_ep, &d.qos_ep))) return rc;
+  if ((rc = upload(ctx, v_qos_rl_off, &d.qos_rl_off))) return rc;
+  if ((rc = upload(ctx, v_rl_rule, &d.rl_rule))) return rc;
+  if ((rc = upload(ctx, v_rl_value, (const int64_t**)&d.rl_value))) return rc;
+  if ((rc = upload(ctx, v_qi_off, &d.quota_item_off))) return rc;
+  if ((rc = upload(ctx, v_qi_type, &d.qitem_type))) return rc;
+  if ((rc = upload(ctx, v_qi_val, (const int64_t**)&d.qitem_value))) return rc;
+  if ((rc = upload(ctx, v_ep_off, &d.ep_backend_off))) return rc;
+  if ((rc = upload(ctx, v_bw, &d.backend_weight))) return rc;
+  ctx->d_backend_weight = const_cast<int32_t*>(d.backend_weight);
+  d.rate = ctx->d_rate;
+  d.quota = ctx->d_quota;
+  d.n_qos = t->n_qos;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->dt = d;
+  ctx->ht = std::move(ht);
+  ctx->loaded = true;
+  return 0;
+}
+
+int arks_update_endpoint_weights(arks_ctx* ctx, uint32_t ep, uint32_t n, const int32_t* w) {
+  if (!ctx || !ctx->loaded) return ARKS_E_NOT_LOADED;
+  if (ep >= ctx->ht.n_endpoints || ctx->ht.ep_backend_off[ep + 1] - ctx->ht.ep_backend_off[ep] != n)
+    return fail(ctx, ARKS_E_INVALID_ARG, "endpoint %u has a different backend count", ep);
+  CK(cudaSetDevice(ctx->device));
+  // stream-ordered: lands between the previous and the next batch
+  CK(cudaMemcpyAsync(ctx->d_backend_weight + ctx->ht.ep_backend_off[ep], w, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// fixed-window roll-over: a new window is a new Redis key, i.e. every counter of that rule reads 0
+static int roll_windows(arks_ctx* ctx, int64_t now) {
+  for (int r = 0; r < 4; r++)
+    if (window_start(now, r) < ctx->last_win[r])
+      return fail(ctx, ARKS_E_TIME_WENT_BACK, "now_unix %lld is before the current %s window", (long long)now,
+                  r == 0 ? "rpm" : r == 1 ? "rpd" : r == 2 ? "tpm" : "tpd");
+  for (int r = 0; r < 4; r++) {
+    int64_t ws = window_start(now, r);
+    if (ws != ctx->last_win[r]) {
+      if (ctx->last_win[r] != INT64_MIN && ctx->ht.n_qos)
+        CK(cudaMemsetAsync(ctx->d_rate + (size_t)r * ctx->ht.n_qos, 0, (size_t)8 * ctx->ht.n_qos, ctx->stream));
+      ctx->last_win[r] = ws;
+    }
+  }
+  return 0;
+}
+
+// ---- staging slots --------------------------------------------------------------------------------
+static int ensure_slot(arks_ctx* ctx, int k, bool want_req, bool want_resp) {
+  arks_ctx::Slot& sl = ctx->slots[k];
+  if (want_req && !sl.d_req_bodies) {
+    CK(cudaMalloc(&sl.d_req_bodies, ctx->max_bytes));
+    CK(cudaMalloc(&sl.d_req_meta, ctx->meta_cap));
+    CK(cudaMallocHost(&sl.h_req_meta, ctx->meta_cap));
+    CK(cudaEventCreateWithFlags(&sl.req_copied, cudaEventDisableTiming));
+  }
+  if (want_resp && !sl.d_resp_bodies) {
+    CK(cudaMalloc(&sl.d_resp_bodies, ctx->max_bytes));
+    CK(cudaMalloc(&sl.d_resp_meta, ctx->meta_cap));
+    CK(cudaMallocHost(&sl.h_resp_meta, ctx->meta_cap));
+    CK(cudaEventCreateWithFlags(&sl.resp_copied, cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+int arks_select_slot(arks_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= arks_ctx::kSlots) return ARKS_E_INVALID_ARG;
+  ctx->cur = slot;
+  return 0;
+}
+
+int arks_set_profiling(arks_ctx* ctx, int on) {
+  if (!ctx) return ARKS_E_INVALID_ARG;
+  ctx->prof = on != 0;
+  return 0;
+}
+
+int arks_last_kernel_ms(arks_ctx* ctx, float* ms, int cap) {
+  if (!ctx || !ms) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int n = ctx->ev_n > 0 ? ctx->ev_n - 1 : 0;
+  for (int k = 0; k < n && k < cap; k++) CK(cudaEventElapsedTime(&ms[k], ctx->ev[k], ctx->ev[k + 1]));
+  return n;
+}
+
+// ---- request phase ------------------------------------------------------------------------------
+int arks_stage_request_batch(arks_ctx* ctx, const arks_request_batch* b) {
+  if (!ctx || !b) return ARKS_E_INVALID_ARG;
+  if (!ctx->loaded) return fail(ctx, ARKS_E_NOT_LOADED, "arks_load_tables has not been called");
+  const uint32_t n = b->n;
+  if (n > ctx->max_batch) return fail(ctx, ARKS_E_CAPACITY, "batch of %u exceeds max_batch %u", n, ctx->max_batch);
+  if (b->bodies_bytes > ctx->max_bytes) return fail(ctx, ARKS_E_CAPACITY, "batch bytes exceed max_batch_bytes");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_slot(ctx, ctx->cur, true, false);
+  if (rc) return rc;
+  arks_ctx::Slot& sl = ctx->slots[ctx->cur];
+  sl.req_n = n;
+  sl.req_staged = true;
+  if (n == 0) return 0;
+  for (uint32_t i = 0; i < n; i++)
+    if ((b->body_off[i] & 15u) || (uint64_t)b->body_off[i] + b->body_len[i] > b->bodies_bytes)
+      return fail(ctx, ARKS_E_INVALID_ARG, "body %u: offset not 16-byte aligned or out of range", i);
+  const size_t tok_bytes = b->token_off[n];
+  size_t o_off = 0, o_len = o_off + align_up((size_t)n * 4, 256), o_toff = o_len + align_up((size_t)n * 4, 256),
+         o_rand = o_toff + align_up((size_t)(n + 1) * 4, 256), o_tok = o_rand + align_up((size_t)n * 8, 256),
+         total = o_tok + align_up(tok_bytes + 1, 256);
+  if (total > ctx->meta_cap) return fail(ctx, ARKS_E_CAPACITY, "token bytes exceed capacity");
+  CK(cudaEventSynchronize(sl.req_copied));  // the pinned block may still feed the previous copy of this slot
+  uint8_t* h = sl.h_req_meta;
+  memcpy(h + o_off, b->body_off, (size_t)n * 4);
+  memcpy(h + o_len, b->body_len, (size_t)n * 4);
+  memcpy(h + o_toff, b->token_off, (size_t)(n + 1) * 4);
+  if (b->pick_rand) memcpy(h + o_rand, b->pick_rand, (size_t)n * 8);
+  memcpy(h + o_tok, b->tokens, tok_bytes);
+  CK(cudaMemcpyAsync(sl.d_req_bodies, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(sl.d_req_meta, h, total, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(sl.req_copied, ctx->stream));
+  ReqDev& r = sl.rq;
+  r.bodies = sl.d_req_bodies;
+  r.body_off = (const uint32_t*)(sl.d_req_meta + o_off);
+  r.body_len = (const uint32_t*)(sl.d_req_meta + o_len);
+  r.token_off = (const uint32_t*)(sl.d_req_meta + o_toff);
+  r.pick_rand = b->pick_rand ? (const unsigned long long*)(sl.d_req_meta + o_rand) : nullptr;
+  r.tokens = sl.d_req_meta + o_tok;
+  r.n = n;
+  return 0;
+}
+
+static void carve_request(arks_ctx* ctx, ReqDev& r) {
+  const size_t n = ctx->max_batch;
+  uint8_t* p = ctx->d_inter;
+  r.st_reason = p; p += align_up(n, 256);
+  r.st_flags = p; p += align_up(n, 256);
+  r.st_qos = (int32_t*)p; p += align_up(n * 4, 256);
+  r.st_tok = (int32_t*)p; p += align_up(n * 4, 256);
+  r.gslot = (int32_t*)p; p += align_up(n * 4, 256);
+  r.gkey = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);
+  r.gcnt = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);
+  r.gdone = (int32_t*)p;
+  uint8_t* q = ctx->d_result;
+  r.reason = q; q += align_up(n, 256);
+  r.detail = q; q += align_up(n, 256);
+  r.flags = q; q += align_up(n, 256);
+  r.qos = (int32_t*)q; q += align_up(n * 4, 256);
+  r.token = (int32_t*)q; q += align_up(n * 4, 256);
+  r.pick = (int32_t*)q; q += align_up(n * 4, 256);
+  r.cur_usage = (long long*)q; q += align_up(n * 8, 256);
+  r.limit_max = (long long*)q;
+}
+
+int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
+  if (!ctx || !ctx->loaded) return ARKS_E_INVALID_ARG;
+  arks_ctx::Slot& sl = ctx->slots[ctx->cur];
+  if (!sl.req_staged) return fail(ctx, ARKS_E_INVALID_ARG, "no request batch staged in slot %d", ctx->cur);
+  CK(cudaSetDevice(ctx->device));
+  int rc = roll_windows(ctx, now_unix);
+  if (rc) return rc;
+  const uint32_t n = sl.req_n;
+  ctx->fetch_n = n;
+  ctx->ev_n = 0;
+  if (n == 0) return 0;
+  ReqDev& r = sl.rq;
+  carve_request(ctx, r);
+  // batch-local group table sized to the batch (2x, power of two); the three arrays are contiguous
+  uint32_t g = 64;
+  while (g < 2 * n) g <<= 1;
+  r.gmask = g - 1;
+  CK(cudaMemsetAsync(r.gkey, 0xff, (size_t)g * 4, ctx->stream));
+  CK(cudaMemsetAsync(r.gcnt, 0, (size_t)g * 4, ctx->stream));
+  CK(cudaMemsetAsync(r.gdone, 0, (size_t)g * 4, ctx->stream));
+  uint32_t blocks = (n + 127) / 128;
+  if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  scan_request_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->dt, r);
+  if (ctx->prof) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  limit_admit_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->dt, r);
+  if (ctx->prof) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_n = 3; }
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int arks_fetch_request_result(arks_ctx* ctx, arks_request_result* out) {
+  if (!ctx || !out) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = ctx->fetch_n;
+  if (n == 0) return 0;
+  const size_t cap = ctx->max_batch;
+  uint8_t* h = ctx->h_result;
+  const uint8_t* d = ctx->d_result;
+  size_t o1 = align_up(cap, 256), o4 = align_up(cap * 4, 256), o8 = align_up(cap * 8, 256);
+  size_t offs[8] = {0, o1, 2 * o1, 3 * o1, 3 * o1 + o4, 3 * o1 + 2 * o4, 3 * o1 + 3 * o4, 3 * o1 + 3 * o4 + o8};
+  size_t widths[8] = {1, 1, 1, 4, 4, 4, 8, 8};
+  if (n * 8 >= cap) {  // dense batch: a single copy of the whole block
+    CK(cudaMemcpyAsync(h, d, offs[7] + n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    for (int k = 0; k < 8; k++) CK(cudaMemcpyAsync(h + offs[k], d + offs[k], n * widths[k], cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(out->reason, h + offs[0], n);
+  memcpy(out->detail, h + offs[1], n);
+  memcpy(out->flags, h + offs[2], n);
+  memcpy(out->qos, h + offs[3], n * 4);
+  memcpy(out->token, h + offs[4], n * 4);
+  memcpy(out->pick, h + offs[5], n * 4);
+  memcpy(out->cur_usage, h + offs[6], n * 8);
+  memcpy(out->limit_max, h + offs[7], n * 8);
+  return 0;
+}
+
+int arks_submit_request_batch(arks_ctx* ctx, const arks_request_batch* b, arks_request_result* r) {
+  int rc = arks_stage_request_batch(ctx, b);
+  if (rc) return rc;
+  rc = arks_run_request_batch(ctx, b->now_unix);
+  if (rc) return rc;
+  return arks_fetch_request_result(ctx, r);
+}
+
+// ---- response phase -----------------------------------------------------------------------------
+int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
+  if (!ctx || !b) return ARKS_E_INVALID_ARG;
+  if (!ctx->loaded) return fail(ctx, ARKS_E_NOT_LOADED, "arks_load_tables has not been called");
+  const uint32_t n = b->n;
+  if (n > ctx->max_batch) return fail(ctx, ARKS_E_CAPACITY, "batch of %u exceeds max_batch %u", n, ctx->max_batch);
+  if (b->bodies_bytes > ctx->max_bytes) return fail(ctx, ARKS_E_CAPACITY, "batch bytes exceed max_batch_bytes");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_slot(ctx, ctx->cur, false, true);
+  if (rc) return rc;
+  arks_ctx::Slot& sl = ctx->slots[ctx->cur];
+  sl.resp_n = n;
+  sl.resp_staged = true;
+  if (n == 0) return 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if (b->qos[i] < 0 || (uint32_t)b->qos[i] >= ctx->ht.n_qos) return fail(ctx, ARKS_E_INVALID_ARG, "response %u: bad qos index", i);
+    if ((b->body_off[i] & 15u) || (uint64_t)b->body_off[i] + b->body_len[i] > b->bodies_bytes)
+      return fail(ctx, ARKS_E_INVALID_ARG, "body %u: offset not 16-byte aligned or out of range", i);
+  }
+  size_t o_off = 0, o_len = align_up((size_t)n * 4, 256), o_qos = o_len * 2, o_fl = o_len * 3, total = o_fl + align_up(n, 256);
+  CK(cudaEventSynchronize(sl.resp_copied));
+  uint8_t* h = sl.h_resp_meta;
+  memcpy(h + o_off, b->body_off, (size_t)n * 4);
+  memcpy(h + o_len, b->body_len, (size_t)n * 4);
+  memcpy(h + o_qos, b->qos, (size_t)n * 4);
+  memcpy(h + o_fl, b->flags, n);
+  CK(cudaMemcpyAsync(sl.d_resp_bodies, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(sl.d_resp_meta, h, total, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(sl.resp_copied, ctx->stream));
+  RespDev& r = sl.rp;
+  r.bodies = sl.d_resp_bodies;
+  r.body_off = (const uint32_t*)(sl.d_resp_meta + o_off);
+  r.body_len = (const uint32_t*)(sl.d_resp_meta + o_len);
+  r.qos = (const int32_t*)(sl.d_resp_meta + o_qos);
+  r.flags = sl.d_resp_meta + o_fl;
+  r.n = n;
+  const size_t cap = ctx->max_batch;
+  r.reason = ctx->d_result;
+  r.counted = ctx->d_result + align_up(cap, 256);
+  r.usage = (long long*)(ctx->d_result + 2 * align_up(cap, 256));
+  return 0;
+}
+
+int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
+  if (!ctx || !ctx->loaded) return ARKS_E_INVALID_ARG;
+  arks_ctx::Slot& sl = ctx->slots[ctx->cur];
+  if (!sl.resp_staged) return fail(ctx, ARKS_E_INVALID_ARG, "no response batch staged in slot %d", ctx->cur);
+  CK(cudaSetDevice(ctx->device));
+  int rc = roll_windows(ctx, now_unix);
+  if (rc) return rc;
+  const uint32_t n = sl.resp_n;
+  ctx->fetch_n = n;
+  ctx->ev_n = 0;
+  if (n == 0) return 0;
+  uint32_t blocks = (n + 127) / 128;
+  if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  scan_response_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->dt, sl.rp);
+  if (ctx->prof) { CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_n = 2; }
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int arks_fetch_response_result(arks_ctx* ctx, arks_response_result* out) {
+  if (!ctx || !out) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = ctx->fetch_n;
+  if (n == 0) return 0;
+  const size_t cap = ctx->max_batch;
+  size_t o1 = align_up(cap, 256);
+  uint8_t* h = ctx->h_result;
+  CK(cudaMemcpyAsync(h, ctx->d_result, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h + o1, ctx->d_result + o1, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h + 2 * o1, ctx->d_result + 2 * o1, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(out->reason, h, n);
+  memcpy(out->counted, h + o1, n);
+  memcpy(out->usage, h + 2 * o1, n * 24);
+  return 0;
+}
+
+int arks_submit_response_batch(arks_ctx* ctx, const arks_response_batch* b, arks_response_result* r) {
+  int rc = arks_stage_response_batch(ctx, b);
+  if (rc) return rc;
+  rc = arks_run_response_batch(ctx, b->now_unix);
+  if (rc) return rc;
+  return arks_fetch_response_result(ctx, r);
+}
+
+// ---- quota.QuotaService surface / snapshots -------------------------------------------------------
+int arks_snapshot_quota(arks_ctx* ctx, int64_t* usage) {
+  if (!ctx || !ctx->loaded) return ARKS_E_NOT_LOADED;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->ht.n_quotas) CK(cudaMemcpy(usage, ctx->d_quota, (size_t)24 * ctx->ht.n_quotas, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int arks_set_quota_usage(arks_ctx* ctx, uint32_t quota, const int64_t usage[3]) {
+  if (!ctx || !ctx->loaded) return ARKS_E_NOT_LOADED;
+  if (quota >= ctx->ht.n_quotas) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(ctx->d_quota + (size_t)3 * quota, usage, 24, cudaMemcpyHostToDevice));
+  return 0;
+}
+int arks_incr_quota_usage(arks_ctx* ctx, uint32_t quota, const int64_t delta[3]) {
+  if (!ctx || !ctx->loaded) return ARKS_E_NOT_LOADED;
+  if (quota >= ctx->ht.n_quotas) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  long long cur[3];
+  CK(cudaMemcpy(cur, ctx->d_quota + (size_t)3 * quota, 24, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 3; k++) cur[k] = (long long)((unsigned long long)cur[k] + (unsigned long long)delta[k]);
+  CK(cudaMemcpy(ctx->d_quota + (size_t)3 * quota, cur, 24, cudaMemcpyHostToDevice));
+  return 0;
+}
+int arks_snapshot_rate(arks_ctx* ctx, int64_t now_unix, int64_t* counters) {
+  if (!ctx || !ctx->loaded) return ARKS_E_NOT_LOADED;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t nq = ctx->ht.n_qos;
+  std::vector<long long> tmp(4 * nq + 1);
+  if (nq) CK(cudaMemcpy(tmp.data(), ctx->d_rate, 32 * nq, cudaMemcpyDeviceToHost));
+  for (size_t q = 0; q < nq; q++)
+    for (int r = 0; r < 4; r++)
+      counters[q * 4 + r] = window_start(now_unix, r) == ctx->last_win[r] ? tmp[(size_t)r * nq + q] : 0;
+  return 0;
+}
+
+// multi-GPU quota delta folding is not wired in this build (single-owner keys only)
+int arks_take_quota_delta(arks_ctx* ctx, int64_t*) { return fail(ctx, ARKS_E_INVALID_ARG, "not built"); }
+int arks_apply_quota_delta(arks_ctx* ctx, const int64_t*) { return fail(ctx, ARKS_E_INVALID_ARG, "not built"); }
+void* arks_quota_delta_dev(arks_ctx*) { return nullptr; }
+int arks_fold_quota_delta_dev(arks_ctx* ctx, const void*, const void*) { return fail(ctx, ARKS_E_INVALID_ARG, "not built"); }
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+"""Host-side mirror of the reference's plugin seams over libarksgw.so (the C ABI in include/arks_gateway.h).
+
+The reference wires three interfaces into its ext_proc server (cmd/gateway/main.go:233-270):
+  ratelimiter.RateLimterInterface  (CheckLimit / DoLimit)            pkg/gateway/ratelimiter/rate_limiter.go:21-28
+  quota.QuotaService               (IncrUsage / SetUsage / GetUsage) pkg/gateway/quota/types.go:24-28
+  qosconfig.ConfigProvider         (GetQosByToken / GetQuotaConfig / GetModelList)  pkg/gateway/qosconfig/provider.go:29-37
+On the B200 they are one object, because config, limiter windows and quota usage live together in HBM and a
+request is decided in one pass over its body. `Gateway` is that object; `handle_request_body` /
+`handle_response_body` keep the names of the Go handlers they batch (pkg/gateway/handle_request.go:83,
+pkg/gateway/handle_response.go:80).
+
+There is no CPU fallback: if the shared library or a CUDA device is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import (ArksRequestBatch, ArksRequestResult, ArksResponseBatch, ArksResponseResult, ArksTables,
+                  RequestBatch, RequestResult, ResponseBatch, ResponseResult)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libarksgw.so")
+_lib = None
+
+
+class ArksError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"arks error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load libarksgw.so (built in-tree by __graft_entry__.build()). Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.arks_abi_version.restype = C.c_int
+        L.arks_create.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.POINTER(vp)]
+        L.arks_destroy.argtypes = [vp]
+        L.arks_last_error.restype = C.c_char_p
+        L.arks_last_error.argtypes = [vp]
+        L.arks_load_tables.argtypes = [vp, C.POINTER(ArksTables)]
+        L.arks_update_endpoint_weights.argtypes = [vp, C.c_uint32, C.c_uint32, abi.i32p]
+        L.arks_submit_request_batch.argtypes = [vp, C.POINTER(ArksRequestBatch), C.POINTER(ArksRequestResult)]
+        L.arks_submit_response_batch.argtypes = [vp, C.POINTER(ArksResponseBatch), C.POINTER(ArksResponseResult)]
+        L.arks_stage_request_batch.argtypes = [vp, C.POINTER(ArksRequestBatch)]
+        L.arks_run_request_batch.argtypes = [vp, C.c_int64]
+        L.arks_fetch_request_result.argtypes = [vp, C.POINTER(ArksRequestResult)]
+        L.arks_stage_response_batch.argtypes = [vp, C.POINTER(ArksResponseBatch)]
+        L.arks_run_response_batch.argtypes = [vp, C.c_int64]
+        L.arks_fetch_response_result.argtypes = [vp, C.POINTER(ArksResponseResult)]
+        L.arks_select_slot.argtypes = [vp, C.c_int]
+        L.arks_set_profiling.argtypes = [vp, C.c_int]
+        L.arks_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+        L.arks_stream.restype = vp
+        L.arks_stream.argtypes = [vp]
+        L.arks_launch_count.restype = C.c_uint64
+        L.arks_launch_count.argtypes = [vp]
+        L.arks_snapshot_quota.argtypes = [vp, abi.i64p]
+        L.arks_set_quota_usage.argtypes = [vp, C.c_uint32, abi.i64p]
+        L.arks_incr_quota_usage.argtypes = [vp, C.c_uint32, abi.i64p]
+        L.arks_snapshot_rate.argtypes = [vp, C.c_int64, abi.i64p]
+        L.arks_extract_bearer.restype = C.c_size_t
+        _lib = L
+    return _lib
+
+
+EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/test_abi.py)
+    "arks_abi_version", "arks_create", "arks_destroy", "arks_last_error", "arks_load_tables",
+    "arks_update_endpoint_weights", "arks_extract_bearer", "arks_submit_request_batch",
+    "arks_submit_response_batch", "arks_stage_request_batch", "arks_run_request_batch",
+    "arks_fetch_request_result", "arks_stage_response_batch", "arks_run_response_batch",
+    "arks_fetch_response_result", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_snapshot_quota",
+    "arks_set_quota_usage", "arks_incr_quota_usage", "arks_snapshot_rate", "arks_take_quota_delta",
+    "arks_apply_quota_delta", "arks_quota_delta_dev", "arks_fold_quota_delta_dev",
+]
+
+
+class Gateway:
+    """One per GPU. All mutable gateway state (rate windows, quota usage) lives in this object's HBM."""
+
+    def __init__(self, device: int = 0, max_batch: int = 65536, max_batch_bytes: int = 96 << 20):
+        self._h = C.c_void_p()
+        rc = lib().arks_create(device, max_batch, max_batch_bytes, C.byref(self._h))
+        if rc:
+            msg = lib().arks_last_error(self._h).decode() if self._h else "no CUDA device (there is no CPU fallback)"
+            h, self._h = self._h, C.c_void_p()
+            if h:
+                lib().arks_destroy(h)
+            raise ArksError(rc, msg)
+        self.tables = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().arks_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise ArksError(rc, lib().arks_last_error(self._h).decode())
+
+    # ---- qosconfig.ConfigProvider: informer snapshot -> HBM tables
+    def load_tables(self, tables):
+        ts = tables.c_struct()
+        self._ck(lib().arks_load_tables(self._h, C.byref(ts)))
+        self.tables = tables
+
+    def update_endpoint_weights(self, endpoint: int, weights):
+        w = np.ascontiguousarray(weights, np.int32)
+        self._ck(lib().arks_update_endpoint_weights(self._h, endpoint, len(w), abi.ptr(w, abi.i32p)))
+
+    # ---- HandleRequestBody for a micro-batch of streams
+    def handle_request_body(self, b: RequestBatch, out: RequestResult | None = None) -> RequestResult:
+        r = out if out is not None else RequestResult.empty(b.n)
+        bs, rs = b.c_struct(), r.c_struct()
+        self._ck(lib().arks_submit_request_batch(self._h, C.byref(bs), C.byref(rs)))
+        return r
+
+    # ---- HandleResponseBody (status 200) for a micro-batch of chunks / complete bodies
+    def handle_response_body(self, b: ResponseBatch, out: ResponseResult | None = None) -> ResponseResult:
+        r = out if out is not None else ResponseResult.empty(b.n)
+        bs, rs = b.c_struct(), r.c_struct()
+        self._ck(lib().arks_submit_response_batch(self._h, C.byref(bs), C.byref(rs)))
+        return r
+
+    # ---- split form (bench: kernel-only timing with inputs resident in HBM)
+    def stage_request(self, b: RequestBatch):
+        bs = b.c_struct()
+        self._ck(lib().arks_stage_request_batch(self._h, C.byref(bs)))
+
+    def run_request(self, now_unix: int):
+        self._ck(lib().arks_run_request_batch(self._h, int(now_unix)))
+
+    def fetch_request(self, n: int, out: RequestResult | None = None) -> RequestResult:
+        r = out if out is not None else RequestResult.empty(n)
+        rs = r.c_struct()
+        self._ck(lib().arks_fetch_request_result(self._h, C.byref(rs)))
+        return r
+
+    def stage_response(self, b: ResponseBatch):
+        bs = b.c_struct()
+        self._ck(lib().arks_stage_response_batch(self._h, C.byref(bs)))
+
+    def run_response(self, now_unix: int):
+        self._ck(lib().arks_run_response_batch(self._h, int(now_unix)))
+
+    def fetch_response(self, n: int, out: ResponseResult | None = None) -> ResponseResult:
+        r = out if out is not None else ResponseResult.empty(n)
+        rs = r.c_struct()
+        self._ck(lib().arks_fetch_response_result(self._h, C.byref(rs)))
+        return r
+
+    def select_slot(self, slot: int):
+        self._ck(lib().arks_select_slot(self._h, int(slot)))
+
+    def set_profiling(self, on: bool):
+        self._ck(lib().arks_set_profiling(self._h, int(bool(on))))
+
+    def last_kernel_ms(self):
+        buf = (C.c_float * 4)()
+        n = lib().arks_last_kernel_ms(self._h, buf, 4)
+        if n < 0:
+            self._ck(n)
+        return [float(buf[k]) for k in range(n)]
+
+    @property
+    def stream_handle(self) -> int:
+        return int(lib().arks_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().arks_launch_count(self._h))
+
+    # ---- quota.QuotaService surface + A14 snapshot
+    def snapshot_quota(self) -> np.ndarray:
+        out = np.zeros((self.tables.n_quotas, 3), np.int64)
+        self._ck(lib().arks_snapshot_quota(self._h, abi.ptr(out, abi.i64p)))
+        return out
+
+    def snapshot_rate(self, now_unix: int) -> np.ndarray:
+        out = np.zeros((self.tables.n_qos, 4), np.int64)
+        self._ck(lib().arks_snapshot_rate(self._h, int(now_unix), abi.ptr(out, abi.i64p)))
+        return out
+
+    def set_quota_usage(self, quota: int, usage):
+        u = np.ascontiguousarray(usage, np.int64)
+        self._ck(lib().arks_set_quota_usage(self._h, quota, abi.ptr(u, abi.i64p)))
+
+    def incr_quota_usage(self, quota: int, delta):
+        u = np.ascontiguousarray(delta, np.int64)
+        self._ck(lib().arks_incr_quota_usage(self._h, quota, abi.ptr(u, abi.i64p)))
+
+    # ---- reply shaping helpers (what the Go host puts on the wire; handle_request.go:208-247, util.go:40-77)
+    def request_headers(self, r: RequestResult, i: int) -> dict:
+        """The three routing headers of an admitted request: model, namespace, username."""
+        t = self.tables
+        return {"model": t.qos_model_name[int(r.qos[i])], "namespace": t.token_namespace[int(r.token[i])],
+                "username": t.token_user[int(r.token[i])]}
+
+
+def extract_bearer(headers) -> bytes:
+    """HandleRequestHeaders bearer extraction (handle_request.go:38-46) through the C ABI. headers: [(key, value)]."""
+    n = len(headers)
+    keys = [k if isinstance(k, bytes) else k.encode() for k, _ in headers]
+    vals = [v if isinstance(v, bytes) else v.encode() for _, v in headers]
+    kbuf = [C.create_string_buffer(k, max(len(k), 1)) for k in keys]
+    vbuf = [C.create_string_buffer(v, max(len(v), 1)) for v in vals]
+    KA = (C.c_void_p * max(n, 1))(*[C.addressof(b) for b in kbuf])
+    VA = (C.c_void_p * max(n, 1))(*[C.addressof(b) for b in vbuf])
+    KL = (C.c_size_t * max(n, 1))(*[len(k) for k in keys])
+    VL = (C.c_size_t * max(n, 1))(*[len(v) for v in vals])
+    tok = C.c_void_p()
+    ln = lib().arks_extract_bearer(KA, KL, VA, VL, C.c_size_t(n), C.byref(tok))
+    if not ln:
+        return b""
+    return C.string_at(tok.value, ln)

@@ -211,6 +211,13 @@ int arks_fetch_request_result(arks_ctx* ctx, arks_request_result* r);      /* D2
 int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b);
 int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix);
 int arks_fetch_response_result(arks_ctx* ctx, arks_response_result* r);
+/* up to 4 staging slots so that several batches can be resident in HBM at once (bench: rotate batches so the
+ * timed inputs exceed L2). stage_/run_ calls act on the selected slot (default 0); fetch_ returns the last run. */
+int arks_select_slot(arks_ctx* ctx, int slot);
+/* per-kernel device timing of the last run_* call: CUDA events around every launch on the library's stream.
+ * arks_last_kernel_ms returns the number of kernels timed and fills ms[] (request: scan, admit; response: scan). */
+int arks_set_profiling(arks_ctx* ctx, int on);
+int arks_last_kernel_ms(arks_ctx* ctx, float* ms, int cap);
 /* CUDA stream handle (cudaStream_t) the kernels are launched on, for event timing by the caller */
 void* arks_stream(arks_ctx* ctx);
 /* number of kernel launches issued by this context so far */

@@ -1,0 +1,217 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Bit-exact on every output array (reason, detail, flags, qos, token, pick, currentUsage, limitMax, usage ints,
+counted) and on the counter snapshots (rate windows, quota usage) after every batch."""
+import re
+
+import numpy as np
+import pytest
+
+import orklib
+from arks_b200 import abi, traffic
+from arks_b200.abi import RequestBatch, ResponseBatch
+from arks_b200.tables import Tables, simple_endpoint, simple_quota, simple_token
+from jsonfuzz import Gen
+
+pytestmark = pytest.mark.gpu
+NOW = 1_700_000_000
+D2 = re.compile(rb"[0-9.]{17,}|[eE][+-]?[0-9]{2,}")
+
+
+@pytest.fixture(scope="module")
+def gwmod():
+    import __graft_entry__ as ge
+    ge.build()
+    from arks_b200 import gateway
+    return gateway
+
+
+def pair(gwmod, tables, max_batch=4096, max_bytes=16 << 20):
+    g = gwmod.Gateway(0, max_batch, max_bytes)
+    g.load_tables(tables)
+    return g, orklib.Oracle(tables)
+
+
+def same(a, b, ctx=""):
+    for k, v in a.fields().items():
+        w = b.fields()[k]
+        if not np.array_equal(v, w):
+            bad = np.nonzero(np.any(np.atleast_2d((v != w).reshape(len(v), -1)), axis=1) if v.ndim > 1 else (v != w))[0]
+            raise AssertionError(f"{ctx} field {k}: {len(bad)} mismatches, first at {bad[:5]}: gpu={v[bad[:5]]} oracle={w[bad[:5]]}")
+
+
+def state_same(g, o, now):
+    assert np.array_equal(g.snapshot_rate(now), o.snapshot_rate(now)), "rate counters differ"
+    assert np.array_equal(g.snapshot_quota(), o.snapshot_quota()), "quota usage differs"
+
+
+def test_quickstart_config1(gwmod):
+    import json, os
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "quickstart.json")))
+    t = Tables(fx["tokens"], fx["quotas"], fx["endpoints"], {("default", "qwen-7b"): ["arks-application-qwen-7b"]})
+    g, o = pair(gwmod, t)
+    req = RequestBatch.from_lists([fx["request_body"].encode()] * 7, [b"sk-test123456"] * 7, NOW, pick_rand=np.arange(7))
+    a = g.handle_request_body(req)
+    same(a, o.request_batch(req), "quickstart")
+    assert a.reason.tolist() == [0] * 5 + [abi.R_RATE_LIMIT] * 2
+    assert g.request_headers(a, 0) == {"model": "qwen-7b", "namespace": "default", "username": "example-token"}
+    resp = ResponseBatch.from_lists([fx["response_body"].encode()], [0], [abi.RESP_END_OF_STREAM], NOW + 1)
+    c = g.handle_response_body(resp)
+    same(c, o.response_batch(resp))
+    assert c.usage[0].tolist() == [25, 20, 45]
+    assert g.snapshot_rate(NOW + 1)[0].tolist() == [5, 5, 45, 45]
+    assert g.snapshot_quota()[0].tolist() == [25, 20, 45]
+    state_same(g, o, NOW + 1)
+
+
+def test_waves_with_noise_and_window_rollover(gwmod):
+    w = traffic.Workload(n_tenants=300, seed=3)
+    g, o = pair(gwmod, w.tables, 4096, 16 << 20)
+    now = NOW
+    for wave in range(9):
+        req = w.request_batch(3000, now, seed=100 + wave, stream_frac=0.3, noise_frac=0.15)
+        a = g.handle_request_body(req)
+        same(a, o.request_batch(req), f"wave {wave} request")
+        state_same(g, o, now)
+        resp = w.response_batch(a, now + 3, seed=200 + wave, noise_frac=0.1)
+        if resp.n > 4096:
+            resp = ResponseBatch(resp.bodies, resp.body_off[:4096], resp.body_len[:4096], resp.qos[:4096], resp.flags[:4096], resp.now_unix)
+        c = g.handle_response_body(resp)
+        same(c, o.response_batch(resp), f"wave {wave} response")
+        state_same(g, o, now + 3)
+        now += [7, 25, 40, 61, 3, 86400, 59, 1, 30][wave]  # several minute roll-overs and one day roll-over
+
+
+def test_hot_tenant_crosses_limit_inside_a_batch(gwmod):
+    toks = [simple_token("hot", "ns0", "tk-hot", "m", [("rpm", 37), ("tpm", 10**9), ("rpd", 50), ("tpd", 10**9)]),
+            simple_token("dup", "ns1", "tk-dup", "m", [("rpm", 9), ("rpm", 5), ("rpd", 100)]),
+            simple_token("cold", "ns2", "tk-cold", "m", [("rpm", 10**6)])]
+    eps = [simple_endpoint("m", ns) for ns in ("ns0", "ns1", "ns2")]
+    g, o = pair(gwmod, Tables(toks, [], eps))
+    rng = np.random.default_rng(5)
+    for rnd in range(4):
+        who = rng.choice([b"tk-hot", b"tk-dup", b"tk-cold"], size=1500, p=[0.5, 0.2, 0.3])
+        req = RequestBatch.from_lists([b'{"model":"m"}'] * 1500, list(who), NOW + 20 * rnd)
+        a = g.handle_request_body(req)
+        same(a, o.request_batch(req), f"round {rnd}")
+        state_same(g, o, NOW + 20 * rnd)
+
+
+def test_quota_shapes(gwmod):
+    toks = [simple_token("a", "ns", "ta", "m", [("rpm", 100)], "shared"),
+            simple_token("b", "ns", "tb", "m", [("tpm", 50)], "shared"),
+            simple_token("c", "ns", "tc", "m", [], "absent"),           # ArksQuota missing -> 500 x-error-quota
+            simple_token("d", "ns", "td", "m", [], ""),                 # no quota
+            {"metadata": {"name": "e", "namespace": "ns"},
+             "spec": {"token": "te", "qos": [{"arksEndpoint": {"name": "m2"}, "rateLimits": [{"type": "rpd", "value": 3}]},
+                                             {"arksEndpoint": {"name": "m"}, "quota": {"name": "promptonly"}}]}}]
+    quotas = [simple_quota("shared", "ns", [("prompt", 120), ("total", 1000), ("total", 400)]),
+              simple_quota("promptonly", "ns", [("prompt", 60)])]
+    eps = [simple_endpoint("m", "ns"), simple_endpoint("m2", "ns")]
+    g, o = pair(gwmod, Tables(toks, quotas, eps))
+    rng = np.random.default_rng(9)
+    now = NOW
+    for rnd in range(6):
+        who = rng.choice([b"ta", b"tb", b"tc", b"td", b"te"], size=400)
+        bodies = [b'{"model":"m2"}' if (t == b"te" and rng.random() < 0.5) else b'{"model":"m"}' for t in who]
+        req = RequestBatch.from_lists(bodies, list(who), now)
+        a = g.handle_request_body(req)
+        same(a, o.request_batch(req), f"round {rnd}")
+        ok = np.nonzero(a.reason == 0)[0][:200]
+        rb = [b'{"model":"m","usage":{"prompt_tokens":%d,"completion_tokens":%d,"total_tokens":%d}}'
+              % (p, c, p + c) for p, c in rng.integers(0, 9, (len(ok), 2))]
+        if len(ok):
+            resp = ResponseBatch.from_lists(rb, a.qos[ok], [abi.RESP_END_OF_STREAM] * len(ok), now + 1)
+            same(g.handle_response_body(resp), o.response_batch(resp), f"round {rnd} resp")
+        state_same(g, o, now + 1)
+        now += 13
+
+
+@pytest.mark.parametrize("seed", [41, 42])
+def test_fuzzed_request_bodies(gwmod, seed):
+    w = traffic.Workload(n_tenants=8, seed=1)
+    g, o = pair(gwmod, w.tables)
+    gen = Gen(seed)
+    bodies = [gen.request() for _ in range(4000)]
+    toks = [w.token_strings[i % 8] for i in range(4000)]
+    req = RequestBatch.from_lists(bodies, toks, NOW)
+    same(g.handle_request_body(req), o.request_batch(req), "fuzz")
+    state_same(g, o, NOW)
+
+
+@pytest.mark.parametrize("seed", [51, 52])
+def test_fuzzed_response_bodies_and_sse(gwmod, seed):
+    w = traffic.Workload(n_tenants=8, seed=1)
+    g, o = pair(gwmod, w.tables)
+    gen = Gen(seed)
+    bodies, flags = [], []
+    while len(bodies) < 4000:
+        if gen.r.random() < 0.5:
+            b, f = gen.response(), abi.RESP_END_OF_STREAM
+        else:
+            b, f = gen.sse_chunk(), abi.RESP_STREAM
+        if D2.search(b):
+            continue
+        bodies.append(b)
+        flags.append(f if gen.r.random() < 0.97 else 0)
+    resp = ResponseBatch.from_lists(bodies, [i % 8 for i in range(4000)], flags, NOW)
+    same(g.handle_response_body(resp), o.response_batch(resp), "fuzz resp")
+    state_same(g, o, NOW)
+
+
+def test_edges_empty_large_reload_and_time(gwmod):
+    w = traffic.Workload(n_tenants=16, seed=2)
+    g, o = pair(gwmod, w.tables, 512, 8 << 20)
+    # empty batch
+    e = RequestBatch.from_lists([], [], NOW)
+    assert g.handle_request_body(e).reason.shape == (0,)
+    # zero-length body, 64 KiB and 1 MiB bodies, a body that is only whitespace
+    rng = np.random.default_rng(1)
+    big = traffic.chat_request_body(rng, 65536)
+    huge = traffic.chat_request_body(rng, 1 << 20)
+    req = RequestBatch.from_lists([b"", big, huge, b"   \n", big[:-1]], [w.token_strings[i] for i in range(5)], NOW)
+    same(g.handle_request_body(req), o.request_batch(req), "edges")
+    # SetUsage / IncrUsage surface
+    g.set_quota_usage(3, [5, 6, 7]); o.set_quota_usage(3, [5, 6, 7])
+    g.incr_quota_usage(3, [1, 1, 1]); o.incr_quota_usage(3, [1, 1, 1])
+    state_same(g, o, NOW)
+    # endpoint weight churn (config 5): picks follow the new weights
+    g.update_endpoint_weights(2, [0, 0, 9]); o.update_endpoint_weights(2, [0, 0, 9])
+    req = w.request_batch(400, NOW + 1, seed=8)
+    same(g.handle_request_body(req), o.request_batch(req), "after weight update")
+    # reload with one tenant removed and limits changed: counters carried over by key
+    w2 = traffic.Workload(n_tenants=15, seed=2)
+    g.load_tables(w2.tables); o.reload(w2.tables)
+    state_same(g, o, NOW + 1)
+    req = w2.request_batch(400, NOW + 2, seed=9)
+    same(g.handle_request_body(req), o.request_batch(req), "after reload")
+    # the clock must not fall into an earlier window
+    with pytest.raises(gwmod.ArksError) as ei:
+        g.handle_request_body(w2.request_batch(4, NOW - 120, seed=1))
+    assert ei.value.code == abi.E_TIME_WENT_BACK
+
+
+def test_full_size_wave_64k(gwmod):
+    """BASELINE config 2 at full size: 65 536 x 1 KiB requests over 10 000 tenants, three waves, vs the oracle;
+    plus the size-independent invariants (admissions never exceed a window's limit; counters == admissions)."""
+    w = traffic.Workload(n_tenants=10_000, seed=0xA2C5)
+    g, o = pair(gwmod, w.tables, 65536, 80 << 20)
+    now = NOW
+    admitted_per_tenant = np.zeros(10_000, np.int64)
+    for wave in range(3):
+        req = w.request_batch(65536, now, seed=300 + wave, n_templates=256)
+        a = g.handle_request_body(req)
+        same(a, o.request_batch(req), f"wave {wave}")
+        ok = a.reason == 0
+        np.add.at(admitted_per_tenant, a.token[ok], 1)
+        rate = g.snapshot_rate(now)
+        assert np.array_equal(rate[:, 0], admitted_per_tenant)          # rpm counter == admissions this minute
+        lim = w.tables.rl_value.reshape(-1, 4)[:, 0]
+        assert np.all(rate[:, 0] <= lim)
+        resp = w.response_batch(a, now + 2, seed=400 + wave)
+        n = min(resp.n, 65536)
+        resp = ResponseBatch(resp.bodies, resp.body_off[:n], resp.body_len[:n], resp.qos[:n], resp.flags[:n], resp.now_unix)
+        c = g.handle_response_body(resp)
+        same(c, o.response_batch(resp), f"wave {wave} resp")
+        assert np.array_equal(c.usage[:, 0] + c.usage[:, 1], c.usage[:, 2])
+        state_same(g, o, now + 2)
+        now += 20
