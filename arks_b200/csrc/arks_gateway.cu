@@ -85,10 +85,12 @@ struct ReqDev {  // request batch, device resident
   int32_t* st_qos;
   int32_t* st_tok;
   int32_t* gslot;  // group slot per request or -1
-  // group table
+  int32_t* gnext;  // next (earlier-registered) member of the same group, -1 ends the list
+  // group table (batch local): qos -> slot
   int32_t* gkey;
+  int32_t* ghead;
   int32_t* gcnt;
-  int32_t* gdone;
+  long long* gsnap;  // [slot][4] window counters as they were before this batch
   uint32_t gmask;
   // results (SoA, packed in one buffer for a single D2H)
   uint8_t* reason;
@@ -124,25 +126,84 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
   return r;
 }
 
-// feed a whole body to a machine, 16 bytes per global load (bodies start 16-byte aligned and are padded)
-template <class M>
-__device__ __forceinline__ void feed_body(M& m, const uint8_t* body, uint32_t len) {
-  const uint4* p = reinterpret_cast<const uint4*>(body);
-  uint32_t pos = 0;
-  while (pos < len) {
-    uint4 v = ld_nc_v4(p++);
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+// ------------------------------------------------------------------------------------------------
+// Warp-tiled body feed.
+//
+// One warp owns 32 bodies, one per lane. The bodies are streamed through shared memory in windows of kWin bytes per
+// body with a kStages-deep cp.async pipeline: in every stage the warp copies 32 x kWin bytes with 16-byte LDGSTS
+// (8 lanes cover one 128-byte line of one body, so HBM sees full lines), and each lane then parses its own kWin
+// bytes out of shared memory. Unit u of body b sits at 16-byte slot u*32 + ((b + u) & 31): the 8 lanes that store
+// one body's line hit 8 different bank groups, and the 32 lanes that each read "their" unit u hit 32 different
+// slots of one 512-byte row, so both sides of the transpose are conflict-free when lanes move in lock step.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWin = 128;                        // bytes per body per stage
+constexpr int kUnits = kWin / 16;                // 16-byte units per body per stage
+constexpr int kStages = 3;
+constexpr int kStageBytes = 32 * kWin;           // 4 KiB per warp per stage
+constexpr int kWarpsPerBlock = 4;
+constexpr int kSmemPerBlock = kWarpsPerBlock * kStages * kStageBytes;  // 48 KiB
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// issue the copies of window `w` (bytes [w*kWin, (w+1)*kWin) of all 32 bodies) into stage buffer `stage_smem`
+__device__ __forceinline__ void issue_window(uint32_t stage_smem, const uint8_t* my_body, uint32_t my_padded, uint32_t w,
+                                             uint32_t lane) {
+  const uint32_t u = lane & 7;             // unit within the window handled by this lane
+  const uint32_t off = w * kWin + u * 16;  // byte offset inside the body
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      uint32_t x = w[k];
-#pragma unroll 1
-      for (int b = 0; b < 4; b++) {
-        if (pos < len) m.step((uint8_t)(x & 0xff), pos);
-        x >>= 8;
-        pos++;
-      }
-    }
+  for (int k = 0; k < 8; k++) {
+    const uint32_t b = (lane >> 3) + 4 * k;  // body (== owning lane) this copy belongs to
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, (unsigned long long)my_body, b));
+    const uint32_t plen = __shfl_sync(0xffffffffu, my_padded, b);
+    const uint32_t slot = u * 32 + ((b + u) & 31);
+    const bool in = off < plen;
+    cp_async16(stage_smem + slot * 16, in ? base + off : base, in ? 16u : 0u);
   }
+}
+static_assert(kUnits == 8, "issue_window assumes 8 units per window");
+
+// Parse 32 bodies, one per lane, with machine `m` (lanes beyond the batch pass len == 0).
+template <class M>
+__device__ __forceinline__ void feed_tiled(M& m, const uint8_t* body, uint32_t len, uint8_t* warp_smem) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t padded = (len + 15u) & ~15u;
+  uint32_t maxlen = len;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, d));
+  const uint32_t n_win = (maxlen + kWin - 1) / kWin;
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(warp_smem);
+  // prologue
+#pragma unroll
+  for (int s = 0; s < kStages - 1; s++) {
+    if ((uint32_t)s < n_win) issue_window(smem0 + s * kStageBytes, body, padded, s, lane);
+    cp_async_commit();
+  }
+  uint32_t pos = 0;
+  for (uint32_t w = 0; w < n_win; w++) {
+    const uint32_t nxt = w + kStages - 1;
+    if (nxt < n_win) issue_window(smem0 + (nxt % kStages) * kStageBytes, body, padded, nxt, lane);
+    cp_async_commit();
+    cp_async_wait<kStages - 1>();
+    __syncwarp();
+    const uint8_t* st = warp_smem + (w % kStages) * kStageBytes;
+    const uint32_t wbeg = w * kWin;
+    uint32_t lim = min(len, wbeg + kWin);
+    consume(m, pos, lim, [&](uint32_t u) {
+      const uint32_t ul = u - (wbeg >> 4);
+      const uint4 v = *reinterpret_cast<const uint4*>(st + (ul * 32 + ((lane + ul) & 31)) * 16);
+      Unit16 q;
+      q.w[0] = v.x; q.w[1] = v.y; q.w[2] = v.z; q.w[3] = v.w;
+      return q;
+    });
+    if (m.dead()) pos = len;  // nothing further can change the verdict
+    __syncwarp();  // everyone is done with this stage before it is overwritten
+  }
+  cp_async_wait<0>();
 }
 
 __device__ __forceinline__ unsigned long long fnv1a64(const uint8_t* p, uint32_t n) {
@@ -172,17 +233,19 @@ __device__ bool model_equals(const uint8_t* body, const JsonM& m, const uint8_t*
 // ------------------------------------------------------------------------------------------------
 // kernel 1: scan_request — A3 (body parse), A4 (GetQosByToken), A5 (GetModelList) of SURVEY.md §8a
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) scan_request_kernel(DevTables T, ReqDev B) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B.n) return;
-  const uint8_t* body = B.bodies + B.body_off[i];
-  uint32_t len = B.body_len[i];
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) scan_request_kernel(DevTables T, ReqDev B) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < B.n;
+  const uint8_t* body = B.bodies + (live ? B.body_off[i] : 0);
+  const uint32_t len = live ? B.body_len[i] : 0;
 
   JsonM m;
   m.init(K_REQ, body);
-  feed_body(m, body, len);
+  feed_tiled(m, body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
+  if (!live) return;
 
-  uint8_t reason = ARKS_R_OK, flags = 0;
+  uint8_t reason = ARKS_R_OK, flags = 0, claimer = 0;
   int32_t tok = -1, qos = -1, slot = -1;
   do {
     if (!m.ok_at_end()) { reason = ARKS_R_REQUEST_BODY; break; }           // handle_request.go:97-104
@@ -211,18 +274,27 @@ __global__ void __launch_bounds__(128) scan_request_kernel(DevTables T, ReqDev B
     bool stream = m.stream3 == 2;
     if (stream && !(m.so_present && m.iu3 == 2)) { reason = ARKS_R_STREAM_OPTIONS; break; }  // :156-171
     flags = stream ? 1 : 0;
-    // register in the batch-local group table: qos -> dense slot, count arrivals
+    // register in the batch-local group table: qos -> dense slot, arrival count, member list
     uint32_t g = ((uint32_t)qos * 2654435761u) & B.gmask;
     for (;;) {
       int32_t prev = atomicCAS(&B.gkey[g], -1, qos);
-      if (prev == -1 || prev == qos) break;
+      if (prev == -1) {
+        // the claimer snapshots the group's window counters: limit_admit reads only the snapshot, so the one lane
+        // that later writes the counters back races with nobody
+        claimer = 1;
+#pragma unroll
+        for (int r = 0; r < 4; r++) B.gsnap[(size_t)g * 4 + r] = T.rate[(size_t)r * T.n_qos + qos];
+        break;
+      }
+      if (prev == qos) break;
       g = (g + 1) & B.gmask;
     }
     atomicAdd(&B.gcnt[g], 1);
+    B.gnext[i] = atomicExch(&B.ghead[g], (int32_t)i);
     slot = (int32_t)g;
   } while (0);
   B.st_reason[i] = reason;
-  B.st_flags[i] = flags;
+  B.st_flags[i] = flags | (claimer << 7);
   B.st_qos[i] = qos;
   B.st_tok[i] = tok;
   B.gslot[i] = slot;
@@ -250,7 +322,7 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
     const long long n_g = B.gcnt[slot];
     long long cur[4], cnt[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int r = 0; r < 4; r++) cur[r] = T.rate[(size_t)r * T.n_qos + qos];
+    for (int r = 0; r < 4; r++) cur[r] = B.gsnap[(size_t)slot * 4 + r];  // pre-batch values (claimer's snapshot)
     for (uint32_t j = rl0; j < rl1; j++) cnt[T.rl_rule[j]]++;
     // how many of this group can be admitted
     long long k = n_g;
@@ -281,8 +353,19 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
     if (k >= n_g) admitted = true;
     else if (k <= 0) admitted = false;
     else {
+      // the group straddles its limit: arrival rank = members with a smaller index
       long long rank = 0;
-      for (uint32_t j = 0; j < i; j++) rank += B.gslot[j] == slot;
+      if (n_g <= 256) {
+        for (int32_t j = B.ghead[slot]; j >= 0; j = B.gnext[j]) rank += (uint32_t)j < i;
+      } else {  // hot tenant: dense scan of the slot column, 4 entries per load
+        const int4* gs = reinterpret_cast<const int4*>(B.gslot);
+        uint32_t j4 = 0;
+        for (; (j4 + 1) * 4 <= i; j4++) {
+          int4 v = gs[j4];
+          rank += (v.x == slot) + (v.y == slot) + (v.z == slot) + (v.w == slot);
+        }
+        for (uint32_t j = j4 * 4; j < i; j++) rank += B.gslot[j] == slot;
+      }
       admitted = rank < k;
     }
     if (!admitted) {
@@ -313,11 +396,8 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
         }
       }
     }
-    // the last lane of the group to finish reading commits the group's increments (DoLimit INCRBY 1 x admitted)
-    __threadfence();
-    int done = atomicAdd(&B.gdone[slot], 1);
-    if (done == (int)n_g - 1) {
-      __threadfence();
+    // the group's claimer commits the increments (DoLimit INCRBY 1 x admitted); nobody reads T.rate in this kernel
+    if (B.st_flags[i] & 0x80) {
       long long adm = k < n_g ? (k < 0 ? 0 : k) : n_g;
       if (adm > 0) {
         if (cnt[0]) T.rate[(size_t)0 * T.n_qos + qos] = cur[0] + adm * cnt[0];
@@ -327,7 +407,7 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
   }
   B.reason[i] = reason;
   B.detail[i] = detail;
-  B.flags[i] = reason == ARKS_R_OK ? B.st_flags[i] : 0;
+  B.flags[i] = reason == ARKS_R_OK ? (B.st_flags[i] & 0x7f) : 0;
   B.qos[i] = qos;
   B.token[i] = B.st_tok[i];
   B.pick[i] = pick;
@@ -353,34 +433,48 @@ __device__ __forceinline__ void warp_agg_add(long long* addr, long long v, bool 
   if ((int)(threadIdx.x & 31) == leader) atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)sum);
 }
 
-__global__ void __launch_bounds__(128) scan_response_kernel(DevTables T, RespDev B) {
+// per-lane response machine: an SSE chunk (stream) or one JSON document (non-stream); one engine instance serves both
+struct RespM {
+  SseM s;
+  bool sse;
+  __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { if (sse) s.step(c, pos); else s.ev.step(c, pos); }
+  __device__ __forceinline__ bool can_fast() const { return sse ? s.can_fast() : s.ev.can_fast(); }
+  __device__ __forceinline__ void skip(uint32_t k) { if (sse) s.skip(k); }
+  __device__ __forceinline__ bool dead() const { return sse ? s.dead() : s.ev.dead(); }
+};
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) scan_response_kernel(DevTables T, RespDev B) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool live = i < B.n;
   uint8_t reason = ARKS_R_OK, counted = 0;
   long long u0 = 0, u1 = 0, u2 = 0;
   int32_t qos = 0;
-  if (live) {
-    const uint8_t* body = B.bodies + B.body_off[i];
-    uint32_t len = B.body_len[i];
-    uint8_t fl = B.flags[i];
-    qos = B.qos[i];
-    SseM s;
-    if (fl & ARKS_RESP_STREAM) {  // handle_response.go:113-133, every chunk in isolation
-      s.init(body);
-      feed_body(s, body, len);
-      if (!s.finish(len)) reason = ARKS_R_STREAMING;
-      else { u0 = s.usage[0]; u1 = s.usage[1]; u2 = s.usage[2]; }
-    } else if (!(fl & ARKS_RESP_END_OF_STREAM)) {  // :141-149
-      reason = ARKS_R_PENDING;
-    } else {
-      s.ev.init(K_RESP, body);
-      feed_body(s.ev, body, len);
-      if (!s.ev.ok_at_end()) reason = ARKS_R_RESPONSE_UNMARSHAL;  // :157-166
-      else if (s.ev.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // :167-181
-      else { u0 = s.ev.usage[0]; u1 = s.ev.usage[1]; u2 = s.ev.usage[2]; }
+  {
+    const uint8_t* body = B.bodies + (live ? B.body_off[i] : 0);
+    uint8_t fl = live ? B.flags[i] : ARKS_RESP_END_OF_STREAM;
+    const bool pending = !(fl & (ARKS_RESP_STREAM | ARKS_RESP_END_OF_STREAM));  // handle_response.go:141-149
+    uint32_t len = live && !pending ? B.body_len[i] : 0;
+    qos = live ? B.qos[i] : 0;
+    RespM rm;
+    rm.sse = fl & ARKS_RESP_STREAM;
+    if (rm.sse) rm.s.init(body); else rm.s.ev.init(K_RESP, body);
+    feed_tiled(rm, body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
+    if (live) {
+      SseM& s = rm.s;
+      if (rm.sse) {  // handle_response.go:113-133, every chunk in isolation
+        if (!s.finish(len)) reason = ARKS_R_STREAMING;
+        else { u0 = s.usage[0]; u1 = s.usage[1]; u2 = s.usage[2]; }
+      } else if (pending) {
+        reason = ARKS_R_PENDING;
+      } else {
+        if (!s.ev.ok_at_end()) reason = ARKS_R_RESPONSE_UNMARSHAL;  // :157-166
+        else if (s.ev.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // :167-181
+        else { u0 = s.ev.usage[0]; u1 = s.ev.usage[1]; u2 = s.ev.usage[2]; }
+      }
+      if (reason != ARKS_R_OK) { u0 = u1 = u2 = 0; }
+      counted = reason == ARKS_R_OK && u2 != 0;  // :186
     }
-    if (reason != ARKS_R_OK) { u0 = u1 = u2 = 0; }
-    counted = reason == ARKS_R_OK && u2 != 0;  // :186
   }
   // doTokenRateLimit: += total on every token-type entry (check.go:47-59). Warp-aggregated per address.
   int32_t qt = ARKS_QUOTA_NONE;
@@ -552,10 +646,12 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   // meta: body_off, body_len, token_off(n+1), pick_rand, qos, flags + token bytes (256 B per request budget)
   ctx->meta_cap = align_up(n * 4, 256) * 4 + align_up(n * 8, 256) + align_up(n, 256) + align_up(n * 256, 256);
   for (int k = 0; k < 4; k++) CK(cudaEventCreate(&ctx->ev[k]));
+  CK(cudaFuncSetAttribute(scan_request_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
+  CK(cudaFuncSetAttribute(scan_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
   uint32_t g = 64;
   while (g < 2 * n) g <<= 1;
   ctx->gsize = g;
-  size_t inter = align_up(n, 256) * 2 + align_up(n * 4, 256) * 3 + align_up((size_t)g * 4, 256) * 3;
+  size_t inter = align_up(n, 256) * 2 + align_up(n * 4, 256) * 4 + align_up((size_t)g * 4, 256) * 3 + (size_t)g * 32 + 256;
   CK(cudaMalloc(&ctx->d_inter, inter));
   ctx->result_cap = align_up(n, 256) * 3 + align_up(n * 4, 256) * 3 + align_up(n * 8, 256) * 3;
   CK(cudaMalloc(&ctx->d_result, ctx->result_cap));
@@ -858,9 +954,11 @@ static void carve_request(arks_ctx* ctx, ReqDev& r) {
   r.st_qos = (int32_t*)p; p += align_up(n * 4, 256);
   r.st_tok = (int32_t*)p; p += align_up(n * 4, 256);
   r.gslot = (int32_t*)p; p += align_up(n * 4, 256);
-  r.gkey = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);
+  r.gnext = (int32_t*)p; p += align_up(n * 4, 256);
+  r.gkey = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);   // gkey and ghead are contiguous: one memset(-1)
+  r.ghead = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);
   r.gcnt = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);
-  r.gdone = (int32_t*)p;
+  r.gsnap = (long long*)p;
   uint8_t* q = ctx->d_result;
   r.reason = q; q += align_up(n, 256);
   r.detail = q; q += align_up(n, 256);
@@ -890,13 +988,13 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   while (g < 2 * n) g <<= 1;
   r.gmask = g - 1;
   CK(cudaMemsetAsync(r.gkey, 0xff, (size_t)g * 4, ctx->stream));
+  CK(cudaMemsetAsync(r.ghead, 0xff, (size_t)g * 4, ctx->stream));
   CK(cudaMemsetAsync(r.gcnt, 0, (size_t)g * 4, ctx->stream));
-  CK(cudaMemsetAsync(r.gdone, 0, (size_t)g * 4, ctx->stream));
-  uint32_t blocks = (n + 127) / 128;
+  const uint32_t tpb = kWarpsPerBlock * 32;
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  scan_request_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->dt, r);
+  scan_request_kernel<<<(n + tpb - 1) / tpb, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, r);
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  limit_admit_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->dt, r);
+  limit_admit_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dt, r);
   if (ctx->prof) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_n = 3; }
   ctx->launches += 2;
   CK(cudaGetLastError());
@@ -993,9 +1091,9 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
   ctx->fetch_n = n;
   ctx->ev_n = 0;
   if (n == 0) return 0;
-  uint32_t blocks = (n + 127) / 128;
+  const uint32_t tpb = kWarpsPerBlock * 32;
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  scan_response_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->dt, sl.rp);
+  scan_response_kernel<<<(n + tpb - 1) / tpb, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
   if (ctx->prof) { CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_n = 2; }
   ctx->launches += 1;
   CK(cudaGetLastError());

@@ -652,6 +652,16 @@ struct JsonM {
 
   // end of input: jsoniter Unmarshal / encoding/json checkValid verdict
   ARKS_HD bool ok_at_end() const { return !err && (st == S_FINISH || st == S_STOP); }
+
+  // ---- bulk interface used by the tiled kernels ----
+  // True while the machine sits inside a string whose ordinary bytes need no per-byte action: the caller may then
+  // skip ahead to the next '"', '\\' or byte < 0x20 without calling step() (skipped bytes are never control bytes,
+  // so the jsoniter "control character before the first backslash" rule cannot be missed).
+  ARKS_HD bool can_fast() const {
+    return (st == S_STR_E) | ((st == S_STR) & (skind < SK_KEY_STRUCT) & (skind != SK_VALUE_UINT));
+  }
+  ARKS_HD void skip(uint32_t) {}
+  ARKS_HD bool dead() const { return err | (st == S_STOP); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -759,11 +769,89 @@ struct SseM {
     }
     line_byte(c, pos);
   }
+  // bulk interface: inside a data value, inside a JSON string, with all line bookkeeping that depends on single
+  // bytes already settled (the [DONE] probe has its 8 bytes, no CR is pending, the 64 KiB limit is far away)
+  ARKS_HD bool can_fast() const {
+    return (phase == 2) & (field == 1) & !done & !fail & !pending_cr & (data_pos >= 8) & (line_len < 65000) & ev.can_fast();
+  }
+  ARKS_HD void skip(uint32_t k) {
+    line_len += k;
+    data_pos += k;
+  }
+  ARKS_HD bool dead() const { return fail; }
   // end of chunk: an unterminated last line is still a token; a pending event is dropped
   ARKS_HD bool finish(uint32_t pos) {
     if (!fail && line_len > 0) end_line(pos);
     return !fail;
   }
 };
+
+// ---------------------------------------------------------------------------------------------
+// Bulk consumption: 16-byte units, SWAR search for the next byte a string cares about
+// ---------------------------------------------------------------------------------------------
+struct Unit16 {
+  uint32_t w[4];
+};
+
+// bit k set  <=>  byte k of the unit may be '"', '\\' or < 0x20. The lowest set bit at or above any offset is always
+// exact; higher bits of the same 32-bit word can be false positives (borrow of the has-zero-byte trick), which only
+// costs a step() call on an ordinary byte.
+ARKS_HD uint32_t special_mask16(const Unit16& q) {
+  uint32_t m = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; k++) {
+    uint32_t w = q.w[k];
+    uint32_t y = w ^ 0x22222222u, z = w ^ 0x5c5c5c5cu;
+    uint32_t f = ((y - 0x01010101u) & ~y) | ((z - 0x01010101u) & ~z) | ((w - 0x20202020u) & ~w);
+    f = (f >> 7) & 0x01010101u;
+    m |= ((f * 0x01020408u) >> 24 & 0xfu) << (4 * k);
+  }
+  return m;
+}
+
+// Feed bytes [pos, lim) of one body to machine `m`; `load(u)` returns 16-byte unit u of the body (bytes past the
+// body's end may hold anything). Advances pos. Ordinary string bytes are skipped 16 at a time.
+template <class M, class L>
+ARKS_HD void consume(M& m, uint32_t& pos, uint32_t lim, L&& load) {
+  uint32_t cu = 0xffffffffu, mask = 0;
+  bool mask_ok = false;
+  Unit16 q;
+  q.w[0] = q.w[1] = q.w[2] = q.w[3] = 0;
+  while (pos < lim && !m.dead()) {
+    uint32_t u = pos >> 4, o = pos & 15;
+    if (u != cu) {
+      q = load(u);
+      cu = u;
+      mask_ok = false;
+    }
+    if (m.can_fast()) {
+      if (!mask_ok) {
+        mask = special_mask16(q);
+        mask_ok = true;
+      }
+      uint32_t rest = mask >> o;
+      uint32_t run = rest ? (uint32_t)(
+#if defined(__CUDA_ARCH__)
+                                __ffs((int)rest)
+#else
+                                __builtin_ffs((int)rest)
+#endif
+                                - 1)
+                          : 16u - o;
+      uint32_t avail = lim - pos;
+      if (run > avail) run = avail;
+      if (run) {
+        m.skip(run);
+        pos += run;
+        continue;
+      }
+    }
+    uint8_t c = (uint8_t)(q.w[o >> 2] >> (8 * (o & 3)));
+    m.step(c, pos);
+    pos++;
+  }
+}
 
 }  // namespace arks
