@@ -240,8 +240,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) scan_request_kernel(De
   const uint8_t* body = B.bodies + (live ? B.body_off[i] : 0);
   const uint32_t len = live ? B.body_len[i] : 0;
 
+  uint32_t stack_words[kStackWords];  // local memory, touched only beyond 32 levels of nesting
   JsonM m;
-  m.init(K_REQ, body);
+  m.init(K_REQ, body, stack_words);
   feed_tiled(m, body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
   if (!live) return;
 
@@ -433,16 +434,61 @@ __device__ __forceinline__ void warp_agg_add(long long* addr, long long v, bool 
   if ((int)(threadIdx.x & 31) == leader) atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)sum);
 }
 
-// per-lane response machine: an SSE chunk (stream) or one JSON document (non-stream); one engine instance serves both
-struct RespM {
+// per-lane response machine: an SSE chunk (stream) or one JSON document (non-stream). MODE 1 / 2 are the
+// all-JSON / all-SSE specialisations the host picks when a batch is homogeneous (smaller live state); MODE 0 mixes.
+template <int MODE>
+struct RespM;
+template <>
+struct RespM<1> {
+  JsonM ev;
+  static constexpr bool sse = false;
+  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk) { ev.init(K_RESP, body, stk); }
+  __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { ev.step(c, pos); }
+  __device__ __forceinline__ bool can_fast() const { return ev.can_fast(); }
+  __device__ __forceinline__ void skip(uint32_t k, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) { ev.skip(k, o, q0, q1, q2, q3); }
+  __device__ __forceinline__ bool dead() const { return ev.dead(); }
+  __device__ __forceinline__ JsonM& json() { return ev; }
+  __device__ __forceinline__ bool finish(uint32_t, long long&, long long&, long long&) { return true; }
+};
+template <>
+struct RespM<2> {
+  SseM s;
+  static constexpr bool sse = true;
+  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk) { s.init(body, stk); }
+  __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { s.step(c, pos); }
+  __device__ __forceinline__ bool can_fast() const { return s.can_fast(); }
+  __device__ __forceinline__ void skip(uint32_t k, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) { s.skip(k, o, q0, q1, q2, q3); }
+  __device__ __forceinline__ bool dead() const { return s.dead(); }
+  __device__ __forceinline__ JsonM& json() { return s.ev; }
+  __device__ __forceinline__ bool finish(uint32_t len, long long& u0, long long& u1, long long& u2) {
+    bool ok = s.finish(len);
+    u0 = s.usage[0]; u1 = s.usage[1]; u2 = s.usage[2];
+    return ok;
+  }
+};
+template <>
+struct RespM<0> {
   SseM s;
   bool sse;
+  __device__ __forceinline__ void init(bool is_sse, const uint8_t* body, uint32_t* stk) {
+    sse = is_sse;
+    if (sse) s.init(body, stk); else s.ev.init(K_RESP, body, stk);
+  }
   __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { if (sse) s.step(c, pos); else s.ev.step(c, pos); }
   __device__ __forceinline__ bool can_fast() const { return sse ? s.can_fast() : s.ev.can_fast(); }
-  __device__ __forceinline__ void skip(uint32_t k) { if (sse) s.skip(k); }
+  __device__ __forceinline__ void skip(uint32_t k, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
+    if (sse) s.skip(k, o, q0, q1, q2, q3); else s.ev.skip(k, o, q0, q1, q2, q3);
+  }
   __device__ __forceinline__ bool dead() const { return sse ? s.dead() : s.ev.dead(); }
+  __device__ __forceinline__ JsonM& json() { return s.ev; }
+  __device__ __forceinline__ bool finish(uint32_t len, long long& u0, long long& u1, long long& u2) {
+    bool ok = s.finish(len);
+    u0 = s.usage[0]; u1 = s.usage[1]; u2 = s.usage[2];
+    return ok;
+  }
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) scan_response_kernel(DevTables T, RespDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,21 +502,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) scan_response_kernel(D
     const bool pending = !(fl & (ARKS_RESP_STREAM | ARKS_RESP_END_OF_STREAM));  // handle_response.go:141-149
     uint32_t len = live && !pending ? B.body_len[i] : 0;
     qos = live ? B.qos[i] : 0;
-    RespM rm;
-    rm.sse = fl & ARKS_RESP_STREAM;
-    if (rm.sse) rm.s.init(body); else rm.s.ev.init(K_RESP, body);
+    uint32_t stack_words[kStackWords];  // local memory, touched only beyond 32 levels of nesting
+    RespM<MODE> rm;
+    const bool is_sse = MODE == 2 || (MODE == 0 && (fl & ARKS_RESP_STREAM));
+    rm.init(is_sse, body, stack_words);
     feed_tiled(rm, body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
     if (live) {
-      SseM& s = rm.s;
-      if (rm.sse) {  // handle_response.go:113-133, every chunk in isolation
-        if (!s.finish(len)) reason = ARKS_R_STREAMING;
-        else { u0 = s.usage[0]; u1 = s.usage[1]; u2 = s.usage[2]; }
+      if (is_sse) {  // handle_response.go:113-133, every chunk in isolation
+        if (!rm.finish(len, u0, u1, u2)) reason = ARKS_R_STREAMING;
       } else if (pending) {
         reason = ARKS_R_PENDING;
       } else {
-        if (!s.ev.ok_at_end()) reason = ARKS_R_RESPONSE_UNMARSHAL;  // :157-166
-        else if (s.ev.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // :167-181
-        else { u0 = s.ev.usage[0]; u1 = s.ev.usage[1]; u2 = s.ev.usage[2]; }
+        JsonM& ev = rm.json();
+        if (!ev.ok_at_end()) reason = ARKS_R_RESPONSE_UNMARSHAL;  // :157-166
+        else if (ev.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // :167-181
+        else { u0 = ev.usage[0]; u1 = ev.usage[1]; u2 = ev.usage[2]; }
       }
       if (reason != ARKS_R_OK) { u0 = u1 = u2 = 0; }
       counted = reason == ARKS_R_OK && u2 != 0;  // :186
@@ -547,6 +593,7 @@ struct arks_ctx {
     ReqDev rq{};
     RespDev rp{};
     uint32_t req_n = 0, resp_n = 0;
+    int resp_mode = 0;  // 1 all JSON documents, 2 all SSE chunks, 0 mixed
     bool req_staged = false, resp_staged = false;
   };
   static constexpr int kSlots = 4;
@@ -647,7 +694,9 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   ctx->meta_cap = align_up(n * 4, 256) * 4 + align_up(n * 8, 256) + align_up(n, 256) + align_up(n * 256, 256);
   for (int k = 0; k < 4; k++) CK(cudaEventCreate(&ctx->ev[k]));
   CK(cudaFuncSetAttribute(scan_request_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
-  CK(cudaFuncSetAttribute(scan_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
+  CK(cudaFuncSetAttribute(scan_response_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
+  CK(cudaFuncSetAttribute(scan_response_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
+  CK(cudaFuncSetAttribute(scan_response_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
   uint32_t g = 64;
   while (g < 2 * n) g <<= 1;
   ctx->gsize = g;
@@ -1051,11 +1100,14 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   sl.resp_n = n;
   sl.resp_staged = true;
   if (n == 0) return 0;
+  uint32_t n_sse = 0;
   for (uint32_t i = 0; i < n; i++) {
+    n_sse += (b->flags[i] & ARKS_RESP_STREAM) != 0;
     if (b->qos[i] < 0 || (uint32_t)b->qos[i] >= ctx->ht.n_qos) return fail(ctx, ARKS_E_INVALID_ARG, "response %u: bad qos index", i);
     if ((b->body_off[i] & 15u) || (uint64_t)b->body_off[i] + b->body_len[i] > b->bodies_bytes)
       return fail(ctx, ARKS_E_INVALID_ARG, "body %u: offset not 16-byte aligned or out of range", i);
   }
+  sl.resp_mode = n_sse == 0 ? 1 : n_sse == n ? 2 : 0;
   size_t o_off = 0, o_len = align_up((size_t)n * 4, 256), o_qos = o_len * 2, o_fl = o_len * 3, total = o_fl + align_up(n, 256);
   CK(cudaEventSynchronize(sl.resp_copied));
   uint8_t* h = sl.h_resp_meta;
@@ -1093,7 +1145,10 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
   if (n == 0) return 0;
   const uint32_t tpb = kWarpsPerBlock * 32;
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  scan_response_kernel<<<(n + tpb - 1) / tpb, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
+  const dim3 grid((n + tpb - 1) / tpb);
+  if (sl.resp_mode == 1) scan_response_kernel<1><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
+  else if (sl.resp_mode == 2) scan_response_kernel<2><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
+  else scan_response_kernel<0><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
   if (ctx->prof) { CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_n = 2; }
   ctx->launches += 1;
   CK(cudaGetLastError());

@@ -59,6 +59,7 @@ enum : uint8_t { L2_NONE = 0, L2_SO, L2_USAGE };
 enum : uint8_t { F_MINUS = 0, F_ZERO, F_INT, F_DOT, F_FRAC, F_E, F_ESIGN, F_EXP, F_DEAD };
 
 static constexpr uint32_t kMaxDepth = 10000;  // jsoniter maxDepth == encoding/json maxNestingDepth
+static constexpr uint32_t kStackWords = (kMaxDepth + 31) / 32 + 1;
 
 // jsoniter readFieldHash: int64 0x811c9dc5, ^= lower(byte), *= 0x1000193 (iter_object.go)
 ARKS_HD constexpr uint64_t fhash_step(uint64_t h, uint8_t b) {
@@ -209,13 +210,14 @@ struct JsonM {
   uint8_t m_esc;               // raw span contains a backslash
   uint8_t stream3, so_present, iu3;
   int64_t usage[3];
-  int64_t cand[3];
+  int64_t cand0, cand1, cand2;  // scalars, not an array: a dynamically indexed array would live in local memory
   uint8_t cand_set, cand_nonnull;
   uint8_t has_error_key, n_choices;
-  uint32_t stk[(kMaxDepth + 31) / 32 + 1];
+  uint32_t* stk;  // container-type stack beyond the cached word: (kMaxDepth+31)/32+1 words, owned by the caller
 
-  ARKS_HD void init(uint8_t k, const uint8_t* b) {
+  ARKS_HD void init(uint8_t k, const uint8_t* b, uint32_t* stack_words) {
     base = b;
+    stk = stack_words;
     kind = k;
     st = (k == K_EVT) ? S_VAL : S_TOP;
     err = 0;
@@ -228,14 +230,15 @@ struct JsonM {
     m_start = 0; m_rawlen = 0; m_esc = 0;
     stream3 = 0; so_present = 0; iu3 = 0;
     usage[0] = usage[1] = usage[2] = 0;
-    cand[0] = cand[1] = cand[2] = 0;
+    cand0 = cand1 = cand2 = 0;
     cand_set = 0; cand_nonnull = 0;
     has_error_key = 0; n_choices = 0;
   }
   // restart for the next SSE event (fresh ChatCompletionChunk per event)
   ARKS_HD void reset_event() {
     const uint8_t* b = base;
-    init(K_EVT, b);
+    uint32_t* sw = stk;
+    init(K_EVT, b, sw);
   }
 
   ARKS_HD bool top_is_object() const { return (cur_word >> ((depth - 1) & 31)) & 1u; }
@@ -260,10 +263,13 @@ struct JsonM {
   }
   ARKS_HD void value_done() { st = depth == 0 ? S_FINISH : S_AFTER; }
 
+  ARKS_HD void set_cand(int64_t v) {
+    if (ufield == 0) cand0 = v; else if (ufield == 1) cand1 = v; else cand2 = v;
+  }
   ARKS_HD void commit_usage_cands() {
     // apijson struct decoder over node.Map(): last duplicate wins; null leaves the field untouched
     for (int f = 0; f < 3; f++)
-      if ((cand_set >> f) & (cand_nonnull >> f) & 1) usage[f] = cand[f];
+      if ((cand_set >> f) & (cand_nonnull >> f) & 1) usage[f] = f == 0 ? cand0 : f == 1 ? cand1 : cand2;
   }
   ARKS_HD void close_container(uint8_t c) {
     bool obj = top_is_object();
@@ -345,9 +351,9 @@ struct JsonM {
       case VM_UINT:  // a usage counter: gjson Result.Int by JSON type
         cand_set |= (uint8_t)(1u << ufield);
         cand_nonnull |= (uint8_t)(1u << ufield);
-        cand[ufield] = 0;
+        set_cand(0);
         if (c == '"') { begin_string(SK_VALUE_UINT, pos); return; }
-        if (c == 't') cand[ufield] = 1;
+        if (c == 't') set_cand(1);
         if (c == 'n') cand_nonnull &= (uint8_t)~(1u << ufield);
         ncap = 1;
         break;  // generic dispatch below (ncap only matters for numbers)
@@ -441,7 +447,7 @@ struct JsonM {
       case SK_VALUE_UINT: {  // gjson String -> parseInt(t.Str)
         int64_t v = 0;
         if (!s_esc && sval_ok && sval_any) v = nneg ? (int64_t)(0 - nacc) : (int64_t)nacc;
-        cand[ufield] = v;
+        set_cand(v);
         value_done();
         break;
       }
@@ -474,7 +480,7 @@ struct JsonM {
         else v = nneg ? -(int64_t)m : (int64_t)m;
       }
     }
-    cand[ufield] = v;
+    set_cand(v);
   }
 
   // returns true when `c` was consumed, false when the number ended before `c` (reprocess it)
@@ -548,105 +554,99 @@ struct JsonM {
     return true;
   }
 
+  // token-level states (whitespace already excluded); if-chain ordered by frequency instead of a jump table
+  ARKS_HD void step_token(uint8_t c, uint32_t pos) {
+    const uint8_t s0 = st;
+    if (s0 == S_AFTER) {
+      if (c == ',') {
+        if (top_is_object()) {
+          bool strct = kind != K_EVT && (depth == 1 || (depth == 2 && l2 == L2_SO));
+          st = strct ? S_STRUCT_KEY : S_OBJ_KEY;
+        } else {
+          st = S_VAL;
+        }
+        vm = VM_SKIP;
+      } else if (c == '}' || c == ']') {
+        close_container(c);
+      } else {
+        err = 1;
+      }
+    } else if (s0 == S_COLON) {
+      if (c == ':') st = S_VAL; else err = 1;
+    } else if (s0 == S_VAL) {
+      begin_value(c, pos);
+    } else if (s0 == S_OBJ_KEY) {
+      if (c == '"') begin_key(pos);
+      else if (c == 'n' && kind != K_EVT) begin_literal(c, true);  // ReadString() accepts null as a key
+      else err = 1;
+    } else if (s0 == S_STRUCT_KEY) {
+      if (c == '"') begin_key(pos); else err = 1;
+    } else if (s0 == S_OBJ_FIRST || s0 == S_STRUCT_FIRST) {
+      if (c == '"') begin_key(pos);
+      else if (c == '}') close_container(c);
+      else err = 1;
+    } else if (s0 == S_ARR_FIRST) {
+      if (c == ']') { close_container(c); return; }
+      if (in_choices && depth == 2) n_choices = 1;
+      begin_value(c, pos);
+    } else if (s0 == S_TOP) {  // readObjectStart
+      if (c == '{') { push(true); st = S_STRUCT_FIRST; }
+      else if (c == 'n') begin_literal(c, false);
+      else err = 1;
+    } else {  // S_FINISH
+      if (c == 0 && kind != K_EVT) st = S_STOP;  // frozenConfig.Unmarshal: `if c == 0` also matches a NUL byte
+      else err = 1;
+    }
+  }
+
   ARKS_HD void step(uint8_t c, uint32_t pos) {
     for (;;) {
       if (err | (st == S_STOP)) return;
-      if (st < S_TOKEN_STATES) {
-        if (is_ws(c)) return;
-        switch (st) {
-          case S_TOP:  // readObjectStart
-            if (c == '{') { push(true); st = S_STRUCT_FIRST; }
-            else if (c == 'n') begin_literal(c, false);
-            else err = 1;
-            return;
-          case S_VAL: begin_value(c, pos); return;
-          case S_ARR_FIRST:
-            if (c == ']') { close_container(c); return; }
-            if (in_choices && depth == 2) n_choices = 1;
-            begin_value(c, pos);
-            return;
-          case S_OBJ_FIRST:
-            if (c == '"') begin_key(pos);
-            else if (c == '}') close_container(c);
-            else err = 1;
-            return;
-          case S_OBJ_KEY:
-            if (c == '"') begin_key(pos);
-            else if (c == 'n' && kind != K_EVT) begin_literal(c, true);  // ReadString() accepts null as a key
-            else err = 1;
-            return;
-          case S_STRUCT_FIRST:
-            if (c == '}') close_container(c);
-            else if (c == '"') begin_key(pos);
-            else err = 1;
-            return;
-          case S_STRUCT_KEY:
-            if (c == '"') begin_key(pos);
-            else err = 1;
-            return;
-          case S_COLON:
-            if (c == ':') st = S_VAL;
-            else err = 1;
-            return;
-          case S_AFTER:
-            if (c == ',') {
-              if (top_is_object()) {
-                bool strct = kind != K_EVT && (depth == 1 || (depth == 2 && l2 == L2_SO));
-                st = strct ? S_STRUCT_KEY : S_OBJ_KEY;
-                vm = VM_SKIP;
-              } else {
-                st = S_VAL;
-                vm = VM_SKIP;
-              }
-            } else if (c == '}' || c == ']') {
-              close_container(c);
-            } else {
-              err = 1;
-            }
-            return;
-          default:  // S_FINISH
-            if (c == 0 && kind != K_EVT) st = S_STOP;  // frozenConfig.Unmarshal: `if c == 0` also matches a NUL byte
-            else err = 1;
-            return;
+      const uint8_t s0 = st;
+      if (s0 == S_STR) {
+        if (c == '"') { end_string(pos); return; }
+        if (c == '\\') { s_esc = 1; st = S_ESC; return; }
+        if (c < 0x20 && skind != SK_KEY_STRUCT) { err = 1; return; }  // readFieldHash has no such check
+        if (skind >= SK_KEY_STRUCT) khash = skind == SK_KEY_STRUCT ? fhash_step(khash, c) : xhash_step(khash, c);
+        else if (skind == SK_VALUE_UINT) {
+          if (c == '-' && !sval_any && !nneg && pos == sstart) nneg = 1;
+          else if (is_digit(c)) { nacc = nacc * 10 + (uint64_t)(c - '0'); sval_any = 1; }
+          else sval_ok = 0;
         }
+        return;
       }
-      switch (st) {
-        case S_STR:
-          if (c == '"') { end_string(pos); return; }
-          if (c == '\\') { s_esc = 1; st = S_ESC; return; }
-          if (c < 0x20 && skind != SK_KEY_STRUCT) { err = 1; return; }  // readFieldHash has no such check
-          if (skind >= SK_KEY_STRUCT) khash = skind == SK_KEY_STRUCT ? fhash_step(khash, c) : xhash_step(khash, c);
-          else if (skind == SK_VALUE_UINT) {
-            if (c == '-' && !sval_any && !nneg && pos == sstart) nneg = 1;
-            else if (is_digit(c)) { nacc = nacc * 10 + (uint64_t)(c - '0'); sval_any = 1; }
-            else sval_ok = 0;
-          }
-          return;
-        case S_STR_E:
-          if (c == '"') { end_string(pos); return; }
-          if (c == '\\') { st = S_ESC; return; }
-          if (c < 0x20 && kind == K_EVT) err = 1;  // jsoniter's slow path does not check control characters
-          return;
-        case S_ESC:
-          if (c == 'u') { ucnt = 4; st = S_U; }
-          else if (c == '"' || c == '\\' || c == '/' || c == 'b' || c == 'f' || c == 'n' || c == 'r' || c == 't') st = S_STR_E;
-          else err = 1;
-          return;
-        case S_U:
-          if (hexval(c) < 0) { err = 1; return; }
-          if (--ucnt == 0) st = S_STR_E;
-          return;
-        case S_LIT:
-          if (c != (uint8_t)(lit & 0xff)) { err = 1; return; }
-          lit >>= 8;
-          if (lit == 0) {
-            if (lit_is_key) st = S_COLON; else value_done();
-          }
-          return;
-        default:  // S_NUM
-          if (step_number(c)) return;
-          break;  // reprocess c in the new state
+      if (s0 < S_TOKEN_STATES) {
+        if (!is_ws(c)) step_token(c, pos);
+        return;
       }
+      if (s0 == S_STR_E) {
+        if (c == '"') { end_string(pos); return; }
+        if (c == '\\') { st = S_ESC; return; }
+        if (c < 0x20 && kind == K_EVT) err = 1;  // jsoniter's slow path does not check control characters
+        return;
+      }
+      if (s0 == S_LIT) {
+        if (c != (uint8_t)(lit & 0xff)) { err = 1; return; }
+        lit >>= 8;
+        if (lit == 0) {
+          if (lit_is_key) st = S_COLON; else value_done();
+        }
+        return;
+      }
+      if (s0 == S_NUM) {
+        if (step_number(c)) return;
+        continue;  // the number ended before c: reprocess c in the new state
+      }
+      if (s0 == S_ESC) {
+        if (c == 'u') { ucnt = 4; st = S_U; }
+        else if (c == '"' || c == '\\' || c == '/' || c == 'b' || c == 'f' || c == 'n' || c == 'r' || c == 't') st = S_STR_E;
+        else err = 1;
+        return;
+      }
+      // S_U
+      if (hexval(c) < 0) { err = 1; return; }
+      if (--ucnt == 0) st = S_STR_E;
+      return;
     }
   }
 
@@ -657,10 +657,20 @@ struct JsonM {
   // True while the machine sits inside a string whose ordinary bytes need no per-byte action: the caller may then
   // skip ahead to the next '"', '\\' or byte < 0x20 without calling step() (skipped bytes are never control bytes,
   // so the jsoniter "control character before the first backslash" rule cannot be missed).
-  ARKS_HD bool can_fast() const {
-    return (st == S_STR_E) | ((st == S_STR) & (skind < SK_KEY_STRUCT) & (skind != SK_VALUE_UINT));
+  ARKS_HD bool can_fast() const { return (st == S_STR_E) | ((st == S_STR) & (skind != SK_VALUE_UINT)); }
+  // the `n` ordinary bytes being skipped are bytes [o, o+n) of the unit (q0..q3): hashed keys still need them
+  ARKS_HD void skip(uint32_t n, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
+    if ((st == S_STR) & (skind >= SK_KEY_STRUCT)) {
+      uint64_t h = khash;
+      const bool fold = skind == SK_KEY_STRUCT;
+      for (uint32_t k = o; k < o + n; k++) {
+        const uint32_t lo = (k & 8) ? q2 : q0, hi = (k & 8) ? q3 : q1;
+        const uint8_t b = (uint8_t)(((k & 4) ? hi : lo) >> (8 * (k & 3)));
+        h = fold ? fhash_step(h, b) : xhash_step(h, b);
+      }
+      khash = h;
+    }
   }
-  ARKS_HD void skip(uint32_t) {}
   ARKS_HD bool dead() const { return err | (st == S_STOP); }
 };
 
@@ -681,8 +691,8 @@ struct SseM {
   uint8_t field;       // 0 other, 1 data, 2 event
   uint8_t pending_cr, done, fail, thread_evt, ev_len_any;
 
-  ARKS_HD void init(const uint8_t* base) {
-    ev.init(K_EVT, base);
+  ARKS_HD void init(const uint8_t* base, uint32_t* stack_words) {
+    ev.init(K_EVT, base, stack_words);
     usage[0] = usage[1] = usage[2] = 0;
     line_len = 0; name_len = 0; name_acc = 0; data_pos = 0; data_head = 0; ev_match = 0;
     phase = 0; field = 0; pending_cr = 0; done = 0; fail = 0; thread_evt = 0; ev_len_any = 0;
@@ -774,9 +784,10 @@ struct SseM {
   ARKS_HD bool can_fast() const {
     return (phase == 2) & (field == 1) & !done & !fail & !pending_cr & (data_pos >= 8) & (line_len < 65000) & ev.can_fast();
   }
-  ARKS_HD void skip(uint32_t k) {
+  ARKS_HD void skip(uint32_t k, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
     line_len += k;
     data_pos += k;
+    ev.skip(k, o, q0, q1, q2, q3);
   }
   ARKS_HD bool dead() const { return fail; }
   // end of chunk: an unterminated last line is still a token; a pending event is dropped
@@ -793,64 +804,67 @@ struct Unit16 {
   uint32_t w[4];
 };
 
-// bit k set  <=>  byte k of the unit may be '"', '\\' or < 0x20. The lowest set bit at or above any offset is always
-// exact; higher bits of the same 32-bit word can be false positives (borrow of the has-zero-byte trick), which only
-// costs a step() call on an ordinary byte.
-ARKS_HD uint32_t special_mask16(const Unit16& q) {
-  uint32_t m = 0;
+// bit 7 of byte k set  <=>  byte k of the word may be '"', '\\' or < 0x20 (other bits are garbage). The lowest flagged
+// byte is always exact; higher bytes can be false positives (borrow of the subtract), which only costs a step() call on
+// an ordinary byte. x ^ 0x02 maps {0x00..0x1f, '"'} onto the contiguous range 0x00..0x20, so two range tests suffice.
+ARKS_HD uint32_t special_flags(uint32_t w) {
+  uint32_t a = w ^ 0x02020202u, b = w ^ 0x5c5c5c5cu;
+  return ((a - 0x21212121u) & ~a) | ((b - 0x01010101u) & ~b);
+}
+ARKS_HD uint32_t special_mask16(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
+  uint32_t f0 = (special_flags(q0) >> 7) & 0x01010101u, f1 = (special_flags(q1) >> 7) & 0x01010101u;
+  uint32_t f2 = (special_flags(q2) >> 7) & 0x01010101u, f3 = (special_flags(q3) >> 7) & 0x01010101u;
+  return ((f0 * 0x01020408u) >> 24 & 0xfu) | ((f1 * 0x01020408u) >> 20 & 0xf0u) | ((f2 * 0x01020408u) >> 16 & 0xf00u) |
+         ((f3 * 0x01020408u) >> 12 & 0xf000u);
+}
+ARKS_HD uint32_t first_set(uint32_t x) {
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+  return (uint32_t)__ffs((int)x) - 1u;
+#else
+  return (uint32_t)__builtin_ffs((int)x) - 1u;
 #endif
-  for (int k = 0; k < 4; k++) {
-    uint32_t w = q.w[k];
-    uint32_t y = w ^ 0x22222222u, z = w ^ 0x5c5c5c5cu;
-    uint32_t f = ((y - 0x01010101u) & ~y) | ((z - 0x01010101u) & ~z) | ((w - 0x20202020u) & ~w);
-    f = (f >> 7) & 0x01010101u;
-    m |= ((f * 0x01020408u) >> 24 & 0xfu) << (4 * k);
-  }
-  return m;
 }
 
 // Feed bytes [pos, lim) of one body to machine `m`; `load(u)` returns 16-byte unit u of the body (bytes past the
-// body's end may hold anything). Advances pos. Ordinary string bytes are skipped 16 at a time.
+// body's end may hold anything). Advances pos. Inside strings, units without a special byte are skipped whole.
 template <class M, class L>
 ARKS_HD void consume(M& m, uint32_t& pos, uint32_t lim, L&& load) {
-  uint32_t cu = 0xffffffffu, mask = 0;
-  bool mask_ok = false;
-  Unit16 q;
-  q.w[0] = q.w[1] = q.w[2] = q.w[3] = 0;
-  while (pos < lim && !m.dead()) {
-    uint32_t u = pos >> 4, o = pos & 15;
+  uint32_t cu = 0xffffffffu;
+  uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+  while (pos < lim) {
+    const uint32_t u = pos >> 4, o = pos & 15;
     if (u != cu) {
-      q = load(u);
+      Unit16 q = load(u);
+      q0 = q.w[0]; q1 = q.w[1]; q2 = q.w[2]; q3 = q.w[3];
       cu = u;
-      mask_ok = false;
     }
     if (m.can_fast()) {
-      if (!mask_ok) {
-        mask = special_mask16(q);
-        mask_ok = true;
-      }
-      uint32_t rest = mask >> o;
-      uint32_t run = rest ? (uint32_t)(
-#if defined(__CUDA_ARCH__)
-                                __ffs((int)rest)
-#else
-                                __builtin_ffs((int)rest)
-#endif
-                                - 1)
-                          : 16u - o;
-      uint32_t avail = lim - pos;
+      const uint32_t avail = lim - pos;
+      const uint32_t rest = special_mask16(q0, q1, q2, q3) >> o;
+      uint32_t run = rest ? first_set(rest) : 16u - o;
       if (run > avail) run = avail;
       if (run) {
-        m.skip(run);
+        m.skip(run, o, q0, q1, q2, q3);
         pos += run;
+        // long plain stretch: keep swallowing whole clean units without re-entering the outer loop
+        if (o + run == 16) {
+          while (lim - pos >= 16) {
+            Unit16 n = load(pos >> 4);
+            const uint32_t any = (special_flags(n.w[0]) | special_flags(n.w[1]) | special_flags(n.w[2]) | special_flags(n.w[3])) & 0x80808080u;
+            if (any) break;
+            m.skip(16, 0, n.w[0], n.w[1], n.w[2], n.w[3]);
+            pos += 16;
+          }
+        }
         continue;
       }
     }
-    uint8_t c = (uint8_t)(q.w[o >> 2] >> (8 * (o & 3)));
-    m.step(c, pos);
+    // byte o of the unit, without indexing the registers dynamically
+    const uint32_t lo = (o & 8) ? q2 : q0, hi = (o & 8) ? q3 : q1;
+    const uint32_t w = (o & 4) ? hi : lo;
+    m.step((uint8_t)(w >> (8 * (o & 3))), pos);
     pos++;
+    if (m.dead()) return;
   }
 }
 

@@ -39,13 +39,14 @@ BODY = 1024
 RESP_BODY = 600
 N_WAVES = 3
 NOW0 = 1_700_000_000
+STEP_S = 86_400  # `now` advances one day per step: fresh rpm/tpm and rpd/tpd windows each step (stationary admission pattern)
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--wave", type=int, default=WAVE)
     ap.add_argument("--tenants", type=int, default=TENANTS)
@@ -137,7 +138,7 @@ def cpu_baseline(workload, wave, seconds=12.0, threads=None):
     a = o.request_batch(req, threads=threads)
     resp = workload.response_batch(a, NOW0 + 1, seed=4243, body_size=RESP_BODY)
     o.response_batch(resp, threads=threads)
-    now, done, t_used, steps = NOW0 + 60, 0, 0.0, 0
+    now, done, t_used, steps = NOW0 + STEP_S, 0, 0.0, 0
     while t_used < seconds and steps < 400:
         req.now_unix, resp.now_unix = now, now + 1
         t0 = time.perf_counter()
@@ -145,7 +146,7 @@ def cpu_baseline(workload, wave, seconds=12.0, threads=None):
         o.response_batch(resp, threads=threads)
         t_used += time.perf_counter() - t0
         done += req.n
-        now += 60
+        now += STEP_S
         steps += 1
     return {"value": done / t_used, "unit": "req/s", "cores": threads, "kind": "port",
             "sample": f"{steps} waves of {req.n} requests + {resp.n} responses, oracle/libarks_oracle.so "
@@ -166,18 +167,18 @@ def run_reference(args):
     a = o.request_batch(req, threads=threads)
     resp = w.response_batch(a, NOW0 + 1, seed=2000, body_size=RESP_BODY)
     o.response_batch(resp, threads=threads)
-    now = NOW0 + 60
+    now = NOW0 + STEP_S
     for _ in range(args.warmup):
         req.now_unix, resp.now_unix = now, now + 1
         o.request_batch(req, threads=threads)
         o.response_batch(resp, threads=threads)
-        now += 60
+        now += STEP_S
     t0 = time.perf_counter()
     for _ in range(args.steps):
         req.now_unix, resp.now_unix = now, now + 1
         o.request_batch(req, threads=threads)
         o.response_batch(resp, threads=threads)
-        now += 60
+        now += STEP_S
     dt = time.perf_counter() - t0
     v = args.steps * req.n / dt
     sample = (f"{args.steps} waves of {req.n} requests + {resp.n} responses per step; the Go gateway cannot be built here "
@@ -226,12 +227,12 @@ def run_b200(args):
     # dry pass to learn which requests are admitted in a fresh window, then build the matching response waves
     resps = []
     for k, rb in enumerate(reqs):
-        rb.now_unix = NOW0 + 60 * k
+        rb.now_unix = NOW0 + STEP_S * k
         a = g.handle_request_body(rb)
-        resps.append(pin_batch(w.response_batch(a, NOW0 + 60 * k + 1, seed=3000 + k, body_size=RESP_BODY)))
+        resps.append(pin_batch(w.response_batch(a, NOW0 + STEP_S * k + 1, seed=3000 + k, body_size=RESP_BODY)))
     req_out = [abi.RequestResult.empty(b.n) for b in reqs]
     resp_out = [abi.ResponseResult.empty(b.n) for b in resps]
-    now = NOW0 + 60 * N_WAVES
+    now = NOW0 + STEP_S * N_WAVES
     ext = torch.cuda.ExternalStream(g.stream_handle, device=torch.device("cuda", local))
 
     def barrier():
@@ -254,21 +255,27 @@ def run_b200(args):
 
     for i in range(args.warmup):
         resident_step(i, now)
-        now += 60
+        now += STEP_S
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
+    # keep the GPU under this workload until nvidia-smi has produced its first samples
+    t_spin = time.perf_counter()
+    i = 0
+    while time.perf_counter() - t_spin < 0.6:
+        resident_step(i, now)
+        now += STEP_S
+        i += 1
+    barrier()
     launches0 = g.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
     for i in range(args.steps):
         resident_step(args.warmup + i, now)
-        now += 60
+        now += STEP_S
     e1.record(ext)
     barrier()
     launches = g.launch_count - launches0
     dev_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     # per-kernel timing for the roofline (separate pass so event records do not sit inside the timed region)
     g.set_profiling(True)
     scan_ms, admit_ms, resp_ms = [], [], []
@@ -280,7 +287,7 @@ def run_b200(args):
         scan_ms.append(ms[0]); admit_ms.append(ms[1])
         g.run_response(now + 1)
         resp_ms.append(g.last_kernel_ms()[0])
-        now += 60
+        now += STEP_S
     g.set_profiling(False)
 
     # ---- end-to-end arm: host buffers through the public API --------------------------------------
@@ -290,7 +297,7 @@ def run_b200(args):
         reqs[k].now_unix, resps[k].now_unix = now, now + 1
         g.handle_request_body(reqs[k], req_out[k])
         g.handle_response_body(resps[k], resp_out[k])
-        now += 60
+        now += STEP_S
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -298,9 +305,10 @@ def run_b200(args):
         reqs[k].now_unix, resps[k].now_unix = now, now + 1
         g.handle_request_body(reqs[k], req_out[k])
         g.handle_response_body(resps[k], resp_out[k])
-        now += 60
+        now += STEP_S
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()  # sampled across both timed regions (kernel-only and end-to-end)
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s * 1e3], device=f"cuda:{local}", dtype=torch.float64)
@@ -319,6 +327,10 @@ def run_b200(args):
     scan_s = float(np.mean(scan_ms)) / 1e3
     peak, how = peaks()
     achieved = req_bytes / scan_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        traffic = json.load(open(tp)).get("scan_request_kernel", {}).get("dram_bytes_per_launch")
     h2d = int(np.mean([b.bodies.nbytes + b.body_off.nbytes + b.body_len.nbytes + b.tokens.nbytes + b.token_off.nbytes +
                        b.pick_rand.nbytes for b in reqs]) +
               np.mean([b.bodies.nbytes + b.body_off.nbytes + b.body_len.nbytes + b.qos.nbytes + b.flags.nbytes for b in resps]))
@@ -335,7 +347,7 @@ def run_b200(args):
         "kernels_ms": {"scan_request": float(np.mean(scan_ms)), "limit_admit": float(np.mean(admit_ms)),
                        "scan_response": float(np.mean(resp_ms))},
         "roofline": {"bound": "hbm", "kernel": "scan_request_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": how,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": how,
                      "algorithmic_bytes_per_launch": req_bytes},
         "body_bytes_over_8TBps": (float(np.mean([int(b.body_len.sum()) for b in reqs])) +
                                   float(np.mean([int(b.body_len.sum()) for b in resps]))) * args.steps * world / (dev_ms / 1e3) / 8e12,

@@ -32,7 +32,8 @@ extern "C" {
 int hm_parse_request(const uint8_t* body, size_t len, uint8_t* model_out, size_t cap, size_t* model_len, int* stream,
                      int* so_present, int* iu) {
   static thread_local JsonM m;
-  m.init(K_REQ, body);
+  static thread_local uint32_t stk[kStackWords];
+  m.init(K_REQ, body, stk);
   feed(m, body, len);
   *stream = m.stream3;
   *so_present = m.so_present;
@@ -54,7 +55,8 @@ int hm_parse_request(const uint8_t* body, size_t len, uint8_t* model_out, size_t
 }
 int hm_parse_response(const uint8_t* body, size_t len, size_t* model_nonempty, int64_t usage[3]) {
   static thread_local JsonM m;
-  m.init(K_RESP, body);
+  static thread_local uint32_t stk[kStackWords];
+  m.init(K_RESP, body, stk);
   feed(m, body, len);
   *model_nonempty = m.m_rawlen > 0;
   for (int k = 0; k < 3; k++) usage[k] = m.usage[k];
@@ -62,7 +64,8 @@ int hm_parse_response(const uint8_t* body, size_t len, size_t* model_nonempty, i
 }
 int hm_parse_sse(const uint8_t* body, size_t len, int64_t usage[3]) {
   static thread_local SseM m;
-  m.init(body);
+  static thread_local uint32_t stk[kStackWords];
+  m.init(body, stk);
   feed(m, body, len);
   bool ok = m.finish((uint32_t)len);
   for (int k = 0; k < 3; k++) usage[k] = m.usage[k];

@@ -98,3 +98,46 @@ def test_sse_line_limit_64k():
     for impl in (orklib, hm):
         assert impl.parse_sse_chunk(ok)[0] == 0
         assert impl.parse_sse_chunk(bad)[0] == 1
+
+
+def _long_doc(r, kind):
+    """chat-shaped documents whose strings are long and salted with escapes / control bytes / UTF-8 at every alignment:
+    exercises the 16-byte skip path of consume()"""
+    salt = [b'\\n', b'\\"', b'\\\\', b'\\u00e9', b'\\ud83d\\ude00', b'\xc3\xa9', b'\xe4\xb8\xad', b'"', b'\\', b'\n', b'\x1f', b'\\x',
+            b'\\u12', b'\t', b'\r\n', b'\x00', b'/', b'{', b'}', b':', b',', b'[', b']']
+    def text(n):
+        out = bytearray()
+        while len(out) < n:
+            out += bytes(r.choice(b"abcdefghijklmnopqrstuvwxyz      .,'-0123456789") for _ in range(r.randint(1, 70)))
+            if r.random() < 0.5:
+                out += r.choice(salt[:7] if r.random() < 0.8 else salt)
+        return bytes(out)
+    pad = b" " * r.randint(0, 17)
+    if kind == "req":
+        return (pad + b'{"model":"qwen-7b","messages":[{"role":"user","content":"' + text(r.randint(0, 900)) + b'"},{"role":"' +
+                text(r.randint(0, 40)) + b'","content":"' + text(r.randint(0, 300)) + b'"}],"stream":true}')
+    if kind == "resp":
+        return (pad + b'{"id":"x","model":"m","choices":[{"message":{"content":"' + text(r.randint(0, 700)) +
+                b'"}}],"usage":{"prompt_tokens":12,"completion_tokens":30,"total_tokens":42}}')
+    frames = b"".join(b'data: {"choices":[{"delta":{"content":"' + text(r.randint(0, 200)) + b'"}}]}' + r.choice([b"\n\n", b"\r\n\r\n"])
+                      for _ in range(r.randint(1, 4)))
+    return frames + b'data: {"choices":[],"usage":{"prompt_tokens":1,"completion_tokens":2,"total_tokens":3}}\n\ndata: [DONE]\n\n'
+
+
+@pytest.mark.parametrize("seed", [61, 62, 63])
+def test_long_strings_bulk_path(seed):
+    import random
+    r = random.Random(seed)
+    n_ok = 0
+    for _ in range(6000):
+        b = _long_doc(r, "req")
+        a, c = orklib.parse_request_body(b), hm.parse_request_body(b)
+        assert a[0] == c[0] and (a[0] == 1 or a == c), (b, a, c)
+        n_ok += a[0] == 0
+        b = _long_doc(r, "resp")
+        a, c = orklib.parse_response_body(b), hm.parse_response_body(b)
+        assert a[0] == c[0] and (a[0] == 1 or (a[1] > 0, a[2]) == (c[1] > 0, c[2])), (b, a, c)
+        b = _long_doc(r, "sse")
+        a, c = orklib.parse_sse_chunk(b), hm.parse_sse_chunk(b)
+        assert a[0] == c[0] and (a[0] == 1 or a == c), (b, a, c)
+    assert n_ok > 500  # the corpus is not all errors
