@@ -15,6 +15,7 @@
  *   QosToQuotaRequests                                 pkg/gateway/qosconfig/types.go:45-72
  *   GetQosByToken / GetQuotaConfig / GetModelList      pkg/gateway/qosconfig/arks_impl.go:303-376
  */
+#define _POSIX_C_SOURCE 200809L
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -542,6 +543,8 @@ typedef struct {
   const arks_response_batch* pb;
   arks_response_result* pr;
   int tid, nt;
+  uint16_t* shard;           /* per item: owning thread (computed in parallel, slice per thread) */
+  pthread_barrier_t* bar;
 } mt_arg;
 static uint32_t ns_shard(const ork* o, uint32_t tok, int nt) {
   size_t l;
@@ -550,48 +553,61 @@ static uint32_t ns_shard(const ork* o, uint32_t tok, int nt) {
 }
 static void* mt_req(void* p) {
   mt_arg* a = (mt_arg*)p;
-  for (uint32_t i = 0; i < a->rb->n; i++) {
+  uint32_t n = a->rb->n;
+  uint32_t lo = (uint32_t)((uint64_t)n * a->tid / a->nt), hi = (uint32_t)((uint64_t)n * (a->tid + 1) / a->nt);
+  for (uint32_t i = lo; i < hi; i++) {
     int32_t t = find_token(a->o, a->rb->tokens + a->rb->token_off[i], a->rb->token_off[i + 1] - a->rb->token_off[i]);
-    uint32_t sh = t >= 0 ? ns_shard(a->o, (uint32_t)t, a->nt) : i % (uint32_t)a->nt;
-    if ((int)sh == a->tid) handle_request(a->o, a->rb, a->rr, i);
+    a->shard[i] = (uint16_t)(t >= 0 ? ns_shard(a->o, (uint32_t)t, a->nt) : i % (uint32_t)a->nt);
   }
+  pthread_barrier_wait(a->bar);
+  for (uint32_t i = 0; i < n; i++)
+    if (a->shard[i] == a->tid) handle_request(a->o, a->rb, a->rr, i);
   return NULL;
 }
 static void* mt_resp(void* p) {
   mt_arg* a = (mt_arg*)p;
-  for (uint32_t i = 0; i < a->pb->n; i++) {
-    uint32_t sh = ns_shard(a->o, a->o->qos_token[a->pb->qos[i]], a->nt);
-    if ((int)sh == a->tid) handle_response(a->o, a->pb, a->pr, i);
-  }
+  uint32_t n = a->pb->n;
+  uint32_t lo = (uint32_t)((uint64_t)n * a->tid / a->nt), hi = (uint32_t)((uint64_t)n * (a->tid + 1) / a->nt);
+  for (uint32_t i = lo; i < hi; i++) a->shard[i] = (uint16_t)ns_shard(a->o, a->o->qos_token[a->pb->qos[i]], a->nt);
+  pthread_barrier_wait(a->bar);
+  for (uint32_t i = 0; i < n; i++)
+    if (a->shard[i] == a->tid) handle_response(a->o, a->pb, a->pr, i);
   return NULL;
 }
-static int run_mt(void* (*fn)(void*), mt_arg* base, int nt) {
+static int run_mt(void* (*fn)(void*), mt_arg* base, int nt, uint32_t n) {
   if (nt < 1) nt = 1;
   if (nt > 256) nt = 256;
   pthread_t th[256];
   mt_arg args[256];
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, NULL, (unsigned)nt);
+  uint16_t* shard = (uint16_t*)malloc((size_t)n * 2 + 2);
   for (int t = 0; t < nt; t++) {
     args[t] = *base;
     args[t].tid = t;
     args[t].nt = nt;
+    args[t].shard = shard;
+    args[t].bar = &bar;
     pthread_create(&th[t], NULL, fn, &args[t]);
   }
   for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
+  pthread_barrier_destroy(&bar);
+  free(shard);
   return 0;
 }
 int ork_request_batch_mt(ork* o, const arks_request_batch* b, arks_request_result* r, int nt) {
   int rc = check_time(o, b->now_unix);
   if (rc) return rc;
-  mt_arg a = {o, b, r, NULL, NULL, 0, nt};
-  return run_mt(mt_req, &a, nt);
+  mt_arg a = {o, b, r, NULL, NULL, 0, nt, NULL, NULL};
+  return run_mt(mt_req, &a, nt, b->n);
 }
 int ork_response_batch_mt(ork* o, const arks_response_batch* b, arks_response_result* r, int nt) {
   int rc = check_time(o, b->now_unix);
   if (rc) return rc;
   for (uint32_t i = 0; i < b->n; i++)
     if (b->qos[i] < 0 || (uint32_t)b->qos[i] >= o->n_qos) return ARKS_E_INVALID_ARG;
-  mt_arg a = {o, NULL, NULL, b, r, 0, nt};
-  return run_mt(mt_resp, &a, nt);
+  mt_arg a = {o, NULL, NULL, b, r, 0, nt, NULL, NULL};
+  return run_mt(mt_resp, &a, nt, b->n);
 }
 
 /* ---------- quota.QuotaService surface + snapshots ---------- */
