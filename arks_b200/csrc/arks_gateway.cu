@@ -140,8 +140,8 @@ constexpr int kWin = 128;                        // bytes per body per stage
 constexpr int kUnits = kWin / 16;                // 16-byte units per body per stage
 constexpr int kStages = 3;
 constexpr int kStageBytes = 32 * kWin;           // 4 KiB per warp per stage
-constexpr int kWarpsPerBlock = 4;
-constexpr int kSmemPerBlock = kWarpsPerBlock * kStages * kStageBytes;  // 48 KiB
+constexpr int kWarpsPerBlock = 2;
+constexpr int kSmemPerBlock = kWarpsPerBlock * kStages * kStageBytes;  // 24 KiB
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes));
@@ -233,7 +233,7 @@ __device__ bool model_equals(const uint8_t* body, const JsonM& m, const uint8_t*
 // ------------------------------------------------------------------------------------------------
 // kernel 1: scan_request — A3 (body parse), A4 (GetQosByToken), A5 (GetModelList) of SURVEY.md §8a
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) scan_request_kernel(DevTables T, ReqDev B) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(DevTables T, ReqDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < B.n;
@@ -489,7 +489,7 @@ struct RespM<0> {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) scan_response_kernel(DevTables T, RespDev B) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_response_kernel(DevTables T, RespDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool live = i < B.n;

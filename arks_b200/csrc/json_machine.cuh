@@ -19,8 +19,12 @@
 
 #if defined(__CUDACC__)
 #define ARKS_HD __host__ __device__ __forceinline__
+// rare paths are kept out of line as PURE functions of plain values (never of the machine object, whose address must
+// not be taken or its fields leave the register file): keeps them from being speculated into the per-byte path
+#define ARKS_OUTLINE __host__ __device__ __noinline__
 #else
 #define ARKS_HD inline
+#define ARKS_OUTLINE inline
 #endif
 
 namespace arks {
@@ -187,14 +191,70 @@ ARKS_HD void decode_span(const uint8_t* p, uint32_t n, F&& f) {
   }
 }
 
+// ---- out-of-line slow paths (pure functions) ----
+// exact comparison of a raw (validated) key span with candidate `id`
+static ARKS_OUTLINE bool exact_verify_span(const uint8_t* p, uint32_t n, uint32_t has_esc, int id) {
+  const char* s = xkey_str(id);
+  int L = xkey_len(id);
+  if (!has_esc) {
+    if ((int)n != L) return false;
+    for (int i = 0; i < L; i++)
+      if (p[i] != (uint8_t)s[i]) return false;
+    return true;
+  }
+  int k = 0;
+  bool ok = true;
+  decode_span(p, n, [&](uint8_t b) {
+    if (k >= L || (uint8_t)s[k] != b) ok = false;
+    k++;
+  });
+  return ok && k == L;
+}
+// which exact-key candidate in [lo, hi) the span equals, or -1 (khash only valid when !has_esc)
+static ARKS_OUTLINE int exact_key_match(const uint8_t* p, uint32_t n, uint32_t has_esc, uint64_t khash, int lo, int hi) {
+  int hit = -1;
+  for (int id = lo; id < hi; id++) {
+    uint64_t want = id == 0 ? X_PROMPT : id == 1 ? X_COMPL : id == 2 ? X_TOTAL : id == 3 ? X_ERROR : id == 4 ? X_CHOICES : X_USAGE;
+    if ((has_esc || khash == want) && exact_verify_span(p, n, has_esc, id)) hit = id;
+  }
+  return hit;
+}
+// readFieldHash slow path: the hash of a key that contains a backslash (restarts from the first byte)
+static ARKS_OUTLINE uint64_t struct_key_hash_slow(const uint8_t* p, uint32_t n) {
+  uint64_t h = 0x811c9dc5ull;
+  uint32_t i = 0;
+  while (p[i] != '\\') h = fhash_step(h, p[i++]);
+  decode_span(p + i, n - i, [&](uint8_t b) { h = fhash_step(h, b); });
+  return h;
+}
+// gjson Result.Int for a Number token from its captured pieces
+static ARKS_OUTLINE int64_t captured_number_value(uint64_t nacc, uint32_t nneg, uint32_t nplain, uint32_t novf, int32_t nfrac,
+                                                   int32_t nexp, uint32_t nexpneg) {
+  if (nplain) return nneg ? (int64_t)(0 - nacc) : (int64_t)nacc;  // safeInt / parseInt agree with a wrapping parse
+  // mantissa * 10^(exp - frac) truncated toward zero; exact for the documented domain (<= 18 digits)
+  int64_t e10 = (int64_t)(nexpneg ? -nexp : nexp) - (int64_t)nfrac;
+  uint64_t m = nacc;
+  bool ovf = novf;
+  if (m == 0) return 0;
+  while (e10 < 0 && m) { m /= 10; e10++; }
+  while (e10 > 0 && !ovf) {
+    if (m > 0xFFFFFFFFFFFFFFFFull / 10) ovf = true; else m *= 10;
+    e10--;
+  }
+  if (ovf || m > 0x7FFFFFFFFFFFFFFFull) return INT64_MIN;
+  return nneg ? -(int64_t)m : (int64_t)m;
+}
+
 struct JsonM {
   // ---- configuration ----
   const uint8_t* base;  // body bytes (global memory): only slow paths and key verification read it
-  uint8_t kind;
+  // NB: 32-bit fields on purpose. Byte-sized members get packed four to a register and every access then costs
+  // PRMT/LOP3 shuffles (ncu: 12 % of scan_response_kernel's instructions were on `if (err | st == S_STOP)`).
+  uint32_t kind;
   // ---- automaton ----
-  uint8_t st, err, vm, skind, s_esc, ucnt, lit_is_key;
-  uint8_t nf, tsn, tsn_any, tsn_dot, tsn_need, ncap;  // number sub-machines
-  uint8_t l2, in_choices, ufield;
+  uint32_t st, err, vm, skind, s_esc, ucnt, lit_is_key;
+  uint32_t nf, tsn, tsn_any, tsn_dot, tsn_need, ncap;  // number sub-machines
+  uint32_t l2, in_choices, ufield;
   uint32_t lit;      // remaining literal bytes, low byte first
   uint32_t depth;
   uint32_t sstart;   // offset of the first content byte of the current string
@@ -202,20 +262,20 @@ struct JsonM {
   uint32_t cur_word; // cached word of the container-type stack (bit = 1 object, 0 array)
   // number capture (usage counters; gjson Result.Int)
   uint64_t nacc;     // wrapping decimal accumulation of all digits of the mantissa
-  uint8_t nneg, nplain, novf, sval_ok, sval_any, ncphase;
+  uint32_t nneg, nplain, novf, sval_ok, sval_any, ncphase;
   int32_t nfrac, nexp;
-  uint8_t nexpneg;
+  uint32_t nexpneg;
   // ---- outputs ----
   uint32_t m_start, m_rawlen;  // model string raw span
-  uint8_t m_esc;               // raw span contains a backslash
-  uint8_t stream3, so_present, iu3;
+  uint32_t m_esc;              // raw span contains a backslash
+  uint32_t stream3, so_present, iu3;
   int64_t usage[3];
   int64_t cand0, cand1, cand2;  // scalars, not an array: a dynamically indexed array would live in local memory
-  uint8_t cand_set, cand_nonnull;
-  uint8_t has_error_key, n_choices;
+  uint32_t cand_set, cand_nonnull;
+  uint32_t has_error_key, n_choices;
   uint32_t* stk;  // container-type stack beyond the cached word: (kMaxDepth+31)/32+1 words, owned by the caller
 
-  ARKS_HD void init(uint8_t k, const uint8_t* b, uint32_t* stack_words) {
+  ARKS_HD void init(uint32_t k, const uint8_t* b, uint32_t* stack_words) {
     base = b;
     stk = stack_words;
     kind = k;
@@ -286,7 +346,7 @@ struct JsonM {
     value_done();
   }
 
-  ARKS_HD void begin_string(uint8_t kindv, uint32_t pos) {
+  ARKS_HD void begin_string(uint32_t kindv, uint32_t pos) {
     skind = kindv;
     s_esc = 0;
     sstart = pos + 1;
@@ -297,7 +357,7 @@ struct JsonM {
     }
   }
   ARKS_HD void begin_key(uint32_t pos) {
-    uint8_t k = SK_KEY_SKIP;
+    uint32_t k = SK_KEY_SKIP;
     if (kind != K_EVT) {
       if (depth == 1 || (depth == 2 && l2 == L2_SO)) k = SK_KEY_STRUCT;
       else if (depth == 2 && l2 == L2_USAGE) k = SK_KEY_EXACT;
@@ -325,7 +385,7 @@ struct JsonM {
   }
   // value start byte (whitespace already skipped)
   ARKS_HD void begin_value(uint8_t c, uint32_t pos) {
-    uint8_t m = vm;
+    uint32_t m = vm;
     vm = VM_SKIP;
     ncap = 0;
     switch (m) {
@@ -336,7 +396,7 @@ struct JsonM {
         return;
       case VM_BOOL_STREAM:
       case VM_BOOL_IU: {  // OptionalDecoder{boolCodec}: ReadNil / ReadBool
-        uint8_t v;
+        uint32_t v;
         if (c == 'n') v = 0; else if (c == 'f') v = 1; else if (c == 't') v = 2;
         else { err = 1; return; }
         if (m == VM_BOOL_STREAM) stream3 = v; else iu3 = v;
@@ -349,12 +409,12 @@ struct JsonM {
         else err = 1;
         return;
       case VM_UINT:  // a usage counter: gjson Result.Int by JSON type
-        cand_set |= (uint8_t)(1u << ufield);
-        cand_nonnull |= (uint8_t)(1u << ufield);
+        cand_set |= 1u << ufield;
+        cand_nonnull |= 1u << ufield;
         set_cand(0);
         if (c == '"') { begin_string(SK_VALUE_UINT, pos); return; }
         if (c == 't') set_cand(1);
-        if (c == 'n') cand_nonnull &= (uint8_t)~(1u << ufield);
+        if (c == 'n') cand_nonnull &= ~(1u << ufield);
         ncap = 1;
         break;  // generic dispatch below (ncap only matters for numbers)
       case VM_USAGE:
@@ -380,14 +440,7 @@ struct JsonM {
   // ---- key dispatch at the closing quote ----
   ARKS_HD void struct_key_end(uint32_t pos) {
     uint64_t h = khash;
-    if (s_esc) {  // readFieldHash slow path: hash continues over the decoded remainder
-      // bytes before the first backslash were hashed incrementally; find it again
-      const uint8_t* p = base + sstart;
-      uint32_t n = pos - sstart, i = 0;
-      h = 0x811c9dc5ull;
-      while (p[i] != '\\') h = fhash_step(h, p[i++]);
-      decode_span(p + i, n - i, [&](uint8_t b) { h = fhash_step(h, b); });
-    }
+    if (s_esc) h = struct_key_hash_slow(base + sstart, pos - sstart);  // readFieldHash slow path
     if (depth == 1) {
       if (h == H_MODEL) vm = VM_MODEL;
       else if (kind == K_REQ && h == H_STREAM) vm = VM_BOOL_STREAM;
@@ -397,41 +450,11 @@ struct JsonM {
       if (h == H_IU) vm = VM_BOOL_IU;
     }
   }
-  ARKS_HD bool exact_verify(int id, uint32_t pos) const {
-    const char* s = xkey_str(id);
-    int L = xkey_len(id);
-    const uint8_t* p = base + sstart;
-    uint32_t n = pos - sstart;
-    if (!s_esc) {
-      if ((int)n != L) return false;
-      for (int i = 0; i < L; i++)
-        if (p[i] != (uint8_t)s[i]) return false;
-      return true;
-    }
-    int k = 0;
-    bool ok = true;
-    decode_span(p, n, [&](uint8_t b) {
-      if (k >= L || (uint8_t)s[k] != b) ok = false;
-      k++;
-    });
-    return ok && k == L;
-  }
   ARKS_HD void exact_key_end(uint32_t pos) {
-    int lo, hi;
-    if (depth == 2) { lo = 0; hi = 3; } else { lo = 3; hi = 6; }
-    int hit = -1;
-    if (!s_esc) {
-      uint64_t h = khash;
-      for (int id = lo; id < hi; id++) {
-        uint64_t want = id == 0 ? X_PROMPT : id == 1 ? X_COMPL : id == 2 ? X_TOTAL : id == 3 ? X_ERROR : id == 4 ? X_CHOICES : X_USAGE;
-        if (h == want && exact_verify(id, pos)) hit = id;
-      }
-    } else {
-      for (int id = lo; id < hi; id++)
-        if (exact_verify(id, pos)) hit = id;
-    }
+    const int lo = depth == 2 ? 0 : 3;
+    const int hit = exact_key_match(base + sstart, pos - sstart, s_esc, khash, lo, lo + 3);
     if (hit < 0) return;
-    if (hit < 3) { ufield = (uint8_t)hit; vm = VM_UINT; }
+    if (hit < 3) { ufield = (uint32_t)hit; vm = VM_UINT; }
     else if (hit == 3) has_error_key = 1;
     else if (hit == 4) vm = VM_ECHOICES;
     else vm = VM_USAGE;
@@ -461,26 +484,7 @@ struct JsonM {
   ARKS_HD void finish_number_capture() {
     if (!ncap) return;
     ncap = 0;
-    int64_t v;
-    if (nplain) {
-      v = nneg ? (int64_t)(0 - nacc) : (int64_t)nacc;  // safeInt / parseInt agree with a wrapping parse
-    } else {
-      // mantissa * 10^(exp - frac) truncated toward zero; exact for the documented domain (<= 18 digits)
-      int64_t e10 = (int64_t)(nexpneg ? -nexp : nexp) - (int64_t)nfrac;
-      uint64_t m = nacc;
-      bool ovf = novf;
-      if (m == 0) { v = 0; }
-      else {
-        while (e10 < 0 && m) { m /= 10; e10++; }
-        while (e10 > 0 && !ovf) {
-          if (m > 0xFFFFFFFFFFFFFFFFull / 10) ovf = true; else m *= 10;
-          e10--;
-        }
-        if (ovf || m > 0x7FFFFFFFFFFFFFFFull) v = INT64_MIN;
-        else v = nneg ? -(int64_t)m : (int64_t)m;
-      }
-    }
-    set_cand(v);
+    set_cand(captured_number_value(nacc, nneg, nplain, novf, nfrac, nexp, nexpneg));
   }
 
   // returns true when `c` was consumed, false when the number ended before `c` (reprocess it)
@@ -517,7 +521,7 @@ struct JsonM {
       err = 1;
       return true;
     }
-    uint8_t f = nf, nx = F_DEAD;
+    uint32_t f = nf, nx = F_DEAD;
     if (is_digit(c)) {
       if (f == F_MINUS) nx = c == '0' ? F_ZERO : F_INT;
       else if (f == F_INT) nx = F_INT;
@@ -556,7 +560,7 @@ struct JsonM {
 
   // token-level states (whitespace already excluded); if-chain ordered by frequency instead of a jump table
   ARKS_HD void step_token(uint8_t c, uint32_t pos) {
-    const uint8_t s0 = st;
+    const uint32_t s0 = st;
     if (s0 == S_AFTER) {
       if (c == ',') {
         if (top_is_object()) {
@@ -600,9 +604,9 @@ struct JsonM {
   }
 
   ARKS_HD void step(uint8_t c, uint32_t pos) {
-    for (;;) {
+    {
       if (err | (st == S_STOP)) return;
-      const uint8_t s0 = st;
+      const uint32_t s0 = st;
       if (s0 == S_STR) {
         if (c == '"') { end_string(pos); return; }
         if (c == '\\') { s_esc = 1; st = S_ESC; return; }
@@ -634,8 +638,9 @@ struct JsonM {
         return;
       }
       if (s0 == S_NUM) {
-        if (step_number(c)) return;
-        continue;  // the number ended before c: reprocess c in the new state
+        // when the number ends before c, c is reprocessed in the new state (S_AFTER or S_FINISH: both token level)
+        if (!step_number(c) && !err && !is_ws(c)) step_token(c, pos);
+        return;
       }
       if (s0 == S_ESC) {
         if (c == 'u') { ucnt = 4; st = S_U; }
@@ -687,9 +692,9 @@ struct SseM {
   uint32_t data_pos;   // bytes of event data fed so far
   uint64_t data_head;  // first 8 bytes of the event data (the [DONE] probe)
   uint32_t ev_match;   // progress of matching the event type against "thread."
-  uint8_t phase;       // 0 name, 1 just after ':', 2 value
-  uint8_t field;       // 0 other, 1 data, 2 event
-  uint8_t pending_cr, done, fail, thread_evt, ev_len_any;
+  uint32_t phase;      // 0 name, 1 just after ':', 2 value
+  uint32_t field;      // 0 other, 1 data, 2 event
+  uint32_t pending_cr, done, fail, thread_evt, ev_len_any;
 
   ARKS_HD void init(const uint8_t* base, uint32_t* stack_words) {
     ev.init(K_EVT, base, stack_words);
@@ -736,7 +741,7 @@ struct SseM {
       else if (!ev.ok_at_end() || ev.has_error_key) fail = 1;
       else {
         bool wrapped = thread_evt;
-        uint8_t nc = wrapped ? 0 : ev.n_choices;
+        uint32_t nc = wrapped ? 0 : ev.n_choices;
         if (nc == 0) {  // handle_response.go:119-123
           usage[0] = wrapped ? 0 : ev.usage[0];
           usage[1] = wrapped ? 0 : ev.usage[1];
