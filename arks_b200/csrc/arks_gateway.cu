@@ -68,6 +68,7 @@ struct DevTables {
   // state
   long long* rate;   // [4][n_qos]
   long long* quota;  // [n_quotas][3]
+  long long* qdelta; // [n_quotas][3] increments not yet folded into the other GPUs' copies, or null (single-owner keys)
   uint32_t n_qos;
 };
 
@@ -547,6 +548,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_response_kernel(D
 #pragma unroll
   for (int ty = 0; ty < 3; ty++)
     warp_agg_add(T.quota + (size_t)(qt >= 0 ? qt : 0) * 3 + ty, add[ty], counted && qt >= 0 && add[ty] != 0);
+  if (T.qdelta) {  // quota shared across GPUs: remember what the other replicas have not seen yet
+#pragma unroll
+    for (int ty = 0; ty < 3; ty++)
+      warp_agg_add(T.qdelta + (size_t)(qt >= 0 ? qt : 0) * 3 + ty, add[ty], counted && qt >= 0 && add[ty] != 0);
+  }
   if (live) {
     B.reason[i] = reason;
     B.counted[i] = counted;
@@ -554,6 +560,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_response_kernel(D
     B.usage[3 * (size_t)i + 1] = u1;
     B.usage[3 * (size_t)i + 2] = u2;
   }
+}
+
+// quota[i] += reduced[i] - own[i]; own[i] = 0  — applies what the OTHER GPUs added since the last fold
+__global__ void fold_quota_delta_kernel(long long* quota, long long* own, const long long* reduced, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    quota[i] += reduced[i] - own[i];
+    own[i] = 0;
+  }
+}
+__global__ void add_quota_kernel(long long* quota, const long long* add, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) quota[i] += add[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -579,6 +598,9 @@ struct arks_ctx {
   DevTables dt{};
   long long* d_rate = nullptr;
   long long* d_quota = nullptr;
+  long long* d_qdelta = nullptr;   // allocated when quota sharing is enabled
+  long long* d_qtmp = nullptr;
+  bool share_quota = false;
   int32_t* d_backend_weight = nullptr;
   int64_t last_win[4];
   // batch buffers: kSlots independent staging slots so several batches can be resident in HBM at once
@@ -720,6 +742,8 @@ void arks_destroy(arks_ctx* ctx) {
   free_tables(ctx);
   cudaFree(ctx->d_rate);
   cudaFree(ctx->d_quota);
+  cudaFree(ctx->d_qdelta);
+  cudaFree(ctx->d_qtmp);
   for (auto& sl : ctx->slots) {
     cudaFree(sl.d_req_bodies);
     cudaFree(sl.d_req_meta);
@@ -875,8 +899,17 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
   if ((rc = upload(ctx, v_ep_off, &d.ep_backend_off))) return rc;
   if ((rc = upload(ctx, v_bw, &d.backend_weight))) return rc;
   ctx->d_backend_weight = const_cast<int32_t*>(d.backend_weight);
+  cudaFree(ctx->d_qdelta);
+  cudaFree(ctx->d_qtmp);
+  ctx->d_qdelta = ctx->d_qtmp = nullptr;
+  if (ctx->share_quota) {
+    CK(cudaMalloc(&ctx->d_qdelta, (size_t)24 * t->n_quotas + 64));
+    CK(cudaMalloc(&ctx->d_qtmp, (size_t)24 * t->n_quotas + 64));
+    CK(cudaMemsetAsync(ctx->d_qdelta, 0, (size_t)24 * t->n_quotas + 64, ctx->stream));
+  }
   d.rate = ctx->d_rate;
   d.quota = ctx->d_quota;
+  d.qdelta = ctx->d_qdelta;
   d.n_qos = t->n_qos;
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->dt = d;
@@ -1221,10 +1254,55 @@ int arks_snapshot_rate(arks_ctx* ctx, int64_t now_unix, int64_t* counters) {
   return 0;
 }
 
-// multi-GPU quota delta folding is not wired in this build (single-owner keys only)
-int arks_take_quota_delta(arks_ctx* ctx, int64_t*) { return fail(ctx, ARKS_E_INVALID_ARG, "not built"); }
-int arks_apply_quota_delta(arks_ctx* ctx, const int64_t*) { return fail(ctx, ARKS_E_INVALID_ARG, "not built"); }
-void* arks_quota_delta_dev(arks_ctx*) { return nullptr; }
-int arks_fold_quota_delta_dev(arks_ctx* ctx, const void*, const void*) { return fail(ctx, ARKS_E_INVALID_ARG, "not built"); }
+// ---- multi-GPU: quotas shared across GPUs -------------------------------------------
+// Every GPU applies its own increments to its replica immediately and also accumulates them in a delta vector.
+// A fold epoch = sum the delta vectors over all GPUs (caller: ncclAllReduce / torch.distributed), then on every GPU
+// quota += reduced - own_delta, own_delta = 0. Between epochs a replica lags the others' increments (bounded
+// staleness, the same class of over-admission the reference's non-atomic Redis path has).
+int arks_enable_quota_sharing(arks_ctx* ctx, int on) {
+  if (!ctx) return ARKS_E_INVALID_ARG;
+  if (ctx->loaded) return fail(ctx, ARKS_E_INVALID_ARG, "enable quota sharing before arks_load_tables");
+  ctx->share_quota = on != 0;
+  return 0;
+}
+int arks_take_quota_delta(arks_ctx* ctx, int64_t* delta_out) {
+  if (!ctx || !ctx->loaded || !ctx->d_qdelta) return fail(ctx, ARKS_E_INVALID_ARG, "quota sharing is not enabled");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)3 * ctx->ht.n_quotas;
+  CK(cudaMemcpyAsync(delta_out, ctx->d_qdelta, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_qdelta, 0, n * 8, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int arks_apply_quota_delta(arks_ctx* ctx, const int64_t* remote_delta) {
+  if (!ctx || !ctx->loaded || !ctx->d_qdelta) return fail(ctx, ARKS_E_INVALID_ARG, "quota sharing is not enabled");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)3 * ctx->ht.n_quotas;
+  if (!n) return 0;
+  CK(cudaMemcpyAsync(ctx->d_qtmp, remote_delta, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  add_quota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_quota, ctx->d_qtmp, n);
+  ctx->launches += 1;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+void* arks_quota_delta_dev(arks_ctx* ctx) { return ctx ? (void*)ctx->d_qdelta : nullptr; }
+int arks_export_quota_delta_dev(arks_ctx* ctx, void* dst_dev) {
+  if (!ctx || !ctx->loaded || !ctx->d_qdelta) return fail(ctx, ARKS_E_INVALID_ARG, "quota sharing is not enabled");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst_dev, ctx->d_qdelta, (size_t)24 * ctx->ht.n_quotas, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int arks_fold_quota_delta_dev(arks_ctx* ctx, const void* reduced_dev, const void* own_dev) {
+  if (!ctx || !ctx->loaded || !ctx->d_qdelta) return fail(ctx, ARKS_E_INVALID_ARG, "quota sharing is not enabled");
+  (void)own_dev;  // the library's own delta vector is authoritative
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)3 * ctx->ht.n_quotas;
+  if (!n) return 0;
+  fold_quota_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_quota, ctx->d_qdelta, (const long long*)reduced_dev, n);
+  ctx->launches += 1;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
 
 }  // extern "C"

@@ -67,6 +67,11 @@ def lib():
         L.arks_set_quota_usage.argtypes = [vp, C.c_uint32, abi.i64p]
         L.arks_incr_quota_usage.argtypes = [vp, C.c_uint32, abi.i64p]
         L.arks_snapshot_rate.argtypes = [vp, C.c_int64, abi.i64p]
+        L.arks_enable_quota_sharing.argtypes = [vp, C.c_int]
+        L.arks_take_quota_delta.argtypes = [vp, abi.i64p]
+        L.arks_apply_quota_delta.argtypes = [vp, abi.i64p]
+        L.arks_export_quota_delta_dev.argtypes = [vp, vp]
+        L.arks_fold_quota_delta_dev.argtypes = [vp, vp, vp]
         L.arks_extract_bearer.restype = C.c_size_t
         _lib = L
     return _lib
@@ -79,16 +84,20 @@ EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/t
     "arks_fetch_request_result", "arks_stage_response_batch", "arks_run_response_batch",
     "arks_fetch_response_result", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_snapshot_quota",
     "arks_set_quota_usage", "arks_incr_quota_usage", "arks_snapshot_rate", "arks_take_quota_delta",
-    "arks_apply_quota_delta", "arks_quota_delta_dev", "arks_fold_quota_delta_dev",
+    "arks_apply_quota_delta", "arks_quota_delta_dev", "arks_fold_quota_delta_dev", "arks_enable_quota_sharing",
+    "arks_export_quota_delta_dev",
 ]
 
 
 class Gateway:
     """One per GPU. All mutable gateway state (rate windows, quota usage) lives in this object's HBM."""
 
-    def __init__(self, device: int = 0, max_batch: int = 65536, max_batch_bytes: int = 96 << 20):
+    def __init__(self, device: int = 0, max_batch: int = 65536, max_batch_bytes: int = 96 << 20,
+                 share_quota: bool = False):
         self._h = C.c_void_p()
         rc = lib().arks_create(device, max_batch, max_batch_bytes, C.byref(self._h))
+        if not rc and share_quota:
+            rc = lib().arks_enable_quota_sharing(self._h, 1)
         if rc:
             msg = lib().arks_last_error(self._h).decode() if self._h else "no CUDA device (there is no CPU fallback)"
             h, self._h = self._h, C.c_void_p()
@@ -202,6 +211,22 @@ class Gateway:
     def incr_quota_usage(self, quota: int, delta):
         u = np.ascontiguousarray(delta, np.int64)
         self._ck(lib().arks_incr_quota_usage(self._h, quota, abi.ptr(u, abi.i64p)))
+
+    # ---- quotas shared across GPUs: delta exchange (sharding.QuotaDeltaExchange drives these)
+    def take_quota_delta(self) -> np.ndarray:
+        out = np.zeros((self.tables.n_quotas, 3), np.int64)
+        self._ck(lib().arks_take_quota_delta(self._h, abi.ptr(out, abi.i64p)))
+        return out
+
+    def apply_quota_delta(self, remote):
+        u = np.ascontiguousarray(remote, np.int64)
+        self._ck(lib().arks_apply_quota_delta(self._h, abi.ptr(u, abi.i64p)))
+
+    def export_quota_delta_dev(self, dst_ptr: int):
+        self._ck(lib().arks_export_quota_delta_dev(self._h, C.c_void_p(dst_ptr)))
+
+    def fold_quota_delta_dev(self, reduced_ptr: int):
+        self._ck(lib().arks_fold_quota_delta_dev(self._h, C.c_void_p(reduced_ptr), None))
 
     # ---- reply shaping helpers (what the Go host puts on the wire; handle_request.go:208-247, util.go:40-77)
     def request_headers(self, r: RequestResult, i: int) -> dict:

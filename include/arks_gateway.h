@@ -230,13 +230,17 @@ int arks_incr_quota_usage(arks_ctx* ctx, uint32_t quota, const int64_t delta[3])
 /* rate counters of the CURRENT windows (value 0 if the stored window is older than now_unix's) */
 int arks_snapshot_rate(arks_ctx* ctx, int64_t now_unix, int64_t* counters /* 4 * n_qos */);
 
-/* multi-GPU: fold per-GPU deltas of quotas shared across GPUs. `delta_out` receives this
- * GPU's not-yet-folded deltas (3*n_quotas) and zeroes them; `arks_apply_quota_delta` adds the reduced
- * remote part. The reduction itself is the caller's (NCCL all-reduce of int64). */
+/* multi-GPU: ArksQuotas shared across GPUs. Off by default (tenant-sharded, single-owner keys, exact).
+ * When enabled (before arks_load_tables) every response-phase quota increment is also accumulated in a per-GPU delta
+ * vector (3*n_quotas int64). A fold epoch: all-reduce(sum) the delta vectors (the caller's NCCL / torch.distributed
+ * call), then on every GPU quota += reduced - own_delta and own_delta = 0. Host-buffer form: take (returns and zeroes
+ * the delta) + apply (adds the sum of the OTHER GPUs' deltas). Device form: export (D2D copy of the delta into the
+ * caller's buffer, e.g. a torch tensor handed to ncclAllReduce) + fold (reads the reduced vector from device memory). */
+int arks_enable_quota_sharing(arks_ctx* ctx, int on);
 int arks_take_quota_delta(arks_ctx* ctx, int64_t* delta_out);
 int arks_apply_quota_delta(arks_ctx* ctx, const int64_t* remote_delta);
-/* device pointer of the delta vector (3*n_quotas int64) for an in-place ncclAllReduce */
 void* arks_quota_delta_dev(arks_ctx* ctx);
+int arks_export_quota_delta_dev(arks_ctx* ctx, void* dst_dev);
 int arks_fold_quota_delta_dev(arks_ctx* ctx, const void* reduced_dev, const void* own_dev);
 
 #ifdef __cplusplus
