@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(De
       if (prev == qos) break;
       g = (g + 1) & B.gmask;
     }
-    atomicAdd(&B.gcnt[g], 1);
+    atomicAdd(&B.gcnt[g], 1);  // the table is memset to 0xff: counts start at -1
     B.gnext[i] = atomicExch(&B.ghead[g], (int32_t)i);
     slot = (int32_t)g;
   } while (0);
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
   long long cur_out = 0, lim_out = 0;
   if (slot >= 0) {
     const uint32_t rl0 = T.qos_rl_off[qos], rl1 = T.qos_rl_off[qos + 1];
-    const long long n_g = B.gcnt[slot];
+    const long long n_g = (long long)B.gcnt[slot] + 1;  // counts start at -1 (single memset of the group table)
     long long cur[4], cnt[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int r = 0; r < 4; r++) cur[r] = B.gsnap[(size_t)slot * 4 + r];  // pre-batch values (claimer's snapshot)
@@ -612,6 +612,10 @@ struct arks_ctx {
     uint8_t* h_req_meta = nullptr;     // pinned staging for the meta blocks
     uint8_t* h_resp_meta = nullptr;
     cudaEvent_t req_copied = nullptr, resp_copied = nullptr;
+    uint8_t* h_req_result = nullptr;   // pinned, per slot: asynchronous submits keep several batches in flight
+    uint8_t* h_resp_result = nullptr;
+    cudaEvent_t req_done = nullptr, resp_done = nullptr;
+    uint32_t req_fetch_n = 0, resp_fetch_n = 0;
     ReqDev rq{};
     RespDev rp{};
     uint32_t req_n = 0, resp_n = 0;
@@ -629,7 +633,6 @@ struct arks_ctx {
   int ev_n = 0;
   uint8_t* d_inter = nullptr;    // intermediates + group table
   uint8_t* d_result = nullptr;   // packed results
-  uint8_t* h_result = nullptr;   // pinned
   size_t result_cap = 0;
   uint32_t gsize = 0;
 };
@@ -726,7 +729,6 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaMalloc(&ctx->d_inter, inter));
   ctx->result_cap = align_up(n, 256) * 3 + align_up(n * 4, 256) * 3 + align_up(n * 8, 256) * 3;
   CK(cudaMalloc(&ctx->d_result, ctx->result_cap));
-  CK(cudaMallocHost(&ctx->h_result, ctx->result_cap));
   return 0;
 }
 
@@ -751,6 +753,10 @@ void arks_destroy(arks_ctx* ctx) {
     cudaFree(sl.d_resp_meta);
     cudaFreeHost(sl.h_req_meta);
     cudaFreeHost(sl.h_resp_meta);
+    cudaFreeHost(sl.h_req_result);
+    cudaFreeHost(sl.h_resp_result);
+    if (sl.req_done) cudaEventDestroy(sl.req_done);
+    if (sl.resp_done) cudaEventDestroy(sl.resp_done);
     if (sl.req_copied) cudaEventDestroy(sl.req_copied);
     if (sl.resp_copied) cudaEventDestroy(sl.resp_copied);
   }
@@ -758,7 +764,6 @@ void arks_destroy(arks_ctx* ctx) {
     if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
   cudaFree(ctx->d_inter);
   cudaFree(ctx->d_result);
-  cudaFreeHost(ctx->h_result);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -954,12 +959,16 @@ static int ensure_slot(arks_ctx* ctx, int k, bool want_req, bool want_resp) {
     CK(cudaMalloc(&sl.d_req_meta, ctx->meta_cap));
     CK(cudaMallocHost(&sl.h_req_meta, ctx->meta_cap));
     CK(cudaEventCreateWithFlags(&sl.req_copied, cudaEventDisableTiming));
+    CK(cudaMallocHost(&sl.h_req_result, ctx->result_cap));
+    CK(cudaEventCreateWithFlags(&sl.req_done, cudaEventDisableTiming));
   }
   if (want_resp && !sl.d_resp_bodies) {
     CK(cudaMalloc(&sl.d_resp_bodies, ctx->max_bytes));
     CK(cudaMalloc(&sl.d_resp_meta, ctx->meta_cap));
     CK(cudaMallocHost(&sl.h_resp_meta, ctx->meta_cap));
     CK(cudaEventCreateWithFlags(&sl.resp_copied, cudaEventDisableTiming));
+    CK(cudaMallocHost(&sl.h_resp_result, ctx->result_cap));
+    CK(cudaEventCreateWithFlags(&sl.resp_done, cudaEventDisableTiming));
   }
   return 0;
 }
@@ -1028,7 +1037,13 @@ int arks_stage_request_batch(arks_ctx* ctx, const arks_request_batch* b) {
   return 0;
 }
 
-static void carve_request(arks_ctx* ctx, ReqDev& r) {
+// offsets of the 8 result arrays inside the packed result block of a batch of n (dense: one D2H for any n)
+static void result_offsets(size_t n, size_t offs[9]) {
+  const size_t a1 = align_up(n, 16), a4 = align_up(n * 4, 16), a8 = align_up(n * 8, 16);
+  offs[0] = 0; offs[1] = a1; offs[2] = 2 * a1; offs[3] = 3 * a1; offs[4] = offs[3] + a4; offs[5] = offs[4] + a4;
+  offs[6] = offs[5] + a4; offs[7] = offs[6] + a8; offs[8] = offs[7] + a8;
+}
+static void carve_request(arks_ctx* ctx, ReqDev& r, size_t batch_n) {
   const size_t n = ctx->max_batch;
   uint8_t* p = ctx->d_inter;
   r.st_reason = p; p += align_up(n, 256);
@@ -1041,15 +1056,17 @@ static void carve_request(arks_ctx* ctx, ReqDev& r) {
   r.ghead = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);
   r.gcnt = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);
   r.gsnap = (long long*)p;
+  size_t offs[9];
+  result_offsets(batch_n, offs);
   uint8_t* q = ctx->d_result;
-  r.reason = q; q += align_up(n, 256);
-  r.detail = q; q += align_up(n, 256);
-  r.flags = q; q += align_up(n, 256);
-  r.qos = (int32_t*)q; q += align_up(n * 4, 256);
-  r.token = (int32_t*)q; q += align_up(n * 4, 256);
-  r.pick = (int32_t*)q; q += align_up(n * 4, 256);
-  r.cur_usage = (long long*)q; q += align_up(n * 8, 256);
-  r.limit_max = (long long*)q;
+  r.reason = q + offs[0];
+  r.detail = q + offs[1];
+  r.flags = q + offs[2];
+  r.qos = (int32_t*)(q + offs[3]);
+  r.token = (int32_t*)(q + offs[4]);
+  r.pick = (int32_t*)(q + offs[5]);
+  r.cur_usage = (long long*)(q + offs[6]);
+  r.limit_max = (long long*)(q + offs[7]);
 }
 
 int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
@@ -1064,14 +1081,15 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   ctx->ev_n = 0;
   if (n == 0) return 0;
   ReqDev& r = sl.rq;
-  carve_request(ctx, r);
+  carve_request(ctx, r, n);
   // batch-local group table sized to the batch (2x, power of two); the three arrays are contiguous
   uint32_t g = 64;
   while (g < 2 * n) g <<= 1;
   r.gmask = g - 1;
-  CK(cudaMemsetAsync(r.gkey, 0xff, (size_t)g * 4, ctx->stream));
-  CK(cudaMemsetAsync(r.ghead, 0xff, (size_t)g * 4, ctx->stream));
-  CK(cudaMemsetAsync(r.gcnt, 0, (size_t)g * 4, ctx->stream));
+  // gkey | ghead | gcnt are laid out back to back for THIS batch's table size: one memset(0xff) clears all three
+  r.ghead = r.gkey + g;
+  r.gcnt = r.gkey + 2 * (size_t)g;
+  CK(cudaMemsetAsync(r.gkey, 0xff, (size_t)g * 12, ctx->stream));
   const uint32_t tpb = kWarpsPerBlock * 32;
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   scan_request_kernel<<<(n + tpb - 1) / tpb, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, r);
@@ -1083,23 +1101,26 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   return 0;
 }
 
-int arks_fetch_request_result(arks_ctx* ctx, arks_request_result* out) {
-  if (!ctx || !out) return ARKS_E_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
+// enqueue the D2H of the packed result block of the batch just run in the current slot (no host wait)
+static int enqueue_request_fetch(arks_ctx* ctx) {
+  arks_ctx::Slot& sl = ctx->slots[ctx->cur];
   const size_t n = ctx->fetch_n;
+  sl.req_fetch_n = (uint32_t)n;
   if (n == 0) return 0;
-  const size_t cap = ctx->max_batch;
-  uint8_t* h = ctx->h_result;
-  const uint8_t* d = ctx->d_result;
-  size_t o1 = align_up(cap, 256), o4 = align_up(cap * 4, 256), o8 = align_up(cap * 8, 256);
-  size_t offs[8] = {0, o1, 2 * o1, 3 * o1, 3 * o1 + o4, 3 * o1 + 2 * o4, 3 * o1 + 3 * o4, 3 * o1 + 3 * o4 + o8};
-  size_t widths[8] = {1, 1, 1, 4, 4, 4, 8, 8};
-  if (n * 8 >= cap) {  // dense batch: a single copy of the whole block
-    CK(cudaMemcpyAsync(h, d, offs[7] + n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  } else {
-    for (int k = 0; k < 8; k++) CK(cudaMemcpyAsync(h + offs[k], d + offs[k], n * widths[k], cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  CK(cudaStreamSynchronize(ctx->stream));
+  size_t offs[9];
+  result_offsets(n, offs);
+  CK(cudaMemcpyAsync(sl.h_req_result, ctx->d_result, offs[8], cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(sl.req_done, ctx->stream));
+  return 0;
+}
+static int finish_request_fetch(arks_ctx* ctx, int slot, arks_request_result* out) {
+  arks_ctx::Slot& sl = ctx->slots[slot];
+  const size_t n = sl.req_fetch_n;
+  if (n == 0) return 0;
+  CK(cudaEventSynchronize(sl.req_done));
+  const uint8_t* h = sl.h_req_result;
+  size_t offs[9];
+  result_offsets(n, offs);
   memcpy(out->reason, h + offs[0], n);
   memcpy(out->detail, h + offs[1], n);
   memcpy(out->flags, h + offs[2], n);
@@ -1109,6 +1130,29 @@ int arks_fetch_request_result(arks_ctx* ctx, arks_request_result* out) {
   memcpy(out->cur_usage, h + offs[6], n * 8);
   memcpy(out->limit_max, h + offs[7], n * 8);
   return 0;
+}
+int arks_fetch_request_result(arks_ctx* ctx, arks_request_result* out) {
+  if (!ctx || !out) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_slot(ctx, ctx->cur, true, false);
+  if (rc) return rc;
+  rc = enqueue_request_fetch(ctx);
+  if (rc) return rc;
+  return finish_request_fetch(ctx, ctx->cur, out);
+}
+// asynchronous form: H2D + kernels + D2H are queued on the stream and the call returns; arks_wait_request blocks
+// until that slot's results are in `out`. Up to kSlots batches can be in flight (one per slot).
+int arks_submit_request_async(arks_ctx* ctx, const arks_request_batch* b) {
+  int rc = arks_stage_request_batch(ctx, b);
+  if (rc) return rc;
+  rc = arks_run_request_batch(ctx, b->now_unix);
+  if (rc) return rc;
+  return enqueue_request_fetch(ctx);
+}
+int arks_wait_request(arks_ctx* ctx, int slot, arks_request_result* out) {
+  if (!ctx || !out || slot < 0 || slot >= arks_ctx::kSlots) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  return finish_request_fetch(ctx, slot, out);
 }
 
 int arks_submit_request_batch(arks_ctx* ctx, const arks_request_batch* b, arks_request_result* r) {
@@ -1158,10 +1202,9 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   r.qos = (const int32_t*)(sl.d_resp_meta + o_qos);
   r.flags = sl.d_resp_meta + o_fl;
   r.n = n;
-  const size_t cap = ctx->max_batch;
   r.reason = ctx->d_result;
-  r.counted = ctx->d_result + align_up(cap, 256);
-  r.usage = (long long*)(ctx->d_result + 2 * align_up(cap, 256));
+  r.counted = ctx->d_result + align_up(n, 16);
+  r.usage = (long long*)(ctx->d_result + 2 * align_up(n, 16));
   return 0;
 }
 
@@ -1188,22 +1231,48 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
   return 0;
 }
 
-int arks_fetch_response_result(arks_ctx* ctx, arks_response_result* out) {
-  if (!ctx || !out) return ARKS_E_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
+static int enqueue_response_fetch(arks_ctx* ctx) {
+  arks_ctx::Slot& sl = ctx->slots[ctx->cur];
   const size_t n = ctx->fetch_n;
+  sl.resp_fetch_n = (uint32_t)n;
   if (n == 0) return 0;
-  const size_t cap = ctx->max_batch;
-  size_t o1 = align_up(cap, 256);
-  uint8_t* h = ctx->h_result;
-  CK(cudaMemcpyAsync(h, ctx->d_result, n, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(h + o1, ctx->d_result + o1, n, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(h + 2 * o1, ctx->d_result + 2 * o1, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t o1 = align_up(n, 16);
+  CK(cudaMemcpyAsync(sl.h_resp_result, ctx->d_result, 2 * o1 + n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(sl.resp_done, ctx->stream));
+  return 0;
+}
+static int finish_response_fetch(arks_ctx* ctx, int slot, arks_response_result* out) {
+  arks_ctx::Slot& sl = ctx->slots[slot];
+  const size_t n = sl.resp_fetch_n;
+  if (n == 0) return 0;
+  CK(cudaEventSynchronize(sl.resp_done));
+  const size_t o1 = align_up(n, 16);
+  const uint8_t* h = sl.h_resp_result;
   memcpy(out->reason, h, n);
   memcpy(out->counted, h + o1, n);
   memcpy(out->usage, h + 2 * o1, n * 24);
   return 0;
+}
+int arks_fetch_response_result(arks_ctx* ctx, arks_response_result* out) {
+  if (!ctx || !out) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_slot(ctx, ctx->cur, false, true);
+  if (rc) return rc;
+  rc = enqueue_response_fetch(ctx);
+  if (rc) return rc;
+  return finish_response_fetch(ctx, ctx->cur, out);
+}
+int arks_submit_response_async(arks_ctx* ctx, const arks_response_batch* b) {
+  int rc = arks_stage_response_batch(ctx, b);
+  if (rc) return rc;
+  rc = arks_run_response_batch(ctx, b->now_unix);
+  if (rc) return rc;
+  return enqueue_response_fetch(ctx);
+}
+int arks_wait_response(arks_ctx* ctx, int slot, arks_response_result* out) {
+  if (!ctx || !out || slot < 0 || slot >= arks_ctx::kSlots) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  return finish_response_fetch(ctx, slot, out);
 }
 
 int arks_submit_response_batch(arks_ctx* ctx, const arks_response_batch* b, arks_response_result* r) {

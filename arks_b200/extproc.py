@@ -1,0 +1,302 @@
+"""ext_proc gRPC surface of arks-gateway-plugins over the batched engine (BASELINE config 1: loopback plumbing).
+
+Host-side mirror of `Server.Process` and its four handlers (pkg/gateway/gateway.go:77-138,
+handle_request.go:33-249, handle_response.go:37-268, util.go:40-77 of the reference): one bidi stream per HTTP
+request, messages RequestHeaders -> RequestBody -> ResponseHeaders -> ResponseBody*, replies shaped like the Go
+server's. What used to be Redis/informer calls inside the handlers is one enqueue into a micro-batcher whose worker
+calls `engine.handle_request_body / handle_response_body` (the C ABI on a GPU; the parity tests plug the oracle in on
+CPU boxes because the product has no CPU path).
+
+No protoc / grpc_tools in this image: the handful of envoy.service.ext_proc.v3 / envoy.config.core.v3 messages used
+on this path are declared programmatically below with the upstream field numbers (envoy API v3 as vendored by
+go-control-plane v1.32.4; written from the published .proto layout — re-check against the .proto files before
+pointing a real Envoy at it).
+"""
+from __future__ import annotations
+
+import json
+import queue
+import threading
+import time
+from concurrent import futures
+
+import numpy as np
+from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+
+from . import abi
+from .abi import RequestBatch, ResponseBatch
+
+# --------------------------------------------------------------------------------------------------
+# protobuf messages
+# --------------------------------------------------------------------------------------------------
+_T = descriptor_pb2.FieldDescriptorProto
+
+
+def _build_messages():
+    f = descriptor_pb2.FileDescriptorProto()
+    f.name, f.package, f.syntax = "arks_extproc_subset.proto", "envoy.service.ext_proc.v3", "proto3"
+
+    def msg(name, fields, oneof=None):
+        m = f.message_type.add()
+        m.name = name
+        if oneof:
+            m.oneof_decl.add().name = oneof
+        for fname, num, ftype, tname, rep, in_oneof in fields:
+            fd = m.field.add()
+            fd.name, fd.number, fd.type = fname, num, ftype
+            fd.label = _T.LABEL_REPEATED if rep else _T.LABEL_OPTIONAL
+            if tname:
+                fd.type_name = ".envoy.service.ext_proc.v3." + tname
+            if in_oneof:
+                fd.oneof_index = 0
+        return m
+
+    M, S, B, BY, I32 = _T.TYPE_MESSAGE, _T.TYPE_STRING, _T.TYPE_BOOL, _T.TYPE_BYTES, _T.TYPE_INT32
+    # envoy.config.core.v3 (flattened into this package: only the wire format matters for the loopback)
+    msg("HeaderValue", [("key", 1, S, None, 0, 0), ("value", 2, S, None, 0, 0), ("raw_value", 3, BY, None, 0, 0)])
+    msg("HeaderMap", [("headers", 1, M, "HeaderValue", 1, 0)])
+    msg("HeaderValueOption", [("header", 1, M, "HeaderValue", 0, 0)])
+    msg("HttpStatus", [("code", 1, I32, None, 0, 0)])
+    # envoy.service.ext_proc.v3
+    msg("HttpHeaders", [("headers", 1, M, "HeaderMap", 0, 0), ("end_of_stream", 3, B, None, 0, 0)])
+    msg("HttpBody", [("body", 1, BY, None, 0, 0), ("end_of_stream", 2, B, None, 0, 0)])
+    msg("HeaderMutation", [("set_headers", 1, M, "HeaderValueOption", 1, 0), ("remove_headers", 2, S, None, 1, 0)])
+    msg("CommonResponse", [("status", 1, I32, None, 0, 0), ("header_mutation", 2, M, "HeaderMutation", 0, 0),
+                           ("clear_route_cache", 5, B, None, 0, 0)])
+    msg("HeadersResponse", [("response", 1, M, "CommonResponse", 0, 0)])
+    msg("BodyResponse", [("response", 1, M, "CommonResponse", 0, 0)])
+    msg("ImmediateResponse", [("status", 1, M, "HttpStatus", 0, 0), ("headers", 2, M, "HeaderMutation", 0, 0),
+                              ("body", 3, BY, None, 0, 0), ("details", 5, S, None, 0, 0)])
+    msg("ProcessingRequest", [("request_headers", 2, M, "HttpHeaders", 0, 1), ("response_headers", 3, M, "HttpHeaders", 0, 1),
+                              ("request_body", 4, M, "HttpBody", 0, 1), ("response_body", 5, M, "HttpBody", 0, 1)],
+        oneof="request")
+    msg("ProcessingResponse", [("request_headers", 1, M, "HeadersResponse", 0, 1),
+                               ("response_headers", 2, M, "HeadersResponse", 0, 1),
+                               ("request_body", 3, M, "BodyResponse", 0, 1), ("response_body", 4, M, "BodyResponse", 0, 1),
+                               ("immediate_response", 7, M, "ImmediateResponse", 0, 1)], oneof="response")
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(f)
+    get = lambda n: message_factory.GetMessageClass(pool.FindMessageTypeByName("envoy.service.ext_proc.v3." + n))
+    return {n: get(n) for n in ("HeaderValue", "HeaderMap", "HeaderValueOption", "HttpStatus", "HttpHeaders", "HttpBody",
+                                "HeaderMutation", "CommonResponse", "HeadersResponse", "BodyResponse",
+                                "ImmediateResponse", "ProcessingRequest", "ProcessingResponse")}
+
+
+PB = _build_messages()
+SERVICE = "envoy.service.ext_proc.v3.ExternalProcessor"
+
+# header names, pkg/gateway/types.go:24-56
+H_WENT_REQ, H_WENT_RESP = "x-went-into-req-headers", "x-went-into-resp-headers"
+
+
+def _set_headers(pairs):
+    mut = PB["HeaderMutation"]()
+    for k, v in pairs:
+        o = mut.set_headers.add()
+        o.header.key = k
+        o.header.raw_value = v if isinstance(v, bytes) else str(v).encode()
+    return mut
+
+
+def error_response(status: int, header: str, header_value, message: str):
+    """generateErrorResponse, pkg/gateway/util.go:40-77: status + x-error-* header + Content-Type + JSON body."""
+    r = PB["ProcessingResponse"]()
+    im = r.immediate_response
+    im.status.code = status
+    im.headers.CopyFrom(_set_headers([(header, header_value)]))
+    ct = im.headers.set_headers.add()
+    ct.header.key, ct.header.value = "Content-Type", "application/json"
+    im.body = json.dumps({"error": {"message": message, "code": status}}).encode()
+    return r
+
+
+# --------------------------------------------------------------------------------------------------
+# micro-batcher (the Python twin of host/go/b200/batcher.go)
+# --------------------------------------------------------------------------------------------------
+class Batcher:
+    """Stream handlers enqueue; one worker thread cuts batches by deadline (max_wait_s) or size and makes one engine
+    call per batch. `clock()` stamps each batch (the engine never reads a clock)."""
+
+    def __init__(self, engine, max_batch=4096, max_wait_s=200e-6, clock=time.time):
+        self.engine, self.max_batch, self.max_wait, self.clock = engine, max_batch, max_wait_s, clock
+        self.q: queue.Queue = queue.Queue()
+        self.batches = 0
+        self._stop = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def close(self):
+        self._stop = True
+        self.q.put(None)
+        self.t.join(timeout=5)
+
+    def request(self, body: bytes, token: bytes):
+        ev = threading.Event()
+        item = {"kind": "req", "body": body, "token": token, "ev": ev}
+        self.q.put(item)
+        ev.wait()
+        return item["out"]
+
+    def response(self, body: bytes, qos: int, flags: int):
+        ev = threading.Event()
+        item = {"kind": "resp", "body": body, "qos": qos, "flags": flags, "ev": ev}
+        self.q.put(item)
+        ev.wait()
+        return item["out"]
+
+    def _run(self):
+        while not self._stop:
+            first = self.q.get()
+            if first is None:
+                return
+            items = [first]
+            deadline = time.perf_counter() + self.max_wait
+            while len(items) < self.max_batch:
+                left = deadline - time.perf_counter()
+                if left <= 0:
+                    break
+                try:
+                    it = self.q.get(timeout=left)
+                except queue.Empty:
+                    break
+                if it is None:
+                    self._stop = True
+                    break
+                items.append(it)
+            now = int(self.clock())
+            reqs = [i for i in items if i["kind"] == "req"]
+            resps = [i for i in items if i["kind"] == "resp"]
+            if reqs:  # arrival order inside the batch == index order == the linearisation the decisions follow
+                rnd = np.random.default_rng(self.batches).integers(0, 1 << 63, len(reqs), dtype=np.uint64)
+                r = self.engine.handle_request_body(
+                    RequestBatch.from_lists([i["body"] for i in reqs], [i["token"] for i in reqs], now, pick_rand=rnd))
+                for k, i in enumerate(reqs):
+                    i["out"] = {f: v[k] for f, v in r.fields().items()}
+                    i["ev"].set()
+            if resps:
+                r = self.engine.handle_response_body(
+                    ResponseBatch.from_lists([i["body"] for i in resps], [i["qos"] for i in resps],
+                                             [i["flags"] for i in resps], now))
+                for k, i in enumerate(resps):
+                    i["out"] = {"reason": r.reason[k], "counted": r.counted[k], "usage": r.usage[k]}
+                    i["ev"].set()
+            self.batches += 1
+
+
+# --------------------------------------------------------------------------------------------------
+# the ext_proc server
+# --------------------------------------------------------------------------------------------------
+class ExtProcServer:
+    def __init__(self, engine, tables, extract_bearer, max_wait_s=200e-6, clock=time.time):
+        """engine: handle_request_body / handle_response_body; tables: arks_b200.tables.Tables (names for the routing
+        headers); extract_bearer: HandleRequestHeaders' scan (the C ABI's host function)."""
+        self.tables = tables
+        self.extract_bearer = extract_bearer
+        self.batcher = Batcher(engine, max_wait_s=max_wait_s, clock=clock)
+
+    # ---- Server.Process, gateway.go:77-138
+    def Process(self, request_iterator, context):
+        token, qos, stream, status = b"", -1, False, 0
+        buffered = bytearray()
+        for req in request_iterator:
+            kind = req.WhichOneof("request")
+            if kind == "request_headers":
+                resp, token = self.handle_request_headers(req)
+            elif kind == "request_body":
+                resp, qos, stream = self.handle_request_body(req, token)
+            elif kind == "response_headers":
+                resp, status = self.handle_response_headers(req)
+                if status == 500:  # gateway.go:115-121
+                    resp = error_response(500, "x-error-response", "true", "")
+            elif kind == "response_body":
+                if status != 200:  # gateway.go:122-126: pass the upstream error through
+                    resp = error_response(status, "x-error-response", "true", req.response_body.body.decode("latin1"))
+                else:
+                    resp = self.handle_response_body(req, qos, stream, buffered)
+            else:
+                resp = PB["ProcessingResponse"]()
+            yield resp
+
+    # ---- HandleRequestHeaders, handle_request.go:33-81
+    def handle_request_headers(self, req):
+        hs = [(h.key, h.raw_value or h.value.encode()) for h in req.request_headers.headers.headers]
+        token = self.extract_bearer(hs)
+        if not token:
+            return error_response(401, "x-error-token", "true", "no token found in request headers"), b""
+        r = PB["ProcessingResponse"]()
+        r.request_headers.response.header_mutation.CopyFrom(_set_headers([(H_WENT_REQ, "true")]))
+        r.request_headers.response.clear_route_cache = True
+        return r, token
+
+    # ---- HandleRequestBody, handle_request.go:83-249 (decision comes from the engine)
+    def handle_request_body(self, req, token):
+        out = self.batcher.request(bytes(req.request_body.body), token)
+        reason = int(out["reason"])
+        if reason != abi.R_OK:
+            status, header = abi.REASON_HTTP[reason]
+            detail = {"reason": reason, "ruleIndex": int(out["detail"]), "currentUsage": int(out["cur_usage"]),
+                      "limitMax": int(out["limit_max"]), "overLimit": reason in (abi.R_RATE_LIMIT, abi.R_QUOTA)}
+            return error_response(status, header, "true", json.dumps(detail)), -1, False
+        t = self.tables
+        q, tok = int(out["qos"]), int(out["token"])
+        r = PB["ProcessingResponse"]()
+        r.request_body.response.header_mutation.CopyFrom(_set_headers([
+            ("model", t.qos_model_name[q]), ("namespace", t.token_namespace[tok]), ("username", t.token_user[tok])]))
+        return r, q, bool(out["flags"] & 1)
+
+    # ---- HandleResponseHeaders, handle_response.go:37-78
+    def handle_response_headers(self, req):
+        pairs, status = [(H_WENT_RESP, "true")], 0
+        for h in req.response_headers.headers.headers:
+            v = h.raw_value or h.value.encode()
+            if h.key == ":status":
+                try:
+                    status = int(v)
+                except ValueError:
+                    status = 0
+            pairs.append((h.key, v))
+        r = PB["ProcessingResponse"]()
+        r.response_headers.response.header_mutation.CopyFrom(_set_headers(pairs))
+        r.response_headers.response.clear_route_cache = True
+        return r, status
+
+    # ---- HandleResponseBody, handle_response.go:80-268
+    def handle_response_body(self, req, qos, stream, buffered):
+        body, eos = bytes(req.response_body.body), req.response_body.end_of_stream
+        if stream:
+            out = self.batcher.response(body, qos, abi.RESP_STREAM)
+        else:
+            buffered += body  # requestBuffers, handle_response.go:134-155
+            if not eos:
+                r = PB["ProcessingResponse"]()
+                r.response_body.response.SetInParent()
+                return r
+            out = self.batcher.response(bytes(buffered), qos, abi.RESP_END_OF_STREAM)
+        reason = int(out["reason"])
+        if reason not in (abi.R_OK, abi.R_PENDING):
+            status, header = abi.REASON_HTTP[reason]
+            return error_response(status, header, "true", "response processing error")
+        r = PB["ProcessingResponse"]()
+        r.response_body.response.header_mutation.SetInParent()
+        return r
+
+
+def serve(server: ExtProcServer, port: int = 50052, max_workers: int = 64):
+    """grpc.NewServer() + RegisterExternalProcessorServer (gateway.go:175-192); plaintext, default options."""
+    import grpc
+    handler = grpc.method_handlers_generic_handler(SERVICE, {
+        "Process": grpc.stream_stream_rpc_method_handler(
+            server.Process, request_deserializer=PB["ProcessingRequest"].FromString,
+            response_serializer=PB["ProcessingResponse"].SerializeToString)})
+    s = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers))
+    s.add_generic_rpc_handlers((handler,))
+    bound = s.add_insecure_port(f"127.0.0.1:{port}")
+    s.start()
+    return s, bound
+
+
+def client_stub(port: int):
+    import grpc
+    ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+    return ch, ch.stream_stream(f"/{SERVICE}/Process", request_serializer=PB["ProcessingRequest"].SerializeToString,
+                                response_deserializer=PB["ProcessingResponse"].FromString)

@@ -56,6 +56,10 @@ def lib():
         L.arks_stage_response_batch.argtypes = [vp, C.POINTER(ArksResponseBatch)]
         L.arks_run_response_batch.argtypes = [vp, C.c_int64]
         L.arks_fetch_response_result.argtypes = [vp, C.POINTER(ArksResponseResult)]
+        L.arks_submit_request_async.argtypes = [vp, C.POINTER(ArksRequestBatch)]
+        L.arks_wait_request.argtypes = [vp, C.c_int, C.POINTER(ArksRequestResult)]
+        L.arks_submit_response_async.argtypes = [vp, C.POINTER(ArksResponseBatch)]
+        L.arks_wait_response.argtypes = [vp, C.c_int, C.POINTER(ArksResponseResult)]
         L.arks_select_slot.argtypes = [vp, C.c_int]
         L.arks_set_profiling.argtypes = [vp, C.c_int]
         L.arks_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
@@ -82,7 +86,8 @@ EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/t
     "arks_update_endpoint_weights", "arks_extract_bearer", "arks_submit_request_batch",
     "arks_submit_response_batch", "arks_stage_request_batch", "arks_run_request_batch",
     "arks_fetch_request_result", "arks_stage_response_batch", "arks_run_response_batch",
-    "arks_fetch_response_result", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_snapshot_quota",
+    "arks_fetch_response_result", "arks_submit_request_async", "arks_wait_request", "arks_submit_response_async",
+    "arks_wait_response", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_snapshot_quota",
     "arks_set_quota_usage", "arks_incr_quota_usage", "arks_snapshot_rate", "arks_take_quota_delta",
     "arks_apply_quota_delta", "arks_quota_delta_dev", "arks_fold_quota_delta_dev", "arks_enable_quota_sharing",
     "arks_export_quota_delta_dev",
@@ -144,6 +149,25 @@ class Gateway:
         bs, rs = b.c_struct(), r.c_struct()
         self._ck(lib().arks_submit_response_batch(self._h, C.byref(bs), C.byref(rs)))
         return r
+
+    # ---- asynchronous form: one batch in flight per staging slot
+    def submit_request_async(self, b: RequestBatch):
+        bs = b.c_struct()
+        self._ck(lib().arks_submit_request_async(self._h, C.byref(bs)))
+
+    def wait_request(self, slot: int, out: RequestResult) -> RequestResult:
+        rs = out.c_struct()
+        self._ck(lib().arks_wait_request(self._h, slot, C.byref(rs)))
+        return out
+
+    def submit_response_async(self, b: ResponseBatch):
+        bs = b.c_struct()
+        self._ck(lib().arks_submit_response_async(self._h, C.byref(bs)))
+
+    def wait_response(self, slot: int, out: ResponseResult) -> ResponseResult:
+        rs = out.c_struct()
+        self._ck(lib().arks_wait_response(self._h, slot, C.byref(rs)))
+        return out
 
     # ---- split form (bench: kernel-only timing with inputs resident in HBM)
     def stage_request(self, b: RequestBatch):

@@ -290,24 +290,51 @@ def run_b200(args):
     g.set_profiling(False)
 
     # ---- end-to-end arm: host buffers through the public API --------------------------------------
-    g.select_slot(0)
-    for i in range(args.warmup):
-        k = i % N_WAVES
-        reqs[k].now_unix, resps[k].now_unix = now, now + 1
-        g.handle_request_body(reqs[k], req_out[k])
-        g.handle_response_body(resps[k], resp_out[k])
-        now += STEP_S
+    # Every step copies that step's bodies/tokens H2D from pinned host memory and reads the decision arrays back D2H.
+    # Submits are asynchronous with two batches in flight (slot ping-pong): the host packs and queues step i+1 while
+    # the PCIe copies and kernels of step i run; results of step i are consumed before step i+2 is queued.
+    def e2e_steps(n_steps, now):
+        inflight = None
+        for i in range(n_steps):
+            k, slot = i % N_WAVES, i % 2
+            reqs[k].now_unix, resps[k].now_unix = now, now + 1
+            g.select_slot(slot)
+            g.submit_request_async(reqs[k])
+            g.submit_response_async(resps[k])
+            if inflight is not None:
+                g.wait_request(inflight[0], req_out[inflight[1]])
+                g.wait_response(inflight[0], resp_out[inflight[1]])
+            inflight = (slot, k)
+            now += STEP_S
+        g.wait_request(inflight[0], req_out[inflight[1]])
+        g.wait_response(inflight[0], resp_out[inflight[1]])
+        return now
+
+    now = e2e_steps(max(args.warmup, 2), now)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        k = i % N_WAVES
-        reqs[k].now_unix, resps[k].now_unix = now, now + 1
-        g.handle_request_body(reqs[k], req_out[k])
-        g.handle_response_body(resps[k], resp_out[k])
-        now += STEP_S
+    now = e2e_steps(args.steps, now)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()  # sampled across both timed regions (kernel-only and end-to-end)
+    assert int((req_out[0].reason == 0).sum()) > 0  # the decisions really came back
+
+    # ---- added latency of one synchronous micro-batch (submit -> decisions on the host), small batches -------------
+    latency = {}
+    if rank == 0:
+        g.select_slot(0)
+        for bs in (64, 256, 1024, 4096):
+            small = pin_batch(w.request_batch(bs, now, seed=7000 + bs, body_size=BODY, n_templates=64))
+            out_small = abi.RequestResult.empty(bs)
+            ts = []
+            for it in range(220):
+                small.now_unix = now
+                t1 = time.perf_counter()
+                g.handle_request_body(small, out_small)
+                ts.append(time.perf_counter() - t1)
+                now += STEP_S
+            ts = np.sort(np.array(ts[20:])) * 1e6
+            latency[str(bs)] = {"p50_us": float(ts[len(ts) // 2]), "p99_us": float(ts[int(len(ts) * 0.99)])}
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s * 1e3], device=f"cuda:{local}", dtype=torch.float64)
@@ -348,7 +375,10 @@ def run_b200(args):
         "config": workload_config(args, world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "req/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / args.steps, "note": "pinned host buffers, synchronous submit per phase"},
+                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "note": "pinned host buffers; asynchronous submits, two batches in flight; PCIe-bound"},
+        "latency_us": {"what": "one synchronous request micro-batch through the C ABI (H2D + 2 kernels + D2H), host wall clock",
+                       "by_batch_size": latency},
         "gpu_launches": int(launches),
         "kernels_ms": {"scan_request": float(np.mean(scan_ms)), "limit_admit": float(np.mean(admit_ms)),
                        "scan_response": float(np.mean(resp_ms))},

@@ -211,6 +211,13 @@ int arks_fetch_request_result(arks_ctx* ctx, arks_request_result* r);      /* D2
 int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b);
 int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix);
 int arks_fetch_response_result(arks_ctx* ctx, arks_response_result* r);
+/* asynchronous submits: H2D, kernels and D2H are queued on the library's stream and the call returns at once; results
+ * land in `out` when arks_wait_* returns. One batch may be in flight per slot (select the slot first), which lets the
+ * host overlap packing batch k+1 with the PCIe traffic and kernels of batch k. Batches still apply in call order. */
+int arks_submit_request_async(arks_ctx* ctx, const arks_request_batch* b);
+int arks_wait_request(arks_ctx* ctx, int slot, arks_request_result* out);
+int arks_submit_response_async(arks_ctx* ctx, const arks_response_batch* b);
+int arks_wait_response(arks_ctx* ctx, int slot, arks_response_result* out);
 /* up to 4 staging slots so that several batches can be resident in HBM at once (bench: rotate batches so the
  * timed inputs exceed L2). stage_/run_ calls act on the selected slot (default 0); fetch_ returns the last run. */
 int arks_select_slot(arks_ctx* ctx, int slot);

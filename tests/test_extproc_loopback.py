@@ -1,0 +1,135 @@
+"""BASELINE config 1: ext_proc gRPC loopback, 1 ArksToken, 1 /v1/chat/completions request.
+Pass = 4 ext_proc replies with the header sets of pkg/gateway/handle_request.go / handle_response.go and counters
+rpm=1 rpd=1 tpm=45 tpd=45, quota 25/20/45 (README.md:161-192, examples/quickstart/quickstart.yaml:56-110).
+
+CPU: the engine behind the server is the oracle (plumbing check; the product has no CPU path).
+GPU: the engine is the CUDA library through the C ABI."""
+import json
+import os
+
+import pytest
+
+import orklib
+from arks_b200 import abi, extproc, gateway
+from arks_b200.extproc import PB
+from arks_b200.tables import Tables
+
+FX = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "quickstart.json")))
+NOW = 1_700_000_000
+
+
+class OracleEngine:
+    def __init__(self, tables):
+        self.o = orklib.Oracle(tables)
+
+    def handle_request_body(self, b):
+        return self.o.request_batch(b)
+
+    def handle_response_body(self, b):
+        return self.o.response_batch(b)
+
+    def snapshot_rate(self, now):
+        return self.o.snapshot_rate(now)
+
+    def snapshot_quota(self):
+        return self.o.snapshot_quota()
+
+
+def hdrs(pairs, end=False):
+    m = PB["ProcessingRequest"]()
+    for k, v in pairs:
+        h = m.request_headers.headers.headers.add()
+        h.key, h.raw_value = k, v.encode()
+    m.request_headers.end_of_stream = end
+    return m
+
+
+def resp_hdrs(pairs):
+    m = PB["ProcessingRequest"]()
+    for k, v in pairs:
+        h = m.response_headers.headers.headers.add()
+        h.key, h.raw_value = k, v.encode()
+    return m
+
+
+def body(b, which, eos=True):
+    m = PB["ProcessingRequest"]()
+    getattr(m, which).body = b
+    getattr(m, which).end_of_stream = eos
+    return m
+
+
+def set_headers(mut):
+    return {o.header.key: (o.header.raw_value or o.header.value.encode()).decode() for o in mut.set_headers}
+
+
+def run_loopback(engine, tables):
+    import __graft_entry__ as ge
+    ge.build()  # arks_extract_bearer lives in the C ABI (pure host function)
+    srv = extproc.ExtProcServer(engine, tables, gateway.extract_bearer, clock=lambda: NOW)
+    server, port = extproc.serve(srv, port=0)
+    ch, stub = extproc.client_stub(port)
+    try:
+        msgs = [hdrs([(":method", "POST"), (":path", "/v1/chat/completions"), ("authorization", "Bearer sk-test123456"),
+                      ("content-type", "application/json")]),
+                body(FX["request_body"].encode(), "request_body"),
+                resp_hdrs([(":status", "200"), ("content-type", "application/json")]),
+                body(FX["response_body"].encode()[:100], "response_body", eos=False),
+                body(FX["response_body"].encode()[100:], "response_body", eos=True)]
+        replies = list(stub(iter(msgs)))
+        assert [r.WhichOneof("response") for r in replies] == ["request_headers", "request_body", "response_headers",
+                                                               "response_body", "response_body"]
+        assert set_headers(replies[0].request_headers.response.header_mutation) == {"x-went-into-req-headers": "true"}
+        assert replies[0].request_headers.response.clear_route_cache
+        assert set_headers(replies[1].request_body.response.header_mutation) == {
+            "model": "qwen-7b", "namespace": "default", "username": "example-token"}
+        h3 = set_headers(replies[2].response_headers.response.header_mutation)
+        assert h3 == {"x-went-into-resp-headers": "true", ":status": "200", "content-type": "application/json"}
+        assert len(replies[4].response_body.response.header_mutation.set_headers) == 0
+        assert engine.snapshot_rate(NOW)[0].tolist() == [1, 1, 45, 45]
+        assert engine.snapshot_quota()[0].tolist() == [25, 20, 45]
+
+        # no bearer -> 401 x-error-token on the headers message (handle_request.go:48-56)
+        r = list(stub(iter([hdrs([("content-type", "application/json")])])))
+        assert r[0].WhichOneof("response") == "immediate_response" and r[0].immediate_response.status.code == 401
+        assert set_headers(r[0].immediate_response.headers)["x-error-token"] == "true"
+        assert json.loads(r[0].immediate_response.body)["error"]["code"] == 401
+
+        # rpm 5: requests 2..5 pass, the 6th is 429 x-error-rate-limit with currentUsage 5 / limitMax 5
+        codes = []
+        for _ in range(5):
+            r = list(stub(iter([hdrs([("Authorization", "Bearer sk-test123456")]),
+                                body(FX["request_body"].encode(), "request_body")])))
+            codes.append(r[1].WhichOneof("response"))
+        assert codes == ["request_body"] * 4 + ["immediate_response"]
+        assert r[1].immediate_response.status.code == 429
+        assert "x-error-rate-limit" in set_headers(r[1].immediate_response.headers)
+        detail = json.loads(json.loads(r[1].immediate_response.body)["error"]["message"])
+        assert (detail["currentUsage"], detail["limitMax"], detail["ruleIndex"]) == (5, 5, 0)
+
+        # streaming request + SSE chunks
+        sse = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sse_stream.json")))
+        srv.batcher.clock = lambda: NOW + 60
+        sreq = b'{"model":"qwen-7b","stream":true,"stream_options":{"include_usage":true},"messages":[]}'
+        msgs = [hdrs([("authorization", "Bearer sk-test123456")]), body(sreq, "request_body"), resp_hdrs([(":status", "200")])]
+        msgs += [body(c.encode(), "response_body", eos=(i == len(sse["chunks"]) - 1)) for i, c in enumerate(sse["chunks"])]
+        replies = list(stub(iter(msgs)))
+        assert all(r.WhichOneof("response") != "immediate_response" for r in replies)
+        assert engine.snapshot_rate(NOW + 60)[0].tolist() == [1, 6, 45, 90]
+    finally:
+        ch.close()
+        server.stop(0)
+        srv.batcher.close()
+
+
+def test_loopback_plumbing_cpu_oracle_engine():
+    t = Tables(FX["tokens"], FX["quotas"], FX["endpoints"])
+    run_loopback(OracleEngine(t), t)
+
+
+@pytest.mark.gpu
+def test_loopback_gpu_engine():
+    t = Tables(FX["tokens"], FX["quotas"], FX["endpoints"])
+    g = gateway.Gateway(0, 4096, 8 << 20)
+    g.load_tables(t)
+    run_loopback(g, t)

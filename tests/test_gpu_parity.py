@@ -215,3 +215,23 @@ def test_full_size_wave_64k(gwmod):
         assert np.array_equal(c.usage[:, 0] + c.usage[:, 1], c.usage[:, 2])
         state_same(g, o, now + 2)
         now += 10  # NOW % 60 == 20: all three waves stay inside one minute window
+
+
+def test_async_pipelined_submits_match_serial_oracle(gwmod):
+    """Two batches in flight (slot ping-pong) still apply in call order: same results as the serial oracle."""
+    w = traffic.Workload(n_tenants=200, seed=11)
+    g, o = pair(gwmod, w.tables, 2048, 8 << 20)
+    now = NOW
+    reqs = [w.request_batch(1500, now + 3 * k, seed=600 + k, stream_frac=0.2, noise_frac=0.1) for k in range(6)]
+    outs = [abi.RequestResult.empty(r.n) for r in reqs]
+    inflight = None
+    for k, r in enumerate(reqs):
+        g.select_slot(k % 2)
+        g.submit_request_async(r)
+        if inflight is not None:
+            g.wait_request(inflight % 2, outs[inflight])
+        inflight = k
+    g.wait_request(inflight % 2, outs[inflight])
+    for k, r in enumerate(reqs):
+        same(outs[k], o.request_batch(r), f"async batch {k}")
+    state_same(g, o, now + 15)
