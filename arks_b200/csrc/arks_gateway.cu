@@ -119,6 +119,25 @@ struct RespDev {
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
+// skip-automaton tables (generated header): global copies, staged into shared memory once per block
+__device__ const uint8_t g_skip_cls[256] = ARKS_SKIP_CLASS_TABLE;
+__device__ const uint16_t g_skip_tab_j[kSkipStatesJ * kSkipClasses] = ARKS_SKIP_TABLE_J;
+__device__ const uint16_t g_skip_tab_e[kSkipStatesE * kSkipClasses] = ARKS_SKIP_TABLE_E;
+
+template <bool NEED_J, bool NEED_E>
+struct SkipSmem {
+  uint8_t cls[256];
+  uint16_t tab_j[NEED_J ? kSkipStatesJ * kSkipClasses : 2];
+  uint16_t tab_e[NEED_E ? kSkipStatesE * kSkipClasses : 2];
+  __device__ __forceinline__ SkipTables stage() {  // all threads of the block must call
+    if (!ARKS_SKIP_DFA) return SkipTables{cls, tab_j, tab_e};
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) cls[i] = g_skip_cls[i];
+    if (NEED_J) for (int i = threadIdx.x; i < kSkipStatesJ * kSkipClasses; i += blockDim.x) tab_j[i] = g_skip_tab_j[i];
+    if (NEED_E) for (int i = threadIdx.x; i < kSkipStatesE * kSkipClasses; i += blockDim.x) tab_e[i] = g_skip_tab_e[i];
+    __syncthreads();
+    return SkipTables{cls, tab_j, tab_e};
+  }
+};
 __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -242,8 +261,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(De
   const uint32_t len = live ? B.body_len[i] : 0;
 
   uint32_t stack_words[kStackWords];  // local memory, touched only beyond 32 levels of nesting
+  __shared__ SkipSmem<true, false> skip_smem;
+  const SkipTables tabs = skip_smem.stage();
   JsonM m;
-  m.init(K_REQ, body, stack_words);
+  m.init(K_REQ, body, stack_words, tabs);
   feed_tiled(m, body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
   if (!live) return;
 
@@ -443,7 +464,7 @@ template <>
 struct RespM<1> {
   JsonM ev;
   static constexpr bool sse = false;
-  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk) { ev.init(K_RESP, body, stk); }
+  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk, const SkipTables& t) { ev.init(K_RESP, body, stk, t); }
   __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { ev.step(c, pos); }
   __device__ __forceinline__ bool can_fast() const { return ev.can_fast(); }
   __device__ __forceinline__ void skip(uint32_t k, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) { ev.skip(k, o, q0, q1, q2, q3); }
@@ -455,7 +476,7 @@ template <>
 struct RespM<2> {
   SseM s;
   static constexpr bool sse = true;
-  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk) { s.init(body, stk); }
+  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk, const SkipTables& t) { s.init(body, stk, t); }
   __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { s.step(c, pos); }
   __device__ __forceinline__ bool can_fast() const { return s.can_fast(); }
   __device__ __forceinline__ void skip(uint32_t k, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) { s.skip(k, o, q0, q1, q2, q3); }
@@ -471,9 +492,9 @@ template <>
 struct RespM<0> {
   SseM s;
   bool sse;
-  __device__ __forceinline__ void init(bool is_sse, const uint8_t* body, uint32_t* stk) {
+  __device__ __forceinline__ void init(bool is_sse, const uint8_t* body, uint32_t* stk, const SkipTables& t) {
     sse = is_sse;
-    if (sse) s.init(body, stk); else s.ev.init(K_RESP, body, stk);
+    if (sse) s.init(body, stk, t); else s.ev.init(K_RESP, body, stk, t);
   }
   __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { if (sse) s.step(c, pos); else s.ev.step(c, pos); }
   __device__ __forceinline__ bool can_fast() const { return sse ? s.can_fast() : s.ev.can_fast(); }
@@ -504,9 +525,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_response_kernel(D
     uint32_t len = live && !pending ? B.body_len[i] : 0;
     qos = live ? B.qos[i] : 0;
     uint32_t stack_words[kStackWords];  // local memory, touched only beyond 32 levels of nesting
+    __shared__ SkipSmem<MODE != 2, MODE != 1> skip_smem;
+    const SkipTables tabs = skip_smem.stage();
     RespM<MODE> rm;
     const bool is_sse = MODE == 2 || (MODE == 0 && (fl & ARKS_RESP_STREAM));
-    rm.init(is_sse, body, stack_words);
+    rm.init(is_sse, body, stack_words, tabs);
     feed_tiled(rm, body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
     if (live) {
       if (is_sse) {  // handle_response.go:113-133, every chunk in isolation

@@ -17,6 +17,16 @@
 #pragma once
 #include <stdint.h>
 
+#include "skip_dfa_tables.h"
+
+// Table-driven validation of skipped subtrees (skip_step). Measured on B200 (round 1): it cuts executed instructions
+// by 15 % but every byte then pays two DEPENDENT shared-memory lookups, and with ~3.4 resident warps per scheduler
+// (64k bodies / 148 SMs) the scan kernels are latency-bound, not issue-bound: scan_response went 157 -> 212 us.
+// Kept behind this switch for batches large enough to hide that latency.
+#ifndef ARKS_SKIP_DFA
+#define ARKS_SKIP_DFA 0
+#endif
+
 #if defined(__CUDACC__)
 #define ARKS_HD __host__ __device__ __forceinline__
 // rare paths are kept out of line as PURE functions of plain values (never of the machine object, whose address must
@@ -33,7 +43,7 @@ enum : uint8_t { K_REQ = 0, K_RESP = 1, K_EVT = 2 };
 
 // token-level states first (they share the whitespace skip), then in-token states
 enum : uint8_t {
-  S_TOP = 0,       // jsoniter readObjectStart at depth 0 (K_REQ / K_RESP)
+  S_TOP = 0,       // (unused: the top-level value is S_VAL with vm == VM_TOP, jsoniter readObjectStart)
   S_VAL,           // expecting a value
   S_ARR_FIRST,     // after '[': value or ']'
   S_OBJ_FIRST,     // after '{' (ReadObjectCB / encoding/json): key string or '}'
@@ -51,12 +61,13 @@ enum : uint8_t {
   S_LIT,           // rest of null / true / false
   S_NUM,           // number
   S_STOP,          // jsoniter Unmarshal met a NUL byte after the value: accepted, rest ignored
+  S_SKIP,          // inside a skipped subtree: the table-driven automaton of skip_dfa_tables.h runs (state in `ss`)
 };
 
 // what a string is (decides what happens at its closing quote)
 enum : uint8_t { SK_VALUE_SKIP = 0, SK_VALUE_MODEL, SK_VALUE_UINT, SK_KEY_SKIP, SK_KEY_STRUCT, SK_KEY_EXACT };
 // how the next value is consumed
-enum : uint8_t { VM_SKIP = 0, VM_MODEL, VM_BOOL_STREAM, VM_BOOL_IU, VM_SO, VM_USAGE, VM_UINT, VM_ECHOICES };
+enum : uint8_t { VM_SKIP = 0, VM_MODEL, VM_BOOL_STREAM, VM_BOOL_IU, VM_SO, VM_USAGE, VM_UINT, VM_ECHOICES, VM_TOP };
 // special object one level below the top-level object
 enum : uint8_t { L2_NONE = 0, L2_SO, L2_USAGE };
 // RFC 8259 number DFA
@@ -191,6 +202,20 @@ ARKS_HD void decode_span(const uint8_t* p, uint32_t n, F&& f) {
   }
 }
 
+// The skip automaton's tables (generated, tools/gen_skip_dfa.py). On the device the kernels copy them into shared
+// memory once per block and hand the machines pointers to that copy; the host build points at the arrays directly.
+struct SkipTables {
+  const uint8_t* cls;     // 256: byte -> class
+  const uint16_t* tab_j;  // kSkipStatesJ x kSkipClasses, jsoniter strict Skip()
+  const uint16_t* tab_e;  // kSkipStatesE x kSkipClasses, encoding/json checkValid
+};
+#if !defined(__CUDA_ARCH__)
+static const uint8_t kSkipClsHost[256] = ARKS_SKIP_CLASS_TABLE;
+static const uint16_t kSkipTabJHost[kSkipStatesJ * kSkipClasses] = ARKS_SKIP_TABLE_J;
+static const uint16_t kSkipTabEHost[kSkipStatesE * kSkipClasses] = ARKS_SKIP_TABLE_E;
+inline SkipTables host_skip_tables() { return SkipTables{kSkipClsHost, kSkipTabJHost, kSkipTabEHost}; }
+#endif
+
 // ---- out-of-line slow paths (pure functions) ----
 // exact comparison of a raw (validated) key span with candidate `id`
 static ARKS_OUTLINE bool exact_verify_span(const uint8_t* p, uint32_t n, uint32_t has_esc, int id) {
@@ -273,15 +298,21 @@ struct JsonM {
   int64_t cand0, cand1, cand2;  // scalars, not an array: a dynamically indexed array would live in local memory
   uint32_t cand_set, cand_nonnull;
   uint32_t has_error_key, n_choices;
+  uint32_t ss, skip_base;   // skip automaton state; depth of the subtree's root container
+  const uint16_t* skt;      // skip table of this document's flavor
+  const uint8_t* skc;       // byte -> class
   uint32_t* stk;  // container-type stack beyond the cached word: (kMaxDepth+31)/32+1 words, owned by the caller
 
-  ARKS_HD void init(uint32_t k, const uint8_t* b, uint32_t* stack_words) {
+  ARKS_HD void init(uint32_t k, const uint8_t* b, uint32_t* stack_words, const SkipTables& tabs) {
     base = b;
     stk = stack_words;
+    skc = tabs.cls;
+    skt = k == K_EVT ? tabs.tab_e : tabs.tab_j;
+    ss = 0; skip_base = 0;
     kind = k;
-    st = (k == K_EVT) ? S_VAL : S_TOP;
+    st = S_VAL;
     err = 0;
-    vm = VM_SKIP;
+    vm = (k == K_EVT) ? VM_SKIP : VM_TOP;  // jsoniter's struct decoder only accepts '{' or null at the top
     skind = 0; s_esc = 0; ucnt = 0; lit_is_key = 0;
     nf = 0; tsn = 0; tsn_any = 0; tsn_dot = 0; tsn_need = 0; ncap = 0;
     l2 = L2_NONE; in_choices = 0; ufield = 255;
@@ -298,7 +329,8 @@ struct JsonM {
   ARKS_HD void reset_event() {
     const uint8_t* b = base;
     uint32_t* sw = stk;
-    init(K_EVT, b, sw);
+    const SkipTables t{skc, skt, skt};
+    init(K_EVT, b, sw, t);
   }
 
   ARKS_HD bool top_is_object() const { return (cur_word >> ((depth - 1) & 31)) & 1u; }
@@ -383,58 +415,87 @@ struct JsonM {
       nplain = 1; novf = 0; nfrac = 0; nexp = 0; nexpneg = 0; ncphase = 0;
     }
   }
-  // value start byte (whitespace already skipped)
+  // value start byte (whitespace already skipped). Decide first, act once: every primitive (begin_string, push, ...)
+  // is inlined exactly once, which keeps the per-byte loop small enough for the instruction cache.
   ARKS_HD void begin_value(uint8_t c, uint32_t pos) {
-    uint32_t m = vm;
+    enum : uint32_t { W_ERR = 0, W_STR, W_LIT, W_NUM, W_OBJ, W_ARR };
+    const uint32_t m = vm;
     vm = VM_SKIP;
     ncap = 0;
-    switch (m) {
-      case VM_MODEL:  // stringCodec -> ReadString: string or null
-        if (c == '"') begin_string(SK_VALUE_MODEL, pos);
-        else if (c == 'n') { m_start = 0; m_rawlen = 0; m_esc = 0; begin_literal(c, false); }
-        else err = 1;
-        return;
-      case VM_BOOL_STREAM:
-      case VM_BOOL_IU: {  // OptionalDecoder{boolCodec}: ReadNil / ReadBool
-        uint32_t v;
-        if (c == 'n') v = 0; else if (c == 'f') v = 1; else if (c == 't') v = 2;
-        else { err = 1; return; }
-        if (m == VM_BOOL_STREAM) stream3 = v; else iu3 = v;
-        begin_literal(c, false);
-        return;
-      }
-      case VM_SO:  // OptionalDecoder{oneFieldStructDecoder}
-        if (c == 'n') { so_present = 0; iu3 = 0; begin_literal(c, false); }
-        else if (c == '{') { so_present = 1; push(true); l2 = L2_SO; st = S_STRUCT_FIRST; }
-        else err = 1;
-        return;
-      case VM_UINT:  // a usage counter: gjson Result.Int by JSON type
+    // Iterator.Skip / encoding/json value
+    uint32_t what = c == '"' ? W_STR : (c == 'n' || c == 't' || c == 'f') ? W_LIT : (c == '-' || is_digit(c)) ? W_NUM
+                    : c == '[' ? W_ARR : c == '{' ? W_OBJ : W_ERR;
+    uint32_t skv = SK_VALUE_SKIP, next = S_OBJ_FIRST, l2v = 0xffu, choices = 0;
+    if (m != VM_SKIP) {
+      if (m == VM_MODEL) {  // stringCodec -> ReadString: string or null
+        skv = SK_VALUE_MODEL;
+        if (c == 'n') { m_start = 0; m_rawlen = 0; m_esc = 0; }
+        else if (c != '"') what = W_ERR;
+      } else if (m == VM_BOOL_STREAM || m == VM_BOOL_IU) {  // OptionalDecoder{boolCodec}: ReadNil / ReadBool
+        const uint32_t v = c == 'n' ? 0u : c == 'f' ? 1u : 2u;
+        if (what != W_LIT) what = W_ERR;
+        else if (m == VM_BOOL_STREAM) stream3 = v; else iu3 = v;
+      } else if (m == VM_SO) {  // OptionalDecoder{oneFieldStructDecoder}
+        if (c == 'n') { so_present = 0; iu3 = 0; }
+        else if (c == '{') { so_present = 1; next = S_STRUCT_FIRST; l2v = L2_SO; }
+        else what = W_ERR;
+      } else if (m == VM_TOP) {  // readObjectStart: '{' or null
+        if (c == '{') next = S_STRUCT_FIRST;
+        else if (c != 'n') what = W_ERR;
+      } else if (m == VM_UINT) {  // a usage counter: gjson Result.Int by JSON type
         cand_set |= 1u << ufield;
         cand_nonnull |= 1u << ufield;
-        set_cand(0);
-        if (c == '"') { begin_string(SK_VALUE_UINT, pos); return; }
-        if (c == 't') set_cand(1);
+        set_cand(c == 't' ? 1 : 0);
         if (c == 'n') cand_nonnull &= ~(1u << ufield);
-        ncap = 1;
-        break;  // generic dispatch below (ncap only matters for numbers)
-      case VM_USAGE:
+        skv = SK_VALUE_UINT;
+        ncap = 1;  // only matters for numbers
+      } else if (m == VM_USAGE) {
         if (kind == K_EVT) { usage[0] = usage[1] = usage[2] = 0; }  // Map(): the last "usage" member wins outright
         cand_set = 0; cand_nonnull = 0;
-        if (c == '{') { push(true); l2 = L2_USAGE; st = S_OBJ_FIRST; return; }
-        break;
-      case VM_ECHOICES:
+        if (c == '{') l2v = L2_USAGE;
+      } else {  // VM_ECHOICES
         n_choices = 0;
-        if (c == '[') { push(false); in_choices = 1; st = S_ARR_FIRST; return; }
-        break;
-      default: break;
+        choices = c == '[';
+      }
     }
-    // Iterator.Skip / encoding/json value
-    if (c == '"') begin_string(SK_VALUE_SKIP, pos);
-    else if (c == 'n' || c == 't' || c == 'f') begin_literal(c, false);
-    else if (c == '-' || is_digit(c)) begin_number(c);
-    else if (c == '[') { push(false); st = S_ARR_FIRST; }
-    else if (c == '{') { push(true); st = S_OBJ_FIRST; }
-    else err = 1;
+    if (what == W_STR) begin_string(skv, pos);
+    else if (what == W_LIT) begin_literal(c, false);
+    else if (what == W_NUM) begin_number(c);
+    else if (what == W_ERR) err = 1;
+    else {
+      const bool generic = ARKS_SKIP_DFA && depth >= 1 && l2v == 0xffu && next == S_OBJ_FIRST && !choices;
+      push(what == W_OBJ);
+      if (generic) {  // nothing below this container is ever read: validate it with the table-driven automaton
+        st = S_SKIP;
+        ss = what == W_OBJ ? K_OBJ_FIRST : K_ARR_FIRST;
+        skip_base = depth;
+      } else if (what == W_OBJ) { if (l2v != 0xffu) l2 = l2v; st = next; }
+      else { in_choices = choices ? 1u : in_choices; st = S_ARR_FIRST; }
+    }
+  }
+
+  // one byte inside a skipped subtree: two table lookups; stack work only on brackets and at the end of scalars
+  ARKS_HD void skip_step(uint8_t c) {
+    for (;;) {
+      const uint32_t t = skt[ss * kSkipClasses + skc[c]];
+      const uint32_t f = t >> 6;
+      ss = t & 63u;
+      if (f == SKF_NONE) return;
+      if (f == SKF_ERR) { err = 1; return; }
+      if (f == SKF_PUSHO || f == SKF_PUSHA) { push(f == SKF_PUSHO); return; }
+      if (f == SKF_DONE || f == SKF_DONE_RE) {
+        ss = top_is_object() ? K_AFTER_OBJ : K_AFTER_ARR;
+        if (f == SKF_DONE) return;
+        continue;  // the number ended before this byte: dispatch the byte again in the after-value state
+      }
+      // pop
+      if (top_is_object() != (f == SKF_POPO)) { err = 1; return; }
+      const bool root = depth == skip_base;
+      pop();
+      if (root) value_done();  // back to the semantic machine
+      else ss = top_is_object() ? K_AFTER_OBJ : K_AFTER_ARR;
+      return;
+    }
   }
 
   // ---- key dispatch at the closing quote ----
@@ -558,58 +619,15 @@ struct JsonM {
     return true;
   }
 
-  // token-level states (whitespace already excluded); if-chain ordered by frequency instead of a jump table
-  ARKS_HD void step_token(uint8_t c, uint32_t pos) {
-    const uint32_t s0 = st;
-    if (s0 == S_AFTER) {
-      if (c == ',') {
-        if (top_is_object()) {
-          bool strct = kind != K_EVT && (depth == 1 || (depth == 2 && l2 == L2_SO));
-          st = strct ? S_STRUCT_KEY : S_OBJ_KEY;
-        } else {
-          st = S_VAL;
-        }
-        vm = VM_SKIP;
-      } else if (c == '}' || c == ']') {
-        close_container(c);
-      } else {
-        err = 1;
-      }
-    } else if (s0 == S_COLON) {
-      if (c == ':') st = S_VAL; else err = 1;
-    } else if (s0 == S_VAL) {
-      begin_value(c, pos);
-    } else if (s0 == S_OBJ_KEY) {
-      if (c == '"') begin_key(pos);
-      else if (c == 'n' && kind != K_EVT) begin_literal(c, true);  // ReadString() accepts null as a key
-      else err = 1;
-    } else if (s0 == S_STRUCT_KEY) {
-      if (c == '"') begin_key(pos); else err = 1;
-    } else if (s0 == S_OBJ_FIRST || s0 == S_STRUCT_FIRST) {
-      if (c == '"') begin_key(pos);
-      else if (c == '}') close_container(c);
-      else err = 1;
-    } else if (s0 == S_ARR_FIRST) {
-      if (c == ']') { close_container(c); return; }
-      if (in_choices && depth == 2) n_choices = 1;
-      begin_value(c, pos);
-    } else if (s0 == S_TOP) {  // readObjectStart
-      if (c == '{') { push(true); st = S_STRUCT_FIRST; }
-      else if (c == 'n') begin_literal(c, false);
-      else err = 1;
-    } else {  // S_FINISH
-      if (c == 0 && kind != K_EVT) st = S_STOP;  // frozenConfig.Unmarshal: `if c == 0` also matches a NUL byte
-      else err = 1;
-    }
-  }
-
   ARKS_HD void step(uint8_t c, uint32_t pos) {
-    {
-      if (err | (st == S_STOP)) return;
-      const uint32_t s0 = st;
+    if (err | (st == S_STOP)) return;
+    uint32_t s0 = st;
+    if (s0 == S_SKIP) { skip_step(c); return; }
+    // ---- inside a token
+    if (s0 == S_STR || s0 == S_STR_E) {
+      if (c == '"') { end_string(pos); return; }
+      if (c == '\\') { s_esc = 1; st = S_ESC; return; }
       if (s0 == S_STR) {
-        if (c == '"') { end_string(pos); return; }
-        if (c == '\\') { s_esc = 1; st = S_ESC; return; }
         if (c < 0x20 && skind != SK_KEY_STRUCT) { err = 1; return; }  // readFieldHash has no such check
         if (skind >= SK_KEY_STRUCT) khash = skind == SK_KEY_STRUCT ? fhash_step(khash, c) : xhash_step(khash, c);
         else if (skind == SK_VALUE_UINT) {
@@ -617,18 +635,12 @@ struct JsonM {
           else if (is_digit(c)) { nacc = nacc * 10 + (uint64_t)(c - '0'); sval_any = 1; }
           else sval_ok = 0;
         }
-        return;
+      } else if (c < 0x20 && kind == K_EVT) {
+        err = 1;  // jsoniter's slow path does not check control characters, encoding/json does
       }
-      if (s0 < S_TOKEN_STATES) {
-        if (!is_ws(c)) step_token(c, pos);
-        return;
-      }
-      if (s0 == S_STR_E) {
-        if (c == '"') { end_string(pos); return; }
-        if (c == '\\') { st = S_ESC; return; }
-        if (c < 0x20 && kind == K_EVT) err = 1;  // jsoniter's slow path does not check control characters
-        return;
-      }
+      return;
+    }
+    if (s0 > S_TOKEN_STATES) {
       if (s0 == S_LIT) {
         if (c != (uint8_t)(lit & 0xff)) { err = 1; return; }
         lit >>= 8;
@@ -637,22 +649,63 @@ struct JsonM {
         }
         return;
       }
-      if (s0 == S_NUM) {
-        // when the number ends before c, c is reprocessed in the new state (S_AFTER or S_FINISH: both token level)
-        if (!step_number(c) && !err && !is_ws(c)) step_token(c, pos);
-        return;
-      }
       if (s0 == S_ESC) {
         if (c == 'u') { ucnt = 4; st = S_U; }
         else if (c == '"' || c == '\\' || c == '/' || c == 'b' || c == 'f' || c == 'n' || c == 'r' || c == 't') st = S_STR_E;
         else err = 1;
         return;
       }
-      // S_U
-      if (hexval(c) < 0) { err = 1; return; }
-      if (--ucnt == 0) st = S_STR_E;
-      return;
+      if (s0 == S_U) {
+        if (hexval(c) < 0) { err = 1; return; }
+        if (--ucnt == 0) st = S_STR_E;
+        return;
+      }
+      // S_NUM: when the number ends before c, c is handled below in the new (token-level) state
+      if (step_number(c) || err) return;
+      s0 = st;
     }
+    // ---- between tokens: decide, then act once
+    if (is_ws(c)) return;
+    enum : uint32_t { A_ERR = 0, A_NONE, A_VALUE, A_KEY, A_CLOSE };
+    uint32_t act = A_ERR;
+    if (s0 == S_AFTER) {
+      if (c == ',') {
+        if (top_is_object()) {
+          const bool strct = kind != K_EVT && (depth == 1 || (depth == 2 && l2 == L2_SO));
+          st = strct ? S_STRUCT_KEY : S_OBJ_KEY;
+        } else {
+          st = S_VAL;
+        }
+        vm = VM_SKIP;
+        act = A_NONE;
+      } else if (c == '}' || c == ']') {
+        act = A_CLOSE;
+      }
+    } else if (s0 == S_COLON) {
+      if (c == ':') { st = S_VAL; act = A_NONE; }
+    } else if (s0 == S_VAL) {
+      act = A_VALUE;
+    } else if (s0 == S_OBJ_KEY) {
+      if (c == '"') act = A_KEY;
+      else if (c == 'n' && kind != K_EVT) { begin_literal(c, true); act = A_NONE; }  // ReadString() accepts null as a key
+    } else if (s0 == S_STRUCT_KEY) {
+      if (c == '"') act = A_KEY;
+    } else if (s0 == S_OBJ_FIRST || s0 == S_STRUCT_FIRST) {
+      if (c == '"') act = A_KEY;
+      else if (c == '}') act = A_CLOSE;
+    } else if (s0 == S_ARR_FIRST) {
+      if (c == ']') act = A_CLOSE;
+      else {
+        if (in_choices && depth == 2) n_choices = 1;
+        act = A_VALUE;
+      }
+    } else {  // S_FINISH
+      if (c == 0 && kind != K_EVT) { st = S_STOP; act = A_NONE; }  // frozenConfig.Unmarshal: `if c == 0` also matches a NUL byte
+    }
+    if (act == A_VALUE) begin_value(c, pos);
+    else if (act == A_KEY) begin_key(pos);
+    else if (act == A_CLOSE) close_container(c);
+    else if (act == A_ERR) err = 1;
   }
 
   // end of input: jsoniter Unmarshal / encoding/json checkValid verdict
@@ -662,7 +715,9 @@ struct JsonM {
   // True while the machine sits inside a string whose ordinary bytes need no per-byte action: the caller may then
   // skip ahead to the next '"', '\\' or byte < 0x20 without calling step() (skipped bytes are never control bytes,
   // so the jsoniter "control character before the first backslash" rule cannot be missed).
-  ARKS_HD bool can_fast() const { return (st == S_STR_E) | ((st == S_STR) & (skind != SK_VALUE_UINT)); }
+  ARKS_HD bool can_fast() const {
+    return (st == S_SKIP) ? (ss < 4u) : ((st == S_STR_E) | ((st == S_STR) & (skind != SK_VALUE_UINT)));
+  }
   // the `n` ordinary bytes being skipped are bytes [o, o+n) of the unit (q0..q3): hashed keys still need them
   ARKS_HD void skip(uint32_t n, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
     if ((st == S_STR) & (skind >= SK_KEY_STRUCT)) {
@@ -696,8 +751,8 @@ struct SseM {
   uint32_t field;      // 0 other, 1 data, 2 event
   uint32_t pending_cr, done, fail, thread_evt, ev_len_any;
 
-  ARKS_HD void init(const uint8_t* base, uint32_t* stack_words) {
-    ev.init(K_EVT, base, stack_words);
+  ARKS_HD void init(const uint8_t* base, uint32_t* stack_words, const SkipTables& tabs) {
+    ev.init(K_EVT, base, stack_words, tabs);
     usage[0] = usage[1] = usage[2] = 0;
     line_len = 0; name_len = 0; name_acc = 0; data_pos = 0; data_head = 0; ev_match = 0;
     phase = 0; field = 0; pending_cr = 0; done = 0; fail = 0; thread_evt = 0; ev_len_any = 0;
@@ -830,6 +885,9 @@ ARKS_HD uint32_t first_set(uint32_t x) {
 #endif
 }
 
+// NB (measured, round 1): every loop iteration lets EVERY lane make progress — lanes inside strings swallow up to a unit,
+// lanes between tokens step one byte. A variant that stepped token bytes in a tight inner loop was 40 % slower: the
+// string lanes of the warp sat masked off while the token lanes looped, so the two kinds of work stopped overlapping.
 // Feed bytes [pos, lim) of one body to machine `m`; `load(u)` returns 16-byte unit u of the body (bytes past the
 // body's end may hold anything). Advances pos. Inside strings, units without a special byte are skipped whole.
 template <class M, class L>

@@ -33,7 +33,7 @@ int hm_parse_request(const uint8_t* body, size_t len, uint8_t* model_out, size_t
                      int* so_present, int* iu) {
   static thread_local JsonM m;
   static thread_local uint32_t stk[kStackWords];
-  m.init(K_REQ, body, stk);
+  m.init(K_REQ, body, stk, host_skip_tables());
   feed(m, body, len);
   *stream = m.stream3;
   *so_present = m.so_present;
@@ -56,7 +56,7 @@ int hm_parse_request(const uint8_t* body, size_t len, uint8_t* model_out, size_t
 int hm_parse_response(const uint8_t* body, size_t len, size_t* model_nonempty, int64_t usage[3]) {
   static thread_local JsonM m;
   static thread_local uint32_t stk[kStackWords];
-  m.init(K_RESP, body, stk);
+  m.init(K_RESP, body, stk, host_skip_tables());
   feed(m, body, len);
   *model_nonempty = m.m_rawlen > 0;
   for (int k = 0; k < 3; k++) usage[k] = m.usage[k];
@@ -65,7 +65,7 @@ int hm_parse_response(const uint8_t* body, size_t len, size_t* model_nonempty, i
 int hm_parse_sse(const uint8_t* body, size_t len, int64_t usage[3]) {
   static thread_local SseM m;
   static thread_local uint32_t stk[kStackWords];
-  m.init(body, stk);
+  m.init(body, stk, host_skip_tables());
   feed(m, body, len);
   bool ok = m.finish((uint32_t)len);
   for (int k = 0; k < 3; k++) usage[k] = m.usage[k];
