@@ -93,6 +93,10 @@ struct ReqDev {  // request batch, device resident
   int32_t* gcnt;
   long long* gsnap;  // [slot][4] window counters as they were before this batch
   uint32_t gmask;
+  // hot groups (> kHotGroup arrivals in this batch): arrival ranks computed by rank_hot_groups_kernel
+  int32_t* hot_n;     // [1]
+  int32_t* hot_list;  // slots
+  int32_t* hotrank;   // per request, valid for members of hot groups
   // results (SoA, packed in one buffer for a single D2H)
   uint8_t* reason;
   uint8_t* detail;
@@ -334,21 +338,82 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(De
 // are admitted (k = 0 if any token-type entry or quota item is already over) and every later one is denied by
 // the first entry that is over with `k` admissions applied.
 // ------------------------------------------------------------------------------------------------
+constexpr int kHotGroup = 256;  // above this many arrivals of one qos entry in a batch the member list is not walked
+
+// kernel 2a: collect the slots of hot groups (BASELINE config 4: Zipf-hot tenants send thousands of requests per wave)
+__global__ void find_hot_groups_kernel(ReqDev B) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s <= B.gmask && B.gcnt[s] + 1 > kHotGroup) B.hot_list[atomicAdd(B.hot_n, 1)] = (int32_t)s;
+}
+// kernel 2b: one block per hot group sweeps the slot column once, front to back, and hands every member its arrival
+// rank (members with a smaller request index). n / 256 coalesced tile loads per hot group.
+__global__ void __launch_bounds__(256) rank_hot_groups_kernel(ReqDev B) {
+  __shared__ uint32_t warp_tot[8];
+  const int n_hot = *B.hot_n;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int h = blockIdx.x; h < n_hot; h += gridDim.x) {
+    const int32_t s = B.hot_list[h];
+    uint32_t base = 0;
+    for (uint32_t t0 = 0; t0 < B.n; t0 += 1024) {  // 4 consecutive entries per thread, 1024 per tile
+      const uint32_t j = t0 + threadIdx.x * 4;
+      int4 v = make_int4(-1, -1, -1, -1);
+      if (j + 3 < B.n) v = *reinterpret_cast<const int4*>(B.gslot + j);
+      else {
+        if (j < B.n) v.x = B.gslot[j];
+        if (j + 1 < B.n) v.y = B.gslot[j + 1];
+        if (j + 2 < B.n) v.z = B.gslot[j + 2];
+      }
+      const uint32_t f0 = v.x == s, f1 = v.y == s, f2 = v.z == s, f3 = v.w == s;
+      const uint32_t mine = f0 + f1 + f2 + f3;
+      uint32_t incl = mine;  // inclusive scan of the per-thread counts over the warp
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+      }
+      if (lane == 31) warp_tot[wid] = incl;
+      __syncthreads();
+      uint32_t before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        const uint32_t t = warp_tot[w];
+        before += (uint32_t)w < wid ? t : 0;
+        total += t;
+      }
+      uint32_t r = base + before + incl - mine;
+      if (f0) B.hotrank[j] = (int32_t)r;
+      r += f0;
+      if (f1) B.hotrank[j + 1] = (int32_t)r;
+      r += f1;
+      if (f2) B.hotrank[j + 2] = (int32_t)r;
+      r += f2;
+      if (f3) B.hotrank[j + 3] = (int32_t)r;
+      base += total;
+      __syncthreads();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B.n) return;
-  uint8_t reason = B.st_reason[i], detail = 0;
-  int32_t qos = B.st_qos[i], slot = B.gslot[i], pick = -1;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < B.n;
+  uint8_t reason = live ? B.st_reason[i] : 0, detail = 0;
+  const int32_t qos = live ? B.st_qos[i] : -1, slot = live ? B.gslot[i] : -1;
+  int32_t pick = -1;
   long long cur_out = 0, lim_out = 0;
+  // ---- phase A (per lane): how many arrivals of my group can be admitted
+  uint32_t rl0 = 0, rl1 = 0;
+  long long n_g = 0, k = 0, cur[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0}, q_cur = 0, q_lim = 0;
+  int32_t qt = ARKS_QUOTA_NONE;
+  int quota_fail = -1;  // first over-limit item
   if (slot >= 0) {
-    const uint32_t rl0 = T.qos_rl_off[qos], rl1 = T.qos_rl_off[qos + 1];
-    const long long n_g = (long long)B.gcnt[slot] + 1;  // counts start at -1 (single memset of the group table)
-    long long cur[4], cnt[4] = {0, 0, 0, 0};
+    rl0 = T.qos_rl_off[qos];
+    rl1 = T.qos_rl_off[qos + 1];
+    n_g = (long long)B.gcnt[slot] + 1;  // counts start at -1 (single memset of the group table)
 #pragma unroll
     for (int r = 0; r < 4; r++) cur[r] = B.gsnap[(size_t)slot * 4 + r];  // pre-batch values (claimer's snapshot)
     for (uint32_t j = rl0; j < rl1; j++) cnt[T.rl_rule[j]]++;
-    // how many of this group can be admitted
-    long long k = n_g;
+    k = n_g;
     for (uint32_t j = rl0; j < rl1; j++) {
       int rule = T.rl_rule[j];
       long long lim = T.rl_value[j];
@@ -360,9 +425,7 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
         k = 0;  // "token is not caculated in request": cur + 0 > limit (check.go:124-126)
       }
     }
-    int32_t qt = T.qos_quota[qos];
-    int quota_fail = -1;  // first over-limit item
-    long long q_cur = 0, q_lim = 0;
+    qt = T.qos_quota[qos];
     if (qt >= 0) {
       uint32_t i0 = T.quota_item_off[qt], i1 = T.quota_item_off[qt + 1];
       for (uint32_t j = i0; j < i1; j++) {
@@ -371,26 +434,17 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
       }
     }
     if (qt == ARKS_QUOTA_MISSING || quota_fail >= 0) k = 0;
-    // arrival rank inside the group, only needed when the group straddles its limit
-    bool admitted;
-    if (k >= n_g) admitted = true;
-    else if (k <= 0) admitted = false;
-    else {
-      // the group straddles its limit: arrival rank = members with a smaller index
-      long long rank = 0;
-      if (n_g <= 256) {
-        for (int32_t j = B.ghead[slot]; j >= 0; j = B.gnext[j]) rank += (uint32_t)j < i;
-      } else {  // hot tenant: dense scan of the slot column, 4 entries per load
-        const int4* gs = reinterpret_cast<const int4*>(B.gslot);
-        uint32_t j4 = 0;
-        for (; (j4 + 1) * 4 <= i; j4++) {
-          int4 v = gs[j4];
-          rank += (v.x == slot) + (v.y == slot) + (v.z == slot) + (v.w == slot);
-        }
-        for (uint32_t j = j4 * 4; j < i; j++) rank += B.gslot[j] == slot;
-      }
-      admitted = rank < k;
-    }
+  }
+  // ---- phase B: arrival rank inside the group, only for groups that straddle their limit (0 < k < n_g)
+  const bool need_rank = slot >= 0 && k > 0 && k < n_g;
+  long long rank = 0;
+  if (need_rank && n_g <= kHotGroup) {  // small group: walk its member list
+    for (int32_t j = B.ghead[slot]; j >= 0; j = B.gnext[j]) rank += (uint32_t)j < i;
+  }
+  if (need_rank && n_g > kHotGroup) rank = B.hotrank[i];  // hot tenant: ranked by rank_hot_groups_kernel
+  // ---- phase C: decision, commit, pick
+  if (slot >= 0) {
+    const bool admitted = k >= n_g ? true : k <= 0 ? false : rank < k;
     if (!admitted) {
       // first entry over its limit once k admissions are applied (RateLimitResponse.currentUsage = cur + k*cnt)
       reason = 0;
@@ -428,6 +482,7 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
       }
     }
   }
+  if (!live) return;
   B.reason[i] = reason;
   B.detail[i] = detail;
   B.flags[i] = reason == ARKS_R_OK ? (B.st_flags[i] & 0x7f) : 0;
@@ -748,7 +803,8 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   uint32_t g = 64;
   while (g < 2 * n) g <<= 1;
   ctx->gsize = g;
-  size_t inter = align_up(n, 256) * 2 + align_up(n * 4, 256) * 4 + align_up((size_t)g * 4, 256) * 3 + (size_t)g * 32 + 256;
+  size_t inter = align_up(n, 256) * 2 + align_up(n * 4, 256) * 5 + align_up((size_t)g * 4, 256) * 3 + (size_t)g * 32 + 1024 +
+                 align_up((n / kHotGroup + 2) * 4, 256);
   CK(cudaMalloc(&ctx->d_inter, inter));
   ctx->result_cap = align_up(n, 256) * 3 + align_up(n * 4, 256) * 3 + align_up(n * 8, 256) * 3;
   CK(cudaMalloc(&ctx->d_result, ctx->result_cap));
@@ -1078,7 +1134,10 @@ static void carve_request(arks_ctx* ctx, ReqDev& r, size_t batch_n) {
   r.gkey = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);   // gkey and ghead are contiguous: one memset(-1)
   r.ghead = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);
   r.gcnt = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);
-  r.gsnap = (long long*)p;
+  r.gsnap = (long long*)p; p += align_up((size_t)ctx->gsize * 32, 256);
+  r.hot_n = (int32_t*)p; p += 256;
+  r.hot_list = (int32_t*)p; p += align_up((n / kHotGroup + 2) * 4, 256);
+  r.hotrank = (int32_t*)p;
   size_t offs[9];
   result_offsets(batch_n, offs);
   uint8_t* q = ctx->d_result;
@@ -1117,6 +1176,12 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   scan_request_kernel<<<(n + tpb - 1) / tpb, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, r);
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (n > (uint32_t)kHotGroup) {  // a group can only be hot if the batch is larger than the threshold
+    CK(cudaMemsetAsync(r.hot_n, 0, 4, ctx->stream));
+    find_hot_groups_kernel<<<(g + 255) / 256, 256, 0, ctx->stream>>>(r);
+    rank_hot_groups_kernel<<<296, 256, 0, ctx->stream>>>(r);
+    ctx->launches += 2;
+  }
   limit_admit_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dt, r);
   if (ctx->prof) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_n = 3; }
   ctx->launches += 2;

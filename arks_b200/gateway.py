@@ -23,7 +23,7 @@ from .abi import (ArksRequestBatch, ArksRequestResult, ArksResponseBatch, ArksRe
                   RequestBatch, RequestResult, ResponseBatch, ResponseResult)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libarksgw.so")
+LIB_PATH = os.environ.get("ARKS_LIB", os.path.join(_HERE, "libarksgw.so"))  # ARKS_LIB: A/B builds in experiments
 _lib = None
 
 
