@@ -29,7 +29,7 @@
 #include <vector>
 
 #include "../../include/arks_gateway.h"
-#include "json_machine.cuh"
+#include "json_engine.cuh"
 
 using namespace arks;
 
@@ -123,25 +123,30 @@ struct RespDev {
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
-// skip-automaton tables (generated header): global copies, staged into shared memory once per block
-__device__ const uint8_t g_skip_cls[256] = ARKS_SKIP_CLASS_TABLE;
-__device__ const uint16_t g_skip_tab_j[kSkipStatesJ * kSkipClasses] = ARKS_SKIP_TABLE_J;
-__device__ const uint16_t g_skip_tab_e[kSkipStatesE * kSkipClasses] = ARKS_SKIP_TABLE_E;
+// automaton tables (generated header json_tables.h): global copies, staged into shared memory once per block so that the
+// two lookups per byte are LDS (32 banks, random 2-byte reads) instead of constant-cache replays
+__device__ const uint8_t g_json_cls[256] = ARKS_JSON_CLASS_TABLE;
+__device__ const uint8_t g_json_tab_j[kJsonStatesJ * kJsonClasses] = ARKS_JSON_TABLE_J;
+__device__ const uint8_t g_json_tab_e[kJsonStatesE * kJsonClasses] = ARKS_JSON_TABLE_E;
 
 template <bool NEED_J, bool NEED_E>
-struct SkipSmem {
+struct JsonSmem {
+  uint8_t tab_j[NEED_J ? kJsonStatesJ * kJsonClasses : 4];
+  uint8_t tab_e[NEED_E ? kJsonStatesE * kJsonClasses : 4];
   uint8_t cls[256];
-  uint16_t tab_j[NEED_J ? kSkipStatesJ * kSkipClasses : 2];
-  uint16_t tab_e[NEED_E ? kSkipStatesE * kSkipClasses : 2];
-  __device__ __forceinline__ SkipTables stage() {  // all threads of the block must call
-    if (!ARKS_SKIP_DFA) return SkipTables{cls, tab_j, tab_e};
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) cls[i] = g_skip_cls[i];
-    if (NEED_J) for (int i = threadIdx.x; i < kSkipStatesJ * kSkipClasses; i += blockDim.x) tab_j[i] = g_skip_tab_j[i];
-    if (NEED_E) for (int i = threadIdx.x; i < kSkipStatesE * kSkipClasses; i += blockDim.x) tab_e[i] = g_skip_tab_e[i];
+  __device__ __forceinline__ JsonTables stage() {  // all threads of the block must call
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) reinterpret_cast<uint32_t*>(cls)[i] = reinterpret_cast<const uint32_t*>(g_json_cls)[i];
+    if (NEED_J)
+      for (int i = threadIdx.x; i < kJsonStatesJ * kJsonClasses / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(tab_j)[i] = reinterpret_cast<const uint32_t*>(g_json_tab_j)[i];
+    if (NEED_E)
+      for (int i = threadIdx.x; i < kJsonStatesE * kJsonClasses / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(tab_e)[i] = reinterpret_cast<const uint32_t*>(g_json_tab_e)[i];
     __syncthreads();
-    return SkipTables{cls, tab_j, tab_e};
+    return JsonTables{cls, tab_j, tab_e};
   }
 };
+
 __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -217,7 +222,7 @@ __device__ __forceinline__ void feed_tiled(M& m, const uint8_t* body, uint32_t l
     const uint8_t* st = warp_smem + (w % kStages) * kStageBytes;
     const uint32_t wbeg = w * kWin;
     uint32_t lim = min(len, wbeg + kWin);
-    consume(m, pos, lim, [&](uint32_t u) {
+    consume_t(m, pos, lim, [&](uint32_t u) {
       const uint32_t ul = u - (wbeg >> 4);
       const uint4 v = *reinterpret_cast<const uint4*>(st + (ul * 32 + ((lane + ul) & 31)) * 16);
       Unit16 q;
@@ -237,7 +242,7 @@ __device__ __forceinline__ unsigned long long fnv1a64(const uint8_t* p, uint32_t
 }
 
 // compare the (possibly escaped) model span of a body with a pool string
-__device__ bool model_equals(const uint8_t* body, const JsonM& m, const uint8_t* name, uint32_t nlen) {
+__device__ bool model_equals(const uint8_t* body, const JsonCold& m, const uint8_t* name, uint32_t nlen) {
   const uint8_t* p = body + m.m_start;
   if (!m.m_esc) {
     if (m.m_rawlen != nlen) return false;
@@ -265,10 +270,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(De
   const uint32_t len = live ? B.body_len[i] : 0;
 
   uint32_t stack_words[kStackWords];  // local memory, touched only beyond 32 levels of nesting
-  __shared__ SkipSmem<true, false> skip_smem;
-  const SkipTables tabs = skip_smem.stage();
-  JsonM m;
-  m.init(K_REQ, body, stack_words, tabs);
+  __shared__ __align__(16) JsonSmem<true, false> json_smem;
+  const JsonTables tabs = json_smem.stage();
+  JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
+  JsonT m;
+  m.init(K_REQ, body, stack_words, &cold, tabs);
   feed_tiled(m, body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
   if (!live) return;
 
@@ -276,7 +282,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(De
   int32_t tok = -1, qos = -1, slot = -1;
   do {
     if (!m.ok_at_end()) { reason = ARKS_R_REQUEST_BODY; break; }           // handle_request.go:97-104
-    if (m.m_rawlen == 0) { reason = ARKS_R_NO_MODEL; break; }              // :106-115
+    if (cold.m_rawlen == 0) { reason = ARKS_R_NO_MODEL; break; }              // :106-115
     // GetQosByToken: first ArksToken whose spec.token equals the bearer      arks_impl.go:303-338
     const uint8_t* tk = B.tokens + B.token_off[i];
     uint32_t tkl = B.token_off[i + 1] - B.token_off[i];
@@ -295,11 +301,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(De
     }
     if (tok < 0) { reason = ARKS_R_TOKEN_NOT_FOUND; break; }
     for (uint32_t q = T.tok_qos_off[tok]; q < T.tok_qos_off[tok + 1]; q++)
-      if (model_equals(body, m, T.pool + T.qos_model_off[q], T.qos_model_len[q])) { qos = (int32_t)q; break; }
+      if (model_equals(body, cold, T.pool + T.qos_model_off[q], T.qos_model_len[q])) { qos = (int32_t)q; break; }
     if (qos < 0) { reason = ARKS_R_MODEL_NOT_IN_TOKEN; break; }
     if (T.qos_ep[qos] < 0) { reason = ARKS_R_NO_MODEL_BACKENDS; break; }   // handle_request.go:137-154
-    bool stream = m.stream3 == 2;
-    if (stream && !(m.so_present && m.iu3 == 2)) { reason = ARKS_R_STREAM_OPTIONS; break; }  // :156-171
+    bool stream = cold.stream3 == 2;
+    if (stream && !(cold.so_present && cold.iu3 == 2)) { reason = ARKS_R_STREAM_OPTIONS; break; }  // :156-171
     flags = stream ? 1 : 0;
     // register in the batch-local group table: qos -> dense slot, arrival count, member list
     uint32_t g = ((uint32_t)qos * 2654435761u) & B.gmask;
@@ -517,26 +523,26 @@ template <int MODE>
 struct RespM;
 template <>
 struct RespM<1> {
-  JsonM ev;
+  JsonT ev;
   static constexpr bool sse = false;
-  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk, const SkipTables& t) { ev.init(K_RESP, body, stk, t); }
+  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk, JsonCold* cold, const JsonTables& t) { ev.init(K_RESP, body, stk, cold, t); }
   __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { ev.step(c, pos); }
   __device__ __forceinline__ bool can_fast() const { return ev.can_fast(); }
   __device__ __forceinline__ void skip(uint32_t k, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) { ev.skip(k, o, q0, q1, q2, q3); }
   __device__ __forceinline__ bool dead() const { return ev.dead(); }
-  __device__ __forceinline__ JsonM& json() { return ev; }
+  __device__ __forceinline__ JsonT& json() { return ev; }
   __device__ __forceinline__ bool finish(uint32_t, long long&, long long&, long long&) { return true; }
 };
 template <>
 struct RespM<2> {
-  SseM s;
+  SseT s;
   static constexpr bool sse = true;
-  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk, const SkipTables& t) { s.init(body, stk, t); }
+  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk, JsonCold* cold, const JsonTables& t) { s.init(body, stk, cold, t); }
   __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { s.step(c, pos); }
   __device__ __forceinline__ bool can_fast() const { return s.can_fast(); }
   __device__ __forceinline__ void skip(uint32_t k, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) { s.skip(k, o, q0, q1, q2, q3); }
   __device__ __forceinline__ bool dead() const { return s.dead(); }
-  __device__ __forceinline__ JsonM& json() { return s.ev; }
+  __device__ __forceinline__ JsonT& json() { return s.ev; }
   __device__ __forceinline__ bool finish(uint32_t len, long long& u0, long long& u1, long long& u2) {
     bool ok = s.finish(len);
     u0 = s.usage[0]; u1 = s.usage[1]; u2 = s.usage[2];
@@ -545,11 +551,11 @@ struct RespM<2> {
 };
 template <>
 struct RespM<0> {
-  SseM s;
+  SseT s;
   bool sse;
-  __device__ __forceinline__ void init(bool is_sse, const uint8_t* body, uint32_t* stk, const SkipTables& t) {
+  __device__ __forceinline__ void init(bool is_sse, const uint8_t* body, uint32_t* stk, JsonCold* cold, const JsonTables& t) {
     sse = is_sse;
-    if (sse) s.init(body, stk, t); else s.ev.init(K_RESP, body, stk, t);
+    if (sse) s.init(body, stk, cold, t); else s.ev.init(K_RESP, body, stk, cold, t);
   }
   __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { if (sse) s.step(c, pos); else s.ev.step(c, pos); }
   __device__ __forceinline__ bool can_fast() const { return sse ? s.can_fast() : s.ev.can_fast(); }
@@ -557,7 +563,7 @@ struct RespM<0> {
     if (sse) s.skip(k, o, q0, q1, q2, q3); else s.ev.skip(k, o, q0, q1, q2, q3);
   }
   __device__ __forceinline__ bool dead() const { return sse ? s.dead() : s.ev.dead(); }
-  __device__ __forceinline__ JsonM& json() { return s.ev; }
+  __device__ __forceinline__ JsonT& json() { return s.ev; }
   __device__ __forceinline__ bool finish(uint32_t len, long long& u0, long long& u1, long long& u2) {
     bool ok = s.finish(len);
     u0 = s.usage[0]; u1 = s.usage[1]; u2 = s.usage[2];
@@ -580,11 +586,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_response_kernel(D
     uint32_t len = live && !pending ? B.body_len[i] : 0;
     qos = live ? B.qos[i] : 0;
     uint32_t stack_words[kStackWords];  // local memory, touched only beyond 32 levels of nesting
-    __shared__ SkipSmem<MODE != 2, MODE != 1> skip_smem;
-    const SkipTables tabs = skip_smem.stage();
+    __shared__ __align__(16) JsonSmem<MODE != 2, MODE != 1> json_smem;
+    const JsonTables tabs = json_smem.stage();
     RespM<MODE> rm;
     const bool is_sse = MODE == 2 || (MODE == 0 && (fl & ARKS_RESP_STREAM));
-    rm.init(is_sse, body, stack_words, tabs);
+    JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
+    rm.init(is_sse, body, stack_words, &cold, tabs);
     feed_tiled(rm, body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
     if (live) {
       if (is_sse) {  // handle_response.go:113-133, every chunk in isolation
@@ -592,10 +599,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_response_kernel(D
       } else if (pending) {
         reason = ARKS_R_PENDING;
       } else {
-        JsonM& ev = rm.json();
+        JsonT& ev = rm.json();
         if (!ev.ok_at_end()) reason = ARKS_R_RESPONSE_UNMARSHAL;  // :157-166
-        else if (ev.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // :167-181
-        else { u0 = ev.usage[0]; u1 = ev.usage[1]; u2 = ev.usage[2]; }
+        else if (cold.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // :167-181
+        else { u0 = cold.usage[0]; u1 = cold.usage[1]; u2 = cold.usage[2]; }
       }
       if (reason != ARKS_R_OK) { u0 = u1 = u2 = 0; }
       counted = reason == ARKS_R_OK && u2 != 0;  // :186

@@ -74,7 +74,7 @@ enum : uint8_t { L2_NONE = 0, L2_SO, L2_USAGE };
 enum : uint8_t { F_MINUS = 0, F_ZERO, F_INT, F_DOT, F_FRAC, F_E, F_ESIGN, F_EXP, F_DEAD };
 
 static constexpr uint32_t kMaxDepth = 10000;  // jsoniter maxDepth == encoding/json maxNestingDepth
-static constexpr uint32_t kStackWords = (kMaxDepth + 31) / 32 + 1;
+static constexpr uint32_t kStackWords = (kMaxDepth + 15) / 16 + 1;  // 2 bits per level (json_engine.cuh)
 
 // jsoniter readFieldHash: int64 0x811c9dc5, ^= lower(byte), *= 0x1000193 (iter_object.go)
 ARKS_HD constexpr uint64_t fhash_step(uint64_t h, uint8_t b) {

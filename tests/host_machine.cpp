@@ -3,7 +3,7 @@
 #include <stddef.h>
 #include <string.h>
 
-#include "../arks_b200/csrc/json_machine.cuh"
+#include "../arks_b200/csrc/json_engine.cuh"
 
 using namespace arks;
 
@@ -14,7 +14,7 @@ static void feed(M& m, const uint8_t* body, size_t len) {
   // exercise window boundaries like the tiled kernels do: consume in 128-byte windows
   for (uint32_t wbeg = 0; wbeg < len; wbeg += 128) {
     uint32_t lim = (uint32_t)(len < wbeg + 128 ? len : wbeg + 128);
-    consume(m, pos, lim, [&](uint32_t u) {
+    consume_t(m, pos, lim, [&](uint32_t u) {
       Unit16 q;
       uint8_t tmp[16] = {0};
       size_t o = (size_t)u * 16;
@@ -31,41 +31,44 @@ static void feed(M& m, const uint8_t* body, size_t len) {
 extern "C" {
 int hm_parse_request(const uint8_t* body, size_t len, uint8_t* model_out, size_t cap, size_t* model_len, int* stream,
                      int* so_present, int* iu) {
-  static thread_local JsonM m;
+  static thread_local JsonT m;
   static thread_local uint32_t stk[kStackWords];
-  m.init(K_REQ, body, stk, host_skip_tables());
+  static thread_local JsonCold cold;
+  m.init(K_REQ, body, stk, &cold, host_json_tables());
   feed(m, body, len);
-  *stream = m.stream3;
-  *so_present = m.so_present;
-  *iu = m.iu3;
+  *stream = cold.stream3;
+  *so_present = cold.so_present;
+  *iu = cold.iu3;
   size_t k = 0;
   if (m.ok_at_end()) {
-    if (m.m_esc)
-      decode_span(body + m.m_start, m.m_rawlen, [&](uint8_t b) {
+    if (cold.m_esc)
+      decode_span(body + cold.m_start, cold.m_rawlen, [&](uint8_t b) {
         if (k < cap) model_out[k] = b;
         k++;
       });
     else {
-      k = m.m_rawlen;
-      memcpy(model_out, body + m.m_start, k < cap ? k : cap);
+      k = cold.m_rawlen;
+      memcpy(model_out, body + cold.m_start, k < cap ? k : cap);
     }
   }
   *model_len = k;
   return m.ok_at_end() ? 0 : 1;
 }
 int hm_parse_response(const uint8_t* body, size_t len, size_t* model_nonempty, int64_t usage[3]) {
-  static thread_local JsonM m;
+  static thread_local JsonT m;
   static thread_local uint32_t stk[kStackWords];
-  m.init(K_RESP, body, stk, host_skip_tables());
+  static thread_local JsonCold cold;
+  m.init(K_RESP, body, stk, &cold, host_json_tables());
   feed(m, body, len);
-  *model_nonempty = m.m_rawlen > 0;
-  for (int k = 0; k < 3; k++) usage[k] = m.usage[k];
+  *model_nonempty = cold.m_rawlen > 0;
+  for (int k = 0; k < 3; k++) usage[k] = cold.usage[k];
   return m.ok_at_end() ? 0 : 1;
 }
 int hm_parse_sse(const uint8_t* body, size_t len, int64_t usage[3]) {
-  static thread_local SseM m;
+  static thread_local SseT m;
   static thread_local uint32_t stk[kStackWords];
-  m.init(body, stk, host_skip_tables());
+  static thread_local JsonCold cold;
+  m.init(body, stk, &cold, host_json_tables());
   feed(m, body, len);
   bool ok = m.finish((uint32_t)len);
   for (int k = 0; k < 3; k++) usage[k] = m.usage[k];

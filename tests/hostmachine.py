@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "host_machine.cpp")
-HDR = os.path.join(ROOT, "arks_b200", "csrc", "json_machine.cuh")
+HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_machine.cuh", "json_engine.cuh", "json_tables.h")]
 OUT = os.path.join(ROOT, "tests", "_build", "libhost_machine.so")
 _lib = None
 
@@ -16,7 +16,7 @@ def lib():
     global _lib
     if _lib is None:
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        if not os.path.exists(OUT) or max(os.path.getmtime(SRC), os.path.getmtime(HDR)) > os.path.getmtime(OUT):
+        if not os.path.exists(OUT) or max([os.path.getmtime(SRC)] + [os.path.getmtime(h) for h in HDRS]) > os.path.getmtime(OUT):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", OUT, SRC])
         L = C.CDLL(OUT)
         i64p = C.POINTER(C.c_int64)
