@@ -165,6 +165,7 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
 // one body's line hit 8 different bank groups, and the 32 lanes that each read "their" unit u hit 32 different
 // slots of one 512-byte row, so both sides of the transpose are conflict-free when lanes move in lock step.
 // ------------------------------------------------------------------------------------------------
+constexpr int kHotGroup = 256;  // above this many arrivals of one qos entry in a batch the member list is not walked
 constexpr int kWin = 128;                        // bytes per body per stage
 constexpr int kUnits = kWin / 16;                // 16-byte units per body per stage
 constexpr int kStages = 3;
@@ -196,43 +197,52 @@ __device__ __forceinline__ void issue_window(uint32_t stage_smem, const uint8_t*
 }
 static_assert(kUnits == 8, "issue_window assumes 8 units per window");
 
-// Parse 32 bodies, one per lane, with machine `m` (lanes beyond the batch pass len == 0).
-template <class M>
-__device__ __forceinline__ void feed_tiled(M& m, const uint8_t* body, uint32_t len, uint8_t* warp_smem) {
+// Stream bytes [0, end) of 32 spans, one per lane (lanes without work pass end == 0), through a STAGES-deep window
+// pipeline; per_window(wbeg, lim, load) is called by every lane for every window, load(u) returns the lane's own
+// 16-byte unit u (absolute unit index inside the span).
+template <int STAGES, class F>
+__device__ __forceinline__ void tiled_windows(const uint8_t* body, uint32_t end, uint8_t* warp_smem, F&& per_window) {
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t padded = (len + 15u) & ~15u;
-  uint32_t maxlen = len;
+  const uint32_t padded = (end + 15u) & ~15u;
+  uint32_t maxlen = end;
 #pragma unroll
   for (int d = 16; d; d >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, d));
   const uint32_t n_win = (maxlen + kWin - 1) / kWin;
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(warp_smem);
   // prologue
 #pragma unroll
-  for (int s = 0; s < kStages - 1; s++) {
+  for (int s = 0; s < STAGES - 1; s++) {
     if ((uint32_t)s < n_win) issue_window(smem0 + s * kStageBytes, body, padded, s, lane);
     cp_async_commit();
   }
-  uint32_t pos = 0;
   for (uint32_t w = 0; w < n_win; w++) {
-    const uint32_t nxt = w + kStages - 1;
-    if (nxt < n_win) issue_window(smem0 + (nxt % kStages) * kStageBytes, body, padded, nxt, lane);
+    const uint32_t nxt = w + STAGES - 1;
+    if (nxt < n_win) issue_window(smem0 + (nxt % STAGES) * kStageBytes, body, padded, nxt, lane);
     cp_async_commit();
-    cp_async_wait<kStages - 1>();
+    cp_async_wait<STAGES - 1>();
     __syncwarp();
-    const uint8_t* st = warp_smem + (w % kStages) * kStageBytes;
+    const uint8_t* st = warp_smem + (w % STAGES) * kStageBytes;
     const uint32_t wbeg = w * kWin;
-    uint32_t lim = min(len, wbeg + kWin);
-    consume_t(m, pos, lim, [&](uint32_t u) {
+    per_window(wbeg, min(end, wbeg + kWin), [&](uint32_t u) {
       const uint32_t ul = u - (wbeg >> 4);
       const uint4 v = *reinterpret_cast<const uint4*>(st + (ul * 32 + ((lane + ul) & 31)) * 16);
       Unit16 q;
       q.w[0] = v.x; q.w[1] = v.y; q.w[2] = v.z; q.w[3] = v.w;
       return q;
     });
-    if (m.dead()) pos = len;  // nothing further can change the verdict
     __syncwarp();  // everyone is done with this stage before it is overwritten
   }
   cp_async_wait<0>();
+}
+
+// Parse bytes [begin, end) (begin < 16) of 32 spans with machine `m`, one span per lane.
+template <int STAGES = kStages, class M>
+__device__ __forceinline__ void feed_tiled(M& m, const uint8_t* body, uint32_t begin, uint32_t end, uint8_t* warp_smem) {
+  uint32_t pos = begin;
+  tiled_windows<STAGES>(body, end, warp_smem, [&](uint32_t, uint32_t lim, auto&& load) {
+    consume_t(m, pos, lim, load);
+    if (m.dead()) pos = end;  // nothing further can change the verdict
+  });
 }
 
 __device__ __forceinline__ unsigned long long fnv1a64(const uint8_t* p, uint32_t n) {
@@ -275,7 +285,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(De
   JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
   JsonT m;
   m.init(K_REQ, body, stack_words, &cold, tabs);
-  feed_tiled(m, body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
+  feed_tiled(m, body, 0, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
   if (!live) return;
 
   uint8_t reason = ARKS_R_OK, flags = 0, claimer = 0;
@@ -322,7 +332,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(De
       if (prev == qos) break;
       g = (g + 1) & B.gmask;
     }
-    atomicAdd(&B.gcnt[g], 1);  // the table is memset to 0xff: counts start at -1
+    // the table is memset to 0xff: counts start at -1. The arrival that takes a group past the hot threshold lists it.
+    if (atomicAdd(&B.gcnt[g], 1) + 2 == kHotGroup + 1) B.hot_list[atomicAdd(B.hot_n, 1) + 1] = (int32_t)g;
     B.gnext[i] = atomicExch(&B.ghead[g], (int32_t)i);
     slot = (int32_t)g;
   } while (0);
@@ -344,18 +355,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(De
 // are admitted (k = 0 if any token-type entry or quota item is already over) and every later one is denied by
 // the first entry that is over with `k` admissions applied.
 // ------------------------------------------------------------------------------------------------
-constexpr int kHotGroup = 256;  // above this many arrivals of one qos entry in a batch the member list is not walked
-
-// kernel 2a: collect the slots of hot groups (BASELINE config 4: Zipf-hot tenants send thousands of requests per wave)
-__global__ void find_hot_groups_kernel(ReqDev B) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s <= B.gmask && B.gcnt[s] + 1 > kHotGroup) B.hot_list[atomicAdd(B.hot_n, 1)] = (int32_t)s;
-}
 // kernel 2b: one block per hot group sweeps the slot column once, front to back, and hands every member its arrival
 // rank (members with a smaller request index). n / 256 coalesced tile loads per hot group.
 __global__ void __launch_bounds__(256) rank_hot_groups_kernel(ReqDev B) {
   __shared__ uint32_t warp_tot[8];
-  const int n_hot = *B.hot_n;
+  const int n_hot = *B.hot_n + 1;  // the counter starts at -1 (it is part of the group-table memset)
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int h = blockIdx.x; h < n_hot; h += gridDim.x) {
     const int32_t s = B.hot_list[h];
@@ -517,6 +521,48 @@ __device__ __forceinline__ void warp_agg_add(long long* addr, long long v, bool 
   if ((int)(threadIdx.x & 31) == leader) atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)sum);
 }
 
+// A11 for one response per lane (all 32 lanes must call): doTokenRateLimit / doTokenQuotaLimit and the result row.
+__device__ __forceinline__ void account_usage(const DevTables& T, const RespDev& B, uint32_t i, bool live, int32_t qos, uint8_t reason,
+                                              uint8_t counted, long long u0, long long u1, long long u2) {
+  // doTokenRateLimit: += total on every token-type entry (check.go:47-59). Warp-aggregated per address.
+  int32_t qt = ARKS_QUOTA_NONE;
+  uint32_t nt[2] = {0, 0};
+  if (counted) {
+    for (uint32_t j = T.qos_rl_off[qos]; j < T.qos_rl_off[qos + 1]; j++) {
+      int rule = T.rl_rule[j];
+      if (rule >= 2) nt[rule - 2]++;
+    }
+    qt = T.qos_quota[qos];
+  }
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+    warp_agg_add(T.rate + (size_t)(2 + r) * T.n_qos + qos, u2 * (long long)nt[r], counted && nt[r]);
+  // doTokenQuotaLimit: QosToQuotaRequests + IncrUsage (check.go:62-72, qosconfig/types.go:45-72)
+  long long add[3] = {0, 0, 0};
+  if (counted && qt == ARKS_QUOTA_MISSING) reason = ARKS_R_QUOTA_CONFIG_RESP;
+  if (counted && qt >= 0) {
+    for (uint32_t j = T.quota_item_off[qt]; j < T.quota_item_off[qt + 1]; j++) {
+      int ty = T.qitem_type[j];
+      add[ty] += ty == 0 ? u0 : ty == 1 ? u1 : u2;
+    }
+  }
+#pragma unroll
+  for (int ty = 0; ty < 3; ty++)
+    warp_agg_add(T.quota + (size_t)(qt >= 0 ? qt : 0) * 3 + ty, add[ty], counted && qt >= 0 && add[ty] != 0);
+  if (T.qdelta) {  // quota shared across GPUs: remember what the other replicas have not seen yet (SURVEY.md §8e)
+#pragma unroll
+    for (int ty = 0; ty < 3; ty++)
+      warp_agg_add(T.qdelta + (size_t)(qt >= 0 ? qt : 0) * 3 + ty, add[ty], counted && qt >= 0 && add[ty] != 0);
+  }
+  if (live) {
+    B.reason[i] = reason;
+    B.counted[i] = counted;
+    B.usage[3 * (size_t)i + 0] = u0;
+    B.usage[3 * (size_t)i + 1] = u1;
+    B.usage[3 * (size_t)i + 2] = u2;
+  }
+}
+
 // per-lane response machine: an SSE chunk (stream) or one JSON document (non-stream). MODE 1 / 2 are the
 // all-JSON / all-SSE specialisations the host picks when a batch is homogeneous (smaller live state); MODE 0 mixes.
 template <int MODE>
@@ -592,7 +638,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_response_kernel(D
     const bool is_sse = MODE == 2 || (MODE == 0 && (fl & ARKS_RESP_STREAM));
     JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
     rm.init(is_sse, body, stack_words, &cold, tabs);
-    feed_tiled(rm, body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
+    feed_tiled(rm, body, 0, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
     if (live) {
       if (is_sse) {  // handle_response.go:113-133, every chunk in isolation
         if (!rm.finish(len, u0, u1, u2)) reason = ARKS_R_STREAMING;
@@ -608,43 +654,116 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_response_kernel(D
       counted = reason == ARKS_R_OK && u2 != 0;  // :186
     }
   }
-  // doTokenRateLimit: += total on every token-type entry (check.go:47-59). Warp-aggregated per address.
-  int32_t qt = ARKS_QUOTA_NONE;
-  uint32_t nt[2] = {0, 0};
-  if (counted) {
-    for (uint32_t j = T.qos_rl_off[qos]; j < T.qos_rl_off[qos + 1]; j++) {
-      int rule = T.rl_rule[j];
-      if (rule >= 2) nt[rule - 2]++;
+  account_usage(T, B, i, live, qos, reason, counted, u0, u1, u2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 3b: scan_sse — the all-SSE batch (BASELINE config 3). Same verdicts as scan_response_kernel<2>, different
+// work split. A lane that walks a whole chunk sits at an arbitrary phase of the frame structure, so a warp of 32
+// chunks runs ~9 lanes wide. Here a warp first cuts its 32 chunks into events (SseSplit, 16 bytes per step, one lane
+// per chunk), then parses the events one per lane — every lane starts on the '{' of a frame and frames of one server
+// look alike, so the lanes stay together — and finally every chunk's lane folds its events' verdicts in order.
+// Irregular chunks (anything SseSplit does not understand) run the sequential SseT machine in their own lane.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSseStages = 2;
+constexpr int kSseEvCap = 320;  // events per warp tile (32 chunks); a chunk that does not fit is parsed sequentially
+constexpr int kSseSmemPerBlock = kWarpsPerBlock * kSseStages * kStageBytes;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_sse_kernel(DevTables T, RespDev B) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(16) JsonSmem<false, true> json_smem;
+  __shared__ uint2 s_desc[kWarpsPerBlock][kSseEvCap];  // x: byte offset of the payload in B.bodies; y: len | owner<<16 | seq<<21
+  __shared__ long long s_usage[kWarpsPerBlock][32][3];
+  __shared__ uint32_t s_best[kWarpsPerBlock][32], s_fail[kWarpsPerBlock][32], s_n[kWarpsPerBlock];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool live = i < B.n;
+  uint8_t* wsmem = smem + warp * (kSseStages * kStageBytes);
+  const JsonTables tabs = json_smem.stage();
+  const uint32_t chunk_off = live ? B.body_off[i] : 0;
+  const uint32_t len = live ? B.body_len[i] : 0;
+  const uint8_t* body = B.bodies + chunk_off;
+  const int32_t qos = live ? B.qos[i] : 0;
+  uint32_t stack_words[kStackWords];
+  JsonCold cold;
+  s_best[warp][lane] = 0;
+  s_fail[warp][lane] = 0;
+  if (lane == 0) s_n[warp] = 0;
+  __syncwarp();
+
+  // phase 1: lines -> events
+  SseSplit sp;
+  sp.init();
+  {
+    uint32_t seq = 0;
+    auto emit = [&](uint32_t off, uint32_t l) {
+      const uint32_t slot = atomicAdd(&s_n[warp], 1u);
+      if (slot < (uint32_t)kSseEvCap) s_desc[warp][slot] = make_uint2(chunk_off + off, l | lane << 16 | seq << 21);
+      else sp.flags |= SseSplit::F_IRREGULAR;
+      seq++;
+    };
+    tiled_windows<kSseStages>(body, len, wsmem, [&](uint32_t wbeg, uint32_t lim, auto&& load) {
+      for (uint32_t ub = wbeg; ub < lim; ub += 16) {
+        const Unit16 q = load(ub >> 4);
+        sp.unit(ub, lim - ub, q.w[0], q.w[1], q.w[2], q.w[3], emit);
+      }
+    });
+    sp.finish(len);
+  }
+  __syncwarp();
+  const uint32_t n_ev = min(s_n[warp], (uint32_t)kSseEvCap);
+
+  // phase 2: one event per lane
+  for (uint32_t r0 = 0; r0 < n_ev; r0 += 32) {
+    const uint32_t slot = r0 + lane;
+    const bool has = slot < n_ev;
+    const uint2 d = has ? s_desc[warp][slot] : make_uint2(0u, 0u);
+    const uint32_t owner = (d.y >> 16) & 31u, seq1 = (d.y >> 21) + 1u;
+    const uint8_t* base = B.bodies + (d.x & ~15u);
+    const uint32_t begin = d.x & 15u, end = has ? begin + (d.y & 0xffffu) : 0u;
+    JsonT ev;
+    ev.init(K_EVT, base, stack_words, &cold, tabs);
+    feed_tiled<kSseStages>(ev, base, begin, end, wsmem);
+    bool wins = false;
+    if (has) {
+      const SseEventVerdict v = sse_event_verdict(ev, end);
+      if (v.fail) s_fail[warp][owner] = 1;
+      else if (v.no_choices) { atomicMax(&s_best[warp][owner], seq1); wins = true; }
     }
-    qt = T.qos_quota[qos];
-  }
-#pragma unroll
-  for (int r = 0; r < 2; r++)
-    warp_agg_add(T.rate + (size_t)(2 + r) * T.n_qos + qos, u2 * (long long)nt[r], counted && nt[r]);
-  // doTokenQuotaLimit: QosToQuotaRequests + IncrUsage (check.go:62-72, qosconfig/types.go:45-72)
-  long long add[3] = {0, 0, 0};
-  if (counted && qt == ARKS_QUOTA_MISSING) reason = ARKS_R_QUOTA_CONFIG_RESP;
-  if (counted && qt >= 0) {
-    for (uint32_t j = T.quota_item_off[qt]; j < T.quota_item_off[qt + 1]; j++) {
-      int ty = T.qitem_type[j];
-      add[ty] += ty == 0 ? u0 : ty == 1 ? u1 : u2;
+    __syncwarp();
+    if (wins && s_best[warp][owner] == seq1) {  // the last usage-bearing event of its chunk so far (handle_response.go:119-123)
+      s_usage[warp][owner][0] = cold.usage[0];
+      s_usage[warp][owner][1] = cold.usage[1];
+      s_usage[warp][owner][2] = cold.usage[2];
     }
+    __syncwarp();
   }
-#pragma unroll
-  for (int ty = 0; ty < 3; ty++)
-    warp_agg_add(T.quota + (size_t)(qt >= 0 ? qt : 0) * 3 + ty, add[ty], counted && qt >= 0 && add[ty] != 0);
-  if (T.qdelta) {  // quota shared across GPUs: remember what the other replicas have not seen yet (SURVEY.md §8e)
-#pragma unroll
-    for (int ty = 0; ty < 3; ty++)
-      warp_agg_add(T.qdelta + (size_t)(qt >= 0 ? qt : 0) * 3 + ty, add[ty], counted && qt >= 0 && add[ty] != 0);
-  }
+
+  // phase 3: the chunk's verdict
+  uint8_t reason = ARKS_R_OK, counted = 0;
+  long long u0 = 0, u1 = 0, u2 = 0;
   if (live) {
-    B.reason[i] = reason;
-    B.counted[i] = counted;
-    B.usage[3 * (size_t)i + 0] = u0;
-    B.usage[3 * (size_t)i + 1] = u1;
-    B.usage[3 * (size_t)i + 2] = u2;
+    if (!sp.irregular()) {
+      if (s_fail[warp][lane]) reason = ARKS_R_STREAMING;
+      else if (s_best[warp][lane]) { u0 = s_usage[warp][lane][0]; u1 = s_usage[warp][lane][1]; u2 = s_usage[warp][lane][2]; }
+    } else {
+      SseT st;
+      st.init(body, stack_words, &cold, tabs);
+      uint32_t pos = 0;
+      const uint4* units = reinterpret_cast<const uint4*>(body);
+      consume_t(st, pos, len, [&](uint32_t u) {
+        const uint4 v = ld_nc_v4(units + u);
+        Unit16 q;
+        q.w[0] = v.x; q.w[1] = v.y; q.w[2] = v.z; q.w[3] = v.w;
+        return q;
+      });
+      if (!st.finish(len)) reason = ARKS_R_STREAMING;
+      else { u0 = st.usage[0]; u1 = st.usage[1]; u2 = st.usage[2]; }
+    }
+    counted = reason == ARKS_R_OK && u2 != 0;  // handle_response.go:186
   }
+  __syncwarp();
+  account_usage(T, B, i, live, qos, reason, counted, u0, u1, u2);
 }
 
 // quota[i] += reduced[i] - own[i]; own[i] = 0  — applies what the OTHER GPUs added since the last fold
@@ -714,6 +833,7 @@ struct arks_ctx {
   uint32_t fetch_n = 0;          // batch size of the last run_* call (what fetch_* copies back)
   // optional per-kernel timing (bench roofline): events around each launch of the last run_* call
   bool prof = false;
+  bool sse_sequential = false;  // ARKS_SSE_SEQUENTIAL=1: all-SSE batches use scan_response_kernel<2> (A/B measurements)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int ev_n = 0;
   uint8_t* d_inter = nullptr;    // intermediates + group table
@@ -793,6 +913,7 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return ARKS_E_NO_DEVICE;
   arks_ctx* ctx = new arks_ctx();
   ctx->device = device;
+  if (const char* e = getenv("ARKS_SSE_SEQUENTIAL")) ctx->sse_sequential = e[0] == '1';
   ctx->max_batch = max_batch;
   ctx->max_bytes = align_up(max_batch_bytes + 16, 256);
   for (int r = 0; r < 4; r++) ctx->last_win[r] = INT64_MIN;
@@ -807,10 +928,11 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaFuncSetAttribute(scan_response_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
   CK(cudaFuncSetAttribute(scan_response_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
   CK(cudaFuncSetAttribute(scan_response_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
+  CK(cudaFuncSetAttribute(scan_sse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSseSmemPerBlock));
   uint32_t g = 64;
   while (g < 2 * n) g <<= 1;
   ctx->gsize = g;
-  size_t inter = align_up(n, 256) * 2 + align_up(n * 4, 256) * 5 + align_up((size_t)g * 4, 256) * 3 + (size_t)g * 32 + 1024 +
+  size_t inter = align_up(n, 256) * 2 + align_up(n * 4, 256) * 5 + align_up((size_t)g * 4, 256) * 3 + (size_t)g * 32 + 2048 +
                  align_up((n / kHotGroup + 2) * 4, 256);
   CK(cudaMalloc(&ctx->d_inter, inter));
   ctx->result_cap = align_up(n, 256) * 3 + align_up(n * 4, 256) * 3 + align_up(n * 8, 256) * 3;
@@ -1140,7 +1262,7 @@ static void carve_request(arks_ctx* ctx, ReqDev& r, size_t batch_n) {
   r.gnext = (int32_t*)p; p += align_up(n * 4, 256);
   r.gkey = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);   // gkey and ghead are contiguous: one memset(-1)
   r.ghead = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);
-  r.gcnt = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256);
+  r.gcnt = (int32_t*)p; p += align_up((size_t)ctx->gsize * 4, 256) + 256;  // + the hot-group counter word
   r.gsnap = (long long*)p; p += align_up((size_t)ctx->gsize * 32, 256);
   r.hot_n = (int32_t*)p; p += 256;
   r.hot_list = (int32_t*)p; p += align_up((n / kHotGroup + 2) * 4, 256);
@@ -1178,16 +1300,15 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   // gkey | ghead | gcnt are laid out back to back for THIS batch's table size: one memset(0xff) clears all three
   r.ghead = r.gkey + g;
   r.gcnt = r.gkey + 2 * (size_t)g;
-  CK(cudaMemsetAsync(r.gkey, 0xff, (size_t)g * 12, ctx->stream));
+  r.hot_n = r.gkey + 3 * (size_t)g;  // one more word: the hot-group counter, also starting at -1
+  CK(cudaMemsetAsync(r.gkey, 0xff, (size_t)g * 12 + 4, ctx->stream));
   const uint32_t tpb = kWarpsPerBlock * 32;
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   scan_request_kernel<<<(n + tpb - 1) / tpb, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, r);
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   if (n > (uint32_t)kHotGroup) {  // a group can only be hot if the batch is larger than the threshold
-    CK(cudaMemsetAsync(r.hot_n, 0, 4, ctx->stream));
-    find_hot_groups_kernel<<<(g + 255) / 256, 256, 0, ctx->stream>>>(r);
-    rank_hot_groups_kernel<<<296, 256, 0, ctx->stream>>>(r);
-    ctx->launches += 2;
+    rank_hot_groups_kernel<<<296, 256, 0, ctx->stream>>>(r);  // exits at once when scan_request listed no hot group
+    ctx->launches += 1;
   }
   limit_admit_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dt, r);
   if (ctx->prof) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_n = 3; }
@@ -1318,6 +1439,7 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   const dim3 grid((n + tpb - 1) / tpb);
   if (sl.resp_mode == 1) scan_response_kernel<1><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
+  else if (sl.resp_mode == 2 && !ctx->sse_sequential) scan_sse_kernel<<<grid, tpb, kSseSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
   else if (sl.resp_mode == 2) scan_response_kernel<2><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
   else scan_response_kernel<0><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
   if (ctx->prof) { CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_n = 2; }

@@ -10,7 +10,7 @@
 //   K_RESP  {model, usage{prompt,completion,total}}                         pkg/gateway/handle_response.go:89-93,157
 //   K_EVT   {error?, len(choices)==0, usage} of one SSE event's data        pkg/gateway/handle_response.go:113-124
 #pragma once
-#include "json_machine.cuh"  // shared pieces: hashes, decode_span, out-of-line slow paths, SWAR byte masks
+#include "json_common.cuh"  // shared pieces: hashes, decode_span, out-of-line slow paths, SWAR byte masks
 #include "json_tables.h"
 
 namespace arks {
@@ -304,7 +304,8 @@ struct JsonT {
       }
       // the remaining events handle something and then dispatch the same byte again from another state
       if (t == EV_VALUE_BEGIN) {
-        if (special_value_begin(c, pos, ps)) return;
+        // most members of S / X objects are not read by the gateway: skip the handler for them
+        if (((vm() != VM_SKIP) | (ps == TS_VAL_T)) && special_value_begin(c, pos, ps)) return;
         ss = ps == TS_VAL_S ? TS_VALG_S : ps == TS_VAL_X ? TS_VALG_X : TS_VALG_T;
       } else if (t == EV_NUM_DONE) {
         if (ncap()) finish_number_capture();
@@ -464,6 +465,115 @@ struct SseT {
     return !fail;
   }
 };
+
+// ---------------------------------------------------------------------------------------------
+// SseSplit — the line layer of SseT alone, 16 bytes at a time, for chunks that look the way every OpenAI-compatible
+// server writes them: only `data:` lines, comment lines and blank lines, no CR, exactly one data line per event and
+// no line of 64 KiB. For such a chunk it reports the payload span of every event the decoder would dispatch, in
+// order, stopping at the first `[DONE]`; the events can then be parsed independently of each other (one lane each,
+// all lanes starting at the first byte of a JSON document, which is what keeps a warp converged). Anything else
+// (`event:` lines, CR LF, multi-line data, empty events, over-long lines ...) sets `irregular` and the caller runs
+// SseT over the whole chunk instead, so the verdict never depends on which of the two paths ran.
+// ---------------------------------------------------------------------------------------------
+ARKS_HD uint32_t eq_mask16(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3, uint32_t c4) {
+  uint32_t f[4] = {q0 ^ c4, q1 ^ c4, q2 ^ c4, q3 ^ c4};
+  uint32_t m = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; k++) {
+    const uint32_t t = ~(((f[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | f[k]) & 0x80808080u;  // bit 7 of every zero byte, exact
+    m |= (((t >> 7) * 0x01020408u) >> 24 & 0xfu) << (4 * k);
+  }
+  return m;
+}
+
+struct SseSplit {
+  uint32_t s;         // start of the current line
+  uint32_t have;      // bytes of the line head captured so far (<= 16)
+  uint64_t h0, h1;    // first 16 bytes of the current line, little endian
+  uint32_t pend_off, pend_len;
+  uint32_t flags;     // F_*
+  enum : uint32_t { F_PEND = 1, F_PEND_DONE = 2, F_STOPPED = 4, F_IRREGULAR = 8 };
+
+  ARKS_HD void init() { s = 0; have = 0; h0 = h1 = 0; pend_off = pend_len = 0; flags = 0; }
+  ARKS_HD bool irregular() const { return flags & F_IRREGULAR; }
+
+  // append the bytes of unit `ub` that belong to the head of the current line
+  ARKS_HD void capture(uint32_t ub, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
+    const uint32_t o = s + have - ub;  // first unit byte that is not captured yet (s + have >= ub by construction)
+    if (o >= 16) return;
+    uint64_t lo = (uint64_t)q0 | (uint64_t)q1 << 32, hi = (uint64_t)q2 | (uint64_t)q3 << 32;
+    if (o >= 8) { lo = hi >> (8 * (o - 8)); hi = 0; }
+    else if (o) { lo = (lo >> (8 * o)) | (hi << (64 - 8 * o)); hi >>= 8 * o; }
+    // (lo, hi) now start at the first new byte; place them behind the `have` bytes already there
+    if (have == 0) { h0 = lo; h1 = hi; }
+    else if (have >= 8) { h1 |= lo << (8 * (have - 8)); }
+    else { h0 |= lo << (8 * have); h1 |= (lo >> (64 - 8 * have)) | (hi << (8 * have)); }
+    have += 16 - o;
+    if (have > 16) have = 16;
+  }
+  template <class E>
+  ARKS_HD void end_line(uint32_t p, E&& emit) {
+    const uint32_t L = p - s;
+    if (L >= 65536) { flags |= F_IRREGULAR; return; }  // bufio.Scanner: token too long
+    if (L == 0) {                                      // blank line: dispatch
+      if (flags & F_PEND) {
+        if (!(flags & F_STOPPED)) {
+          if (flags & F_PEND_DONE) flags |= F_STOPPED;
+          else emit(pend_off, pend_len);
+        }
+        flags &= ~(uint32_t)(F_PEND | F_PEND_DONE);
+      } else if (!(flags & F_STOPPED)) {
+        flags |= F_IRREGULAR;  // an event without data: not JSON, the stream fails
+      }
+      return;
+    }
+    if ((uint8_t)h0 == ':') return;  // comment
+    if (L >= 5 && (h0 & 0xFFFFFFFFFFull) == 0x3a61746164ull /* "data:" */) {
+      if (flags & F_PEND) { flags |= F_IRREGULAR; return; }  // multi-line data
+      const uint32_t sp = (L >= 6 && (uint8_t)(h0 >> 40) == ' ') ? 1u : 0u;
+      pend_off = s + 5 + sp;
+      pend_len = L - 5 - sp;
+      // first six payload bytes = head bytes [5+sp, 11+sp)
+      const uint64_t six = sp ? ((h0 >> 48) | (h1 << 16)) : ((h0 >> 40) | (h1 << 24));
+      flags |= F_PEND;
+      if (pend_len >= 6 && (six & 0xFFFFFFFFFFFFull) == 0x5d454e4f445bull /* "[DONE]" */) flags |= F_PEND_DONE;
+      return;
+    }
+    flags |= F_IRREGULAR;  // any other field, or a line without a colon
+  }
+  // one 16-byte unit starting at byte `ub`, `nvalid` of its bytes inside the chunk
+  template <class E>
+  ARKS_HD void unit(uint32_t ub, uint32_t nvalid, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3, E&& emit) {
+    const uint32_t valid = nvalid >= 16 ? 0xffffu : ((1u << nvalid) - 1u);
+    uint32_t nl = eq_mask16(q0, q1, q2, q3, 0x0a0a0a0au) & valid;
+    if (eq_mask16(q0, q1, q2, q3, 0x0d0d0d0du) & valid) flags |= F_IRREGULAR;
+    if (have < 16) capture(ub, q0, q1, q2, q3);
+    while (nl) {
+      const uint32_t p = ub + first_set(nl);
+      nl &= nl - 1;
+      end_line(p, emit);
+      s = p + 1; have = 0; h0 = h1 = 0;
+      capture(ub, q0, q1, q2, q3);
+    }
+  }
+  ARKS_HD void finish(uint32_t len) {
+    if (len - s >= 65536) flags |= F_IRREGULAR;  // unterminated over-long last line
+  }
+};
+
+// verdict of one event parsed on its own (SseT::dispatch for a regular chunk)
+struct SseEventVerdict {
+  uint32_t fail, no_choices;
+};
+ARKS_HD SseEventVerdict sse_event_verdict(JsonT& ev, uint32_t end_pos) {
+  if (!ev.dead()) ev.step('\n', end_pos);  // the decoder joins data lines with '\n'
+  SseEventVerdict v;
+  v.fail = !ev.ok_at_end() || ev.cold->has_error_key;
+  v.no_choices = !v.fail && ev.cold->n_choices == 0;
+  return v;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Feed bytes [pos, lim) of one document to machine `m`; `load(u)` returns its 16-byte unit u (bytes past the end may

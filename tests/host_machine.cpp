@@ -1,4 +1,4 @@
-// host_machine.cpp — TEST-ONLY build of arks_b200/csrc/json_machine.cuh with g++ so the device state
+// host_machine.cpp — TEST-ONLY build of arks_b200/csrc/json_engine.cuh with g++ so the device state
 // machines can be fuzzed against the oracle on CPU (tests/test_machine_vs_oracle.py). Not shipped.
 #include <stddef.h>
 #include <string.h>
@@ -9,8 +9,8 @@ using namespace arks;
 
 // same bulk loop the kernels run, with units read straight from memory (zero padded past the end)
 template <class M>
-static void feed(M& m, const uint8_t* body, size_t len) {
-  uint32_t pos = 0;
+static void feed(M& m, const uint8_t* body, size_t len, uint32_t begin = 0) {
+  uint32_t pos = begin;
   // exercise window boundaries like the tiled kernels do: consume in 128-byte windows
   for (uint32_t wbeg = 0; wbeg < len; wbeg += 128) {
     uint32_t lim = (uint32_t)(len < wbeg + 128 ? len : wbeg + 128);
@@ -73,5 +73,42 @@ int hm_parse_sse(const uint8_t* body, size_t len, int64_t usage[3]) {
   bool ok = m.finish((uint32_t)len);
   for (int k = 0; k < 3; k++) usage[k] = m.usage[k];
   return ok ? 0 : 1;
+}
+// The split path of the SSE kernel: SseSplit finds the events, every event is parsed on its own from a 16-byte
+// aligned base (like a lane of the event phase), verdicts are combined in order. Returns 0/1 like hm_parse_sse, +2
+// when the chunk was irregular and SseT ran instead.
+int hm_parse_sse_split(const uint8_t* body, size_t len, int64_t usage[3]) {
+  static thread_local uint32_t stk[kStackWords];
+  static thread_local JsonCold cold;
+  SseSplit sp;
+  sp.init();
+  uint32_t offs[4096], lens[4096], n_ev = 0;
+  bool overflow = false;
+  for (size_t ub = 0; ub < len; ub += 16) {
+    uint8_t tmp[16];
+    size_t n = len - ub < 16 ? len - ub : 16;
+    for (int k = 0; k < 16; k++) tmp[k] = k < (int)n ? body[ub + k] : (uint8_t)(0x0a ^ (k & 1 ? 0x07 : 0));  // hostile padding: LF / CR
+    uint32_t q[4];
+    memcpy(q, tmp, 16);
+    sp.unit((uint32_t)ub, (uint32_t)n, q[0], q[1], q[2], q[3], [&](uint32_t off, uint32_t l) {
+      if (n_ev < 4096) { offs[n_ev] = off; lens[n_ev] = l; n_ev++; } else overflow = true;
+    });
+  }
+  sp.finish((uint32_t)len);
+  if (sp.irregular() || overflow) return hm_parse_sse(body, len, usage) + 2;
+  usage[0] = usage[1] = usage[2] = 0;
+  bool fail = false;
+  for (uint32_t e = 0; e < n_ev && !fail; e++) {
+    const uint8_t* base = body + (offs[e] & ~15u);
+    const uint32_t begin = offs[e] & 15u, end = begin + lens[e];
+    JsonT m;
+    m.init(K_EVT, base, stk, &cold, host_json_tables());
+    feed(m, base, end, begin);
+    SseEventVerdict v = sse_event_verdict(m, end);
+    if (v.fail) fail = true;
+    else if (v.no_choices) for (int k = 0; k < 3; k++) usage[k] = cold.usage[k];
+  }
+  if (fail) usage[0] = usage[1] = usage[2] = 0;
+  return fail ? 1 : 0;
 }
 }

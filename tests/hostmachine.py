@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "host_machine.cpp")
-HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_machine.cuh", "json_engine.cuh", "json_tables.h")]
+HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_common.cuh", "json_engine.cuh", "json_tables.h")]
 OUT = os.path.join(ROOT, "tests", "_build", "libhost_machine.so")
 _lib = None
 
@@ -24,6 +24,7 @@ def lib():
                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.hm_parse_response.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), i64p]
         L.hm_parse_sse.argtypes = [C.c_char_p, C.c_size_t, i64p]
+        L.hm_parse_sse_split.argtypes = [C.c_char_p, C.c_size_t, i64p]
         _lib = L
     return _lib
 
@@ -46,3 +47,10 @@ def parse_sse_chunk(body: bytes):
     u = np.zeros(3, np.int64)
     rc = lib().hm_parse_sse(body, len(body), u.ctypes.data_as(C.POINTER(C.c_int64)))
     return rc, tuple(int(x) for x in u)
+
+
+def parse_sse_chunk_split(body: bytes):
+    """the event-parallel path of the SSE kernel (SseSplit + one JsonT per event); third item: fell back to SseT"""
+    u = np.zeros(3, np.int64)
+    rc = lib().hm_parse_sse_split(body, len(body), u.ctypes.data_as(C.POINTER(C.c_int64)))
+    return rc & 1, tuple(int(x) for x in u), bool(rc & 2)

@@ -158,6 +158,57 @@ def test_fuzzed_response_bodies_and_sse(gwmod, seed):
     state_same(g, o, NOW)
 
 
+@pytest.mark.parametrize("seed", [61, 62])
+def test_all_sse_batches_event_parallel_kernel(gwmod, seed):
+    """Homogeneous SSE batches take scan_sse_kernel (events cut out by SseSplit, one lane per event). Feed it real-server
+    shaped chunks, fuzzed chunks (CR LF, event: lines, multi-line data -> the sequential fallback inside the same
+    kernel), chunks with hundreds of tiny events (per-warp event list overflows) and unaligned event starts."""
+    w = traffic.Workload(n_tenants=8, seed=1)
+    g, o = pair(gwmod, w.tables, 8192, 32 << 20)
+    gen = Gen(seed)
+    r = gen.r
+    usage_ev = b'{"id":"c","choices":[],"usage":{"prompt_tokens":%d,"completion_tokens":%d,"total_tokens":%d}}'
+    delta_ev = b'{"id":"c","object":"chat.completion.chunk","choices":[{"index":0,"delta":{"content":"%s"},"finish_reason":null}],"usage":null}'
+    bodies = []
+    while len(bodies) < 6000:
+        k = r.random()
+        if k < 0.35:
+            b = gen.sse_chunk()
+            if r.random() < 0.5:
+                b = b.replace(b"\r\n", b"\n")
+        elif k < 0.8:  # what servers send: a few content deltas, sometimes the usage frame and [DONE]
+            parts = [b": " + b"k" * r.randint(0, 20) + b"\n\n"] if r.random() < 0.3 else []
+            for _ in range(r.randint(1, 8)):
+                parts.append(b"data: " + delta_ev % (b"w" * r.randint(0, 40)) + b"\n\n")
+            if r.random() < 0.5:
+                p, c = r.randint(0, 5000), r.randint(0, 5000)
+                parts.append(b"data: " + usage_ev % (p, c, p + c) + b"\n\n")
+                if r.random() < 0.3:
+                    parts.append(b"data: " + delta_ev % b"after" + b"\n\n")
+            if r.random() < 0.5:
+                parts.append(b"data: [DONE]\n\n")
+                if r.random() < 0.3:
+                    parts.append(b"data: {not json\n\n")
+            if r.random() < 0.1:
+                parts.insert(r.randint(0, len(parts)), b"data: {\"error\":{\"message\":\"boom\"}}\n\n")
+            b = b"".join(parts)
+            if r.random() < 0.1:
+                b = b[:r.randint(0, len(b))]
+        elif k < 0.9:  # many tiny events: 32 of these overflow the warp's event list
+            n = r.randint(20, 400)
+            b = b"".join(b"data: {}\n\n" if r.random() < 0.9 else b"data: " + usage_ev % (1, 2, 3) + b"\n\n" for _ in range(n))
+        else:
+            b = b"data: " + delta_ev % (b"x" * r.randint(100, 3000)) + b"\n\n" + b"data: " + usage_ev % (7, 8, 15) + b"\n\n"
+        if D2.search(b):
+            continue
+        bodies.append(b)
+    for lo in range(0, 6000, 3000):
+        part = bodies[lo:lo + 3000]
+        resp = ResponseBatch.from_lists(part, [i % 8 for i in range(len(part))], [abi.RESP_STREAM] * len(part), NOW + lo)
+        same(g.handle_response_body(resp), o.response_batch(resp), f"all-sse {lo}")
+        state_same(g, o, NOW + lo)
+
+
 def test_edges_empty_large_reload_and_time(gwmod):
     w = traffic.Workload(n_tenants=16, seed=2)
     g, o = pair(gwmod, w.tables, 512, 8 << 20)

@@ -1,4 +1,4 @@
-"""Differential fuzz on CPU: the device byte state machines (arks_b200/csrc/json_machine.cuh, compiled for the host
+"""Differential fuzz on CPU: the device byte state machines (arks_b200/csrc/json_engine.cuh, compiled for the host
 by tests/host_machine.cpp) against the oracle's function-by-function restatement of jsoniter / ssestream / gjson
 (oracle/ork_json.c). Any disagreement on (error?, model bytes, stream flags, usage ints) fails.
 
@@ -50,6 +50,60 @@ def test_sse_chunk_machine(seed):
             continue
         a, c = orklib.parse_sse_chunk(b), hm.parse_sse_chunk(b)
         assert a[0] == c[0] and (a[0] == 1 or a == c), (b, a, c)
+
+
+@pytest.mark.parametrize("seed", [33, 34])
+def test_sse_chunk_split_path(seed):
+    """SseSplit + per-event parse + in-order combine gives the oracle's verdict on every chunk, whether the chunk is
+    regular (event-parallel path) or not (falls back to the sequential machine); both paths must be exercised."""
+    g = Gen(seed)
+    n_reg = n_irr = 0
+    for it in range(30000):
+        b = g.sse_chunk()
+        if it % 3 == 0:  # the fuzzer likes CR LF and odd fields; make a share of the corpus look like real servers
+            b = b.replace(b"\r\n", b"\n").replace(b"data:  ", b"data: ")
+        if it % 7 == 0:
+            b = b": ping\n\n".join([b] * 1) + b""
+        if d2(b):
+            continue
+        a = orklib.parse_sse_chunk(b)
+        rc, usage, fell_back = hm.parse_sse_chunk_split(b)
+        n_irr += fell_back
+        n_reg += not fell_back
+        assert a[0] == rc and (rc == 1 or a[1] == usage), (b, a, rc, usage, fell_back)
+    assert n_reg > 3000 and n_irr > 3000, (n_reg, n_irr)
+
+
+def test_sse_split_cases():
+    ev = b'{"id":"x","choices":[],"usage":{"prompt_tokens":3,"completion_tokens":4,"total_tokens":7}}'
+    ch = b'{"id":"x","choices":[{"index":0,"delta":{"content":"hi"}}],"usage":null}'
+    cases = [
+        b"data: " + ch + b"\n\ndata: " + ev + b"\n\ndata: [DONE]\n\n",
+        b"data: " + ev + b"\n\ndata: [DONE]\n\ndata: {broken\n\n",       # nothing after [DONE] is parsed
+        b"data: " + ev + b"\n\ndata: {broken\n\ndata: [DONE]\n\n",       # a bad event before it fails the stream
+        b"data:" + ev + b"\n\n",                                           # no space after the colon
+        b"data: " + ev + b"\n",                                             # never dispatched
+        b"data: " + ev + b"\n\n\n",                                        # empty event -> not JSON
+        b": comment\ndata: " + ev + b"\n: another\n\n",
+        b"data: " + ev + b"\ndata: x\n\n",                                 # multi-line data (irregular)
+        b"data: " + ev + b"\r\n\r\n",                                      # CR LF (irregular)
+        b"event: thread.run\ndata: " + ev + b"\n\n",                       # wrapped event (irregular)
+        b"data: [DONE] trailing\n\ndata: " + ev + b"\n\n",                # HasPrefix("[DONE]")
+        b"data: [DONE\n\ndata: " + ev + b"\n\n",
+        b"data: \n\n", b"data:\n\n", b"data\n\n", b"\n", b"", b"data: 5\n\n", b"data: null\n\n",
+        b"x" * 15 + b"\n",
+    ]
+    for pad in range(0, 20):  # every alignment of the line starts against the 16-byte units
+        for c in cases:
+            b = b": " + b"p" * pad + b"\n" + c
+            a = orklib.parse_sse_chunk(b)
+            rc, usage, _ = hm.parse_sse_chunk_split(b)
+            assert a[0] == rc and (rc == 1 or a[1] == usage), (b, a, rc, usage)
+    ok = b"data: " + b'{"a":"' + b"x" * 65000 + b'"}\n\n'
+    bad = b"data: " + b'{"a":"' + b"x" * 65600 + b'"}\n\n'
+    tail = b"data: [DONE]\n\n" + b"y" * 70000
+    assert hm.parse_sse_chunk_split(ok)[0] == 0 and hm.parse_sse_chunk_split(bad)[0] == 1
+    assert hm.parse_sse_chunk_split(tail)[0] == orklib.parse_sse_chunk(tail)[0] == 1
 
 
 CASES_REQ = [
