@@ -166,12 +166,29 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
 // slots of one 512-byte row, so both sides of the transpose are conflict-free when lanes move in lock step.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHotGroup = 256;  // above this many arrivals of one qos entry in a batch the member list is not walked
-constexpr int kWin = 128;                        // bytes per body per stage
+#ifndef ARKS_KWIN
+#define ARKS_KWIN 128
+#endif
+#ifndef ARKS_KSTAGES
+#define ARKS_KSTAGES 3
+#endif
+#ifndef ARKS_SSE_STAGES
+#define ARKS_SSE_STAGES 2
+#endif
+#ifndef ARKS_MINBLK
+#define ARKS_MINBLK 7
+#endif
+#ifndef ARKS_SSE_MINBLK
+#define ARKS_SSE_MINBLK 7
+#endif
+constexpr int kWin = ARKS_KWIN;                  // bytes per body per stage
 constexpr int kUnits = kWin / 16;                // 16-byte units per body per stage
-constexpr int kStages = 3;
-constexpr int kStageBytes = 32 * kWin;           // 4 KiB per warp per stage
+constexpr int kStages = ARKS_KSTAGES;
+constexpr int kStageBytes = 32 * kWin;           // per warp per stage
 constexpr int kWarpsPerBlock = 2;
-constexpr int kSmemPerBlock = kWarpsPerBlock * kStages * kStageBytes;  // 24 KiB
+constexpr int kMinBlocks = ARKS_MINBLK;          // resident blocks per SM the scan kernels are compiled for
+constexpr int kSmemPerBlock = kWarpsPerBlock * kStages * kStageBytes;
+static_assert(kUnits == 8 || kUnits == 4, "window = 4 or 8 units");
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes));
@@ -180,14 +197,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// issue the copies of window `w` (bytes [w*kWin, (w+1)*kWin) of all 32 bodies) into stage buffer `stage_smem`
+// issue the copies of window `w` (bytes [w*kWin, (w+1)*kWin) of all 32 bodies) into stage buffer `stage_smem`:
+// kUnits neighbouring lanes copy one body's window, 32 / kUnits bodies per pass
 __device__ __forceinline__ void issue_window(uint32_t stage_smem, const uint8_t* my_body, uint32_t my_padded, uint32_t w,
                                              uint32_t lane) {
-  const uint32_t u = lane & 7;             // unit within the window handled by this lane
-  const uint32_t off = w * kWin + u * 16;  // byte offset inside the body
+  const uint32_t u = lane & (kUnits - 1);   // unit within the window handled by this lane
+  const uint32_t off = w * kWin + u * 16;   // byte offset inside the body
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const uint32_t b = (lane >> 3) + 4 * k;  // body (== owning lane) this copy belongs to
+  for (int k = 0; k < kUnits; k++) {
+    const uint32_t b = lane / kUnits + (32 / kUnits) * k;  // body (== owning lane) this copy belongs to
     const uint8_t* base = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, (unsigned long long)my_body, b));
     const uint32_t plen = __shfl_sync(0xffffffffu, my_padded, b);
     const uint32_t slot = u * 32 + ((b + u) & 31);
@@ -195,7 +213,7 @@ __device__ __forceinline__ void issue_window(uint32_t stage_smem, const uint8_t*
     cp_async16(stage_smem + slot * 16, in ? base + off : base, in ? 16u : 0u);
   }
 }
-static_assert(kUnits == 8, "issue_window assumes 8 units per window");
+
 
 // Stream bytes [0, end) of 32 spans, one per lane (lanes without work pass end == 0), through a STAGES-deep window
 // pipeline; per_window(wbeg, lim, load) is called by every lane for every window, load(u) returns the lane's own
@@ -236,11 +254,33 @@ __device__ __forceinline__ void tiled_windows(const uint8_t* body, uint32_t end,
 }
 
 // Parse bytes [begin, end) (begin < 16) of 32 spans with machine `m`, one span per lane.
-template <int STAGES = kStages, class M>
+template <int STAGES = kStages, bool EVSYNC = false, class M>
 __device__ __forceinline__ void feed_tiled(M& m, const uint8_t* body, uint32_t begin, uint32_t end, uint8_t* warp_smem) {
   uint32_t pos = begin;
-  tiled_windows<STAGES>(body, end, warp_smem, [&](uint32_t, uint32_t lim, auto&& load) {
-    consume_t(m, pos, lim, load);
+  tiled_windows<STAGES>(body, end, warp_smem, [&](uint32_t wbeg, uint32_t lim, auto&& load) {
+    if constexpr (EVSYNC) {
+      // special-byte masks of this window's units, computed up front with the warp converged (inside the parse loop the
+      // lanes cross unit boundaries at different iterations, so the same code would run ~7 lanes wide)
+      uint32_t mk[kUnits / 2];
+#pragma unroll
+      for (int j = 0; j < kUnits / 2; j++) mk[j] = 0;
+#pragma unroll
+      for (int j = 0; j < kUnits; j++) {
+        if (wbeg + 16u * j < lim) {
+          const Unit16 q = load((wbeg >> 4) + j);
+          mk[j >> 1] |= special_mask16(q.w[0], q.w[1], q.w[2], q.w[3]) << (16 * (j & 1));
+        }
+      }
+      consume_evsync(m, pos, lim, load, [&](uint32_t u, uint32_t, uint32_t, uint32_t, uint32_t) {
+        const uint32_t ul = u - (wbeg >> 4);
+        uint32_t w;
+        if constexpr (kUnits == 8) w = (ul & 4) ? ((ul & 2) ? mk[3] : mk[2]) : ((ul & 2) ? mk[1] : mk[0]);
+        else w = (ul & 2) ? mk[1] : mk[0];
+        return (w >> (16 * (ul & 1))) & 0xffffu;
+      });
+    } else {
+      consume_t(m, pos, lim, load);
+    }
     if (m.dead()) pos = end;  // nothing further can change the verdict
   });
 }
@@ -272,7 +312,8 @@ __device__ bool model_equals(const uint8_t* body, const JsonCold& m, const uint8
 // ------------------------------------------------------------------------------------------------
 // kernel 1: scan_request — A3 (body parse), A4 (GetQosByToken), A5 (GetModelList) of SURVEY.md §8a
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(DevTables T, ReqDev B) {
+template <bool EVSYNC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_request_kernel(DevTables T, ReqDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < B.n;
@@ -285,7 +326,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_request_kernel(De
   JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
   JsonT m;
   m.init(K_REQ, body, stack_words, &cold, tabs);
-  feed_tiled(m, body, 0, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
+  feed_tiled<kStages, EVSYNC>(m, body, 0, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
   if (!live) return;
 
   uint8_t reason = ARKS_R_OK, flags = 0, claimer = 0;
@@ -617,8 +658,8 @@ struct RespM<0> {
   }
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_response_kernel(DevTables T, RespDev B) {
+template <int MODE, bool EVSYNC = false>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response_kernel(DevTables T, RespDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool live = i < B.n;
@@ -638,7 +679,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_response_kernel(D
     const bool is_sse = MODE == 2 || (MODE == 0 && (fl & ARKS_RESP_STREAM));
     JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
     rm.init(is_sse, body, stack_words, &cold, tabs);
-    feed_tiled(rm, body, 0, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
+    if constexpr (EVSYNC) feed_tiled<kStages, true>(rm.json(), body, 0, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
+    else feed_tiled(rm, body, 0, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
     if (live) {
       if (is_sse) {  // handle_response.go:113-133, every chunk in isolation
         if (!rm.finish(len, u0, u1, u2)) reason = ARKS_R_STREAMING;
@@ -665,11 +707,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_response_kernel(D
 // look alike, so the lanes stay together — and finally every chunk's lane folds its events' verdicts in order.
 // Irregular chunks (anything SseSplit does not understand) run the sequential SseT machine in their own lane.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSseStages = 2;
+constexpr int kSseStages = ARKS_SSE_STAGES;
 constexpr int kSseEvCap = 320;  // events per warp tile (32 chunks); a chunk that does not fit is parsed sequentially
 constexpr int kSseSmemPerBlock = kWarpsPerBlock * kSseStages * kStageBytes;
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_sse_kernel(DevTables T, RespDev B) {
+template <bool EVSYNC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, ARKS_SSE_MINBLK) scan_sse_kernel(DevTables T, RespDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(16) JsonSmem<false, true> json_smem;
   __shared__ uint2 s_desc[kWarpsPerBlock][kSseEvCap];  // x: byte offset of the payload in B.bodies; y: len | owner<<16 | seq<<21
@@ -723,7 +766,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) scan_sse_kernel(DevTab
     const uint32_t begin = d.x & 15u, end = has ? begin + (d.y & 0xffffu) : 0u;
     JsonT ev;
     ev.init(K_EVT, base, stack_words, &cold, tabs);
-    feed_tiled<kSseStages>(ev, base, begin, end, wsmem);
+    feed_tiled<kSseStages, EVSYNC>(ev, base, begin, end, wsmem);
     bool wins = false;
     if (has) {
       const SseEventVerdict v = sse_event_verdict(ev, end);
@@ -791,7 +834,8 @@ struct HostTables {  // what we need to remember for reloads, snapshots and vali
 
 struct arks_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;  // kernels, counter memsets, result D2H: the order of this stream IS the linearisation
+  cudaStream_t h2d = nullptr;     // batch uploads (overlap the kernels of earlier batches)
   char err[512] = {0};
   uint32_t max_batch = 0;
   uint64_t max_bytes = 0;
@@ -819,6 +863,7 @@ struct arks_ctx {
     uint8_t* h_req_result = nullptr;   // pinned, per slot: asynchronous submits keep several batches in flight
     uint8_t* h_resp_result = nullptr;
     cudaEvent_t req_done = nullptr, resp_done = nullptr;
+    cudaEvent_t req_ran = nullptr, resp_ran = nullptr;  // the slot's device buffers are free again (kernels done)
     uint32_t req_fetch_n = 0, resp_fetch_n = 0;
     ReqDev rq{};
     RespDev rp{};
@@ -833,6 +878,7 @@ struct arks_ctx {
   uint32_t fetch_n = 0;          // batch size of the last run_* call (what fetch_* copies back)
   // optional per-kernel timing (bench roofline): events around each launch of the last run_* call
   bool prof = false;
+  int evsync = 6;  // which scans run the event-synchronised schedule (consume_evsync): 1 request, 2 JSON response, 4 SSE event phase; ARKS_EVSYNC overrides (A/B)
   bool sse_sequential = false;  // ARKS_SSE_SEQUENTIAL=1: all-SSE batches use scan_response_kernel<2> (A/B measurements)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int ev_n = 0;
@@ -914,21 +960,26 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   arks_ctx* ctx = new arks_ctx();
   ctx->device = device;
   if (const char* e = getenv("ARKS_SSE_SEQUENTIAL")) ctx->sse_sequential = e[0] == '1';
+  if (const char* e = getenv("ARKS_EVSYNC")) ctx->evsync = atoi(e);
   ctx->max_batch = max_batch;
   ctx->max_bytes = align_up(max_batch_bytes + 16, 256);
   for (int r = 0; r < 4; r++) ctx->last_win[r] = INT64_MIN;
   *out = ctx;
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
   size_t n = max_batch;
   // meta: body_off, body_len, token_off(n+1), pick_rand, qos, flags + token bytes (256 B per request budget)
   ctx->meta_cap = align_up(n * 4, 256) * 4 + align_up(n * 8, 256) + align_up(n, 256) + align_up(n * 256, 256);
   for (int k = 0; k < 4; k++) CK(cudaEventCreate(&ctx->ev[k]));
-  CK(cudaFuncSetAttribute(scan_request_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
+  CK(cudaFuncSetAttribute(scan_request_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
+  CK(cudaFuncSetAttribute(scan_request_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
+  CK((cudaFuncSetAttribute(scan_response_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock)));
   CK(cudaFuncSetAttribute(scan_response_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
   CK(cudaFuncSetAttribute(scan_response_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
   CK(cudaFuncSetAttribute(scan_response_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
-  CK(cudaFuncSetAttribute(scan_sse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSseSmemPerBlock));
+  CK(cudaFuncSetAttribute(scan_sse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSseSmemPerBlock));
+  CK(cudaFuncSetAttribute(scan_sse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSseSmemPerBlock));
   uint32_t g = 64;
   while (g < 2 * n) g <<= 1;
   ctx->gsize = g;
@@ -948,6 +999,7 @@ static void free_tables(arks_ctx* ctx) {
 void arks_destroy(arks_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_tables(ctx);
   cudaFree(ctx->d_rate);
@@ -964,6 +1016,8 @@ void arks_destroy(arks_ctx* ctx) {
     cudaFreeHost(sl.h_req_result);
     cudaFreeHost(sl.h_resp_result);
     if (sl.req_done) cudaEventDestroy(sl.req_done);
+    if (sl.req_ran) cudaEventDestroy(sl.req_ran);
+    if (sl.resp_ran) cudaEventDestroy(sl.resp_ran);
     if (sl.resp_done) cudaEventDestroy(sl.resp_done);
     if (sl.req_copied) cudaEventDestroy(sl.req_copied);
     if (sl.resp_copied) cudaEventDestroy(sl.resp_copied);
@@ -973,6 +1027,7 @@ void arks_destroy(arks_ctx* ctx) {
   cudaFree(ctx->d_inter);
   cudaFree(ctx->d_result);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
   delete ctx;
 }
 
@@ -1169,6 +1224,7 @@ static int ensure_slot(arks_ctx* ctx, int k, bool want_req, bool want_resp) {
     CK(cudaEventCreateWithFlags(&sl.req_copied, cudaEventDisableTiming));
     CK(cudaMallocHost(&sl.h_req_result, ctx->result_cap));
     CK(cudaEventCreateWithFlags(&sl.req_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sl.req_ran, cudaEventDisableTiming));
   }
   if (want_resp && !sl.d_resp_bodies) {
     CK(cudaMalloc(&sl.d_resp_bodies, ctx->max_bytes));
@@ -1177,6 +1233,7 @@ static int ensure_slot(arks_ctx* ctx, int k, bool want_req, bool want_resp) {
     CK(cudaEventCreateWithFlags(&sl.resp_copied, cudaEventDisableTiming));
     CK(cudaMallocHost(&sl.h_resp_result, ctx->result_cap));
     CK(cudaEventCreateWithFlags(&sl.resp_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sl.resp_ran, cudaEventDisableTiming));
   }
   return 0;
 }
@@ -1231,9 +1288,11 @@ int arks_stage_request_batch(arks_ctx* ctx, const arks_request_batch* b) {
   memcpy(h + o_toff, b->token_off, (size_t)(n + 1) * 4);
   if (b->pick_rand) memcpy(h + o_rand, b->pick_rand, (size_t)n * 8);
   memcpy(h + o_tok, b->tokens, tok_bytes);
-  CK(cudaMemcpyAsync(sl.d_req_bodies, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(sl.d_req_meta, h, total, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaEventRecord(sl.req_copied, ctx->stream));
+  // uploads run on their own stream so that they overlap the kernels of the batches queued before this one
+  CK(cudaStreamWaitEvent(ctx->h2d, sl.req_ran, 0));  // the previous tenant of this slot's device buffers is done
+  CK(cudaMemcpyAsync(sl.d_req_bodies, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->h2d));
+  CK(cudaMemcpyAsync(sl.d_req_meta, h, total, cudaMemcpyHostToDevice, ctx->h2d));
+  CK(cudaEventRecord(sl.req_copied, ctx->h2d));
   ReqDev& r = sl.rq;
   r.bodies = sl.d_req_bodies;
   r.body_off = (const uint32_t*)(sl.d_req_meta + o_off);
@@ -1291,6 +1350,7 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   ctx->fetch_n = n;
   ctx->ev_n = 0;
   if (n == 0) return 0;
+  CK(cudaStreamWaitEvent(ctx->stream, sl.req_copied, 0));
   ReqDev& r = sl.rq;
   carve_request(ctx, r, n);
   // batch-local group table sized to the batch (2x, power of two); the three arrays are contiguous
@@ -1304,7 +1364,8 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   CK(cudaMemsetAsync(r.gkey, 0xff, (size_t)g * 12 + 4, ctx->stream));
   const uint32_t tpb = kWarpsPerBlock * 32;
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  scan_request_kernel<<<(n + tpb - 1) / tpb, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, r);
+  if (ctx->evsync & 1) scan_request_kernel<true><<<(n + tpb - 1) / tpb, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, r);
+  else scan_request_kernel<false><<<(n + tpb - 1) / tpb, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, r);
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   if (n > (uint32_t)kHotGroup) {  // a group can only be hot if the batch is larger than the threshold
     rank_hot_groups_kernel<<<296, 256, 0, ctx->stream>>>(r);  // exits at once when scan_request listed no hot group
@@ -1312,6 +1373,7 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   }
   limit_admit_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dt, r);
   if (ctx->prof) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_n = 3; }
+  CK(cudaEventRecord(sl.req_ran, ctx->stream));
   ctx->launches += 2;
   CK(cudaGetLastError());
   return 0;
@@ -1408,9 +1470,10 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   memcpy(h + o_len, b->body_len, (size_t)n * 4);
   memcpy(h + o_qos, b->qos, (size_t)n * 4);
   memcpy(h + o_fl, b->flags, n);
-  CK(cudaMemcpyAsync(sl.d_resp_bodies, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(sl.d_resp_meta, h, total, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaEventRecord(sl.resp_copied, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->h2d, sl.resp_ran, 0));
+  CK(cudaMemcpyAsync(sl.d_resp_bodies, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->h2d));
+  CK(cudaMemcpyAsync(sl.d_resp_meta, h, total, cudaMemcpyHostToDevice, ctx->h2d));
+  CK(cudaEventRecord(sl.resp_copied, ctx->h2d));
   RespDev& r = sl.rp;
   r.bodies = sl.d_resp_bodies;
   r.body_off = (const uint32_t*)(sl.d_resp_meta + o_off);
@@ -1436,13 +1499,17 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
   ctx->ev_n = 0;
   if (n == 0) return 0;
   const uint32_t tpb = kWarpsPerBlock * 32;
+  CK(cudaStreamWaitEvent(ctx->stream, sl.resp_copied, 0));
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   const dim3 grid((n + tpb - 1) / tpb);
-  if (sl.resp_mode == 1) scan_response_kernel<1><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
-  else if (sl.resp_mode == 2 && !ctx->sse_sequential) scan_sse_kernel<<<grid, tpb, kSseSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
+  if (sl.resp_mode == 1 && (ctx->evsync & 2)) scan_response_kernel<1, true><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
+  else if (sl.resp_mode == 1) scan_response_kernel<1><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
+  else if (sl.resp_mode == 2 && !ctx->sse_sequential && (ctx->evsync & 4)) scan_sse_kernel<true><<<grid, tpb, kSseSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
+  else if (sl.resp_mode == 2 && !ctx->sse_sequential) scan_sse_kernel<false><<<grid, tpb, kSseSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
   else if (sl.resp_mode == 2) scan_response_kernel<2><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
   else scan_response_kernel<0><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
   if (ctx->prof) { CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_n = 2; }
+  CK(cudaEventRecord(sl.resp_ran, ctx->stream));
   ctx->launches += 1;
   CK(cudaGetLastError());
   return 0;

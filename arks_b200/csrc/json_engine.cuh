@@ -581,8 +581,8 @@ ARKS_HD SseEventVerdict sse_event_verdict(JsonT& ev, uint32_t end_pos) {
 // bytes up to the next special byte of this unit; (2) push one byte through the table. The special-byte mask of a unit is
 // computed once, when the unit is loaded.
 // ---------------------------------------------------------------------------------------------
-template <class M, class L>
-ARKS_HD void consume_t(M& m, uint32_t& pos, uint32_t lim, L&& load) {
+template <class M, class L, class K>
+ARKS_HD void consume_t(M& m, uint32_t& pos, uint32_t lim, L&& load, K&& mask_of) {
   uint32_t cu = 0xffffffffu, q0 = 0, q1 = 0, q2 = 0, q3 = 0, umask = 0;
   while (pos < lim) {
     uint32_t o = pos & 15;
@@ -590,7 +590,7 @@ ARKS_HD void consume_t(M& m, uint32_t& pos, uint32_t lim, L&& load) {
       cu = pos >> 4;
       const Unit16 q = load(cu);
       q0 = q.w[0]; q1 = q.w[1]; q2 = q.w[2]; q3 = q.w[3];
-      umask = special_mask16(q0, q1, q2, q3);
+      umask = mask_of(cu, q0, q1, q2, q3);
     }
     if (m.can_fast()) {
       const uint32_t rest = umask >> o;
@@ -611,5 +611,65 @@ ARKS_HD void consume_t(M& m, uint32_t& pos, uint32_t lim, L&& load) {
     if (m.dead()) return;
   }
 }
+
+// Same contract as consume_t for a bare JsonT, different schedule: every lane first runs its ordinary transitions
+// (and bulk skips) up to the next byte that raises an event, then the warp handles one event per lane together.
+// When the 32 documents of a warp share a template (frames of one SSE stream format, completions of one server) the
+// k-th event of every lane is the same kind, so event() runs with the warp converged instead of ~10 lanes wide;
+// documents that do not line up only cost idle lanes, never a different result.
+struct MaskOnTheSpot {
+  ARKS_HD uint32_t operator()(uint32_t, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) const { return special_mask16(q0, q1, q2, q3); }
+};
+template <class M, class L>
+ARKS_HD void consume_t(M& m, uint32_t& pos, uint32_t lim, L&& load) { consume_t(m, pos, lim, load, MaskOnTheSpot()); }
+
+template <class L, class K>
+ARKS_HD void consume_evsync(JsonT& m, uint32_t& pos, uint32_t lim, L&& load, K&& mask_of) {
+  uint32_t cu = 0xffffffffu, q0 = 0, q1 = 0, q2 = 0, q3 = 0, umask = 0;
+  while (pos < lim) {
+    uint32_t t = 0, k = 0;
+    uint8_t c = 0;
+    bool ev = false;
+    while (pos < lim) {
+      uint32_t o = pos & 15;
+      if ((pos >> 4) != cu) {
+        cu = pos >> 4;
+        const Unit16 q = load(cu);
+        q0 = q.w[0]; q1 = q.w[1]; q2 = q.w[2]; q3 = q.w[3];
+        umask = mask_of(cu, q0, q1, q2, q3);
+      }
+      if (m.can_fast()) {
+        const uint32_t rest = umask >> o;
+        uint32_t run = rest ? first_set(rest) : 16u - o;
+        const uint32_t avail = lim - pos;
+        if (run > avail) run = avail;
+        if (run) {
+          m.skip(run, o, q0, q1, q2, q3);
+          pos += run;
+          o += run;
+        }
+        if ((o == 16) | (pos >= lim)) continue;
+      }
+      const uint32_t lo = (o & 8) ? q2 : q0, hi = (o & 8) ? q3 : q1;
+      const uint32_t w = (o & 4) ? hi : lo;
+      c = (uint8_t)(w >> (8 * (o & 3)));
+      k = m.cls[c];
+      t = m.tab[m.ss * kJsonClasses + k];
+      if (t >= EV_BASE) { ev = true; break; }
+      const uint32_t ps = m.ss;
+      m.ss = t;
+      if (m.hb & JsonT::kSideMask) m.side_work(ps, c, pos);
+      pos++;
+      if (m.dead()) return;
+    }
+    if (!ev) return;
+    m.event(t, k, c, pos);
+    pos++;
+    if (m.dead()) return;
+  }
+}
+
+template <class L>
+ARKS_HD void consume_evsync(JsonT& m, uint32_t& pos, uint32_t lim, L&& load) { consume_evsync(m, pos, lim, load, MaskOnTheSpot()); }
 
 }  // namespace arks

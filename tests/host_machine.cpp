@@ -5,7 +5,11 @@
 
 #include "../arks_b200/csrc/json_engine.cuh"
 
+#include <type_traits>
+
 using namespace arks;
+
+static int g_evsync = 0;  // 1: JsonT documents go through consume_evsync (the schedule of the EVSYNC kernels)
 
 // same bulk loop the kernels run, with units read straight from memory (zero padded past the end)
 template <class M>
@@ -14,7 +18,7 @@ static void feed(M& m, const uint8_t* body, size_t len, uint32_t begin = 0) {
   // exercise window boundaries like the tiled kernels do: consume in 128-byte windows
   for (uint32_t wbeg = 0; wbeg < len; wbeg += 128) {
     uint32_t lim = (uint32_t)(len < wbeg + 128 ? len : wbeg + 128);
-    consume_t(m, pos, lim, [&](uint32_t u) {
+    auto load = [&](uint32_t u) {
       Unit16 q;
       uint8_t tmp[16] = {0};
       size_t o = (size_t)u * 16;
@@ -23,12 +27,19 @@ static void feed(M& m, const uint8_t* body, size_t len, uint32_t begin = 0) {
       for (int k = 0; k < 16; k++) tmp[k] = k < (int)n ? tmp[k] : (uint8_t)(0xA5 ^ k);  // garbage past the end
       memcpy(q.w, tmp, 16);
       return q;
-    });
+    };
+    if constexpr (std::is_same<M, JsonT>::value) {
+      if (g_evsync) consume_evsync(m, pos, lim, load);
+      else consume_t(m, pos, lim, load);
+    } else {
+      consume_t(m, pos, lim, load);
+    }
     if (m.dead()) break;
   }
 }
 
 extern "C" {
+void hm_set_evsync(int on) { g_evsync = on; }
 int hm_parse_request(const uint8_t* body, size_t len, uint8_t* model_out, size_t cap, size_t* model_len, int* stream,
                      int* so_present, int* iu) {
   static thread_local JsonT m;

@@ -54,3 +54,8 @@ def parse_sse_chunk_split(body: bytes):
     u = np.zeros(3, np.int64)
     rc = lib().hm_parse_sse_split(body, len(body), u.ctypes.data_as(C.POINTER(C.c_int64)))
     return rc & 1, tuple(int(x) for x in u), bool(rc & 2)
+
+
+def set_evsync(on: bool):
+    """route JsonT documents through consume_evsync (event-synchronised schedule) instead of consume_t"""
+    lib().hm_set_evsync(1 if on else 0)

@@ -4,6 +4,7 @@ by tests/host_machine.cpp) against the oracle's function-by-function restatement
 
 Documents containing a usage-shaped number with a fraction/exponent and more than 15 significant digits are outside
 the documented exact domain (divergence D2) and are skipped."""
+import random
 import re
 
 import pytest
@@ -104,6 +105,34 @@ def test_sse_split_cases():
     tail = b"data: [DONE]\n\n" + b"y" * 70000
     assert hm.parse_sse_chunk_split(ok)[0] == 0 and hm.parse_sse_chunk_split(bad)[0] == 1
     assert hm.parse_sse_chunk_split(tail)[0] == orklib.parse_sse_chunk(tail)[0] == 1
+
+
+def test_evsync_schedule_same_results():
+    """consume_evsync (events handled warp-synchronously) is only a different schedule of the same machine."""
+    hm.set_evsync(True)
+    try:
+        g = Gen(41)
+        for _ in range(12000):
+            b = g.request()
+            if not d2(b):
+                a, c = orklib.parse_request_body(b), hm.parse_request_body(b)
+                assert a[0] == c[0] and (a[0] == 1 or a == c), (b, a, c)
+            b = g.response()
+            if not d2(b):
+                a, c = orklib.parse_response_body(b), hm.parse_response_body(b)
+                assert a[0] == c[0] and (a[0] == 1 or (a[1] > 0, a[2]) == (c[1] > 0, c[2])), (b, a, c)
+            b = g.sse_chunk().replace(b"\r\n", b"\n")
+            if not d2(b):
+                a = orklib.parse_sse_chunk(b)
+                rc, usage, _ = hm.parse_sse_chunk_split(b)
+                assert a[0] == rc and (rc == 1 or a[1] == usage), (b, a, rc, usage)
+        r = random.Random(5)
+        for _ in range(300):
+            b = _long_doc(r, "req")
+            a, c = orklib.parse_request_body(b), hm.parse_request_body(b)
+            assert a[0] == c[0] and (a[0] == 1 or a == c), (b, a, c)
+    finally:
+        hm.set_evsync(False)
 
 
 CASES_REQ = [
