@@ -125,27 +125,30 @@ struct RespDev {
 // ------------------------------------------------------------------------------------------------
 // automaton tables (generated header json_tables.h): global copies, staged into shared memory once per block so that the
 // two lookups per byte are LDS (32 banks, random 2-byte reads) instead of constant-cache replays
-__device__ const uint8_t g_json_cls[256] = ARKS_JSON_CLASS_TABLE;
-__device__ const uint8_t g_json_tab_j[kJsonStatesJ * kJsonClasses] = ARKS_JSON_TABLE_J;
-__device__ const uint8_t g_json_tab_e[kJsonStatesE * kJsonClasses] = ARKS_JSON_TABLE_E;
+__device__ __align__(16) const uint8_t g_json_cls[256] = ARKS_JSON_CLASS_TABLE;
+__device__ __align__(16) const uint8_t g_json_tab_j[kJsonStatesJ * kJsonClasses] = ARKS_JSON_TABLE_J;
+__device__ __align__(16) const uint8_t g_json_tab_e[kJsonStatesE * kJsonClasses] = ARKS_JSON_TABLE_E;
 
 template <bool NEED_J, bool NEED_E>
 struct JsonSmem {
-  uint8_t tab_j[NEED_J ? kJsonStatesJ * kJsonClasses : 4];
-  uint8_t tab_e[NEED_E ? kJsonStatesE * kJsonClasses : 4];
-  uint8_t cls[256];
-  __device__ __forceinline__ JsonTables stage() {  // all threads of the block must call
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) reinterpret_cast<uint32_t*>(cls)[i] = reinterpret_cast<const uint32_t*>(g_json_cls)[i];
-    if (NEED_J)
-      for (int i = threadIdx.x; i < kJsonStatesJ * kJsonClasses / 4; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(tab_j)[i] = reinterpret_cast<const uint32_t*>(g_json_tab_j)[i];
-    if (NEED_E)
-      for (int i = threadIdx.x; i < kJsonStatesE * kJsonClasses / 4; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(tab_e)[i] = reinterpret_cast<const uint32_t*>(g_json_tab_e)[i];
-    __syncthreads();
+  alignas(16) uint8_t tab_j[NEED_J ? kJsonStatesJ * kJsonClasses : 16];
+  alignas(16) uint8_t tab_e[NEED_E ? kJsonStatesE * kJsonClasses : 16];
+  alignas(16) uint8_t cls[256];
+  // Issue the table copies as one cp.async group (all threads of the block). The caller overlaps them with other work,
+  // then waits for the group and calls __syncthreads() before the first lookup.
+  __device__ __forceinline__ JsonTables stage_async() {
+    auto copy = [&](uint8_t* dst, const uint8_t* src, int bytes) {
+      for (int o = threadIdx.x * 16; o < bytes; o += blockDim.x * 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + o)), "l"(src + o));
+    };
+    copy(cls, g_json_cls, 256);
+    if (NEED_J) copy(tab_j, g_json_tab_j, kJsonStatesJ * kJsonClasses);
+    if (NEED_E) copy(tab_e, g_json_tab_e, kJsonStatesE * kJsonClasses);
+    asm volatile("cp.async.commit_group;");
     return JsonTables{cls, tab_j, tab_e};
   }
 };
+static_assert((kJsonStatesJ * kJsonClasses) % 16 == 0 && (kJsonStatesE * kJsonClasses) % 16 == 0, "tables are copied in 16-byte pieces");
 
 __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
   uint4 r;
@@ -216,48 +219,65 @@ __device__ __forceinline__ void issue_window(uint32_t stage_smem, const uint8_t*
 
 
 // Stream bytes [0, end) of 32 spans, one per lane (lanes without work pass end == 0), through a STAGES-deep window
-// pipeline; per_window(wbeg, lim, load) is called by every lane for every window, load(u) returns the lane's own
-// 16-byte unit u (absolute unit index inside the span).
+// pipeline. start() issues the first STAGES-1 windows (one cp.async group each) and returns, so the caller can do
+// unrelated long-latency work before run(); run() calls per_window(wbeg, lim, load) on every lane for every window,
+// load(u) returns the lane's own 16-byte unit u (absolute unit index inside the span).
+template <int STAGES>
+struct WindowPipe {
+  const uint8_t* body;
+  uint8_t* warp_smem;
+  uint32_t end, padded, n_win, lane, smem0;
+  __device__ __forceinline__ void start(const uint8_t* body_, uint32_t end_, uint8_t* warp_smem_) {
+    body = body_; end = end_; warp_smem = warp_smem_;
+    lane = threadIdx.x & 31;
+    padded = (end + 15u) & ~15u;
+    uint32_t maxlen = end;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, d));
+    n_win = (maxlen + kWin - 1) / kWin;
+    smem0 = (uint32_t)__cvta_generic_to_shared(warp_smem);
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+      if ((uint32_t)s < n_win) issue_window(smem0 + s * kStageBytes, body, padded, s, lane);
+      cp_async_commit();
+    }
+  }
+  template <class F>
+  __device__ __forceinline__ void run(F&& per_window) {
+    for (uint32_t w = 0; w < n_win; w++) {
+      const uint32_t nxt = w + STAGES - 1;
+      if (nxt < n_win) issue_window(smem0 + (nxt % STAGES) * kStageBytes, body, padded, nxt, lane);
+      cp_async_commit();
+      cp_async_wait<STAGES - 1>();
+      __syncwarp();
+      const uint8_t* st = warp_smem + (w % STAGES) * kStageBytes;
+      const uint32_t wbeg = w * kWin;
+      const uint32_t ln = lane;
+      per_window(wbeg, min(end, wbeg + kWin), [st, wbeg, ln](uint32_t u) {
+        const uint32_t ul = u - (wbeg >> 4);
+        const uint4 v = *reinterpret_cast<const uint4*>(st + (ul * 32 + ((ln + ul) & 31)) * 16);
+        Unit16 q;
+        q.w[0] = v.x; q.w[1] = v.y; q.w[2] = v.z; q.w[3] = v.w;
+        return q;
+      });
+      __syncwarp();  // everyone is done with this stage before it is overwritten
+    }
+    cp_async_wait<0>();
+  }
+};
 template <int STAGES, class F>
 __device__ __forceinline__ void tiled_windows(const uint8_t* body, uint32_t end, uint8_t* warp_smem, F&& per_window) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t padded = (end + 15u) & ~15u;
-  uint32_t maxlen = end;
-#pragma unroll
-  for (int d = 16; d; d >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, d));
-  const uint32_t n_win = (maxlen + kWin - 1) / kWin;
-  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(warp_smem);
-  // prologue
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; s++) {
-    if ((uint32_t)s < n_win) issue_window(smem0 + s * kStageBytes, body, padded, s, lane);
-    cp_async_commit();
-  }
-  for (uint32_t w = 0; w < n_win; w++) {
-    const uint32_t nxt = w + STAGES - 1;
-    if (nxt < n_win) issue_window(smem0 + (nxt % STAGES) * kStageBytes, body, padded, nxt, lane);
-    cp_async_commit();
-    cp_async_wait<STAGES - 1>();
-    __syncwarp();
-    const uint8_t* st = warp_smem + (w % STAGES) * kStageBytes;
-    const uint32_t wbeg = w * kWin;
-    per_window(wbeg, min(end, wbeg + kWin), [&](uint32_t u) {
-      const uint32_t ul = u - (wbeg >> 4);
-      const uint4 v = *reinterpret_cast<const uint4*>(st + (ul * 32 + ((lane + ul) & 31)) * 16);
-      Unit16 q;
-      q.w[0] = v.x; q.w[1] = v.y; q.w[2] = v.z; q.w[3] = v.w;
-      return q;
-    });
-    __syncwarp();  // everyone is done with this stage before it is overwritten
-  }
-  cp_async_wait<0>();
+  WindowPipe<STAGES> pipe;
+  pipe.start(body, end, warp_smem);
+  pipe.run(per_window);
 }
 
 // Parse bytes [begin, end) (begin < 16) of 32 spans with machine `m`, one span per lane.
-template <int STAGES = kStages, bool EVSYNC = false, class M>
-__device__ __forceinline__ void feed_tiled(M& m, const uint8_t* body, uint32_t begin, uint32_t end, uint8_t* warp_smem) {
+template <bool EVSYNC, int STAGES, class M>
+__device__ __forceinline__ void feed_pipe(M& m, WindowPipe<STAGES>& pipe, uint32_t begin) {
   uint32_t pos = begin;
-  tiled_windows<STAGES>(body, end, warp_smem, [&](uint32_t wbeg, uint32_t lim, auto&& load) {
+  const uint32_t end = pipe.end;
+  pipe.run([&](uint32_t wbeg, uint32_t lim, auto&& load) {
     if constexpr (EVSYNC) {
       // special-byte masks of this window's units, computed up front with the warp converged (inside the parse loop the
       // lanes cross unit boundaries at different iterations, so the same code would run ~7 lanes wide)
@@ -284,6 +304,12 @@ __device__ __forceinline__ void feed_tiled(M& m, const uint8_t* body, uint32_t b
     if (m.dead()) pos = end;  // nothing further can change the verdict
   });
 }
+template <int STAGES = kStages, bool EVSYNC = false, class M>
+__device__ __forceinline__ void feed_tiled(M& m, const uint8_t* body, uint32_t begin, uint32_t end, uint8_t* warp_smem) {
+  WindowPipe<STAGES> pipe;
+  pipe.start(body, end, warp_smem);
+  feed_pipe<EVSYNC>(m, pipe, begin);
+}
 
 __device__ __forceinline__ unsigned long long fnv1a64(const uint8_t* p, uint32_t n) {
   unsigned long long h = 0xcbf29ce484222325ull;
@@ -296,9 +322,9 @@ __device__ bool model_equals(const uint8_t* body, const JsonCold& m, const uint8
   const uint8_t* p = body + m.m_start;
   if (!m.m_esc) {
     if (m.m_rawlen != nlen) return false;
-    for (uint32_t i = 0; i < nlen; i++)
-      if (p[i] != name[i]) return false;
-    return true;
+    uint32_t diff = 0;  // no early exit: the loads of all bytes are in flight together
+    for (uint32_t i = 0; i < nlen; i++) diff |= (uint32_t)(p[i] ^ name[i]);
+    return diff == 0;
   }
   uint32_t k = 0;
   bool ok = true;
@@ -322,34 +348,46 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_request_
 
   uint32_t stack_words[kStackWords];  // local memory, touched only beyond 32 levels of nesting
   __shared__ __align__(16) JsonSmem<true, false> json_smem;
-  const JsonTables tabs = json_smem.stage();
-  JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
-  JsonT m;
-  m.init(K_REQ, body, stack_words, &cold, tabs);
-  feed_tiled<kStages, EVSYNC>(m, body, 0, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
-  if (!live) return;
+  const JsonTables tabs = json_smem.stage_async();
+  WindowPipe<kStages> pipe;
+  pipe.start(body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
 
-  uint8_t reason = ARKS_R_OK, flags = 0, claimer = 0;
-  int32_t tok = -1, qos = -1, slot = -1;
-  do {
-    if (!m.ok_at_end()) { reason = ARKS_R_REQUEST_BODY; break; }           // handle_request.go:97-104
-    if (cold.m_rawlen == 0) { reason = ARKS_R_NO_MODEL; break; }              // :106-115
-    // GetQosByToken: first ArksToken whose spec.token equals the bearer      arks_impl.go:303-338
+  // GetQosByToken: first ArksToken whose spec.token equals the bearer      arks_impl.go:303-338
+  // A chain of dependent global loads (token bytes -> hash slot -> token string); it does not need the body, so it runs
+  // here, while the automaton tables and the first body windows are still in flight.
+  int32_t tok = -1;
+  if (live) {
     const uint8_t* tk = B.tokens + B.token_off[i];
-    uint32_t tkl = B.token_off[i + 1] - B.token_off[i];
-    unsigned long long h = fnv1a64(tk, tkl);
+    const uint32_t tkl = B.token_off[i + 1] - B.token_off[i];
+    const unsigned long long h = fnv1a64(tk, tkl);
     uint32_t s = (uint32_t)h & T.tok_mask;
     for (;;) {
       TokSlot e = T.tok_slots[s];
       if (e.tok < 0) break;
       if (e.hash == h && T.tok_str_len[e.tok] == tkl) {
         const uint8_t* q = T.pool + T.tok_str_off[e.tok];
-        bool eq = true;
-        for (uint32_t k = 0; k < tkl; k++) eq &= q[k] == tk[k];
-        if (eq) { tok = e.tok; break; }
+        uint32_t diff = 0;
+        for (uint32_t k = 0; k < tkl; k++) diff |= (uint32_t)(q[k] ^ tk[k]);
+        if (diff == 0) { tok = e.tok; break; }
       }
       s = (s + 1) & T.tok_mask;
     }
+  }
+  cp_async_wait<kStages - 1>();  // the table group is the oldest one
+  __syncthreads();
+
+  JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
+  JsonT m;
+  m.init(K_REQ, body, stack_words, &cold, tabs);
+  feed_pipe<EVSYNC>(m, pipe, 0);
+  if (!live) return;
+
+  uint8_t reason = ARKS_R_OK, flags = 0, claimer = 0;
+  int32_t qos = -1, slot = -1, tok_seen = -1;  // the token is only reported once the decision reached GetQosByToken
+  do {
+    if (!m.ok_at_end()) { reason = ARKS_R_REQUEST_BODY; break; }           // handle_request.go:97-104
+    if (cold.m_rawlen == 0) { reason = ARKS_R_NO_MODEL; break; }              // :106-115
+    tok_seen = tok;
     if (tok < 0) { reason = ARKS_R_TOKEN_NOT_FOUND; break; }
     for (uint32_t q = T.tok_qos_off[tok]; q < T.tok_qos_off[tok + 1]; q++)
       if (model_equals(body, cold, T.pool + T.qos_model_off[q], T.qos_model_len[q])) { qos = (int32_t)q; break; }
@@ -381,7 +419,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_request_
   B.st_reason[i] = reason;
   B.st_flags[i] = flags | (claimer << 7);
   B.st_qos[i] = qos;
-  B.st_tok[i] = tok;
+  B.st_tok[i] = tok_seen;
   B.gslot[i] = slot;
 }
 
@@ -562,30 +600,47 @@ __device__ __forceinline__ void warp_agg_add(long long* addr, long long v, bool 
   if ((int)(threadIdx.x & 31) == leader) atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)sum);
 }
 
-// A11 for one response per lane (all 32 lanes must call): doTokenRateLimit / doTokenQuotaLimit and the result row.
-__device__ __forceinline__ void account_usage(const DevTables& T, const RespDev& B, uint32_t i, bool live, int32_t qos, uint8_t reason,
-                                              uint8_t counted, long long u0, long long u1, long long u2) {
-  // doTokenRateLimit: += total on every token-type entry (check.go:47-59). Warp-aggregated per address.
-  int32_t qt = ARKS_QUOTA_NONE;
-  uint32_t nt[2] = {0, 0};
-  if (counted) {
-    for (uint32_t j = T.qos_rl_off[qos]; j < T.qos_rl_off[qos + 1]; j++) {
-      int rule = T.rl_rule[j];
-      if (rule >= 2) nt[rule - 2]++;
-    }
-    qt = T.qos_quota[qos];
+// What A11 needs to know about a qos entry: how many of its rate-limit rules are tpm / tpd and how many items of each
+// type its quota has. Two levels of dependent global loads, fetched while the first body windows are in flight.
+struct QosAcct {
+  int32_t qt;        // quota index, ARKS_QUOTA_NONE or ARKS_QUOTA_MISSING
+  uint32_t nt[2];    // rules of type tpm, tpd
+  uint32_t nq[3];    // quota items of type prompt, response, total
+};
+__device__ __forceinline__ QosAcct load_qos_acct(const DevTables& T, int32_t qos, bool live) {
+  QosAcct a;
+  a.qt = ARKS_QUOTA_NONE;
+  a.nt[0] = a.nt[1] = 0;
+  a.nq[0] = a.nq[1] = a.nq[2] = 0;
+  if (!live) return a;
+  for (uint32_t j = T.qos_rl_off[qos]; j < T.qos_rl_off[qos + 1]; j++) {
+    const int rule = T.rl_rule[j];
+    if (rule >= 2) a.nt[rule - 2]++;
   }
+  a.qt = T.qos_quota[qos];
+  if (a.qt >= 0)
+    for (uint32_t j = T.quota_item_off[a.qt]; j < T.quota_item_off[a.qt + 1]; j++) {
+      const int ty = T.qitem_type[j];
+      a.nq[0] += ty == 0; a.nq[1] += ty == 1; a.nq[2] += ty == 2;
+    }
+  return a;
+}
+
+// A11 for one response per lane (all 32 lanes must call): doTokenRateLimit / doTokenQuotaLimit and the result row.
+__device__ __forceinline__ void account_usage(const DevTables& T, const RespDev& B, uint32_t i, bool live, int32_t qos, const QosAcct& acct,
+                                              uint8_t reason, uint8_t counted, long long u0, long long u1, long long u2) {
+  // doTokenRateLimit: += total on every token-type entry (check.go:47-59). Warp-aggregated per address.
+  const int32_t qt = counted ? acct.qt : ARKS_QUOTA_NONE;
 #pragma unroll
   for (int r = 0; r < 2; r++)
-    warp_agg_add(T.rate + (size_t)(2 + r) * T.n_qos + qos, u2 * (long long)nt[r], counted && nt[r]);
+    warp_agg_add(T.rate + (size_t)(2 + r) * T.n_qos + qos, u2 * (long long)acct.nt[r], counted && acct.nt[r]);
   // doTokenQuotaLimit: QosToQuotaRequests + IncrUsage (check.go:62-72, qosconfig/types.go:45-72)
   long long add[3] = {0, 0, 0};
   if (counted && qt == ARKS_QUOTA_MISSING) reason = ARKS_R_QUOTA_CONFIG_RESP;
   if (counted && qt >= 0) {
-    for (uint32_t j = T.quota_item_off[qt]; j < T.quota_item_off[qt + 1]; j++) {
-      int ty = T.qitem_type[j];
-      add[ty] += ty == 0 ? u0 : ty == 1 ? u1 : u2;
-    }
+    add[0] = u0 * (long long)acct.nq[0];
+    add[1] = u1 * (long long)acct.nq[1];
+    add[2] = u2 * (long long)acct.nq[2];
   }
 #pragma unroll
   for (int ty = 0; ty < 3; ty++)
@@ -666,6 +721,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response
   uint8_t reason = ARKS_R_OK, counted = 0;
   long long u0 = 0, u1 = 0, u2 = 0;
   int32_t qos = 0;
+  QosAcct acct;
   {
     const uint8_t* body = B.bodies + (live ? B.body_off[i] : 0);
     uint8_t fl = live ? B.flags[i] : ARKS_RESP_END_OF_STREAM;
@@ -674,13 +730,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response
     qos = live ? B.qos[i] : 0;
     uint32_t stack_words[kStackWords];  // local memory, touched only beyond 32 levels of nesting
     __shared__ __align__(16) JsonSmem<MODE != 2, MODE != 1> json_smem;
-    const JsonTables tabs = json_smem.stage();
+    const JsonTables tabs = json_smem.stage_async();
+    WindowPipe<kStages> pipe;
+    pipe.start(body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
+    acct = load_qos_acct(T, qos, live);  // global latency chain, hidden behind the copies issued above
+    cp_async_wait<kStages - 1>();        // the table group is the oldest one
+    __syncthreads();
     RespM<MODE> rm;
     const bool is_sse = MODE == 2 || (MODE == 0 && (fl & ARKS_RESP_STREAM));
     JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
     rm.init(is_sse, body, stack_words, &cold, tabs);
-    if constexpr (EVSYNC) feed_tiled<kStages, true>(rm.json(), body, 0, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
-    else feed_tiled(rm, body, 0, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
+    if constexpr (EVSYNC) feed_pipe<true>(rm.json(), pipe, 0);
+    else feed_pipe<false>(rm, pipe, 0);
     if (live) {
       if (is_sse) {  // handle_response.go:113-133, every chunk in isolation
         if (!rm.finish(len, u0, u1, u2)) reason = ARKS_R_STREAMING;
@@ -696,7 +757,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response
       counted = reason == ARKS_R_OK && u2 != 0;  // :186
     }
   }
-  account_usage(T, B, i, live, qos, reason, counted, u0, u1, u2);
+  account_usage(T, B, i, live, qos, acct, reason, counted, u0, u1, u2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -722,11 +783,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, ARKS_SSE_MINBLK) scan_sse
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool live = i < B.n;
   uint8_t* wsmem = smem + warp * (kSseStages * kStageBytes);
-  const JsonTables tabs = json_smem.stage();
+  const JsonTables tabs = json_smem.stage_async();
   const uint32_t chunk_off = live ? B.body_off[i] : 0;
   const uint32_t len = live ? B.body_len[i] : 0;
   const uint8_t* body = B.bodies + chunk_off;
   const int32_t qos = live ? B.qos[i] : 0;
+  WindowPipe<kSseStages> pipe1;
+  pipe1.start(body, len, wsmem);
+  const QosAcct acct = load_qos_acct(T, qos, live);  // global latency chain, hidden behind the copies issued above
+  cp_async_wait<kSseStages - 1>();                   // the table group is the oldest one
+  __syncthreads();
   uint32_t stack_words[kStackWords];
   JsonCold cold;
   s_best[warp][lane] = 0;
@@ -745,7 +811,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, ARKS_SSE_MINBLK) scan_sse
       else sp.flags |= SseSplit::F_IRREGULAR;
       seq++;
     };
-    tiled_windows<kSseStages>(body, len, wsmem, [&](uint32_t wbeg, uint32_t lim, auto&& load) {
+    pipe1.run([&](uint32_t wbeg, uint32_t lim, auto&& load) {
       for (uint32_t ub = wbeg; ub < lim; ub += 16) {
         const Unit16 q = load(ub >> 4);
         sp.unit(ub, lim - ub, q.w[0], q.w[1], q.w[2], q.w[3], emit);
@@ -806,7 +872,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, ARKS_SSE_MINBLK) scan_sse
     counted = reason == ARKS_R_OK && u2 != 0;  // handle_response.go:186
   }
   __syncwarp();
-  account_usage(T, B, i, live, qos, reason, counted, u0, u1, u2);
+  account_usage(T, B, i, live, qos, acct, reason, counted, u0, u1, u2);
 }
 
 // quota[i] += reduced[i] - own[i]; own[i] = 0  — applies what the OTHER GPUs added since the last fold

@@ -59,6 +59,18 @@ ARKS_HD const char* xkey_str(int id) {
   }
 }
 ARKS_HD constexpr int xkey_len(int id) { return id == 0 ? 13 : id == 1 ? 17 : id == 2 ? 12 : id == 3 ? 5 : id == 4 ? 7 : 5; }
+// bytes [8w, 8w+8) of a key literal as a little-endian word (zero padded): exact comparison against immediates
+ARKS_HD constexpr uint64_t lit_word(const char* s, int n, int w) {
+  uint64_t v = 0;
+  for (int i = 0; i < 8; i++)
+    if (8 * w + i < n) v |= (uint64_t)(uint8_t)s[8 * w + i] << (8 * i);
+  return v;
+}
+ARKS_HD constexpr uint64_t xkey_word(int id, int w) {
+  return id == 0 ? lit_word("prompt_tokens", 13, w) : id == 1 ? lit_word("completion_tokens", 17, w)
+       : id == 2 ? lit_word("total_tokens", 12, w) : id == 3 ? lit_word("error", 5, w)
+       : id == 4 ? lit_word("choices", 7, w) : lit_word("usage", 5, w);
+}
 static constexpr uint64_t X_PROMPT = xhash_lit("prompt_tokens", 13);
 static constexpr uint64_t X_COMPL = xhash_lit("completion_tokens", 17);
 static constexpr uint64_t X_TOTAL = xhash_lit("total_tokens", 12);
@@ -158,9 +170,26 @@ static ARKS_OUTLINE bool exact_verify_span(const uint8_t* p, uint32_t n, uint32_
   int L = xkey_len(id);
   if (!has_esc) {
     if ((int)n != L) return false;
-    for (int i = 0; i < L; i++)
-      if (p[i] != (uint8_t)s[i]) return false;
-    return true;
+    // all (<= 17) byte loads are issued together and compared against immediates: a loop with an early exit makes
+    // every byte wait for the previous one's round trip to L2 (the key was hashed on the fly, this only confirms it)
+    uint64_t w0 = 0, w1 = 0, w2 = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int i = 0; i < 17; i++) {
+      const uint64_t b = i < L ? (uint64_t)p[i] : 0ull;
+      if (i < 8) w0 |= b << (8 * i);
+      else if (i < 16) w1 |= b << (8 * (i - 8));
+      else w2 |= b;
+    }
+    uint64_t d = 0;
+    switch (id) {
+#define ARKS_XK(ID) case ID: d = (w0 ^ xkey_word(ID, 0)) | (w1 ^ xkey_word(ID, 1)) | (w2 ^ xkey_word(ID, 2)); break;
+      ARKS_XK(0) ARKS_XK(1) ARKS_XK(2) ARKS_XK(3) ARKS_XK(4)
+      default: d = (w0 ^ xkey_word(5, 0)) | (w1 ^ xkey_word(5, 1)) | (w2 ^ xkey_word(5, 2)); break;
+#undef ARKS_XK
+    }
+    return d == 0;
   }
   int k = 0;
   bool ok = true;
