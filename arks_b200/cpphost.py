@@ -1,0 +1,168 @@
+"""ctypes view of the C++ host library (host/cpp/arks_host.{h,cc}): the compiled micro-batcher and ext_proc stream state
+machine that sit above the C ABI where the reference has its Go server. Python only drives it (tests, bench load
+generation); the batching, threading and waiting all happen in C++.
+
+`build(against=...)` links the host against a given provider of the C ABI: arks_b200/libarksgw.so (the product) or, in
+CPU-only tests, tests/_build/libarksgw_shim.so (the oracle behind the same three entry points)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "host", "cpp", "arks_host.cc")
+HDR = os.path.join(ROOT, "host", "cpp", "arks_host.h")
+LIB = os.path.join(ROOT, "host", "cpp", "libarkshost.so")
+
+
+class RequestDecision(C.Structure):
+    _fields_ = [("reason", C.c_uint8), ("detail", C.c_uint8), ("flags", C.c_uint8), ("qos", C.c_int32), ("token", C.c_int32),
+                ("pick", C.c_int32), ("cur_usage", C.c_int64), ("limit_max", C.c_int64), ("cycle", C.c_uint64),
+                ("index", C.c_uint32), ("now_unix", C.c_int64)]
+
+
+class ResponseDecision(C.Structure):
+    _fields_ = [("reason", C.c_uint8), ("counted", C.c_uint8), ("usage", C.c_int64 * 3), ("cycle", C.c_uint64),
+                ("index", C.c_uint32), ("now_unix", C.c_int64)]
+
+
+class BatcherStats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("cycles", "request_batches", "response_batches", "requests", "responses",
+                                          "max_request_batch", "max_response_batch")]
+
+
+REQ_DTYPE = np.dtype(RequestDecision)
+RESP_DTYPE = np.dtype(ResponseDecision)
+EXPORTED = ["arks_host_create", "arks_host_destroy", "arks_host_set_fixed_clock", "arks_host_request", "arks_host_response",
+            "arks_host_stats", "arks_host_run_requests", "arks_host_run_responses", "arks_host_open_loop_requests",
+            "arks_host_stream_transcript"]
+
+
+def build(out: str = LIB, against: str = None, force: bool = False) -> str:
+    """g++ the host library, linked against `against` (default arks_b200/libarksgw.so)."""
+    against = against or os.path.join(ROOT, "arks_b200", "libarksgw.so")
+    srcs = [SRC, HDR, os.path.join(ROOT, "include", "arks_gateway.h"), against]
+    if force or not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        d, f = os.path.split(against)
+        assert f.startswith("lib") and f.endswith(".so")
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-shared", "-fPIC", "-pthread", "-Wall", "-o", out, SRC,
+                               "-L" + d, "-l" + f[3:-3],
+                               "-Wl,-rpath,$ORIGIN/" + os.path.relpath(d, os.path.dirname(out))])  # relocatable with the tree
+    return out
+
+
+def load(path: str = LIB):
+    L = C.CDLL(path)
+    vp, u8p, u32p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+    L.arks_host_create.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+    L.arks_host_destroy.argtypes = [vp]
+    L.arks_host_destroy.restype = None
+    L.arks_host_set_fixed_clock.argtypes = [vp, C.c_int64]
+    L.arks_host_set_fixed_clock.restype = None
+    L.arks_host_request.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint64, C.POINTER(RequestDecision)]
+    L.arks_host_response.argtypes = [vp, C.c_int32, C.c_char_p, C.c_uint32, C.c_uint8, C.POINTER(ResponseDecision)]
+    L.arks_host_stats.argtypes = [vp, C.POINTER(BatcherStats)]
+    L.arks_host_stats.restype = None
+    L.arks_host_run_requests.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.arks_host_run_requests.restype = C.c_int64
+    L.arks_host_run_responses.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
+    L.arks_host_run_responses.restype = C.c_int64
+    L.arks_host_open_loop_requests.argtypes = [vp, C.c_uint32, C.c_double, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.arks_host_open_loop_requests.restype = C.c_int64
+    cpp = C.POINTER(C.c_char_p)
+    L.arks_host_stream_transcript.argtypes = [vp, cpp, C.c_uint32, cpp, cpp, C.c_uint32, cpp, cpp, C.c_uint32, C.c_char_p,
+                                              C.c_uint32, cpp, cpp, C.c_uint32, C.POINTER(C.c_char_p), u32p, C.c_uint32,
+                                              C.c_uint64, C.c_char_p, C.c_uint32]
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Batcher:
+    """arks_host::Batcher over an arks_ctx handle (Gateway._h, or the CPU shim's context in tests)."""
+
+    def __init__(self, lib, ctx_handle, max_batch=4096, max_bytes=16 << 20, linger_us=0, max_inflight=1):
+        self.L = lib
+        h = C.c_void_p()
+        rc = lib.arks_host_create(ctx_handle, max_batch, max_bytes, linger_us, max_inflight, C.byref(h))
+        if rc:
+            raise RuntimeError(f"arks_host_create: {rc}")
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self.L.arks_host_destroy(self._h)
+            self._h = None
+
+    def set_fixed_clock(self, now: int):
+        self.L.arks_host_set_fixed_clock(self._h, int(now))
+
+    def request(self, token: bytes, body: bytes, pick_rand: int = 0) -> RequestDecision:
+        d = RequestDecision()
+        self.L.arks_host_request(self._h, token, len(token), body, len(body), pick_rand, C.byref(d))
+        return d
+
+    def response(self, qos: int, body: bytes, flags: int) -> ResponseDecision:
+        d = ResponseDecision()
+        self.L.arks_host_response(self._h, qos, body, len(body), flags, C.byref(d))
+        return d
+
+    def stats(self) -> dict:
+        s = BatcherStats()
+        self.L.arks_host_stats(self._h, C.byref(s))
+        return {k: int(getattr(s, k)) for k, _ in BatcherStats._fields_}
+
+    def run_requests(self, batch, threads: int):
+        """every row of an abi.RequestBatch as one blocking HandleRequestBody call, issued by `threads` C++ threads.
+        Returns (decisions as a structured array in row order, latency_ns per call, wall seconds)."""
+        out = np.zeros(batch.n, REQ_DTYPE)
+        lat = np.zeros(batch.n, np.int64)
+        bodies = np.ascontiguousarray(batch.bodies)
+        ns = self.L.arks_host_run_requests(self._h, batch.n, threads, _ptr(bodies), _ptr(batch.body_off), _ptr(batch.body_len),
+                                           _ptr(batch.tokens), _ptr(batch.token_off), _ptr(batch.pick_rand), _ptr(out), _ptr(lat))
+        return out, lat, ns * 1e-9
+
+    def open_loop_requests(self, batch, rate_per_s: float, producers: int = 4):
+        """rows of `batch` ARRIVE at rate_per_s (exponential gaps) through the asynchronous SubmitRequest, whether or not
+        earlier ones are answered; latency = decision handed over - scheduled arrival (no coordinated omission)."""
+        out = np.zeros(batch.n, REQ_DTYPE)
+        lat = np.zeros(batch.n, np.int64)
+        bodies = np.ascontiguousarray(batch.bodies)
+        ns = self.L.arks_host_open_loop_requests(self._h, batch.n, float(rate_per_s), producers, _ptr(bodies), _ptr(batch.body_off),
+                                                 _ptr(batch.body_len), _ptr(batch.tokens), _ptr(batch.token_off),
+                                                 _ptr(batch.pick_rand), _ptr(out), _ptr(lat))
+        return out, lat, ns * 1e-9
+
+    def run_responses(self, batch, threads: int):
+        out = np.zeros(batch.n, RESP_DTYPE)
+        lat = np.zeros(batch.n, np.int64)
+        bodies = np.ascontiguousarray(batch.bodies)
+        ns = self.L.arks_host_run_responses(self._h, batch.n, threads, _ptr(bodies), _ptr(batch.body_off), _ptr(batch.body_len),
+                                            _ptr(batch.qos), _ptr(batch.flags), _ptr(out), _ptr(lat))
+        return out, lat, ns * 1e-9
+
+    def stream_transcript(self, names, req_headers, req_body: bytes, resp_headers, resp_chunks, pick_rand: int = 0) -> str:
+        """drive one ext_proc stream through arks_host::StreamProcessor; `names` = (qos_model, token_namespace, token_user)"""
+        def arr(strs):
+            a = (C.c_char_p * max(len(strs), 1))()
+            for i, s in enumerate(strs):
+                a[i] = s if isinstance(s, bytes) else s.encode()
+            return a
+        qm, tn, tu = names
+        rk, rv = arr([k for k, _ in req_headers]), arr([v for _, v in req_headers])
+        pk, pv = arr([k for k, _ in resp_headers]), arr([v for _, v in resp_headers])
+        chunks = (C.c_char_p * max(len(resp_chunks), 1))()
+        lens = (C.c_uint32 * max(len(resp_chunks), 1))()
+        for i, c in enumerate(resp_chunks):
+            chunks[i], lens[i] = c, len(c)
+        buf = C.create_string_buffer(1 << 20)
+        n = self.L.arks_host_stream_transcript(self._h, arr(qm), len(qm), arr(tn), arr(tu), len(tn), rk, rv, len(req_headers),
+                                               req_body, len(req_body), pk, pv, len(resp_headers), chunks, lens,
+                                               len(resp_chunks), pick_rand, buf, len(buf))
+        if n < 0:
+            raise RuntimeError("transcript buffer too small")
+        return buf.raw[:n].decode("latin1")

@@ -1100,6 +1100,14 @@ void arks_destroy(arks_ctx* ctx) {
 void* arks_stream(arks_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t arks_launch_count(const arks_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+void* arks_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void arks_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 // ---- config plane -------------------------------------------------------------------------------
 int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
   if (!ctx || !t) return ARKS_E_INVALID_ARG;

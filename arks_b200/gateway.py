@@ -87,7 +87,7 @@ EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/t
     "arks_submit_response_batch", "arks_stage_request_batch", "arks_run_request_batch",
     "arks_fetch_request_result", "arks_stage_response_batch", "arks_run_response_batch",
     "arks_fetch_response_result", "arks_submit_request_async", "arks_wait_request", "arks_submit_response_async",
-    "arks_wait_response", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_snapshot_quota",
+    "arks_wait_response", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_alloc_pinned", "arks_free_pinned", "arks_snapshot_quota",
     "arks_set_quota_usage", "arks_incr_quota_usage", "arks_snapshot_rate", "arks_take_quota_delta",
     "arks_apply_quota_delta", "arks_quota_delta_dev", "arks_fold_quota_delta_dev", "arks_enable_quota_sharing",
     "arks_export_quota_delta_dev",

@@ -335,6 +335,41 @@ def run_b200(args):
                 now += STEP_S
             ts = np.sort(np.array(ts[20:])) * 1e6
             latency[str(bs)] = {"p50_us": float(ts[len(ts) // 2]), "p99_us": float(ts[int(len(ts) * 0.99)])}
+    # ---- the same through the compiled host: N concurrent ext_proc streams, each one blocking HandleRequestBody call at a
+    # time, micro-batched by host/cpp's Batcher (per-call latency seen by a stream thread, C++ clock) --------------------
+    streams_lat, open_lat = {}, {}
+    if rank == 0:
+        from arks_b200 import cpphost
+        hb = cpphost.Batcher(cpphost.load(cpphost.build()), g._h, max_batch=8192, max_bytes=16 << 20)
+        hb.set_fixed_clock(now)
+        for streams in (1, 64):
+            n_calls = {1: 2000, 64: 40000}[streams]
+            load = w.request_batch(n_calls, now, seed=7100 + streams, body_size=BODY, n_templates=64)
+            before = hb.stats()
+            _, lat_ns, wall = hb.run_requests(load, threads=streams)
+            after = hb.stats()
+            lat_us = np.sort(lat_ns[n_calls // 10:]) / 1e3
+            nb = after["request_batches"] - before["request_batches"]
+            streams_lat[str(streams)] = {"p50_us": float(lat_us[len(lat_us) // 2]), "p99_us": float(lat_us[int(len(lat_us) * 0.99)]),
+                                         "req_per_s": n_calls / wall, "mean_batch": n_calls / max(nb, 1)}
+            now += STEP_S
+            hb.set_fixed_clock(now)
+        # open loop: requests ARRIVE at a fixed rate through the asynchronous API; 1.25 M/s per GPU is the share of one GPU
+        # in BASELINE's "10 M req/s on 8 GPUs with p99 < 200 us" operating point
+        for rate in (250_000, 1_250_000):
+            n_calls = int(rate * 0.15)
+            load = w.request_batch(n_calls, now, seed=7200 + rate % 97, body_size=BODY, n_templates=64)
+            before = hb.stats()
+            dec, lat_ns, wall = hb.open_loop_requests(load, rate_per_s=rate, producers=8)
+            after = hb.stats()
+            lat_us = np.sort(lat_ns[n_calls // 10:]) / 1e3
+            nb = after["request_batches"] - before["request_batches"]
+            open_lat[str(rate)] = {"p50_us": float(lat_us[len(lat_us) // 2]), "p99_us": float(lat_us[int(len(lat_us) * 0.99)]),
+                                   "achieved_req_per_s": n_calls / wall, "mean_batch": n_calls / max(nb, 1),
+                                   "admitted": int((dec["reason"] == 0).sum())}
+            now += STEP_S
+            hb.set_fixed_clock(now)
+        hb.close()
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s * 1e3], device=f"cuda:{local}", dtype=torch.float64)
@@ -378,7 +413,11 @@ def run_b200(args):
                 "ms_per_step": 1e3 * e2e_s / args.steps,
                 "note": "pinned host buffers; asynchronous submits, two batches in flight; PCIe-bound"},
         "latency_us": {"what": "one synchronous request micro-batch through the C ABI (H2D + 2 kernels + D2H), host wall clock",
-                       "by_batch_size": latency},
+                       "by_batch_size": latency,
+                       "by_concurrent_streams": streams_lat,
+                       "open_loop_by_arrival_rate": open_lat,
+                       "open_loop_what": "requests arrive at the given rate (exponential gaps, 8 producer threads) through host/cpp Batcher::SubmitRequest; latency = decision callback - scheduled arrival",
+                       "streams_what": "N stream threads, one blocking HandleRequestBody at a time each, through host/cpp Batcher (C++); per-call latency"},
         "gpu_launches": int(launches),
         "kernels_ms": {"scan_request": float(np.mean(scan_ms)), "limit_admit": float(np.mean(admit_ms)),
                        "scan_response": float(np.mean(resp_ms))},

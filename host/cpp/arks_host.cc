@@ -1,0 +1,668 @@
+// arks_host.cc — see arks_host.h. Build: g++ -O2 -std=c++20 -shared -fPIC -pthread, linked against libarksgw.so
+// (no CUDA headers or runtime needed here: the C ABI is the only thing this file knows about the device).
+#include "arks_host.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
+namespace arks_host {
+
+namespace {
+
+constexpr uint8_t kReasonHostError = 255;
+constexpr int kSlots = 4;           // staging slots of the library: batches in flight on the device
+constexpr int kBlocks = kSlots + 2; // host staging blocks per kind: in flight + one open + one being handed back
+
+inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+template <class T>
+T* pinned(size_t n) {  // page-locked so the library's cudaMemcpyAsync is a real DMA; falls back to pageable memory
+  void* p = arks_alloc_pinned(n * sizeof(T) + 64);
+  if (!p) p = aligned_alloc(64, (n * sizeof(T) + 127) & ~size_t(63));
+  return static_cast<T*>(p);
+}
+
+// One staging block: rows are reserved under the batcher mutex, filled by their owners without it.
+struct Block {
+  uint8_t* bodies = nullptr;
+  uint32_t *body_off = nullptr, *body_len = nullptr;
+  uint8_t* tokens = nullptr;      // requests
+  uint32_t* token_off = nullptr;  // n + 1
+  uint64_t* rnd = nullptr;
+  int32_t* qos = nullptr;         // responses
+  uint8_t* flags = nullptr;
+  // per-row completion
+  RequestCallback* rcb = nullptr;
+  ResponseCallback* pcb = nullptr;
+  void** user = nullptr;
+  // results
+  uint8_t *reason = nullptr, *detail = nullptr, *rflags = nullptr, *counted = nullptr;
+  int32_t *rqos = nullptr, *rtoken = nullptr, *rpick = nullptr;
+  int64_t *cur_usage = nullptr, *limit_max = nullptr, *usage = nullptr;
+  // bookkeeping
+  uint32_t n = 0;
+  size_t bytes = 0, tok_bytes = 0;
+  std::atomic<uint32_t> filled{0};  // rows whose owner finished copying
+  uint64_t cycle = 0;
+  int64_t now = 0;
+};
+
+struct InFlight {
+  Block* req;  // either may be null
+  Block* resp;
+  int slot;
+  int rc_req, rc_resp;
+};
+
+// what a blocking call parks on
+struct Parked {
+  std::atomic<uint32_t> ready{0};
+  RequestDecision rd{};
+  ResponseDecision pd{};
+};
+void wake_request(void* user, const RequestDecision& d) {
+  Parked* p = static_cast<Parked*>(user);
+  p->rd = d;
+  p->ready.store(1, std::memory_order_release);
+  p->ready.notify_one();
+}
+void wake_response(void* user, const ResponseDecision& d) {
+  Parked* p = static_cast<Parked*>(user);
+  p->pd = d;
+  p->ready.store(1, std::memory_order_release);
+  p->ready.notify_one();
+}
+
+}  // namespace
+
+struct Batcher::Impl {
+  arks_ctx* ctx;
+  BatcherOptions opt;
+  size_t tok_cap;
+  Block req_blk[kBlocks], resp_blk[kBlocks];
+  std::vector<Block*> free_req, free_resp;  // blocks nobody uses
+  Block *open_req = nullptr, *open_resp = nullptr;
+  std::deque<InFlight> inflight;            // submitted, not completed (FIFO == device order)
+  bool slot_busy[kSlots] = {false, false, false, false};
+  mutable std::mutex mu;
+  std::condition_variable cv_work, cv_space, cv_done;
+  bool stop = false;
+  uint64_t cycle = 0;
+  int64_t (*clock)(void*) = nullptr;
+  void* clock_arg = nullptr;
+  BatcherStats st{};
+  std::thread dispatcher, completer;
+
+  void alloc(Block& b, bool is_req) {
+    const uint32_t m = opt.max_batch;
+    b.bodies = pinned<uint8_t>(opt.max_bytes + 16);
+    b.body_off = pinned<uint32_t>(m);
+    b.body_len = pinned<uint32_t>(m);
+    b.user = new void*[m];
+    if (is_req) {
+      b.tokens = pinned<uint8_t>(tok_cap);
+      b.token_off = pinned<uint32_t>(m + 1);
+      b.rnd = pinned<uint64_t>(m);
+      b.rcb = new RequestCallback[m];
+      b.reason = new uint8_t[m]; b.detail = new uint8_t[m]; b.rflags = new uint8_t[m];
+      b.rqos = new int32_t[m]; b.rtoken = new int32_t[m]; b.rpick = new int32_t[m];
+      b.cur_usage = new int64_t[m]; b.limit_max = new int64_t[m];
+    } else {
+      b.qos = pinned<int32_t>(m);
+      b.flags = pinned<uint8_t>(m);
+      b.pcb = new ResponseCallback[m];
+      b.reason = new uint8_t[m]; b.counted = new uint8_t[m]; b.usage = new int64_t[3 * (size_t)m];
+    }
+  }
+
+  static void wait_filled(Block& b) {
+    while (b.filled.load(std::memory_order_acquire) != b.n) std::this_thread::yield();
+  }
+  int free_slot() const {  // -1 while max_inflight batches are already queued on the device
+    int busy = 0, first = -1;
+    for (int k = 0; k < kSlots; k++) {
+      if (slot_busy[k]) busy++;
+      else if (first < 0) first = k;
+    }
+    return busy < (int)opt.max_inflight ? first : -1;
+  }
+
+  // Thread 1: closes the open blocks and queues them on the device (asynchronous submits, one staging slot each).
+  void dispatch_loop() {
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      cv_work.wait(lk, [&] { return stop || ((open_req->n || open_resp->n) && free_slot() >= 0 && !free_req.empty() && !free_resp.empty()); });
+      if (stop && !open_req->n && !open_resp->n) return;
+      if (opt.linger_us) {  // give concurrent streams a moment to join the cycle
+        lk.unlock();
+        std::this_thread::sleep_for(std::chrono::microseconds(opt.linger_us));
+        lk.lock();
+      }
+      InFlight f{nullptr, nullptr, free_slot(), 0, 0};
+      slot_busy[f.slot] = true;
+      if (open_req->n) { f.req = open_req; open_req = free_req.back(); free_req.pop_back(); }
+      if (open_resp->n) { f.resp = open_resp; open_resp = free_resp.back(); free_resp.pop_back(); }
+      const uint64_t cyc = cycle++;
+      const int64_t now = clock ? clock(clock_arg) : (int64_t)time(nullptr);
+      lk.unlock();
+      cv_space.notify_all();
+      arks_select_slot(ctx, f.slot);
+      if (f.req) {
+        Block& b = *f.req;
+        wait_filled(b);
+        b.cycle = cyc; b.now = now;
+        b.token_off[b.n] = (uint32_t)b.tok_bytes;
+        arks_request_batch rb{};
+        rb.n = b.n; rb.bodies = b.bodies; rb.body_off = b.body_off; rb.body_len = b.body_len; rb.bodies_bytes = b.bytes;
+        rb.tokens = b.tokens; rb.token_off = b.token_off; rb.pick_rand = b.rnd; rb.now_unix = now;
+        f.rc_req = arks_submit_request_async(ctx, &rb);
+      }
+      if (f.resp) {
+        Block& b = *f.resp;
+        wait_filled(b);
+        b.cycle = cyc; b.now = now;
+        arks_response_batch rb{};
+        rb.n = b.n; rb.bodies = b.bodies; rb.body_off = b.body_off; rb.body_len = b.body_len; rb.bodies_bytes = b.bytes;
+        rb.qos = b.qos; rb.flags = b.flags; rb.now_unix = now;
+        f.rc_resp = arks_submit_response_async(ctx, &rb);
+      }
+      lk.lock();
+      inflight.push_back(f);
+      cv_done.notify_one();
+    }
+  }
+
+  // Thread 2: waits for the oldest batch, hands every row its decision, recycles block and slot.
+  void complete_loop() {
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      cv_done.wait(lk, [&] { return !inflight.empty() || (stop && !open_req->n && !open_resp->n); });
+      if (inflight.empty()) {
+        bool busy = false;
+        for (int k = 0; k < kSlots; k++) busy |= slot_busy[k];
+        if (!busy) return;  // stop requested, nothing queued, nothing being submitted
+        cv_done.wait_for(lk, std::chrono::milliseconds(1));
+        continue;
+      }
+      InFlight f = inflight.front();
+      inflight.pop_front();
+      lk.unlock();
+      if (f.req) {
+        Block& b = *f.req;
+        int rc = f.rc_req;
+        if (rc == 0) {
+          arks_request_result rr{b.reason, b.detail, b.rflags, b.rqos, b.rtoken, b.rpick, b.cur_usage, b.limit_max};
+          rc = arks_wait_request(ctx, f.slot, &rr);
+        }
+        for (uint32_t i = 0; i < b.n; i++) {
+          RequestDecision d{};
+          if (rc) d.reason = kReasonHostError;
+          else {
+            d.reason = b.reason[i]; d.detail = b.detail[i]; d.flags = b.rflags[i];
+            d.qos = b.rqos[i]; d.token = b.rtoken[i]; d.pick = b.rpick[i];
+            d.cur_usage = b.cur_usage[i]; d.limit_max = b.limit_max[i];
+          }
+          d.cycle = b.cycle; d.index = i; d.now_unix = b.now;
+          b.rcb[i](b.user[i], d);
+        }
+      }
+      if (f.resp) {
+        Block& b = *f.resp;
+        int rc = f.rc_resp;
+        if (rc == 0) {
+          arks_response_result rr{b.reason, b.counted, b.usage};
+          rc = arks_wait_response(ctx, f.slot, &rr);
+        }
+        for (uint32_t i = 0; i < b.n; i++) {
+          ResponseDecision d{};
+          if (rc) d.reason = kReasonHostError;
+          else {
+            d.reason = b.reason[i]; d.counted = b.counted[i];
+            for (int k = 0; k < 3; k++) d.usage[k] = b.usage[3 * (size_t)i + k];
+          }
+          d.cycle = b.cycle; d.index = i; d.now_unix = b.now;
+          b.pcb[i](b.user[i], d);
+        }
+      }
+      lk.lock();
+      st.cycles++;
+      if (f.req) {
+        st.request_batches++; st.requests += f.req->n;
+        if (f.req->n > st.max_request_batch) st.max_request_batch = f.req->n;
+        f.req->n = 0; f.req->bytes = 0; f.req->tok_bytes = 0; f.req->filled.store(0, std::memory_order_relaxed);
+        free_req.push_back(f.req);
+      }
+      if (f.resp) {
+        st.response_batches++; st.responses += f.resp->n;
+        if (f.resp->n > st.max_response_batch) st.max_response_batch = f.resp->n;
+        f.resp->n = 0; f.resp->bytes = 0; f.resp->filled.store(0, std::memory_order_relaxed);
+        free_resp.push_back(f.resp);
+      }
+      slot_busy[f.slot] = false;
+      cv_work.notify_one();
+    }
+  }
+};
+
+Batcher::Batcher(arks_ctx* ctx, const BatcherOptions& opt) : p_(new Impl()) {
+  p_->ctx = ctx;
+  p_->opt = opt;
+  p_->tok_cap = (size_t)opt.max_batch * 256;
+  for (int k = 0; k < kBlocks; k++) {
+    p_->alloc(p_->req_blk[k], true);
+    p_->alloc(p_->resp_blk[k], false);
+    p_->free_req.push_back(&p_->req_blk[k]);
+    p_->free_resp.push_back(&p_->resp_blk[k]);
+  }
+  p_->open_req = p_->free_req.back(); p_->free_req.pop_back();
+  p_->open_resp = p_->free_resp.back(); p_->free_resp.pop_back();
+  p_->dispatcher = std::thread([this] { p_->dispatch_loop(); });
+  p_->completer = std::thread([this] { p_->complete_loop(); });
+}
+Batcher::~Batcher() {
+  {
+    std::lock_guard<std::mutex> g(p_->mu);
+    p_->stop = true;
+  }
+  p_->cv_work.notify_all();
+  p_->dispatcher.join();
+  p_->cv_done.notify_all();
+  p_->completer.join();
+  delete p_;  // staging blocks are left to the process (pinned host memory of a long-lived server object)
+}
+void Batcher::SetClock(int64_t (*clock)(void*), void* arg) {
+  std::lock_guard<std::mutex> g(p_->mu);
+  p_->clock = clock;
+  p_->clock_arg = arg;
+}
+BatcherStats Batcher::Stats() const {
+  std::lock_guard<std::mutex> g(p_->mu);
+  return p_->st;
+}
+
+bool Batcher::SubmitRequest(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user) {
+  Impl& I = *p_;
+  const size_t need = align16(body.size());
+  if (need > I.opt.max_bytes || token.size() > 255) return false;
+  std::unique_lock<std::mutex> lk(I.mu);
+  Block* b;
+  for (;;) {
+    b = I.open_req;
+    if (b->n < I.opt.max_batch && b->bytes + need <= I.opt.max_bytes && b->tok_bytes + token.size() <= I.tok_cap) break;
+    I.cv_work.notify_one();
+    I.cv_space.wait(lk);  // the open block is full: wait for the dispatcher to swap
+  }
+  const uint32_t row = b->n++;
+  const size_t off = b->bytes, toff = b->tok_bytes;
+  b->bytes += need;
+  b->tok_bytes += token.size();
+  b->body_off[row] = (uint32_t)off;
+  b->body_len[row] = (uint32_t)body.size();
+  b->token_off[row] = (uint32_t)toff;
+  b->rnd[row] = pick_rand;
+  b->rcb[row] = cb;
+  b->user[row] = user;
+  lk.unlock();
+  if (row == 0) I.cv_work.notify_one();
+  memcpy(b->bodies + off, body.data(), body.size());
+  memset(b->bodies + off + body.size(), 0, need - body.size());
+  memcpy(b->tokens + toff, token.data(), token.size());
+  b->filled.fetch_add(1, std::memory_order_release);
+  return true;
+}
+
+bool Batcher::SubmitResponse(int32_t qos, std::string_view body, uint8_t flags, ResponseCallback cb, void* user) {
+  Impl& I = *p_;
+  const size_t need = align16(body.size());
+  if (need > I.opt.max_bytes) return false;
+  std::unique_lock<std::mutex> lk(I.mu);
+  Block* b;
+  for (;;) {
+    b = I.open_resp;
+    if (b->n < I.opt.max_batch && b->bytes + need <= I.opt.max_bytes) break;
+    I.cv_work.notify_one();
+    I.cv_space.wait(lk);
+  }
+  const uint32_t row = b->n++;
+  const size_t off = b->bytes;
+  b->bytes += need;
+  b->body_off[row] = (uint32_t)off;
+  b->body_len[row] = (uint32_t)body.size();
+  b->qos[row] = qos;
+  b->flags[row] = flags;
+  b->pcb[row] = cb;
+  b->user[row] = user;
+  lk.unlock();
+  if (row == 0) I.cv_work.notify_one();
+  memcpy(b->bodies + off, body.data(), body.size());
+  memset(b->bodies + off + body.size(), 0, need - body.size());
+  b->filled.fetch_add(1, std::memory_order_release);
+  return true;
+}
+
+RequestDecision Batcher::HandleRequestBody(std::string_view token, std::string_view body, uint64_t pick_rand) {
+  Parked p;
+  if (!SubmitRequest(token, body, pick_rand, wake_request, &p)) {
+    RequestDecision d{};
+    d.reason = kReasonHostError;
+    return d;
+  }
+  p.ready.wait(0, std::memory_order_acquire);  // futex sleep until the completion thread hands the decision over
+  return p.rd;
+}
+ResponseDecision Batcher::HandleResponseBody(int32_t qos, std::string_view body, uint8_t flags) {
+  Parked p;
+  if (!SubmitResponse(qos, body, flags, wake_response, &p)) {
+    ResponseDecision d{};
+    d.reason = kReasonHostError;
+    return d;
+  }
+  p.ready.wait(0, std::memory_order_acquire);
+  return p.pd;
+}
+
+// ---- error shaping (A13) ---------------------------------------------------------------------------------------
+int ReasonHttpStatus(uint8_t r) {
+  switch (r) {
+    case ARKS_R_OK: case ARKS_R_PENDING: return 200;
+    case ARKS_R_NO_TOKEN: return 401;
+    case ARKS_R_REQUEST_BODY: case ARKS_R_NO_MODEL: case ARKS_R_NO_MODEL_BACKENDS: case ARKS_R_STREAM_OPTIONS: return 400;
+    case ARKS_R_RATE_LIMIT: case ARKS_R_QUOTA: return 429;
+    default: return 500;
+  }
+}
+const char* ReasonHeader(uint8_t r) {
+  switch (r) {
+    case ARKS_R_NO_TOKEN: case ARKS_R_TOKEN_NOT_FOUND: case ARKS_R_MODEL_NOT_IN_TOKEN: return "x-error-token";
+    case ARKS_R_REQUEST_BODY: return "x-error-request-body-processing";
+    case ARKS_R_NO_MODEL: return "x-error-no-model-in-request";
+    case ARKS_R_NO_MODEL_BACKENDS: return "x-error-no-model-backends";
+    case ARKS_R_STREAM_OPTIONS: return "x-error-no-stream-options-include-usage";
+    case ARKS_R_RATE_LIMIT: return "x-error-rate-limit";
+    case ARKS_R_QUOTA: case ARKS_R_QUOTA_CONFIG: case ARKS_R_QUOTA_CONFIG_RESP: return "x-error-quota";
+    case ARKS_R_STREAMING: return "x-error-streaming";
+    case ARKS_R_RESPONSE_UNMARSHAL: return "x-error-response-unmarshal";
+    case ARKS_R_RESPONSE_UNKNOWN: return "x-error-response-unknown";
+    default: return "x-error-response";
+  }
+}
+static std::string json_escape(const std::string& s) {
+  std::string o;
+  for (unsigned char c : s) {
+    if (c == '"' || c == '\\') { o += '\\'; o += (char)c; }
+    else if (c == '\n') o += "\\n";
+    else if (c == '\r') o += "\\r";
+    else if (c == '\t') o += "\\t";
+    else if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+    else o += (char)c;
+  }
+  return o;
+}
+Action ErrorResponse(int status, const char* header, const std::string& message) {
+  Action a;
+  a.kind = Action::kImmediate;
+  a.status = status;
+  a.set_headers.push_back({header, "true"});
+  a.set_headers.push_back({"Content-Type", "application/json"});
+  a.body = "{\"error\": {\"message\": \"" + json_escape(message) + "\", \"code\": " + std::to_string(status) + "}}";
+  return a;
+}
+
+// ---- StreamProcessor --------------------------------------------------------------------------------------------
+Action StreamProcessor::OnRequestHeaders(const std::vector<Header>& headers) {
+  std::vector<const uint8_t*> k(headers.size()), v(headers.size());
+  std::vector<size_t> kl(headers.size()), vl(headers.size());
+  for (size_t i = 0; i < headers.size(); i++) {
+    k[i] = (const uint8_t*)headers[i].key.data(); kl[i] = headers[i].key.size();
+    v[i] = (const uint8_t*)headers[i].value.data(); vl[i] = headers[i].value.size();
+  }
+  const uint8_t* tok = nullptr;
+  const size_t n = arks_extract_bearer(k.data(), kl.data(), v.data(), vl.data(), headers.size(), &tok);
+  if (n == 0) return ErrorResponse(401, "x-error-token", "no token found in request headers");
+  token_.assign((const char*)tok, n);
+  Action a;
+  a.kind = Action::kContinueRequestHeaders;
+  a.set_headers.push_back({"x-went-into-req-headers", "true"});
+  a.clear_route_cache = true;
+  return a;
+}
+Action StreamProcessor::OnRequestBody(std::string_view body, uint64_t pick_rand) {
+  req_ = b_->HandleRequestBody(token_, body, pick_rand);
+  if (req_.reason != ARKS_R_OK) {
+    char msg[192];
+    snprintf(msg, sizeof msg, "{\"reason\": %u, \"ruleIndex\": %u, \"currentUsage\": %lld, \"limitMax\": %lld, \"overLimit\": %s}",
+             req_.reason, req_.detail, (long long)req_.cur_usage, (long long)req_.limit_max,
+             (req_.reason == ARKS_R_RATE_LIMIT || req_.reason == ARKS_R_QUOTA) ? "true" : "false");
+    return ErrorResponse(ReasonHttpStatus(req_.reason), ReasonHeader(req_.reason), msg);
+  }
+  qos_ = req_.qos;
+  stream_ = req_.flags & 1;
+  Action a;
+  a.kind = Action::kContinueRequestBody;
+  a.set_headers.push_back({"model", names_->qos_model[(size_t)req_.qos]});
+  a.set_headers.push_back({"namespace", names_->token_namespace[(size_t)req_.token]});
+  a.set_headers.push_back({"username", names_->token_user[(size_t)req_.token]});
+  return a;
+}
+Action StreamProcessor::OnResponseHeaders(const std::vector<Header>& headers) {
+  Action a;
+  a.kind = Action::kContinueResponseHeaders;
+  a.set_headers.push_back({"x-went-into-resp-headers", "true"});
+  status_ = 0;
+  for (const Header& h : headers) {
+    if (h.key == ":status") {
+      char* end = nullptr;
+      const long s = strtol(h.value.c_str(), &end, 10);
+      status_ = (end && *end == 0 && !h.value.empty()) ? (int)s : 0;
+    }
+    a.set_headers.push_back(h);
+  }
+  a.clear_route_cache = true;
+  if (status_ == 500) return ErrorResponse(500, "x-error-response", "");  // gateway.go:115-121
+  return a;
+}
+Action StreamProcessor::OnResponseBody(std::string_view body, bool end_of_stream) {
+  if (status_ != 200) return ErrorResponse(status_, "x-error-response", std::string(body));  // gateway.go:122-126
+  if (stream_) {
+    resp_ = b_->HandleResponseBody(qos_, body, ARKS_RESP_STREAM);
+  } else {
+    buffered_.append(body);  // requestBuffers, handle_response.go:134-155
+    if (!end_of_stream) {
+      Action a;
+      a.kind = Action::kContinueResponseBody;
+      return a;
+    }
+    resp_ = b_->HandleResponseBody(qos_, buffered_, ARKS_RESP_END_OF_STREAM);
+  }
+  if (resp_.reason != ARKS_R_OK && resp_.reason != ARKS_R_PENDING)
+    return ErrorResponse(ReasonHttpStatus(resp_.reason), ReasonHeader(resp_.reason), "response processing error");
+  Action a;
+  a.kind = Action::kContinueResponseBody;
+  return a;
+}
+
+}  // namespace arks_host
+
+// ---- flat C surface ---------------------------------------------------------------------------------------------
+using namespace arks_host;
+
+struct arks_host_batcher {
+  Batcher* b;
+  std::atomic<int64_t> fixed_now{0};
+};
+template <class F>
+static int64_t run_threads(uint32_t n, uint32_t threads, int64_t* latency_ns, F&& one) {
+  if (threads == 0) threads = 1;
+  std::vector<std::thread> ts;
+  std::atomic<uint32_t> ready{0};
+  std::atomic<bool> go{false};
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t t = 0; t < threads; t++)
+    ts.emplace_back([&, t] {
+      ready.fetch_add(1);
+      while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+      for (uint32_t i = t; i < n; i += threads) {
+        const auto a = std::chrono::steady_clock::now();
+        one(i);
+        const auto b = std::chrono::steady_clock::now();
+        if (latency_ns) latency_ns[i] = std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count();
+      }
+    });
+  while (ready.load() != threads) std::this_thread::yield();
+  const auto t1 = std::chrono::steady_clock::now();
+  go.store(true, std::memory_order_release);
+  for (auto& t : ts) t.join();
+  (void)t0;
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t1).count();
+}
+static int64_t fixed_clock(void* arg) { return static_cast<arks_host_batcher*>(arg)->fixed_now.load(); }
+
+extern "C" {
+int arks_host_create(arks_ctx* ctx, uint32_t max_batch, uint64_t max_bytes, uint32_t linger_us, uint32_t max_inflight,
+                     arks_host_batcher** out) {
+  if (!ctx || !out) return ARKS_E_INVALID_ARG;
+  BatcherOptions o;
+  o.max_batch = max_batch; o.max_bytes = (size_t)max_bytes; o.linger_us = linger_us;
+  if (max_inflight >= 1 && max_inflight <= 4) o.max_inflight = max_inflight;
+  auto* h = new arks_host_batcher();
+  h->b = new Batcher(ctx, o);
+  *out = h;
+  return 0;
+}
+void arks_host_destroy(arks_host_batcher* h) {
+  if (!h) return;
+  delete h->b;
+  delete h;
+}
+void arks_host_set_fixed_clock(arks_host_batcher* h, int64_t now_unix) {
+  h->fixed_now.store(now_unix);
+  h->b->SetClock(fixed_clock, h);
+}
+int arks_host_request(arks_host_batcher* h, const uint8_t* token, uint32_t token_len, const uint8_t* body, uint32_t body_len,
+                      uint64_t pick_rand, RequestDecision* out) {
+  *out = h->b->HandleRequestBody(std::string_view((const char*)token, token_len), std::string_view((const char*)body, body_len), pick_rand);
+  return out->reason == 255 ? ARKS_E_INVALID_ARG : 0;
+}
+int arks_host_response(arks_host_batcher* h, int32_t qos, const uint8_t* body, uint32_t body_len, uint8_t flags, ResponseDecision* out) {
+  *out = h->b->HandleResponseBody(qos, std::string_view((const char*)body, body_len), flags);
+  return out->reason == 255 ? ARKS_E_INVALID_ARG : 0;
+}
+void arks_host_stats(arks_host_batcher* h, BatcherStats* out) { *out = h->b->Stats(); }
+
+int64_t arks_host_run_requests(arks_host_batcher* h, uint32_t n, uint32_t threads, const uint8_t* bodies, const uint32_t* body_off,
+                               const uint32_t* body_len, const uint8_t* tokens, const uint32_t* token_off, const uint64_t* pick_rand,
+                               RequestDecision* out, int64_t* latency_ns) {
+  return run_threads(n, threads, latency_ns, [&](uint32_t i) {
+    out[i] = h->b->HandleRequestBody(std::string_view((const char*)tokens + token_off[i], token_off[i + 1] - token_off[i]),
+                                     std::string_view((const char*)bodies + body_off[i], body_len[i]), pick_rand ? pick_rand[i] : 0);
+  });
+}
+int64_t arks_host_run_responses(arks_host_batcher* h, uint32_t n, uint32_t threads, const uint8_t* bodies, const uint32_t* body_off,
+                                const uint32_t* body_len, const int32_t* qos, const uint8_t* flags, ResponseDecision* out,
+                                int64_t* latency_ns) {
+  return run_threads(n, threads, latency_ns, [&](uint32_t i) {
+    out[i] = h->b->HandleResponseBody(qos[i], std::string_view((const char*)bodies + body_off[i], body_len[i]), flags[i]);
+  });
+}
+
+// Open-loop load: requests ARRIVE at `rate_per_s` (exponential gaps, `producers` threads each owning every
+// producers-th row) whether or not earlier ones have been answered; latency = decision handed over - scheduled arrival,
+// so a stalled batcher shows up as latency instead of silently slowing the generator down.
+struct OpenRow {
+  int64_t sched_ns;
+  int64_t* latency;
+  arks_host::RequestDecision* out;
+  std::atomic<uint32_t>* left;
+};
+static inline int64_t mono_ns() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static void open_row_done(void* user, const arks_host::RequestDecision& d) {
+  OpenRow* r = static_cast<OpenRow*>(user);
+  *r->latency = mono_ns() - r->sched_ns;
+  *r->out = d;
+  r->left->fetch_sub(1, std::memory_order_release);
+}
+int64_t arks_host_open_loop_requests(arks_host_batcher* h, uint32_t n, double rate_per_s, uint32_t producers, const uint8_t* bodies,
+                                     const uint32_t* body_off, const uint32_t* body_len, const uint8_t* tokens, const uint32_t* token_off,
+                                     const uint64_t* pick_rand, arks_host::RequestDecision* out, int64_t* latency_ns) {
+  if (producers == 0) producers = 1;
+  std::vector<OpenRow> rows(n);
+  std::atomic<uint32_t> left{n};
+  std::vector<std::thread> ts;
+  const int64_t t0 = mono_ns() + 2'000'000;  // everybody starts 2 ms from now
+  const double mean_gap_ns = 1e9 * producers / rate_per_s;
+  for (uint32_t p = 0; p < producers; p++)
+    ts.emplace_back([&, p] {
+      uint64_t x = 0x9E3779B97F4A7C15ull * (p + 1);
+      double t = (double)t0;
+      for (uint32_t i = p; i < n; i += producers) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;  // xorshift64
+        const double u = ((x >> 11) + 1) * (1.0 / 9007199254740993.0);
+        t += -mean_gap_ns * __builtin_log(u);
+        const int64_t due = (int64_t)t;
+        for (;;) {
+          const int64_t now = mono_ns();
+          if (now >= due) break;
+          if (due - now > 200'000) std::this_thread::sleep_for(std::chrono::microseconds(100));
+        }
+        rows[i] = OpenRow{due, &latency_ns[i], &out[i], &left};
+        const bool ok = h->b->SubmitRequest(std::string_view((const char*)tokens + token_off[i], token_off[i + 1] - token_off[i]),
+                                            std::string_view((const char*)bodies + body_off[i], body_len[i]),
+                                            pick_rand ? pick_rand[i] : 0, open_row_done, &rows[i]);
+        if (!ok) { out[i] = arks_host::RequestDecision{}; out[i].reason = 255; latency_ns[i] = 0; left.fetch_sub(1); }
+      }
+    });
+  for (auto& t : ts) t.join();
+  while (left.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+  return mono_ns() - t0;
+}
+
+static void dump(std::string& o, const Action& a) {
+  o += std::to_string((int)a.kind) + " " + std::to_string(a.status) + " " + (a.clear_route_cache ? "1" : "0") + "\n";
+  for (const Header& h : a.set_headers) o += h.key + ": " + h.value + "\n";
+  o += "\n" + a.body + "\n--\n";
+}
+int arks_host_stream_transcript(arks_host_batcher* h, const char* const* qos_model, uint32_t n_qos, const char* const* tok_ns,
+                                const char* const* tok_user, uint32_t n_tok, const char* const* req_hdr_keys,
+                                const char* const* req_hdr_vals, uint32_t n_req_hdr, const uint8_t* req_body, uint32_t req_body_len,
+                                const char* const* resp_hdr_keys, const char* const* resp_hdr_vals, uint32_t n_resp_hdr,
+                                const uint8_t* const* resp_chunks, const uint32_t* resp_chunk_len, uint32_t n_resp_chunks,
+                                uint64_t pick_rand, char* out, uint32_t out_cap) {
+  NameTables names;
+  for (uint32_t i = 0; i < n_qos; i++) names.qos_model.emplace_back(qos_model[i]);
+  for (uint32_t i = 0; i < n_tok; i++) { names.token_namespace.emplace_back(tok_ns[i]); names.token_user.emplace_back(tok_user[i]); }
+  StreamProcessor sp(h->b, &names);
+  std::string o;
+  std::vector<Header> rh, ph;
+  for (uint32_t i = 0; i < n_req_hdr; i++) rh.push_back({req_hdr_keys[i], req_hdr_vals[i]});
+  for (uint32_t i = 0; i < n_resp_hdr; i++) ph.push_back({resp_hdr_keys[i], resp_hdr_vals[i]});
+  // Server.Process: every message is answered; an ImmediateResponse ends the exchange on Envoy's side
+  Action a = sp.OnRequestHeaders(rh);
+  dump(o, a);
+  if (a.kind != Action::kImmediate) {
+    a = sp.OnRequestBody(std::string_view((const char*)req_body, req_body_len), pick_rand);
+    dump(o, a);
+  }
+  if (a.kind != Action::kImmediate) {
+    a = sp.OnResponseHeaders(ph);
+    dump(o, a);
+    for (uint32_t c = 0; c < n_resp_chunks && a.kind != Action::kImmediate; c++) {
+      a = sp.OnResponseBody(std::string_view((const char*)resp_chunks[c], resp_chunk_len[c]), c + 1 == n_resp_chunks);
+      dump(o, a);
+    }
+  }
+  if (o.size() + 1 > out_cap) return -1;
+  memcpy(out, o.c_str(), o.size() + 1);
+  return (int)o.size();
+}
+}

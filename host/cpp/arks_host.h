@@ -1,0 +1,164 @@
+// arks_host.h — C++ host side above the C ABI (include/arks_gateway.h): what the reference's Go server does around the
+// device path. The reference host is Go (pkg/gateway/*.go); no Go toolchain exists in the build image, so the compiled
+// host lives here in C++, with the reference's names:
+//
+//   Batcher          micro-batches the concurrent ext_proc streams of one GPU: a stream reserves a row of the open
+//                    pinned staging block and copies its own body; a dispatcher thread closes the block and queues it
+//                    on the device (arks_submit_*_async, up to 4 batches in flight, no timer: the next block fills
+//                    while earlier ones are on the GPU); a completion thread waits for the oldest batch and hands
+//                    every row its decision (callback, or futex wake of a blocked caller). host/go/b200/batcher.go
+//                    is the Go twin.
+//   StreamProcessor  Server.Process's per-stream state machine (pkg/gateway/gateway.go:77-138) and the four handlers
+//                    (handle_request.go:33-249, handle_response.go:37-268) over decoded ext_proc messages; the gRPC /
+//                    protobuf transport stays with the embedding server
+//
+// Linearisation: dispatcher cycles in order (one device stream); inside a cycle the request batch, then the response
+// batch; inside a batch rows in reservation order. Every decision carries (cycle, index, now_unix) so a test can replay the exact order.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <string_view>
+#include <vector>
+
+#include "../../include/arks_gateway.h"
+
+namespace arks_host {
+
+struct RequestDecision {
+  uint8_t reason, detail, flags;
+  int32_t qos, token, pick;
+  int64_t cur_usage, limit_max;
+  uint64_t cycle;    // dispatcher cycle that carried the request
+  uint32_t index;    // row inside that cycle's request batch
+  int64_t now_unix;  // the batch's clock reading
+};
+struct ResponseDecision {
+  uint8_t reason, counted;
+  int64_t usage[3];
+  uint64_t cycle;
+  uint32_t index;
+  int64_t now_unix;
+};
+
+struct BatcherOptions {
+  uint32_t max_batch = 4096;
+  size_t max_bytes = 16u << 20;
+  uint32_t linger_us = 0;  // after the first row of a cycle, wait this long for company before submitting (0: submit
+                           // at once; under load the next block fills while the previous one is on the GPU)
+  uint32_t max_inflight = 1;  // batches queued on the device at once (1..4). A small batch costs the GPU about the same
+                              // ~60 us whatever its size, so queueing several tiny batches only adds waiting; measured
+                              // on B200 (tools/host_latency_sweep.py): depth 1 gives the lowest p99 from 0.25 to 1.25 M
+                              // arrivals/s (150 / 200 us p50 / p99 at 1.25 M/s), deeper queues help only bulk replay
+};
+
+struct BatcherStats {
+  uint64_t cycles, request_batches, response_batches, requests, responses, max_request_batch, max_response_batch;
+};
+
+typedef void (*RequestCallback)(void* user, const RequestDecision&);    // run on the batcher's completion thread
+typedef void (*ResponseCallback)(void* user, const ResponseDecision&);
+
+class Batcher {
+ public:
+  Batcher(arks_ctx* ctx, const BatcherOptions& opt);
+  ~Batcher();
+  Batcher(const Batcher&) = delete;
+  Batcher& operator=(const Batcher&) = delete;
+
+  // Blocking, callable from any number of threads. `pick_rand`: the stream's random draw for the weighted pick.
+  // A row that can never fit (body larger than max_bytes) is answered with reason 255 without touching the device.
+  RequestDecision HandleRequestBody(std::string_view token, std::string_view body, uint64_t pick_rand);
+  ResponseDecision HandleResponseBody(int32_t qos, std::string_view body, uint8_t flags);
+  // Asynchronous form for event-driven servers: returns once the row is staged (the body is copied, the caller's buffer
+  // is free again); `cb(user, decision)` runs later on the completion thread, rows of a batch in order. false: the row
+  // can never fit, cb is not called.
+  bool SubmitRequest(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user);
+  bool SubmitResponse(int32_t qos, std::string_view body, uint8_t flags, ResponseCallback cb, void* user);
+
+  void SetClock(int64_t (*clock)(void*), void* arg);  // default: time(nullptr)
+  BatcherStats Stats() const;
+
+ private:
+  struct Impl;
+  Impl* p_;
+};
+
+// ---- ext_proc per-stream state machine --------------------------------------------------------------------------
+struct Header {
+  std::string key, value;
+};
+// names the routing headers are built from (arks_impl.go: qos -> model, token -> namespace / user)
+struct NameTables {
+  std::vector<std::string> qos_model, token_namespace, token_user;
+};
+struct Action {
+  enum Kind { kContinueRequestHeaders, kContinueRequestBody, kContinueResponseHeaders, kContinueResponseBody, kImmediate };
+  Kind kind = kContinueRequestHeaders;
+  int status = 0;                    // kImmediate: HTTP status
+  std::vector<Header> set_headers;   // header mutation (continue) or response headers (immediate)
+  std::string body;                  // kImmediate: JSON error body (util.go:40-77)
+  bool clear_route_cache = false;
+};
+
+class StreamProcessor {
+ public:
+  StreamProcessor(Batcher* batcher, const NameTables* names) : b_(batcher), names_(names) {}
+  Action OnRequestHeaders(const std::vector<Header>& headers);              // handle_request.go:33-81
+  Action OnRequestBody(std::string_view body, uint64_t pick_rand);          // handle_request.go:83-249
+  Action OnResponseHeaders(const std::vector<Header>& headers);             // handle_response.go:37-78
+  Action OnResponseBody(std::string_view body, bool end_of_stream);         // handle_response.go:80-268
+  const RequestDecision& request_decision() const { return req_; }
+  const ResponseDecision& response_decision() const { return resp_; }
+
+ private:
+  Batcher* b_;
+  const NameTables* names_;
+  std::string token_, buffered_;
+  int32_t qos_ = -1;
+  bool stream_ = false;
+  int status_ = 0;
+  RequestDecision req_{};
+  ResponseDecision resp_{};
+};
+
+Action ErrorResponse(int status, const char* header, const std::string& message);  // generateErrorResponse, util.go:40-77
+int ReasonHttpStatus(uint8_t reason);
+const char* ReasonHeader(uint8_t reason);
+
+}  // namespace arks_host
+
+// ---- flat C surface for tests / load generation (ctypes) ----------------------------------------------------------
+extern "C" {
+typedef struct arks_host_batcher arks_host_batcher;
+int arks_host_create(arks_ctx* ctx, uint32_t max_batch, uint64_t max_bytes, uint32_t linger_us, uint32_t max_inflight,
+                     arks_host_batcher** out);
+void arks_host_destroy(arks_host_batcher* b);
+void arks_host_set_fixed_clock(arks_host_batcher* b, int64_t now_unix);
+int arks_host_request(arks_host_batcher* b, const uint8_t* token, uint32_t token_len, const uint8_t* body, uint32_t body_len,
+                      uint64_t pick_rand, arks_host::RequestDecision* out);
+int arks_host_response(arks_host_batcher* b, int32_t qos, const uint8_t* body, uint32_t body_len, uint8_t flags,
+                       arks_host::ResponseDecision* out);
+void arks_host_stats(arks_host_batcher* b, arks_host::BatcherStats* out);
+// n requests issued by `threads` stream threads (thread t owns rows t, t+threads, ...; each row is one blocking
+// HandleRequestBody). Decisions and per-call latencies (ns) come back in row order; returns wall nanoseconds.
+int64_t arks_host_run_requests(arks_host_batcher* b, uint32_t n, uint32_t threads, const uint8_t* bodies, const uint32_t* body_off,
+                               const uint32_t* body_len, const uint8_t* tokens, const uint32_t* token_off, const uint64_t* pick_rand,
+                               arks_host::RequestDecision* out, int64_t* latency_ns);
+int64_t arks_host_run_responses(arks_host_batcher* b, uint32_t n, uint32_t threads, const uint8_t* bodies, const uint32_t* body_off,
+                                const uint32_t* body_len, const int32_t* qos, const uint8_t* flags, arks_host::ResponseDecision* out,
+                                int64_t* latency_ns);
+// open-loop arrivals at rate_per_s (exponential gaps) from `producers` threads through SubmitRequest; latency_ns[i] =
+// decision handed over - scheduled arrival of row i; returns wall nanoseconds
+int64_t arks_host_open_loop_requests(arks_host_batcher* b, uint32_t n, double rate_per_s, uint32_t producers, const uint8_t* bodies,
+                                     const uint32_t* body_off, const uint32_t* body_len, const uint8_t* tokens, const uint32_t* token_off,
+                                     const uint64_t* pick_rand, arks_host::RequestDecision* out, int64_t* latency_ns);
+// one ext_proc stream driven end to end; the transcript of actions is written as text (one action per block:
+// "kind status clear\nkey: value\n...\n\nbody\n--\n") for comparison with the Python mirror
+int arks_host_stream_transcript(arks_host_batcher* b, const char* const* qos_model, uint32_t n_qos, const char* const* tok_ns,
+                                const char* const* tok_user, uint32_t n_tok, const char* const* req_hdr_keys,
+                                const char* const* req_hdr_vals, uint32_t n_req_hdr, const uint8_t* req_body, uint32_t req_body_len,
+                                const char* const* resp_hdr_keys, const char* const* resp_hdr_vals, uint32_t n_resp_hdr,
+                                const uint8_t* const* resp_chunks, const uint32_t* resp_chunk_len, uint32_t n_resp_chunks,
+                                uint64_t pick_rand, char* out, uint32_t out_cap);
+}

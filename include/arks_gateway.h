@@ -213,7 +213,9 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix);
 int arks_fetch_response_result(arks_ctx* ctx, arks_response_result* r);
 /* asynchronous submits: H2D, kernels and D2H are queued on the library's stream and the call returns at once; results
  * land in `out` when arks_wait_* returns. One batch may be in flight per slot (select the slot first), which lets the
- * host overlap packing batch k+1 with the PCIe traffic and kernels of batch k. Batches still apply in call order. */
+ * host overlap packing batch k+1 with the PCIe traffic and kernels of batch k. Batches still apply in call order.
+ * Threads: all submit / stage / run / select calls of a context come from one thread at a time; arks_wait_* may run on
+ * another thread for a slot whose submit call has returned (host/cpp's completion thread does exactly that). */
 int arks_submit_request_async(arks_ctx* ctx, const arks_request_batch* b);
 int arks_wait_request(arks_ctx* ctx, int slot, arks_request_result* out);
 int arks_submit_response_async(arks_ctx* ctx, const arks_response_batch* b);
@@ -229,6 +231,11 @@ int arks_last_kernel_ms(arks_ctx* ctx, float* ms, int cap);
 void* arks_stream(arks_ctx* ctx);
 /* number of kernel launches issued by this context so far */
 uint64_t arks_launch_count(const arks_ctx* ctx);
+
+/* page-locked host memory for batch staging (bodies / SoA arrays handed to arks_submit_*): makes the uploads real DMA
+ * without making the caller link the CUDA runtime. NULL when the allocation fails. */
+void* arks_alloc_pinned(size_t bytes);
+void arks_free_pinned(void* p);
 
 /* quota.QuotaService surface (quota/redis_impl.go:38-107) and A14 snapshot/restore (arks_impl.go:217-300) */
 int arks_snapshot_quota(arks_ctx* ctx, int64_t* usage /* 3 * n_quotas: prompt,response,total */);

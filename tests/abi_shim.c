@@ -1,0 +1,88 @@
+/* abi_shim.c — TEST-ONLY stand-in for libarksgw.so on machines without a GPU: the three entry points the C++ host
+ * (host/cpp/arks_host.cc) calls, answered by the CPU oracle. It lets the batcher's concurrency, ordering and the
+ * ext_proc state machine be tested here; the GPU tests run the same host code against the real library. */
+#include <stdlib.h>
+
+#include "../include/arks_gateway.h"
+#include "../oracle/arks_oracle.h"
+
+#include <string.h>
+
+#define SHIM_SLOTS 4
+struct slot_res {
+  uint32_t n;
+  uint8_t *reason, *detail, *flags, *counted;
+  int32_t *qos, *token, *pick;
+  int64_t *cur, *lim, *usage;
+  int rc;
+};
+struct arks_ctx {
+  ork* o;
+  int cur;
+  struct slot_res rq[SHIM_SLOTS], rs[SHIM_SLOTS];
+};
+
+int arks_shim_create(const arks_tables* t, arks_ctx** out) {
+  arks_ctx* c = (arks_ctx*)calloc(1, sizeof *c);
+  c->o = ork_create(t);
+  if (!c->o) { free(c); return ARKS_E_BAD_TABLE; }
+  *out = c;
+  return 0;
+}
+void arks_shim_destroy(arks_ctx* c) {
+  if (!c) return;
+  ork_destroy(c->o);
+  free(c);
+}
+int arks_submit_request_batch(arks_ctx* c, const arks_request_batch* b, arks_request_result* r) { return ork_request_batch(c->o, b, r); }
+int arks_submit_response_batch(arks_ctx* c, const arks_response_batch* b, arks_response_result* r) { return ork_response_batch(c->o, b, r); }
+void* arks_alloc_pinned(size_t bytes) { return aligned_alloc(64, (bytes + 127) & ~(size_t)63); }
+void arks_free_pinned(void* p) { free(p); }
+size_t arks_extract_bearer(const uint8_t* const* keys, const size_t* key_lens, const uint8_t* const* values,
+                           const size_t* value_lens, size_t n_headers, const uint8_t** token) {
+  return ork_extract_bearer(keys, key_lens, values, value_lens, n_headers, token);
+}
+
+/* asynchronous surface: the oracle answers at submit time, the answer is parked per slot until arks_wait_* */
+int arks_select_slot(arks_ctx* c, int slot) {
+  if (slot < 0 || slot >= SHIM_SLOTS) return ARKS_E_INVALID_ARG;
+  c->cur = slot;
+  return 0;
+}
+static void grow(struct slot_res* s, uint32_t n) {
+  if (s->n >= n && s->reason) return;
+  s->n = n;
+  s->reason = realloc(s->reason, n); s->detail = realloc(s->detail, n); s->flags = realloc(s->flags, n); s->counted = realloc(s->counted, n);
+  s->qos = realloc(s->qos, 4 * (size_t)n); s->token = realloc(s->token, 4 * (size_t)n); s->pick = realloc(s->pick, 4 * (size_t)n);
+  s->cur = realloc(s->cur, 8 * (size_t)n); s->lim = realloc(s->lim, 8 * (size_t)n); s->usage = realloc(s->usage, 24 * (size_t)n);
+}
+int arks_submit_request_async(arks_ctx* c, const arks_request_batch* b) {
+  struct slot_res* s = &c->rq[c->cur];
+  grow(s, b->n ? b->n : 1);
+  s->n = b->n;
+  arks_request_result r = {s->reason, s->detail, s->flags, s->qos, s->token, s->pick, s->cur, s->lim};
+  s->rc = ork_request_batch(c->o, b, &r);
+  return s->rc;
+}
+int arks_wait_request(arks_ctx* c, int slot, arks_request_result* out) {
+  struct slot_res* s = &c->rq[slot];
+  size_t n = s->n;
+  memcpy(out->reason, s->reason, n); memcpy(out->detail, s->detail, n); memcpy(out->flags, s->flags, n);
+  memcpy(out->qos, s->qos, 4 * n); memcpy(out->token, s->token, 4 * n); memcpy(out->pick, s->pick, 4 * n);
+  memcpy(out->cur_usage, s->cur, 8 * n); memcpy(out->limit_max, s->lim, 8 * n);
+  return s->rc;
+}
+int arks_submit_response_async(arks_ctx* c, const arks_response_batch* b) {
+  struct slot_res* s = &c->rs[c->cur];
+  grow(s, b->n ? b->n : 1);
+  s->n = b->n;
+  arks_response_result r = {s->reason, s->counted, s->usage};
+  s->rc = ork_response_batch(c->o, b, &r);
+  return s->rc;
+}
+int arks_wait_response(arks_ctx* c, int slot, arks_response_result* out) {
+  struct slot_res* s = &c->rs[slot];
+  size_t n = s->n;
+  memcpy(out->reason, s->reason, n); memcpy(out->counted, s->counted, n); memcpy(out->usage, s->usage, 24 * n);
+  return s->rc;
+}

@@ -1,0 +1,239 @@
+"""The compiled host (host/cpp): micro-batcher + ext_proc stream state machine above the C ABI.
+
+CPU: the host library is linked against tests/abi_shim.c (the oracle behind arks_submit_*), so what is tested here is the
+host's own logic: rows reserved concurrently end up in well-formed batches, every decision equals what a fresh oracle
+gives when the SAME batches are replayed in cycle order (the linearisation the header promises), and the stream state
+machine emits the reference's replies.
+GPU: the same tests against arks_b200/libarksgw.so."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orklib
+from arks_b200 import abi, cpphost, traffic
+from arks_b200.abi import RequestBatch, ResponseBatch
+from arks_b200.tables import Tables
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BUILD = os.path.join(HERE, "_build")
+FX = json.load(open(os.path.join(HERE, "golden", "quickstart.json")))
+NOW = 1_700_000_000
+
+
+def _shim():
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, "libarksgw_shim.so")
+    src = os.path.join(HERE, "abi_shim.c")
+    ork = orklib.build_oracle()
+    if not os.path.exists(out) or max(os.path.getmtime(src), os.path.getmtime(ork)) > os.path.getmtime(out):
+        d = os.path.dirname(ork)
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", out, src, "-L" + d, "-larks_oracle", "-Wl,-rpath," + d])
+    return out
+
+
+class CpuEngine:
+    """the host library over the oracle shim"""
+
+    def __init__(self, tables, **kw):
+        shim = _shim()
+        self.shim = C.CDLL(shim, mode=C.RTLD_GLOBAL)
+        self.L = cpphost.load(cpphost.build(os.path.join(BUILD, "libarkshost_cpu.so"), against=shim))
+        self._ts = tables.c_struct()
+        self.ctx = C.c_void_p()
+        self.shim.arks_shim_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        assert self.shim.arks_shim_create(C.byref(self._ts), C.byref(self.ctx)) == 0
+        self.b = cpphost.Batcher(self.L, self.ctx, **kw)
+
+    def close(self):
+        self.b.close()
+
+
+class GpuEngine:
+    def __init__(self, tables, **kw):
+        import __graft_entry__ as ge
+        ge.build()
+        from arks_b200 import gateway
+        self.g = gateway.Gateway(0, kw.get("max_batch", 4096), kw.get("max_bytes", 16 << 20))
+        self.g.load_tables(tables)
+        self.L = cpphost.load(cpphost.build())
+        self.b = cpphost.Batcher(self.L, self.g._h, **kw)
+
+    def close(self):
+        self.b.close()
+
+
+def replay_requests(tables, batch: RequestBatch, dec):
+    """group the rows by (cycle, index), push the same batches through a fresh oracle, compare every decision"""
+    o = orklib.Oracle(tables)
+    order = np.lexsort((dec["index"], dec["cycle"]))
+    cycles = dec["cycle"][order]
+    cuts = np.flatnonzero(np.diff(cycles)) + 1
+    n_batches = 0
+    for grp in np.split(order, cuts):
+        assert dec["index"][grp].tolist() == list(range(len(grp))), "rows of a cycle are 0..n-1"
+        now = int(dec["now_unix"][grp[0]])
+        assert np.all(dec["now_unix"][grp] == now)
+        bodies = [bytes(batch.bodies[batch.body_off[i]:batch.body_off[i] + batch.body_len[i]]) for i in grp]
+        toks = [bytes(batch.tokens[batch.token_off[i]:batch.token_off[i + 1]]) for i in grp]
+        rb = RequestBatch.from_lists(bodies, toks, now, pick_rand=batch.pick_rand[grp] if batch.pick_rand is not None else None)
+        want = o.request_batch(rb)
+        for f in ("reason", "detail", "flags", "qos", "token", "pick", "cur_usage", "limit_max"):
+            got = dec[f][grp]
+            assert np.array_equal(got, getattr(want, f)), (f, got[:8], getattr(want, f)[:8])
+        n_batches += 1
+    return o, n_batches
+
+
+def replay_responses(o, batch: ResponseBatch, dec):
+    order = np.lexsort((dec["index"], dec["cycle"]))
+    cuts = np.flatnonzero(np.diff(dec["cycle"][order])) + 1
+    for grp in np.split(order, cuts):
+        now = int(dec["now_unix"][grp[0]])
+        bodies = [bytes(batch.bodies[batch.body_off[i]:batch.body_off[i] + batch.body_len[i]]) for i in grp]
+        rb = ResponseBatch.from_lists(bodies, batch.qos[grp], batch.flags[grp], now)
+        want = o.response_batch(rb)
+        assert np.array_equal(dec["reason"][grp], want.reason)
+        assert np.array_equal(dec["counted"][grp], want.counted)
+        assert np.array_equal(dec["usage"][grp], want.usage)
+
+
+def run_batcher_checks(make_engine):
+    w = traffic.Workload(n_tenants=40, seed=11)  # few tenants, many requests: limits are crossed inside cycles
+    eng = make_engine(w.tables, max_batch=512, max_bytes=2 << 20)
+    try:
+        eng.b.set_fixed_clock(NOW)
+        req = w.request_batch(6000, NOW, seed=5, stream_frac=0.2, noise_frac=0.1)
+        # one stream: every call is its own cycle, in call order
+        d1, _, _ = eng.b.run_requests(RequestBatch(req.bodies, req.body_off[:200].copy(), req.body_len[:200].copy(), req.tokens,
+                                                   req.token_off[:201].copy(), NOW, req.pick_rand[:200].copy()), threads=1)
+        assert np.all(np.diff(d1["cycle"].astype(np.int64)) > 0) and np.all(d1["index"] == 0)
+        st0 = eng.b.stats()
+        assert st0["request_batches"] == 200 and st0["max_request_batch"] == 1
+        # 48 concurrent streams over the rest; the whole history (200 singles + the concurrent cycles) must replay
+        rest = RequestBatch(req.bodies, req.body_off[200:].copy(), req.body_len[200:].copy(), req.tokens,
+                            req.token_off[200:].copy(), NOW, req.pick_rand[200:].copy())
+        d2, lat, wall = eng.b.run_requests(rest, threads=48)
+        st = eng.b.stats()
+        assert st["requests"] == 6000 and st["max_request_batch"] <= 512
+        assert st["max_request_batch"] > 1, "concurrent streams never shared a batch"
+        assert np.all(lat > 0) and wall > 0
+        full = np.concatenate([d1, d2])
+        o, n_batches = replay_requests(w.tables, req, full)
+        assert n_batches == st["request_batches"]
+        assert (full["reason"] == abi.R_RATE_LIMIT).sum() + (full["reason"] == abi.R_QUOTA).sum() > 0
+        # responses for the admitted ones, 32 streams
+        ok = np.flatnonzero(full["reason"] == abi.R_OK)
+        adm = abi.RequestResult.empty(len(ok))
+        adm.reason[:] = 0
+        adm.qos[:] = full["qos"][ok]
+        adm.flags[:] = full["flags"][ok]
+        eng.b.set_fixed_clock(NOW + 2)
+        resp = w.response_batch(adm, NOW + 2, seed=6, noise_frac=0.1)
+        d3, _, _ = eng.b.run_responses(resp, threads=32)
+        replay_responses(o, resp, d3)
+        assert d3["counted"].sum() > 0
+        # open-loop arrivals through the asynchronous API (callbacks on the completion thread): same replay property
+        eng.b.set_fixed_clock(NOW + 120)
+        req2 = w.request_batch(3000, NOW + 120, seed=9, noise_frac=0.05)
+        d4, lat4, _ = eng.b.open_loop_requests(req2, rate_per_s=200_000, producers=3)
+        assert np.all(lat4 > 0)
+        # (`o` already holds the history above: NOW + 120 starts new minute windows, day counters and quota carry on)
+        order = np.lexsort((d4["index"], d4["cycle"]))
+        cuts = np.flatnonzero(np.diff(d4["cycle"][order])) + 1
+        for grp in np.split(order, cuts):
+            bodies = [bytes(req2.bodies[req2.body_off[i]:req2.body_off[i] + req2.body_len[i]]) for i in grp]
+            toks = [bytes(req2.tokens[req2.token_off[i]:req2.token_off[i + 1]]) for i in grp]
+            want = o.request_batch(RequestBatch.from_lists(bodies, toks, NOW + 120, pick_rand=req2.pick_rand[grp]))
+            for f in ("reason", "detail", "flags", "qos", "token", "pick", "cur_usage", "limit_max"):
+                assert np.array_equal(d4[f][grp], getattr(want, f)), f
+        # a body that can never fit is refused on the host
+        big = eng.b.request(b"t", b"x" * (3 << 20))
+        assert big.reason == 255
+    finally:
+        eng.close()
+
+
+def expected_transcript(kind, status=0, clear=0, headers=(), body=""):
+    return f"{kind} {status} {clear}\n" + "".join(f"{k}: {v}\n" for k, v in headers) + "\n" + body + "\n--\n"
+
+
+def run_stream_checks(make_engine):
+    t = Tables(FX["tokens"], FX["quotas"], FX["endpoints"])
+    eng = make_engine(t, max_batch=64, max_bytes=1 << 20)
+    try:
+        eng.b.set_fixed_clock(NOW)
+        names = (t.qos_model_name, t.token_namespace, t.token_user)
+        req_h = [(":method", "POST"), ("authorization", "Bearer sk-test123456"), ("content-type", "application/json")]
+        body = FX["request_body"].encode()
+        rbody = FX["response_body"].encode()
+        # happy path, response split in two (non-stream: buffered until end_of_stream), handle_*.go header sets
+        got = eng.b.stream_transcript(names, req_h, body, [(":status", "200"), ("content-type", "application/json")],
+                                      [rbody[:100], rbody[100:]])
+        want = (expected_transcript(0, 0, 1, [("x-went-into-req-headers", "true")]) +
+                expected_transcript(1, 0, 0, [("model", "qwen-7b"), ("namespace", "default"), ("username", "example-token")]) +
+                expected_transcript(2, 0, 1, [("x-went-into-resp-headers", "true"), (":status", "200"),
+                                              ("content-type", "application/json")]) +
+                expected_transcript(3) + expected_transcript(3))
+        assert got == want
+        # no bearer -> 401 on the headers message, nothing else is processed (handle_request.go:48-56)
+        got = eng.b.stream_transcript(names, [("content-type", "application/json")], body, [], [])
+        err = json.dumps({"error": {"message": "no token found in request headers", "code": 401}})
+        assert got == expected_transcript(4, 401, 0, [("x-error-token", "true"), ("Content-Type", "application/json")], err)
+        # upstream 500 is rewritten on the response headers; other non-200 bodies pass through (gateway.go:115-126)
+        got = eng.b.stream_transcript(names, req_h, body, [(":status", "500")], [b"boom"])
+        assert got.split("--\n")[2].startswith("4 500 0\nx-error-response: true\n")
+        got = eng.b.stream_transcript(names, req_h, body, [(":status", "404")], [b'{"detail":"nope"}'])
+        blocks = got.split("--\n")
+        assert blocks[3].startswith("4 404 0\nx-error-response: true\n")
+        assert json.loads(blocks[3].split("\n\n", 1)[1])["error"]["message"] == '{"detail":"nope"}'
+        # rpm 5: four more pass (two were admitted above: the 500 and the 404 streams), then 429 with usage 5/5
+        kinds = []
+        for _ in range(2):
+            kinds.append(eng.b.stream_transcript(names, req_h, body, [(":status", "200")], [rbody]).split("--\n")[1][0])
+        assert kinds == ["1", "1"]
+        got = eng.b.stream_transcript(names, req_h, body, [(":status", "200")], [rbody])
+        blk = got.split("--\n")[1]
+        assert blk.startswith("4 429 0\nx-error-rate-limit: true\n")
+        detail = json.loads(json.loads(blk.split("\n\n", 1)[1])["error"]["message"])
+        assert (detail["currentUsage"], detail["limitMax"], detail["ruleIndex"], detail["overLimit"]) == (5, 5, 0, True)
+        # streaming: every SSE chunk is a batch row of its own
+        sse = json.load(open(os.path.join(HERE, "golden", "sse_stream.json")))
+        eng.b.set_fixed_clock(NOW + 60)
+        sreq = b'{"model":"qwen-7b","stream":true,"stream_options":{"include_usage":true},"messages":[]}'
+        got = eng.b.stream_transcript(names, req_h, sreq, [(":status", "200")], [c.encode() for c in sse["chunks"]])
+        assert got.count("--\n") == 3 + len(sse["chunks"]) and "\n4 " not in "\n" + got
+        assert eng.b.stats()["responses"] >= len(sse["chunks"])
+    finally:
+        eng.close()
+
+
+def test_host_library_exports():
+    L = CpuEngine(Tables(FX["tokens"], FX["quotas"], FX["endpoints"]))
+    try:
+        for s in cpphost.EXPORTED:
+            assert hasattr(L.L, s), s
+    finally:
+        L.close()
+
+
+def test_batcher_concurrent_streams_replay_cpu():
+    run_batcher_checks(CpuEngine)
+
+
+def test_stream_processor_cpu():
+    run_stream_checks(CpuEngine)
+
+
+@pytest.mark.gpu
+def test_batcher_concurrent_streams_replay_gpu():
+    run_batcher_checks(GpuEngine)
+
+
+@pytest.mark.gpu
+def test_stream_processor_gpu():
+    run_stream_checks(GpuEngine)
