@@ -16,8 +16,13 @@
 //                          static decision, and registration in the batch-local group table
 //   limit_admit_kernel     one lane per request: closed-form fixed-window admission in arrival order
 //                          (SURVEY.md §8a A6), quota check, one commit per group, weighted pick (A12)
+//   rank_hot_groups_kernel arrival ranks inside groups with more than 256 arrivals in one batch (a hot tenant)
 //   scan_response_kernel   one lane per response: JSON / SSE machine, usage extraction and the unconditional
 //                          counter increments (check.go:47-72) as warp-aggregated 64-bit atomics
+//   scan_sse_kernel        all-SSE batches: chunks cut into events (one lane per chunk), events parsed one per lane,
+//                          verdicts folded per chunk; same results as scan_response_kernel<2>
+//
+// Streams: uploads on `h2d`, everything that touches counters on `stream` (its order is the linearisation).
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -265,13 +270,6 @@ struct WindowPipe {
     cp_async_wait<0>();
   }
 };
-template <int STAGES, class F>
-__device__ __forceinline__ void tiled_windows(const uint8_t* body, uint32_t end, uint8_t* warp_smem, F&& per_window) {
-  WindowPipe<STAGES> pipe;
-  pipe.start(body, end, warp_smem);
-  pipe.run(per_window);
-}
-
 // Parse bytes [begin, end) (begin < 16) of 32 spans with machine `m`, one span per lane.
 template <bool EVSYNC, int STAGES, class M>
 __device__ __forceinline__ void feed_pipe(M& m, WindowPipe<STAGES>& pipe, uint32_t begin) {

@@ -1,9 +1,10 @@
 // json_engine.cuh — the table-driven JSON / SSE engine of the scan kernels (device code, sm_100a; host build for tests).
 //
 // One lane == one document, 32 lanes in lock step. Every byte costs the same short instruction sequence on every lane:
-//     class = CLS[byte];  entry = TAB[state * 32 + class];  state = entry & 127;  flag = entry >> 7
-// and only flagged transitions (brackets, key boundaries, the end of a scalar) run handler code, so lanes that sit in
-// different places of different documents stay converged. The tables are generated (tools/gen_json_tables.py) from the
+//     class = CLS[byte];  t = TAB[state * 32 + class];  t < 240: next state, t >= 240: one of the EV_* events
+// and only events (brackets, key boundaries, the end of a scalar) run handler code, so lanes that sit in different places
+// of different documents stay converged. Two schedules drive it: consume_t (a byte or a bulk skip per lane per
+// iteration) and consume_evsync (every lane runs up to its next event, then the warp handles the events together). The tables are generated (tools/gen_json_tables.py) from the
 // grammar the oracle restates: flavor J = json-iterator ConfigFastest (request / response bodies), flavor E =
 // encoding/json checkValid (SSE event data). What the gateway extracts is layered on top as hooks:
 //   K_REQ   {model, stream, stream_options.include_usage}                   pkg/gateway/handle_request.go:87-104
