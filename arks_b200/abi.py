@@ -41,7 +41,9 @@ REASON_HTTP = {
     R_PENDING: (200, None),
 }
 
-RESP_STREAM, RESP_END_OF_STREAM = 1, 2
+RESP_STREAM, RESP_END_OF_STREAM, RESP_COMPLETED = 1, 2, 4
+# metric row layout (include/arks_gateway.h ARKS_METRIC_*)
+METRIC_COLS, METRIC_HITS, METRIC_USAGE, METRIC_HIST_IN, METRIC_HIST_OUT, METRIC_HIST_BUCKETS, METRIC_MESSAGES = 44, 0, 4, 6, 24, 18, 42
 
 E_INVALID_ARG, E_NO_DEVICE, E_CUDA, E_TIME_WENT_BACK, E_BAD_TABLE, E_CAPACITY, E_NOT_LOADED = -1, -2, -3, -4, -5, -6, -7
 

@@ -74,6 +74,7 @@ struct DevTables {
   long long* rate;   // [4][n_qos]
   long long* quota;  // [n_quotas][3]
   long long* qdelta; // [n_quotas][3] increments not yet folded into the other GPUs' copies, or null (single-owner keys)
+  long long* metrics; // [n_qos][ARKS_METRIC_COLS] Prometheus series (include/arks_gateway.h), or null when not enabled
   uint32_t n_qos;
 };
 
@@ -540,7 +541,11 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
         long long lim = T.rl_value[j];
         long long c = rule < 2 ? cur[rule] + k * cnt[rule] : cur[rule];
         long long req = rule < 2 ? 1 : 0;
-        if (c + req > lim) { reason = ARKS_R_RATE_LIMIT; detail = (uint8_t)(j - rl0); cur_out = c; lim_out = lim; }
+        if (c + req > lim) {
+          reason = ARKS_R_RATE_LIMIT; detail = (uint8_t)(j - rl0); cur_out = c; lim_out = lim;
+          if (T.metrics)  // RecordRateLimitHit(ns, user, model, RuleName), check.go:145
+            atomicAdd(reinterpret_cast<unsigned long long*>(T.metrics + (size_t)qos * ARKS_METRIC_COLS + ARKS_METRIC_HITS + rule), 1ull);
+        }
       }
       if (!reason) {
         if (qt == ARKS_QUOTA_MISSING) reason = ARKS_R_QUOTA_CONFIG;
@@ -625,8 +630,27 @@ __device__ __forceinline__ QosAcct load_qos_acct(const DevTables& T, int32_t qos
 }
 
 // A11 for one response per lane (all 32 lanes must call): doTokenRateLimit / doTokenQuotaLimit and the result row.
+// bucket of gateway_token_distribution (ExponentialBuckets(1, 2, 17) + Inf): the first upper bound >= v
+__device__ __forceinline__ int token_bucket(long long v) {
+  if (v <= 1) return 0;
+  if (v > 65536) return ARKS_METRIC_HIST_BUCKETS - 1;
+  return 64 - __clzll(v - 1);
+}
+
 __device__ __forceinline__ void account_usage(const DevTables& T, const RespDev& B, uint32_t i, bool live, int32_t qos, const QosAcct& acct,
                                               uint8_t reason, uint8_t counted, long long u0, long long u1, long long u2) {
+  if (T.metrics && live) {  // N3: the series the reference updates per response-body message
+    unsigned long long* row = reinterpret_cast<unsigned long long*>(T.metrics + (size_t)qos * ARKS_METRIC_COLS);
+    const uint8_t fl = B.flags[i];
+    atomicAdd(row + ARKS_METRIC_MESSAGES, 1ull);  // RecordRequest(..., "200"), gateway.go:129
+    // RecordTokenUsage: `!hasCompleted && complete && EndOfStream`, handle_response.go:102-104
+    if (counted && (fl & ARKS_RESP_END_OF_STREAM) && !(fl & ARKS_RESP_COMPLETED)) {
+      atomicAdd(row + ARKS_METRIC_USAGE + 0, (unsigned long long)u0);
+      atomicAdd(row + ARKS_METRIC_USAGE + 1, (unsigned long long)u1);
+      atomicAdd(row + ARKS_METRIC_HIST_IN + token_bucket(u0), 1ull);
+      atomicAdd(row + ARKS_METRIC_HIST_OUT + token_bucket(u1), 1ull);
+    }
+  }
   // doTokenRateLimit: += total on every token-type entry (check.go:47-59). Warp-aggregated per address.
   const int32_t qt = counted ? acct.qt : ARKS_QUOTA_NONE;
 #pragma unroll
@@ -909,6 +933,8 @@ struct arks_ctx {
   std::vector<void*> table_allocs;
   DevTables dt{};
   long long* d_rate = nullptr;
+  long long* d_metrics = nullptr;  // [n_qos][ARKS_METRIC_COLS] when metrics are enabled
+  bool metrics_on = false;
   long long* d_quota = nullptr;
   long long* d_qdelta = nullptr;   // allocated when quota sharing is enabled
   long long* d_qtmp = nullptr;
@@ -1067,6 +1093,7 @@ void arks_destroy(arks_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_tables(ctx);
   cudaFree(ctx->d_rate);
+  cudaFree(ctx->d_metrics);
   cudaFree(ctx->d_quota);
   cudaFree(ctx->d_qdelta);
   cudaFree(ctx->d_qtmp);
@@ -1097,6 +1124,21 @@ void arks_destroy(arks_ctx* ctx) {
 
 void* arks_stream(arks_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t arks_launch_count(const arks_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int arks_enable_metrics(arks_ctx* ctx, int on) {
+  if (!ctx) return ARKS_E_INVALID_ARG;
+  ctx->metrics_on = on != 0;
+  if (ctx->loaded) ctx->dt.metrics = ctx->metrics_on ? ctx->d_metrics : nullptr;
+  return 0;
+}
+int arks_snapshot_metrics(arks_ctx* ctx, int64_t* rows) {
+  if (!ctx || !ctx->loaded) return ARKS_E_NOT_LOADED;
+  if (!rows) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->ht.n_qos) CK(cudaMemcpy(rows, ctx->d_metrics, (size_t)8 * ARKS_METRIC_COLS * ctx->ht.n_qos, cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 void* arks_alloc_pinned(size_t bytes) {
   void* p = nullptr;
@@ -1180,18 +1222,25 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
 
   // carry counters over by key (Redis keys survive a CRD edit)
   std::vector<long long> new_rate((size_t)4 * t->n_qos + 1, 0), new_quota((size_t)3 * t->n_quotas + 1, 0);
+  std::vector<long long> new_metrics((size_t)ARKS_METRIC_COLS * t->n_qos + 1, 0);  // series live as long as the process
   if (ctx->loaded) {
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<long long> old_rate((size_t)4 * ctx->ht.n_qos + 1), old_quota((size_t)3 * ctx->ht.n_quotas + 1);
     if (ctx->ht.n_qos) CK(cudaMemcpy(old_rate.data(), ctx->d_rate, (size_t)32 * ctx->ht.n_qos, cudaMemcpyDeviceToHost));
     if (ctx->ht.n_quotas) CK(cudaMemcpy(old_quota.data(), ctx->d_quota, (size_t)24 * ctx->ht.n_quotas, cudaMemcpyDeviceToHost));
+    std::vector<long long> old_metrics((size_t)ARKS_METRIC_COLS * ctx->ht.n_qos + 1, 0);
+    if (ctx->d_metrics && ctx->ht.n_qos)
+      CK(cudaMemcpy(old_metrics.data(), ctx->d_metrics, (size_t)8 * ARKS_METRIC_COLS * ctx->ht.n_qos, cudaMemcpyDeviceToHost));
     std::unordered_map<std::string, uint32_t> oq, ou;
     for (uint32_t q = 0; q < ctx->ht.n_qos; q++) oq.emplace(ctx->ht.qos_key[q], q);
     for (uint32_t q = 0; q < ctx->ht.n_quotas; q++) ou.emplace(ctx->ht.quota_key[q], q);
     for (uint32_t q = 0; q < t->n_qos; q++) {
       auto it = oq.find(ht.qos_key[q]);
-      if (it != oq.end())
+      if (it != oq.end()) {
         for (int r = 0; r < 4; r++) new_rate[(size_t)r * t->n_qos + q] = old_rate[(size_t)r * ctx->ht.n_qos + it->second];
+        for (int c = 0; c < ARKS_METRIC_COLS; c++)
+          new_metrics[(size_t)ARKS_METRIC_COLS * q + c] = old_metrics[(size_t)ARKS_METRIC_COLS * it->second + c];
+      }
     }
     for (uint32_t q = 0; q < t->n_quotas; q++) {
       auto it = ou.find(ht.quota_key[q]);
@@ -1202,7 +1251,10 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
   free_tables(ctx);
   cudaFree(ctx->d_rate);
   cudaFree(ctx->d_quota);
-  ctx->d_rate = ctx->d_quota = nullptr;
+  cudaFree(ctx->d_metrics);
+  ctx->d_rate = ctx->d_quota = ctx->d_metrics = nullptr;
+  CK(cudaMalloc(&ctx->d_metrics, (size_t)8 * ARKS_METRIC_COLS * t->n_qos + 64));
+  CK(cudaMemcpyAsync(ctx->d_metrics, new_metrics.data(), (size_t)8 * ARKS_METRIC_COLS * t->n_qos, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMalloc(&ctx->d_rate, (size_t)32 * t->n_qos + 64));
   CK(cudaMalloc(&ctx->d_quota, (size_t)24 * t->n_quotas + 64));
   CK(cudaMemcpyAsync(ctx->d_rate, new_rate.data(), (size_t)32 * t->n_qos, cudaMemcpyHostToDevice, ctx->stream));
@@ -1248,6 +1300,7 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
     CK(cudaMemsetAsync(ctx->d_qdelta, 0, (size_t)24 * t->n_quotas + 64, ctx->stream));
   }
   d.rate = ctx->d_rate;
+  d.metrics = ctx->metrics_on ? ctx->d_metrics : nullptr;
   d.quota = ctx->d_quota;
   d.qdelta = ctx->d_qdelta;
   d.n_qos = t->n_qos;

@@ -71,6 +71,8 @@ def lib():
         L.arks_set_quota_usage.argtypes = [vp, C.c_uint32, abi.i64p]
         L.arks_incr_quota_usage.argtypes = [vp, C.c_uint32, abi.i64p]
         L.arks_snapshot_rate.argtypes = [vp, C.c_int64, abi.i64p]
+        L.arks_enable_metrics.argtypes = [vp, C.c_int]
+        L.arks_snapshot_metrics.argtypes = [vp, abi.i64p]
         L.arks_enable_quota_sharing.argtypes = [vp, C.c_int]
         L.arks_take_quota_delta.argtypes = [vp, abi.i64p]
         L.arks_apply_quota_delta.argtypes = [vp, abi.i64p]
@@ -87,7 +89,7 @@ EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/t
     "arks_submit_response_batch", "arks_stage_request_batch", "arks_run_request_batch",
     "arks_fetch_request_result", "arks_stage_response_batch", "arks_run_response_batch",
     "arks_fetch_response_result", "arks_submit_request_async", "arks_wait_request", "arks_submit_response_async",
-    "arks_wait_response", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_alloc_pinned", "arks_free_pinned", "arks_snapshot_quota",
+    "arks_wait_response", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_enable_metrics", "arks_snapshot_metrics", "arks_alloc_pinned", "arks_free_pinned", "arks_snapshot_quota",
     "arks_set_quota_usage", "arks_incr_quota_usage", "arks_snapshot_rate", "arks_take_quota_delta",
     "arks_apply_quota_delta", "arks_quota_delta_dev", "arks_fold_quota_delta_dev", "arks_enable_quota_sharing",
     "arks_export_quota_delta_dev",
@@ -221,6 +223,16 @@ class Gateway:
     def snapshot_quota(self) -> np.ndarray:
         out = np.zeros((self.tables.n_quotas, 3), np.int64)
         self._ck(lib().arks_snapshot_quota(self._h, abi.ptr(out, abi.i64p)))
+        return out
+
+    def enable_metrics(self, on: bool = True):
+        """accumulate the gateway's Prometheus series on the device (N3); off by default"""
+        self._ck(lib().arks_enable_metrics(self._h, 1 if on else 0))
+
+    def snapshot_metrics(self) -> np.ndarray:
+        """[n_qos, METRIC_COLS] int64, layout abi.METRIC_*"""
+        out = np.zeros((self.tables.n_qos, abi.METRIC_COLS), np.int64)
+        self._ck(lib().arks_snapshot_metrics(self._h, abi.ptr(out, abi.i64p)))
         return out
 
     def snapshot_rate(self, now_unix: int) -> np.ndarray:

@@ -159,7 +159,10 @@ typedef struct arks_request_result {
 
 /* ---- response phase (ProcessingRequest_ResponseBody with :status 200, handle_response.go:80-268) ---- */
 #define ARKS_RESP_STREAM 1u        /* the request had stream:true  -> body is one SSE chunk, decoded in isolation */
-#define ARKS_RESP_END_OF_STREAM 2u /* non-stream: `body` is the complete concatenated response body               */
+#define ARKS_RESP_END_OF_STREAM 2u /* non-stream: `body` is the complete concatenated response body; stream: the last
+                                    * chunk (only the metrics read it there)                                      */
+#define ARKS_RESP_COMPLETED 4u     /* this stream already had a usage-bearing message (`completed`, gateway.go:127):
+                                    * read by the metrics only                                                     */
 typedef struct arks_response_batch {
   uint32_t n;
   const uint8_t* bodies;
@@ -231,6 +234,25 @@ int arks_last_kernel_ms(arks_ctx* ctx, float* ms, int cap);
 void* arks_stream(arks_ctx* ctx);
 /* number of kernel launches issued by this context so far */
 uint64_t arks_launch_count(const arks_ctx* ctx);
+
+/* N3: the gateway's Prometheus series that are functions of the request stream
+ * (pkg/gateway/metrics/metrics.go:24-98, collector.go:35-53), accumulated on the device next to the counters and read at
+ * scrape time. One row of ARKS_METRIC_COLS int64 per qos entry == label set (namespace, user, model); durations stay on
+ * the host (wall clock). Off by default; counters survive arks_load_tables by key like the rate windows.
+ *   [0..3]   gateway_rate_limit_hits_total{rule_type=rpm,rpd,tpm,tpd}     check.go:145
+ *   [4..5]   gateway_token_usage{type=input,output}                        handle_response.go:102-104
+ *   [6..23]  gateway_token_distribution{type=input} buckets le=1,2,4..65536,+Inf (non-cumulative counts)
+ *   [24..41] gateway_token_distribution{type=output}
+ *   [42]     gateway_requests_total{status="200"}: one per response-body message (gateway.go:129)               */
+#define ARKS_METRIC_COLS 44
+#define ARKS_METRIC_HITS 0
+#define ARKS_METRIC_USAGE 4
+#define ARKS_METRIC_HIST_IN 6
+#define ARKS_METRIC_HIST_OUT 24
+#define ARKS_METRIC_HIST_BUCKETS 18
+#define ARKS_METRIC_MESSAGES 42
+int arks_enable_metrics(arks_ctx* ctx, int on);
+int arks_snapshot_metrics(arks_ctx* ctx, int64_t* rows /* n_qos * ARKS_METRIC_COLS */);
 
 /* page-locked host memory for batch staging (bodies / SoA arrays handed to arks_submit_*): makes the uploads real DMA
  * without making the caller link the CUDA runtime. NULL when the allocation fails. */

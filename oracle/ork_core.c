@@ -54,6 +54,7 @@ struct ork {
   int64_t* rate_win; /* n_qos * 4: window start the value belongs to (the key suffix) */
   int64_t* rate_val; /* n_qos * 4 */
   int64_t* quota_use; /* n_quotas * 3 */
+  int64_t* metrics;   /* n_qos * ARKS_METRIC_COLS: the Prometheus series that are functions of the request stream */
   int64_t last_win[4];
 };
 
@@ -254,6 +255,7 @@ ork* ork_create(const arks_tables* t) {
   o->rate_win = (int64_t*)calloc((size_t)o->n_qos * 4 + 1, 8);
   o->rate_val = (int64_t*)calloc((size_t)o->n_qos * 4 + 1, 8);
   o->quota_use = (int64_t*)calloc((size_t)o->n_quotas * 3 + 1, 8);
+  o->metrics = (int64_t*)calloc((size_t)o->n_qos * ARKS_METRIC_COLS + 1, 8);
   for (int r = 0; r < 4; r++) o->last_win[r] = INT64_MIN;
   return o;
 }
@@ -263,6 +265,7 @@ void ork_destroy(ork* o) {
   free(o->rate_win);
   free(o->rate_val);
   free(o->quota_use);
+  free(o->metrics);
   free(o);
 }
 
@@ -283,6 +286,7 @@ int ork_reload(ork* o, const arks_tables* t) {
           str_eq(o, o->qos_model_str[p], md, c)) {
         memcpy(n->rate_win + 4 * (size_t)q, o->rate_win + 4 * (size_t)p, 32);
         memcpy(n->rate_val + 4 * (size_t)q, o->rate_val + 4 * (size_t)p, 32);
+        memcpy(n->metrics + ARKS_METRIC_COLS * (size_t)q, o->metrics + ARKS_METRIC_COLS * (size_t)p, 8 * ARKS_METRIC_COLS);
         break;
       }
     }
@@ -427,6 +431,7 @@ static void handle_request(ork* o, const arks_request_batch* b, arks_request_res
     int64_t req = RULE_IS_REQUEST[rule] ? 1 : 0; /* "token is not caculated in request" check.go:124-126 */
     if ((int64_t)((uint64_t)cur + (uint64_t)req) > o->rl_value[j]) {
       r->reason[i] = ARKS_R_RATE_LIMIT;
+      o->metrics[(size_t)q * ARKS_METRIC_COLS + ARKS_METRIC_HITS + rule]++; /* RecordRateLimitHit, check.go:145 */
       r->detail[i] = (uint8_t)(j - rl0);
       r->cur_usage[i] = cur;
       r->limit_max[i] = o->rl_value[j];
@@ -465,8 +470,28 @@ static void handle_request(ork* o, const arks_request_batch* b, arks_request_res
   }
 }
 
-/* ---------- HandleResponseBody (:status 200) ---------- */
+/* bucket of gateway_token_distribution: ExponentialBuckets(1, 2, 17) + Inf, metrics.go:62-69 */
+static int token_bucket(int64_t v) {
+  int64_t le = 1;
+  for (int k = 0; k < ARKS_METRIC_HIST_BUCKETS - 1; k++, le *= 2)
+    if (v <= le) return k;
+  return ARKS_METRIC_HIST_BUCKETS - 1;
+}
+static void handle_response_inner(ork* o, const arks_response_batch* b, arks_response_result* r, uint32_t i);
+/* Server.Process + the deferred block of HandleResponseBody: gateway.go:122-129, handle_response.go:99-109 */
 static void handle_response(ork* o, const arks_response_batch* b, arks_response_result* r, uint32_t i) {
+  handle_response_inner(o, b, r, i);
+  int64_t* row = o->metrics + (size_t)b->qos[i] * ARKS_METRIC_COLS;
+  row[ARKS_METRIC_MESSAGES]++; /* RecordRequest(ns, user, model, dur, "200") for every response-body message */
+  /* `!hasCompleted && complete && EndOfStream`: complete was set by THIS message (usage.total_tokens != 0) */
+  if (r->counted[i] && (b->flags[i] & ARKS_RESP_END_OF_STREAM) && !(b->flags[i] & ARKS_RESP_COMPLETED)) {
+    row[ARKS_METRIC_USAGE + 0] = (int64_t)((uint64_t)row[ARKS_METRIC_USAGE + 0] + (uint64_t)r->usage[3 * i + 0]);
+    row[ARKS_METRIC_USAGE + 1] = (int64_t)((uint64_t)row[ARKS_METRIC_USAGE + 1] + (uint64_t)r->usage[3 * i + 1]);
+    row[ARKS_METRIC_HIST_IN + token_bucket(r->usage[3 * i + 0])]++;
+    row[ARKS_METRIC_HIST_OUT + token_bucket(r->usage[3 * i + 1])]++;
+  }
+}
+static void handle_response_inner(ork* o, const arks_response_batch* b, arks_response_result* r, uint32_t i) {
   const uint8_t* body = b->bodies + b->body_off[i];
   size_t len = b->body_len[i];
   int32_t q = b->qos[i];
@@ -624,6 +649,10 @@ int ork_incr_quota_usage(ork* o, uint32_t quota, const int64_t delta[3]) {
   if (quota >= o->n_quotas) return ARKS_E_INVALID_ARG;
   for (int k = 0; k < 3; k++)
     o->quota_use[3 * (size_t)quota + k] = (int64_t)((uint64_t)o->quota_use[3 * (size_t)quota + k] + (uint64_t)delta[k]);
+  return 0;
+}
+int ork_snapshot_metrics(ork* o, int64_t* rows) {
+  memcpy(rows, o->metrics, (size_t)o->n_qos * ARKS_METRIC_COLS * 8);
   return 0;
 }
 int ork_snapshot_rate(ork* o, int64_t now, int64_t* c) {

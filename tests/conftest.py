@@ -25,3 +25,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="module")
+def gwmod():
+    """the CUDA library's Python wrapper, built on demand (GPU tests only)"""
+    import __graft_entry__ as ge
+    ge.build()
+    from arks_b200 import gateway
+    return gateway

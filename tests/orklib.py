@@ -53,6 +53,7 @@ def lib():
         L.ork_set_quota_usage.argtypes = [C.c_void_p, C.c_uint32, abi.i64p]
         L.ork_incr_quota_usage.argtypes = [C.c_void_p, C.c_uint32, abi.i64p]
         L.ork_snapshot_rate.argtypes = [C.c_void_p, C.c_int64, abi.i64p]
+        L.ork_snapshot_metrics.argtypes = [C.c_void_p, abi.i64p]
         L.ork_parse_request_body.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
                                              C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                              C.POINTER(C.c_int)]
@@ -120,6 +121,11 @@ class Oracle:
     def snapshot_quota(self) -> np.ndarray:
         out = np.zeros((self.tables.n_quotas, 3), np.int64)
         lib().ork_snapshot_quota(self.h, abi.ptr(out, abi.i64p))
+        return out
+
+    def snapshot_metrics(self) -> np.ndarray:
+        out = np.zeros((self.tables.n_qos, abi.METRIC_COLS), np.int64)
+        lib().ork_snapshot_metrics(self.h, abi.ptr(out, abi.i64p))
         return out
 
     def snapshot_rate(self, now) -> np.ndarray:

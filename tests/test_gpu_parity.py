@@ -17,14 +17,6 @@ NOW = 1_700_000_000
 D2 = re.compile(rb"[0-9.]{17,}|[eE][+-]?[0-9]{2,}")
 
 
-@pytest.fixture(scope="module")
-def gwmod():
-    import __graft_entry__ as ge
-    ge.build()
-    from arks_b200 import gateway
-    return gateway
-
-
 def pair(gwmod, tables, max_batch=4096, max_bytes=16 << 20):
     g = gwmod.Gateway(0, max_batch, max_bytes)
     g.load_tables(tables)
