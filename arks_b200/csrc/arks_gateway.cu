@@ -897,6 +897,35 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, ARKS_SSE_MINBLK) scan_sse
   account_usage(T, B, i, live, qos, acct, reason, counted, u0, u1, u2);
 }
 
+// syncQuotaUsage (arks_impl.go:226-296): one lane per ArksQuota, in place on the device copies of the CR status
+__global__ void sync_quota_kernel(const uint32_t* item_off, const uint8_t* item_type, long long* quota, uint32_t n_quotas, int restore,
+                                  uint32_t* present, long long* used, uint8_t* action) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_quotas) return;
+  uint32_t pres = present[q];
+  long long u[3] = {used[3 * (size_t)q], used[3 * (size_t)q + 1], used[3 * (size_t)q + 2]};
+  long long* cur = quota + 3 * (size_t)q;
+  int update_cr = 0, update_quota = 0;
+  for (uint32_t j = item_off[q]; j < item_off[q + 1]; j++) {
+    const int ty = item_type[j];
+    if (pres & (1u << ty)) {
+      if (u[ty] < cur[ty]) { update_cr = 1; u[ty] = cur[ty]; }
+      else if (u[ty] > cur[ty]) update_quota = 1;
+    } else {
+      update_cr = 1; pres |= 1u << ty; u[ty] = cur[ty];
+    }
+  }
+  if (update_quota)
+    for (uint32_t j = item_off[q]; j < item_off[q + 1]; j++) {
+      const int ty = item_type[j];
+      if (!restore) cur[ty] = 0;  // SetUsage(QosToQuotaRequests(conf, nil)): Request == 0
+      else if (u[ty] > cur[ty]) cur[ty] = u[ty];
+    }
+  present[q] = pres;
+  used[3 * (size_t)q] = u[0]; used[3 * (size_t)q + 1] = u[1]; used[3 * (size_t)q + 2] = u[2];
+  action[q] = (uint8_t)(update_cr | update_quota << 1);
+}
+
 // quota[i] += reduced[i] - own[i]; own[i] = 0  — applies what the OTHER GPUs added since the last fold
 __global__ void fold_quota_delta_kernel(long long* quota, long long* own, const long long* reduced, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1124,6 +1153,31 @@ void arks_destroy(arks_ctx* ctx) {
 
 void* arks_stream(arks_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t arks_launch_count(const arks_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int arks_sync_quota_usage(arks_ctx* ctx, int mode, uint32_t* status_present, int64_t* status_used, uint8_t* action) {
+  if (!ctx || !ctx->loaded) return ARKS_E_NOT_LOADED;
+  if (!status_present || !status_used || !action || (mode != ARKS_SYNC_REFERENCE && mode != ARKS_SYNC_RESTORE)) return ARKS_E_INVALID_ARG;
+  const uint32_t n = ctx->ht.n_quotas;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  uint32_t* d_pres = nullptr;
+  long long* d_used = nullptr;
+  uint8_t* d_act = nullptr;
+  CK(cudaMalloc(&d_pres, (size_t)4 * n));
+  CK(cudaMalloc(&d_used, (size_t)24 * n));
+  CK(cudaMalloc(&d_act, n));
+  CK(cudaMemcpyAsync(d_pres, status_present, (size_t)4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_used, status_used, (size_t)24 * n, cudaMemcpyHostToDevice, ctx->stream));
+  sync_quota_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->dt.quota_item_off, ctx->dt.qitem_type, ctx->d_quota, n,
+                                                            mode == ARKS_SYNC_RESTORE, d_pres, d_used, d_act);
+  CK(cudaMemcpyAsync(status_present, d_pres, (size_t)4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(status_used, d_used, (size_t)24 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(action, d_act, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_pres); cudaFree(d_used); cudaFree(d_act);
+  ctx->launches += 1;
+  return 0;
+}
 
 int arks_enable_metrics(arks_ctx* ctx, int on) {
   if (!ctx) return ARKS_E_INVALID_ARG;

@@ -71,6 +71,7 @@ def lib():
         L.arks_set_quota_usage.argtypes = [vp, C.c_uint32, abi.i64p]
         L.arks_incr_quota_usage.argtypes = [vp, C.c_uint32, abi.i64p]
         L.arks_snapshot_rate.argtypes = [vp, C.c_int64, abi.i64p]
+        L.arks_sync_quota_usage.argtypes = [vp, C.c_int, abi.u32p, abi.i64p, abi.u8p]
         L.arks_enable_metrics.argtypes = [vp, C.c_int]
         L.arks_snapshot_metrics.argtypes = [vp, abi.i64p]
         L.arks_enable_quota_sharing.argtypes = [vp, C.c_int]
@@ -89,7 +90,7 @@ EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/t
     "arks_submit_response_batch", "arks_stage_request_batch", "arks_run_request_batch",
     "arks_fetch_request_result", "arks_stage_response_batch", "arks_run_response_batch",
     "arks_fetch_response_result", "arks_submit_request_async", "arks_wait_request", "arks_submit_response_async",
-    "arks_wait_response", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_enable_metrics", "arks_snapshot_metrics", "arks_alloc_pinned", "arks_free_pinned", "arks_snapshot_quota",
+    "arks_wait_response", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_enable_metrics", "arks_snapshot_metrics", "arks_sync_quota_usage", "arks_alloc_pinned", "arks_free_pinned", "arks_snapshot_quota",
     "arks_set_quota_usage", "arks_incr_quota_usage", "arks_snapshot_rate", "arks_take_quota_delta",
     "arks_apply_quota_delta", "arks_quota_delta_dev", "arks_fold_quota_delta_dev", "arks_enable_quota_sharing",
     "arks_export_quota_delta_dev",
@@ -224,6 +225,17 @@ class Gateway:
         out = np.zeros((self.tables.n_quotas, 3), np.int64)
         self._ck(lib().arks_snapshot_quota(self._h, abi.ptr(out, abi.i64p)))
         return out
+
+    def sync_quota_usage(self, status_present: np.ndarray, status_used: np.ndarray, restore: bool = False) -> np.ndarray:
+        """syncQuotaUsage over all ArksQuotas (arks_impl.go:217-300). status_present [n_quotas] uint32 bit masks and
+        status_used [n_quotas, 3] int64 are updated in place (the CR status to write back); returns action[n_quotas]:
+        bit0 update the CR, bit1 the store was outdated (reference: zeroed; restore=True: raised to the CR value)."""
+        n = self.tables.n_quotas
+        assert status_present.dtype == np.uint32 and status_used.dtype == np.int64 and status_used.shape == (n, 3)
+        action = np.zeros(n, np.uint8)
+        self._ck(lib().arks_sync_quota_usage(self._h, 1 if restore else 0, abi.ptr(status_present, abi.u32p),
+                                             abi.ptr(status_used, abi.i64p), abi.ptr(action, abi.u8p)))
+        return action
 
     def enable_metrics(self, on: bool = True):
         """accumulate the gateway's Prometheus series on the device (N3); off by default"""

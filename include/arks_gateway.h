@@ -262,6 +262,14 @@ void arks_free_pinned(void* p);
 /* quota.QuotaService surface (quota/redis_impl.go:38-107) and A14 snapshot/restore (arks_impl.go:217-300) */
 int arks_snapshot_quota(arks_ctx* ctx, int64_t* usage /* 3 * n_quotas: prompt,response,total */);
 int arks_set_quota_usage(arks_ctx* ctx, uint32_t quota, const int64_t usage[3]); /* SetUsage */
+/* syncQuotaUsage (arks_impl.go:217-300), all ArksQuotas in one pass, between batches. In/out per quota: status_present
+ * (bit t: Status.QuotaStatus has type t) and status_used[3]; out: action[q] bit0 = update the CR status, bit1 = the store
+ * was outdated. mode ARKS_SYNC_REFERENCE reproduces the reference (an outdated store is zeroed, because SetUsage is
+ * called with Request == 0), ARKS_SYNC_RESTORE raises the store to the CR's value (the intended restore on start). */
+#define ARKS_SYNC_REFERENCE 0
+#define ARKS_SYNC_RESTORE 1
+int arks_sync_quota_usage(arks_ctx* ctx, int mode, uint32_t* status_present /* n_quotas */, int64_t* status_used /* 3 * n_quotas */,
+                          uint8_t* action /* n_quotas */);
 int arks_incr_quota_usage(arks_ctx* ctx, uint32_t quota, const int64_t delta[3]); /* IncrUsage */
 /* rate counters of the CURRENT windows (value 0 if the stored window is older than now_unix's) */
 int arks_snapshot_rate(arks_ctx* ctx, int64_t now_unix, int64_t* counters /* 4 * n_qos */);

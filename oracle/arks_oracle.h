@@ -36,6 +36,8 @@ int ork_snapshot_quota(ork* o, int64_t* usage);
 int ork_set_quota_usage(ork* o, uint32_t quota, const int64_t usage[3]);
 int ork_incr_quota_usage(ork* o, uint32_t quota, const int64_t delta[3]);
 int ork_snapshot_rate(ork* o, int64_t now_unix, int64_t* counters);
+/* syncQuotaUsage for one ArksQuota (arks_impl.go:226-296); restore 0 = the reference (zeroes on outdated), 1 = repaired */
+int ork_sync_quota_usage(ork* o, uint32_t quota, uint32_t* status_present, int64_t status_used[3], int restore);
 /* the Prometheus series of include/arks_gateway.h (ARKS_METRIC_*), always accumulated: n_qos * ARKS_METRIC_COLS */
 int ork_snapshot_metrics(ork* o, int64_t* rows);
 

@@ -651,6 +651,35 @@ int ork_incr_quota_usage(ork* o, uint32_t quota, const int64_t delta[3]) {
     o->quota_use[3 * (size_t)quota + k] = (int64_t)((uint64_t)o->quota_use[3 * (size_t)quota + k] + (uint64_t)delta[k]);
   return 0;
 }
+/* syncQuotaUsage for one ArksQuota (qosconfig/arks_impl.go:226-296). status_present: bit t set when
+ * quota.Status.QuotaStatus has an entry of type t; status_used[t] its Used. Returns bit0 = shouldUpdateCR, bit1 =
+ * shouldUpdateQuota. The CR side is updated in place; on shouldUpdateQuota the reference calls SetUsage with requests
+ * built by QosToQuotaRequests(conf, nil), i.e. Request == 0 for every item: the usage of every spec'd type is ZEROED
+ * (restore == 0). restore == 1 is the repaired behaviour: the store is raised to the CR's value instead. */
+int ork_sync_quota_usage(ork* o, uint32_t q, uint32_t* status_present, int64_t status_used[3], int restore) {
+  if (q >= o->n_quotas) return ARKS_E_INVALID_ARG;
+  int update_cr = 0, update_quota = 0;
+  for (uint32_t j = o->quota_item_off[q]; j < o->quota_item_off[q + 1]; j++) {
+    int ty = o->qitem_type[j];
+    int64_t cur = o->quota_use[(size_t)q * 3 + (size_t)ty];
+    if (*status_present & (1u << ty)) {
+      if (status_used[ty] < cur) { update_cr = 1; status_used[ty] = cur; }
+      else if (status_used[ty] > cur) update_quota = 1;
+    } else { /* add new status */
+      update_cr = 1;
+      *status_present |= 1u << ty;
+      status_used[ty] = cur;
+    }
+  }
+  if (update_quota)
+    for (uint32_t j = o->quota_item_off[q]; j < o->quota_item_off[q + 1]; j++) {
+      int ty = o->qitem_type[j];
+      int64_t* u = &o->quota_use[(size_t)q * 3 + (size_t)ty];
+      if (!restore) *u = 0;
+      else if (status_used[ty] > *u) *u = status_used[ty];
+    }
+  return update_cr | update_quota << 1;
+}
 int ork_snapshot_metrics(ork* o, int64_t* rows) {
   memcpy(rows, o->metrics, (size_t)o->n_qos * ARKS_METRIC_COLS * 8);
   return 0;

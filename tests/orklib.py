@@ -54,6 +54,7 @@ def lib():
         L.ork_incr_quota_usage.argtypes = [C.c_void_p, C.c_uint32, abi.i64p]
         L.ork_snapshot_rate.argtypes = [C.c_void_p, C.c_int64, abi.i64p]
         L.ork_snapshot_metrics.argtypes = [C.c_void_p, abi.i64p]
+        L.ork_sync_quota_usage.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), abi.i64p, C.c_int]
         L.ork_parse_request_body.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
                                              C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                              C.POINTER(C.c_int)]
@@ -122,6 +123,17 @@ class Oracle:
         out = np.zeros((self.tables.n_quotas, 3), np.int64)
         lib().ork_snapshot_quota(self.h, abi.ptr(out, abi.i64p))
         return out
+
+    def sync_quota_usage(self, status_present, status_used, restore=False) -> np.ndarray:
+        """syncQuotaUsage, quota by quota in list order, same in/out convention as Gateway.sync_quota_usage"""
+        action = np.zeros(self.tables.n_quotas, np.uint8)
+        for q in range(self.tables.n_quotas):
+            p = C.c_uint32(int(status_present[q]))
+            u = np.ascontiguousarray(status_used[q], np.int64)
+            action[q] = lib().ork_sync_quota_usage(self.h, q, C.byref(p), abi.ptr(u, abi.i64p), 1 if restore else 0)
+            status_present[q] = p.value
+            status_used[q] = u
+        return action
 
     def snapshot_metrics(self) -> np.ndarray:
         out = np.zeros((self.tables.n_qos, abi.METRIC_COLS), np.int64)
