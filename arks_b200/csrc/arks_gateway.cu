@@ -494,12 +494,24 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
   long long n_g = 0, k = 0, cur[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0}, q_cur = 0, q_lim = 0;
   int32_t qt = ARKS_QUOTA_NONE;
   int quota_fail = -1;  // first over-limit item
+  // Everything a decision may need is fetched in three rounds of independent loads (the kernel is a chain of dependent
+  // global round trips, nothing else): round 1 the qos row, round 2 what the row points at, round 3 their contents.
+  uint32_t i0 = 0, i1 = 0, b0 = 0, b1 = 0;
+  int32_t ep = -1;
+  unsigned long long prand = 0;
   if (slot >= 0) {
     rl0 = T.qos_rl_off[qos];
     rl1 = T.qos_rl_off[qos + 1];
+    qt = T.qos_quota[qos];
+    ep = T.qos_ep[qos];
+    prand = B.pick_rand ? B.pick_rand[i] : 0ull;
     n_g = (long long)B.gcnt[slot] + 1;  // counts start at -1 (single memset of the group table)
 #pragma unroll
     for (int r = 0; r < 4; r++) cur[r] = B.gsnap[(size_t)slot * 4 + r];  // pre-batch values (claimer's snapshot)
+    const uint32_t qs = qt >= 0 ? (uint32_t)qt : 0u, es = ep >= 0 ? (uint32_t)ep : 0u;  // safe rows for the prefetch
+    i0 = T.quota_item_off[qs]; i1 = T.quota_item_off[qs + 1];
+    b0 = T.ep_backend_off[es]; b1 = T.ep_backend_off[es + 1];
+    const long long qu0 = T.quota[(size_t)qs * 3], qu1 = T.quota[(size_t)qs * 3 + 1], qu2 = T.quota[(size_t)qs * 3 + 2];
     for (uint32_t j = rl0; j < rl1; j++) cnt[T.rl_rule[j]]++;
     k = n_g;
     for (uint32_t j = rl0; j < rl1; j++) {
@@ -513,11 +525,10 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
         k = 0;  // "token is not caculated in request": cur + 0 > limit (check.go:124-126)
       }
     }
-    qt = T.qos_quota[qos];
     if (qt >= 0) {
-      uint32_t i0 = T.quota_item_off[qt], i1 = T.quota_item_off[qt + 1];
       for (uint32_t j = i0; j < i1; j++) {
-        long long c = T.quota[(size_t)qt * 3 + T.qitem_type[j]];
+        const int ty = T.qitem_type[j];
+        const long long c = ty == 0 ? qu0 : ty == 1 ? qu1 : qu2;
         if (c > T.qitem_value[j]) { quota_fail = (int)(j - i0); q_cur = c; q_lim = T.qitem_value[j]; break; }
       }
     }
@@ -553,12 +564,10 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
       }
     } else if (B.pick_rand) {
       // Envoy's weighted choice over the HTTPRoute backendRefs order (arksendpoint_controller.go:283-347)
-      int32_t ep = T.qos_ep[qos];
-      uint32_t b0 = T.ep_backend_off[ep], b1 = T.ep_backend_off[ep + 1];
       unsigned long long sum = 0;
       for (uint32_t b = b0; b < b1; b++) sum += (unsigned long long)max(T.backend_weight[b], 0);
       if (sum) {
-        unsigned long long x = B.pick_rand[i] % sum, acc = 0;
+        unsigned long long x = prand % sum, acc = 0;
         for (uint32_t b = b0; b < b1; b++) {
           acc += (unsigned long long)max(T.backend_weight[b], 0);
           if (x < acc) { pick = (int32_t)(b - b0); break; }
