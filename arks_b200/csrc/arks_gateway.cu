@@ -86,6 +86,8 @@ struct ReqDev {  // request batch, device resident
   const uint32_t* token_off;
   const unsigned long long* pick_rand;  // may be null
   uint32_t n;
+  const uint32_t* perm;  // lane -> body: bodies of one warp have (nearly) the same length; null = identity
+  uint32_t bpw;          // bodies per warp (1..32): small batches are spread over more warps, see bodies_per_warp()
   // intermediates
   uint8_t* st_reason;  // static reason after scan (ARKS_R_OK == reached the limiter)
   uint8_t* st_flags;
@@ -121,6 +123,8 @@ struct RespDev {
   const int32_t* qos;
   const uint8_t* flags;
   uint32_t n;
+  const uint32_t* perm;  // lane -> body (see ReqDev)
+  uint32_t bpw;          // bodies per warp
   uint8_t* reason;
   uint8_t* counted;
   long long* usage;  // 3n
@@ -272,12 +276,13 @@ struct WindowPipe {
   }
 };
 // Parse bytes [begin, end) (begin < 16) of 32 spans with machine `m`, one span per lane.
-template <bool EVSYNC, int STAGES, class M>
+// SCHED: 0 = consume_t (any machine), 1 = consume_evsync, 8 = consume_rounds<8> (JsonT; all lanes must call)
+template <int SCHED, int STAGES, class M>
 __device__ __forceinline__ void feed_pipe(M& m, WindowPipe<STAGES>& pipe, uint32_t begin) {
   uint32_t pos = begin;
   const uint32_t end = pipe.end;
   pipe.run([&](uint32_t wbeg, uint32_t lim, auto&& load) {
-    if constexpr (EVSYNC) {
+    if constexpr (SCHED != 0) {
       // special-byte masks of this window's units, computed up front with the warp converged (inside the parse loop the
       // lanes cross unit boundaries at different iterations, so the same code would run ~7 lanes wide)
       uint32_t mk[kUnits / 2];
@@ -290,24 +295,26 @@ __device__ __forceinline__ void feed_pipe(M& m, WindowPipe<STAGES>& pipe, uint32
           mk[j >> 1] |= special_mask16(q.w[0], q.w[1], q.w[2], q.w[3]) << (16 * (j & 1));
         }
       }
-      consume_evsync(m, pos, lim, load, [&](uint32_t u, uint32_t, uint32_t, uint32_t, uint32_t) {
+      auto mask_of = [&](uint32_t u, uint32_t, uint32_t, uint32_t, uint32_t) {
         const uint32_t ul = u - (wbeg >> 4);
         uint32_t w;
         if constexpr (kUnits == 8) w = (ul & 4) ? ((ul & 2) ? mk[3] : mk[2]) : ((ul & 2) ? mk[1] : mk[0]);
         else w = (ul & 2) ? mk[1] : mk[0];
         return (w >> (16 * (ul & 1))) & 0xffffu;
-      });
+      };
+      if constexpr (SCHED == 1) consume_evsync(m, pos, lim, load, mask_of);
+      else consume_rounds<SCHED>(m, pos, lim, load, mask_of);
     } else {
       consume_t(m, pos, lim, load);
     }
     if (m.dead()) pos = end;  // nothing further can change the verdict
   });
 }
-template <int STAGES = kStages, bool EVSYNC = false, class M>
+template <int STAGES = kStages, int SCHED = 0, class M>
 __device__ __forceinline__ void feed_tiled(M& m, const uint8_t* body, uint32_t begin, uint32_t end, uint8_t* warp_smem) {
   WindowPipe<STAGES> pipe;
   pipe.start(body, end, warp_smem);
-  feed_pipe<EVSYNC>(m, pipe, begin);
+  feed_pipe<SCHED>(m, pipe, begin);
 }
 
 __device__ __forceinline__ unsigned long long fnv1a64(const uint8_t* p, uint32_t n) {
@@ -335,13 +342,75 @@ __device__ bool model_equals(const uint8_t* body, const JsonCold& m, const uint8
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lane assignment: bodies are handed to lanes in order of length (counting sort, arbitrary order inside a bucket). Lanes of a warp run in lock step window by window, so a warp is as slow as its longest / densest
+// body; with equal lengths, bodies that share a shape (the completions of one serving stack, the requests of one
+// application) also reach their structure-dense regions in the same windows. Measured on B200, 65 536 completions of
+// one shape with lengths 330-1000 B: 584 us in arrival order, 118 us in length order. Decisions do not depend on the
+// assignment: every output is indexed by the body, and arrival order enters only through limit_admit's ranks.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLenBuckets = 4096;  // byte-exact below 2 KiB (a one-byte offset already misaligns two bodies), 32-byte steps above
+__device__ __forceinline__ uint32_t len_bucket(uint32_t len) {
+  return len < 2048u ? len : min(2048u + ((len - 2048u) >> 5), (uint32_t)kLenBuckets - 1u);
+}
+
+__global__ void len_hist_kernel(const uint32_t* body_len, uint32_t n, uint32_t* hist) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const uint32_t b = live ? len_bucket(body_len[i]) : 0xffffffffu;
+  const unsigned peers = __match_any_sync(0xffffffffu, b);  // one atomic per distinct bucket in the warp
+  if (live && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[b], (uint32_t)__popc(peers));
+}
+// exclusive scan of the kLenBuckets counters in place (one block of 1024 threads, 4 counters each)
+__global__ void __launch_bounds__(1024) len_scan_kernel(uint32_t* hist) {
+  __shared__ uint32_t warp_tot[32];
+  const uint32_t t = threadIdx.x;
+  uint32_t v[4], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = hist[4 * t + k]; sum += v[k]; }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((t & 31) >= (uint32_t)d) incl += o;
+  }
+  if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    uint32_t w = warp_tot[t], wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+      if (t >= (uint32_t)d) wi += o;
+    }
+    warp_tot[t] = wi - w;
+  }
+  __syncthreads();
+  uint32_t base = warp_tot[t >> 5] + incl - sum;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { hist[4 * t + k] = base; base += v[k]; }
+}
+__global__ void len_scatter_kernel(const uint32_t* body_len, uint32_t n, uint32_t* offs, uint32_t* perm) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const uint32_t b = live ? len_bucket(body_len[i]) : 0xffffffffu;
+  const unsigned peers = __match_any_sync(0xffffffffu, b);
+  const int leader = __ffs(peers) - 1;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (live && (int)lane == leader) base = atomicAdd(&offs[b], (uint32_t)__popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (live) perm[base + __popc(peers & ((1u << lane) - 1u))] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
 // kernel 1: scan_request — A3 (body parse), A4 (GetQosByToken), A5 (GetModelList) of SURVEY.md §8a
 // ------------------------------------------------------------------------------------------------
-template <bool EVSYNC>
+template <int SCHED>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_request_kernel(DevTables T, ReqDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < B.n;
+  const uint32_t lane_id = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * B.bpw + (threadIdx.x & 31);
+  const bool live = (threadIdx.x & 31) < B.bpw && lane_id < B.n;
+  const uint32_t i = live ? (B.perm ? B.perm[lane_id] : lane_id) : 0;  // the body this lane parses
   const uint8_t* body = B.bodies + (live ? B.body_off[i] : 0);
   const uint32_t len = live ? B.body_len[i] : 0;
 
@@ -378,7 +447,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_request_
   JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
   JsonT m;
   m.init(K_REQ, body, stack_words, &cold, tabs);
-  feed_pipe<EVSYNC>(m, pipe, 0);
+  feed_pipe<SCHED>(m, pipe, 0);
   if (!live) return;
 
   uint8_t reason = ARKS_R_OK, flags = 0, claimer = 0;
@@ -744,11 +813,12 @@ struct RespM<0> {
   }
 };
 
-template <int MODE, bool EVSYNC = false>
+template <int MODE, int SCHED = 0>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response_kernel(DevTables T, RespDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool live = i < B.n;
+  const uint32_t lane_id = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * B.bpw + (threadIdx.x & 31);
+  const bool live = (threadIdx.x & 31) < B.bpw && lane_id < B.n;
+  const uint32_t i = live ? (B.perm ? B.perm[lane_id] : lane_id) : 0;  // the body this lane parses
   uint8_t reason = ARKS_R_OK, counted = 0;
   long long u0 = 0, u1 = 0, u2 = 0;
   int32_t qos = 0;
@@ -771,8 +841,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response
     const bool is_sse = MODE == 2 || (MODE == 0 && (fl & ARKS_RESP_STREAM));
     JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
     rm.init(is_sse, body, stack_words, &cold, tabs);
-    if constexpr (EVSYNC) feed_pipe<true>(rm.json(), pipe, 0);
-    else feed_pipe<false>(rm, pipe, 0);
+    if constexpr (SCHED != 0) feed_pipe<SCHED>(rm.json(), pipe, 0);
+    else feed_pipe<0>(rm, pipe, 0);
     if (live) {
       if (is_sse) {  // handle_response.go:113-133, every chunk in isolation
         if (!rm.finish(len, u0, u1, u2)) reason = ARKS_R_STREAMING;
@@ -803,16 +873,17 @@ constexpr int kSseStages = ARKS_SSE_STAGES;
 constexpr int kSseEvCap = 320;  // events per warp tile (32 chunks); a chunk that does not fit is parsed sequentially
 constexpr int kSseSmemPerBlock = kWarpsPerBlock * kSseStages * kStageBytes;
 
-template <bool EVSYNC>
+template <int SCHED>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, ARKS_SSE_MINBLK) scan_sse_kernel(DevTables T, RespDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(16) JsonSmem<false, true> json_smem;
   __shared__ uint2 s_desc[kWarpsPerBlock][kSseEvCap];  // x: byte offset of the payload in B.bodies; y: len | owner<<16 | seq<<21
   __shared__ long long s_usage[kWarpsPerBlock][32][3];
   __shared__ uint32_t s_best[kWarpsPerBlock][32], s_fail[kWarpsPerBlock][32], s_n[kWarpsPerBlock];
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool live = i < B.n;
+  const uint32_t lane_id = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * B.bpw + lane;
+  const bool live = lane < B.bpw && lane_id < B.n;
+  const uint32_t i = live ? (B.perm ? B.perm[lane_id] : lane_id) : 0;  // the chunk this lane cuts and accounts
   uint8_t* wsmem = smem + warp * (kSseStages * kStageBytes);
   const JsonTables tabs = json_smem.stage_async();
   const uint32_t chunk_off = live ? B.body_off[i] : 0;
@@ -863,7 +934,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, ARKS_SSE_MINBLK) scan_sse
     const uint32_t begin = d.x & 15u, end = has ? begin + (d.y & 0xffffu) : 0u;
     JsonT ev;
     ev.init(K_EVT, base, stack_words, &cold, tabs);
-    feed_tiled<kSseStages, EVSYNC>(ev, base, begin, end, wsmem);
+    feed_tiled<kSseStages, SCHED>(ev, base, begin, end, wsmem);
     bool wins = false;
     if (has) {
       const SseEventVerdict v = sse_event_verdict(ev, end);
@@ -1006,11 +1077,15 @@ struct arks_ctx {
   uint32_t fetch_n = 0;          // batch size of the last run_* call (what fetch_* copies back)
   // optional per-kernel timing (bench roofline): events around each launch of the last run_* call
   bool prof = false;
-  int evsync = 6;  // which scans run the event-synchronised schedule (consume_evsync): 1 request, 2 JSON response, 4 SSE event phase; ARKS_EVSYNC overrides (A/B)
+  int sched[3] = {8, 8, 1};  // parse schedule of the request scan, the JSON response scan, the SSE event phase: 0 consume_t,
+                             // 1 consume_evsync, 8 consume_rounds<8> (json_engine.cuh). ARKS_SCHED="r,p,s" overrides (A/B runs)
   bool sse_sequential = false;  // ARKS_SSE_SEQUENTIAL=1: all-SSE batches use scan_response_kernel<2> (A/B measurements)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int ev_n = 0;
   uint8_t* d_inter = nullptr;    // intermediates + group table
+  uint32_t* d_perm = nullptr;    // lane -> body permutation of the batch being scanned (length order)
+  uint32_t* d_lenhist = nullptr; // kLenBuckets counters / offsets
+  bool sort_lanes = true;        // ARKS_SORT=0 scans in arrival order (A/B runs)
   uint8_t* d_result = nullptr;   // packed results
   size_t result_cap = 0;
   uint32_t gsize = 0;
@@ -1088,7 +1163,14 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   arks_ctx* ctx = new arks_ctx();
   ctx->device = device;
   if (const char* e = getenv("ARKS_SSE_SEQUENTIAL")) ctx->sse_sequential = e[0] == '1';
-  if (const char* e = getenv("ARKS_EVSYNC")) ctx->evsync = atoi(e);
+  if (const char* e = getenv("ARKS_SORT")) ctx->sort_lanes = e[0] != '0';
+  if (const char* e = getenv("ARKS_SCHED")) {
+    int a = 8, b = 8, c = 8;
+    if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3) {
+      auto ok = [](int v) { return v == 0 || v == 1 || v == 8; };
+      if (ok(a) && ok(b) && ok(c)) { ctx->sched[0] = a; ctx->sched[1] = b; ctx->sched[2] = c; }
+    }
+  }
   ctx->max_batch = max_batch;
   ctx->max_bytes = align_up(max_batch_bytes + 16, 256);
   for (int r = 0; r < 4; r++) ctx->last_win[r] = INT64_MIN;
@@ -1100,20 +1182,23 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   // meta: body_off, body_len, token_off(n+1), pick_rand, qos, flags + token bytes (256 B per request budget)
   ctx->meta_cap = align_up(n * 4, 256) * 4 + align_up(n * 8, 256) + align_up(n, 256) + align_up(n * 256, 256);
   for (int k = 0; k < 4; k++) CK(cudaEventCreate(&ctx->ev[k]));
-  CK(cudaFuncSetAttribute(scan_request_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
-  CK(cudaFuncSetAttribute(scan_request_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
-  CK((cudaFuncSetAttribute(scan_response_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock)));
+#define ARKS_FOR_SCHED(X) X(0) X(1) X(8)
+#define ARKS_SET(S)                                                                                                        \
+  CK(cudaFuncSetAttribute(scan_request_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));            \
+  CK((cudaFuncSetAttribute(scan_response_kernel<1, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock)));      \
+  CK(cudaFuncSetAttribute(scan_sse_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSseSmemPerBlock));
+  ARKS_FOR_SCHED(ARKS_SET)
+#undef ARKS_SET
   CK(cudaFuncSetAttribute(scan_response_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
-  CK(cudaFuncSetAttribute(scan_response_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
   CK(cudaFuncSetAttribute(scan_response_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
-  CK(cudaFuncSetAttribute(scan_sse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSseSmemPerBlock));
-  CK(cudaFuncSetAttribute(scan_sse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSseSmemPerBlock));
   uint32_t g = 64;
   while (g < 2 * n) g <<= 1;
   ctx->gsize = g;
   size_t inter = align_up(n, 256) * 2 + align_up(n * 4, 256) * 5 + align_up((size_t)g * 4, 256) * 3 + (size_t)g * 32 + 2048 +
                  align_up((n / kHotGroup + 2) * 4, 256);
   CK(cudaMalloc(&ctx->d_inter, inter));
+  CK(cudaMalloc(&ctx->d_perm, (size_t)4 * max_batch + 256));
+  CK(cudaMalloc(&ctx->d_lenhist, (size_t)4 * kLenBuckets));
   ctx->result_cap = align_up(n, 256) * 3 + align_up(n * 4, 256) * 3 + align_up(n * 8, 256) * 3;
   CK(cudaMalloc(&ctx->d_result, ctx->result_cap));
   return 0;
@@ -1154,6 +1239,8 @@ void arks_destroy(arks_ctx* ctx) {
   for (int k = 0; k < 4; k++)
     if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
   cudaFree(ctx->d_inter);
+  cudaFree(ctx->d_perm);
+  cudaFree(ctx->d_lenhist);
   cudaFree(ctx->d_result);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
@@ -1527,6 +1614,28 @@ static void carve_request(arks_ctx* ctx, ReqDev& r, size_t batch_n) {
   r.limit_max = (long long*)(q + offs[7]);
 }
 
+// A warp is as slow as its slowest body and pays for every code path any of its lanes takes, so a small batch is spread
+// over more warps with fewer bodies each (the SMs are idle anyway): about 2048 warps, the number one full wave keeps
+// resident, is the target. 64 requests -> 64 warps of one body; 65 536 -> 2048 warps of 32.
+static uint32_t bodies_per_warp(uint32_t n) {
+  const uint32_t b = (n + 2047) / 2048;
+  return b < 1 ? 1 : b > 32 ? 32 : b;
+}
+static uint32_t scan_grid(uint32_t n, uint32_t bpw) { return ((n + bpw - 1) / bpw + kWarpsPerBlock - 1) / kWarpsPerBlock; }
+
+// batches below this size are a handful of warps: the three small launches would cost more than they save
+constexpr uint32_t kSortMinBatch = 4096;
+// queue the counting sort by body length; returns the permutation (device pointer) or null when the batch is scanned as is
+static const uint32_t* queue_length_order(arks_ctx* ctx, const uint32_t* d_body_len, uint32_t n) {
+  if (!ctx->sort_lanes || n < kSortMinBatch) return nullptr;
+  cudaMemsetAsync(ctx->d_lenhist, 0, (size_t)4 * kLenBuckets, ctx->stream);
+  len_hist_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_body_len, n, ctx->d_lenhist);
+  len_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_lenhist);
+  len_scatter_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_body_len, n, ctx->d_lenhist, ctx->d_perm);
+  ctx->launches += 3;
+  return ctx->d_perm;
+}
+
 int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   if (!ctx || !ctx->loaded) return ARKS_E_INVALID_ARG;
   arks_ctx::Slot& sl = ctx->slots[ctx->cur];
@@ -1552,8 +1661,13 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   CK(cudaMemsetAsync(r.gkey, 0xff, (size_t)g * 12 + 4, ctx->stream));
   const uint32_t tpb = kWarpsPerBlock * 32;
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  if (ctx->evsync & 1) scan_request_kernel<true><<<(n + tpb - 1) / tpb, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, r);
-  else scan_request_kernel<false><<<(n + tpb - 1) / tpb, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, r);
+  r.perm = queue_length_order(ctx, r.body_len, n);
+  r.bpw = bodies_per_warp(n);
+  switch (ctx->sched[0]) {
+#define ARKS_LAUNCH(S) case S: scan_request_kernel<S><<<scan_grid(n, r.bpw), tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, r); break;
+    ARKS_FOR_SCHED(ARKS_LAUNCH)
+#undef ARKS_LAUNCH
+  }
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   if (n > (uint32_t)kHotGroup) {  // a group can only be hot if the batch is larger than the threshold
     rank_hot_groups_kernel<<<296, 256, 0, ctx->stream>>>(r);  // exits at once when scan_request listed no hot group
@@ -1689,11 +1803,22 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
   const uint32_t tpb = kWarpsPerBlock * 32;
   CK(cudaStreamWaitEvent(ctx->stream, sl.resp_copied, 0));
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  const dim3 grid((n + tpb - 1) / tpb);
-  if (sl.resp_mode == 1 && (ctx->evsync & 2)) scan_response_kernel<1, true><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
-  else if (sl.resp_mode == 1) scan_response_kernel<1><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
-  else if (sl.resp_mode == 2 && !ctx->sse_sequential && (ctx->evsync & 4)) scan_sse_kernel<true><<<grid, tpb, kSseSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
-  else if (sl.resp_mode == 2 && !ctx->sse_sequential) scan_sse_kernel<false><<<grid, tpb, kSseSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
+  sl.rp.perm = queue_length_order(ctx, sl.rp.body_len, n);
+  sl.rp.bpw = bodies_per_warp(n);
+  const dim3 grid(scan_grid(n, sl.rp.bpw));
+  if (sl.resp_mode == 1) {
+    switch (ctx->sched[1]) {
+#define ARKS_LAUNCH(S) case S: scan_response_kernel<1, S><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp); break;
+      ARKS_FOR_SCHED(ARKS_LAUNCH)
+#undef ARKS_LAUNCH
+    }
+  } else if (sl.resp_mode == 2 && !ctx->sse_sequential) {
+    switch (ctx->sched[2]) {
+#define ARKS_LAUNCH(S) case S: scan_sse_kernel<S><<<grid, tpb, kSseSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp); break;
+      ARKS_FOR_SCHED(ARKS_LAUNCH)
+#undef ARKS_LAUNCH
+    }
+  }
   else if (sl.resp_mode == 2) scan_response_kernel<2><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
   else scan_response_kernel<0><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
   if (ctx->prof) { CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_n = 2; }

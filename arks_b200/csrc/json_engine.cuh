@@ -618,6 +618,81 @@ ARKS_HD void consume_t(M& m, uint32_t& pos, uint32_t lim, L&& load, K&& mask_of)
 // When the 32 documents of a warp share a template (frames of one SSE stream format, completions of one server) the
 // k-th event of every lane is the same kind, so event() runs with the warp converged instead of ~10 lanes wide;
 // documents that do not line up only cost idle lanes, never a different result.
+// ---------------------------------------------------------------------------------------------
+// consume_rounds — the schedule the scan kernels use for heterogeneous documents. One round = up to R ordinary
+// advances per lane (a bulk skip and / or one table step each), then ONE event per lane for the lanes that ran into
+// one, then the warp re-converges (__syncwarp). Without the forced re-convergence the lanes of a warp whose documents
+// differ drift apart for good (Volta+ schedules diverged lanes independently and a loop with early exits has no
+// convergence point inside): measured on B200, 32 different chat requests per warp ran 4.4 lanes wide, 8x slower
+// than 32 identical ones. With rounds, a lane that reaches an event early idles for at most R-1 short advances, and
+// the expensive event code runs once per round instead of once per byte position of any lane.
+// ALL 32 lanes of the warp must call this together (lanes without work pass pos >= lim). Host build: a plain loop.
+// ---------------------------------------------------------------------------------------------
+template <int R, class L, class K>
+ARKS_HD void consume_rounds(JsonT& m, uint32_t& pos, uint32_t lim, L&& load, K&& mask_of) {
+  uint32_t cu = 0xffffffffu, q0 = 0, q1 = 0, q2 = 0, q3 = 0, umask = 0;
+#ifdef __CUDA_ARCH__
+  while (__any_sync(0xffffffffu, pos < lim)) {
+#else
+  while (pos < lim) {
+#endif
+    uint32_t t = 0, k = 0;
+    uint8_t c = 0;
+    bool ev = false;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (int r = 0; r < R; r++) {
+      if (!ev && pos < lim) {
+        uint32_t o = pos & 15;
+        if ((pos >> 4) != cu) {
+          cu = pos >> 4;
+          const Unit16 q = load(cu);
+          q0 = q.w[0]; q1 = q.w[1]; q2 = q.w[2]; q3 = q.w[3];
+          umask = mask_of(cu, q0, q1, q2, q3);
+        }
+        bool more = true;
+        if (m.can_fast()) {
+          const uint32_t rest = umask >> o;
+          uint32_t run = rest ? first_set(rest) : 16u - o;
+          const uint32_t avail = lim - pos;
+          if (run > avail) run = avail;
+          if (run) {
+            m.skip(run, o, q0, q1, q2, q3);
+            pos += run;
+            o += run;
+          }
+          more = (o < 16) & (pos < lim);
+        }
+        if (more) {
+          const uint32_t lo = (o & 8) ? q2 : q0, hi = (o & 8) ? q3 : q1;
+          const uint32_t w = (o & 4) ? hi : lo;
+          c = (uint8_t)(w >> (8 * (o & 3)));
+          k = m.cls[c];
+          t = m.tab[m.ss * kJsonClasses + k];
+          if (t >= EV_BASE) {
+            ev = true;
+          } else {
+            const uint32_t ps = m.ss;
+            m.ss = t;
+            if (m.hb & JsonT::kSideMask) m.side_work(ps, c, pos);
+            pos++;
+            if (m.dead()) pos = lim;
+          }
+        }
+      }
+    }
+    if (ev) {
+      m.event(t, k, c, pos);
+      pos++;
+      if (m.dead()) pos = lim;
+    }
+#ifdef __CUDA_ARCH__
+    __syncwarp();
+#endif
+  }
+}
+
 struct MaskOnTheSpot {
   ARKS_HD uint32_t operator()(uint32_t, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) const { return special_mask16(q0, q1, q2, q3); }
 };
@@ -672,5 +747,8 @@ ARKS_HD void consume_evsync(JsonT& m, uint32_t& pos, uint32_t lim, L&& load, K&&
 
 template <class L>
 ARKS_HD void consume_evsync(JsonT& m, uint32_t& pos, uint32_t lim, L&& load) { consume_evsync(m, pos, lim, load, MaskOnTheSpot()); }
+
+template <int R, class L>
+ARKS_HD void consume_rounds(JsonT& m, uint32_t& pos, uint32_t lim, L&& load) { consume_rounds<R>(m, pos, lim, load, MaskOnTheSpot()); }
 
 }  // namespace arks

@@ -42,6 +42,122 @@ def chat_request_body(rng, size: int = 1024, stream: bool = False) -> bytes:
     return (head + _text(rng, size - len(head) - len(tail)) + tail).encode()
 
 
+# ---- varied traffic: what a gateway in front of many different clients sees ------------------------------------
+_ESC = ['\\n', '\\"', '\\t', '\\u00e9', '\\u4f60\\u597d', '\\\\', '\\/']
+
+
+def _prose(rng, nbytes: int) -> str:
+    """text for a JSON string: words, with the escapes real prompts carry (newlines, quotes, \\u sequences) and some
+    raw UTF-8, at irregular positions"""
+    out, n = [], 0
+    while n < nbytes:
+        r = rng.random()
+        if r < 0.04:
+            w = _ESC[int(rng.integers(len(_ESC)))]
+        elif r < 0.06:
+            w = ("é", "你好", "—", "🙂")[int(rng.integers(4))]
+        else:
+            w = WORDS[int(rng.integers(len(WORDS)))]
+        out.append(w)
+        n += len(w.encode()) + 1
+    return " ".join(out)
+
+
+class ClientApp:
+    """One application talking to the gateway: it always sends the same parameters in the same order, the same system
+    prompt and the same JSON style (that is what an SDK call site produces); what changes per request is the
+    conversation — how many turns and how long each one is."""
+
+    def __init__(self, rng):
+        params = []
+        if rng.random() < 0.5: params.append('"temperature":%s' % ("0.7", "1", "0", "0.25")[int(rng.integers(4))])
+        if rng.random() < 0.5: params.append('"max_tokens":%d' % int(rng.integers(16, 4096)))
+        if rng.random() < 0.3: params.append('"top_p":0.%d' % int(rng.integers(1, 10)))
+        if rng.random() < 0.2: params.append('"user":"u-%06d"' % int(rng.integers(10**6)))
+        if rng.random() < 0.15: params.append('"stop":["\\n\\n","###"]')
+        if rng.random() < 0.1: params.append('"presence_penalty":0,"frequency_penalty":0.5')
+        if rng.random() < 0.1: params.append('"response_format":{"type":"json_object"}')
+        if rng.random() < 0.1: params.append('"n":1,"seed":%d' % int(rng.integers(1 << 31)))
+        self.explicit_no_stream = rng.random() < 0.3
+        rng.shuffle(params)
+        self.params = params
+        self.cut = int(rng.integers(len(params) + 1))
+        self.system = _prose(rng, int(rng.integers(40, 400))) if rng.random() < 0.5 else None
+        self.sep = ("", " ")[int(rng.random() < 0.15)]       # some clients pretty-print a little
+        self.model_first = rng.random() >= 0.3               # model is not always the first key
+        self.max_turns = int(rng.integers(1, 7))
+
+
+_APPS = {}
+
+
+def client_apps(n_apps: int = 256, seed: int = 0xC11E):
+    apps = _APPS.get((n_apps, seed))
+    if apps is None:
+        r = np.random.default_rng(seed)
+        apps = _APPS[(n_apps, seed)] = [ClientApp(r) for _ in range(n_apps)]
+    return apps
+
+
+def chat_request_body_varied(rng, mean_size: int = 1024, stream: bool = False, app: ClientApp = None) -> bytes:
+    """An OpenAI chat request from one of a few hundred client applications (ClientApp): per-app parameters, key order,
+    system prompt and JSON style; per-request 1..max_turns turns of very different lengths, total size spread around
+    `mean_size` (roughly 0.4x-1.7x)."""
+    if app is None:
+        apps = client_apps()
+        app = apps[int(rng.integers(len(apps)))]
+    target = int(mean_size * (0.34 + 1.32 * rng.random()))
+    params = list(app.params)
+    tail = []
+    if stream:
+        tail = ['"stream":true', '"stream_options":{"include_usage":true}']
+    elif app.explicit_no_stream:
+        tail = ['"stream":false']
+    n_turns = int(rng.integers(1, app.max_turns + 1))
+    roles = [("user", "assistant")[k % 2] for k in range(n_turns)]
+    if roles[-1] != "user":
+        roles.append("user")
+    budget = max(target - (len(app.system) if app.system else 0) - 80, 32)
+    shares = rng.random(len(roles)) ** 2 + 0.02
+    shares = shares / shares.sum()
+    msgs = (['{"role":"system","content":"%s"}' % app.system] if app.system else []) + \
+           ['{"role":"%s","content":"%s"}' % (r, _prose(rng, max(int(budget * sh) - 40, 1))) for r, sh in zip(roles, shares)]
+    sep = app.sep
+    model = ['"model":"%s"' % MODEL]
+    messages = ['"messages":%s[%s]' % (sep, ("," + sep).join(msgs))]
+    if app.model_first:
+        fields = model + params[:app.cut] + messages + params[app.cut:] + tail
+    else:
+        fields = params[:app.cut] + messages + model + params[app.cut:] + tail
+    return ("{" + ("," + sep).join(fields) + "}").encode()
+
+
+def chat_response_body_varied(rng, prompt: int, completion: int, mean_size: int = 600) -> bytes:
+    """A non-streaming completion as vLLM / SGLang / OpenAI-compatible servers write it: field sets and order differ,
+    content length spread around `mean_size`."""
+    content = _prose(rng, max(int(mean_size * (0.3 + 1.4 * rng.random())) - 395, 4))
+    style = int(rng.integers(3))
+    usage_fields = ['"prompt_tokens":%d' % prompt, '"completion_tokens":%d' % completion, '"total_tokens":%d' % (prompt + completion)]
+    if style == 0:
+        usage_fields = [usage_fields[0], usage_fields[2], usage_fields[1], '"prompt_tokens_details":null']
+    elif style == 1:
+        usage_fields.append('"prompt_tokens_details":{"cached_tokens":%d},"completion_tokens_details":{"reasoning_tokens":0}'
+                            % int(rng.integers(0, prompt + 1)))
+    usage = '"usage":{%s}' % ",".join(usage_fields)
+    msg = '"message":{"role":"assistant","content":"%s"%s}' % (
+        content, ("", ',"reasoning_content":null,"tool_calls":null', ',"refusal":null,"annotations":[]')[style])
+    choice = '{"index":0,%s,"logprobs":null,"finish_reason":"%s"%s}' % (
+        msg, ("stop", "length")[int(rng.random() < 0.2)], (',"matched_stop":151645', "", ',"stop_reason":null')[style])
+    head = ['"id":"chatcmpl-%08x"' % int(rng.integers(1 << 32)), '"object":"chat.completion"', '"created":17%08d' % int(rng.integers(10**8)),
+            '"model":"%s"' % MODEL]
+    if style == 2:
+        head.append('"system_fingerprint":"fp_%06x","service_tier":"default"' % int(rng.integers(1 << 24)))
+    body = head + ['"choices":[%s]' % choice, usage]
+    if style == 1:  # usage before choices
+        body = head + [usage, '"choices":[%s]' % choice]
+    return ("{" + ",".join(body) + "}").encode()
+
+
 _FILL = {}
 
 
@@ -139,22 +255,25 @@ class Workload:
         return rng.choice(self.n_tenants, size=n, p=self.popularity)
 
     def request_batch(self, n: int, now_unix: int, seed: int = 1, body_size: int = 1024, stream_frac: float = 0.0,
-                      noise_frac: float = 0.0, n_templates: int = 0) -> RequestBatch:
+                      noise_frac: float = 0.0, n_templates: int = 0, varied: bool = False) -> RequestBatch:
         """n requests from tenants drawn by popularity. `noise_frac` mixes in malformed / unauthorised requests
-        (parity tests); `n_templates` > 0 reuses that many distinct bodies (faster generation for big waves)."""
+        (parity tests); `n_templates` > 0 reuses that many distinct bodies (faster generation for big waves);
+        `varied`: bodies differ in structure and size (mean `body_size`) instead of one fixed shape of exactly
+        `body_size` bytes."""
         rng = np.random.default_rng([self.seed, seed])
         tenants = self.draw_tenants(rng, n)
         bodies, tokens = [], []
         templ = None
+        make = chat_request_body_varied if varied else chat_request_body
         if n_templates:
-            templ = [chat_request_body(rng, body_size, stream=(k < n_templates * stream_frac)) for k in range(n_templates)]
+            templ = [make(rng, body_size, stream=(k < n_templates * stream_frac)) for k in range(n_templates)]
         noise = rng.random(n) < noise_frac if noise_frac > 0 else np.zeros(n, bool)
         for i in range(n):
             tok = self.token_strings[int(tenants[i])]
             if templ is not None:
                 body = templ[int(rng.integers(n_templates))]
             else:
-                body = chat_request_body(rng, body_size, stream=bool(rng.random() < stream_frac))
+                body = make(rng, body_size, stream=bool(rng.random() < stream_frac))
             if noise[i]:
                 k = int(rng.integers(8))
                 if k == 0:
@@ -179,11 +298,16 @@ class Workload:
         return RequestBatch.from_lists(bodies, tokens, now_unix, pick_rand=pick)
 
     def response_batch(self, req_result: RequestResult, now_unix: int, seed: int = 2, body_size: int = 600,
-                       sse_total: int = 4096, noise_frac: float = 0.0) -> ResponseBatch:
+                       sse_total: int = 4096, noise_frac: float = 0.0, varied: bool = False, n_templates: int = 0) -> ResponseBatch:
         """One response (non-stream: the complete body; stream: its final SSE chunk preceded by its content chunks)
-        for every admitted request of `req_result`."""
+        for every admitted request of `req_result`. `varied`: completions differ in field set, order and size (mean
+        `body_size`); `n_templates` > 0 (with `varied`) draws every non-stream body from that many pre-generated ones."""
         rng = np.random.default_rng([self.seed, seed])
         bodies, qos, flags = [], [], []
+        templ = None
+        if varied and n_templates:
+            templ = [chat_response_body_varied(rng, int(rng.integers(50, 401)), int(rng.integers(1, 513)), body_size)
+                     for _ in range(n_templates)]
         for i in np.nonzero(req_result.reason == abi.R_OK)[0]:
             prompt, completion = int(rng.integers(50, 401)), int(rng.integers(1, 513))
             if req_result.flags[i] & 1:
@@ -192,7 +316,10 @@ class Workload:
                     qos.append(int(req_result.qos[i]))
                     flags.append(abi.RESP_STREAM)
             else:
-                body = chat_response_body(rng, prompt, completion, body_size)
+                if templ is not None:
+                    body = templ[int(rng.integers(n_templates))]
+                else:
+                    body = (chat_response_body_varied if varied else chat_response_body)(rng, prompt, completion, body_size)
                 if noise_frac and rng.random() < noise_frac:
                     k = int(rng.integers(4))
                     if k == 0:

@@ -37,6 +37,7 @@ TENANTS = 10_000
 BODY = 1024
 RESP_BODY = 600
 N_WAVES = 3
+N_TEMPL = 0  # 0: every request / completion of a wave is generated on its own (no repeated bodies)
 NOW0 = 1_700_000_000
 STEP_S = 86_400  # `now` advances one day per step: fresh rpm/tpm and rpd/tpd windows each step (stationary admission pattern)
 
@@ -101,7 +102,7 @@ class ClockSampler:
 def build_waves(workload, n_waves, wave, rank):
     """n_waves distinct (request wave, matching response wave) pairs; responses answer the requests the ORACLE-FREE
     first pass admits, so they are produced after a dry request pass on the device (see run_b200)."""
-    return [workload.request_batch(wave, NOW0, seed=1000 + 17 * rank + k, body_size=BODY, n_templates=512)
+    return [workload.request_batch(wave, NOW0, seed=1000 + 17 * rank + k, body_size=BODY, n_templates=N_TEMPL, varied=True)
             for k in range(n_waves)]
 
 
@@ -133,9 +134,9 @@ def cpu_baseline(workload, wave, seconds=12.0, threads=None):
     import orklib
     threads = threads or (os.cpu_count() or 1)
     o = orklib.Oracle(workload.tables)
-    req = workload.request_batch(wave, NOW0, seed=4242, body_size=BODY, n_templates=512)
+    req = workload.request_batch(wave, NOW0, seed=4242, body_size=BODY, n_templates=N_TEMPL, varied=True)
     a = o.request_batch(req, threads=threads)
-    resp = workload.response_batch(a, NOW0 + 1, seed=4243, body_size=RESP_BODY)
+    resp = workload.response_batch(a, NOW0 + 1, seed=4243, body_size=RESP_BODY, varied=True, n_templates=N_TEMPL)
     o.response_batch(resp, threads=threads)
     now, done, t_used, steps = NOW0 + STEP_S, 0, 0.0, 0
     while t_used < seconds and steps < 400:
@@ -162,9 +163,9 @@ def run_reference(args):
     import orklib
     threads = os.cpu_count() or 1
     o = orklib.Oracle(w.tables)
-    req = w.request_batch(args.wave, NOW0, seed=1000, body_size=BODY, n_templates=512)
+    req = w.request_batch(args.wave, NOW0, seed=1000, body_size=BODY, n_templates=N_TEMPL, varied=True)
     a = o.request_batch(req, threads=threads)
-    resp = w.response_batch(a, NOW0 + 1, seed=2000, body_size=RESP_BODY)
+    resp = w.response_batch(a, NOW0 + 1, seed=2000, body_size=RESP_BODY, varied=True, n_templates=N_TEMPL)
     o.response_batch(resp, threads=threads)
     now = NOW0 + STEP_S
     for _ in range(args.warmup):
@@ -195,9 +196,11 @@ def run_reference(args):
 
 def workload_config(args, world):
     return {"workload": f"BASELINE config 2: {args.wave} concurrent non-streaming /v1/chat/completions requests per wave, "
-                        f"{BODY} B prompts (OpenAI chat JSON, model qwen-7b), {args.tenants} tenants "
-                        f"(ArksToken+ArksQuota+ArksEndpoint each, rpm/tpm/rpd/tpd + 3-item quota), ~{RESP_BODY} B completion "
-                        f"JSON with usage; request phase + response phase per step",
+                        f"~{BODY} B prompts on average (OpenAI chat JSON, model qwen-7b; every body distinct: 256 client applications "
+                        f"with their own parameters, key order, system prompt and JSON style, 1-6 turns of random lengths, escapes and "
+                        f"UTF-8 in the text: 0.3-1.7 KiB), {args.tenants} tenants "
+                        f"(ArksToken+ArksQuota+ArksEndpoint each, rpm/tpm/rpd/tpd + 3-item quota), ~{RESP_BODY} B completion JSON with "
+                        f"usage in three server dialects; request phase + response phase per step",
             "tenants_per_gpu": args.tenants, "requests_per_wave_per_gpu": args.wave, "parallelism": f"tenant-sharded x{world}",
             "l2": f"inputs larger than L2: {N_WAVES} distinct waves rotate through staging slots (~{N_WAVES * (args.wave * (BODY + RESP_BODY)) >> 20} MiB)"}
 
@@ -228,7 +231,8 @@ def run_b200(args):
     for k, rb in enumerate(reqs):
         rb.now_unix = NOW0 + STEP_S * k
         a = g.handle_request_body(rb)
-        resps.append(pin_batch(w.response_batch(a, NOW0 + STEP_S * k + 1, seed=3000 + k, body_size=RESP_BODY)))
+        resps.append(pin_batch(w.response_batch(a, NOW0 + STEP_S * k + 1, seed=3000 + k, body_size=RESP_BODY, varied=True,
+                                                n_templates=N_TEMPL)))
     req_out = [abi.RequestResult.empty(b.n) for b in reqs]
     resp_out = [abi.ResponseResult.empty(b.n) for b in resps]
     now = NOW0 + STEP_S * N_WAVES
@@ -324,7 +328,7 @@ def run_b200(args):
     if rank == 0:
         g.select_slot(0)
         for bs in (64, 256, 1024, 4096):
-            small = pin_batch(w.request_batch(bs, now, seed=7000 + bs, body_size=BODY, n_templates=64))
+            small = pin_batch(w.request_batch(bs, now, seed=7000 + bs, body_size=BODY, n_templates=64, varied=True))
             out_small = abi.RequestResult.empty(bs)
             ts = []
             for it in range(220):
@@ -344,7 +348,7 @@ def run_b200(args):
         hb.set_fixed_clock(now)
         for streams in (1, 64):
             n_calls = {1: 2000, 64: 40000}[streams]
-            load = w.request_batch(n_calls, now, seed=7100 + streams, body_size=BODY, n_templates=64)
+            load = w.request_batch(n_calls, now, seed=7100 + streams, body_size=BODY, n_templates=256, varied=True)
             before = hb.stats()
             _, lat_ns, wall = hb.run_requests(load, threads=streams)
             after = hb.stats()
@@ -358,7 +362,7 @@ def run_b200(args):
         # in BASELINE's "10 M req/s on 8 GPUs with p99 < 200 us" operating point
         for rate in (250_000, 1_250_000):
             n_calls = int(rate * 0.15)
-            load = w.request_batch(n_calls, now, seed=7200 + rate % 97, body_size=BODY, n_templates=64)
+            load = w.request_batch(n_calls, now, seed=7200 + rate % 97, body_size=BODY, n_templates=256, varied=True)
             before = hb.stats()
             dec, lat_ns, wall = hb.open_loop_requests(load, rate_per_s=rate, producers=8)
             after = hb.stats()
@@ -370,6 +374,30 @@ def run_b200(args):
             now += STEP_S
             hb.set_fixed_clock(now)
         hb.close()
+
+    # ---- the same step on single-shape traffic (every request / completion the same template, exactly BODY / RESP_BODY
+    # bytes): the lanes of a warp then move in lock step. Reported next to the headline because the scan kernels are
+    # sensitive to how much the 32 bodies of a warp differ ----------------------------------------
+    uniform = None
+    if rank == 0:
+        ureq = pin_batch(w.request_batch(args.wave, now, seed=9001, body_size=BODY, n_templates=512))
+        g.select_slot(0)
+        ures = pin_batch(w.response_batch(g.handle_request_body(ureq), now + 1, seed=9002, body_size=RESP_BODY))
+        g.stage_request(ureq)
+        g.stage_response(ures)
+        now += STEP_S
+        torch.cuda.synchronize()
+        for _ in range(3):
+            g.run_request(now); g.run_response(now + 1); now += STEP_S
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record(ext)
+        for _ in range(20):
+            g.run_request(now); g.run_response(now + 1); now += STEP_S
+        u1.record(ext)
+        torch.cuda.synchronize()
+        uniform = {"value": args.wave * 20 / (u0.elapsed_time(u1) / 1e3), "unit": "req/s per GPU",
+                   "ms_per_step": u0.elapsed_time(u1) / 20,
+                   "what": f"same step, every request {BODY} B of one shape and every completion {RESP_BODY} B of one shape (best case)"}
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s * 1e3], device=f"cuda:{local}", dtype=torch.float64)
@@ -419,6 +447,7 @@ def run_b200(args):
                        "open_loop_what": "requests arrive at the given rate (exponential gaps, 8 producer threads) through host/cpp Batcher::SubmitRequest; latency = decision callback - scheduled arrival",
                        "streams_what": "N stream threads, one blocking HandleRequestBody at a time each, through host/cpp Batcher (C++); per-call latency"},
         "gpu_launches": int(launches),
+        "single_shape_traffic": uniform,
         "kernels_ms": {"scan_request": float(np.mean(scan_ms)), "limit_admit": float(np.mean(admit_ms)),
                        "scan_response": float(np.mean(resp_ms))},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

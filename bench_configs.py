@@ -48,7 +48,7 @@ def config3(wave=65536, steps=20):
     w = traffic.Workload(10_000, seed=0xA2C5)
     g = Gateway(0, wave, int(wave * 1100 * 1.05)); g.load_tables(w.tables)
     o = orklib.Oracle(w.tables)
-    req = pin_batch(w.request_batch(wave, NOW0, seed=31, stream_frac=1.0, n_templates=256))
+    req = pin_batch(w.request_batch(wave, NOW0, seed=31, stream_frac=1.0, n_templates=2048, varied=True))
     a = g.handle_request_body(req)
     assert same(a, o.request_batch(req))
     allresp = w.response_batch(a, NOW0 + 1, seed=32)
@@ -88,13 +88,13 @@ def config4(wave=65536, steps=20):
     w = traffic.Workload(100_000, seed=0xA2C6, zipf_alpha=1.1)
     g = Gateway(0, wave, int(wave * 1100 * 1.05)); g.load_tables(w.tables)
     o = orklib.Oracle(w.tables)
-    reqs = [pin_batch(w.request_batch(wave, NOW0 + 5 * k, seed=41 + k, n_templates=256)) for k in range(3)]
+    reqs = [pin_batch(w.request_batch(wave, NOW0 + 5 * k, seed=41 + k, n_templates=2048, varied=True)) for k in range(3)]
     flips = 0
     for k, r in enumerate(reqs):  # serial-order parity incl. the exact index at which each tenant flips to deny
         a, b = g.handle_request_body(r), o.request_batch(r)
         assert same(a, b), f"wave {k}"
         flips += int(((a.reason == abi.R_RATE_LIMIT) | (a.reason == abi.R_QUOTA)).sum())
-        resp = w.response_batch(a, NOW0 + 5 * k + 1, seed=51 + k)
+        resp = w.response_batch(a, NOW0 + 5 * k + 1, seed=51 + k, varied=True, n_templates=2048)
         n = min(resp.n, wave)
         resp = ResponseBatch(resp.bodies, resp.body_off[:n], resp.body_len[:n], resp.qos[:n], resp.flags[:n], resp.now_unix)
         assert same(g.handle_response_body(resp), o.response_batch(resp))
@@ -125,7 +125,7 @@ def config5(wave=65536, steps=40):
     w = traffic.Workload(1000, seed=0xA2C7, n_backends=16)
     g = Gateway(0, wave, int(wave * 1100 * 1.05)); g.load_tables(w.tables)
     o = orklib.Oracle(w.tables)
-    req = pin_batch(w.request_batch(wave, NOW0, seed=61, n_templates=256))
+    req = pin_batch(w.request_batch(wave, NOW0, seed=61, n_templates=2048, varied=True))
     for rnd in range(6):
         ep = int(rng.integers(1000)); wts = rng.integers(0, 100, 16)
         g.update_endpoint_weights(ep, wts); o.update_endpoint_weights(ep, wts)

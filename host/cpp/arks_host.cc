@@ -20,7 +20,7 @@ namespace {
 
 constexpr uint8_t kReasonHostError = 255;
 constexpr int kSlots = 4;           // staging slots of the library: batches in flight on the device
-constexpr int kBlocks = kSlots + 2; // host staging blocks per kind: in flight + one open + one being handed back
+constexpr int kBlocks = kSlots + 3; // host staging blocks per kind: in flight + open (two for responses) + one being handed back
 
 inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
@@ -90,7 +90,10 @@ struct Batcher::Impl {
   size_t tok_cap;
   Block req_blk[kBlocks], resp_blk[kBlocks];
   std::vector<Block*> free_req, free_resp;  // blocks nobody uses
-  Block *open_req = nullptr, *open_resp = nullptr;
+  Block* open_req = nullptr;
+  Block* open_resp[2] = {nullptr, nullptr};  // complete bodies / SSE chunks: kept apart so that every batch is homogeneous
+                                             // (the library has faster kernels for all-JSON and all-SSE batches)
+  int resp_turn = 0;
   std::deque<InFlight> inflight;            // submitted, not completed (FIFO == device order)
   bool slot_busy[kSlots] = {false, false, false, false};
   mutable std::mutex mu;
@@ -140,8 +143,10 @@ struct Batcher::Impl {
   void dispatch_loop() {
     std::unique_lock<std::mutex> lk(mu);
     for (;;) {
-      cv_work.wait(lk, [&] { return stop || ((open_req->n || open_resp->n) && free_slot() >= 0 && !free_req.empty() && !free_resp.empty()); });
-      if (stop && !open_req->n && !open_resp->n) return;
+      cv_work.wait(lk, [&] {
+        return stop || ((open_req->n || open_resp[0]->n || open_resp[1]->n) && free_slot() >= 0 && !free_req.empty() && !free_resp.empty());
+      });
+      if (stop && !open_req->n && !open_resp[0]->n && !open_resp[1]->n) return;
       if (opt.linger_us) {  // give concurrent streams a moment to join the cycle
         lk.unlock();
         std::this_thread::sleep_for(std::chrono::microseconds(opt.linger_us));
@@ -150,7 +155,9 @@ struct Batcher::Impl {
       InFlight f{nullptr, nullptr, free_slot(), 0, 0};
       slot_busy[f.slot] = true;
       if (open_req->n) { f.req = open_req; open_req = free_req.back(); free_req.pop_back(); }
-      if (open_resp->n) { f.resp = open_resp; open_resp = free_resp.back(); free_resp.pop_back(); }
+      // one response batch per cycle (a staging slot holds one): alternate when both kinds are waiting
+      int kind = open_resp[0]->n && open_resp[1]->n ? (resp_turn ^= 1) : (open_resp[1]->n ? 1 : 0);
+      if (open_resp[kind]->n) { f.resp = open_resp[kind]; open_resp[kind] = free_resp.back(); free_resp.pop_back(); }
       const uint64_t cyc = cycle++;
       const int64_t now = clock ? clock(clock_arg) : (int64_t)time(nullptr);
       lk.unlock();
@@ -185,7 +192,7 @@ struct Batcher::Impl {
   void complete_loop() {
     std::unique_lock<std::mutex> lk(mu);
     for (;;) {
-      cv_done.wait(lk, [&] { return !inflight.empty() || (stop && !open_req->n && !open_resp->n); });
+      cv_done.wait(lk, [&] { return !inflight.empty() || (stop && !open_req->n && !open_resp[0]->n && !open_resp[1]->n); });
       if (inflight.empty()) {
         bool busy = false;
         for (int k = 0; k < kSlots; k++) busy |= slot_busy[k];
@@ -264,7 +271,7 @@ Batcher::Batcher(arks_ctx* ctx, const BatcherOptions& opt) : p_(new Impl()) {
     p_->free_resp.push_back(&p_->resp_blk[k]);
   }
   p_->open_req = p_->free_req.back(); p_->free_req.pop_back();
-  p_->open_resp = p_->free_resp.back(); p_->free_resp.pop_back();
+  for (int k = 0; k < 2; k++) { p_->open_resp[k] = p_->free_resp.back(); p_->free_resp.pop_back(); }
   p_->dispatcher = std::thread([this] { p_->dispatch_loop(); });
   p_->completer = std::thread([this] { p_->complete_loop(); });
 }
@@ -327,7 +334,7 @@ bool Batcher::SubmitResponse(int32_t qos, std::string_view body, uint8_t flags, 
   std::unique_lock<std::mutex> lk(I.mu);
   Block* b;
   for (;;) {
-    b = I.open_resp;
+    b = I.open_resp[(flags & ARKS_RESP_STREAM) ? 1 : 0];
     if (b->n < I.opt.max_batch && b->bytes + need <= I.opt.max_bytes) break;
     I.cv_work.notify_one();
     I.cv_space.wait(lk);

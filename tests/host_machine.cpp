@@ -9,7 +9,7 @@
 
 using namespace arks;
 
-static int g_evsync = 0;  // 1: JsonT documents go through consume_evsync (the schedule of the EVSYNC kernels)
+static int g_evsync = 0;  // schedule for JsonT documents: 0 consume_t, 1 consume_evsync, 4 / 8 consume_rounds<R>
 
 // same bulk loop the kernels run, with units read straight from memory (zero padded past the end)
 template <class M>
@@ -29,7 +29,9 @@ static void feed(M& m, const uint8_t* body, size_t len, uint32_t begin = 0) {
       return q;
     };
     if constexpr (std::is_same<M, JsonT>::value) {
-      if (g_evsync) consume_evsync(m, pos, lim, load);
+      if (g_evsync == 1) consume_evsync(m, pos, lim, load);
+      else if (g_evsync == 4) consume_rounds<4>(m, pos, lim, load);
+      else if (g_evsync == 8) consume_rounds<8>(m, pos, lim, load);
       else consume_t(m, pos, lim, load);
     } else {
       consume_t(m, pos, lim, load);

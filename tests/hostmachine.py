@@ -56,6 +56,6 @@ def parse_sse_chunk_split(body: bytes):
     return rc & 1, tuple(int(x) for x in u), bool(rc & 2)
 
 
-def set_evsync(on: bool):
-    """route JsonT documents through consume_evsync (event-synchronised schedule) instead of consume_t"""
-    lib().hm_set_evsync(1 if on else 0)
+def set_evsync(mode):
+    """schedule for JsonT documents: 0 / False consume_t, 1 / True consume_evsync, 4 or 8 consume_rounds<R>"""
+    lib().hm_set_evsync(int(mode))

@@ -60,11 +60,11 @@ def test_waves_with_noise_and_window_rollover(gwmod):
     g, o = pair(gwmod, w.tables, 4096, 16 << 20)
     now = NOW
     for wave in range(9):
-        req = w.request_batch(3000, now, seed=100 + wave, stream_frac=0.3, noise_frac=0.15)
+        req = w.request_batch(3000, now, seed=100 + wave, stream_frac=0.3, noise_frac=0.15, varied=bool(wave & 1))
         a = g.handle_request_body(req)
         same(a, o.request_batch(req), f"wave {wave} request")
         state_same(g, o, now)
-        resp = w.response_batch(a, now + 3, seed=200 + wave, noise_frac=0.1)
+        resp = w.response_batch(a, now + 3, seed=200 + wave, noise_frac=0.1, varied=bool(wave & 1))
         if resp.n > 4096:
             resp = ResponseBatch(resp.bodies, resp.body_off[:4096], resp.body_len[:4096], resp.qos[:4096], resp.flags[:4096], resp.now_unix)
         c = g.handle_response_body(resp)
@@ -241,7 +241,7 @@ def test_full_size_wave_64k(gwmod):
     now = NOW
     admitted_per_tenant = np.zeros(10_000, np.int64)
     for wave in range(3):
-        req = w.request_batch(65536, now, seed=300 + wave, n_templates=256)
+        req = w.request_batch(65536, now, seed=300 + wave, n_templates=2048, varied=wave != 1)
         a = g.handle_request_body(req)
         same(a, o.request_batch(req), f"wave {wave}")
         ok = a.reason == 0
@@ -250,7 +250,7 @@ def test_full_size_wave_64k(gwmod):
         assert np.array_equal(rate[:, 0], admitted_per_tenant)          # rpm counter == admissions this minute
         lim = w.tables.rl_value.reshape(-1, 4)[:, 0]
         assert np.all(rate[:, 0] <= lim)
-        resp = w.response_batch(a, now + 2, seed=400 + wave)
+        resp = w.response_batch(a, now + 2, seed=400 + wave, varied=wave != 1, n_templates=2048)
         n = min(resp.n, 65536)
         resp = ResponseBatch(resp.bodies, resp.body_off[:n], resp.body_len[:n], resp.qos[:n], resp.flags[:n], resp.now_unix)
         c = g.handle_response_body(resp)

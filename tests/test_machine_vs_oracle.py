@@ -107,12 +107,13 @@ def test_sse_split_cases():
     assert hm.parse_sse_chunk_split(tail)[0] == orklib.parse_sse_chunk(tail)[0] == 1
 
 
-def test_evsync_schedule_same_results():
-    """consume_evsync (events handled warp-synchronously) is only a different schedule of the same machine."""
-    hm.set_evsync(True)
+@pytest.mark.parametrize("mode", [1, 4, 8])
+def test_other_schedules_same_results(mode):
+    """consume_evsync / consume_rounds<R> are only different schedules of the same machine."""
+    hm.set_evsync(mode)
     try:
-        g = Gen(41)
-        for _ in range(12000):
+        g = Gen(41 + mode)
+        for _ in range(8000):
             b = g.request()
             if not d2(b):
                 a, c = orklib.parse_request_body(b), hm.parse_request_body(b)
