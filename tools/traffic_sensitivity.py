@@ -18,6 +18,7 @@ def time_req(name, make, nt=N):
     templ = [make() for _ in range(nt)]
     bodies = templ if nt == N else [templ[int(k)] for k in rng.integers(0, nt, N)]
     if SORT: bodies.sort(key=len)
+    if "sigsort" in sys.argv: bodies.sort(key=lambda x: (x[:48], len(x)))
     b = RequestBatch.from_lists(bodies, toks, now[0])
     g.set_profiling(True)
     ts = []
