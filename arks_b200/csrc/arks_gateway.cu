@@ -360,6 +360,7 @@ __global__ void len_hist_kernel(const uint32_t* body_len, uint32_t n, uint32_t* 
   const unsigned peers = __match_any_sync(0xffffffffu, b);  // one atomic per distinct bucket in the warp
   if (live && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[b], (uint32_t)__popc(peers));
 }
+static_assert(kLenBuckets == 4096, "len_scan_kernel: one block of 1024 threads, 4 counters each");
 // exclusive scan of the kLenBuckets counters in place (one block of 1024 threads, 4 counters each)
 __global__ void __launch_bounds__(1024) len_scan_kernel(uint32_t* hist) {
   __shared__ uint32_t warp_tot[32];

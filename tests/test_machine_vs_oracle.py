@@ -225,3 +225,25 @@ def test_long_strings_bulk_path(seed):
         a, c = orklib.parse_sse_chunk(b), hm.parse_sse_chunk(b)
         assert a[0] == c[0] and (a[0] == 1 or a == c), (b, a, c)
     assert n_ok > 500  # the corpus is not all errors
+
+
+@pytest.mark.parametrize("mode", [0, 1, 8])
+def test_client_app_traffic_through_the_engine(mode):
+    """the bench's heterogeneous bodies (arks_b200.traffic: client applications, server dialects, escapes, UTF-8) are
+    valid for the oracle and give the same extraction in every schedule of the engine"""
+    import numpy as np
+    from arks_b200 import traffic
+    rng = np.random.default_rng(77 + mode)
+    hm.set_evsync(mode)
+    try:
+        for it in range(1500):
+            stream = bool(it % 3 == 0)
+            b = traffic.chat_request_body_varied(rng, 1024, stream=stream)
+            a, c = orklib.parse_request_body(b), hm.parse_request_body(b)
+            assert a == c and a[0] == 0 and a[1] == traffic.MODEL.encode() and a[2] == (2 if stream else a[2]), (b, a, c)
+            p, q = int(rng.integers(1, 5000)), int(rng.integers(1, 5000))
+            b = traffic.chat_response_body_varied(rng, p, q, 600)
+            a, c = orklib.parse_response_body(b), hm.parse_response_body(b)
+            assert a[0] == c[0] == 0 and a[2] == c[2] == (p, q, p + q), (b, a, c)
+    finally:
+        hm.set_evsync(0)
