@@ -1,7 +1,9 @@
 """Sweep of host/cpp Batcher settings on a GPU box: queue depth x linger, closed loop (64 stream threads) and open loop
 (arrival rates); prints (p50 us, p99 us, achieved req/s, mean batch) per case. Used to pick BatcherOptions defaults."""
 import sys, json, numpy as np
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+import os
+_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _R); sys.path.insert(0, os.path.join(_R, "tests"))
 import __graft_entry__ as ge; ge.build()
 from arks_b200 import cpphost, traffic
 from arks_b200.gateway import Gateway

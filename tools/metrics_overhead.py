@@ -1,5 +1,7 @@
 import sys, json, numpy as np
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+import os
+_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _R); sys.path.insert(0, os.path.join(_R, "tests"))
 import __graft_entry__ as ge; ge.build()
 from arks_b200 import traffic
 from arks_b200.gateway import Gateway

@@ -1,6 +1,8 @@
 """one varied request wave + its responses through the library (for ncu captures of the diverged case)"""
 import sys, numpy as np
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+import os
+_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _R); sys.path.insert(0, os.path.join(_R, "tests"))
 import __graft_entry__ as ge; ge.build()
 from arks_b200 import traffic
 from arks_b200.gateway import Gateway
