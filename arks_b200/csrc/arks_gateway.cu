@@ -17,10 +17,10 @@
 //   limit_admit_kernel     one lane per request: closed-form fixed-window admission in arrival order
 //                          (SURVEY.md §8a A6), quota check, one commit per group, weighted pick (A12)
 //   rank_hot_groups_kernel arrival ranks inside groups with more than 256 arrivals in one batch (a hot tenant)
-//   scan_response_kernel   one lane per response: JSON / SSE machine, usage extraction and the unconditional
+//   scan_response_kernel   one lane per complete response body: JSON machine, usage extraction and the unconditional
 //                          counter increments (check.go:47-72) as warp-aggregated 64-bit atomics
 //   scan_sse_kernel        all-SSE batches: chunks cut into events (one lane per chunk), events parsed one per lane,
-//                          verdicts folded per chunk; same results as scan_response_kernel<2>
+//                          verdicts folded per chunk
 //
 // Streams: uploads on `h2d`, everything that touches counters on `stream` (its order is the linearisation).
 #include <cuda_runtime.h>
@@ -760,61 +760,8 @@ __device__ __forceinline__ void account_usage(const DevTables& T, const RespDev&
   }
 }
 
-// per-lane response machine: an SSE chunk (stream) or one JSON document (non-stream). MODE 1 / 2 are the
-// all-JSON / all-SSE specialisations the host picks when a batch is homogeneous (smaller live state); MODE 0 mixes.
-template <int MODE>
-struct RespM;
-template <>
-struct RespM<1> {
-  JsonT ev;
-  static constexpr bool sse = false;
-  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk, JsonCold* cold, const JsonTables& t) { ev.init(K_RESP, body, stk, cold, t); }
-  __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { ev.step(c, pos); }
-  __device__ __forceinline__ bool can_fast() const { return ev.can_fast(); }
-  __device__ __forceinline__ void skip(uint32_t k, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) { ev.skip(k, o, q0, q1, q2, q3); }
-  __device__ __forceinline__ bool dead() const { return ev.dead(); }
-  __device__ __forceinline__ JsonT& json() { return ev; }
-  __device__ __forceinline__ bool finish(uint32_t, long long&, long long&, long long&) { return true; }
-};
-template <>
-struct RespM<2> {
-  SseT s;
-  static constexpr bool sse = true;
-  __device__ __forceinline__ void init(bool, const uint8_t* body, uint32_t* stk, JsonCold* cold, const JsonTables& t) { s.init(body, stk, cold, t); }
-  __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { s.step(c, pos); }
-  __device__ __forceinline__ bool can_fast() const { return s.can_fast(); }
-  __device__ __forceinline__ void skip(uint32_t k, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) { s.skip(k, o, q0, q1, q2, q3); }
-  __device__ __forceinline__ bool dead() const { return s.dead(); }
-  __device__ __forceinline__ JsonT& json() { return s.ev; }
-  __device__ __forceinline__ bool finish(uint32_t len, long long& u0, long long& u1, long long& u2) {
-    bool ok = s.finish(len);
-    u0 = s.usage[0]; u1 = s.usage[1]; u2 = s.usage[2];
-    return ok;
-  }
-};
-template <>
-struct RespM<0> {
-  SseT s;
-  bool sse;
-  __device__ __forceinline__ void init(bool is_sse, const uint8_t* body, uint32_t* stk, JsonCold* cold, const JsonTables& t) {
-    sse = is_sse;
-    if (sse) s.init(body, stk, cold, t); else s.ev.init(K_RESP, body, stk, cold, t);
-  }
-  __device__ __forceinline__ void step(uint8_t c, uint32_t pos) { if (sse) s.step(c, pos); else s.ev.step(c, pos); }
-  __device__ __forceinline__ bool can_fast() const { return sse ? s.can_fast() : s.ev.can_fast(); }
-  __device__ __forceinline__ void skip(uint32_t k, uint32_t o, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
-    if (sse) s.skip(k, o, q0, q1, q2, q3); else s.ev.skip(k, o, q0, q1, q2, q3);
-  }
-  __device__ __forceinline__ bool dead() const { return sse ? s.dead() : s.ev.dead(); }
-  __device__ __forceinline__ JsonT& json() { return s.ev; }
-  __device__ __forceinline__ bool finish(uint32_t len, long long& u0, long long& u1, long long& u2) {
-    bool ok = s.finish(len);
-    u0 = s.usage[0]; u1 = s.usage[1]; u2 = s.usage[2];
-    return ok;
-  }
-};
-
-template <int MODE, int SCHED = 0>
+// complete (non-stream) response bodies: one JSON document per lane
+template <int SCHED>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response_kernel(DevTables T, RespDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t lane_id = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * B.bpw + (threadIdx.x & 31);
@@ -826,36 +773,27 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response
   QosAcct acct;
   {
     const uint8_t* body = B.bodies + (live ? B.body_off[i] : 0);
-    uint8_t fl = live ? B.flags[i] : ARKS_RESP_END_OF_STREAM;
-    const bool pending = !(fl & (ARKS_RESP_STREAM | ARKS_RESP_END_OF_STREAM));  // handle_response.go:141-149
-    uint32_t len = live && !pending ? B.body_len[i] : 0;
+    const uint8_t fl = live ? B.flags[i] : ARKS_RESP_END_OF_STREAM;
+    const bool pending = !(fl & ARKS_RESP_END_OF_STREAM);  // more of the body is still to come: handle_response.go:141-149
+    const uint32_t len = live && !pending ? B.body_len[i] : 0;
     qos = live ? B.qos[i] : 0;
     uint32_t stack_words[kStackWords];  // local memory, touched only beyond 32 levels of nesting
-    __shared__ __align__(16) JsonSmem<MODE != 2, MODE != 1> json_smem;
+    __shared__ __align__(16) JsonSmem<true, false> json_smem;
     const JsonTables tabs = json_smem.stage_async();
     WindowPipe<kStages> pipe;
     pipe.start(body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
     acct = load_qos_acct(T, qos, live);  // global latency chain, hidden behind the copies issued above
     cp_async_wait<kStages - 1>();        // the table group is the oldest one
     __syncthreads();
-    RespM<MODE> rm;
-    const bool is_sse = MODE == 2 || (MODE == 0 && (fl & ARKS_RESP_STREAM));
     JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
-    rm.init(is_sse, body, stack_words, &cold, tabs);
-    if constexpr (SCHED != 0) feed_pipe<SCHED>(rm.json(), pipe, 0);
-    else feed_pipe<0>(rm, pipe, 0);
+    JsonT ev;
+    ev.init(K_RESP, body, stack_words, &cold, tabs);
+    feed_pipe<SCHED>(ev, pipe, 0);
     if (live) {
-      if (is_sse) {  // handle_response.go:113-133, every chunk in isolation
-        if (!rm.finish(len, u0, u1, u2)) reason = ARKS_R_STREAMING;
-      } else if (pending) {
-        reason = ARKS_R_PENDING;
-      } else {
-        JsonT& ev = rm.json();
-        if (!ev.ok_at_end()) reason = ARKS_R_RESPONSE_UNMARSHAL;  // :157-166
-        else if (cold.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // :167-181
-        else { u0 = cold.usage[0]; u1 = cold.usage[1]; u2 = cold.usage[2]; }
-      }
-      if (reason != ARKS_R_OK) { u0 = u1 = u2 = 0; }
+      if (pending) reason = ARKS_R_PENDING;
+      else if (!ev.ok_at_end()) reason = ARKS_R_RESPONSE_UNMARSHAL;   // :157-166
+      else if (cold.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // :167-181
+      else { u0 = cold.usage[0]; u1 = cold.usage[1]; u2 = cold.usage[2]; }
       counted = reason == ARKS_R_OK && u2 != 0;  // :186
     }
   }
@@ -863,7 +801,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel 3b: scan_sse — the all-SSE batch (BASELINE config 3). Same verdicts as scan_response_kernel<2>, different
+// kernel 3b: scan_sse — SSE chunks (BASELINE config 3). Same verdicts as the sequential machine SseT, different
 // work split. A lane that walks a whole chunk sits at an arbitrary phase of the frame structure, so a warp of 32
 // chunks runs ~9 lanes wide. Here a warp first cuts its 32 chunks into events (SseSplit, 16 bytes per step, one lane
 // per chunk), then parses the events one per lane — every lane starts on the '{' of a frame and frames of one server
@@ -1069,6 +1007,8 @@ struct arks_ctx {
     RespDev rp{};
     uint32_t req_n = 0, resp_n = 0;
     int resp_mode = 0;  // 1 all JSON documents, 2 all SSE chunks, 0 mixed
+    uint32_t resp_n_sse = 0;
+    const uint32_t* d_resp_kind = nullptr;  // mixed batch: row indices, complete bodies first then SSE chunks
     bool req_staged = false, resp_staged = false;
   };
   static constexpr int kSlots = 4;
@@ -1080,7 +1020,6 @@ struct arks_ctx {
   bool prof = false;
   int sched[3] = {8, 8, 1};  // parse schedule of the request scan, the JSON response scan, the SSE event phase: 0 consume_t,
                              // 1 consume_evsync, 8 consume_rounds<8> (json_engine.cuh). ARKS_SCHED="r,p,s" overrides (A/B runs)
-  bool sse_sequential = false;  // ARKS_SSE_SEQUENTIAL=1: all-SSE batches use scan_response_kernel<2> (A/B measurements)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int ev_n = 0;
   uint8_t* d_inter = nullptr;    // intermediates + group table
@@ -1163,7 +1102,6 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return ARKS_E_NO_DEVICE;
   arks_ctx* ctx = new arks_ctx();
   ctx->device = device;
-  if (const char* e = getenv("ARKS_SSE_SEQUENTIAL")) ctx->sse_sequential = e[0] == '1';
   if (const char* e = getenv("ARKS_SORT")) ctx->sort_lanes = e[0] != '0';
   if (const char* e = getenv("ARKS_SCHED")) {
     int a = 8, b = 8, c = 8;
@@ -1186,12 +1124,10 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
 #define ARKS_FOR_SCHED(X) X(0) X(1) X(8)
 #define ARKS_SET(S)                                                                                                        \
   CK(cudaFuncSetAttribute(scan_request_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));            \
-  CK((cudaFuncSetAttribute(scan_response_kernel<1, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock)));      \
+  CK(cudaFuncSetAttribute(scan_response_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));           \
   CK(cudaFuncSetAttribute(scan_sse_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSseSmemPerBlock));
   ARKS_FOR_SCHED(ARKS_SET)
 #undef ARKS_SET
-  CK(cudaFuncSetAttribute(scan_response_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
-  CK(cudaFuncSetAttribute(scan_response_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));
   uint32_t g = 64;
   while (g < 2 * n) g <<= 1;
   ctx->gsize = g;
@@ -1766,9 +1702,16 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
       return fail(ctx, ARKS_E_INVALID_ARG, "body %u: offset not 16-byte aligned or out of range", i);
   }
   sl.resp_mode = n_sse == 0 ? 1 : n_sse == n ? 2 : 0;
-  size_t o_off = 0, o_len = align_up((size_t)n * 4, 256), o_qos = o_len * 2, o_fl = o_len * 3, total = o_fl + align_up(n, 256);
+  sl.resp_n_sse = n_sse;
+  size_t o_off = 0, o_len = align_up((size_t)n * 4, 256), o_qos = o_len * 2, o_fl = o_len * 3, o_kind = o_fl + align_up(n, 256),
+         total = o_kind + (sl.resp_mode == 0 ? o_len : 0);
   CK(cudaEventSynchronize(sl.resp_copied));
   uint8_t* h = sl.h_resp_meta;
+  if (sl.resp_mode == 0) {  // mixed batch: complete bodies first, SSE chunks after; each kind goes to its own kernel
+    uint32_t* kind = reinterpret_cast<uint32_t*>(h + o_kind);
+    uint32_t a = 0, c = n - n_sse;
+    for (uint32_t i = 0; i < n; i++) kind[(b->flags[i] & ARKS_RESP_STREAM) ? c++ : a++] = i;
+  }
   memcpy(h + o_off, b->body_off, (size_t)n * 4);
   memcpy(h + o_len, b->body_len, (size_t)n * 4);
   memcpy(h + o_qos, b->qos, (size_t)n * 4);
@@ -1784,6 +1727,7 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   r.qos = (const int32_t*)(sl.d_resp_meta + o_qos);
   r.flags = sl.d_resp_meta + o_fl;
   r.n = n;
+  sl.d_resp_kind = reinterpret_cast<const uint32_t*>(sl.d_resp_meta + o_kind);
   r.reason = ctx->d_result;
   r.counted = ctx->d_result + align_up(n, 16);
   r.usage = (long long*)(ctx->d_result + 2 * align_up(n, 16));
@@ -1804,24 +1748,37 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
   const uint32_t tpb = kWarpsPerBlock * 32;
   CK(cudaStreamWaitEvent(ctx->stream, sl.resp_copied, 0));
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  sl.rp.perm = queue_length_order(ctx, sl.rp.body_len, n);
-  sl.rp.bpw = bodies_per_warp(n);
-  const dim3 grid(scan_grid(n, sl.rp.bpw));
-  if (sl.resp_mode == 1) {
+  // complete bodies and SSE chunks have their own kernels; a mixed batch is two launches over the two halves of its
+  // kind index (arrival order inside a kind), a homogeneous one a single launch in length order
+  auto launch_json = [&](RespDev rp) {
+    rp.bpw = bodies_per_warp(rp.n);
+    const dim3 grid(scan_grid(rp.n, rp.bpw));
     switch (ctx->sched[1]) {
-#define ARKS_LAUNCH(S) case S: scan_response_kernel<1, S><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp); break;
+#define ARKS_LAUNCH(S) case S: scan_response_kernel<S><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, rp); break;
       ARKS_FOR_SCHED(ARKS_LAUNCH)
 #undef ARKS_LAUNCH
     }
-  } else if (sl.resp_mode == 2 && !ctx->sse_sequential) {
+  };
+  auto launch_sse = [&](RespDev rp) {
+    rp.bpw = bodies_per_warp(rp.n);
+    const dim3 grid(scan_grid(rp.n, rp.bpw));
     switch (ctx->sched[2]) {
-#define ARKS_LAUNCH(S) case S: scan_sse_kernel<S><<<grid, tpb, kSseSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp); break;
+#define ARKS_LAUNCH(S) case S: scan_sse_kernel<S><<<grid, tpb, kSseSmemPerBlock, ctx->stream>>>(ctx->dt, rp); break;
       ARKS_FOR_SCHED(ARKS_LAUNCH)
 #undef ARKS_LAUNCH
     }
+  };
+  if (sl.resp_mode == 0) {
+    RespDev rj = sl.rp, rs = sl.rp;
+    rj.n = n - sl.resp_n_sse; rj.perm = sl.d_resp_kind;
+    rs.n = sl.resp_n_sse;     rs.perm = sl.d_resp_kind + rj.n;
+    launch_json(rj);
+    launch_sse(rs);
+    ctx->launches += 1;
+  } else {
+    sl.rp.perm = queue_length_order(ctx, sl.rp.body_len, n);
+    if (sl.resp_mode == 1) launch_json(sl.rp); else launch_sse(sl.rp);
   }
-  else if (sl.resp_mode == 2) scan_response_kernel<2><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
-  else scan_response_kernel<0><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, sl.rp);
   if (ctx->prof) { CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_n = 2; }
   CK(cudaEventRecord(sl.resp_ran, ctx->stream));
   ctx->launches += 1;
