@@ -364,40 +364,41 @@ static int check_time(ork* o, int64_t now) {
 }
 
 /* ---------- HandleRequestBody ---------- */
-static void handle_request(ork* o, const arks_request_batch* b, arks_request_result* r, uint32_t i) {
+/* row i of the batch; results go to row `out` of r (out == i except for the threaded baseline's private buffers) */
+static void handle_request(ork* o, const arks_request_batch* b, arks_request_result* r, uint32_t i, uint32_t out) {
   const uint8_t* body = b->bodies + b->body_off[i];
   size_t len = b->body_len[i];
   const uint8_t* tk = b->tokens + b->token_off[i];
   size_t tkl = b->token_off[i + 1] - b->token_off[i];
-  r->reason[i] = ARKS_R_OK;
-  r->detail[i] = 0;
-  r->flags[i] = 0;
-  r->qos[i] = -1;
-  r->token[i] = -1;
-  r->pick[i] = -1;
-  r->cur_usage[i] = 0;
-  r->limit_max[i] = 0;
+  r->reason[out] = ARKS_R_OK;
+  r->detail[out] = 0;
+  r->flags[out] = 0;
+  r->qos[out] = -1;
+  r->token[out] = -1;
+  r->pick[out] = -1;
+  r->cur_usage[out] = 0;
+  r->limit_max[out] = 0;
 
   /* 1. jsonUnmarshal(body, &reqBody)                                   handle_request.go:97-104 */
   uint8_t mbuf[1024];
   ork_sink model = {mbuf, 0, sizeof mbuf, 0, 0};
   int stream3, so_present, iu3;
   if (ork_json_request(body, len, &model, &stream3, &so_present, &iu3)) {
-    r->reason[i] = ARKS_R_REQUEST_BODY;
+    r->reason[out] = ARKS_R_REQUEST_BODY;
     return;
   }
   /* 2. model == ""                                                     :106-115 */
   if (model.len == 0) {
-    r->reason[i] = ARKS_R_NO_MODEL;
+    r->reason[out] = ARKS_R_NO_MODEL;
     return;
   }
   /* 3. GetQosByToken(token, model)                                     :118-134, arks_impl.go:303-338 */
   int32_t t = find_token(o, tk, tkl);
   if (t < 0) {
-    r->reason[i] = ARKS_R_TOKEN_NOT_FOUND;
+    r->reason[out] = ARKS_R_TOKEN_NOT_FOUND;
     return;
   }
-  r->token[i] = t;
+  r->token[out] = t;
   int32_t q = -1;
   if (model.len <= model.cap) /* names longer than the sink cannot equal a (<= 253 byte) object name */
     for (uint32_t k = o->tok_qos_off[t]; k < o->tok_qos_off[t + 1]; k++)
@@ -406,20 +407,20 @@ static void handle_request(ork* o, const arks_request_batch* b, arks_request_res
         break;
       }
   if (q < 0) {
-    r->reason[i] = ARKS_R_MODEL_NOT_IN_TOKEN;
+    r->reason[out] = ARKS_R_MODEL_NOT_IN_TOKEN;
     return;
   }
-  r->qos[i] = q;
+  r->qos[out] = q;
   /* 4. GetModelList(qos.Namespace) contains model                      :137-154, arks_impl.go:364-376 */
   int32_t ep = find_endpoint(o, o->tok_ns_str[t], mbuf, model.len);
   if (ep < 0) {
-    r->reason[i] = ARKS_R_NO_MODEL_BACKENDS;
+    r->reason[out] = ARKS_R_NO_MODEL_BACKENDS;
     return;
   }
   /* 5. stream requires stream_options.include_usage == true            :156-171 */
   int stream = stream3 == 2;
   if (stream && !(so_present && iu3 == 2)) {
-    r->reason[i] = ARKS_R_STREAM_OPTIONS;
+    r->reason[out] = ARKS_R_STREAM_OPTIONS;
     return;
   }
   /* 6. checkRateLimit -> CheckLimit                                    check.go:108-156, redis_impl.go:47-114 */
@@ -430,18 +431,18 @@ static void handle_request(ork* o, const arks_request_batch* b, arks_request_res
     int64_t cur = rate_get(o, (uint32_t)q, rule, ws);
     int64_t req = RULE_IS_REQUEST[rule] ? 1 : 0; /* "token is not caculated in request" check.go:124-126 */
     if ((int64_t)((uint64_t)cur + (uint64_t)req) > o->rl_value[j]) {
-      r->reason[i] = ARKS_R_RATE_LIMIT;
+      r->reason[out] = ARKS_R_RATE_LIMIT;
       o->metrics[(size_t)q * ARKS_METRIC_COLS + ARKS_METRIC_HITS + rule]++; /* RecordRateLimitHit, check.go:145 */
-      r->detail[i] = (uint8_t)(j - rl0);
-      r->cur_usage[i] = cur;
-      r->limit_max[i] = o->rl_value[j];
+      r->detail[out] = (uint8_t)(j - rl0);
+      r->cur_usage[out] = cur;
+      r->limit_max[out] = o->rl_value[j];
       return;
     }
   }
   /* 7. checkTokenQuotaLimit -> GetUsage: cur > limit (strict)          check.go:75-106, quota/redis_impl.go:63-107 */
   int32_t qt = o->qos_quota[q];
   if (qt == ARKS_QUOTA_MISSING) {
-    r->reason[i] = ARKS_R_QUOTA_CONFIG;
+    r->reason[out] = ARKS_R_QUOTA_CONFIG;
     return;
   }
   if (qt >= 0) {
@@ -449,10 +450,10 @@ static void handle_request(ork* o, const arks_request_batch* b, arks_request_res
     for (uint32_t j = i0; j < i1; j++) {
       int64_t cur = o->quota_use[(size_t)qt * 3 + o->qitem_type[j]];
       if (cur > o->qitem_value[j]) {
-        r->reason[i] = ARKS_R_QUOTA;
-        r->detail[i] = (uint8_t)(j - i0);
-        r->cur_usage[i] = cur;
-        r->limit_max[i] = o->qitem_value[j];
+        r->reason[out] = ARKS_R_QUOTA;
+        r->detail[out] = (uint8_t)(j - i0);
+        r->cur_usage[out] = cur;
+        r->limit_max[out] = o->qitem_value[j];
         return;
       }
     }
@@ -463,10 +464,10 @@ static void handle_request(ork* o, const arks_request_batch* b, arks_request_res
     if (RULE_IS_REQUEST[rule]) rate_incr(o, (uint32_t)q, rule, ork_window_start(b->now_unix, rule), 1);
   }
   /* 9. BodyResponse{model, namespace, username}; weighted pick is Envoy's (A12) */
-  r->flags[i] = stream ? 1 : 0;
+  r->flags[out] = stream ? 1 : 0;
   if (b->pick_rand) {
     uint32_t b0 = o->ep_backend_off[ep], b1 = o->ep_backend_off[ep + 1];
-    r->pick[i] = ork_weighted_pick(o->backend_weight + b0, b1 - b0, b->pick_rand[i]);
+    r->pick[out] = ork_weighted_pick(o->backend_weight + b0, b1 - b0, b->pick_rand[i]);
   }
 }
 
@@ -477,54 +478,54 @@ static int token_bucket(int64_t v) {
     if (v <= le) return k;
   return ARKS_METRIC_HIST_BUCKETS - 1;
 }
-static void handle_response_inner(ork* o, const arks_response_batch* b, arks_response_result* r, uint32_t i);
+static void handle_response_inner(ork* o, const arks_response_batch* b, arks_response_result* r, uint32_t i, uint32_t out);
 /* Server.Process + the deferred block of HandleResponseBody: gateway.go:122-129, handle_response.go:99-109 */
-static void handle_response(ork* o, const arks_response_batch* b, arks_response_result* r, uint32_t i) {
-  handle_response_inner(o, b, r, i);
+static void handle_response(ork* o, const arks_response_batch* b, arks_response_result* r, uint32_t i, uint32_t out) {
+  handle_response_inner(o, b, r, i, out);
   int64_t* row = o->metrics + (size_t)b->qos[i] * ARKS_METRIC_COLS;
   row[ARKS_METRIC_MESSAGES]++; /* RecordRequest(ns, user, model, dur, "200") for every response-body message */
   /* `!hasCompleted && complete && EndOfStream`: complete was set by THIS message (usage.total_tokens != 0) */
-  if (r->counted[i] && (b->flags[i] & ARKS_RESP_END_OF_STREAM) && !(b->flags[i] & ARKS_RESP_COMPLETED)) {
-    row[ARKS_METRIC_USAGE + 0] = (int64_t)((uint64_t)row[ARKS_METRIC_USAGE + 0] + (uint64_t)r->usage[3 * i + 0]);
-    row[ARKS_METRIC_USAGE + 1] = (int64_t)((uint64_t)row[ARKS_METRIC_USAGE + 1] + (uint64_t)r->usage[3 * i + 1]);
-    row[ARKS_METRIC_HIST_IN + token_bucket(r->usage[3 * i + 0])]++;
-    row[ARKS_METRIC_HIST_OUT + token_bucket(r->usage[3 * i + 1])]++;
+  if (r->counted[out] && (b->flags[i] & ARKS_RESP_END_OF_STREAM) && !(b->flags[i] & ARKS_RESP_COMPLETED)) {
+    row[ARKS_METRIC_USAGE + 0] = (int64_t)((uint64_t)row[ARKS_METRIC_USAGE + 0] + (uint64_t)r->usage[3 * (size_t)out + 0]);
+    row[ARKS_METRIC_USAGE + 1] = (int64_t)((uint64_t)row[ARKS_METRIC_USAGE + 1] + (uint64_t)r->usage[3 * (size_t)out + 1]);
+    row[ARKS_METRIC_HIST_IN + token_bucket(r->usage[3 * (size_t)out + 0])]++;
+    row[ARKS_METRIC_HIST_OUT + token_bucket(r->usage[3 * (size_t)out + 1])]++;
   }
 }
-static void handle_response_inner(ork* o, const arks_response_batch* b, arks_response_result* r, uint32_t i) {
+static void handle_response_inner(ork* o, const arks_response_batch* b, arks_response_result* r, uint32_t i, uint32_t out) {
   const uint8_t* body = b->bodies + b->body_off[i];
   size_t len = b->body_len[i];
   int32_t q = b->qos[i];
   int64_t usage[3] = {0, 0, 0};
-  r->reason[i] = ARKS_R_OK;
-  r->counted[i] = 0;
-  r->usage[3 * i] = r->usage[3 * i + 1] = r->usage[3 * i + 2] = 0;
+  r->reason[out] = ARKS_R_OK;
+  r->counted[out] = 0;
+  r->usage[3 * (size_t)out] = r->usage[3 * (size_t)out + 1] = r->usage[3 * (size_t)out + 2] = 0;
   if (b->flags[i] & ARKS_RESP_STREAM) {
     /* handle_response.go:113-133 — every chunk decoded in isolation */
     if (ork_sse_chunk(body, len, usage)) {
-      r->reason[i] = ARKS_R_STREAMING;
+      r->reason[out] = ARKS_R_STREAMING;
       return;
     }
   } else {
     if (!(b->flags[i] & ARKS_RESP_END_OF_STREAM)) { /* :141-149 */
-      r->reason[i] = ARKS_R_PENDING;
+      r->reason[out] = ARKS_R_PENDING;
       return;
     }
     ork_sink model = {NULL, 0, 0, 0, 0};
     if (ork_json_response(body, len, &model, usage)) { /* :157-166 */
-      r->reason[i] = ARKS_R_RESPONSE_UNMARSHAL;
+      r->reason[out] = ARKS_R_RESPONSE_UNMARSHAL;
       return;
     }
     if (model.len == 0) { /* :167-181 */
-      r->reason[i] = ARKS_R_RESPONSE_UNKNOWN;
+      r->reason[out] = ARKS_R_RESPONSE_UNKNOWN;
       return;
     }
   }
-  r->usage[3 * i] = usage[0];
-  r->usage[3 * i + 1] = usage[1];
-  r->usage[3 * i + 2] = usage[2];
+  r->usage[3 * (size_t)out] = usage[0];
+  r->usage[3 * (size_t)out + 1] = usage[1];
+  r->usage[3 * (size_t)out + 2] = usage[2];
   if (usage[2] != 0) { /* :186 */
-    r->counted[i] = 1;
+    r->counted[out] = 1;
     /* doTokenRateLimit: INCRBY total per token-type entry              check.go:47-59 */
     for (uint32_t j = o->qos_rl_off[q]; j < o->qos_rl_off[q + 1]; j++) {
       int rule = o->rl_rule[j];
@@ -533,7 +534,7 @@ static void handle_response_inner(ork* o, const arks_response_batch* b, arks_res
     /* doTokenQuotaLimit: QosToQuotaRequests(conf, countMap) -> IncrUsage   check.go:62-72 */
     int32_t qt = o->qos_quota[q];
     if (qt == ARKS_QUOTA_MISSING) {
-      r->reason[i] = ARKS_R_QUOTA_CONFIG_RESP;
+      r->reason[out] = ARKS_R_QUOTA_CONFIG_RESP;
       return;
     }
     if (qt >= 0)
@@ -548,7 +549,7 @@ static void handle_response_inner(ork* o, const arks_response_batch* b, arks_res
 int ork_request_batch(ork* o, const arks_request_batch* b, arks_request_result* r) {
   int rc = check_time(o, b->now_unix);
   if (rc) return rc;
-  for (uint32_t i = 0; i < b->n; i++) handle_request(o, b, r, i);
+  for (uint32_t i = 0; i < b->n; i++) handle_request(o, b, r, i, i);
   return 0;
 }
 int ork_response_batch(ork* o, const arks_response_batch* b, arks_response_result* r) {
@@ -556,11 +557,22 @@ int ork_response_batch(ork* o, const arks_response_batch* b, arks_response_resul
   if (rc) return rc;
   for (uint32_t i = 0; i < b->n; i++)
     if (b->qos[i] < 0 || (uint32_t)b->qos[i] >= o->n_qos) return ARKS_E_INVALID_ARG;
-  for (uint32_t i = 0; i < b->n; i++) handle_response(o, b, r, i);
+  for (uint32_t i = 0; i < b->n; i++) handle_response(o, b, r, i, i);
   return 0;
 }
 
-/* ---------- tenant-sharded threads (cpu baseline) ---------- */
+/* ---------- tenant-sharded threads (cpu baseline) ----------
+ * All state of a request lives inside its namespace, so worker t owns the namespaces that hash to t and handles their
+ * rows in arrival order: the decisions equal the serial ones. Three passes per batch, a barrier between them:
+ *   1. (rows split evenly) owner of every row;   2. every worker handles ITS rows, writing results to a private, densely
+ *   packed buffer (neighbouring rows belong to different workers: writing the shared result arrays directly makes every
+ *   cache line bounce between all of them);   3. (rows split evenly) results copied to their rows. */
+typedef struct {
+  uint8_t *reason, *detail, *flags, *counted;
+  int32_t *qos, *token, *pick;
+  int64_t *cur, *lim, *usage;
+  uint32_t n;
+} mt_priv;
 typedef struct {
   ork* o;
   const arks_request_batch* rb;
@@ -568,7 +580,9 @@ typedef struct {
   const arks_response_batch* pb;
   arks_response_result* pr;
   int tid, nt;
-  uint16_t* shard;           /* per item: owning thread (computed in parallel, slice per thread) */
+  uint16_t* shard;   /* per row: owning worker */
+  uint32_t* slot;    /* per row: position inside its owner's private buffer */
+  mt_priv* priv;     /* nt private buffers */
   pthread_barrier_t* bar;
 } mt_arg;
 static uint32_t ns_shard(const ork* o, uint32_t tok, int nt) {
@@ -576,27 +590,80 @@ static uint32_t ns_shard(const ork* o, uint32_t tok, int nt) {
   const uint8_t* s = S(o, o->tok_ns_str[tok], &l);
   return (uint32_t)(fnv64(s, l, 0x9e3779b97f4a7c15ull) % (uint64_t)nt);
 }
+static void priv_alloc(mt_priv* p, uint32_t n, int req) {
+  memset(p, 0, sizeof *p);
+  p->n = n;
+  size_t m = n ? n : 1;
+  p->reason = (uint8_t*)malloc(m);
+  if (req) {
+    p->detail = (uint8_t*)malloc(m); p->flags = (uint8_t*)malloc(m);
+    p->qos = (int32_t*)malloc(4 * m); p->token = (int32_t*)malloc(4 * m); p->pick = (int32_t*)malloc(4 * m);
+    p->cur = (int64_t*)malloc(8 * m); p->lim = (int64_t*)malloc(8 * m);
+  } else {
+    p->counted = (uint8_t*)malloc(m);
+    p->usage = (int64_t*)malloc(24 * m);
+  }
+}
+static void priv_free(mt_priv* p) {
+  free(p->reason); free(p->detail); free(p->flags); free(p->counted);
+  free(p->qos); free(p->token); free(p->pick); free(p->cur); free(p->lim); free(p->usage);
+}
 static void* mt_req(void* p) {
   mt_arg* a = (mt_arg*)p;
-  uint32_t n = a->rb->n;
-  uint32_t lo = (uint32_t)((uint64_t)n * a->tid / a->nt), hi = (uint32_t)((uint64_t)n * (a->tid + 1) / a->nt);
+  const uint32_t n = a->rb->n;
+  const uint32_t lo = (uint32_t)((uint64_t)n * a->tid / a->nt), hi = (uint32_t)((uint64_t)n * (a->tid + 1) / a->nt);
   for (uint32_t i = lo; i < hi; i++) {
     int32_t t = find_token(a->o, a->rb->tokens + a->rb->token_off[i], a->rb->token_off[i + 1] - a->rb->token_off[i]);
     a->shard[i] = (uint16_t)(t >= 0 ? ns_shard(a->o, (uint32_t)t, a->nt) : i % (uint32_t)a->nt);
   }
   pthread_barrier_wait(a->bar);
+  uint32_t mine = 0;
+  for (uint32_t i = 0; i < n; i++) mine += a->shard[i] == a->tid;
+  mt_priv* me = &a->priv[a->tid];
+  priv_alloc(me, mine, 1);
+  arks_request_result pr = {me->reason, me->detail, me->flags, me->qos, me->token, me->pick, me->cur, me->lim};
+  uint32_t k = 0;
   for (uint32_t i = 0; i < n; i++)
-    if (a->shard[i] == a->tid) handle_request(a->o, a->rb, a->rr, i);
+    if (a->shard[i] == a->tid) {
+      a->slot[i] = k;
+      handle_request(a->o, a->rb, &pr, i, k++);
+    }
+  pthread_barrier_wait(a->bar);
+  arks_request_result* r = a->rr;
+  for (uint32_t i = lo; i < hi; i++) {
+    const mt_priv* w = &a->priv[a->shard[i]];
+    const uint32_t j = a->slot[i];
+    r->reason[i] = w->reason[j]; r->detail[i] = w->detail[j]; r->flags[i] = w->flags[j];
+    r->qos[i] = w->qos[j]; r->token[i] = w->token[j]; r->pick[i] = w->pick[j];
+    r->cur_usage[i] = w->cur[j]; r->limit_max[i] = w->lim[j];
+  }
   return NULL;
 }
 static void* mt_resp(void* p) {
   mt_arg* a = (mt_arg*)p;
-  uint32_t n = a->pb->n;
-  uint32_t lo = (uint32_t)((uint64_t)n * a->tid / a->nt), hi = (uint32_t)((uint64_t)n * (a->tid + 1) / a->nt);
+  const uint32_t n = a->pb->n;
+  const uint32_t lo = (uint32_t)((uint64_t)n * a->tid / a->nt), hi = (uint32_t)((uint64_t)n * (a->tid + 1) / a->nt);
   for (uint32_t i = lo; i < hi; i++) a->shard[i] = (uint16_t)ns_shard(a->o, a->o->qos_token[a->pb->qos[i]], a->nt);
   pthread_barrier_wait(a->bar);
+  uint32_t mine = 0;
+  for (uint32_t i = 0; i < n; i++) mine += a->shard[i] == a->tid;
+  mt_priv* me = &a->priv[a->tid];
+  priv_alloc(me, mine, 0);
+  arks_response_result pr = {me->reason, me->counted, me->usage};
+  uint32_t k = 0;
   for (uint32_t i = 0; i < n; i++)
-    if (a->shard[i] == a->tid) handle_response(a->o, a->pb, a->pr, i);
+    if (a->shard[i] == a->tid) {
+      a->slot[i] = k;
+      handle_response(a->o, a->pb, &pr, i, k++);
+    }
+  pthread_barrier_wait(a->bar);
+  arks_response_result* r = a->pr;
+  for (uint32_t i = lo; i < hi; i++) {
+    const mt_priv* w = &a->priv[a->shard[i]];
+    const size_t j = a->slot[i];
+    r->reason[i] = w->reason[j]; r->counted[i] = w->counted[j];
+    r->usage[3 * (size_t)i] = w->usage[3 * j]; r->usage[3 * (size_t)i + 1] = w->usage[3 * j + 1]; r->usage[3 * (size_t)i + 2] = w->usage[3 * j + 2];
+  }
   return NULL;
 }
 static int run_mt(void* (*fn)(void*), mt_arg* base, int nt, uint32_t n) {
@@ -604,26 +671,33 @@ static int run_mt(void* (*fn)(void*), mt_arg* base, int nt, uint32_t n) {
   if (nt > 256) nt = 256;
   pthread_t th[256];
   mt_arg args[256];
+  mt_priv priv[256];
   pthread_barrier_t bar;
   pthread_barrier_init(&bar, NULL, (unsigned)nt);
   uint16_t* shard = (uint16_t*)malloc((size_t)n * 2 + 2);
+  uint32_t* slot = (uint32_t*)malloc((size_t)n * 4 + 4);
+  memset(priv, 0, sizeof priv);
   for (int t = 0; t < nt; t++) {
     args[t] = *base;
     args[t].tid = t;
     args[t].nt = nt;
     args[t].shard = shard;
+    args[t].slot = slot;
+    args[t].priv = priv;
     args[t].bar = &bar;
     pthread_create(&th[t], NULL, fn, &args[t]);
   }
   for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
+  for (int t = 0; t < nt; t++) priv_free(&priv[t]);
   pthread_barrier_destroy(&bar);
   free(shard);
+  free(slot);
   return 0;
 }
 int ork_request_batch_mt(ork* o, const arks_request_batch* b, arks_request_result* r, int nt) {
   int rc = check_time(o, b->now_unix);
   if (rc) return rc;
-  mt_arg a = {o, b, r, NULL, NULL, 0, nt, NULL, NULL};
+  mt_arg a = {o, b, r, NULL, NULL, 0, nt, NULL, NULL, NULL, NULL};
   return run_mt(mt_req, &a, nt, b->n);
 }
 int ork_response_batch_mt(ork* o, const arks_response_batch* b, arks_response_result* r, int nt) {
@@ -631,7 +705,7 @@ int ork_response_batch_mt(ork* o, const arks_response_batch* b, arks_response_re
   if (rc) return rc;
   for (uint32_t i = 0; i < b->n; i++)
     if (b->qos[i] < 0 || (uint32_t)b->qos[i] >= o->n_qos) return ARKS_E_INVALID_ARG;
-  mt_arg a = {o, NULL, NULL, b, r, 0, nt, NULL, NULL};
+  mt_arg a = {o, NULL, NULL, b, r, 0, nt, NULL, NULL, NULL, NULL};
   return run_mt(mt_resp, &a, nt, b->n);
 }
 

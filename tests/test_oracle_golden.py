@@ -180,3 +180,30 @@ def test_sse_fixture():
     whole = b"".join(chunks)
     cut = whole.index(b'"usage"') + 3
     assert orklib.parse_sse_chunk(whole[cut:])[0] == 1
+
+
+def test_threaded_baseline_equals_serial_oracle():
+    """bench.py's cpu_baseline / --impl reference run the oracle tenant-sharded over threads (ork_*_batch_mt): same
+    decisions, counters and metric rows as the serial oracle, whatever the thread count"""
+    import numpy as np
+    import orklib
+    from arks_b200 import traffic
+    w = traffic.Workload(n_tenants=300, seed=9)
+    now = 1_700_000_000
+    serial = orklib.Oracle(w.tables)
+    for threads in (1, 3, 7):
+        o = orklib.Oracle(w.tables)
+        s = orklib.Oracle(w.tables)
+        t = now
+        for wave in range(3):
+            req = w.request_batch(2500, t, seed=20 + wave, stream_frac=0.3, noise_frac=0.15, varied=bool(wave & 1))
+            a, b = s.request_batch(req), o.request_batch(req, threads=threads)
+            assert all(np.array_equal(v, b.fields()[k]) for k, v in a.fields().items()), (threads, wave)
+            resp = w.response_batch(a, t + 1, seed=40 + wave, noise_frac=0.1, varied=bool(wave & 1))
+            c, d = s.response_batch(resp), o.response_batch(resp, threads=threads)
+            assert all(np.array_equal(v, d.fields()[k]) for k, v in c.fields().items()), (threads, wave)
+            assert np.array_equal(s.snapshot_rate(t + 1), o.snapshot_rate(t + 1))
+            assert np.array_equal(s.snapshot_quota(), o.snapshot_quota())
+            assert np.array_equal(s.snapshot_metrics(), o.snapshot_metrics())
+            t += 45
+    del serial
