@@ -666,30 +666,65 @@ static void* mt_resp(void* p) {
   }
   return NULL;
 }
-static int run_mt(void* (*fn)(void*), mt_arg* base, int nt, uint32_t n) {
-  if (nt < 1) nt = 1;
-  if (nt > 256) nt = 256;
+/* Workers are created once (first threaded call, or when the thread count changes) and parked on a barrier between
+ * batches: creating and joining 128 threads per batch costs more than the batch itself. */
+typedef struct {
   pthread_t th[256];
   mt_arg args[256];
   mt_priv priv[256];
-  pthread_barrier_t bar;
-  pthread_barrier_init(&bar, NULL, (unsigned)nt);
+  pthread_barrier_t start, done, mid; /* start / done: nt workers + the caller; mid: the workers' own barrier */
+  void* (*fn)(void*);
+  int nt, quit;
+} mt_pool;
+static mt_pool* g_pool; /* one pool per process: the baseline runs one oracle at a time */
+static void* pool_worker(void* p) {
+  mt_arg* a = (mt_arg*)p;
+  for (;;) {
+    pthread_barrier_wait(&g_pool->start);
+    if (g_pool->quit) return NULL;
+    g_pool->fn(a);
+    pthread_barrier_wait(&g_pool->done);
+  }
+}
+static void pool_stop(void) {
+  if (!g_pool) return;
+  g_pool->quit = 1;
+  pthread_barrier_wait(&g_pool->start);
+  for (int t = 0; t < g_pool->nt; t++) pthread_join(g_pool->th[t], NULL);
+  pthread_barrier_destroy(&g_pool->start);
+  pthread_barrier_destroy(&g_pool->done);
+  pthread_barrier_destroy(&g_pool->mid);
+  free(g_pool);
+  g_pool = NULL;
+}
+static int run_mt(void* (*fn)(void*), mt_arg* base, int nt, uint32_t n) {
+  if (nt < 1) nt = 1;
+  if (nt > 256) nt = 256;
+  if (g_pool && g_pool->nt != nt) pool_stop();
+  if (!g_pool) {
+    g_pool = (mt_pool*)calloc(1, sizeof *g_pool);
+    g_pool->nt = nt;
+    pthread_barrier_init(&g_pool->start, NULL, (unsigned)nt + 1);
+    pthread_barrier_init(&g_pool->done, NULL, (unsigned)nt + 1);
+    pthread_barrier_init(&g_pool->mid, NULL, (unsigned)nt);
+    for (int t = 0; t < nt; t++) pthread_create(&g_pool->th[t], NULL, pool_worker, &g_pool->args[t]);
+  }
   uint16_t* shard = (uint16_t*)malloc((size_t)n * 2 + 2);
   uint32_t* slot = (uint32_t*)malloc((size_t)n * 4 + 4);
-  memset(priv, 0, sizeof priv);
+  memset(g_pool->priv, 0, sizeof g_pool->priv);
   for (int t = 0; t < nt; t++) {
-    args[t] = *base;
-    args[t].tid = t;
-    args[t].nt = nt;
-    args[t].shard = shard;
-    args[t].slot = slot;
-    args[t].priv = priv;
-    args[t].bar = &bar;
-    pthread_create(&th[t], NULL, fn, &args[t]);
+    g_pool->args[t] = *base;
+    g_pool->args[t].tid = t;
+    g_pool->args[t].nt = nt;
+    g_pool->args[t].shard = shard;
+    g_pool->args[t].slot = slot;
+    g_pool->args[t].priv = g_pool->priv;
+    g_pool->args[t].bar = &g_pool->mid;
   }
-  for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
-  for (int t = 0; t < nt; t++) priv_free(&priv[t]);
-  pthread_barrier_destroy(&bar);
+  g_pool->fn = fn;
+  pthread_barrier_wait(&g_pool->start);
+  pthread_barrier_wait(&g_pool->done);
+  for (int t = 0; t < nt; t++) priv_free(&g_pool->priv[t]);
   free(shard);
   free(slot);
   return 0;
