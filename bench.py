@@ -126,6 +126,25 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def best_thread_count(o, req, resp, now):
+    """The threaded oracle does not scale to every hardware thread of every box (hyper-threads, cgroup quotas): time one
+    wave at cpu_count, /2, /4, /8 threads and keep the fastest, so that the baseline is the best the host can do."""
+    n = os.cpu_count() or 1
+    best, best_t = n, None
+    for th in sorted({max(1, n), max(1, n // 2), max(1, n // 4), max(1, n // 8)}, reverse=True):
+        ts = []
+        for _ in range(2):
+            req.now_unix, resp.now_unix = now, now + 1
+            t0 = time.perf_counter()
+            o.request_batch(req, threads=th)
+            o.response_batch(resp, threads=th)
+            ts.append(time.perf_counter() - t0)
+            now += STEP_S
+        if best_t is None or min(ts) < best_t:
+            best, best_t = th, min(ts)
+    return best, now
+
+
 def cpu_baseline(workload, wave, seconds=12.0, threads=None):
     """The reference's CPU path as restated by the oracle (kind=port), tenant-sharded over the host's cores, on a
     bounded sample of the same workload. In-memory counters: it omits the ~9 Redis round trips per request the real
@@ -138,7 +157,8 @@ def cpu_baseline(workload, wave, seconds=12.0, threads=None):
     a = o.request_batch(req, threads=threads)
     resp = workload.response_batch(a, NOW0 + 1, seed=4243, body_size=RESP_BODY, varied=True, n_templates=N_TEMPL)
     o.response_batch(resp, threads=threads)
-    now, done, t_used, steps = NOW0 + STEP_S, 0, 0.0, 0
+    threads, now = best_thread_count(o, req, resp, NOW0 + STEP_S)
+    done, t_used, steps = 0, 0.0, 0
     while t_used < seconds and steps < 400:
         req.now_unix, resp.now_unix = now, now + 1
         t0 = time.perf_counter()
@@ -150,7 +170,8 @@ def cpu_baseline(workload, wave, seconds=12.0, threads=None):
         steps += 1
     return {"value": done / t_used, "unit": "req/s", "cores": threads, "kind": "port",
             "sample": f"{steps} waves of {req.n} requests + {resp.n} responses, oracle/libarks_oracle.so "
-                      f"(C restatement of the Go path, in-memory counters, no Redis), {threads} threads tenant-sharded"}, o
+                      f"(C restatement of the Go path, in-memory counters, no Redis), {threads} threads tenant-sharded "
+                      f"(fastest of cpu_count, /2, /4, /8 on this host)"}, o
 
 
 def run_reference(args):
@@ -167,7 +188,7 @@ def run_reference(args):
     a = o.request_batch(req, threads=threads)
     resp = w.response_batch(a, NOW0 + 1, seed=2000, body_size=RESP_BODY, varied=True, n_templates=N_TEMPL)
     o.response_batch(resp, threads=threads)
-    now = NOW0 + STEP_S
+    threads, now = best_thread_count(o, req, resp, NOW0 + STEP_S)
     for _ in range(args.warmup):
         req.now_unix, resp.now_unix = now, now + 1
         o.request_batch(req, threads=threads)
@@ -183,7 +204,7 @@ def run_reference(args):
     v = args.steps * req.n / dt
     sample = (f"{args.steps} waves of {req.n} requests + {resp.n} responses per step; the Go gateway cannot be built here "
               f"(no Go toolchain), so this is oracle/libarks_oracle.so: a C restatement of the Go path with in-memory "
-              f"counters (no Redis round trips), {threads} threads tenant-sharded")
+              f"counters (no Redis round trips), {threads} threads tenant-sharded (fastest of cpu_count, /2, /4, /8 on this host)")
     print(json.dumps({
         "impl": "reference", "metric": "gateway requests/s (request + response phase)", "value": v, "unit": "req/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
