@@ -133,7 +133,7 @@ def best_thread_count(o, req, resp, now):
     best, best_t = n, None
     for th in sorted({max(1, n), max(1, n // 2), max(1, n // 4), max(1, n // 8)}, reverse=True):
         ts = []
-        for _ in range(2):
+        for _ in range(4):  # the first call at a new thread count also (re)creates the worker pool
             req.now_unix, resp.now_unix = now, now + 1
             t0 = time.perf_counter()
             o.request_batch(req, threads=th)
