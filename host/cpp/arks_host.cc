@@ -182,6 +182,12 @@ struct Batcher::Impl {
         rb.qos = b.qos; rb.flags = b.flags; rb.now_unix = now;
         f.rc_resp = arks_submit_response_async(ctx, &rb);
       }
+      if (opt.max_inflight == 1) {  // nothing else can be queued meanwhile: finish the batch here, one thread hand-off less
+        deliver(f);
+        lk.lock();
+        recycle(f);
+        continue;
+      }
       lk.lock();
       inflight.push_back(f);
       cv_done.notify_one();
@@ -203,60 +209,70 @@ struct Batcher::Impl {
       InFlight f = inflight.front();
       inflight.pop_front();
       lk.unlock();
-      if (f.req) {
-        Block& b = *f.req;
-        int rc = f.rc_req;
-        if (rc == 0) {
-          arks_request_result rr{b.reason, b.detail, b.rflags, b.rqos, b.rtoken, b.rpick, b.cur_usage, b.limit_max};
-          rc = arks_wait_request(ctx, f.slot, &rr);
-        }
-        for (uint32_t i = 0; i < b.n; i++) {
-          RequestDecision d{};
-          if (rc) d.reason = kReasonHostError;
-          else {
-            d.reason = b.reason[i]; d.detail = b.detail[i]; d.flags = b.rflags[i];
-            d.qos = b.rqos[i]; d.token = b.rtoken[i]; d.pick = b.rpick[i];
-            d.cur_usage = b.cur_usage[i]; d.limit_max = b.limit_max[i];
-          }
-          d.cycle = b.cycle; d.index = i; d.now_unix = b.now;
-          b.rcb[i](b.user[i], d);
-        }
-      }
-      if (f.resp) {
-        Block& b = *f.resp;
-        int rc = f.rc_resp;
-        if (rc == 0) {
-          arks_response_result rr{b.reason, b.counted, b.usage};
-          rc = arks_wait_response(ctx, f.slot, &rr);
-        }
-        for (uint32_t i = 0; i < b.n; i++) {
-          ResponseDecision d{};
-          if (rc) d.reason = kReasonHostError;
-          else {
-            d.reason = b.reason[i]; d.counted = b.counted[i];
-            for (int k = 0; k < 3; k++) d.usage[k] = b.usage[3 * (size_t)i + k];
-          }
-          d.cycle = b.cycle; d.index = i; d.now_unix = b.now;
-          b.pcb[i](b.user[i], d);
-        }
-      }
+      deliver(f);
       lk.lock();
-      st.cycles++;
-      if (f.req) {
-        st.request_batches++; st.requests += f.req->n;
-        if (f.req->n > st.max_request_batch) st.max_request_batch = f.req->n;
-        f.req->n = 0; f.req->bytes = 0; f.req->tok_bytes = 0; f.req->filled.store(0, std::memory_order_relaxed);
-        free_req.push_back(f.req);
-      }
-      if (f.resp) {
-        st.response_batches++; st.responses += f.resp->n;
-        if (f.resp->n > st.max_response_batch) st.max_response_batch = f.resp->n;
-        f.resp->n = 0; f.resp->bytes = 0; f.resp->filled.store(0, std::memory_order_relaxed);
-        free_resp.push_back(f.resp);
-      }
-      slot_busy[f.slot] = false;
-      cv_work.notify_one();
+      recycle(f);
     }
+  }
+
+  // wait for a submitted batch and hand every row its decision (no lock held)
+  void deliver(InFlight& f) {
+
+    if (f.req) {
+      Block& b = *f.req;
+      int rc = f.rc_req;
+      if (rc == 0) {
+        arks_request_result rr{b.reason, b.detail, b.rflags, b.rqos, b.rtoken, b.rpick, b.cur_usage, b.limit_max};
+        rc = arks_wait_request(ctx, f.slot, &rr);
+      }
+      for (uint32_t i = 0; i < b.n; i++) {
+        RequestDecision d{};
+        if (rc) d.reason = kReasonHostError;
+        else {
+          d.reason = b.reason[i]; d.detail = b.detail[i]; d.flags = b.rflags[i];
+          d.qos = b.rqos[i]; d.token = b.rtoken[i]; d.pick = b.rpick[i];
+          d.cur_usage = b.cur_usage[i]; d.limit_max = b.limit_max[i];
+        }
+        d.cycle = b.cycle; d.index = i; d.now_unix = b.now;
+        b.rcb[i](b.user[i], d);
+      }
+    }
+    if (f.resp) {
+      Block& b = *f.resp;
+      int rc = f.rc_resp;
+      if (rc == 0) {
+        arks_response_result rr{b.reason, b.counted, b.usage};
+        rc = arks_wait_response(ctx, f.slot, &rr);
+      }
+      for (uint32_t i = 0; i < b.n; i++) {
+        ResponseDecision d{};
+        if (rc) d.reason = kReasonHostError;
+        else {
+          d.reason = b.reason[i]; d.counted = b.counted[i];
+          for (int k = 0; k < 3; k++) d.usage[k] = b.usage[3 * (size_t)i + k];
+        }
+        d.cycle = b.cycle; d.index = i; d.now_unix = b.now;
+        b.pcb[i](b.user[i], d);
+      }
+    }
+  }
+  // stats, block and slot back to the pools (lock held)
+  void recycle(InFlight& f) {
+    st.cycles++;
+    if (f.req) {
+      st.request_batches++; st.requests += f.req->n;
+      if (f.req->n > st.max_request_batch) st.max_request_batch = f.req->n;
+      f.req->n = 0; f.req->bytes = 0; f.req->tok_bytes = 0; f.req->filled.store(0, std::memory_order_relaxed);
+      free_req.push_back(f.req);
+    }
+    if (f.resp) {
+      st.response_batches++; st.responses += f.resp->n;
+      if (f.resp->n > st.max_response_batch) st.max_response_batch = f.resp->n;
+      f.resp->n = 0; f.resp->bytes = 0; f.resp->filled.store(0, std::memory_order_relaxed);
+      free_resp.push_back(f.resp);
+    }
+    slot_busy[f.slot] = false;
+    cv_work.notify_one();
   }
 };
 
@@ -273,7 +289,7 @@ Batcher::Batcher(arks_ctx* ctx, const BatcherOptions& opt) : p_(new Impl()) {
   p_->open_req = p_->free_req.back(); p_->free_req.pop_back();
   for (int k = 0; k < 2; k++) { p_->open_resp[k] = p_->free_resp.back(); p_->free_resp.pop_back(); }
   p_->dispatcher = std::thread([this] { p_->dispatch_loop(); });
-  p_->completer = std::thread([this] { p_->complete_loop(); });
+  if (opt.max_inflight > 1) p_->completer = std::thread([this] { p_->complete_loop(); });
 }
 Batcher::~Batcher() {
   {
@@ -283,7 +299,7 @@ Batcher::~Batcher() {
   p_->cv_work.notify_all();
   p_->dispatcher.join();
   p_->cv_done.notify_all();
-  p_->completer.join();
+  if (p_->completer.joinable()) p_->completer.join();
   delete p_;  // staging blocks are left to the process (pinned host memory of a long-lived server object)
 }
 void Batcher::SetClock(int64_t (*clock)(void*), void* arg) {
