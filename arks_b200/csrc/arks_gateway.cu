@@ -1138,6 +1138,7 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaMalloc(&ctx->d_lenhist, (size_t)4 * kLenBuckets));
   ctx->result_cap = align_up(n, 256) * 3 + align_up(n * 4, 256) * 3 + align_up(n * 8, 256) * 3;
   CK(cudaMalloc(&ctx->d_result, ctx->result_cap));
+  CK(cudaMemset(ctx->d_result, 0, ctx->result_cap));  // the packed block has alignment gaps that the D2H copies too
   return 0;
 }
 
