@@ -99,11 +99,15 @@ struct Batcher::Impl {
   mutable std::mutex mu;
   std::condition_variable cv_work, cv_space, cv_done;
   bool stop = false;
+  bool cycling = false;  // a cycle is being run (by the dispatcher thread or by a leading caller): one submitter at a time
   uint64_t cycle = 0;
   int64_t (*clock)(void*) = nullptr;
   void* clock_arg = nullptr;
   BatcherStats st{};
   std::thread dispatcher, completer;
+
+  bool submit_request(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user, bool can_lead);
+  bool submit_response(int32_t qos, std::string_view body, uint8_t flags, ResponseCallback cb, void* user, bool can_lead);
 
   void alloc(Block& b, bool is_req) {
     const uint32_t m = opt.max_batch;
@@ -139,59 +143,80 @@ struct Batcher::Impl {
     return busy < (int)opt.max_inflight ? first : -1;
   }
 
-  // Thread 1: closes the open blocks and queues them on the device (asynchronous submits, one staging slot each).
+  bool has_work() const { return open_req->n || open_resp[0]->n || open_resp[1]->n; }
+  bool can_cycle() const { return !cycling && has_work() && free_slot() >= 0 && !free_req.empty() && !free_resp.empty(); }
+
+  // One cycle: close the open blocks and queue them on the device (asynchronous submits, one staging slot). Entered
+  // and left with `lk` held and `cycling` set by the caller; the lock is dropped while the device is being talked to.
+  // With one batch in flight the cycle also waits for the batch and hands every row its decision.
+  void run_cycle(std::unique_lock<std::mutex>& lk) {
+    InFlight f{nullptr, nullptr, free_slot(), 0, 0};
+    slot_busy[f.slot] = true;
+    if (open_req->n) { f.req = open_req; open_req = free_req.back(); free_req.pop_back(); }
+    // one response batch per cycle (a staging slot holds one): alternate when both kinds are waiting
+    int kind = open_resp[0]->n && open_resp[1]->n ? (resp_turn ^= 1) : (open_resp[1]->n ? 1 : 0);
+    if (open_resp[kind]->n) { f.resp = open_resp[kind]; open_resp[kind] = free_resp.back(); free_resp.pop_back(); }
+    const uint64_t cyc = cycle++;
+    const int64_t now = clock ? clock(clock_arg) : (int64_t)time(nullptr);
+    lk.unlock();
+    cv_space.notify_all();
+    arks_select_slot(ctx, f.slot);
+    if (f.req) {
+      Block& b = *f.req;
+      wait_filled(b);
+      b.cycle = cyc; b.now = now;
+      b.token_off[b.n] = (uint32_t)b.tok_bytes;
+      arks_request_batch rb{};
+      rb.n = b.n; rb.bodies = b.bodies; rb.body_off = b.body_off; rb.body_len = b.body_len; rb.bodies_bytes = b.bytes;
+      rb.tokens = b.tokens; rb.token_off = b.token_off; rb.pick_rand = b.rnd; rb.now_unix = now;
+      f.rc_req = arks_submit_request_async(ctx, &rb);
+    }
+    if (f.resp) {
+      Block& b = *f.resp;
+      wait_filled(b);
+      b.cycle = cyc; b.now = now;
+      arks_response_batch rb{};
+      rb.n = b.n; rb.bodies = b.bodies; rb.body_off = b.body_off; rb.body_len = b.body_len; rb.bodies_bytes = b.bytes;
+      rb.qos = b.qos; rb.flags = b.flags; rb.now_unix = now;
+      f.rc_resp = arks_submit_response_async(ctx, &rb);
+    }
+    if (opt.max_inflight == 1) {  // nothing else can be queued meanwhile: finish the batch here, one thread hand-off less
+      deliver(f);
+      lk.lock();
+      recycle(f);
+      return;
+    }
+    lk.lock();
+    inflight.push_back(f);
+    cv_done.notify_one();
+  }
+
+  // Thread 1: runs the cycles nobody else runs (see lead_cycle).
   void dispatch_loop() {
     std::unique_lock<std::mutex> lk(mu);
     for (;;) {
-      cv_work.wait(lk, [&] {
-        return stop || ((open_req->n || open_resp[0]->n || open_resp[1]->n) && free_slot() >= 0 && !free_req.empty() && !free_resp.empty());
-      });
-      if (stop && !open_req->n && !open_resp[0]->n && !open_resp[1]->n) return;
+      cv_work.wait(lk, [&] { return (stop && !cycling) || can_cycle(); });
+      if (!can_cycle()) {
+        if (stop && !has_work()) return;
+        continue;
+      }
+      cycling = true;
       if (opt.linger_us) {  // give concurrent streams a moment to join the cycle
         lk.unlock();
         std::this_thread::sleep_for(std::chrono::microseconds(opt.linger_us));
         lk.lock();
       }
-      InFlight f{nullptr, nullptr, free_slot(), 0, 0};
-      slot_busy[f.slot] = true;
-      if (open_req->n) { f.req = open_req; open_req = free_req.back(); free_req.pop_back(); }
-      // one response batch per cycle (a staging slot holds one): alternate when both kinds are waiting
-      int kind = open_resp[0]->n && open_resp[1]->n ? (resp_turn ^= 1) : (open_resp[1]->n ? 1 : 0);
-      if (open_resp[kind]->n) { f.resp = open_resp[kind]; open_resp[kind] = free_resp.back(); free_resp.pop_back(); }
-      const uint64_t cyc = cycle++;
-      const int64_t now = clock ? clock(clock_arg) : (int64_t)time(nullptr);
-      lk.unlock();
-      cv_space.notify_all();
-      arks_select_slot(ctx, f.slot);
-      if (f.req) {
-        Block& b = *f.req;
-        wait_filled(b);
-        b.cycle = cyc; b.now = now;
-        b.token_off[b.n] = (uint32_t)b.tok_bytes;
-        arks_request_batch rb{};
-        rb.n = b.n; rb.bodies = b.bodies; rb.body_off = b.body_off; rb.body_len = b.body_len; rb.bodies_bytes = b.bytes;
-        rb.tokens = b.tokens; rb.token_off = b.token_off; rb.pick_rand = b.rnd; rb.now_unix = now;
-        f.rc_req = arks_submit_request_async(ctx, &rb);
-      }
-      if (f.resp) {
-        Block& b = *f.resp;
-        wait_filled(b);
-        b.cycle = cyc; b.now = now;
-        arks_response_batch rb{};
-        rb.n = b.n; rb.bodies = b.bodies; rb.body_off = b.body_off; rb.body_len = b.body_len; rb.bodies_bytes = b.bytes;
-        rb.qos = b.qos; rb.flags = b.flags; rb.now_unix = now;
-        f.rc_resp = arks_submit_response_async(ctx, &rb);
-      }
-      if (opt.max_inflight == 1) {  // nothing else can be queued meanwhile: finish the batch here, one thread hand-off less
-        deliver(f);
-        lk.lock();
-        recycle(f);
-        continue;
-      }
-      lk.lock();
-      inflight.push_back(f);
-      cv_done.notify_one();
+      run_cycle(lk);
+      cycling = false;
     }
+  }
+  // A blocked caller that finds the batcher idle runs the cycle for its own row itself: on a quiet system a request
+  // then costs no thread hand-off at all (caller -> dispatcher -> caller otherwise). Lock held on entry and exit.
+  bool may_lead() const { return opt.max_inflight == 1 && opt.linger_us == 0 && !cycling && free_slot() >= 0 && !free_req.empty() && !free_resp.empty(); }
+  void lead_cycle(std::unique_lock<std::mutex>& lk) {
+    run_cycle(lk);
+    cycling = false;
+    if (has_work()) cv_work.notify_one();
   }
 
   // Thread 2: waits for the oldest batch, hands every row its decision, recycles block and slot.
@@ -312,8 +337,9 @@ BatcherStats Batcher::Stats() const {
   return p_->st;
 }
 
-bool Batcher::SubmitRequest(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user) {
-  Impl& I = *p_;
+bool Batcher::Impl::submit_request(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user,
+                                   bool can_lead) {
+  Impl& I = *this;
   const size_t need = align16(body.size());
   if (need > I.opt.max_bytes || token.size() > 255) return false;
   std::unique_lock<std::mutex> lk(I.mu);
@@ -334,17 +360,23 @@ bool Batcher::SubmitRequest(std::string_view token, std::string_view body, uint6
   b->rnd[row] = pick_rand;
   b->rcb[row] = cb;
   b->user[row] = user;
+  const bool lead = can_lead && row == 0 && I.may_lead();
+  if (lead) I.cycling = true;
   lk.unlock();
-  if (row == 0) I.cv_work.notify_one();
+  if (row == 0 && !lead) I.cv_work.notify_one();
   memcpy(b->bodies + off, body.data(), body.size());
   memset(b->bodies + off + body.size(), 0, need - body.size());
   memcpy(b->tokens + toff, token.data(), token.size());
   b->filled.fetch_add(1, std::memory_order_release);
+  if (lead) {
+    lk.lock();
+    I.lead_cycle(lk);
+  }
   return true;
 }
 
-bool Batcher::SubmitResponse(int32_t qos, std::string_view body, uint8_t flags, ResponseCallback cb, void* user) {
-  Impl& I = *p_;
+bool Batcher::Impl::submit_response(int32_t qos, std::string_view body, uint8_t flags, ResponseCallback cb, void* user, bool can_lead) {
+  Impl& I = *this;
   const size_t need = align16(body.size());
   if (need > I.opt.max_bytes) return false;
   std::unique_lock<std::mutex> lk(I.mu);
@@ -364,17 +396,30 @@ bool Batcher::SubmitResponse(int32_t qos, std::string_view body, uint8_t flags, 
   b->flags[row] = flags;
   b->pcb[row] = cb;
   b->user[row] = user;
+  const bool lead = can_lead && row == 0 && I.may_lead();
+  if (lead) I.cycling = true;
   lk.unlock();
-  if (row == 0) I.cv_work.notify_one();
+  if (row == 0 && !lead) I.cv_work.notify_one();
   memcpy(b->bodies + off, body.data(), body.size());
   memset(b->bodies + off + body.size(), 0, need - body.size());
   b->filled.fetch_add(1, std::memory_order_release);
+  if (lead) {
+    lk.lock();
+    I.lead_cycle(lk);
+  }
   return true;
+}
+
+bool Batcher::SubmitRequest(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user) {
+  return p_->submit_request(token, body, pick_rand, cb, user, false);
+}
+bool Batcher::SubmitResponse(int32_t qos, std::string_view body, uint8_t flags, ResponseCallback cb, void* user) {
+  return p_->submit_response(qos, body, flags, cb, user, false);
 }
 
 RequestDecision Batcher::HandleRequestBody(std::string_view token, std::string_view body, uint64_t pick_rand) {
   Parked p;
-  if (!SubmitRequest(token, body, pick_rand, wake_request, &p)) {
+  if (!p_->submit_request(token, body, pick_rand, wake_request, &p, true)) {
     RequestDecision d{};
     d.reason = kReasonHostError;
     return d;
@@ -384,7 +429,7 @@ RequestDecision Batcher::HandleRequestBody(std::string_view token, std::string_v
 }
 ResponseDecision Batcher::HandleResponseBody(int32_t qos, std::string_view body, uint8_t flags) {
   Parked p;
-  if (!SubmitResponse(qos, body, flags, wake_response, &p)) {
+  if (!p_->submit_response(qos, body, flags, wake_response, &p, true)) {
     ResponseDecision d{};
     d.reason = kReasonHostError;
     return d;
