@@ -6,8 +6,9 @@
 //                    pinned staging block and copies its own body; a dispatcher thread closes the block and queues it
 //                    on the device (arks_submit_*_async, up to 4 batches in flight, no timer: the next block fills
 //                    while earlier ones are on the GPU); a completion thread waits for the oldest batch and hands
-//                    every row its decision (callback, or futex wake of a blocked caller). host/go/b200/batcher.go
-//                    is the Go twin.
+//                    every row its decision (callback, or futex wake of a blocked caller); with one batch in flight
+//                    (the default) the dispatcher does both, and a blocked caller that finds the batcher idle runs the
+//                    cycle for its own row itself. host/go/b200/batcher.go is the Go twin.
 //   StreamProcessor  Server.Process's per-stream state machine (pkg/gateway/gateway.go:77-138) and the four handlers
 //                    (handle_request.go:33-249, handle_response.go:37-268) over decoded ext_proc messages; the gRPC /
 //                    protobuf transport stays with the embedding server
