@@ -151,3 +151,37 @@ func (c *Ctx) SnapshotQuota(out []int64) error {
 func (c *Ctx) SetQuotaUsage(quota uint32, usage [3]int64) error {
 	return c.err(C.arks_set_quota_usage(c.h, C.uint32_t(quota), (*C.int64_t)(unsafe.Pointer(&usage[0]))))
 }
+
+// SyncQuotaUsage runs the body of syncQuotaUsage (qosconfig/arks_impl.go:217-300) for every ArksQuota in one call.
+// present[q] / used[3q..3q+2] carry Status.QuotaStatus in and out; action[q]&1: write the status back to the CR.
+func (c *Ctx) SyncQuotaUsage(restore bool, present []uint32, used []int64, action []uint8) error {
+	mode := C.int(C.ARKS_SYNC_REFERENCE)
+	if restore {
+		mode = C.int(C.ARKS_SYNC_RESTORE)
+	}
+	return c.err(C.arks_sync_quota_usage(c.h, mode, (*C.uint32_t)(unsafe.Pointer(&present[0])),
+		(*C.int64_t)(unsafe.Pointer(&used[0])), (*C.uint8_t)(unsafe.Pointer(&action[0]))))
+}
+
+// EnableMetrics / SnapshotMetrics: the series of pkg/gateway/metrics that are functions of the request stream, kept on
+// the device (ARKS_METRIC_COLS int64 per qos entry); the Prometheus collector reads them at scrape time.
+func (c *Ctx) EnableMetrics(on bool) error {
+	v := C.int(0)
+	if on {
+		v = 1
+	}
+	return c.err(C.arks_enable_metrics(c.h, v))
+}
+func (c *Ctx) SnapshotMetrics(rows []int64) error {
+	return c.err(C.arks_snapshot_metrics(c.h, (*C.int64_t)(unsafe.Pointer(&rows[0]))))
+}
+
+// AllocPinned returns page-locked memory for batch staging as a byte slice (freed with FreePinned).
+func AllocPinned(n int) []byte {
+	p := C.arks_alloc_pinned(C.size_t(n))
+	if p == nil {
+		return nil
+	}
+	return unsafe.Slice((*byte)(p), n)
+}
+func FreePinned(b []byte) { C.arks_free_pinned(unsafe.Pointer(&b[0])) }
