@@ -178,6 +178,10 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
 // one body's line hit 8 different bank groups, and the 32 lanes that each read "their" unit u hit 32 different
 // slots of one 512-byte row, so both sides of the transpose are conflict-free when lanes move in lock step.
 // ------------------------------------------------------------------------------------------------
+// A micro-batch whose bodies fit here travels as ONE upload (bodies appended to the offsets / tokens block) on the compute
+// stream itself: one copy and one cross-stream event less on the path a lone request takes.
+constexpr size_t kSmallBatchBytes = 256 << 10;
+
 constexpr int kHotGroup = 256;  // above this many arrivals of one qos entry in a batch the member list is not walked
 #ifndef ARKS_KWIN
 #define ARKS_KWIN 128
@@ -1119,7 +1123,7 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
   size_t n = max_batch;
   // meta: body_off, body_len, token_off(n+1), pick_rand, qos, flags + token bytes (256 B per request budget)
-  ctx->meta_cap = align_up(n * 4, 256) * 4 + align_up(n * 8, 256) + align_up(n, 256) + align_up(n * 256, 256);
+  ctx->meta_cap = align_up(n * 4, 256) * 4 + align_up(n * 8, 256) + align_up(n, 256) + align_up(n * 256, 256) + kSmallBatchBytes + 256;
   for (int k = 0; k < 4; k++) CK(cudaEventCreate(&ctx->ev[k]));
 #define ARKS_FOR_SCHED(X) X(0) X(1) X(8)
 #define ARKS_SET(S)                                                                                                        \
@@ -1501,13 +1505,20 @@ int arks_stage_request_batch(arks_ctx* ctx, const arks_request_batch* b) {
   memcpy(h + o_toff, b->token_off, (size_t)(n + 1) * 4);
   if (b->pick_rand) memcpy(h + o_rand, b->pick_rand, (size_t)n * 8);
   memcpy(h + o_tok, b->tokens, tok_bytes);
-  // uploads run on their own stream so that they overlap the kernels of the batches queued before this one
-  CK(cudaStreamWaitEvent(ctx->h2d, sl.req_ran, 0));  // the previous tenant of this slot's device buffers is done
-  CK(cudaMemcpyAsync(sl.d_req_bodies, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->h2d));
-  CK(cudaMemcpyAsync(sl.d_req_meta, h, total, cudaMemcpyHostToDevice, ctx->h2d));
-  CK(cudaEventRecord(sl.req_copied, ctx->h2d));
+  const bool small = b->bodies_bytes <= kSmallBatchBytes;
+  if (small) {
+    memcpy(h + total, b->bodies, b->bodies_bytes);
+    CK(cudaMemcpyAsync(sl.d_req_meta, h, total + b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(sl.req_copied, ctx->stream));
+  } else {
+    // uploads run on their own stream so that they overlap the kernels of the batches queued before this one
+    CK(cudaStreamWaitEvent(ctx->h2d, sl.req_ran, 0));  // the previous tenant of this slot's device buffers is done
+    CK(cudaMemcpyAsync(sl.d_req_bodies, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->h2d));
+    CK(cudaMemcpyAsync(sl.d_req_meta, h, total, cudaMemcpyHostToDevice, ctx->h2d));
+    CK(cudaEventRecord(sl.req_copied, ctx->h2d));
+  }
   ReqDev& r = sl.rq;
-  r.bodies = sl.d_req_bodies;
+  r.bodies = small ? sl.d_req_meta + total : sl.d_req_bodies;
   r.body_off = (const uint32_t*)(sl.d_req_meta + o_off);
   r.body_len = (const uint32_t*)(sl.d_req_meta + o_len);
   r.token_off = (const uint32_t*)(sl.d_req_meta + o_toff);
@@ -1717,12 +1728,19 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   memcpy(h + o_len, b->body_len, (size_t)n * 4);
   memcpy(h + o_qos, b->qos, (size_t)n * 4);
   memcpy(h + o_fl, b->flags, n);
-  CK(cudaStreamWaitEvent(ctx->h2d, sl.resp_ran, 0));
-  CK(cudaMemcpyAsync(sl.d_resp_bodies, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->h2d));
-  CK(cudaMemcpyAsync(sl.d_resp_meta, h, total, cudaMemcpyHostToDevice, ctx->h2d));
-  CK(cudaEventRecord(sl.resp_copied, ctx->h2d));
+  const bool small = b->bodies_bytes <= kSmallBatchBytes;
+  if (small) {  // one upload on the compute stream (see kSmallBatchBytes)
+    memcpy(h + total, b->bodies, b->bodies_bytes);
+    CK(cudaMemcpyAsync(sl.d_resp_meta, h, total + b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(sl.resp_copied, ctx->stream));
+  } else {
+    CK(cudaStreamWaitEvent(ctx->h2d, sl.resp_ran, 0));
+    CK(cudaMemcpyAsync(sl.d_resp_bodies, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->h2d));
+    CK(cudaMemcpyAsync(sl.d_resp_meta, h, total, cudaMemcpyHostToDevice, ctx->h2d));
+    CK(cudaEventRecord(sl.resp_copied, ctx->h2d));
+  }
   RespDev& r = sl.rp;
-  r.bodies = sl.d_resp_bodies;
+  r.bodies = small ? sl.d_resp_meta + total : sl.d_resp_bodies;
   r.body_off = (const uint32_t*)(sl.d_resp_meta + o_off);
   r.body_len = (const uint32_t*)(sl.d_resp_meta + o_len);
   r.qos = (const int32_t*)(sl.d_resp_meta + o_qos);
