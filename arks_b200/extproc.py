@@ -186,13 +186,45 @@ class Batcher:
 # --------------------------------------------------------------------------------------------------
 # the ext_proc server
 # --------------------------------------------------------------------------------------------------
+class CompiledBatcher:
+    """The same interface as Batcher, served by the compiled micro-batcher (host/cpp arks_host::Batcher through
+    arks_b200/cpphost.py): gRPC handler threads block inside C++ (ctypes releases the GIL) and are batched there."""
+
+    def __init__(self, cpp_batcher, clock=time.time):
+        self.b = cpp_batcher
+        self._clock = clock
+        self.b.set_fixed_clock(int(clock()))
+
+    @property
+    def clock(self):
+        return self._clock
+
+    @clock.setter
+    def clock(self, fn):  # the loopback tests move time; a production server leaves the C++ default (time(NULL))
+        self._clock = fn
+        self.b.set_fixed_clock(int(fn()))
+
+    def request(self, body: bytes, token: bytes):
+        d = self.b.request(token, body, 0)
+        return {"reason": d.reason, "detail": d.detail, "flags": d.flags, "qos": d.qos, "token": d.token, "pick": d.pick,
+                "cur_usage": d.cur_usage, "limit_max": d.limit_max}
+
+    def response(self, body: bytes, qos: int, flags: int):
+        d = self.b.response(qos, body, flags)
+        return {"reason": d.reason, "counted": d.counted, "usage": list(d.usage)}
+
+    def close(self):
+        self.b.close()
+
+
 class ExtProcServer:
-    def __init__(self, engine, tables, extract_bearer, max_wait_s=200e-6, clock=time.time):
+    def __init__(self, engine, tables, extract_bearer, max_wait_s=200e-6, clock=time.time, batcher=None):
         """engine: handle_request_body / handle_response_body; tables: arks_b200.tables.Tables (names for the routing
-        headers); extract_bearer: HandleRequestHeaders' scan (the C ABI's host function)."""
+        headers); extract_bearer: HandleRequestHeaders' scan (the C ABI's host function); batcher: a CompiledBatcher to
+        batch in C++ instead of the Python twin."""
         self.tables = tables
         self.extract_bearer = extract_bearer
-        self.batcher = Batcher(engine, max_wait_s=max_wait_s, clock=clock)
+        self.batcher = batcher or Batcher(engine, max_wait_s=max_wait_s, clock=clock)
 
     # ---- Server.Process, gateway.go:77-138
     def Process(self, request_iterator, context):

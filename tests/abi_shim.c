@@ -29,6 +29,7 @@ int arks_shim_create(const arks_tables* t, arks_ctx** out) {
   *out = c;
   return 0;
 }
+void* arks_shim_oracle(arks_ctx* c) { return c->o; } /* for snapshots in tests */
 void arks_shim_destroy(arks_ctx* c) {
   if (!c) return;
   ork_destroy(c->o);

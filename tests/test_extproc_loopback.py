@@ -63,10 +63,11 @@ def set_headers(mut):
     return {o.header.key: (o.header.raw_value or o.header.value.encode()).decode() for o in mut.set_headers}
 
 
-def run_loopback(engine, tables):
+def run_loopback(engine, tables, make_batcher=None):
     import __graft_entry__ as ge
     ge.build()  # arks_extract_bearer lives in the C ABI (pure host function)
-    srv = extproc.ExtProcServer(engine, tables, gateway.extract_bearer, clock=lambda: NOW)
+    srv = extproc.ExtProcServer(engine, tables, gateway.extract_bearer, clock=lambda: NOW,
+                                batcher=make_batcher(lambda: NOW) if make_batcher else None)
     server, port = extproc.serve(srv, port=0)
     ch, stub = extproc.client_stub(port)
     try:
@@ -125,6 +126,48 @@ def run_loopback(engine, tables):
 def test_loopback_plumbing_cpu_oracle_engine():
     t = Tables(FX["tokens"], FX["quotas"], FX["endpoints"])
     run_loopback(OracleEngine(t), t)
+
+
+class ShimEngine:
+    """snapshots of the oracle that sits behind the ABI shim (tests/abi_shim.c) the compiled batcher is linked against"""
+
+    def __init__(self, cpu):
+        import ctypes as C
+        self.cpu, self.C = cpu, C
+        cpu.shim.arks_shim_oracle.restype = C.c_void_p
+        cpu.shim.arks_shim_oracle.argtypes = [C.c_void_p]
+        self.o = orklib.Oracle.__new__(orklib.Oracle)
+        self.o.tables, self.o.h = cpu.tables, cpu.shim.arks_shim_oracle(cpu.ctx)
+
+    def snapshot_rate(self, now):
+        return orklib.Oracle.snapshot_rate(self.o, now)
+
+    def snapshot_quota(self):
+        return orklib.Oracle.snapshot_quota(self.o)
+
+
+def test_loopback_through_the_compiled_batcher_cpu():
+    """the same gRPC loopback, batched by host/cpp's Batcher (linked against the oracle-backed ABI shim)"""
+    from test_cpp_host import CpuEngine
+    from arks_b200 import cpphost
+    t = Tables(FX["tokens"], FX["quotas"], FX["endpoints"])
+    cpu = CpuEngine(t, max_batch=256, max_bytes=1 << 20)
+    cpu.tables = t
+    eng = ShimEngine(cpu)
+    try:
+        run_loopback(eng, t, make_batcher=lambda clock: extproc.CompiledBatcher(cpu.b, clock))
+    finally:
+        eng.o.h = None  # the shim owns the oracle
+
+
+@pytest.mark.gpu
+def test_loopback_gpu_compiled_batcher():
+    from arks_b200 import cpphost
+    t = Tables(FX["tokens"], FX["quotas"], FX["endpoints"])
+    g = gateway.Gateway(0, 4096, 8 << 20)
+    g.load_tables(t)
+    hb = cpphost.Batcher(cpphost.load(cpphost.build()), g._h, max_batch=256, max_bytes=1 << 20)
+    run_loopback(g, t, make_batcher=lambda clock: extproc.CompiledBatcher(hb, clock))
 
 
 @pytest.mark.gpu
