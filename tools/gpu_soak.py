@@ -13,7 +13,7 @@ from arks_b200 import abi, traffic
 from arks_b200.abi import RequestBatch, ResponseBatch
 from arks_b200.gateway import Gateway
 import re
-D2 = re.compile(rb"(?<![0-9.eE+\-])-?0[0-9]")  # D2 of DESIGN.md §4: leading-zero numbers are out of the pinned domain
+D2 = re.compile(rb"[0-9.]{17,}|[eE][+-]?[0-9]{2,}")  # D2 of DESIGN.md §4: very long / large-exponent numbers are outside the pinned domain
 
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
