@@ -124,4 +124,45 @@ int hm_parse_sse_split(const uint8_t* body, size_t len, int64_t usage[3]) {
   if (fail) usage[0] = usage[1] = usage[2] = 0;
   return fail ? 1 : 0;
 }
+// Work profile of one document for the lock-step analysis (tools/lockstep_model.py): for every 128-byte window the number
+// of advances the schedules need (one bulk skip and / or one table step each) and the number of events among them.
+int hm_work_profile(int kind, const uint8_t* body, size_t len, uint32_t* advances, uint32_t* events, size_t max_windows) {
+  static thread_local JsonT m;
+  static thread_local uint32_t stk[kStackWords];
+  static thread_local JsonCold cold;
+  m.init(kind == 0 ? K_REQ : K_RESP, body, stk, &cold, host_json_tables());
+  size_t n_win = (len + 127) / 128;
+  if (n_win > max_windows) return -1;
+  for (size_t w = 0; w < n_win; w++) advances[w] = events[w] = 0;
+  uint32_t pos = 0;
+  while (pos < len && !m.dead()) {
+    const size_t w = pos >> 7;
+    const uint32_t lim = (uint32_t)(len < (w + 1) * 128 ? len : (w + 1) * 128);
+    const uint32_t ub = pos & ~15u;
+    uint8_t tmp[16] = {0};
+    memcpy(tmp, body + ub, len - ub < 16 ? len - ub : 16);
+    uint32_t q[4];
+    memcpy(q, tmp, 16);
+    uint32_t o = pos & 15;
+    advances[w]++;
+    bool more = true;
+    if (m.can_fast()) {
+      const uint32_t rest = special_mask16(q[0], q[1], q[2], q[3]) >> o;
+      uint32_t run = rest ? first_set(rest) : 16u - o;
+      if (run > lim - pos) run = lim - pos;
+      if (run) { m.skip(run, o, q[0], q[1], q[2], q[3]); pos += run; o += run; }
+      more = o < 16 && pos < lim;
+    }
+    if (more) {
+      const uint8_t c = body[pos];
+      const uint32_t before = m.ss;
+      const uint32_t t = m.tab[m.ss * kJsonClasses + m.cls[c]];
+      if (t >= EV_BASE) events[w]++;
+      (void)before;
+      m.step(c, pos);
+      pos++;
+    }
+  }
+  return (int)n_win;
+}
 }

@@ -25,6 +25,7 @@ def lib():
         L.hm_parse_response.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), i64p]
         L.hm_parse_sse.argtypes = [C.c_char_p, C.c_size_t, i64p]
         L.hm_parse_sse_split.argtypes = [C.c_char_p, C.c_size_t, i64p]
+        L.hm_work_profile.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t]
         _lib = L
     return _lib
 
@@ -59,3 +60,14 @@ def parse_sse_chunk_split(body: bytes):
 def set_evsync(mode):
     """schedule for JsonT documents: 0 / False consume_t, 1 / True consume_evsync, 4 or 8 consume_rounds<R>"""
     lib().hm_set_evsync(int(mode))
+
+
+def work_profile(body: bytes, kind: int = 0):
+    """(advances, events) per 128-byte window of one request (kind 0) / response (kind 1) body, as the schedules count them"""
+    n = (len(body) + 127) // 128
+    a = np.zeros(max(n, 1), np.uint32)
+    e = np.zeros(max(n, 1), np.uint32)
+    u32p = C.POINTER(C.c_uint32)
+    rc = lib().hm_work_profile(kind, body, len(body), a.ctypes.data_as(u32p), e.ctypes.data_as(u32p), len(a))
+    assert rc >= 0
+    return a[:n], e[:n]
