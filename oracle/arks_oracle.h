@@ -52,6 +52,11 @@ int ork_parse_request_body(const uint8_t* body, size_t len, uint8_t* model_out, 
 int ork_parse_response_body(const uint8_t* body, size_t len, size_t* model_len, int64_t usage[3]);
 /* one SSE chunk (handle_response.go:113-133): 0 ok, 1 stream error. usage[3] as above (zeros if none) */
 int ork_parse_sse_chunk(const uint8_t* body, size_t len, int64_t usage[3]);
+/* the events eventStreamDecoder.Next dispatches for one chunk, serialised as {u32 type_len, u32 data_len,
+ * u32 n_data_lines, type, data} records (data carries the '\n' the decoder appends per data line). Returns the event
+ * count, -1 on a scanner error, -2 if `out` is too small. Pinned against openai-python's SSEDecoder (same Stainless
+ * decoder family as openai-go's ssestream) in tests/test_decoder_pins.py. */
+int ork_sse_events(const uint8_t* body, size_t len, uint8_t* out, size_t cap, size_t* used);
 /* getWindowStart, ratelimiter/cache_key.go:73-80 */
 int64_t ork_window_start(int64_t now_unix, int rule);
 /* CacheKeyGenerator.Generate, ratelimiter/cache_key.go:42-71 and quota/cache_key.go:40-58. Return length. */

@@ -948,14 +948,18 @@ static int sse_event(const uint8_t* type, size_t type_len, const uint8_t* data, 
   return 0;
 }
 
-/* eventStreamDecoder.Next over bufio.Scanner(ScanLines) (ssestream.go); 64 KiB line limit */
-int ork_sse_chunk(const uint8_t* body, size_t len, int64_t usage[3]) {
-  usage[0] = usage[1] = usage[2] = 0;
+/* eventStreamDecoder.Next over bufio.Scanner(ScanLines) (ssestream.go); 64 KiB line limit.
+ * on_event(ctx, type, type_len, data, data_len, n_data_lines) is called for every dispatched event, in order;
+ * a non-zero return stops the scan with rc 1. */
+typedef int (*sse_event_fn)(void* ctx, const uint8_t* type, size_t type_len, const uint8_t* data, size_t data_len,
+                            uint32_t n_data_lines);
+static int sse_scan(const uint8_t* body, size_t len, sse_event_fn on_event, void* ctx) {
   uint8_t* data = (uint8_t*)malloc(len + 16 + len / 2);
   size_t data_len = 0;
+  uint32_t n_lines = 0;
   const uint8_t* ev = NULL;
   size_t ev_len = 0;
-  int done = 0, rc = 0;
+  int rc = 0;
   size_t pos = 0;
   while (pos < len) {
     size_t e = pos;
@@ -972,11 +976,12 @@ int ork_sse_chunk(const uint8_t* body, size_t len, int64_t usage[3]) {
     if (n == 0) {
       if (e >= len && line_len == 0) break; /* no trailing empty token at EOF */
       /* dispatch */
-      if (sse_event(ev, ev_len, data, data_len, &done, usage)) {
+      if (on_event(ctx, ev, ev_len, data, data_len, n_lines)) {
         rc = 1;
         break;
       }
       data_len = 0;
+      n_lines = 0;
       ev = NULL;
       ev_len = 0;
       continue;
@@ -997,8 +1002,56 @@ int ork_sse_chunk(const uint8_t* body, size_t len, int64_t usage[3]) {
       memcpy(data + data_len, val, vlen);
       data_len += vlen;
       data[data_len++] = '\n';
+      n_lines++;
     }
   }
   free(data);
   return rc;
+}
+
+struct sse_usage_ctx {
+  int done;
+  int64_t* usage;
+};
+static int sse_usage_event(void* ctx, const uint8_t* type, size_t type_len, const uint8_t* data, size_t data_len,
+                           uint32_t n_lines) {
+  struct sse_usage_ctx* c = (struct sse_usage_ctx*)ctx;
+  (void)n_lines;
+  return sse_event(type, type_len, data, data_len, &c->done, c->usage);
+}
+int ork_sse_chunk(const uint8_t* body, size_t len, int64_t usage[3]) {
+  usage[0] = usage[1] = usage[2] = 0;
+  struct sse_usage_ctx c = {0, usage};
+  return sse_scan(body, len, sse_usage_event, &c);
+}
+
+/* test hook (tests/test_decoder_pins.py): the events the decoder dispatches for a chunk, serialised into `out` as
+ * records {u32 type_len, u32 data_len, u32 n_data_lines, type bytes, data bytes}. Returns the number of events, or
+ * -1 on a scanner error (line too long), -2 when `out` is too small. */
+struct sse_dump_ctx {
+  uint8_t* out;
+  size_t cap, used;
+  int n, overflow;
+};
+static int sse_dump_event(void* ctx, const uint8_t* type, size_t type_len, const uint8_t* data, size_t data_len,
+                          uint32_t n_lines) {
+  struct sse_dump_ctx* c = (struct sse_dump_ctx*)ctx;
+  if (c->used + 12 + type_len + data_len > c->cap) {
+    c->overflow = 1;
+    return 1;
+  }
+  uint32_t h[3] = {(uint32_t)type_len, (uint32_t)data_len, n_lines};
+  memcpy(c->out + c->used, h, 12);
+  if (type_len) memcpy(c->out + c->used + 12, type, type_len);
+  if (data_len) memcpy(c->out + c->used + 12 + type_len, data, data_len);
+  c->used += 12 + type_len + data_len;
+  c->n++;
+  return 0;
+}
+int ork_sse_events(const uint8_t* body, size_t len, uint8_t* out, size_t cap, size_t* used) {
+  struct sse_dump_ctx c = {out, cap, 0, 0, 0};
+  int rc = sse_scan(body, len, sse_dump_event, &c);
+  if (used) *used = c.used;
+  if (c.overflow) return -2;
+  return rc ? -1 : c.n;
 }

@@ -60,6 +60,7 @@ def lib():
                                              C.POINTER(C.c_int)]
         L.ork_parse_response_body.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), abi.i64p]
         L.ork_parse_sse_chunk.argtypes = [C.c_char_p, C.c_size_t, abi.i64p]
+        L.ork_sse_events.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ork_window_start.restype = C.c_int64
         L.ork_window_start.argtypes = [C.c_int64, C.c_int]
         L.ork_rate_key.restype = C.c_size_t
@@ -173,6 +174,21 @@ def parse_sse_chunk(body: bytes):
     u = np.zeros(3, np.int64)
     rc = lib().ork_parse_sse_chunk(body, len(body), abi.ptr(u, abi.i64p))
     return rc, tuple(int(x) for x in u)
+
+
+def sse_events(body: bytes):
+    """-> (n or negative error, [(type bytes, data bytes, n_data_lines)]) as the oracle's decoder dispatches them"""
+    import struct
+    cap = 64 + 16 * len(body) + 2 * len(body)
+    buf = C.create_string_buffer(cap)
+    used = C.c_size_t()
+    n = lib().ork_sse_events(body, len(body), buf, cap, C.byref(used))
+    out, p, raw = [], 0, buf.raw[:used.value]
+    while p < len(raw):
+        tl, dl, nl = struct.unpack_from("<III", raw, p)
+        out.append((raw[p + 12:p + 12 + tl], raw[p + 12 + tl:p + 12 + tl + dl], nl))
+        p += 12 + tl + dl
+    return n, out
 
 
 def window_start(now, rule):

@@ -1,0 +1,184 @@
+"""Pins the decoders on the valid-input subset against parsers that are not ours.
+
+The reference decodes with json-iterator, openai-go ssestream/apijson/gjson and encoding/json, none of which can run here
+(no Go toolchain). `oracle/ork_json.c` restates them; `json_engine.cuh` is a second formulation. Both were only checked
+against each other. Here they are checked against Python's `json` and openai-python's `SSEDecoder` (tests/pymodel.py
+states the Go struct-binding rules on top of those parsers), on committed vectors (tests/golden/decoder_vectors.json,
+regenerate with tests/golden/make_decoder_vectors.py) and on fresh seeded documents:
+
+  * every RFC-8259-valid request / response document: same error verdict, model, stream / include_usage tri-states,
+    usage integers as json.loads + the binding rules give;
+  * every LF / CRLF chunk: same event split as SSEDecoder, same (error, usage) verdict;
+  * CPU: the oracle; `-m gpu`: the CUDA path through the C ABI.
+"""
+import base64
+import json
+import os
+
+import numpy as np
+import pytest
+
+import orklib
+import pymodel
+from jsonfuzz import Gen
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "decoder_vectors.json")
+NOW = 1_700_000_000
+
+
+@pytest.fixture(scope="module")
+def vec():
+    v = json.load(open(GOLD))
+    for k in ("request", "response", "sse", "sse_split"):
+        for e in v[k]:
+            e["doc"] = base64.b64decode(e["doc"])
+            if "model" in e:
+                e["model"] = base64.b64decode(e["model"])
+    return v
+
+
+def check_request(doc, want):
+    rc, model, st, so, iu = orklib.parse_request_body(doc)
+    assert rc == want["err"], (doc, rc, want)
+    if not rc:
+        assert (model, st, so, iu) == (want["model"], want["stream"], want["so_present"], want["include_usage"]), (doc, want)
+
+
+def check_response(doc, want):
+    rc, ml, usage = orklib.parse_response_body(doc)
+    assert rc == want["err"], (doc, rc, want)
+    if not rc:
+        assert (ml, list(usage)) == (want["model_len"], list(want["usage"])), (doc, ml, usage, want)
+
+
+def check_sse(doc, want):
+    rc, usage = orklib.parse_sse_chunk(doc)
+    assert rc == want["err"], (doc, rc, want)
+    if not rc:
+        assert list(usage) == list(want["usage"]), (doc, usage, want)
+
+
+def check_split(doc, events):
+    n, got = orklib.sse_events(doc)
+    assert n >= 0, doc
+    # openai-go appends '\n' after every data line, openai-python joins the lines with '\n': same bytes up to that newline
+    norm = [[t.decode(), (d[:-1] if nl else d).decode()] for t, d, nl in got]
+    assert norm == [list(e) for e in events], (doc, norm, events)
+
+
+def test_vectors_cover_the_cases(vec):
+    st = vec["_stats"]
+    for k in ("request", "response", "sse"):
+        assert st[k]["kept"] >= 500 and st[k]["errors"] >= 20 and st[k]["kept"] * 4 >= st[k]["generated"]
+    assert any(e["stream"] == 2 and e["include_usage"] == 2 for e in vec["request"] if not e["err"])
+    assert any(e["usage"][2] > 0 for e in vec["response"] if not e["err"])
+    assert any(e["usage"][2] > 0 for e in vec["sse"] if not e["err"])
+    assert any(len(e["events"]) >= 3 for e in vec["sse_split"])
+
+
+def test_oracle_matches_golden_vectors(vec):
+    for e in vec["request"]:
+        check_request(e["doc"], e)
+    for e in vec["response"]:
+        check_response(e["doc"], e)
+    for e in vec["sse"]:
+        check_sse(e["doc"], e)
+    for e in vec["sse_split"]:
+        check_split(e["doc"], e["events"])
+
+
+def test_golden_vectors_are_what_the_independent_parsers_say(vec):
+    """the committed expectations are reproducible from json.loads / SSEDecoder in this image"""
+    pytest.importorskip("openai")
+    for e in vec["request"][::7]:
+        f = pymodel.request_fields(e["doc"])
+        assert f is not None and f["err"] == e["err"] and (f["err"] or f["model"] == e["model"])
+    for e in vec["sse_split"][::7]:
+        assert [list(x) for x in pymodel.sse_split(e["doc"])] == [list(x) for x in e["events"]]
+
+
+@pytest.mark.parametrize("seed", [71, 72, 73])
+def test_oracle_matches_independent_parsers_on_fresh_documents(seed):
+    pytest.importorskip("openai")
+    gen = Gen(seed)
+    took = [0, 0, 0, 0]
+    for _ in range(2500):
+        d = gen.request()
+        f = pymodel.request_fields(d)
+        if f is not None:
+            check_request(d, f); took[0] += 1
+        d = gen.response()
+        f = pymodel.response_fields(d)
+        if f is not None:
+            check_response(d, f); took[1] += 1
+        d = gen.sse_chunk()
+        f = pymodel.sse_fields(d)
+        if f is not None:
+            check_sse(d, f); took[2] += 1
+        ev = pymodel.sse_split(d)
+        if ev is not None:
+            check_split(d, ev); took[3] += 1
+    assert min(took) >= 300, took  # the subset is not a corner: 15-30 % of the (mostly hostile) fuzzed documents take part
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_golden_vectors(vec, gwmod):
+    """the device machines against json.loads / SSEDecoder directly (not via the oracle)"""
+    from arks_b200 import abi, traffic
+    from arks_b200.abi import RequestBatch, ResponseBatch
+    w = traffic.Workload(n_tenants=4, seed=1)
+    g = gwmod.Gateway(0, 4096, 16 << 20)
+    g.load_tables(w.tables)
+    # requests: the error verdict and, through the model / stream checks, the extracted fields
+    reqs = vec["request"]
+    r = g.handle_request_body(RequestBatch.from_lists([e["doc"] for e in reqs], [w.token_strings[0]] * len(reqs), NOW))
+    for i, e in enumerate(reqs):
+        if e["err"]:
+            want = abi.R_REQUEST_BODY
+        elif e["model"] == b"":
+            want = abi.R_NO_MODEL
+        elif e["model"] != traffic.MODEL.encode():
+            want = abi.R_MODEL_NOT_IN_TOKEN
+        elif e["stream"] == 2 and not (e["so_present"] and e["include_usage"] == 2):
+            want = abi.R_STREAM_OPTIONS
+        else:
+            want = None  # reached the limiter: OK / RATE_LIMIT / QUOTA
+        if want is None:
+            assert r.reason[i] in (abi.R_OK, abi.R_RATE_LIMIT, abi.R_QUOTA), (e["doc"], r.reason[i])
+            if r.reason[i] == abi.R_OK:
+                assert (r.flags[i] & 1) == (e["stream"] == 2)
+        else:
+            assert r.reason[i] == want, (e["doc"], r.reason[i], want)
+    # responses and SSE chunks: verdict + usage integers
+    for kind, flag, bad in (("response", abi.RESP_END_OF_STREAM, abi.R_RESPONSE_UNMARSHAL), ("sse", abi.RESP_STREAM, abi.R_STREAMING)):
+        es = vec[kind]
+        c = g.handle_response_body(ResponseBatch.from_lists([e["doc"] for e in es], [0] * len(es), [flag] * len(es), NOW + 1))
+        for i, e in enumerate(es):
+            if e["err"]:
+                assert c.reason[i] == bad, (e["doc"], c.reason[i])
+            elif kind == "response" and e["model_len"] == 0:
+                assert c.reason[i] == abi.R_RESPONSE_UNKNOWN, (e["doc"], c.reason[i])
+            else:
+                assert c.reason[i] in (abi.R_OK, abi.R_QUOTA_CONFIG_RESP) and c.usage[i].tolist() == list(e["usage"]), (e["doc"], c.usage[i])
+
+
+def test_device_engine_host_build_matches_golden_vectors(vec):
+    """json_engine.cuh compiled for the host (tests/host_machine.cpp): the device formulation against the same
+    independent expectations, on CPU"""
+    import hostmachine as hm
+    for e in vec["request"]:
+        rc, model, st, so, iu = hm.parse_request_body(e["doc"])
+        assert rc == e["err"], (e["doc"], rc)
+        if not rc:
+            assert (model, st, so, iu) == (e["model"], e["stream"], e["so_present"], e["include_usage"]), e["doc"]
+    for e in vec["response"]:
+        rc, ml, usage = hm.parse_response_body(e["doc"])
+        assert rc == e["err"], (e["doc"], rc)
+        if not rc:
+            assert (ml > 0, list(usage)) == (e["model_len"] > 0, list(e["usage"])), e["doc"]
+    for e in vec["sse"]:
+        for fn in (hm.parse_sse_chunk, lambda b: hm.parse_sse_chunk_split(b)[:2]):
+            rc, usage = fn(e["doc"])
+            assert rc == e["err"], (e["doc"], rc)
+            if not rc:
+                assert list(usage) == list(e["usage"]), e["doc"]
