@@ -19,7 +19,7 @@ QUOTA_NONE, QUOTA_MISSING = -1, -2
 # enum arks_reason
 (R_OK, R_NO_TOKEN, R_REQUEST_BODY, R_NO_MODEL, R_TOKEN_NOT_FOUND, R_MODEL_NOT_IN_TOKEN, R_NO_MODEL_BACKENDS,
  R_STREAM_OPTIONS, R_RATE_LIMIT, R_QUOTA, R_QUOTA_CONFIG, R_STREAMING, R_RESPONSE_UNMARSHAL, R_RESPONSE_UNKNOWN,
- R_QUOTA_CONFIG_RESP, R_PENDING) = range(16)
+ R_QUOTA_CONFIG_RESP, R_PENDING, R_QOS_GONE) = range(17)
 
 # (http status, x-error-* header) per reason — pkg/gateway/types.go:24-56 and the status map of SURVEY.md §8a
 REASON_HTTP = {
@@ -39,6 +39,7 @@ REASON_HTTP = {
     R_RESPONSE_UNKNOWN: (500, "x-error-response-unknown"),
     R_QUOTA_CONFIG_RESP: (500, "x-error-quota"),
     R_PENDING: (200, None),
+    R_QOS_GONE: (200, None),  # nothing billed; the stream continues (include/arks_gateway.h)
 }
 
 RESP_STREAM, RESP_END_OF_STREAM, RESP_COMPLETED = 1, 2, 4
@@ -72,12 +73,12 @@ class ArksRequestBatch(C.Structure):
 
 class ArksRequestResult(C.Structure):
     _fields_ = [("reason", u8p), ("detail", u8p), ("flags", u8p), ("qos", i32p), ("token", i32p), ("pick", i32p),
-                ("cur_usage", i64p), ("limit_max", i64p)]
+                ("cur_usage", i64p), ("limit_max", i64p), ("model_off", u32p), ("model_len", u32p), ("bpe_count", u32p)]
 
 
 class ArksResponseBatch(C.Structure):
     _fields_ = [("n", C.c_uint32), ("bodies", u8p), ("body_off", u32p), ("body_len", u32p),
-                ("bodies_bytes", C.c_uint64), ("qos", i32p), ("flags", u8p), ("now_unix", C.c_int64)]
+                ("bodies_bytes", C.c_uint64), ("qos", i32p), ("flags", u8p), ("now_unix", C.c_int64), ("gen", u32p)]
 
 
 class ArksResponseResult(C.Structure):
@@ -157,20 +158,31 @@ class RequestResult:
     pick: np.ndarray
     cur_usage: np.ndarray
     limit_max: np.ndarray
+    model_off: np.ndarray = None
+    model_len: np.ndarray = None
+    bpe_count: np.ndarray = None
 
     @classmethod
     def empty(cls, n):
         return cls(np.full(n, 255, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.full(n, -9, np.int32),
-                   np.full(n, -9, np.int32), np.full(n, -9, np.int32), np.zeros(n, np.int64), np.zeros(n, np.int64))
+                   np.full(n, -9, np.int32), np.full(n, -9, np.int32), np.zeros(n, np.int64), np.zeros(n, np.int64),
+                   np.full(n, 0xEEEEEEEE, np.uint32), np.full(n, 0xEEEEEEEE, np.uint32), np.full(n, 0xEEEEEEEE, np.uint32))
 
     def c_struct(self) -> ArksRequestResult:
         return ArksRequestResult(ptr(self.reason, u8p), ptr(self.detail, u8p), ptr(self.flags, u8p),
                                  ptr(self.qos, i32p), ptr(self.token, i32p), ptr(self.pick, i32p),
-                                 ptr(self.cur_usage, i64p), ptr(self.limit_max, i64p))
+                                 ptr(self.cur_usage, i64p), ptr(self.limit_max, i64p), ptr(self.model_off, u32p),
+                                 ptr(self.model_len, u32p), ptr(self.bpe_count, u32p))
 
     def fields(self):
+        """the arrays the reference's decision determines (bpe_count has its own oracle: tests/test_bpe.py)"""
         return {k: getattr(self, k) for k in
-                ("reason", "detail", "flags", "qos", "token", "pick", "cur_usage", "limit_max")}
+                ("reason", "detail", "flags", "qos", "token", "pick", "cur_usage", "limit_max", "model_off", "model_len")}
+
+    def model_bytes(self, batch, i: int) -> bytes:
+        """raw bytes of request i's `model` string inside its body (escapes not decoded)"""
+        o = int(batch.body_off[i]) + int(self.model_off[i])
+        return bytes(batch.bodies[o:o + (int(self.model_len[i]) & 0x7FFFFFFF)])
 
 
 @dataclass
@@ -181,20 +193,22 @@ class ResponseBatch:
     qos: np.ndarray
     flags: np.ndarray
     now_unix: int
+    gen: np.ndarray | None = None  # table generation of each row's request (None: the current one)
 
     @property
     def n(self) -> int:
         return int(self.body_len.shape[0])
 
     @classmethod
-    def from_lists(cls, bodies, qos, flags, now_unix):
+    def from_lists(cls, bodies, qos, flags, now_unix, gen=None):
         bb, bo, bl = pack_blobs(bodies)
         return cls(bb, bo, bl, np.ascontiguousarray(qos, dtype=np.int32), np.ascontiguousarray(flags, dtype=np.uint8),
-                   int(now_unix))
+                   int(now_unix), None if gen is None else np.ascontiguousarray(gen, dtype=np.uint32))
 
     def c_struct(self) -> ArksResponseBatch:
         return ArksResponseBatch(self.n, ptr(self.bodies, u8p), ptr(self.body_off, u32p), ptr(self.body_len, u32p),
-                                 int(self.bodies.shape[0]), ptr(self.qos, i32p), ptr(self.flags, u8p), self.now_unix)
+                                 int(self.bodies.shape[0]), ptr(self.qos, i32p), ptr(self.flags, u8p), self.now_unix,
+                                 ptr(self.gen, u32p))
 
 
 @dataclass

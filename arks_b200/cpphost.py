@@ -19,7 +19,8 @@ LIB = os.path.join(ROOT, "host", "cpp", "libarkshost.so")
 class RequestDecision(C.Structure):
     _fields_ = [("reason", C.c_uint8), ("detail", C.c_uint8), ("flags", C.c_uint8), ("qos", C.c_int32), ("token", C.c_int32),
                 ("pick", C.c_int32), ("cur_usage", C.c_int64), ("limit_max", C.c_int64), ("cycle", C.c_uint64),
-                ("index", C.c_uint32), ("now_unix", C.c_int64)]
+                ("index", C.c_uint32), ("now_unix", C.c_int64), ("gen", C.c_uint32), ("model_off", C.c_uint32),
+                ("model_len", C.c_uint32), ("bpe_count", C.c_uint32)]
 
 
 class ResponseDecision(C.Structure):
@@ -36,7 +37,8 @@ REQ_DTYPE = np.dtype(RequestDecision)
 RESP_DTYPE = np.dtype(ResponseDecision)
 EXPORTED = ["arks_host_create", "arks_host_destroy", "arks_host_set_fixed_clock", "arks_host_request", "arks_host_response",
             "arks_host_stats", "arks_host_run_requests", "arks_host_run_responses", "arks_host_open_loop_requests",
-            "arks_host_stream_transcript"]
+            "arks_host_stream_transcript", "arks_host_load_tables", "arks_host_set_names", "arks_host_request_error_reply",
+            "arks_host_response_error_reply"]
 
 
 def build(out: str = LIB, against: str = None, force: bool = False) -> str:
@@ -62,17 +64,23 @@ def load(path: str = LIB):
     L.arks_host_set_fixed_clock.argtypes = [vp, C.c_int64]
     L.arks_host_set_fixed_clock.restype = None
     L.arks_host_request.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint64, C.POINTER(RequestDecision)]
-    L.arks_host_response.argtypes = [vp, C.c_int32, C.c_char_p, C.c_uint32, C.c_uint8, C.POINTER(ResponseDecision)]
+    L.arks_host_response.argtypes = [vp, C.c_int32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint8, C.POINTER(ResponseDecision)]
+    L.arks_host_load_tables.argtypes = [vp, vp]
+    L.arks_host_set_names.argtypes = [vp, C.c_char_p, C.c_uint32]
+    L.arks_host_request_error_reply.argtypes = [vp, C.POINTER(RequestDecision), C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32,
+                                                C.c_char_p, C.c_uint32]
+    L.arks_host_response_error_reply.argtypes = [vp, C.POINTER(ResponseDecision), C.c_int32, C.c_char_p, C.c_uint32, C.c_char_p,
+                                                 C.c_uint32]
     L.arks_host_stats.argtypes = [vp, C.POINTER(BatcherStats)]
     L.arks_host_stats.restype = None
     L.arks_host_run_requests.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.arks_host_run_requests.restype = C.c_int64
-    L.arks_host_run_responses.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
+    L.arks_host_run_responses.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.arks_host_run_responses.restype = C.c_int64
     L.arks_host_open_loop_requests.argtypes = [vp, C.c_uint32, C.c_double, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.arks_host_open_loop_requests.restype = C.c_int64
     cpp = C.POINTER(C.c_char_p)
-    L.arks_host_stream_transcript.argtypes = [vp, cpp, C.c_uint32, cpp, cpp, C.c_uint32, cpp, cpp, C.c_uint32, C.c_char_p,
+    L.arks_host_stream_transcript.argtypes = [vp, cpp, cpp, C.c_uint32, C.c_char_p,
                                               C.c_uint32, cpp, cpp, C.c_uint32, C.POINTER(C.c_char_p), u32p, C.c_uint32,
                                               C.c_uint64, C.c_char_p, C.c_uint32]
     return L
@@ -106,10 +114,39 @@ class Batcher:
         self.L.arks_host_request(self._h, token, len(token), body, len(body), pick_rand, C.byref(d))
         return d
 
-    def response(self, qos: int, body: bytes, flags: int) -> ResponseDecision:
+    def response(self, qos: int, body: bytes, flags: int, gen: int = None) -> ResponseDecision:
+        """`gen`: RequestDecision.gen of the stream's request; None = the tables have not changed since"""
         d = ResponseDecision()
-        self.L.arks_host_response(self._h, qos, body, len(body), flags, C.byref(d))
+        self.L.arks_host_response(self._h, qos, 0xFFFFFFFF if gen is None else gen, body, len(body), flags, C.byref(d))
         return d
+
+    def load_tables(self, tables):
+        """config reload between two cycles (Batcher::LoadTables); also refreshes the reply-shaping names"""
+        ts = tables.c_struct()
+        rc = self.L.arks_host_load_tables(self._h, C.byref(ts))
+        if rc:
+            raise RuntimeError(f"arks_host_load_tables: {rc}")
+        self.set_names(tables)
+
+    def set_names(self, tables):
+        blob = tables.names_blob()
+        if self.L.arks_host_set_names(self._h, blob, len(blob)):
+            raise RuntimeError("arks_host_set_names: malformed name table")
+
+    def _reply(self, n, buf):
+        if n < 0:
+            raise RuntimeError("reply buffer too small")
+        status, header, value, message = buf.raw[:n].decode("utf-8", "surrogateescape").split("\n", 3)
+        return int(status), header, value, message
+
+    def request_error_reply(self, d: RequestDecision, token: bytes, body: bytes):
+        """(status, x-error header, header value, error message) the reference sends for a failed request decision"""
+        buf = C.create_string_buffer(len(body) + len(token) + 4096)
+        return self._reply(self.L.arks_host_request_error_reply(self._h, C.byref(d), token, len(token), body, len(body), buf, len(buf)), buf)
+
+    def response_error_reply(self, d: ResponseDecision, qos: int, chunk: bytes):
+        buf = C.create_string_buffer(len(chunk) + 4096)
+        return self._reply(self.L.arks_host_response_error_reply(self._h, C.byref(d), qos, chunk, len(chunk), buf, len(buf)), buf)
 
     def stats(self) -> dict:
         s = BatcherStats()
@@ -142,17 +179,16 @@ class Batcher:
         lat = np.zeros(batch.n, np.int64)
         bodies = np.ascontiguousarray(batch.bodies)
         ns = self.L.arks_host_run_responses(self._h, batch.n, threads, _ptr(bodies), _ptr(batch.body_off), _ptr(batch.body_len),
-                                            _ptr(batch.qos), _ptr(batch.flags), _ptr(out), _ptr(lat))
+                                            _ptr(batch.qos), _ptr(getattr(batch, "gen", None)), _ptr(batch.flags), _ptr(out), _ptr(lat))
         return out, lat, ns * 1e-9
 
-    def stream_transcript(self, names, req_headers, req_body: bytes, resp_headers, resp_chunks, pick_rand: int = 0) -> str:
-        """drive one ext_proc stream through arks_host::StreamProcessor; `names` = (qos_model, token_namespace, token_user)"""
+    def stream_transcript(self, req_headers, req_body: bytes, resp_headers, resp_chunks, pick_rand: int = 0) -> str:
+        """drive one ext_proc stream through arks_host::StreamProcessor (names: set_names / load_tables)"""
         def arr(strs):
             a = (C.c_char_p * max(len(strs), 1))()
             for i, s in enumerate(strs):
                 a[i] = s if isinstance(s, bytes) else s.encode()
             return a
-        qm, tn, tu = names
         rk, rv = arr([k for k, _ in req_headers]), arr([v for _, v in req_headers])
         pk, pv = arr([k for k, _ in resp_headers]), arr([v for _, v in resp_headers])
         chunks = (C.c_char_p * max(len(resp_chunks), 1))()
@@ -160,7 +196,7 @@ class Batcher:
         for i, c in enumerate(resp_chunks):
             chunks[i], lens[i] = c, len(c)
         buf = C.create_string_buffer(1 << 20)
-        n = self.L.arks_host_stream_transcript(self._h, arr(qm), len(qm), arr(tn), arr(tu), len(tn), rk, rv, len(req_headers),
+        n = self.L.arks_host_stream_transcript(self._h, rk, rv, len(req_headers),
                                                req_body, len(req_body), pk, pv, len(resp_headers), chunks, lens,
                                                len(resp_chunks), pick_rand, buf, len(buf))
         if n < 0:

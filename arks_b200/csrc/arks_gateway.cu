@@ -29,6 +29,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <deque>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -114,6 +115,9 @@ struct ReqDev {  // request batch, device resident
   int32_t* pick;
   long long* cur_usage;
   long long* limit_max;
+  uint32_t* model_off;  // raw span of the model string inside the body (host-side error shaping)
+  uint32_t* model_len;  // bit 31: the span contains a backslash
+  uint32_t* bpe;        // BPE tokens of the prompt text (0 without a vocabulary)
 };
 
 struct RespDev {
@@ -489,6 +493,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_request_
     B.gnext[i] = atomicExch(&B.ghead[g], (int32_t)i);
     slot = (int32_t)g;
   } while (0);
+  const bool parsed = reason != ARKS_R_REQUEST_BODY;
+  B.model_off[i] = parsed && cold.m_rawlen ? cold.m_start : 0u;
+  B.model_len[i] = parsed && cold.m_rawlen ? (cold.m_rawlen | (cold.m_esc ? 0x80000000u : 0u)) : 0u;
+  B.bpe[i] = 0;
   B.st_reason[i] = reason;
   B.st_flags[i] = flags | (claimer << 7);
   B.st_qos[i] = qos;
@@ -722,7 +730,10 @@ __device__ __forceinline__ int token_bucket(long long v) {
 
 __device__ __forceinline__ void account_usage(const DevTables& T, const RespDev& B, uint32_t i, bool live, int32_t qos, const QosAcct& acct,
                                               uint8_t reason, uint8_t counted, long long u0, long long u1, long long u2) {
-  if (T.metrics && live) {  // N3: the series the reference updates per response-body message
+  if (live && qos < 0) {  // the row's qos entry does not exist in these tables: nothing to bill (ARKS_R_QOS_GONE)
+    reason = ARKS_R_QOS_GONE; counted = 0; u0 = u1 = u2 = 0;
+  }
+  if (T.metrics && live && qos >= 0) {  // N3: the series the reference updates per response-body message
     unsigned long long* row = reinterpret_cast<unsigned long long*>(T.metrics + (size_t)qos * ARKS_METRIC_COLS);
     const uint8_t fl = B.flags[i];
     atomicAdd(row + ARKS_METRIC_MESSAGES, 1ull);  // RecordRequest(..., "200"), gateway.go:129
@@ -779,14 +790,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response
     const uint8_t* body = B.bodies + (live ? B.body_off[i] : 0);
     const uint8_t fl = live ? B.flags[i] : ARKS_RESP_END_OF_STREAM;
     const bool pending = !(fl & ARKS_RESP_END_OF_STREAM);  // more of the body is still to come: handle_response.go:141-149
-    const uint32_t len = live && !pending ? B.body_len[i] : 0;
     qos = live ? B.qos[i] : 0;
+    const uint32_t len = live && !pending && qos >= 0 ? B.body_len[i] : 0;
     uint32_t stack_words[kStackWords];  // local memory, touched only beyond 32 levels of nesting
     __shared__ __align__(16) JsonSmem<true, false> json_smem;
     const JsonTables tabs = json_smem.stage_async();
     WindowPipe<kStages> pipe;
     pipe.start(body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
-    acct = load_qos_acct(T, qos, live);  // global latency chain, hidden behind the copies issued above
+    acct = load_qos_acct(T, qos, live && qos >= 0);  // global latency chain, hidden behind the copies issued above
     cp_async_wait<kStages - 1>();        // the table group is the oldest one
     __syncthreads();
     JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
@@ -830,12 +841,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, ARKS_SSE_MINBLK) scan_sse
   uint8_t* wsmem = smem + warp * (kSseStages * kStageBytes);
   const JsonTables tabs = json_smem.stage_async();
   const uint32_t chunk_off = live ? B.body_off[i] : 0;
-  const uint32_t len = live ? B.body_len[i] : 0;
-  const uint8_t* body = B.bodies + chunk_off;
   const int32_t qos = live ? B.qos[i] : 0;
+  const uint32_t len = live && qos >= 0 ? B.body_len[i] : 0;
+  const uint8_t* body = B.bodies + chunk_off;
   WindowPipe<kSseStages> pipe1;
   pipe1.start(body, len, wsmem);
-  const QosAcct acct = load_qos_acct(T, qos, live);  // global latency chain, hidden behind the copies issued above
+  const QosAcct acct = load_qos_acct(T, qos, live && qos >= 0);  // global latency chain, hidden behind the copies issued above
   cp_async_wait<kSseStages - 1>();                   // the table group is the oldest one
   __syncthreads();
   uint32_t stack_words[kStackWords];
@@ -949,12 +960,13 @@ __global__ void sync_quota_kernel(const uint32_t* item_off, const uint8_t* item_
   action[q] = (uint8_t)(update_cr | update_quota << 1);
 }
 
-// quota[i] += reduced[i] - own[i]; own[i] = 0  — applies what the OTHER GPUs added since the last fold
-__global__ void fold_quota_delta_kernel(long long* quota, long long* own, const long long* reduced, size_t n) {
+// quota[i] += reduced[i] - exported[i]; delta[i] -= exported[i] — applies what the OTHER GPUs added up to their export;
+// increments this GPU made after ITS export stay in the delta vector for the next epoch
+__global__ void fold_quota_delta_kernel(long long* quota, long long* delta, const long long* reduced, const long long* exported, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    quota[i] += reduced[i] - own[i];
-    own[i] = 0;
+    quota[i] += reduced[i] - exported[i];
+    delta[i] -= exported[i];
   }
 }
 __global__ void add_quota_kernel(long long* quota, const long long* add, size_t n) {
@@ -990,7 +1002,11 @@ struct arks_ctx {
   long long* d_quota = nullptr;
   long long* d_qdelta = nullptr;   // allocated when quota sharing is enabled
   long long* d_qtmp = nullptr;
+  long long* d_qexp = nullptr;     // what the last arks_export_quota_delta_dev handed out
+  bool qexp_valid = false;
   bool share_quota = false;
+  uint32_t generation = 0;                  // bumped by every successful arks_load_tables
+  std::deque<std::vector<int32_t>> remap;   // remap[k]: qos index of generation (generation - remap.size() + k) -> the next one, or -1
   int32_t* d_backend_weight = nullptr;
   int64_t last_win[4];
   // batch buffers: kSlots independent staging slots so several batches can be resident in HBM at once
@@ -1056,17 +1072,6 @@ static int64_t window_start(int64_t now, int rule) {            // ratelimiter/c
   int64_t r = (now + 62135596800LL) % w;
   if (r < 0) r += w;
   return now - r;
-}
-
-template <class Tv>
-static int upload(arks_ctx* ctx, const std::vector<Tv>& v, const Tv** out) {
-  void* p = nullptr;
-  size_t bytes = (v.size() + 1) * sizeof(Tv);
-  CK(cudaMalloc(&p, bytes));
-  ctx->table_allocs.push_back(p);
-  if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(Tv), cudaMemcpyHostToDevice, ctx->stream));
-  *out = (const Tv*)p;
-  return 0;
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -1140,7 +1145,7 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaMalloc(&ctx->d_inter, inter));
   CK(cudaMalloc(&ctx->d_perm, (size_t)4 * max_batch + 256));
   CK(cudaMalloc(&ctx->d_lenhist, (size_t)4 * kLenBuckets));
-  ctx->result_cap = align_up(n, 256) * 3 + align_up(n * 4, 256) * 3 + align_up(n * 8, 256) * 3;
+  ctx->result_cap = align_up(n, 256) * 3 + align_up(n * 4, 256) * 6 + align_up(n * 8, 256) * 3;
   CK(cudaMalloc(&ctx->d_result, ctx->result_cap));
   CK(cudaMemset(ctx->d_result, 0, ctx->result_cap));  // the packed block has alignment gaps that the D2H copies too
   return 0;
@@ -1162,6 +1167,7 @@ void arks_destroy(arks_ctx* ctx) {
   cudaFree(ctx->d_quota);
   cudaFree(ctx->d_qdelta);
   cudaFree(ctx->d_qtmp);
+  cudaFree(ctx->d_qexp);
   for (auto& sl : ctx->slots) {
     cudaFree(sl.d_req_bodies);
     cudaFree(sl.d_req_meta);
@@ -1314,12 +1320,17 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
 
   // carry counters over by key (Redis keys survive a CRD edit)
   std::vector<long long> new_rate((size_t)4 * t->n_qos + 1, 0), new_quota((size_t)3 * t->n_quotas + 1, 0);
+  std::vector<long long> new_qdelta((size_t)3 * t->n_quotas + 1, 0);  // unfolded increments travel with their quota
   std::vector<long long> new_metrics((size_t)ARKS_METRIC_COLS * t->n_qos + 1, 0);  // series live as long as the process
+  std::vector<int32_t> old_to_new(ctx->loaded ? ctx->ht.n_qos : 0, -1);  // qos index of the outgoing generation -> this one
   if (ctx->loaded) {
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<long long> old_rate((size_t)4 * ctx->ht.n_qos + 1), old_quota((size_t)3 * ctx->ht.n_quotas + 1);
+    std::vector<long long> old_qdelta((size_t)3 * ctx->ht.n_quotas + 1, 0);
     if (ctx->ht.n_qos) CK(cudaMemcpy(old_rate.data(), ctx->d_rate, (size_t)32 * ctx->ht.n_qos, cudaMemcpyDeviceToHost));
     if (ctx->ht.n_quotas) CK(cudaMemcpy(old_quota.data(), ctx->d_quota, (size_t)24 * ctx->ht.n_quotas, cudaMemcpyDeviceToHost));
+    if (ctx->d_qdelta && ctx->ht.n_quotas)
+      CK(cudaMemcpy(old_qdelta.data(), ctx->d_qdelta, (size_t)24 * ctx->ht.n_quotas, cudaMemcpyDeviceToHost));
     std::vector<long long> old_metrics((size_t)ARKS_METRIC_COLS * ctx->ht.n_qos + 1, 0);
     if (ctx->d_metrics && ctx->ht.n_qos)
       CK(cudaMemcpy(old_metrics.data(), ctx->d_metrics, (size_t)8 * ARKS_METRIC_COLS * ctx->ht.n_qos, cudaMemcpyDeviceToHost));
@@ -1329,6 +1340,7 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
     for (uint32_t q = 0; q < t->n_qos; q++) {
       auto it = oq.find(ht.qos_key[q]);
       if (it != oq.end()) {
+        if (old_to_new[it->second] < 0) old_to_new[it->second] = (int32_t)q;  // first entry with the key, as in the lookup
         for (int r = 0; r < 4; r++) new_rate[(size_t)r * t->n_qos + q] = old_rate[(size_t)r * ctx->ht.n_qos + it->second];
         for (int c = 0; c < ARKS_METRIC_COLS; c++)
           new_metrics[(size_t)ARKS_METRIC_COLS * q + c] = old_metrics[(size_t)ARKS_METRIC_COLS * it->second + c];
@@ -1337,23 +1349,42 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
     for (uint32_t q = 0; q < t->n_quotas; q++) {
       auto it = ou.find(ht.quota_key[q]);
       if (it != ou.end())
-        for (int k = 0; k < 3; k++) new_quota[(size_t)3 * q + k] = old_quota[(size_t)3 * it->second + k];
+        for (int k = 0; k < 3; k++) {
+          new_quota[(size_t)3 * q + k] = old_quota[(size_t)3 * it->second + k];
+          new_qdelta[(size_t)3 * q + k] = old_qdelta[(size_t)3 * it->second + k];
+        }
     }
   }
-  free_tables(ctx);
-  cudaFree(ctx->d_rate);
-  cudaFree(ctx->d_quota);
-  cudaFree(ctx->d_metrics);
-  ctx->d_rate = ctx->d_quota = ctx->d_metrics = nullptr;
-  CK(cudaMalloc(&ctx->d_metrics, (size_t)8 * ARKS_METRIC_COLS * t->n_qos + 64));
-  CK(cudaMemcpyAsync(ctx->d_metrics, new_metrics.data(), (size_t)8 * ARKS_METRIC_COLS * t->n_qos, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMalloc(&ctx->d_rate, (size_t)32 * t->n_qos + 64));
-  CK(cudaMalloc(&ctx->d_quota, (size_t)24 * t->n_quotas + 64));
-  CK(cudaMemcpyAsync(ctx->d_rate, new_rate.data(), (size_t)32 * t->n_qos, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_quota, new_quota.data(), (size_t)24 * t->n_quotas, cudaMemcpyHostToDevice, ctx->stream));
 
+  // Build the new generation completely before touching the old one: a failed allocation or upload leaves the context
+  // serving the previous tables and counters.
+  std::vector<void*> fresh;
+  auto drop_fresh = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : fresh) cudaFree(p);
+  };
+  auto put = [&](const void* src, size_t bytes, void** out, size_t alloc_bytes = 0) -> int {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (alloc_bytes > bytes ? alloc_bytes : bytes) + 64);
+    if (e == cudaSuccess) {
+      fresh.push_back(p);
+      if (bytes) e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e != cudaSuccess) {
+      drop_fresh();
+      return fail(ctx, ARKS_E_CUDA, "arks_load_tables: %s (tables unchanged)", cudaGetErrorString(e));
+    }
+    *out = p;
+    return 0;
+  };
+#define PUT(vec, field)                                                                                          \
+  do {                                                                                                           \
+    void* p_ = nullptr;                                                                                          \
+    int rc_ = put((vec).data(), (vec).size() * sizeof((vec)[0]), &p_);                                           \
+    if (rc_) return rc_;                                                                                         \
+    d.field = reinterpret_cast<decltype(d.field)>(p_);                                                           \
+  } while (0)
   DevTables d{};
-  int rc;
   std::vector<uint32_t> v_tok_qos_off(t->tok_qos_off, t->tok_qos_off + t->n_tokens + 1);
   std::vector<int32_t> v_qos_quota(t->qos_quota, t->qos_quota + t->n_qos);
   std::vector<uint32_t> v_qos_rl_off(t->qos_rl_off, t->qos_rl_off + t->n_qos + 1);
@@ -1364,44 +1395,76 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
   std::vector<int64_t> v_qi_val(t->qitem_value, t->qitem_value + t->n_qitems);
   std::vector<uint32_t> v_ep_off(t->ep_backend_off, t->ep_backend_off + t->n_endpoints + 1);
   std::vector<int32_t> v_bw(t->backend_weight, t->backend_weight + t->n_backends);
-  if ((rc = upload(ctx, pool, &d.pool))) return rc;
-  if ((rc = upload(ctx, slots, &d.tok_slots))) return rc;
+  PUT(pool, pool);
+  PUT(slots, tok_slots);
   d.tok_mask = cap - 1;
-  if ((rc = upload(ctx, tok_off, &d.tok_str_off))) return rc;
-  if ((rc = upload(ctx, tok_len, &d.tok_str_len))) return rc;
-  if ((rc = upload(ctx, v_tok_qos_off, &d.tok_qos_off))) return rc;
-  if ((rc = upload(ctx, qmodel_off, &d.qos_model_off))) return rc;
-  if ((rc = upload(ctx, qmodel_len, &d.qos_model_len))) return rc;
-  if ((rc = upload(ctx, v_qos_quota, &d.qos_quota))) return rc;
-  if ((rc = upload(ctx, qos_ep, &d.qos_ep))) return rc;
-  if ((rc = upload(ctx, v_qos_rl_off, &d.qos_rl_off))) return rc;
-  if ((rc = upload(ctx, v_rl_rule, &d.rl_rule))) return rc;
-  if ((rc = upload(ctx, v_rl_value, (const int64_t**)&d.rl_value))) return rc;
-  if ((rc = upload(ctx, v_qi_off, &d.quota_item_off))) return rc;
-  if ((rc = upload(ctx, v_qi_type, &d.qitem_type))) return rc;
-  if ((rc = upload(ctx, v_qi_val, (const int64_t**)&d.qitem_value))) return rc;
-  if ((rc = upload(ctx, v_ep_off, &d.ep_backend_off))) return rc;
-  if ((rc = upload(ctx, v_bw, &d.backend_weight))) return rc;
-  ctx->d_backend_weight = const_cast<int32_t*>(d.backend_weight);
+  PUT(tok_off, tok_str_off);
+  PUT(tok_len, tok_str_len);
+  PUT(v_tok_qos_off, tok_qos_off);
+  PUT(qmodel_off, qos_model_off);
+  PUT(qmodel_len, qos_model_len);
+  PUT(v_qos_quota, qos_quota);
+  PUT(qos_ep, qos_ep);
+  PUT(v_qos_rl_off, qos_rl_off);
+  PUT(v_rl_rule, rl_rule);
+  PUT(v_rl_value, rl_value);
+  PUT(v_qi_off, quota_item_off);
+  PUT(v_qi_type, qitem_type);
+  PUT(v_qi_val, qitem_value);
+  PUT(v_ep_off, ep_backend_off);
+  PUT(v_bw, backend_weight);
+  const size_t n_table_allocs = fresh.size();
+  long long *n_rate = nullptr, *n_quota = nullptr, *n_metrics = nullptr, *n_qdelta = nullptr, *n_qtmp = nullptr, *n_qexp = nullptr;
+  {
+    int rc;
+    if ((rc = put(new_rate.data(), (size_t)32 * t->n_qos, (void**)&n_rate))) return rc;
+    if ((rc = put(new_quota.data(), (size_t)24 * t->n_quotas, (void**)&n_quota))) return rc;
+    if ((rc = put(new_metrics.data(), (size_t)8 * ARKS_METRIC_COLS * t->n_qos, (void**)&n_metrics))) return rc;
+    if (ctx->share_quota) {
+      if ((rc = put(new_qdelta.data(), (size_t)24 * t->n_quotas, (void**)&n_qdelta))) return rc;
+      // two scratch vectors as long as the delta (host-form apply, export snapshot)
+      if ((rc = put(nullptr, 0, (void**)&n_qtmp, (size_t)24 * t->n_quotas))) return rc;
+      if ((rc = put(nullptr, 0, (void**)&n_qexp, (size_t)24 * t->n_quotas))) return rc;
+    }
+  }
+#undef PUT
+  {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      drop_fresh();
+      return fail(ctx, ARKS_E_CUDA, "arks_load_tables: %s (tables unchanged)", cudaGetErrorString(e));
+    }
+  }
+  // commit: nothing below can fail
+  free_tables(ctx);
+  cudaFree(ctx->d_rate);
+  cudaFree(ctx->d_quota);
+  cudaFree(ctx->d_metrics);
   cudaFree(ctx->d_qdelta);
   cudaFree(ctx->d_qtmp);
-  ctx->d_qdelta = ctx->d_qtmp = nullptr;
-  if (ctx->share_quota) {
-    CK(cudaMalloc(&ctx->d_qdelta, (size_t)24 * t->n_quotas + 64));
-    CK(cudaMalloc(&ctx->d_qtmp, (size_t)24 * t->n_quotas + 64));
-    CK(cudaMemsetAsync(ctx->d_qdelta, 0, (size_t)24 * t->n_quotas + 64, ctx->stream));
-  }
+  cudaFree(ctx->d_qexp);
+  ctx->table_allocs.assign(fresh.begin(), fresh.begin() + n_table_allocs);
+  ctx->d_rate = n_rate; ctx->d_quota = n_quota; ctx->d_metrics = n_metrics;
+  ctx->d_qdelta = n_qdelta; ctx->d_qtmp = n_qtmp; ctx->d_qexp = n_qexp;
+  ctx->qexp_valid = false;
+  ctx->d_backend_weight = const_cast<int32_t*>(d.backend_weight);
   d.rate = ctx->d_rate;
   d.metrics = ctx->metrics_on ? ctx->d_metrics : nullptr;
   d.quota = ctx->d_quota;
   d.qdelta = ctx->d_qdelta;
   d.n_qos = t->n_qos;
-  CK(cudaStreamSynchronize(ctx->stream));
   ctx->dt = d;
+  if (ctx->loaded) {
+    ctx->remap.push_back(std::move(old_to_new));
+    if (ctx->remap.size() > ARKS_GEN_HISTORY) ctx->remap.pop_front();
+  }
   ctx->ht = std::move(ht);
+  ctx->generation++;
   ctx->loaded = true;
   return 0;
 }
+
+uint32_t arks_table_generation(const arks_ctx* ctx) { return ctx ? ctx->generation : 0; }
 
 int arks_update_endpoint_weights(arks_ctx* ctx, uint32_t ep, uint32_t n, const int32_t* w) {
   if (!ctx || !ctx->loaded) return ARKS_E_NOT_LOADED;
@@ -1528,11 +1591,13 @@ int arks_stage_request_batch(arks_ctx* ctx, const arks_request_batch* b) {
   return 0;
 }
 
-// offsets of the 8 result arrays inside the packed result block of a batch of n (dense: one D2H for any n)
-static void result_offsets(size_t n, size_t offs[9]) {
+// offsets of the 11 result arrays inside the packed result block of a batch of n (dense: one D2H for any n)
+constexpr int kReqResultArrays = 11;
+static void result_offsets(size_t n, size_t offs[kReqResultArrays + 1]) {
   const size_t a1 = align_up(n, 16), a4 = align_up(n * 4, 16), a8 = align_up(n * 8, 16);
   offs[0] = 0; offs[1] = a1; offs[2] = 2 * a1; offs[3] = 3 * a1; offs[4] = offs[3] + a4; offs[5] = offs[4] + a4;
   offs[6] = offs[5] + a4; offs[7] = offs[6] + a8; offs[8] = offs[7] + a8;
+  offs[9] = offs[8] + a4; offs[10] = offs[9] + a4; offs[11] = offs[10] + a4;
 }
 static void carve_request(arks_ctx* ctx, ReqDev& r, size_t batch_n) {
   const size_t n = ctx->max_batch;
@@ -1550,7 +1615,7 @@ static void carve_request(arks_ctx* ctx, ReqDev& r, size_t batch_n) {
   r.hot_n = (int32_t*)p; p += 256;
   r.hot_list = (int32_t*)p; p += align_up((n / kHotGroup + 2) * 4, 256);
   r.hotrank = (int32_t*)p;
-  size_t offs[9];
+  size_t offs[kReqResultArrays + 1];
   result_offsets(batch_n, offs);
   uint8_t* q = ctx->d_result;
   r.reason = q + offs[0];
@@ -1561,6 +1626,9 @@ static void carve_request(arks_ctx* ctx, ReqDev& r, size_t batch_n) {
   r.pick = (int32_t*)(q + offs[5]);
   r.cur_usage = (long long*)(q + offs[6]);
   r.limit_max = (long long*)(q + offs[7]);
+  r.model_off = (uint32_t*)(q + offs[8]);
+  r.model_len = (uint32_t*)(q + offs[9]);
+  r.bpe = (uint32_t*)(q + offs[10]);
 }
 
 // A warp is as slow as its slowest body and pays for every code path any of its lanes takes, so a small batch is spread
@@ -1636,9 +1704,9 @@ static int enqueue_request_fetch(arks_ctx* ctx) {
   const size_t n = ctx->fetch_n;
   sl.req_fetch_n = (uint32_t)n;
   if (n == 0) return 0;
-  size_t offs[9];
+  size_t offs[kReqResultArrays + 1];
   result_offsets(n, offs);
-  CK(cudaMemcpyAsync(sl.h_req_result, ctx->d_result, offs[8], cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(sl.h_req_result, ctx->d_result, offs[kReqResultArrays], cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaEventRecord(sl.req_done, ctx->stream));
   return 0;
 }
@@ -1648,7 +1716,7 @@ static int finish_request_fetch(arks_ctx* ctx, int slot, arks_request_result* ou
   if (n == 0) return 0;
   CK(cudaEventSynchronize(sl.req_done));
   const uint8_t* h = sl.h_req_result;
-  size_t offs[9];
+  size_t offs[kReqResultArrays + 1];
   result_offsets(n, offs);
   memcpy(out->reason, h + offs[0], n);
   memcpy(out->detail, h + offs[1], n);
@@ -1658,6 +1726,9 @@ static int finish_request_fetch(arks_ctx* ctx, int slot, arks_request_result* ou
   memcpy(out->pick, h + offs[5], n * 4);
   memcpy(out->cur_usage, h + offs[6], n * 8);
   memcpy(out->limit_max, h + offs[7], n * 8);
+  if (out->model_off) memcpy(out->model_off, h + offs[8], n * 4);
+  if (out->model_len) memcpy(out->model_len, h + offs[9], n * 4);
+  if (out->bpe_count) memcpy(out->bpe_count, h + offs[10], n * 4);
   return 0;
 }
 int arks_fetch_request_result(arks_ctx* ctx, arks_request_result* out) {
@@ -1693,6 +1764,18 @@ int arks_submit_request_batch(arks_ctx* ctx, const arks_request_batch* b, arks_r
 }
 
 // ---- response phase -----------------------------------------------------------------------------
+// qos index `q` issued under table generation `g` -> index in the current tables, or -1
+static int32_t resolve_qos(const arks_ctx* ctx, int32_t q, uint32_t g) {
+  if (q < 0 || g > ctx->generation) return -1;
+  const uint32_t steps = ctx->generation - g;
+  if (steps > ctx->remap.size()) return -1;
+  for (size_t k = ctx->remap.size() - steps; k < ctx->remap.size(); k++) {
+    if ((size_t)q >= ctx->remap[k].size()) return -1;
+    q = ctx->remap[k][(size_t)q];
+    if (q < 0) return -1;
+  }
+  return (uint32_t)q < ctx->ht.n_qos ? q : -1;
+}
 int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   if (!ctx || !b) return ARKS_E_INVALID_ARG;
   if (!ctx->loaded) return fail(ctx, ARKS_E_NOT_LOADED, "arks_load_tables has not been called");
@@ -1709,7 +1792,6 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   uint32_t n_sse = 0;
   for (uint32_t i = 0; i < n; i++) {
     n_sse += (b->flags[i] & ARKS_RESP_STREAM) != 0;
-    if (b->qos[i] < 0 || (uint32_t)b->qos[i] >= ctx->ht.n_qos) return fail(ctx, ARKS_E_INVALID_ARG, "response %u: bad qos index", i);
     if ((b->body_off[i] & 15u) || (uint64_t)b->body_off[i] + b->body_len[i] > b->bodies_bytes)
       return fail(ctx, ARKS_E_INVALID_ARG, "body %u: offset not 16-byte aligned or out of range", i);
   }
@@ -1726,7 +1808,14 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   }
   memcpy(h + o_off, b->body_off, (size_t)n * 4);
   memcpy(h + o_len, b->body_len, (size_t)n * 4);
-  memcpy(h + o_qos, b->qos, (size_t)n * 4);
+  {
+    // A row's qos index is positional in the tables of the generation that decided its request. Rows of an older
+    // generation are carried to the current one by key; a row that cannot be resolved (never had a qos entry, index out
+    // of range, key removed, generation older than the history) is marked -1 and answered ARKS_R_QOS_GONE by the kernel:
+    // one stale stream never fails the micro-batch it shares with other tenants.
+    int32_t* hq = reinterpret_cast<int32_t*>(h + o_qos);
+    for (uint32_t i = 0; i < n; i++) hq[i] = resolve_qos(ctx, b->qos[i], b->gen ? b->gen[i] : ctx->generation);
+  }
   memcpy(h + o_fl, b->flags, n);
   const bool small = b->bodies_bytes <= kSmallBatchBytes;
   if (small) {  // one upload on the compute stream (see kSmallBatchBytes)
@@ -1932,17 +2021,23 @@ void* arks_quota_delta_dev(arks_ctx* ctx) { return ctx ? (void*)ctx->d_qdelta : 
 int arks_export_quota_delta_dev(arks_ctx* ctx, void* dst_dev) {
   if (!ctx || !ctx->loaded || !ctx->d_qdelta) return fail(ctx, ARKS_E_INVALID_ARG, "quota sharing is not enabled");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpyAsync(dst_dev, ctx->d_qdelta, (size_t)24 * ctx->ht.n_quotas, cudaMemcpyDeviceToDevice, ctx->stream));
+  // the library keeps its own copy of what it handed out: the fold subtracts exactly this snapshot
+  CK(cudaMemcpyAsync(ctx->d_qexp, ctx->d_qdelta, (size_t)24 * ctx->ht.n_quotas, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (dst_dev) CK(cudaMemcpyAsync(dst_dev, ctx->d_qexp, (size_t)24 * ctx->ht.n_quotas, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->qexp_valid = true;
   return 0;
 }
 int arks_fold_quota_delta_dev(arks_ctx* ctx, const void* reduced_dev, const void* own_dev) {
   if (!ctx || !ctx->loaded || !ctx->d_qdelta) return fail(ctx, ARKS_E_INVALID_ARG, "quota sharing is not enabled");
-  (void)own_dev;  // the library's own delta vector is authoritative
+  if (!reduced_dev) return fail(ctx, ARKS_E_INVALID_ARG, "reduced_dev is null");
+  if (!own_dev && !ctx->qexp_valid) return fail(ctx, ARKS_E_INVALID_ARG, "fold without a preceding arks_export_quota_delta_dev");
   CK(cudaSetDevice(ctx->device));
   const size_t n = (size_t)3 * ctx->ht.n_quotas;
   if (!n) return 0;
-  fold_quota_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_quota, ctx->d_qdelta, (const long long*)reduced_dev, n);
+  fold_quota_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+      ctx->d_quota, ctx->d_qdelta, (const long long*)reduced_dev, own_dev ? (const long long*)own_dev : ctx->d_qexp, n);
+  ctx->qexp_valid = false;
   ctx->launches += 1;
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;

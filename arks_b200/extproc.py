@@ -23,7 +23,7 @@ from concurrent import futures
 import numpy as np
 from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
 
-from . import abi
+from . import abi, replies
 from .abi import RequestBatch, ResponseBatch
 
 # --------------------------------------------------------------------------------------------------
@@ -106,7 +106,19 @@ def error_response(status: int, header: str, header_value, message: str):
     im.headers.CopyFrom(_set_headers([(header, header_value)]))
     ct = im.headers.set_headers.add()
     ct.header.key, ct.header.value = "Content-Type", "application/json"
-    im.body = json.dumps({"error": {"message": message, "code": status}}).encode()
+    im.body = replies.error_body(message, status)
+    return r
+
+
+def passthrough_error(status: int, headers, message: str):
+    """responseErrorProcessing, gateway.go:281-294: the headers of the reply built so far (none in the body phase)"""
+    r = PB["ProcessingResponse"]()
+    im = r.immediate_response
+    im.status.code = status
+    im.headers.CopyFrom(_set_headers(headers))
+    ct = im.headers.set_headers.add()
+    ct.header.key, ct.header.value = "Content-Type", "application/json"
+    im.body = replies.error_body(message, status)
     return r
 
 
@@ -122,6 +134,7 @@ class Batcher:
         self.q: queue.Queue = queue.Queue()
         self.batches = 0
         self._stop = False
+        self._now = -1 << 62
         self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
 
@@ -137,50 +150,71 @@ class Batcher:
         ev.wait()
         return item["out"]
 
-    def response(self, body: bytes, qos: int, flags: int):
+    def response(self, body: bytes, qos: int, flags: int, gen: int = None):
         ev = threading.Event()
-        item = {"kind": "resp", "body": body, "qos": qos, "flags": flags, "ev": ev}
+        item = {"kind": "resp", "body": body, "qos": qos, "flags": flags, "gen": gen, "ev": ev}
         self.q.put(item)
         ev.wait()
         return item["out"]
 
+    _FAILED = {"reason": 255, "detail": 0, "flags": 0, "qos": -1, "token": -1, "pick": -1, "cur_usage": 0, "limit_max": 0,
+               "counted": 0, "usage": [0, 0, 0], "now": 0, "gen": 0, "model_off": 0, "model_len": 0}
+
     def _run(self):
         while not self._stop:
-            first = self.q.get()
-            if first is None:
-                return
-            items = [first]
-            deadline = time.perf_counter() + self.max_wait
-            while len(items) < self.max_batch:
-                left = deadline - time.perf_counter()
-                if left <= 0:
-                    break
-                try:
-                    it = self.q.get(timeout=left)
-                except queue.Empty:
-                    break
-                if it is None:
-                    self._stop = True
-                    break
-                items.append(it)
-            now = int(self.clock())
-            reqs = [i for i in items if i["kind"] == "req"]
-            resps = [i for i in items if i["kind"] == "resp"]
-            if reqs:  # arrival order inside the batch == index order == the linearisation the decisions follow
-                rnd = np.random.default_rng(self.batches).integers(0, 1 << 63, len(reqs), dtype=np.uint64)
-                r = self.engine.handle_request_body(
-                    RequestBatch.from_lists([i["body"] for i in reqs], [i["token"] for i in reqs], now, pick_rand=rnd))
-                for k, i in enumerate(reqs):
-                    i["out"] = {f: v[k] for f, v in r.fields().items()}
-                    i["ev"].set()
-            if resps:
-                r = self.engine.handle_response_body(
-                    ResponseBatch.from_lists([i["body"] for i in resps], [i["qos"] for i in resps],
-                                             [i["flags"] for i in resps], now))
-                for k, i in enumerate(resps):
-                    i["out"] = {"reason": r.reason[k], "counted": r.counted[k], "usage": r.usage[k]}
-                    i["ev"].set()
-            self.batches += 1
+            items = self._collect()
+            if not items:
+                continue
+            try:
+                self._decide(items)
+            except Exception as e:  # an engine error must neither kill the worker nor strand the handlers of this cycle
+                for i in items:
+                    if "out" not in i:
+                        i["out"] = dict(self._FAILED, error=repr(e))
+                        i["ev"].set()
+
+    def _collect(self):
+        first = self.q.get()
+        if first is None:
+            self._stop = True
+            return []
+        items = [first]
+        deadline = time.perf_counter() + self.max_wait
+        while len(items) < self.max_batch:
+            left = deadline - time.perf_counter()
+            if left <= 0:
+                break
+            try:
+                it = self.q.get(timeout=left)
+            except queue.Empty:
+                break
+            if it is None:
+                self._stop = True
+                break
+            items.append(it)
+        return items
+
+    def _decide(self, items):
+        now = self._now = max(int(self.clock()), self._now)  # a wall clock that steps back must not fail the batch
+        gen = getattr(self.engine, "generation", 0)
+        reqs = [i for i in items if i["kind"] == "req"]
+        resps = [i for i in items if i["kind"] == "resp"]
+        if reqs:  # arrival order inside the batch == index order == the linearisation the decisions follow
+            rnd = np.random.default_rng(self.batches).integers(0, 1 << 63, len(reqs), dtype=np.uint64)
+            r = self.engine.handle_request_body(
+                RequestBatch.from_lists([i["body"] for i in reqs], [i["token"] for i in reqs], now, pick_rand=rnd))
+            for k, i in enumerate(reqs):
+                i["out"] = {f: v[k] for f, v in r.fields().items()}
+                i["out"].update(now=now, gen=gen)
+                i["ev"].set()
+        if resps:
+            r = self.engine.handle_response_body(
+                ResponseBatch.from_lists([i["body"] for i in resps], [i["qos"] for i in resps], [i["flags"] for i in resps], now,
+                                         gen=[gen if i["gen"] is None else i["gen"] for i in resps]))
+            for k, i in enumerate(resps):
+                i["out"] = {"reason": r.reason[k], "counted": r.counted[k], "usage": r.usage[k]}
+                i["ev"].set()
+        self.batches += 1
 
 
 # --------------------------------------------------------------------------------------------------
@@ -190,27 +224,31 @@ class CompiledBatcher:
     """The same interface as Batcher, served by the compiled micro-batcher (host/cpp arks_host::Batcher through
     arks_b200/cpphost.py): gRPC handler threads block inside C++ (ctypes releases the GIL) and are batched there."""
 
-    def __init__(self, cpp_batcher, clock=time.time):
+    def __init__(self, cpp_batcher, clock=None):
+        """clock=None (a production server): the C++ batcher reads the wall clock for every batch, so the rate-limit windows
+        roll. A test passes a callable and the batcher is pinned to its reading."""
         self.b = cpp_batcher
         self._clock = clock
-        self.b.set_fixed_clock(int(clock()))
+        if clock is not None:
+            self.b.set_fixed_clock(int(clock()))
 
     @property
     def clock(self):
         return self._clock
 
     @clock.setter
-    def clock(self, fn):  # the loopback tests move time; a production server leaves the C++ default (time(NULL))
+    def clock(self, fn):  # the loopback tests move time
         self._clock = fn
         self.b.set_fixed_clock(int(fn()))
 
     def request(self, body: bytes, token: bytes):
         d = self.b.request(token, body, 0)
         return {"reason": d.reason, "detail": d.detail, "flags": d.flags, "qos": d.qos, "token": d.token, "pick": d.pick,
-                "cur_usage": d.cur_usage, "limit_max": d.limit_max}
+                "cur_usage": d.cur_usage, "limit_max": d.limit_max, "now": d.now_unix, "gen": d.gen,
+                "model_off": d.model_off, "model_len": d.model_len}
 
-    def response(self, body: bytes, qos: int, flags: int):
-        d = self.b.response(qos, body, flags)
+    def response(self, body: bytes, qos: int, flags: int, gen: int = None):
+        d = self.b.response(qos, body, flags, gen)
         return {"reason": d.reason, "counted": d.counted, "usage": list(d.usage)}
 
     def close(self):
@@ -228,7 +266,7 @@ class ExtProcServer:
 
     # ---- Server.Process, gateway.go:77-138
     def Process(self, request_iterator, context):
-        token, qos, stream, status = b"", -1, False, 0
+        token, qos, stream, status = b"", (-1, None), False, 0
         buffered = bytearray()
         for req in request_iterator:
             kind = req.WhichOneof("request")
@@ -238,11 +276,12 @@ class ExtProcServer:
                 resp, qos, stream = self.handle_request_body(req, token)
             elif kind == "response_headers":
                 resp, status = self.handle_response_headers(req)
-                if status == 500:  # gateway.go:115-121
-                    resp = error_response(500, "x-error-response", "true", "")
+                if status == 500:  # gateway.go:115-121 -> responseErrorProcessing keeps the reply's headers, empty message
+                    hs = [(o.header.key, o.header.raw_value) for o in resp.response_headers.response.header_mutation.set_headers]
+                    resp = passthrough_error(500, hs, "")
             elif kind == "response_body":
                 if status != 200:  # gateway.go:122-126: pass the upstream error through
-                    resp = error_response(status, "x-error-response", "true", req.response_body.body.decode("latin1"))
+                    resp = passthrough_error(status, [], req.response_body.body.decode("utf-8", "surrogateescape"))
                 else:
                     resp = self.handle_response_body(req, qos, stream, buffered)
             else:
@@ -254,7 +293,8 @@ class ExtProcServer:
         hs = [(h.key, h.raw_value or h.value.encode()) for h in req.request_headers.headers.headers]
         token = self.extract_bearer(hs)
         if not token:
-            return error_response(401, "x-error-token", "true", "no token found in request headers"), b""
+            st, h, v, m = replies.request_error_reply(abi.R_NO_TOKEN, 0, 0, 0, 0, self.tables, -1, b"", "")
+            return error_response(st, h, v, m), b""
         r = PB["ProcessingResponse"]()
         r.request_headers.response.header_mutation.CopyFrom(_set_headers([(H_WENT_REQ, "true")]))
         r.request_headers.response.clear_route_cache = True
@@ -262,19 +302,22 @@ class ExtProcServer:
 
     # ---- HandleRequestBody, handle_request.go:83-249 (decision comes from the engine)
     def handle_request_body(self, req, token):
-        out = self.batcher.request(bytes(req.request_body.body), token)
+        body = bytes(req.request_body.body)
+        out = self.batcher.request(body, token)
         reason = int(out["reason"])
         if reason != abi.R_OK:
-            status, header = abi.REASON_HTTP[reason]
-            detail = {"reason": reason, "ruleIndex": int(out["detail"]), "currentUsage": int(out["cur_usage"]),
-                      "limitMax": int(out["limit_max"]), "overLimit": reason in (abi.R_RATE_LIMIT, abi.R_QUOTA)}
-            return error_response(status, header, "true", json.dumps(detail)), -1, False
+            ml = int(out.get("model_len", 0))
+            raw = body[int(out.get("model_off", 0)):int(out.get("model_off", 0)) + (ml & 0x7FFFFFFF)]
+            st, h, v, m = replies.request_error_reply(reason, int(out["detail"]), int(out["cur_usage"]), int(out["limit_max"]),
+                                                      int(out.get("now", 0)), self.tables, int(out["qos"]), token,
+                                                      replies.decode_model(raw, bool(ml >> 31)))
+            return error_response(st, h, v, m), (-1, None), False
         t = self.tables
         q, tok = int(out["qos"]), int(out["token"])
         r = PB["ProcessingResponse"]()
         r.request_body.response.header_mutation.CopyFrom(_set_headers([
             ("model", t.qos_model_name[q]), ("namespace", t.token_namespace[tok]), ("username", t.token_user[tok])]))
-        return r, q, bool(out["flags"] & 1)
+        return r, (q, out.get("gen")), bool(out["flags"] & 1)
 
     # ---- HandleResponseHeaders, handle_response.go:37-78
     def handle_response_headers(self, req):
@@ -295,19 +338,19 @@ class ExtProcServer:
     # ---- HandleResponseBody, handle_response.go:80-268
     def handle_response_body(self, req, qos, stream, buffered):
         body, eos = bytes(req.response_body.body), req.response_body.end_of_stream
+        qos, gen = qos
         if stream:
-            out = self.batcher.response(body, qos, abi.RESP_STREAM)
+            out = self.batcher.response(body, qos, abi.RESP_STREAM, gen)
         else:
             buffered += body  # requestBuffers, handle_response.go:134-155
             if not eos:
                 r = PB["ProcessingResponse"]()
                 r.response_body.response.SetInParent()
                 return r
-            out = self.batcher.response(bytes(buffered), qos, abi.RESP_END_OF_STREAM)
+            out = self.batcher.response(bytes(buffered), qos, abi.RESP_END_OF_STREAM, gen)
         reason = int(out["reason"])
-        if reason not in (abi.R_OK, abi.R_PENDING):
-            status, header = abi.REASON_HTTP[reason]
-            return error_response(status, header, "true", "response processing error")
+        if reason not in (abi.R_OK, abi.R_PENDING, abi.R_QOS_GONE):
+            return error_response(*replies.response_error_reply(reason, self.tables, qos, body))
         r = PB["ProcessingResponse"]()
         r.response_body.response.header_mutation.SetInParent()
         return r

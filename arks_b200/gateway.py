@@ -47,6 +47,8 @@ def lib():
         L.arks_last_error.restype = C.c_char_p
         L.arks_last_error.argtypes = [vp]
         L.arks_load_tables.argtypes = [vp, C.POINTER(ArksTables)]
+        L.arks_table_generation.restype = C.c_uint32
+        L.arks_table_generation.argtypes = [vp]
         L.arks_update_endpoint_weights.argtypes = [vp, C.c_uint32, C.c_uint32, abi.i32p]
         L.arks_submit_request_batch.argtypes = [vp, C.POINTER(ArksRequestBatch), C.POINTER(ArksRequestResult)]
         L.arks_submit_response_batch.argtypes = [vp, C.POINTER(ArksResponseBatch), C.POINTER(ArksResponseResult)]
@@ -85,7 +87,7 @@ def lib():
 
 
 EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/test_abi.py)
-    "arks_abi_version", "arks_create", "arks_destroy", "arks_last_error", "arks_load_tables",
+    "arks_abi_version", "arks_create", "arks_destroy", "arks_last_error", "arks_load_tables", "arks_table_generation",
     "arks_update_endpoint_weights", "arks_extract_bearer", "arks_submit_request_batch",
     "arks_submit_response_batch", "arks_stage_request_batch", "arks_run_request_batch",
     "arks_fetch_request_result", "arks_stage_response_batch", "arks_run_response_batch",
@@ -134,6 +136,11 @@ class Gateway:
         ts = tables.c_struct()
         self._ck(lib().arks_load_tables(self._h, C.byref(ts)))
         self.tables = tables
+
+    @property
+    def generation(self) -> int:
+        """table generation the qos / token indices of request results refer to (carry it with the stream)"""
+        return int(lib().arks_table_generation(self._h))
 
     def update_endpoint_weights(self, endpoint: int, weights):
         w = np.ascontiguousarray(weights, np.int32)
@@ -273,8 +280,9 @@ class Gateway:
     def export_quota_delta_dev(self, dst_ptr: int):
         self._ck(lib().arks_export_quota_delta_dev(self._h, C.c_void_p(dst_ptr)))
 
-    def fold_quota_delta_dev(self, reduced_ptr: int):
-        self._ck(lib().arks_fold_quota_delta_dev(self._h, C.c_void_p(reduced_ptr), None))
+    def fold_quota_delta_dev(self, reduced_ptr: int, own_ptr: int = 0):
+        """quota += reduced - own, delta -= own; own defaults to the library's copy of the last export"""
+        self._ck(lib().arks_fold_quota_delta_dev(self._h, C.c_void_p(reduced_ptr), C.c_void_p(own_ptr) if own_ptr else None))
 
     # ---- reply shaping helpers (what the Go host puts on the wire; handle_request.go:208-247, util.go:40-77)
     def request_headers(self, r: RequestResult, i: int) -> dict:

@@ -55,6 +55,13 @@ class Tables:
         self.token_namespace: list[str] = []
         self.token_user: list[str] = []
         self.qos_model_name: list[str] = []
+        self.token_string: list[str] = []
+        # what the 429 / 500 bodies name (ratelimiter/types.go:98-104, quota/types.go:41-55): per qos entry the rule names of
+        # its rateLimits in order, its quota's name and the item types of that ArksQuota in order
+        self.qos_rule_names: list[list[str]] = []
+        self.qos_quota_name: list[str] = []
+        self.qos_quota_item_types: list[list[str]] = []
+        quota_items = {k: [it["type"] for it in quotas[v]["spec"]["quotas"]] for k, v in quota_index.items()}
         for t in tokens:
             md = t["metadata"]
             ns = md.get("namespace", "default")
@@ -63,11 +70,15 @@ class Tables:
             t_name.append(s(md["name"]))
             self.token_namespace.append(ns)
             self.token_user.append(md["name"])
+            self.token_string.append(t["spec"]["token"])
             for qos in t["spec"].get("qos") or []:
                 model = qos["arksEndpoint"]["name"]
                 qos_model.append(s(model))
                 self.qos_model_name.append(model)
                 qname = (qos.get("quota") or {}).get("name", "")
+                self.qos_rule_names.append([rl["type"] for rl in qos.get("rateLimits") or []])
+                self.qos_quota_name.append(qname)
+                self.qos_quota_item_types.append(quota_items.get((ns, qname), []))
                 if qname == "":
                     qos_quota.append(QUOTA_NONE)
                 else:
@@ -124,6 +135,14 @@ class Tables:
         self.backend_weight = a(b_w, np.int32)
         self.n_tokens, self.n_qos, self.n_quotas, self.n_endpoints = len(t_tok), len(qos_model), len(q_ns), len(e_ns)
         self.qos_token = np.repeat(np.arange(self.n_tokens, dtype=np.int32), np.diff(self.tok_qos_off).astype(np.int64))
+
+    def names_blob(self) -> bytes:
+        """the name tables of host/cpp (arks_host::ParseNameTables): one line per ArksToken / qos entry"""
+        lines = ["T\t%s\t%s" % (ns, u) for ns, u in zip(self.token_namespace, self.token_user)]
+        for q in range(self.n_qos):
+            lines.append("Q\t%d\t%s\t%s\t%s\t%s" % (int(self.qos_token[q]), self.qos_model_name[q], self.qos_quota_name[q],
+                                                    ",".join(self.qos_rule_names[q]), ",".join(self.qos_quota_item_types[q])))
+        return "\n".join(lines).encode()
 
     def c_struct(self) -> ArksTables:
         return ArksTables(

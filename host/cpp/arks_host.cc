@@ -39,6 +39,7 @@ struct Block {
   uint32_t* token_off = nullptr;  // n + 1
   uint64_t* rnd = nullptr;
   int32_t* qos = nullptr;         // responses
+  uint32_t* gen = nullptr;
   uint8_t* flags = nullptr;
   // per-row completion
   RequestCallback* rcb = nullptr;
@@ -48,6 +49,8 @@ struct Block {
   uint8_t *reason = nullptr, *detail = nullptr, *rflags = nullptr, *counted = nullptr;
   int32_t *rqos = nullptr, *rtoken = nullptr, *rpick = nullptr;
   int64_t *cur_usage = nullptr, *limit_max = nullptr, *usage = nullptr;
+  uint32_t *model_off = nullptr, *model_len = nullptr, *bpe = nullptr;
+  uint32_t table_gen = 0;  // arks_table_generation() when the request batch was submitted
   // bookkeeping
   uint32_t n = 0;
   size_t bytes = 0, tok_bytes = 0;
@@ -107,7 +110,8 @@ struct Batcher::Impl {
   std::thread dispatcher, completer;
 
   bool submit_request(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user, bool can_lead);
-  bool submit_response(int32_t qos, std::string_view body, uint8_t flags, ResponseCallback cb, void* user, bool can_lead);
+  bool submit_response(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user, bool can_lead);
+  int64_t last_now = INT64_MIN;  // batches never carry an earlier clock reading than their predecessor
 
   void alloc(Block& b, bool is_req) {
     const uint32_t m = opt.max_batch;
@@ -123,8 +127,10 @@ struct Batcher::Impl {
       b.reason = new uint8_t[m]; b.detail = new uint8_t[m]; b.rflags = new uint8_t[m];
       b.rqos = new int32_t[m]; b.rtoken = new int32_t[m]; b.rpick = new int32_t[m];
       b.cur_usage = new int64_t[m]; b.limit_max = new int64_t[m];
+      b.model_off = new uint32_t[m]; b.model_len = new uint32_t[m]; b.bpe = new uint32_t[m];
     } else {
       b.qos = pinned<int32_t>(m);
+      b.gen = pinned<uint32_t>(m);
       b.flags = pinned<uint8_t>(m);
       b.pcb = new ResponseCallback[m];
       b.reason = new uint8_t[m]; b.counted = new uint8_t[m]; b.usage = new int64_t[3 * (size_t)m];
@@ -157,7 +163,11 @@ struct Batcher::Impl {
     int kind = open_resp[0]->n && open_resp[1]->n ? (resp_turn ^= 1) : (open_resp[1]->n ? 1 : 0);
     if (open_resp[kind]->n) { f.resp = open_resp[kind]; open_resp[kind] = free_resp.back(); free_resp.pop_back(); }
     const uint64_t cyc = cycle++;
-    const int64_t now = clock ? clock(clock_arg) : (int64_t)time(nullptr);
+    int64_t now = clock ? clock(clock_arg) : (int64_t)time(nullptr);
+    // a wall clock that steps back (NTP) must not fail the batch (ARKS_E_TIME_WENT_BACK fails every row of it): the
+    // limiter's windows only move forward, like Redis keys that already exist
+    if (now < last_now) now = last_now;
+    last_now = now;
     lk.unlock();
     cv_space.notify_all();
     arks_select_slot(ctx, f.slot);
@@ -169,6 +179,7 @@ struct Batcher::Impl {
       arks_request_batch rb{};
       rb.n = b.n; rb.bodies = b.bodies; rb.body_off = b.body_off; rb.body_len = b.body_len; rb.bodies_bytes = b.bytes;
       rb.tokens = b.tokens; rb.token_off = b.token_off; rb.pick_rand = b.rnd; rb.now_unix = now;
+      b.table_gen = arks_table_generation(ctx);  // LoadTables only runs between cycles: this is the batch's generation
       f.rc_req = arks_submit_request_async(ctx, &rb);
     }
     if (f.resp) {
@@ -177,7 +188,7 @@ struct Batcher::Impl {
       b.cycle = cyc; b.now = now;
       arks_response_batch rb{};
       rb.n = b.n; rb.bodies = b.bodies; rb.body_off = b.body_off; rb.body_len = b.body_len; rb.bodies_bytes = b.bytes;
-      rb.qos = b.qos; rb.flags = b.flags; rb.now_unix = now;
+      rb.qos = b.qos; rb.flags = b.flags; rb.now_unix = now; rb.gen = b.gen;
       f.rc_resp = arks_submit_response_async(ctx, &rb);
     }
     if (opt.max_inflight == 1) {  // nothing else can be queued meanwhile: finish the batch here, one thread hand-off less
@@ -247,7 +258,8 @@ struct Batcher::Impl {
       Block& b = *f.req;
       int rc = f.rc_req;
       if (rc == 0) {
-        arks_request_result rr{b.reason, b.detail, b.rflags, b.rqos, b.rtoken, b.rpick, b.cur_usage, b.limit_max};
+        arks_request_result rr{b.reason, b.detail, b.rflags, b.rqos, b.rtoken, b.rpick, b.cur_usage, b.limit_max,
+                               b.model_off, b.model_len, b.bpe};
         rc = arks_wait_request(ctx, f.slot, &rr);
       }
       for (uint32_t i = 0; i < b.n; i++) {
@@ -257,8 +269,9 @@ struct Batcher::Impl {
           d.reason = b.reason[i]; d.detail = b.detail[i]; d.flags = b.rflags[i];
           d.qos = b.rqos[i]; d.token = b.rtoken[i]; d.pick = b.rpick[i];
           d.cur_usage = b.cur_usage[i]; d.limit_max = b.limit_max[i];
+          d.model_off = b.model_off[i]; d.model_len = b.model_len[i]; d.bpe_count = b.bpe[i];
         }
-        d.cycle = b.cycle; d.index = i; d.now_unix = b.now;
+        d.cycle = b.cycle; d.index = i; d.now_unix = b.now; d.gen = b.table_gen;
         b.rcb[i](b.user[i], d);
       }
     }
@@ -375,7 +388,8 @@ bool Batcher::Impl::submit_request(std::string_view token, std::string_view body
   return true;
 }
 
-bool Batcher::Impl::submit_response(int32_t qos, std::string_view body, uint8_t flags, ResponseCallback cb, void* user, bool can_lead) {
+bool Batcher::Impl::submit_response(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user,
+                                    bool can_lead) {
   Impl& I = *this;
   const size_t need = align16(body.size());
   if (need > I.opt.max_bytes) return false;
@@ -393,6 +407,7 @@ bool Batcher::Impl::submit_response(int32_t qos, std::string_view body, uint8_t 
   b->body_off[row] = (uint32_t)off;
   b->body_len[row] = (uint32_t)body.size();
   b->qos[row] = qos;
+  b->gen[row] = gen;
   b->flags[row] = flags;
   b->pcb[row] = cb;
   b->user[row] = user;
@@ -413,8 +428,30 @@ bool Batcher::Impl::submit_response(int32_t qos, std::string_view body, uint8_t 
 bool Batcher::SubmitRequest(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user) {
   return p_->submit_request(token, body, pick_rand, cb, user, false);
 }
-bool Batcher::SubmitResponse(int32_t qos, std::string_view body, uint8_t flags, ResponseCallback cb, void* user) {
-  return p_->submit_response(qos, body, flags, cb, user, false);
+bool Batcher::SubmitResponse(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user) {
+  return p_->submit_response(qos, gen, body, flags, cb, user, false);
+}
+uint32_t Batcher::Generation() const { return arks_table_generation(p_->ctx); }
+int Batcher::LoadTables(const arks_tables* t) {
+  Impl& I = *p_;
+  std::unique_lock<std::mutex> lk(I.mu);
+  // become the one "cycle" in progress: no submit can start, and wait for what is queued on the device
+  auto idle = [&] {
+    if (I.cycling) return false;
+    for (int k = 0; k < kSlots; k++)
+      if (I.slot_busy[k]) return false;
+    return true;
+  };
+  while (!idle()) I.cv_space.wait_for(lk, std::chrono::microseconds(100));
+  I.cycling = true;
+  lk.unlock();
+  const int rc = arks_load_tables(I.ctx, t);
+  lk.lock();
+  I.cycling = false;
+  lk.unlock();
+  I.cv_work.notify_all();
+  I.cv_space.notify_all();
+  return rc;
 }
 
 RequestDecision Batcher::HandleRequestBody(std::string_view token, std::string_view body, uint64_t pick_rand) {
@@ -427,9 +464,9 @@ RequestDecision Batcher::HandleRequestBody(std::string_view token, std::string_v
   p.ready.wait(0, std::memory_order_acquire);  // futex sleep until the completion thread hands the decision over
   return p.rd;
 }
-ResponseDecision Batcher::HandleResponseBody(int32_t qos, std::string_view body, uint8_t flags) {
+ResponseDecision Batcher::HandleResponseBody(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags) {
   Parked p;
-  if (!p_->submit_response(qos, body, flags, wake_response, &p, true)) {
+  if (!p_->submit_response(qos, gen, body, flags, wake_response, &p, true)) {
     ResponseDecision d{};
     d.reason = kReasonHostError;
     return d;
@@ -441,7 +478,7 @@ ResponseDecision Batcher::HandleResponseBody(int32_t qos, std::string_view body,
 // ---- error shaping (A13) ---------------------------------------------------------------------------------------
 int ReasonHttpStatus(uint8_t r) {
   switch (r) {
-    case ARKS_R_OK: case ARKS_R_PENDING: return 200;
+    case ARKS_R_OK: case ARKS_R_PENDING: case ARKS_R_QOS_GONE: return 200;
     case ARKS_R_NO_TOKEN: return 401;
     case ARKS_R_REQUEST_BODY: case ARKS_R_NO_MODEL: case ARKS_R_NO_MODEL_BACKENDS: case ARKS_R_STREAM_OPTIONS: return 400;
     case ARKS_R_RATE_LIMIT: case ARKS_R_QUOTA: return 429;
@@ -463,7 +500,8 @@ const char* ReasonHeader(uint8_t r) {
     default: return "x-error-response";
   }
 }
-static std::string json_escape(const std::string& s) {
+// json-iterator ConfigFastest string encoding (EscapeHTML off): `"`, `\` and control bytes are escaped, the rest is raw
+static std::string json_escape(std::string_view s) {
   std::string o;
   for (unsigned char c : s) {
     if (c == '"' || c == '\\') { o += '\\'; o += (char)c; }
@@ -475,17 +513,209 @@ static std::string json_escape(const std::string& s) {
   }
   return o;
 }
-Action ErrorResponse(int status, const char* header, const std::string& message) {
+Action ErrorResponse(int status, std::vector<Header> headers, const std::string& message) {
   Action a;
   a.kind = Action::kImmediate;
   a.status = status;
-  a.set_headers.push_back({header, "true"});
+  a.set_headers = std::move(headers);
   a.set_headers.push_back({"Content-Type", "application/json"});
-  a.body = "{\"error\": {\"message\": \"" + json_escape(message) + "\", \"code\": " + std::to_string(status) + "}}";
+  // generateErrorMessage marshals a map: Go does not fix the order of "message" and "code" (SURVEY.md §8a A13); this is
+  // one of the two byte strings the reference produces
+  a.body = "{\"error\":{\"message\":\"" + json_escape(message) + "\",\"code\":" + std::to_string(status) + "}}";
   return a;
 }
 
+// the string a raw JSON string span decodes to (jsoniter ReadString: surrogate pairs joined, lone surrogates -> U+FFFD)
+std::string DecodeJsonString(std::string_view raw) {
+  std::string o;
+  auto put = [&](uint32_t r) {
+    if (r > 0x10FFFF || (r >= 0xD800 && r <= 0xDFFF)) r = 0xFFFD;
+    if (r <= 0x7F) o += (char)r;
+    else if (r <= 0x7FF) { o += (char)(0xC0 | (r >> 6)); o += (char)(0x80 | (r & 0x3F)); }
+    else if (r <= 0xFFFF) { o += (char)(0xE0 | (r >> 12)); o += (char)(0x80 | ((r >> 6) & 0x3F)); o += (char)(0x80 | (r & 0x3F)); }
+    else { o += (char)(0xF0 | (r >> 18)); o += (char)(0x80 | ((r >> 12) & 0x3F)); o += (char)(0x80 | ((r >> 6) & 0x3F)); o += (char)(0x80 | (r & 0x3F)); }
+  };
+  auto hex4 = [&](size_t i) {
+    uint32_t v = 0;
+    for (size_t k = i; k < i + 4 && k < raw.size(); k++) {
+      const unsigned char c = (unsigned char)raw[k];
+      v = v * 16 + (c <= '9' ? c - '0' : (c | 0x20) - 'a' + 10);
+    }
+    return v;
+  };
+  size_t i = 0;
+  while (i < raw.size()) {
+    const char c = raw[i++];
+    if (c != '\\' || i >= raw.size()) { o += c; continue; }
+    char e = raw[i++];
+    for (;;) {
+      if (e != 'u') {
+        o += e == 'b' ? '\b' : e == 'f' ? '\f' : e == 'n' ? '\n' : e == 'r' ? '\r' : e == 't' ? '\t' : e;
+        break;
+      }
+      uint32_t r = hex4(i);
+      i += 4;
+      if (r < 0xD800 || r > 0xDFFF) { put(r); break; }
+      if (i >= raw.size() || raw[i] != '\\') { put(r); break; }
+      i++;
+      e = i < raw.size() ? raw[i++] : '\\';
+      if (e != 'u') { put(r); continue; }  // the next escape is decoded on its own
+      const uint32_t r2 = hex4(i);
+      i += 4;
+      if (r < 0xDC00 && r2 >= 0xDC00 && r2 < 0xE000) put((((r - 0xD800) << 10) | (r2 - 0xDC00)) + 0x10000);
+      else { put(r); put(r2); }
+      break;
+    }
+  }
+  return o;
+}
+
+static std::string model_of(const RequestDecision& d, std::string_view body) {
+  const uint32_t len = d.model_len & 0x7fffffffu;
+  if (len == 0 || (size_t)d.model_off + len > body.size()) return "";
+  const std::string_view raw = body.substr(d.model_off, len);
+  return (d.model_len & 0x80000000u) ? DecodeJsonString(raw) : std::string(raw);
+}
+// time.Time.MarshalJSON of a whole second in UTC (RFC 3339)
+static std::string rfc3339(int64_t unix_s) {
+  time_t t = (time_t)unix_s;
+  struct tm g;
+  gmtime_r(&t, &g);
+  char b[40];
+  strftime(b, sizeof b, "%Y-%m-%dT%H:%M:%SZ", &g);
+  return b;
+}
+static int64_t window_len(const std::string& rule) { return rule == "rpm" || rule == "tpm" ? 60 : 86400; }  // rate_limiter.go:31-68
+
+ErrorReply RequestErrorReply(const RequestDecision& d, const NameTables& names, std::string_view token, std::string_view body) {
+  ErrorReply e{ReasonHttpStatus(d.reason), ReasonHeader(d.reason), "true", ""};
+  const std::string model = model_of(d, body);
+  switch (d.reason) {
+    case ARKS_R_NO_TOKEN:  // handle_request.go:48-56
+      e.message = "no token found in request headers";
+      break;
+    case ARKS_R_REQUEST_BODY:  // :97-104
+      e.message = "error processing request body";
+      break;
+    case ARKS_R_NO_MODEL:  // :108-115: RawValue []byte(model) with model == ""
+      e.header_value = "";
+      e.message = "no model in request body";
+      break;
+    case ARKS_R_TOKEN_NOT_FOUND:  // :119-126, err from arks_impl.go:313-315
+      e.header_value = "token not found: " + std::string(token);
+      e.message = "error to get qos by token";
+      break;
+    case ARKS_R_MODEL_NOT_IN_TOKEN:  // arks_impl.go:337
+      e.header_value = "model not found: " + model;
+      e.message = "error to get qos by token";
+      break;
+    case ARKS_R_NO_MODEL_BACKENDS:  // :147-154
+      e.header_value = model;
+      e.message = "model " + model + " does not exist";
+      break;
+    case ARKS_R_STREAM_OPTIONS:  // :162-170
+      e.header_value = "include_usage for stream_options not set";
+      e.message = "no stream with usage option available";
+      break;
+    case ARKS_R_RATE_LIMIT: {  // check.go:140-152: RateLimitResponse.JSON(), ratelimiter/types.go:98-114
+      std::string rule = "rpm";
+      if (d.qos >= 0 && (size_t)d.qos < names.qos_rule_names.size() && d.detail < names.qos_rule_names[(size_t)d.qos].size())
+        rule = names.qos_rule_names[(size_t)d.qos][d.detail];
+      // expiresAt = now + TTL(key) in the reference (redis_impl.go:104-110; wall clock with nanoseconds, TTL with jitter):
+      // the one field that is not a function of the request stream. Here: the end of the rule's fixed window.
+      const int64_t w = window_len(rule);
+      int64_t r = (d.now_unix + 62135596800LL) % w;
+      if (r < 0) r += w;
+      e.message = "{\"ruleName\":\"" + rule + "\",\"overLimit\":true,\"currentUsage\":" + std::to_string(d.cur_usage) +
+                  ",\"limitMax\":" + std::to_string(d.limit_max) + ",\"expiresAt\":\"" + rfc3339(d.now_unix - r + w) + "\"}";
+      break;
+    }
+    case ARKS_R_QUOTA: {  // check.go:95-104: QuotaResult.JSON(), quota/types.go:41-55 (Identifier has no json tag)
+      std::string ns, qname, type = "total";
+      if (d.qos >= 0 && (size_t)d.qos < names.qos_quota_name.size()) {
+        qname = names.qos_quota_name[(size_t)d.qos];
+        const int32_t t = names.qos_token[(size_t)d.qos];
+        if (t >= 0 && (size_t)t < names.token_namespace.size()) ns = names.token_namespace[(size_t)t];
+        if (d.detail < names.qos_quota_item_types[(size_t)d.qos].size()) type = names.qos_quota_item_types[(size_t)d.qos][d.detail];
+      }
+      e.message = "{\"Identifier\":[{\"Key\":\"namespace\",\"Value\":\"" + json_escape(ns) + "\"},{\"Key\":\"quotaname\",\"Value\":\"" +
+                  json_escape(qname) + "\"},{\"Key\":\"type\",\"Value\":\"" + type + "\"}],\"overLimit\":true,\"currentUsage\":" +
+                  std::to_string(d.cur_usage) + ",\"limitMax\":" + std::to_string(d.limit_max) + "}";
+      break;
+    }
+    case ARKS_R_QUOTA_CONFIG: {  // check.go:76-84: err.Error() of the client's Get (apimachinery NewNotFound)
+      std::string qname;
+      if (d.qos >= 0 && (size_t)d.qos < names.qos_quota_name.size()) qname = names.qos_quota_name[(size_t)d.qos];
+      e.message = "ArksQuota.arks.ai \"" + qname + "\" not found";
+      break;
+    }
+    default:  // reason 255: the row never reached the device (host error)
+      e.status = 500;
+      e.header = "x-error-rate-limit";
+      e.header_value = "rate limit error";  // handle_request.go:199-205, the reference's only other 500 of this phase
+      e.message = "rate limit error";
+  }
+  return e;
+}
+
+ErrorReply ResponseErrorReply(const ResponseDecision& d, const NameTables& names, int32_t qos, std::string_view last_chunk) {
+  ErrorReply e{ReasonHttpStatus(d.reason), ReasonHeader(d.reason), "true", ""};
+  switch (d.reason) {
+    // the message of the next two is err.Error() of openai-go's stream / json-iterator: third-party wording that is not a
+    // function the reference defines; a fixed text stands in for it
+    case ARKS_R_STREAMING: e.message = "error to unmarshal response"; break;           // handle_response.go:125-133
+    case ARKS_R_RESPONSE_UNMARSHAL: e.message = "error to unmarshal response"; break;  // :157-166
+    case ARKS_R_RESPONSE_UNKNOWN:                                                      // :167-181
+      e.message = last_chunk.empty() ? "unknown response" : std::string(last_chunk);
+      break;
+    case ARKS_R_QUOTA_CONFIG_RESP: {  // :215-223 via check.go:62-72
+      std::string qname;
+      if (qos >= 0 && (size_t)qos < names.qos_quota_name.size()) qname = names.qos_quota_name[(size_t)qos];
+      e.message = "ArksQuota.arks.ai \"" + qname + "\" not found";
+      break;
+    }
+    default: e.status = 500; e.header = "x-error-response-unknown"; e.message = "unknown response";
+  }
+  return e;
+}
+
+bool ParseNameTables(std::string_view text, NameTables* out) {
+  NameTables n;
+  auto split = [](std::string_view s, char sep) {
+    std::vector<std::string> v;
+    size_t p = 0;
+    for (;;) {
+      const size_t q = s.find(sep, p);
+      v.emplace_back(s.substr(p, q == std::string_view::npos ? s.size() - p : q - p));
+      if (q == std::string_view::npos) break;
+      p = q + 1;
+    }
+    return v;
+  };
+  auto list = [&](const std::string& s) { return s.empty() ? std::vector<std::string>() : split(s, ','); };
+  for (const std::string& line : split(text, '\n')) {
+    if (line.empty()) continue;
+    const std::vector<std::string> f = split(line, '\t');
+    if (f[0] == "T" && f.size() == 3) {
+      n.token_namespace.push_back(f[1]);
+      n.token_user.push_back(f[2]);
+    } else if (f[0] == "Q" && f.size() == 6) {
+      n.qos_token.push_back(atoi(f[1].c_str()));
+      n.qos_model.push_back(f[2]);
+      n.qos_quota_name.push_back(f[3]);
+      n.qos_rule_names.push_back(list(f[4]));
+      n.qos_quota_item_types.push_back(list(f[5]));
+    } else {
+      return false;
+    }
+  }
+  *out = std::move(n);
+  return true;
+}
+
 // ---- StreamProcessor --------------------------------------------------------------------------------------------
+static Action reply_action(const ErrorReply& e) { return ErrorResponse(e.status, {{e.header, e.header_value}}, e.message); }
+
 Action StreamProcessor::OnRequestHeaders(const std::vector<Header>& headers) {
   std::vector<const uint8_t*> k(headers.size()), v(headers.size());
   std::vector<size_t> kl(headers.size()), vl(headers.size());
@@ -495,7 +725,11 @@ Action StreamProcessor::OnRequestHeaders(const std::vector<Header>& headers) {
   }
   const uint8_t* tok = nullptr;
   const size_t n = arks_extract_bearer(k.data(), kl.data(), v.data(), vl.data(), headers.size(), &tok);
-  if (n == 0) return ErrorResponse(401, "x-error-token", "no token found in request headers");
+  if (n == 0) {
+    RequestDecision d{};
+    d.reason = ARKS_R_NO_TOKEN;
+    return reply_action(RequestErrorReply(d, *names_, "", ""));
+  }
   token_.assign((const char*)tok, n);
   Action a;
   a.kind = Action::kContinueRequestHeaders;
@@ -505,14 +739,9 @@ Action StreamProcessor::OnRequestHeaders(const std::vector<Header>& headers) {
 }
 Action StreamProcessor::OnRequestBody(std::string_view body, uint64_t pick_rand) {
   req_ = b_->HandleRequestBody(token_, body, pick_rand);
-  if (req_.reason != ARKS_R_OK) {
-    char msg[192];
-    snprintf(msg, sizeof msg, "{\"reason\": %u, \"ruleIndex\": %u, \"currentUsage\": %lld, \"limitMax\": %lld, \"overLimit\": %s}",
-             req_.reason, req_.detail, (long long)req_.cur_usage, (long long)req_.limit_max,
-             (req_.reason == ARKS_R_RATE_LIMIT || req_.reason == ARKS_R_QUOTA) ? "true" : "false");
-    return ErrorResponse(ReasonHttpStatus(req_.reason), ReasonHeader(req_.reason), msg);
-  }
+  if (req_.reason != ARKS_R_OK) return reply_action(RequestErrorReply(req_, *names_, token_, body));
   qos_ = req_.qos;
+  gen_ = req_.gen;
   stream_ = req_.flags & 1;
   Action a;
   a.kind = Action::kContinueRequestBody;
@@ -535,13 +764,15 @@ Action StreamProcessor::OnResponseHeaders(const std::vector<Header>& headers) {
     a.set_headers.push_back(h);
   }
   a.clear_route_cache = true;
-  if (status_ == 500) return ErrorResponse(500, "x-error-response", "");  // gateway.go:115-121
+  // gateway.go:115-121 -> responseErrorProcessing (:281-294): the headers of the reply built so far, an empty message
+  if (status_ == 500) return ErrorResponse(500, a.set_headers, "");
   return a;
 }
 Action StreamProcessor::OnResponseBody(std::string_view body, bool end_of_stream) {
-  if (status_ != 200) return ErrorResponse(status_, "x-error-response", std::string(body));  // gateway.go:122-126
+  // gateway.go:122-126: the upstream's error body is passed on; `resp` is still empty there, so no x-error-* header
+  if (status_ != 200) return ErrorResponse(status_, {}, std::string(body));
   if (stream_) {
-    resp_ = b_->HandleResponseBody(qos_, body, ARKS_RESP_STREAM);
+    resp_ = b_->HandleResponseBody(qos_, gen_, body, ARKS_RESP_STREAM);
   } else {
     buffered_.append(body);  // requestBuffers, handle_response.go:134-155
     if (!end_of_stream) {
@@ -549,10 +780,10 @@ Action StreamProcessor::OnResponseBody(std::string_view body, bool end_of_stream
       a.kind = Action::kContinueResponseBody;
       return a;
     }
-    resp_ = b_->HandleResponseBody(qos_, buffered_, ARKS_RESP_END_OF_STREAM);
+    resp_ = b_->HandleResponseBody(qos_, gen_, buffered_, ARKS_RESP_END_OF_STREAM);
   }
-  if (resp_.reason != ARKS_R_OK && resp_.reason != ARKS_R_PENDING)
-    return ErrorResponse(ReasonHttpStatus(resp_.reason), ReasonHeader(resp_.reason), "response processing error");
+  if (resp_.reason != ARKS_R_OK && resp_.reason != ARKS_R_PENDING && resp_.reason != ARKS_R_QOS_GONE)
+    return reply_action(ResponseErrorReply(resp_, *names_, qos_, body));
   Action a;
   a.kind = Action::kContinueResponseBody;
   return a;
@@ -566,7 +797,14 @@ using namespace arks_host;
 struct arks_host_batcher {
   Batcher* b;
   std::atomic<int64_t> fixed_now{0};
+  NameTables names;
 };
+static int put_reply(const ErrorReply& e, char* out, uint32_t out_cap) {
+  const std::string o = std::to_string(e.status) + "\n" + e.header + "\n" + e.header_value + "\n" + e.message;
+  if (o.size() + 1 > out_cap) return -1;
+  memcpy(out, o.c_str(), o.size() + 1);
+  return (int)o.size();
+}
 template <class F>
 static int64_t run_threads(uint32_t n, uint32_t threads, int64_t* latency_ns, F&& one) {
   if (threads == 0) threads = 1;
@@ -620,9 +858,24 @@ int arks_host_request(arks_host_batcher* h, const uint8_t* token, uint32_t token
   *out = h->b->HandleRequestBody(std::string_view((const char*)token, token_len), std::string_view((const char*)body, body_len), pick_rand);
   return out->reason == 255 ? ARKS_E_INVALID_ARG : 0;
 }
-int arks_host_response(arks_host_batcher* h, int32_t qos, const uint8_t* body, uint32_t body_len, uint8_t flags, ResponseDecision* out) {
-  *out = h->b->HandleResponseBody(qos, std::string_view((const char*)body, body_len), flags);
+int arks_host_response(arks_host_batcher* h, int32_t qos, uint32_t gen, const uint8_t* body, uint32_t body_len, uint8_t flags,
+                       ResponseDecision* out) {
+  if (gen == 0xffffffffu) gen = h->b->Generation();  // "the tables have not changed since the request"
+  *out = h->b->HandleResponseBody(qos, gen, std::string_view((const char*)body, body_len), flags);
   return out->reason == 255 ? ARKS_E_INVALID_ARG : 0;
+}
+int arks_host_load_tables(arks_host_batcher* h, const arks_tables* t) { return h->b->LoadTables(t); }
+int arks_host_set_names(arks_host_batcher* h, const char* text, uint32_t len) {
+  return ParseNameTables(std::string_view(text, len), &h->names) ? 0 : ARKS_E_INVALID_ARG;
+}
+int arks_host_request_error_reply(arks_host_batcher* h, const RequestDecision* d, const uint8_t* token, uint32_t token_len,
+                                  const uint8_t* body, uint32_t body_len, char* out, uint32_t out_cap) {
+  return put_reply(RequestErrorReply(*d, h->names, std::string_view((const char*)token, token_len),
+                                     std::string_view((const char*)body, body_len)), out, out_cap);
+}
+int arks_host_response_error_reply(arks_host_batcher* h, const ResponseDecision* d, int32_t qos, const uint8_t* chunk, uint32_t chunk_len,
+                                   char* out, uint32_t out_cap) {
+  return put_reply(ResponseErrorReply(*d, h->names, qos, std::string_view((const char*)chunk, chunk_len)), out, out_cap);
 }
 void arks_host_stats(arks_host_batcher* h, BatcherStats* out) { *out = h->b->Stats(); }
 
@@ -635,10 +888,11 @@ int64_t arks_host_run_requests(arks_host_batcher* h, uint32_t n, uint32_t thread
   });
 }
 int64_t arks_host_run_responses(arks_host_batcher* h, uint32_t n, uint32_t threads, const uint8_t* bodies, const uint32_t* body_off,
-                                const uint32_t* body_len, const int32_t* qos, const uint8_t* flags, ResponseDecision* out,
+                                const uint32_t* body_len, const int32_t* qos, const uint32_t* gen, const uint8_t* flags, ResponseDecision* out,
                                 int64_t* latency_ns) {
   return run_threads(n, threads, latency_ns, [&](uint32_t i) {
-    out[i] = h->b->HandleResponseBody(qos[i], std::string_view((const char*)bodies + body_off[i], body_len[i]), flags[i]);
+    out[i] = h->b->HandleResponseBody(qos[i], gen ? gen[i] : h->b->Generation(),
+                                      std::string_view((const char*)bodies + body_off[i], body_len[i]), flags[i]);
   });
 }
 
@@ -700,16 +954,12 @@ static void dump(std::string& o, const Action& a) {
   for (const Header& h : a.set_headers) o += h.key + ": " + h.value + "\n";
   o += "\n" + a.body + "\n--\n";
 }
-int arks_host_stream_transcript(arks_host_batcher* h, const char* const* qos_model, uint32_t n_qos, const char* const* tok_ns,
-                                const char* const* tok_user, uint32_t n_tok, const char* const* req_hdr_keys,
+int arks_host_stream_transcript(arks_host_batcher* h, const char* const* req_hdr_keys,
                                 const char* const* req_hdr_vals, uint32_t n_req_hdr, const uint8_t* req_body, uint32_t req_body_len,
                                 const char* const* resp_hdr_keys, const char* const* resp_hdr_vals, uint32_t n_resp_hdr,
                                 const uint8_t* const* resp_chunks, const uint32_t* resp_chunk_len, uint32_t n_resp_chunks,
                                 uint64_t pick_rand, char* out, uint32_t out_cap) {
-  NameTables names;
-  for (uint32_t i = 0; i < n_qos; i++) names.qos_model.emplace_back(qos_model[i]);
-  for (uint32_t i = 0; i < n_tok; i++) { names.token_namespace.emplace_back(tok_ns[i]); names.token_user.emplace_back(tok_user[i]); }
-  StreamProcessor sp(h->b, &names);
+  StreamProcessor sp(h->b, &h->names);
   std::string o;
   std::vector<Header> rh, ph;
   for (uint32_t i = 0; i < n_req_hdr; i++) rh.push_back({req_hdr_keys[i], req_hdr_vals[i]});

@@ -33,6 +33,9 @@ struct RequestDecision {
   uint64_t cycle;    // dispatcher cycle that carried the request
   uint32_t index;    // row inside that cycle's request batch
   int64_t now_unix;  // the batch's clock reading
+  uint32_t gen;      // table generation qos / token refer to: hand it back with the stream's response chunks
+  uint32_t model_off, model_len;  // raw span of the body's model string (bit 31 of model_len: contains escapes)
+  uint32_t bpe_count;             // BPE tokens of the prompt (0 without a vocabulary)
 };
 struct ResponseDecision {
   uint8_t reason, counted;
@@ -70,12 +73,19 @@ class Batcher {
   // Blocking, callable from any number of threads. `pick_rand`: the stream's random draw for the weighted pick.
   // A row that can never fit (body larger than max_bytes) is answered with reason 255 without touching the device.
   RequestDecision HandleRequestBody(std::string_view token, std::string_view body, uint64_t pick_rand);
-  ResponseDecision HandleResponseBody(int32_t qos, std::string_view body, uint8_t flags);
+  // `gen`: RequestDecision::gen of the stream's request (the generation its qos index belongs to)
+  ResponseDecision HandleResponseBody(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags);
   // Asynchronous form for event-driven servers: returns once the row is staged (the body is copied, the caller's buffer
   // is free again); `cb(user, decision)` runs later on the completion thread, rows of a batch in order. false: the row
   // can never fit, cb is not called.
   bool SubmitRequest(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user);
-  bool SubmitResponse(int32_t qos, std::string_view body, uint8_t flags, ResponseCallback cb, void* user);
+  bool SubmitResponse(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user);
+
+  // Config reload between two cycles (qosconfig informer event -> arks_load_tables): waits for the batches queued on the
+  // device, swaps the tables while no cycle runs, and lets the streams go on. Requests decided before the swap keep
+  // their (gen, qos); the library re-maps them by key when their response chunks arrive.
+  int LoadTables(const arks_tables* t);
+  uint32_t Generation() const;  // arks_table_generation of the context
 
   void SetClock(int64_t (*clock)(void*), void* arg);  // default: time(nullptr)
   BatcherStats Stats() const;
@@ -89,10 +99,16 @@ class Batcher {
 struct Header {
   std::string key, value;
 };
-// names the routing headers are built from (arks_impl.go: qos -> model, token -> namespace / user)
+// names the routing headers and the error replies are built from (arks_impl.go: qos -> model, token -> namespace / user)
 struct NameTables {
   std::vector<std::string> qos_model, token_namespace, token_user;
+  std::vector<int32_t> qos_token;                               // owning ArksToken of each qos entry
+  std::vector<std::vector<std::string>> qos_rule_names;         // RateLimit.Type of qos.RateLimits, in order ("rpm", ...)
+  std::vector<std::string> qos_quota_name;                      // qos.Quota.Name, "" when none
+  std::vector<std::vector<std::string>> qos_quota_item_types;   // QuotaItem.Type of the referenced ArksQuota, in order
 };
+// one table line per object: "T\t<namespace>\t<user>" / "Q\t<token index>\t<model>\t<quota name>\t<rule,rule,..>\t<type,type,..>"
+bool ParseNameTables(std::string_view text, NameTables* out);
 struct Action {
   enum Kind { kContinueRequestHeaders, kContinueRequestBody, kContinueResponseHeaders, kContinueResponseBody, kImmediate };
   Kind kind = kContinueRequestHeaders;
@@ -117,15 +133,26 @@ class StreamProcessor {
   const NameTables* names_;
   std::string token_, buffered_;
   int32_t qos_ = -1;
+  uint32_t gen_ = 0;
   bool stream_ = false;
   int status_ = 0;
   RequestDecision req_{};
   ResponseDecision resp_{};
 };
 
-Action ErrorResponse(int status, const char* header, const std::string& message);  // generateErrorResponse, util.go:40-77
+// generateErrorResponse, util.go:40-77: status + headers + Content-Type + {"error":{"message":..,"code":..}}
+Action ErrorResponse(int status, std::vector<Header> headers, const std::string& message);
 int ReasonHttpStatus(uint8_t reason);
 const char* ReasonHeader(uint8_t reason);
+// What the reference puts on the wire for a failed request / response phase: status, x-error-* header with the VALUE the
+// Go code sends, and the error message (handle_request.go:97-205, check.go:88-103,140-152, handle_response.go:125-181).
+struct ErrorReply {
+  int status;
+  std::string header, header_value, message;
+};
+ErrorReply RequestErrorReply(const RequestDecision& d, const NameTables& names, std::string_view token, std::string_view body);
+ErrorReply ResponseErrorReply(const ResponseDecision& d, const NameTables& names, int32_t qos, std::string_view last_chunk);
+std::string DecodeJsonString(std::string_view raw);  // the model name out of its raw span (jsoniter ReadString semantics)
 
 }  // namespace arks_host
 
@@ -138,8 +165,16 @@ void arks_host_destroy(arks_host_batcher* b);
 void arks_host_set_fixed_clock(arks_host_batcher* b, int64_t now_unix);
 int arks_host_request(arks_host_batcher* b, const uint8_t* token, uint32_t token_len, const uint8_t* body, uint32_t body_len,
                       uint64_t pick_rand, arks_host::RequestDecision* out);
-int arks_host_response(arks_host_batcher* b, int32_t qos, const uint8_t* body, uint32_t body_len, uint8_t flags,
-                       arks_host::ResponseDecision* out);
+int arks_host_response(arks_host_batcher* b, int32_t qos, uint32_t gen /* 0xffffffff: the current generation */, const uint8_t* body,
+                       uint32_t body_len, uint8_t flags, arks_host::ResponseDecision* out);
+int arks_host_load_tables(arks_host_batcher* b, const arks_tables* t);
+// names for the reply shapes of arks_host_stream_transcript / arks_host_error_reply (format: ParseNameTables)
+int arks_host_set_names(arks_host_batcher* b, const char* text, uint32_t len);
+// the reference-exact reply of a failed request / response decision as "status\nheader\nheader value\nmessage"
+int arks_host_request_error_reply(arks_host_batcher* b, const arks_host::RequestDecision* d, const uint8_t* token, uint32_t token_len,
+                                  const uint8_t* body, uint32_t body_len, char* out, uint32_t out_cap);
+int arks_host_response_error_reply(arks_host_batcher* b, const arks_host::ResponseDecision* d, int32_t qos, const uint8_t* chunk,
+                                   uint32_t chunk_len, char* out, uint32_t out_cap);
 void arks_host_stats(arks_host_batcher* b, arks_host::BatcherStats* out);
 // n requests issued by `threads` stream threads (thread t owns rows t, t+threads, ...; each row is one blocking
 // HandleRequestBody). Decisions and per-call latencies (ns) come back in row order; returns wall nanoseconds.
@@ -147,8 +182,8 @@ int64_t arks_host_run_requests(arks_host_batcher* b, uint32_t n, uint32_t thread
                                const uint32_t* body_len, const uint8_t* tokens, const uint32_t* token_off, const uint64_t* pick_rand,
                                arks_host::RequestDecision* out, int64_t* latency_ns);
 int64_t arks_host_run_responses(arks_host_batcher* b, uint32_t n, uint32_t threads, const uint8_t* bodies, const uint32_t* body_off,
-                                const uint32_t* body_len, const int32_t* qos, const uint8_t* flags, arks_host::ResponseDecision* out,
-                                int64_t* latency_ns);
+                                const uint32_t* body_len, const int32_t* qos, const uint32_t* gen /* or NULL: current */,
+                                const uint8_t* flags, arks_host::ResponseDecision* out, int64_t* latency_ns);
 // open-loop arrivals at rate_per_s (exponential gaps) from `producers` threads through SubmitRequest; latency_ns[i] =
 // decision handed over - scheduled arrival of row i; returns wall nanoseconds
 int64_t arks_host_open_loop_requests(arks_host_batcher* b, uint32_t n, double rate_per_s, uint32_t producers, const uint8_t* bodies,
@@ -156,8 +191,7 @@ int64_t arks_host_open_loop_requests(arks_host_batcher* b, uint32_t n, double ra
                                      const uint64_t* pick_rand, arks_host::RequestDecision* out, int64_t* latency_ns);
 // one ext_proc stream driven end to end; the transcript of actions is written as text (one action per block:
 // "kind status clear\nkey: value\n...\n\nbody\n--\n") for comparison with the Python mirror
-int arks_host_stream_transcript(arks_host_batcher* b, const char* const* qos_model, uint32_t n_qos, const char* const* tok_ns,
-                                const char* const* tok_user, uint32_t n_tok, const char* const* req_hdr_keys,
+int arks_host_stream_transcript(arks_host_batcher* b, const char* const* req_hdr_keys,
                                 const char* const* req_hdr_vals, uint32_t n_req_hdr, const uint8_t* req_body, uint32_t req_body_len,
                                 const char* const* resp_hdr_keys, const char* const* resp_hdr_vals, uint32_t n_resp_hdr,
                                 const uint8_t* const* resp_chunks, const uint32_t* resp_chunk_len, uint32_t n_resp_chunks,

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ARKS_ABI_VERSION 1
+#define ARKS_ABI_VERSION 2
 
 /* ---- status codes (library-level errors; Go `error` in the reference) ---- */
 enum arks_status {
@@ -86,6 +86,10 @@ enum arks_reason {
   ARKS_R_RESPONSE_UNKNOWN = 13,    /* 500 x-error-response-unknown              handle_response.go:167-181 */
   ARKS_R_QUOTA_CONFIG_RESP = 14,   /* 500 x-error-quota at response time        handle_response.go:215-223 */
   ARKS_R_PENDING = 15,             /* non-stream chunk without end_of_stream: empty CommonResponse :141-149 */
+  ARKS_R_QOS_GONE = 16,            /* response row whose qos entry is unknown to the current tables (never resolved, or
+                                      its (namespace,user,model) key was removed by a config reload since the request):
+                                      nothing is billed, the row is answered like ARKS_R_OK. The reference keeps the
+                                      UserQos by value (gateway.go:78) and would still INCRBY the orphaned Redis keys. */
 };
 
 /* ---- config tables: a flat snapshot of the ArksToken / ArksQuota / ArksEndpoint informer cache ----
@@ -155,6 +159,15 @@ typedef struct arks_request_result {
   int32_t* pick;        /* n: backend index within the endpoint, -1 none / not admitted                      */
   int64_t* cur_usage;   /* n: RateLimitResponse.currentUsage / QuotaResult.currentUsage for 429s, else 0     */
   int64_t* limit_max;   /* n: limitMax for 429s, else 0                                                      */
+  /* optional outputs (each may be NULL) */
+  uint32_t* model_off;  /* n: byte offset, inside body i, of the raw `model` string (first byte after the opening quote) */
+  uint32_t* model_len;  /* n: its raw length (escapes not decoded); bit 31 set iff the span contains a backslash. Both 0
+                         *    when the body did not parse or its last `model` member is not a string. The host needs the
+                         *    name for the x-error-* header values of handle_request.go:112,123,151 and slices its own copy
+                         *    of the body                                                                               */
+  uint32_t* bpe_count;  /* n: BPE tokens of the prompt text (see arks_load_bpe); 0 when no vocabulary is loaded. A side
+                         *    output: the reference counts no tokens at request time (check.go:124-126), so this never
+                         *    feeds admit/deny unless ARKS_OPT_PRECHARGE_TPM is switched on                              */
 } arks_request_result;
 
 /* ---- response phase (ProcessingRequest_ResponseBody with :status 200, handle_response.go:80-268) ---- */
@@ -172,7 +185,12 @@ typedef struct arks_response_batch {
   const int32_t* qos;    /* n: from arks_request_result.qos */
   const uint8_t* flags;  /* n: ARKS_RESP_* */
   int64_t now_unix;
+  const uint32_t* gen;   /* n or NULL: arks_table_generation() at the time each row's request was decided. A qos index is
+                          * positional in the tables of ITS generation; rows of an older generation are re-mapped by their
+                          * (namespace,user,model) key (the last ARKS_GEN_HISTORY generations are kept) or answered
+                          * ARKS_R_QOS_GONE. NULL: every row belongs to the current generation. */
 } arks_response_batch;
+#define ARKS_GEN_HISTORY 16
 
 typedef struct arks_response_result {
   uint8_t* reason;   /* n: ARKS_R_OK / STREAMING / RESPONSE_UNMARSHAL / RESPONSE_UNKNOWN / QUOTA_CONFIG_RESP / PENDING */
@@ -192,6 +210,8 @@ const char* arks_last_error(const arks_ctx* ctx);
  * A load between batches swaps the whole snapshot; counters are carried over by key
  * ((namespace,user,model) and (namespace,quotaName)), like Redis keys survive a CRD edit. */
 int arks_load_tables(arks_ctx* ctx, const arks_tables* t);
+/* bumped by every arks_load_tables that succeeds: the generation the qos / token indices of request results refer to */
+uint32_t arks_table_generation(const arks_ctx* ctx);
 /* routing churn (BASELINE config 5): replace the weights of one endpoint's backends in place */
 int arks_update_endpoint_weights(arks_ctx* ctx, uint32_t endpoint, uint32_t n, const int32_t* weights);
 
@@ -279,12 +299,16 @@ int arks_snapshot_rate(arks_ctx* ctx, int64_t now_unix, int64_t* counters /* 4 *
  * vector (3*n_quotas int64). A fold epoch: all-reduce(sum) the delta vectors (the caller's NCCL / torch.distributed
  * call), then on every GPU quota += reduced - own_delta and own_delta = 0. Host-buffer form: take (returns and zeroes
  * the delta) + apply (adds the sum of the OTHER GPUs' deltas). Device form: export (D2D copy of the delta into the
- * caller's buffer, e.g. a torch tensor handed to ncclAllReduce) + fold (reads the reduced vector from device memory). */
+ * caller's buffer, e.g. a torch tensor handed to ncclAllReduce) + fold (reads the reduced vector from device memory).
+ * The delta vector survives arks_load_tables by (namespace, quotaName) like the usage itself. */
 int arks_enable_quota_sharing(arks_ctx* ctx, int on);
 int arks_take_quota_delta(arks_ctx* ctx, int64_t* delta_out);
 int arks_apply_quota_delta(arks_ctx* ctx, const int64_t* remote_delta);
 void* arks_quota_delta_dev(arks_ctx* ctx);
 int arks_export_quota_delta_dev(arks_ctx* ctx, void* dst_dev);
+/* quota += reduced - own; delta -= own, where `own` is what arks_export_quota_delta_dev handed out (own_dev, or the
+ * library's copy of the last export when own_dev is NULL): increments that arrived between export and fold stay in the
+ * delta vector for the next epoch. */
 int arks_fold_quota_delta_dev(arks_ctx* ctx, const void* reduced_dev, const void* own_dev);
 
 #ifdef __cplusplus

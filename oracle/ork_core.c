@@ -383,7 +383,12 @@ static void handle_request(ork* o, const arks_request_batch* b, arks_request_res
   uint8_t mbuf[1024];
   ork_sink model = {mbuf, 0, sizeof mbuf, 0, 0};
   int stream3, so_present, iu3;
-  if (ork_json_request(body, len, &model, &stream3, &so_present, &iu3)) {
+  uint32_t span[2];
+  int bad = ork_json_request(body, len, &model, &stream3, &so_present, &iu3, span);
+  if (r->model_off) r->model_off[out] = span[0];
+  if (r->model_len) r->model_len[out] = span[1];
+  if (r->bpe_count) r->bpe_count[out] = 0; /* the BPE counter has no reference implementation: its oracle is HF tokenizers */
+  if (bad) {
     r->reason[out] = ARKS_R_REQUEST_BODY;
     return;
   }
@@ -481,6 +486,12 @@ static int token_bucket(int64_t v) {
 static void handle_response_inner(ork* o, const arks_response_batch* b, arks_response_result* r, uint32_t i, uint32_t out);
 /* Server.Process + the deferred block of HandleResponseBody: gateway.go:122-129, handle_response.go:99-109 */
 static void handle_response(ork* o, const arks_response_batch* b, arks_response_result* r, uint32_t i, uint32_t out) {
+  if (b->qos[i] < 0 || (uint32_t)b->qos[i] >= o->n_qos) { /* the stream's qos entry is not in these tables: nothing to bill */
+    r->reason[out] = ARKS_R_QOS_GONE;
+    r->counted[out] = 0;
+    r->usage[3 * (size_t)out] = r->usage[3 * (size_t)out + 1] = r->usage[3 * (size_t)out + 2] = 0;
+    return;
+  }
   handle_response_inner(o, b, r, i, out);
   int64_t* row = o->metrics + (size_t)b->qos[i] * ARKS_METRIC_COLS;
   row[ARKS_METRIC_MESSAGES]++; /* RecordRequest(ns, user, model, dur, "200") for every response-body message */
@@ -555,8 +566,6 @@ int ork_request_batch(ork* o, const arks_request_batch* b, arks_request_result* 
 int ork_response_batch(ork* o, const arks_response_batch* b, arks_response_result* r) {
   int rc = check_time(o, b->now_unix);
   if (rc) return rc;
-  for (uint32_t i = 0; i < b->n; i++)
-    if (b->qos[i] < 0 || (uint32_t)b->qos[i] >= o->n_qos) return ARKS_E_INVALID_ARG;
   for (uint32_t i = 0; i < b->n; i++) handle_response(o, b, r, i, i);
   return 0;
 }
@@ -571,6 +580,7 @@ typedef struct {
   uint8_t *reason, *detail, *flags, *counted;
   int32_t *qos, *token, *pick;
   int64_t *cur, *lim, *usage;
+  uint32_t *moff, *mlen;
   uint32_t n;
 } mt_priv;
 typedef struct {
@@ -599,6 +609,7 @@ static void priv_alloc(mt_priv* p, uint32_t n, int req) {
     p->detail = (uint8_t*)malloc(m); p->flags = (uint8_t*)malloc(m);
     p->qos = (int32_t*)malloc(4 * m); p->token = (int32_t*)malloc(4 * m); p->pick = (int32_t*)malloc(4 * m);
     p->cur = (int64_t*)malloc(8 * m); p->lim = (int64_t*)malloc(8 * m);
+    p->moff = (uint32_t*)malloc(4 * m); p->mlen = (uint32_t*)malloc(4 * m);
   } else {
     p->counted = (uint8_t*)malloc(m);
     p->usage = (int64_t*)malloc(24 * m);
@@ -606,7 +617,7 @@ static void priv_alloc(mt_priv* p, uint32_t n, int req) {
 }
 static void priv_free(mt_priv* p) {
   free(p->reason); free(p->detail); free(p->flags); free(p->counted);
-  free(p->qos); free(p->token); free(p->pick); free(p->cur); free(p->lim); free(p->usage);
+  free(p->qos); free(p->token); free(p->pick); free(p->cur); free(p->lim); free(p->usage); free(p->moff); free(p->mlen);
 }
 static void* mt_req(void* p) {
   mt_arg* a = (mt_arg*)p;
@@ -621,7 +632,7 @@ static void* mt_req(void* p) {
   for (uint32_t i = 0; i < n; i++) mine += a->shard[i] == a->tid;
   mt_priv* me = &a->priv[a->tid];
   priv_alloc(me, mine, 1);
-  arks_request_result pr = {me->reason, me->detail, me->flags, me->qos, me->token, me->pick, me->cur, me->lim};
+  arks_request_result pr = {me->reason, me->detail, me->flags, me->qos, me->token, me->pick, me->cur, me->lim, me->moff, me->mlen, NULL};
   uint32_t k = 0;
   for (uint32_t i = 0; i < n; i++)
     if (a->shard[i] == a->tid) {
@@ -636,6 +647,9 @@ static void* mt_req(void* p) {
     r->reason[i] = w->reason[j]; r->detail[i] = w->detail[j]; r->flags[i] = w->flags[j];
     r->qos[i] = w->qos[j]; r->token[i] = w->token[j]; r->pick[i] = w->pick[j];
     r->cur_usage[i] = w->cur[j]; r->limit_max[i] = w->lim[j];
+    if (r->model_off) r->model_off[i] = w->moff[j];
+    if (r->model_len) r->model_len[i] = w->mlen[j];
+    if (r->bpe_count) r->bpe_count[i] = 0;
   }
   return NULL;
 }
@@ -803,7 +817,7 @@ int ork_snapshot_rate(ork* o, int64_t now, int64_t* c) {
 int ork_parse_request_body(const uint8_t* body, size_t len, uint8_t* model_out, size_t model_cap, size_t* model_len,
                            int* stream, int* so_present, int* include_usage) {
   ork_sink m = {model_out, 0, model_cap, 0, 0};
-  int rc = ork_json_request(body, len, &m, stream, so_present, include_usage);
+  int rc = ork_json_request(body, len, &m, stream, so_present, include_usage, NULL);
   *model_len = m.len;
   return rc;
 }

@@ -14,7 +14,7 @@ typedef struct {
 } ork_sink;
 
 int ork_json_request(const uint8_t* body, size_t len, ork_sink* model, int* stream, int* so_present,
-                     int* include_usage);
+                     int* include_usage, uint32_t span[2]);
 int ork_json_response(const uint8_t* body, size_t len, ork_sink* model, int64_t usage[3]);
 int ork_sse_chunk(const uint8_t* body, size_t len, int64_t usage[3]);
 void ork_usage_from_value(const uint8_t* b, size_t i, size_t e, int64_t usage[3]);

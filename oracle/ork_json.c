@@ -36,6 +36,7 @@ typedef struct {
   int err;   /* a non-EOF error has been reported (iter.Error != nil && != io.EOF) */
   int eof;   /* iter.Error == io.EOF */
   int depth; /* incrementDepth / maxDepth = 10000 (iter.go) */
+  size_t str_start; /* ReadString: first byte after the opening quote of the last string read (model span) */
 } jit;
 
 #define J_MAX_DEPTH 10000
@@ -206,6 +207,7 @@ static void j_read_string_slow(jit* it, ork_sink* s) {
 static int j_read_string(jit* it, ork_sink* s) {
   uint8_t c = j_next_token(it);
   if (c == '"') {
+    it->str_start = it->head;
     for (size_t i = it->head; i < it->tail; i++) {
       c = it->b[i];
       if (c == '"') {
@@ -513,7 +515,7 @@ static int j_finish(jit* it) {
 /* ---- request body: struct{Model string; Stream *bool; StreamOptions *struct{IncludeUsage *bool}} ----
  * threeFieldsStructDecoder + OptionalDecoder + oneFieldStructDecoder (reflect_struct_decoder.go) */
 int ork_json_request(const uint8_t* body, size_t len, ork_sink* model, int* stream, int* so_present,
-                     int* include_usage) {
+                     int* include_usage, uint32_t span[2]) {
   static int64_t H_MODEL, H_STREAM, H_SO, H_IU;
   if (!H_MODEL) {
     H_MODEL = field_hash_of("model");
@@ -521,18 +523,28 @@ int ork_json_request(const uint8_t* body, size_t len, ork_sink* model, int* stre
     H_SO = field_hash_of("stream_options");
     H_IU = field_hash_of("include_usage");
   }
-  jit it = {body, 0, len, 0, 0, 0};
+  jit it = {body, 0, len, 0, 0, 0, 0};
   *stream = 0;
   *so_present = 0;
   *include_usage = 0;
   if (model) model->len = 0;
+  uint32_t sp[2] = {0, 0};
   if (j_read_object_start(&it) && j_inc_depth(&it)) {
     for (;;) {
       int64_t h = j_read_field_hash(&it);
       if (it.err) break;
       if (h == H_MODEL) {
         if (model) model->len = 0;
-        j_read_string(&it, model); /* null -> "" */
+        sp[0] = sp[1] = 0;
+        if (!j_read_string(&it, model) && !it.err) { /* null -> "" */
+          /* raw span between the quotes (the host slices its copy of the body for the x-error-* header values) */
+          size_t e = it.head - 1;
+          sp[0] = (uint32_t)it.str_start;
+          sp[1] = (uint32_t)(e - it.str_start);
+          for (size_t k = it.str_start; k < e; k++)
+            if (body[k] == '\\') sp[1] |= 0x80000000u;
+          if ((sp[1] & 0x7fffffffu) == 0) sp[0] = sp[1] = 0;
+        }
       } else if (h == H_STREAM) {
         j_decode_opt_bool(&it, stream);
       } else if (h == H_SO) {
@@ -564,7 +576,12 @@ int ork_json_request(const uint8_t* body, size_t len, ork_sink* model, int* stre
     }
     j_dec_depth(&it);
   }
-  return j_finish(&it);
+  int rc = j_finish(&it);
+  if (span) {
+    span[0] = rc ? 0 : sp[0];
+    span[1] = rc ? 0 : sp[1];
+  }
+  return rc;
 }
 
 /* =====================================================================================
@@ -738,7 +755,7 @@ int ork_json_response(const uint8_t* body, size_t len, ork_sink* model, int64_t 
     H_MODEL = field_hash_of("model");
     H_USAGE = field_hash_of("usage");
   }
-  jit it = {body, 0, len, 0, 0, 0};
+  jit it = {body, 0, len, 0, 0, 0, 0};
   usage[0] = usage[1] = usage[2] = 0;
   if (model) model->len = 0;
   if (j_read_object_start(&it) && j_inc_depth(&it)) {

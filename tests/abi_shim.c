@@ -14,11 +14,13 @@ struct slot_res {
   uint8_t *reason, *detail, *flags, *counted;
   int32_t *qos, *token, *pick;
   int64_t *cur, *lim, *usage;
+  uint32_t *moff, *mlen, *bpe;
   int rc;
 };
 struct arks_ctx {
   ork* o;
   int cur;
+  uint32_t generation;
   struct slot_res rq[SHIM_SLOTS], rs[SHIM_SLOTS];
 };
 
@@ -26,8 +28,16 @@ int arks_shim_create(const arks_tables* t, arks_ctx** out) {
   arks_ctx* c = (arks_ctx*)calloc(1, sizeof *c);
   c->o = ork_create(t);
   if (!c->o) { free(c); return ARKS_E_BAD_TABLE; }
+  c->generation = 1;
   *out = c;
   return 0;
+}
+uint32_t arks_table_generation(const arks_ctx* c) { return c->generation; }
+/* the shim keeps no key history: rows of an older generation are answered ARKS_R_QOS_GONE (the product re-maps them) */
+int arks_load_tables(arks_ctx* c, const arks_tables* t) {
+  int rc = ork_reload(c->o, t);
+  if (!rc) c->generation++;
+  return rc;
 }
 void* arks_shim_oracle(arks_ctx* c) { return c->o; } /* for snapshots in tests */
 void arks_shim_destroy(arks_ctx* c) {
@@ -56,12 +66,13 @@ static void grow(struct slot_res* s, uint32_t n) {
   s->reason = realloc(s->reason, n); s->detail = realloc(s->detail, n); s->flags = realloc(s->flags, n); s->counted = realloc(s->counted, n);
   s->qos = realloc(s->qos, 4 * (size_t)n); s->token = realloc(s->token, 4 * (size_t)n); s->pick = realloc(s->pick, 4 * (size_t)n);
   s->cur = realloc(s->cur, 8 * (size_t)n); s->lim = realloc(s->lim, 8 * (size_t)n); s->usage = realloc(s->usage, 24 * (size_t)n);
+  s->moff = realloc(s->moff, 4 * (size_t)n); s->mlen = realloc(s->mlen, 4 * (size_t)n); s->bpe = realloc(s->bpe, 4 * (size_t)n);
 }
 int arks_submit_request_async(arks_ctx* c, const arks_request_batch* b) {
   struct slot_res* s = &c->rq[c->cur];
   grow(s, b->n ? b->n : 1);
   s->n = b->n;
-  arks_request_result r = {s->reason, s->detail, s->flags, s->qos, s->token, s->pick, s->cur, s->lim};
+  arks_request_result r = {s->reason, s->detail, s->flags, s->qos, s->token, s->pick, s->cur, s->lim, s->moff, s->mlen, s->bpe};
   s->rc = ork_request_batch(c->o, b, &r);
   return s->rc;
 }
@@ -71,6 +82,9 @@ int arks_wait_request(arks_ctx* c, int slot, arks_request_result* out) {
   memcpy(out->reason, s->reason, n); memcpy(out->detail, s->detail, n); memcpy(out->flags, s->flags, n);
   memcpy(out->qos, s->qos, 4 * n); memcpy(out->token, s->token, 4 * n); memcpy(out->pick, s->pick, 4 * n);
   memcpy(out->cur_usage, s->cur, 8 * n); memcpy(out->limit_max, s->lim, 8 * n);
+  if (out->model_off) memcpy(out->model_off, s->moff, 4 * n);
+  if (out->model_len) memcpy(out->model_len, s->mlen, 4 * n);
+  if (out->bpe_count) memcpy(out->bpe_count, s->bpe, 4 * n);
   return s->rc;
 }
 int arks_submit_response_async(arks_ctx* c, const arks_response_batch* b) {
@@ -78,7 +92,16 @@ int arks_submit_response_async(arks_ctx* c, const arks_response_batch* b) {
   grow(s, b->n ? b->n : 1);
   s->n = b->n;
   arks_response_result r = {s->reason, s->counted, s->usage};
-  s->rc = ork_response_batch(c->o, b, &r);
+  if (b->gen) { /* rows of an older generation: their qos index means nothing in these tables */
+    int32_t* q = (int32_t*)malloc(4 * (size_t)(b->n ? b->n : 1));
+    for (uint32_t i = 0; i < b->n; i++) q[i] = b->gen[i] == c->generation ? b->qos[i] : -1;
+    arks_response_batch b2 = *b;
+    b2.qos = q;
+    s->rc = ork_response_batch(c->o, &b2, &r);
+    free(q);
+  } else {
+    s->rc = ork_response_batch(c->o, b, &r);
+  }
   return s->rc;
 }
 int arks_wait_response(arks_ctx* c, int slot, arks_response_result* out) {

@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"libarksgw.so does not export {n}"
     assert sorted(gateway.EXPORTED) == names
-    assert L.arks_abi_version() == 1
+    assert L.arks_abi_version() == 2
 
 
 def test_no_cpu_fallback():

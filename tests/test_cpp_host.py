@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 import orklib
-from arks_b200 import abi, cpphost, traffic
+from arks_b200 import abi, cpphost, replies, traffic
 from arks_b200.abi import RequestBatch, ResponseBatch
 from arks_b200.tables import Tables
 
@@ -82,7 +82,7 @@ def replay_requests(tables, batch: RequestBatch, dec):
         toks = [bytes(batch.tokens[batch.token_off[i]:batch.token_off[i + 1]]) for i in grp]
         rb = RequestBatch.from_lists(bodies, toks, now, pick_rand=batch.pick_rand[grp] if batch.pick_rand is not None else None)
         want = o.request_batch(rb)
-        for f in ("reason", "detail", "flags", "qos", "token", "pick", "cur_usage", "limit_max"):
+        for f in ("reason", "detail", "flags", "qos", "token", "pick", "cur_usage", "limit_max", "model_off", "model_len"):
             got = dec[f][grp]
             assert np.array_equal(got, getattr(want, f)), (f, got[:8], getattr(want, f)[:8])
         n_batches += 1
@@ -167,12 +167,12 @@ def run_stream_checks(make_engine):
     eng = make_engine(t, max_batch=64, max_bytes=1 << 20)
     try:
         eng.b.set_fixed_clock(NOW)
-        names = (t.qos_model_name, t.token_namespace, t.token_user)
+        eng.b.set_names(t)
         req_h = [(":method", "POST"), ("authorization", "Bearer sk-test123456"), ("content-type", "application/json")]
         body = FX["request_body"].encode()
         rbody = FX["response_body"].encode()
         # happy path, response split in two (non-stream: buffered until end_of_stream), handle_*.go header sets
-        got = eng.b.stream_transcript(names, req_h, body, [(":status", "200"), ("content-type", "application/json")],
+        got = eng.b.stream_transcript(req_h, body, [(":status", "200"), ("content-type", "application/json")],
                                       [rbody[:100], rbody[100:]])
         want = (expected_transcript(0, 0, 1, [("x-went-into-req-headers", "true")]) +
                 expected_transcript(1, 0, 0, [("model", "qwen-7b"), ("namespace", "default"), ("username", "example-token")]) +
@@ -181,31 +181,33 @@ def run_stream_checks(make_engine):
                 expected_transcript(3) + expected_transcript(3))
         assert got == want
         # no bearer -> 401 on the headers message, nothing else is processed (handle_request.go:48-56)
-        got = eng.b.stream_transcript(names, [("content-type", "application/json")], body, [], [])
-        err = json.dumps({"error": {"message": "no token found in request headers", "code": 401}})
+        got = eng.b.stream_transcript([("content-type", "application/json")], body, [], [])
+        err = replies.error_body("no token found in request headers", 401).decode()
         assert got == expected_transcript(4, 401, 0, [("x-error-token", "true"), ("Content-Type", "application/json")], err)
-        # upstream 500 is rewritten on the response headers; other non-200 bodies pass through (gateway.go:115-126)
-        got = eng.b.stream_transcript(names, req_h, body, [(":status", "500")], [b"boom"])
-        assert got.split("--\n")[2].startswith("4 500 0\nx-error-response: true\n")
-        got = eng.b.stream_transcript(names, req_h, body, [(":status", "404")], [b'{"detail":"nope"}'])
+        # upstream 500 is rewritten on the response headers message, keeping that reply's headers; other non-200 bodies pass
+        # through with Content-Type only (gateway.go:115-126, responseErrorProcessing :281-294)
+        got = eng.b.stream_transcript(req_h, body, [(":status", "500")], [b"boom"])
+        assert got.split("--\n")[2] == ("4 500 0\nx-went-into-resp-headers: true\n:status: 500\nContent-Type: application/json\n\n" +
+                                        replies.error_body("", 500).decode() + "\n")
+        got = eng.b.stream_transcript(req_h, body, [(":status", "404")], [b'{"detail":"nope"}'])
         blocks = got.split("--\n")
-        assert blocks[3].startswith("4 404 0\nx-error-response: true\n")
+        assert blocks[3].startswith("4 404 0\nContent-Type: application/json\n\n")
         assert json.loads(blocks[3].split("\n\n", 1)[1])["error"]["message"] == '{"detail":"nope"}'
         # rpm 5: four more pass (two were admitted above: the 500 and the 404 streams), then 429 with usage 5/5
         kinds = []
         for _ in range(2):
-            kinds.append(eng.b.stream_transcript(names, req_h, body, [(":status", "200")], [rbody]).split("--\n")[1][0])
+            kinds.append(eng.b.stream_transcript(req_h, body, [(":status", "200")], [rbody]).split("--\n")[1][0])
         assert kinds == ["1", "1"]
-        got = eng.b.stream_transcript(names, req_h, body, [(":status", "200")], [rbody])
+        got = eng.b.stream_transcript(req_h, body, [(":status", "200")], [rbody])
         blk = got.split("--\n")[1]
         assert blk.startswith("4 429 0\nx-error-rate-limit: true\n")
         detail = json.loads(json.loads(blk.split("\n\n", 1)[1])["error"]["message"])
-        assert (detail["currentUsage"], detail["limitMax"], detail["ruleIndex"], detail["overLimit"]) == (5, 5, 0, True)
+        assert detail == {"ruleName": "rpm", "overLimit": True, "currentUsage": 5, "limitMax": 5, "expiresAt": "2023-11-14T22:14:00Z"}
         # streaming: every SSE chunk is a batch row of its own
         sse = json.load(open(os.path.join(HERE, "golden", "sse_stream.json")))
         eng.b.set_fixed_clock(NOW + 60)
         sreq = b'{"model":"qwen-7b","stream":true,"stream_options":{"include_usage":true},"messages":[]}'
-        got = eng.b.stream_transcript(names, req_h, sreq, [(":status", "200")], [c.encode() for c in sse["chunks"]])
+        got = eng.b.stream_transcript(req_h, sreq, [(":status", "200")], [c.encode() for c in sse["chunks"]])
         assert got.count("--\n") == 3 + len(sse["chunks"]) and "\n4 " not in "\n" + got
         assert eng.b.stats()["responses"] >= len(sse["chunks"])
     finally:

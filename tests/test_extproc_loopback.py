@@ -106,7 +106,9 @@ def run_loopback(engine, tables, make_batcher=None):
         assert r[1].immediate_response.status.code == 429
         assert "x-error-rate-limit" in set_headers(r[1].immediate_response.headers)
         detail = json.loads(json.loads(r[1].immediate_response.body)["error"]["message"])
-        assert (detail["currentUsage"], detail["limitMax"], detail["ruleIndex"]) == (5, 5, 0)
+        # RateLimitResponse.JSON(), ratelimiter/types.go:98-114
+        assert (detail["ruleName"], detail["overLimit"], detail["currentUsage"], detail["limitMax"]) == ("rpm", True, 5, 5)
+        assert detail["expiresAt"] == "2023-11-14T22:14:00Z"  # end of NOW's minute window
 
         # streaming request + SSE chunks
         sse = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sse_stream.json")))
