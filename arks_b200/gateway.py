@@ -67,6 +67,8 @@ def lib():
         L.arks_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
         L.arks_stream.restype = vp
         L.arks_stream.argtypes = [vp]
+        L.arks_last_declined.restype = C.c_int64
+        L.arks_last_declined.argtypes = [vp]
         L.arks_launch_count.restype = C.c_uint64
         L.arks_launch_count.argtypes = [vp]
         L.arks_snapshot_quota.argtypes = [vp, abi.i64p]
@@ -92,7 +94,7 @@ EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/t
     "arks_submit_response_batch", "arks_stage_request_batch", "arks_run_request_batch",
     "arks_fetch_request_result", "arks_stage_response_batch", "arks_run_response_batch",
     "arks_fetch_response_result", "arks_submit_request_async", "arks_wait_request", "arks_submit_response_async",
-    "arks_wait_response", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_enable_metrics", "arks_snapshot_metrics", "arks_sync_quota_usage", "arks_alloc_pinned", "arks_free_pinned", "arks_snapshot_quota",
+    "arks_wait_response", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_last_declined", "arks_enable_metrics", "arks_snapshot_metrics", "arks_sync_quota_usage", "arks_alloc_pinned", "arks_free_pinned", "arks_snapshot_quota",
     "arks_set_quota_usage", "arks_incr_quota_usage", "arks_snapshot_rate", "arks_take_quota_delta",
     "arks_apply_quota_delta", "arks_quota_delta_dev", "arks_fold_quota_delta_dev", "arks_enable_quota_sharing",
     "arks_export_quota_delta_dev",
@@ -222,6 +224,11 @@ class Gateway:
     @property
     def stream_handle(self) -> int:
         return int(lib().arks_stream(self._h) or 0)
+
+    @property
+    def last_declined(self) -> int:
+        """rows of the last batch the warp-per-document scan left to the exact engine (-1: the batch took the fused kernels)"""
+        return int(lib().arks_last_declined(self._h))
 
     @property
     def launch_count(self) -> int:

@@ -166,3 +166,48 @@ int hm_work_profile(int kind, const uint8_t* body, size_t len, uint32_t* advance
   return (int)n_win;
 }
 }
+
+// ---- the warp-per-document fast path (arks_b200/csrc/warp_scan.cuh), host driver: 1 = accepted (fields filled), 0 = the
+// document is left to the exact engine ----
+#include "../arks_b200/csrc/warp_scan.cuh"
+extern "C" {
+int hm_fast_request(const uint8_t* body, size_t len, uint32_t* span /* start, rawlen, esc */, int* stream, int* so_present, int* iu) {
+  static thread_local uint32_t tok[kFastMaxTok + 64];
+  FastOut o{};
+  if (len > 0xffffffffu || !fast_scan_host<K_REQ>(body, (uint32_t)len, o, tok)) return 0;
+  span[0] = o.m_start; span[1] = o.m_rawlen; span[2] = o.m_esc;
+  *stream = (int)o.stream3; *so_present = (int)o.so_present; *iu = (int)o.iu3;
+  return 1;
+}
+int hm_fast_response(const uint8_t* body, size_t len, uint32_t* span, int64_t* usage) {
+  static thread_local uint32_t tok[kFastMaxTok + 64];
+  FastOut o{};
+  if (len > 0xffffffffu || !fast_scan_host<K_RESP>(body, (uint32_t)len, o, tok)) return 0;
+  span[0] = o.m_start; span[1] = o.m_rawlen; span[2] = o.m_esc;
+  usage[0] = o.usage[0]; usage[1] = o.usage[1]; usage[2] = o.usage[2];
+  return 1;
+}
+// what the exact engine reports for the same document, in the same terms (raw model span instead of decoded bytes)
+int hm_engine_request_span(const uint8_t* body, size_t len, uint32_t* span, int* stream, int* so_present, int* iu) {
+  static thread_local JsonT m;
+  static thread_local uint32_t stk[kStackWords];
+  static thread_local JsonCold cold;
+  m.init(K_REQ, body, stk, &cold, host_json_tables());
+  feed(m, body, len);
+  if (!m.ok_at_end()) return 0;
+  span[0] = cold.m_rawlen ? cold.m_start : 0; span[1] = cold.m_rawlen; span[2] = cold.m_rawlen ? cold.m_esc : 0;
+  *stream = (int)cold.stream3; *so_present = (int)cold.so_present; *iu = (int)cold.iu3;
+  return 1;
+}
+int hm_engine_response_span(const uint8_t* body, size_t len, uint32_t* span, int64_t* usage) {
+  static thread_local JsonT m;
+  static thread_local uint32_t stk[kStackWords];
+  static thread_local JsonCold cold;
+  m.init(K_RESP, body, stk, &cold, host_json_tables());
+  feed(m, body, len);
+  if (!m.ok_at_end()) return 0;
+  span[0] = cold.m_rawlen ? cold.m_start : 0; span[1] = cold.m_rawlen; span[2] = cold.m_rawlen ? cold.m_esc : 0;
+  usage[0] = cold.usage[0]; usage[1] = cold.usage[1]; usage[2] = cold.usage[2];
+  return 1;
+}
+}

@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "host_machine.cpp")
-HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_common.cuh", "json_engine.cuh", "json_tables.h")]
+HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_common.cuh", "json_engine.cuh", "json_tables.h", "warp_scan.cuh")]
 OUT = os.path.join(ROOT, "tests", "_build", "libhost_machine.so")
 _lib = None
 
@@ -25,6 +25,12 @@ def lib():
         L.hm_parse_response.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), i64p]
         L.hm_parse_sse.argtypes = [C.c_char_p, C.c_size_t, i64p]
         L.hm_parse_sse_split.argtypes = [C.c_char_p, C.c_size_t, i64p]
+        u32p = C.POINTER(C.c_uint32)
+        ip = C.POINTER(C.c_int)
+        L.hm_fast_request.argtypes = [C.c_char_p, C.c_size_t, u32p, ip, ip, ip]
+        L.hm_engine_request_span.argtypes = [C.c_char_p, C.c_size_t, u32p, ip, ip, ip]
+        L.hm_fast_response.argtypes = [C.c_char_p, C.c_size_t, u32p, i64p]
+        L.hm_engine_response_span.argtypes = [C.c_char_p, C.c_size_t, u32p, i64p]
         L.hm_work_profile.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t]
         _lib = L
     return _lib
@@ -71,3 +77,36 @@ def work_profile(body: bytes, kind: int = 0):
     rc = lib().hm_work_profile(kind, body, len(body), a.ctypes.data_as(u32p), e.ctypes.data_as(u32p), len(a))
     assert rc >= 0
     return a[:n], e[:n]
+
+
+def _req(fn, body):
+    span = (C.c_uint32 * 3)()
+    st, so, iu = C.c_int(), C.c_int(), C.c_int()
+    ok = fn(body, len(body), span, C.byref(st), C.byref(so), C.byref(iu))
+    return (tuple(span), st.value, so.value, iu.value) if ok else None
+
+
+def _resp(fn, body):
+    span = (C.c_uint32 * 3)()
+    u = (C.c_int64 * 3)()
+    ok = fn(body, len(body), span, u)
+    return (tuple(span), tuple(u)) if ok else None
+
+
+def fast_request(body: bytes):
+    """the warp-per-document fast path (host driver of warp_scan.cuh): ((start, rawlen, esc), stream3, so_present, iu3) or
+    None when the document is left to the exact engine"""
+    return _req(lib().hm_fast_request, body)
+
+
+def engine_request(body: bytes):
+    """the exact engine in the same terms, None when it rejects the document"""
+    return _req(lib().hm_engine_request_span, body)
+
+
+def fast_response(body: bytes):
+    return _resp(lib().hm_fast_response, body)
+
+
+def engine_response(body: bytes):
+    return _resp(lib().hm_engine_response_span, body)

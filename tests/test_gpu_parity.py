@@ -278,3 +278,47 @@ def test_async_pipelined_submits_match_serial_oracle(gwmod):
     for k, r in enumerate(reqs):
         same(outs[k], o.request_batch(r), f"async batch {k}")
     state_same(g, o, now + 15)
+
+
+def test_two_stage_scan_fuzzed_and_plain_documents(gwmod):
+    """Batches of 4 096 rows and more go through the warp-per-document scan first and the exact engine for what it declines
+    (arks_b200/csrc/warp_scan.cuh). Hostile documents, plain ones and bodies longer than the resident window in ONE batch:
+    the verdicts must not depend on which path a row took, and both paths must have been taken."""
+    w = traffic.Workload(n_tenants=8, seed=1)
+    g, o = pair(gwmod, w.tables, 16384, 48 << 20)
+    gen = Gen(91)
+    rng = np.random.default_rng(91)
+    bodies = [gen.request() for _ in range(5000)]
+    bodies += [traffic.chat_request_body_varied(rng, 900, stream=bool(rng.random() < 0.3)) for _ in range(4000)]
+    bodies += [traffic.chat_request_body(rng, int(s)) for s in rng.integers(1900, 2300, 300)]  # around the 2 KiB window
+    bodies += [b"", b"{}", b'{"model":"qwen-7b"}', traffic.chat_request_body(rng, 70000)]
+    order = rng.permutation(len(bodies))
+    bodies = [bodies[i] for i in order]
+    req = RequestBatch.from_lists(bodies, [w.token_strings[i % 8] for i in range(len(bodies))], NOW,
+                                  pick_rand=rng.integers(0, 1 << 63, len(bodies), dtype=np.uint64))
+    a = g.handle_request_body(req)
+    declined = g.last_declined
+    same(a, o.request_batch(req), "two-stage requests")
+    state_same(g, o, NOW)
+    assert 2000 < declined < len(bodies) - 4000, declined  # the hostile ones went to the exact engine, the plain ones did not
+    # complete response bodies (a homogeneous JSON batch takes the two-stage path too)
+    rb, flags = [], []
+    while len(rb) < 5000:
+        b = gen.response()
+        if not D2.search(b):
+            rb.append(b)
+            flags.append(abi.RESP_END_OF_STREAM if gen.r.random() < 0.97 else 0)
+    for _ in range(4000):
+        rb.append(traffic.chat_response_body_varied(rng, int(rng.integers(50, 401)), int(rng.integers(1, 513)), 600))
+        flags.append(abi.RESP_END_OF_STREAM)
+    order = rng.permutation(len(rb))
+    resp = ResponseBatch.from_lists([rb[i] for i in order], [int(i) % 8 if i % 97 else -1 for i in range(len(rb))], [flags[i] for i in order], NOW + 1)
+    c = g.handle_response_body(resp)
+    declined = g.last_declined
+    same(c, o.response_batch(resp), "two-stage responses")
+    state_same(g, o, NOW + 1)
+    assert 1500 < declined < len(rb) - 3500, declined
+    # the bench workload itself: nothing declined
+    wave = w.request_batch(8192, NOW + 2, seed=5, varied=True)
+    same(g.handle_request_body(wave), o.request_batch(wave), "plain wave")
+    assert g.last_declined == 0
