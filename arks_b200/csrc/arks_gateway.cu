@@ -36,7 +36,7 @@
 
 #include "../../include/arks_gateway.h"
 #include "json_engine.cuh"
-#include "warp_scan.cuh"
+#include "mask_scan.cuh"
 
 using namespace arks;
 
@@ -97,8 +97,7 @@ struct ReqDev {  // request batch, device resident
   int32_t* st_tok;
   int32_t* gslot;  // group slot per request or -1
   int32_t* gnext;  // next (earlier-registered) member of the same group, -1 ends the list
-  // two-stage scan (large batches): parse state per request (PS_*), and the requests left to the exact engine
-  uint8_t* pstate;
+  // two-stage scan (large batches): the requests the fast path (mask_scan.cuh) leaves to the exact engine
   uint32_t* slow_list;
   uint32_t* slow_n;  // [1]
   // group table (batch local): qos -> slot
@@ -137,8 +136,7 @@ struct RespDev {
   uint8_t* reason;
   uint8_t* counted;
   long long* usage;  // 3n
-  uint8_t* pstate;   // two-stage scan: RS_* per response (usage[] holds the extracted counters)
-  uint32_t* slow_list;
+  uint32_t* slow_list;  // two-stage scan: the bodies left to the exact engine
   uint32_t* slow_n;
 };
 
@@ -206,9 +204,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 constexpr uint8_t PS_STREAM = 1;     // "stream": true
 constexpr uint8_t PS_STREAM_OK = 2;  // stream_options.include_usage == true
 constexpr uint8_t PS_BAD = 0x40;     // the body does not decode (400 x-error-request-body-processing)
-constexpr uint8_t PS_SLOW = 0x80;    // left to the exact engine
-// parse state of a complete response body
-constexpr uint8_t RS_OK = 0, RS_UNMARSHAL = 1, RS_NO_MODEL = 2, RS_PENDING = 3, RS_SLOW = 0x80;
 
 __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
   uint4 r;
@@ -526,16 +521,15 @@ __global__ void len_scatter_kernel(const uint32_t* body_len, uint32_t n, uint32_
 // ------------------------------------------------------------------------------------------------
 // kernel 1: scan_request — A3 (body parse), A4 (GetQosByToken), A5 (GetModelList) of SURVEY.md §8a
 // ------------------------------------------------------------------------------------------------
-// PARSE_ONLY: second stage of the two-stage scan — the requests the warp-per-document path left to the exact engine
-// (B.slow_list); only the parse state and the model span are written, resolve_requests_kernel does the rest.
-template <int SCHED, bool PARSE_ONLY>
+// FROM_LIST: second stage of the two-stage scan — the requests the fast path left to the exact engine (B.slow_list).
+template <int SCHED, bool FROM_LIST>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_request_kernel(DevTables T, ReqDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t n = PARSE_ONLY ? *B.slow_n : B.n;
+  const uint32_t n = FROM_LIST ? *B.slow_n : B.n;
   const uint32_t lane_id = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * B.bpw + (threadIdx.x & 31);
-  if (PARSE_ONLY && ((blockIdx.x * blockDim.x) >> 5) * B.bpw >= n) return;  // nothing left for this block
+  if (FROM_LIST && ((blockIdx.x * blockDim.x) >> 5) * B.bpw >= n) return;  // nothing left for this block
   const bool live = (threadIdx.x & 31) < B.bpw && lane_id < n;
-  const uint32_t i = live ? (PARSE_ONLY ? B.slow_list[lane_id] : B.perm ? B.perm[lane_id] : lane_id) : 0;  // the body this lane parses
+  const uint32_t i = live ? (FROM_LIST ? B.slow_list[lane_id] : B.perm ? B.perm[lane_id] : lane_id) : 0;  // the body this lane parses
   const uint8_t* body = B.bodies + (live ? B.body_off[i] : 0);
   const uint32_t len = live ? B.body_len[i] : 0;
 
@@ -548,7 +542,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_request_
   // GetQosByToken does not need the body, so it runs here, while the automaton tables and the first body windows are
   // still in flight.
   int32_t tok = -1;
-  if (!PARSE_ONLY && live) tok = lookup_token(T, B, i);
+  if (live) tok = lookup_token(T, B, i);
   cp_async_wait<kStages - 1>();  // the table group is the oldest one
   __syncthreads();
 
@@ -565,211 +559,71 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_request_
   B.model_off[i] = m_rawlen ? cold.m_start : 0u;
   B.model_len[i] = m_rawlen ? (m_rawlen | (cold.m_esc ? 0x80000000u : 0u)) : 0u;
   B.bpe[i] = 0;
-  if (PARSE_ONLY) B.pstate[i] = pstate;
-  else resolve_request(T, B, i, body, tok, pstate, cold.m_start, m_rawlen, cold.m_esc);
+  resolve_request(T, B, i, body, tok, pstate, cold.m_start, m_rawlen, cold.m_esc);
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel 1': the warp-per-document scan (warp_scan.cuh) — first stage of the two-stage scan of large batches.
-// Every warp takes documents w, w + W, w + 2W, ...; the NEXT document is already on its way into the warp's second
-// shared-memory stage (one 1-D bulk copy, completion on an mbarrier) while the current one is scanned.
+// kernel 1': the fast path (mask_scan.cuh) — first stage of the two-stage scan of large batches. One lane per body, three
+// convergent passes; a body it accepts is decided here (same tail as the exact kernel), a body it declines is appended
+// to B.slow_list for scan_*_kernel<.., FROM_LIST>.
 // ------------------------------------------------------------------------------------------------
-constexpr int kFastWarps = 4;  // warps per block
-struct __align__(128) FastWarpSmem {
-  uint8_t doc[2][kFastMaxLen];          // bulk-copy destinations
-  uint32_t tok[kFastMaxTok + 32];
-  uint32_t bmap[kFastMaxLen / 32];
-  uint64_t bar[2];
-};
-constexpr int kFastSmemPerBlock = kFastWarps * (int)sizeof(FastWarpSmem);
+__device__ __align__(16) const FastTablesInit g_fast_tables{};
+static_assert(sizeof(FastTables) % 16 == 0, "staged with one bulk copy");
+constexpr int kFastThreads = 128;
 
-// exclusive prefix of the lanes' stack effects (Hillis-Steele over effect_compose)
-__device__ __forceinline__ FastEffect warp_effect_prefix(const FastEffect& own, uint32_t lane, uint32_t* total_bad) {
-  FastEffect inc = own;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    FastEffect o;
-    o.npop = __shfl_up_sync(0xffffffffu, inc.npop, d);
-    o.npush = __shfl_up_sync(0xffffffffu, inc.npush, d);
-    o.pword = __shfl_up_sync(0xffffffffu, inc.pword, d);
-    o.bad = __shfl_up_sync(0xffffffffu, inc.bad, d);
-    o.ptypes = 0;
-    if (lane >= (uint32_t)d) inc = effect_compose(o, inc);
-  }
-  *total_bad = __shfl_sync(0xffffffffu, inc.bad, 31);
-  FastEffect pre;
-  pre.npop = __shfl_up_sync(0xffffffffu, inc.npop, 1);
-  pre.npush = __shfl_up_sync(0xffffffffu, inc.npush, 1);
-  pre.pword = __shfl_up_sync(0xffffffffu, inc.pword, 1);
-  pre.bad = 0;
-  pre.ptypes = 0;
-  if (lane == 0) pre.npop = pre.npush = pre.pword = 0;
-  return pre;
-}
-
-// one document, whole warp; true = accepted, `out` valid on every lane
-template <int KIND>
-__device__ __forceinline__ bool fast_scan_doc(const uint8_t* doc, uint32_t len, FastWarpSmem& sm, FastOut& out) {
-  const uint32_t lane = threadIdx.x & 31;
-  uint32_t ntok = 0, carry_esc = 0, carry_str = 0;
-  bool bad = false;
-  for (uint32_t seg = 0; seg * kFastSeg < len; seg++) {
-    const uint32_t base = seg * kFastSeg + 32u * lane;
-    FastMasks m;
-    {
-      const uint4* p = reinterpret_cast<const uint4*>(doc + base);
-      uint4 a = make_uint4(0, 0, 0, 0), b = a;
-      if (base < len) { a = p[0]; b = p[1]; }
-      m.w[0] = a.x; m.w[1] = a.y; m.w[2] = a.z; m.w[3] = a.w;
-      m.w[4] = b.x; m.w[5] = b.y; m.w[6] = b.z; m.w[7] = b.w;
-    }
-    fast_masks(m, base < len ? min(len - base, 32u) : 0u);
-    const bool allbs = m.B == 0xffffffffu;  // 32 backslashes in a row: exact engine
-    const uint32_t co = odd_tail(m.B);
-    uint32_t prev = __shfl_up_sync(0xffffffffu, co, 1);
-    if (lane == 0) prev = carry_esc;
-    carry_esc = __shfl_sync(0xffffffffu, co, 31);
-    const uint32_t E = find_escaped(m.B, prev);
-    const uint32_t Qu = m.Q & ~E;
-    const uint32_t pm = __ballot_sync(0xffffffffu, __popc(Qu) & 1);
-    const uint32_t inside = ((uint32_t)__popc(pm & ((1u << lane) - 1u)) & 1u) ^ carry_str;
-    carry_str ^= (uint32_t)__popc(pm) & 1u;
-    const uint32_t R = prefix_xor32(Qu) ^ (inside ? 0xffffffffu : 0u);
-    sm.bmap[seg * 32 + lane] = m.B;
-    const bool ok = !allbs && fast_string_checks(doc, len, base, m, E, R);
-    const uint32_t TB = m.V & ~(R & ~Qu);
-    const uint32_t cnt = (uint32_t)__popc(TB);
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= (uint32_t)d) incl += o;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    if (__any_sync(0xffffffffu, !ok) || ntok + total > kFastMaxTok) { bad = true; break; }
-    fast_emit(doc, base, TB, Qu, R, sm.tok, ntok + incl - cnt);
-    ntok += total;
-  }
-  __syncwarp();
-  if (bad || carry_str || ntok == 0) return false;
-  const int c = (int)((ntok + 31) / 32);
-  const int k0 = min((int)lane * c, (int)ntok), k1 = min(k0 + c, (int)ntok);
-  FastEffect eff{0, 0, 0, 0, 0};
-  for (int k = k0; k < k1; k++) effect_token(eff, sm.tok[k]);
-  uint32_t total_bad;
-  const FastEffect pre = warp_effect_prefix(eff, lane, &total_bad);
-  FastFound f;
-  f.n_model = f.n_stream = f.n_so = f.n_iu = f.n_usage = f.n_u[0] = f.n_u[1] = f.n_u[2] = f.bad = 0;
-  f.o.m_start = f.o.m_rawlen = f.o.m_esc = f.o.stream3 = f.o.so_present = f.o.iu3 = 0;
-  f.o.usage[0] = f.o.usage[1] = f.o.usage[2] = 0;
-  bool ok = !total_bad;
-  if (ok && k0 < k1) ok = pre.npop == 0 && fast_walk_chunk<KIND>(doc, sm.bmap, sm.tok, k0, k1, (int)ntok, pre.npush, pre.pword, eff, f);
-  ok = ok && f.n_model <= 1 && f.n_stream <= 1 && f.n_so <= 1 && f.n_iu <= 1 && f.n_usage <= 1 && f.n_u[0] <= 1 && f.n_u[1] <= 1 && f.n_u[2] <= 1;
-  if (__any_sync(0xffffffffu, !ok)) return false;
-  // every member at most once in the whole document; its finder hands the value to everybody
-  const uint32_t bm = __ballot_sync(0xffffffffu, f.n_model), bs = __ballot_sync(0xffffffffu, f.n_stream),
-                 bo = __ballot_sync(0xffffffffu, f.n_so), bu = __ballot_sync(0xffffffffu, f.n_usage);
-  if (__popc(bm) > 1 || __popc(bs) > 1 || __popc(bo) > 1 || __popc(bu) > 1) return false;
-  const int lm = bm ? __ffs(bm) - 1 : 0, ls = bs ? __ffs(bs) - 1 : 0, lo = bo ? __ffs(bo) - 1 : 0, lu = bu ? __ffs(bu) - 1 : 0;
-  out.m_start = __shfl_sync(0xffffffffu, f.o.m_start, lm);
-  out.m_rawlen = __shfl_sync(0xffffffffu, f.o.m_rawlen, lm);
-  out.m_esc = __shfl_sync(0xffffffffu, f.o.m_esc, lm);
-  if (KIND == K_REQ) {
-    out.stream3 = __shfl_sync(0xffffffffu, f.o.stream3, ls);
-    out.so_present = __shfl_sync(0xffffffffu, f.o.so_present, lo);
-    out.iu3 = __shfl_sync(0xffffffffu, f.o.iu3, lo);
-  } else {
-#pragma unroll
-    for (int q = 0; q < 3; q++) out.usage[q] = __shfl_sync(0xffffffffu, f.o.usage[q], lu);
-  }
-  return true;
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(kFastWarps * 32) fast_scan_kernel(ReqDev Q, RespDev P) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  FastWarpSmem& sm = reinterpret_cast<FastWarpSmem*>(smem)[warp];
-  const uint8_t* bodies = KIND == K_REQ ? Q.bodies : P.bodies;
-  const uint32_t* body_off = KIND == K_REQ ? Q.body_off : P.body_off;
-  const uint32_t* body_len = KIND == K_REQ ? Q.body_len : P.body_len;
-  const uint32_t n = KIND == K_REQ ? Q.n : P.n;
-  const uint32_t stride = gridDim.x * kFastWarps;
-  if (lane == 0) {
-    mbar_init(&sm.bar[0], 1);
-    mbar_init(&sm.bar[1], 1);
+// the grammar tables of mask_scan.cuh into shared memory: ONE 1-D bulk copy (TMA) per block, completion on an mbarrier
+__device__ __forceinline__ void stage_fast_tables(FastTables* dst, uint64_t* bar) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, (uint32_t)sizeof(FastTables));
+    bulk_g2s(dst, &g_fast_tables.t, (uint32_t)sizeof(FastTables), bar);
   }
-  __syncwarp();
-  // a document takes the fast path only if it fits the resident window; complete bodies only (pending chunks: nothing to do)
-  auto eligible = [&](uint32_t i, uint32_t* len) {
-    *len = body_len[i];
-    if (KIND == K_RESP && !(P.flags[i] & ARKS_RESP_END_OF_STREAM)) return false;
-    if (KIND == K_RESP && P.qos[i] < 0) return false;
-    return *len > 0 && *len <= kFastMaxLen;
-  };
-  auto issue = [&](uint32_t i, int st) {  // lane 0 only
-    uint32_t len;
-    if (i < n && eligible(i, &len)) {
-      const uint32_t bytes = (len + 15u) & ~15u;
-      fence_proxy_async();
-      mbar_expect_tx(&sm.bar[st], bytes);
-      bulk_g2s(sm.doc[st], bodies + body_off[i], bytes, &sm.bar[st]);
-    }
-  };
-  uint32_t i = blockIdx.x * kFastWarps + warp;
-  uint32_t phase[2] = {0, 0};
-  int st = 0;
-  if (lane == 0) issue(i, 0);
-  for (; i < n; i += stride, st ^= 1) {
-    __syncwarp();  // everybody is done with the other stage (the previous document)
-    if (lane == 0) issue(i + stride, st ^ 1);
-    uint32_t len;
-    const bool elig = eligible(i, &len);
-    bool ok = false;
-    FastOut o;
-    if (elig) {
-      mbar_wait(&sm.bar[st], phase[st]);
-      phase[st] ^= 1;
-      ok = fast_scan_doc<KIND>(sm.doc[st], len, sm, o);
-    }
-    if (lane == 0) {
-      if (KIND == K_REQ) {
-        if (ok) {
-          Q.pstate[i] = (uint8_t)((o.stream3 == 2 ? PS_STREAM : 0) | (o.so_present && o.iu3 == 2 ? PS_STREAM_OK : 0));
-          Q.model_off[i] = o.m_rawlen ? o.m_start : 0u;
-          Q.model_len[i] = o.m_rawlen ? (o.m_rawlen | (o.m_esc ? 0x80000000u : 0u)) : 0u;
-          Q.bpe[i] = 0;
-        } else {
-          Q.pstate[i] = PS_SLOW;
-          Q.slow_list[atomicAdd(Q.slow_n, 1u)] = i;
-        }
-      } else {
-        if (!(P.flags[i] & ARKS_RESP_END_OF_STREAM) || P.qos[i] < 0) {
-          P.pstate[i] = RS_PENDING;  // handle_response.go:141-149 (or a row without a qos entry: account_kernel answers it)
-        } else if (ok) {
-          P.pstate[i] = o.m_rawlen ? RS_OK : RS_NO_MODEL;
-          P.usage[3 * (size_t)i + 0] = o.usage[0];
-          P.usage[3 * (size_t)i + 1] = o.usage[1];
-          P.usage[3 * (size_t)i + 2] = o.usage[2];
-        } else {
-          P.pstate[i] = RS_SLOW;
-          P.slow_list[atomicAdd(P.slow_n, 1u)] = i;
-        }
-      }
-    }
-  }
+  __syncthreads();        // the barrier is initialised before anybody polls it
+  mbar_wait(bar, 0);
 }
 
-// second stage for requests: token lookup, qos / endpoint match, static decision and group registration, one thread per
-// request (the fused kernel does the same in its tail)
-__global__ void __launch_bounds__(128) resolve_requests_kernel(DevTables T, ReqDev B) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B.n) return;
-  const uint8_t ps = B.pstate[i];
-  const uint32_t ml = B.model_len[i];
-  const int32_t tok = (ps & PS_BAD) || (ml & 0x7fffffffu) == 0 ? -1 : lookup_token(T, B, i);
-  resolve_request(T, B, i, B.bodies + B.body_off[i], tok, ps, B.model_off[i], ml & 0x7fffffffu, ml >> 31);
+// passes A-C for the body of one lane; false: declined (or not eligible)
+template <int KIND>
+__device__ __forceinline__ bool fast_scan_lane(const uint8_t* body, uint32_t len, const FastTables& tabs, FastScratch& s, FastOut& o) {
+  if (len == 0 || len > kFastMaxLen) return false;
+  const uint32_t nch = (len + 31) >> 5, plen = (len + 15u) & ~15u;
+  FastCarry c{0, 0, 0};
+  const uint4* p = reinterpret_cast<const uint4*>(body);
+  for (uint32_t j = 0; j < nch; j++) {
+    const uint4 a = ld_nc_v4(p + 2 * j);
+    uint4 b = make_uint4(0, 0, 0, 0);
+    if (32 * j + 16 < plen) b = ld_nc_v4(p + 2 * j + 1);  // never read past the body's 16-byte padding
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    fast_chunk(w, min(len - 32 * j, 32u), body, len, 32 * j, c, &s.tb[j], &s.bm[j]);
+  }
+  if (c.bad || c.in_str) return false;
+  const int nmem = fast_walk(body, tabs, s, nch);
+  if (nmem < 0) return false;
+  return fast_members<KIND>(body, s, nch, nmem, o);
+}
+
+__global__ void __launch_bounds__(kFastThreads) fast_request_kernel(DevTables T, ReqDev B) {
+  __shared__ __align__(128) FastTables tabs;
+  __shared__ uint64_t bar;
+  stage_fast_tables(&tabs, &bar);
+  const uint32_t lane_id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane_id >= B.n) return;
+  const uint32_t i = B.perm ? B.perm[lane_id] : lane_id;
+  const uint8_t* body = B.bodies + B.body_off[i];
+  const uint32_t len = B.body_len[i];
+  FastScratch s;
+  FastOut o;
+  if (!fast_scan_lane<K_REQ>(body, len, tabs, s, o)) {
+    B.slow_list[atomicAdd(B.slow_n, 1u)] = i;
+    return;
+  }
+  B.model_off[i] = o.m_rawlen ? o.m_start : 0u;
+  B.model_len[i] = o.m_rawlen ? (o.m_rawlen | (o.m_esc ? 0x80000000u : 0u)) : 0u;
+  B.bpe[i] = 0;
+  const uint8_t pstate = (uint8_t)((o.stream3 == 2 ? PS_STREAM : 0) | (o.so_present && o.iu3 == 2 ? PS_STREAM_OK : 0));
+  const int32_t tok = o.m_rawlen ? lookup_token(T, B, i) : -1;
+  resolve_request(T, B, i, body, tok, pstate, o.m_start, o.m_rawlen, o.m_esc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1044,16 +898,15 @@ __device__ __forceinline__ void account_usage(const DevTables& T, const RespDev&
 }
 
 // complete (non-stream) response bodies: one JSON document per lane.
-// PARSE_ONLY: second stage of the two-stage scan (the bodies in B.slow_list); only the parse state and the counters are
-// written, account_responses_kernel does A11.
-template <int SCHED, bool PARSE_ONLY>
+// FROM_LIST: second stage of the two-stage scan (the bodies in B.slow_list).
+template <int SCHED, bool FROM_LIST>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response_kernel(DevTables T, RespDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t n = PARSE_ONLY ? *B.slow_n : B.n;
+  const uint32_t n = FROM_LIST ? *B.slow_n : B.n;
   const uint32_t lane_id = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * B.bpw + (threadIdx.x & 31);
-  if (PARSE_ONLY && ((blockIdx.x * blockDim.x) >> 5) * B.bpw >= n) return;
+  if (FROM_LIST && ((blockIdx.x * blockDim.x) >> 5) * B.bpw >= n) return;
   const bool live = (threadIdx.x & 31) < B.bpw && lane_id < n;
-  const uint32_t i = live ? (PARSE_ONLY ? B.slow_list[lane_id] : B.perm ? B.perm[lane_id] : lane_id) : 0;  // the body this lane parses
+  const uint32_t i = live ? (FROM_LIST ? B.slow_list[lane_id] : B.perm ? B.perm[lane_id] : lane_id) : 0;  // the body this lane parses
   uint8_t reason = ARKS_R_OK, counted = 0;
   long long u0 = 0, u1 = 0, u2 = 0;
   int32_t qos = 0;
@@ -1069,7 +922,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response
     const JsonTables tabs = json_smem.stage_async();
     WindowPipe<kStages> pipe;
     pipe.start(body, len, smem + (threadIdx.x >> 5) * (kStages * kStageBytes));
-    if (!PARSE_ONLY) acct = load_qos_acct(T, qos, live && qos >= 0);  // global latency chain, hidden behind the copies issued above
+    acct = load_qos_acct(T, qos, live && qos >= 0);  // global latency chain, hidden behind the copies issued above
     cp_async_wait<kStages - 1>();        // the table group is the oldest one
     __syncthreads();
     JsonCold cold;  // rarely touched parse state: local memory on purpose (json_engine.cuh)
@@ -1084,31 +937,39 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response
       counted = reason == ARKS_R_OK && u2 != 0;  // :186
     }
   }
-  if (PARSE_ONLY) {
-    if (!live) return;
-    B.pstate[i] = reason == ARKS_R_OK ? RS_OK : reason == ARKS_R_RESPONSE_UNMARSHAL ? RS_UNMARSHAL : reason == ARKS_R_PENDING ? RS_PENDING : RS_NO_MODEL;
-    B.usage[3 * (size_t)i + 0] = u0;
-    B.usage[3 * (size_t)i + 1] = u1;
-    B.usage[3 * (size_t)i + 2] = u2;
-    return;
-  }
   account_usage(T, B, i, live, qos, acct, reason, counted, u0, u1, u2);
 }
 
-// second stage for complete response bodies: A11 (doTokenRateLimit / doTokenQuotaLimit) from the parse state, one thread per
-// response, warp-aggregated atomics as in the fused kernel
-__global__ void __launch_bounds__(128) account_responses_kernel(DevTables T, RespDev B) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < B.n;
-  const uint32_t ii = live ? i : 0;
-  const int32_t qos = live ? B.qos[ii] : 0;
-  const uint8_t ps = live ? B.pstate[ii] : RS_PENDING;
-  const QosAcct acct = load_qos_acct(T, qos, live && qos >= 0);
-  uint8_t reason = ps == RS_OK ? ARKS_R_OK : ps == RS_UNMARSHAL ? ARKS_R_RESPONSE_UNMARSHAL : ps == RS_NO_MODEL ? ARKS_R_RESPONSE_UNKNOWN : ARKS_R_PENDING;
+// the fast path for complete response bodies: first stage of the two-stage scan (see fast_request_kernel)
+__global__ void __launch_bounds__(kFastThreads) fast_response_kernel(DevTables T, RespDev B) {
+  __shared__ __align__(128) FastTables tabs;
+  __shared__ uint64_t bar;
+  stage_fast_tables(&tabs, &bar);
+  const uint32_t lane_id = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = lane_id < B.n;
+  const uint32_t i = in ? (B.perm ? B.perm[lane_id] : lane_id) : 0;
+  const int32_t qos = in ? B.qos[i] : 0;
+  const uint8_t fl = in ? B.flags[i] : ARKS_RESP_END_OF_STREAM;
+  const bool pending = !(fl & ARKS_RESP_END_OF_STREAM);
+  uint8_t reason = ARKS_R_OK, counted = 0;
   long long u0 = 0, u1 = 0, u2 = 0;
-  if (live && ps == RS_OK) { u0 = B.usage[3 * (size_t)ii]; u1 = B.usage[3 * (size_t)ii + 1]; u2 = B.usage[3 * (size_t)ii + 2]; }
-  const uint8_t counted = reason == ARKS_R_OK && u2 != 0;  // handle_response.go:186
-  account_usage(T, B, ii, live, qos, acct, reason, counted, u0, u1, u2);
+  bool live = in;
+  if (in && !pending && qos >= 0) {
+    FastScratch s;
+    FastOut o;
+    if (fast_scan_lane<K_RESP>(B.bodies + B.body_off[i], B.body_len[i], tabs, s, o)) {
+      if (o.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // handle_response.go:167-181
+      else { u0 = o.usage[0]; u1 = o.usage[1]; u2 = o.usage[2]; }
+      counted = reason == ARKS_R_OK && u2 != 0;               // :186
+    } else {
+      B.slow_list[atomicAdd(B.slow_n, 1u)] = i;  // the exact engine decides (and accounts) this one
+      live = false;
+    }
+  } else if (in && pending) {
+    reason = ARKS_R_PENDING;  // :141-149 (a row without a qos entry: account_usage answers ARKS_R_QOS_GONE)
+  }
+  const QosAcct acct = load_qos_acct(T, qos, live && qos >= 0);
+  account_usage(T, B, i, live, qos, acct, reason, counted, u0, u1, u2);  // all 32 lanes: warp-aggregated atomics inside
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1338,7 +1199,7 @@ struct arks_ctx {
                              // 1 consume_evsync, 8 consume_rounds<8> (json_engine.cuh). ARKS_SCHED="r,p,s" overrides (A/B runs)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int ev_n = 0;
-  cudaEvent_t ev_fast[2] = {nullptr, nullptr};  // around the warp-per-document kernel alone (roofline of the dominant kernel)
+  cudaEvent_t ev_fast[2] = {nullptr, nullptr};  // around the fast-path kernel alone (roofline of the dominant kernel)
   bool ev_fast_set = false;
   bool last_two_stage = false;
   uint8_t* d_inter = nullptr;    // intermediates + group table
@@ -1347,8 +1208,7 @@ struct arks_ctx {
   bool sort_lanes = true;        // ARKS_SORT=0 scans in arrival order (A/B runs)
   bool fast_scan = true;         // ARKS_FAST=0: large batches also take the fused lane-per-document kernels (A/B runs)
   int n_sm = 148;
-  uint32_t* d_slow = nullptr;    // [0] counter, [64..] the rows left to the exact engine by the warp-per-document scan
-  uint8_t* d_pstate = nullptr;   // parse state per row between the two stages
+  uint32_t* d_slow = nullptr;    // [0] counter, [64..] the rows left to the exact engine by the fast path (mask_scan.cuh)
   uint8_t* d_result = nullptr;   // packed results
   size_t result_cap = 0;
   uint32_t gsize = 0;
@@ -1443,8 +1303,6 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaFuncSetAttribute(scan_sse_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSseSmemPerBlock));
   ARKS_FOR_SCHED(ARKS_SET)
 #undef ARKS_SET
-  CK(cudaFuncSetAttribute(fast_scan_kernel<K_REQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemPerBlock));
-  CK(cudaFuncSetAttribute(fast_scan_kernel<K_RESP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemPerBlock));
   if (const char* e = getenv("ARKS_FAST")) ctx->fast_scan = e[0] != '0';
   {
     cudaDeviceProp prop;
@@ -1459,7 +1317,7 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaMalloc(&ctx->d_inter, inter));
   CK(cudaMalloc(&ctx->d_perm, (size_t)4 * max_batch + 256));
   CK(cudaMalloc(&ctx->d_slow, (size_t)4 * max_batch + 256));
-  CK(cudaMalloc(&ctx->d_pstate, (size_t)max_batch + 256));
+
   CK(cudaMalloc(&ctx->d_lenhist, (size_t)4 * kLenBuckets));
   ctx->result_cap = align_up(n, 256) * 3 + align_up(n * 4, 256) * 6 + align_up(n * 8, 256) * 3;
   CK(cudaMalloc(&ctx->d_result, ctx->result_cap));
@@ -1507,7 +1365,7 @@ void arks_destroy(arks_ctx* ctx) {
   cudaFree(ctx->d_inter);
   cudaFree(ctx->d_perm);
   cudaFree(ctx->d_slow);
-  cudaFree(ctx->d_pstate);
+
   cudaFree(ctx->d_lenhist);
   cudaFree(ctx->d_result);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1865,7 +1723,7 @@ int arks_last_kernel_ms(arks_ctx* ctx, float* ms, int cap) {
   CK(cudaStreamSynchronize(ctx->stream));
   int n = ctx->ev_n > 0 ? ctx->ev_n - 1 : 0;
   for (int k = 0; k < n && k < cap; k++) CK(cudaEventElapsedTime(&ms[k], ctx->ev[k], ctx->ev[k + 1]));
-  if (ctx->ev_fast_set && n < cap) {  // one more entry: the warp-per-document kernel of the two-stage scan on its own
+  if (ctx->ev_fast_set && n < cap) {  // one more entry: the fast-path kernel of the two-stage scan on its own
     CK(cudaEventElapsedTime(&ms[n], ctx->ev_fast[0], ctx->ev_fast[1]));
     n++;
   }
@@ -1975,15 +1833,10 @@ static uint32_t scan_grid(uint32_t n, uint32_t bpw) { return ((n + bpw - 1) / bp
 
 // batches below this size are a handful of warps: the three small launches would cost more than they save
 constexpr uint32_t kSortMinBatch = 4096;
-// from this size on requests / complete response bodies go through the two-stage scan (warp per document first); below it
-// the fused lane-per-document kernel is one launch and the SMs are mostly idle anyway
+// from this size on requests / complete response bodies go through the two-stage scan (mask_scan.cuh first); below it
+// the exact kernel alone is one launch and spreads the few bodies over more warps (bodies_per_warp)
 constexpr uint32_t kFastMinBatch = 4096;
-// persistent-style grid of the warp-per-document scan: enough blocks to fill every SM (6 resident blocks of 4 warps), fewer
-// for batches that do not have that many documents
-static uint32_t fast_grid(const arks_ctx* ctx, uint32_t n) {
-  const uint32_t full = (uint32_t)ctx->n_sm * 6u, need = (n + kFastWarps - 1) / kFastWarps;
-  return need < full ? need : full;
-}
+
 // queue the counting sort by body length; returns the permutation (device pointer) or null when the batch is scanned as is
 static const uint32_t* queue_length_order(arks_ctx* ctx, const uint32_t* d_body_len, uint32_t n) {
   if (!ctx->sort_lanes || n < kSortMinBatch) return nullptr;
@@ -2021,17 +1874,15 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   r.hot_n = r.gkey + 3 * (size_t)g;  // one more word: the hot-group counter, also starting at -1
   CK(cudaMemsetAsync(r.gkey, 0xff, (size_t)g * 12 + 4, ctx->stream));
   const uint32_t tpb = kWarpsPerBlock * 32;
-  r.pstate = ctx->d_pstate;
   r.slow_n = ctx->d_slow;
   r.slow_list = ctx->d_slow + 64;
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   if (ctx->fast_scan && n >= kFastMinBatch) {
-    // two-stage scan: a warp per document (warp_scan.cuh) for everything plain, the exact engine for what it declines,
-    // then one thread per request for the table lookups
+    // two-stage scan: the fast path (mask_scan.cuh) decides everything plain, the exact engine what it declines
     CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
-    RespDev none{};
+    r.perm = queue_length_order(ctx, r.body_len, n);
     if (ctx->prof) CK(cudaEventRecord(ctx->ev_fast[0], ctx->stream));
-    fast_scan_kernel<K_REQ><<<fast_grid(ctx, n), kFastWarps * 32, kFastSmemPerBlock, ctx->stream>>>(r, none);
+    fast_request_kernel<<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, 0, ctx->stream>>>(ctx->dt, r);
     if (ctx->prof) { CK(cudaEventRecord(ctx->ev_fast[1], ctx->stream)); ctx->ev_fast_set = true; }
     r.perm = nullptr;
     r.bpw = 32;
@@ -2040,8 +1891,7 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
       ARKS_FOR_SCHED(ARKS_LAUNCH)
 #undef ARKS_LAUNCH
     }
-    resolve_requests_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dt, r);
-    ctx->launches += 2;
+    ctx->launches += 1;
     ctx->last_two_stage = true;
   } else {
     r.perm = queue_length_order(ctx, r.body_len, n);
@@ -2237,24 +2087,22 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
     }
   };
   auto launch_json_two_stage = [&](RespDev rp) -> int {
-    rp.pstate = ctx->d_pstate;
     rp.slow_n = ctx->d_slow;
     rp.slow_list = ctx->d_slow + 64;
+    CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
+    rp.perm = queue_length_order(ctx, rp.body_len, rp.n);
+    if (ctx->prof) CK(cudaEventRecord(ctx->ev_fast[0], ctx->stream));
+    fast_response_kernel<<<(rp.n + kFastThreads - 1) / kFastThreads, kFastThreads, 0, ctx->stream>>>(ctx->dt, rp);
+    if (ctx->prof) { CK(cudaEventRecord(ctx->ev_fast[1], ctx->stream)); ctx->ev_fast_set = true; }
     rp.perm = nullptr;
     rp.bpw = 32;
-    CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
-    ReqDev none{};
-    if (ctx->prof) CK(cudaEventRecord(ctx->ev_fast[0], ctx->stream));
-    fast_scan_kernel<K_RESP><<<fast_grid(ctx, rp.n), kFastWarps * 32, kFastSmemPerBlock, ctx->stream>>>(none, rp);
-    if (ctx->prof) { CK(cudaEventRecord(ctx->ev_fast[1], ctx->stream)); ctx->ev_fast_set = true; }
     const dim3 grid(scan_grid(rp.n, rp.bpw));
     switch (ctx->sched[1]) {
 #define ARKS_LAUNCH(S) case S: scan_response_kernel<S, true><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, rp); break;
       ARKS_FOR_SCHED(ARKS_LAUNCH)
 #undef ARKS_LAUNCH
     }
-    account_responses_kernel<<<(rp.n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dt, rp);
-    ctx->launches += 2;
+    ctx->launches += 1;
     ctx->last_two_stage = true;
     return 0;
   };

@@ -1,0 +1,454 @@
+// mask_scan.cuh — the fast path of the scan kernels: one lane per document, two CONVERGENT passes (device, sm_100a; host
+// build for tests).
+//
+// json_engine.cuh walks every document through one loop that mixes string skipping, table steps and member hooks, window
+// by window: 32 different documents per warp then execute the union of their code paths and wait for the densest one in
+// every 128-byte window (ncu, round 1: 10.6 of 32 lanes per instruction, 2.7 % of the HBM roofline). A warp-per-document
+// formulation (token-balanced, prefix scans across lanes) was built and measured first: correct, but 0.57 ms per 65 536
+// requests — its serial single-lane sections and warp collectives cost more than they saved. This file keeps a lane per
+// document and instead makes every loop body the same for every lane, whatever its document looks like:
+//
+//   pass A  (32 bytes per step, branch-free)  quote / backslash byte masks (SWAR) -> escaped characters (carry in a
+//           register) -> in-string mask (prefix XOR) -> string content checks -> the bitmap of bytes OUTSIDE strings goes to
+//           a per-lane array. Same instructions for prose, escapes, UTF-8, structure.
+//   pass B  one table step per byte outside strings (a few hundred per KiB of chat JSON, not per byte of text):
+//           class = CLS[byte]; entry = TAB[state][class] -> next state, push / pop / comma actions on a 32-level bit stack,
+//           and three flags that log the members of the top-level object (key span, first byte of the value).
+//   pass C  the logged members are matched against the names the gateway reads and their values extracted; the
+//           stream_options / usage objects are read by a short token walk.
+//   Lanes only differ in trip counts (document length in A, structure bytes in B, members in C); the batch is ordered by
+//   length so that the lanes of a warp get similar ones.
+//
+// This path is a FILTER in front of the exact engine, not a second definition of the decoders: it accepts a document only
+// if it lies in a conservative subset on which json-iterator (and encoding/json) agree with RFC 8259 — no control bytes
+// in strings, valid escapes, RFC numbers and literals, depth <= 32, the top-level value an object, at most kFastMaxLen
+// bytes, the members the gateway reads of the expected JSON type, not duplicated and spelled without escapes. Anything
+// else (every malformed or unusual document) is handed to json_engine.cuh's automaton, which restates the reference's
+// decoders quirk by quirk; so verdicts never depend on which path ran (fuzzed against the engine and the oracle:
+// tests/test_mask_scan.py). One theoretical difference: json-iterator matches struct fields by a 64-bit hash of the
+// lower-cased key; this path compares the bytes, so a different key colliding with a field's hash (2^-64) is not matched.
+#pragma once
+#include "json_common.cuh"
+
+namespace arks {
+
+constexpr uint32_t kFastMaxLen = 2048;             // longer documents: exact engine
+constexpr uint32_t kFastChunks = kFastMaxLen / 32;
+constexpr uint32_t kFastMaxMembers = 24;           // members of the top-level object that are logged
+constexpr uint32_t kFastMiniCap = 192;             // structure bytes read inside stream_options / usage
+
+struct FastOut {
+  uint32_t m_start, m_rawlen, m_esc;  // raw span of the model string (0 / 0 / 0: null or absent)
+  uint32_t stream3, so_present, iu3;  // K_REQ tri-states: 0 nil, 1 false, 2 true
+  int64_t usage[3];                   // K_RESP
+};
+
+// per-lane scratch between the passes (local memory on the device: arrays indexed by the loop counter)
+struct FastScratch {
+  uint32_t tb[kFastChunks];  // bytes outside strings (quotes included)
+  uint32_t bm[kFastChunks];  // backslashes
+  uint32_t mem[kFastMaxMembers * 3];  // key pos, key len, value pos of the top-level members
+};
+
+// ---- byte-plane SWAR: bit 7 of every byte that is zero, exact ----
+ARKS_HD uint32_t zero_bytes(uint32_t x) { return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u; }
+ARKS_HD uint32_t plane_nibble(uint32_t t) { return ((t >> 7) * 0x01020408u) >> 24; }  // the 4 flag bits as a nibble
+
+// characters escaped by a backslash (simdjson's find_escaped on 32-bit words); prev: the first byte is escaped from before
+ARKS_HD uint32_t find_escaped(uint32_t bs, uint32_t prev) {
+  bs &= ~prev;
+  const uint32_t follows = (bs << 1) | prev;
+  const uint32_t even = 0x55555555u;
+  const uint32_t odd_starts = bs & ~even & ~follows;
+  const uint32_t invert = (odd_starts + bs) << 1;
+  return (even ^ invert) & follows;
+}
+ARKS_HD uint32_t prefix_xor32(uint32_t x) {
+  x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
+  return x;
+}
+ARKS_HD uint32_t popc32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return (uint32_t)__popc(x);
+#else
+  return (uint32_t)__builtin_popcount(x);
+#endif
+}
+ARKS_HD uint32_t clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return (uint32_t)__clz((int)x);
+#else
+  return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
+}
+
+// ---- pass A: one 32-byte chunk. w: the bytes as 8 little-endian words; carries live in the caller's registers ----
+struct FastCarry {
+  uint32_t esc;     // the next chunk's first byte is escaped
+  uint32_t in_str;  // the next chunk starts inside a string
+  uint32_t bad;
+};
+ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const uint8_t* doc, uint32_t len, uint32_t base, FastCarry& c,
+                        uint32_t* tb_out, uint32_t* bm_out) {
+  uint32_t Q = 0, B = 0, anyc = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 0; j < 8; j++) {
+    const uint32_t x = w[j];
+    Q |= plane_nibble(zero_bytes(x ^ 0x22222222u)) << (4 * j);
+    B |= plane_nibble(zero_bytes(x ^ 0x5c5c5c5cu)) << (4 * j);
+    anyc |= zero_bytes(x & 0xe0e0e0e0u);
+  }
+  const uint32_t V = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+  Q &= V;
+  B &= V;
+  // a backslash run that fills the whole chunk keeps the carry as it is (32 is even); otherwise the carry out is the
+  // parity of the run that touches the chunk's end (its first backslash cannot be escaped: something else precedes it)
+  const uint32_t E = find_escaped(B, c.esc);
+  c.esc = B == 0xffffffffu ? c.esc : (clz32(~B) & 1u);
+  const uint32_t Qu = Q & ~E;
+  const uint32_t R = prefix_xor32(Qu) ^ (c.in_str ? 0xffffffffu : 0u);  // inside a string, opening quote included
+  c.in_str ^= popc32(Qu) & 1u;
+  uint32_t bad = B & ~R;  // a backslash outside a string
+  if (anyc) {             // rare: some byte < 0x20 in the chunk; inside a string it takes the document off this path
+    uint32_t C = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int j = 0; j < 8; j++) C |= plane_nibble(zero_bytes(w[j] & 0xe0e0e0e0u)) << (4 * j);
+    bad |= C & V & R;
+  }
+  uint32_t e = E & V;
+  while (e) {  // rare: what follows each backslash must be an escape RFC 8259 knows
+    const uint32_t p = base + first_set(e);
+    e &= e - 1;
+    const uint8_t ch = doc[p];
+    if (ch == 'u') {
+      if (p + 4 >= len || (hexval(doc[p + 1]) | hexval(doc[p + 2]) | hexval(doc[p + 3]) | hexval(doc[p + 4])) < 0) bad = 1;
+    } else if (!(ch == '"' || ch == '\\' || ch == '/' || ch == 'b' || ch == 'f' || ch == 'n' || ch == 'r' || ch == 't')) {
+      bad = 1;
+    }
+  }
+  c.bad |= bad;
+  *tb_out = V & ~(R & ~Qu);
+  *bm_out = B;
+}
+
+// ---- pass B: the grammar as a table ----
+enum : uint32_t {
+  G_TOP = 0, G_VAL, G_ARR0, G_OBJ0, G_KEY, G_COLON, G_AFTER, G_STRK, G_STRV,
+  G_T1, G_T2, G_T3, G_F1, G_F2, G_F3, G_F4, G_N1, G_N2, G_N3,   // literals in progress
+  G_NM, G_NZ, G_NI, G_ND, G_NF, G_NE, G_NS, G_NX,               // RFC 8259 number
+  G_ERR, G_NSTATES
+};
+enum : uint32_t {
+  C_QUOTE = 0, C_LBRACE, C_RBRACE, C_LBRACK, C_RBRACK, C_COLON, C_COMMA, C_WS, C_MINUS, C_PLUS, C_ZERO, C_DIG19, C_DOT, C_e, C_E,
+  C_t, C_r, C_u, C_f, C_a, C_l, C_s, C_n, C_OTHER, C_NCLASSES
+};
+constexpr uint32_t kFastTabStride = 32;  // classes per row, padded
+// entry: next state (5 bits) | action << 5 | flags
+enum : uint32_t { A_NONE = 0, A_PUSH_OBJ, A_PUSH_ARR, A_POP_OBJ, A_POP_ARR, A_COMMA, A_ERR };
+constexpr uint32_t F_VALSTART = 1u << 8, F_KEYSTART = 1u << 9, F_KEYEND = 1u << 10;
+
+struct FastTables {
+  uint8_t cls[256];
+  uint16_t tab[G_NSTATES * kFastTabStride];
+};
+constexpr uint32_t fast_class_of(int b) {
+  return b == '"' ? C_QUOTE : b == '{' ? C_LBRACE : b == '}' ? C_RBRACE : b == '[' ? C_LBRACK : b == ']' ? C_RBRACK
+       : b == ':' ? C_COLON : b == ',' ? C_COMMA : (b == ' ' || b == '\t' || b == '\n' || b == '\r') ? C_WS
+       : b == '-' ? C_MINUS : b == '+' ? C_PLUS : b == '0' ? C_ZERO : (b >= '1' && b <= '9') ? C_DIG19 : b == '.' ? C_DOT
+       : b == 'e' ? C_e : b == 'E' ? C_E : b == 't' ? C_t : b == 'r' ? C_r : b == 'u' ? C_u : b == 'f' ? C_f : b == 'a' ? C_a
+       : b == 'l' ? C_l : b == 's' ? C_s : b == 'n' ? C_n : C_OTHER;
+}
+constexpr uint16_t fast_entry(uint32_t next, uint32_t action = A_NONE, uint32_t flags = 0) {
+  return (uint16_t)(next | action << 5 | flags);
+}
+// what a finished value (string, literal, number, container) may be followed by
+constexpr uint16_t fast_after(uint32_t c) {
+  return c == C_WS ? fast_entry(G_AFTER) : c == C_COMMA ? fast_entry(G_AFTER, A_COMMA) : c == C_RBRACE ? fast_entry(G_AFTER, A_POP_OBJ)
+       : c == C_RBRACK ? fast_entry(G_AFTER, A_POP_ARR) : fast_entry(G_ERR, A_ERR);
+}
+constexpr uint16_t fast_value_start(uint32_t c) {
+  return c == C_QUOTE ? fast_entry(G_STRV, A_NONE, F_VALSTART) : c == C_LBRACE ? fast_entry(G_OBJ0, A_PUSH_OBJ, F_VALSTART)
+       : c == C_LBRACK ? fast_entry(G_ARR0, A_PUSH_ARR, F_VALSTART) : c == C_t ? fast_entry(G_T1, A_NONE, F_VALSTART)
+       : c == C_f ? fast_entry(G_F1, A_NONE, F_VALSTART) : c == C_n ? fast_entry(G_N1, A_NONE, F_VALSTART)
+       : c == C_MINUS ? fast_entry(G_NM, A_NONE, F_VALSTART) : c == C_ZERO ? fast_entry(G_NZ, A_NONE, F_VALSTART)
+       : c == C_DIG19 ? fast_entry(G_NI, A_NONE, F_VALSTART) : fast_entry(G_ERR, A_ERR);
+}
+constexpr uint16_t fast_transition(uint32_t g, uint32_t c) {
+  const bool dig = c == C_ZERO || c == C_DIG19, exp = c == C_e || c == C_E;
+  switch (g) {
+    case G_TOP:   return c == C_WS ? fast_entry(G_TOP) : c == C_LBRACE ? fast_entry(G_OBJ0, A_PUSH_OBJ) : fast_entry(G_ERR, A_ERR);
+    case G_VAL:   return c == C_WS ? fast_entry(G_VAL) : fast_value_start(c);
+    case G_ARR0:  return c == C_WS ? fast_entry(G_ARR0) : c == C_RBRACK ? fast_entry(G_AFTER, A_POP_ARR) : fast_value_start(c);
+    case G_OBJ0:  return c == C_WS ? fast_entry(G_OBJ0) : c == C_QUOTE ? fast_entry(G_STRK, A_NONE, F_KEYSTART)
+                       : c == C_RBRACE ? fast_entry(G_AFTER, A_POP_OBJ) : fast_entry(G_ERR, A_ERR);
+    case G_KEY:   return c == C_WS ? fast_entry(G_KEY) : c == C_QUOTE ? fast_entry(G_STRK, A_NONE, F_KEYSTART) : fast_entry(G_ERR, A_ERR);
+    case G_COLON: return c == C_WS ? fast_entry(G_COLON) : c == C_COLON ? fast_entry(G_VAL) : fast_entry(G_ERR, A_ERR);
+    case G_AFTER: return fast_after(c);
+    case G_STRK:  return c == C_QUOTE ? fast_entry(G_COLON, A_NONE, F_KEYEND) : fast_entry(G_ERR, A_ERR);  // only the closing quote
+    case G_STRV:  return c == C_QUOTE ? fast_entry(G_AFTER) : fast_entry(G_ERR, A_ERR);                    // is a token in a string
+    case G_T1: return c == C_r ? fast_entry(G_T2) : fast_entry(G_ERR, A_ERR);
+    case G_T2: return c == C_u ? fast_entry(G_T3) : fast_entry(G_ERR, A_ERR);
+    case G_T3: return c == C_e ? fast_entry(G_AFTER) : fast_entry(G_ERR, A_ERR);
+    case G_F1: return c == C_a ? fast_entry(G_F2) : fast_entry(G_ERR, A_ERR);
+    case G_F2: return c == C_l ? fast_entry(G_F3) : fast_entry(G_ERR, A_ERR);
+    case G_F3: return c == C_s ? fast_entry(G_F4) : fast_entry(G_ERR, A_ERR);
+    case G_F4: return c == C_e ? fast_entry(G_AFTER) : fast_entry(G_ERR, A_ERR);
+    case G_N1: return c == C_u ? fast_entry(G_N2) : fast_entry(G_ERR, A_ERR);
+    case G_N2: return c == C_l ? fast_entry(G_N3) : fast_entry(G_ERR, A_ERR);
+    case G_N3: return c == C_l ? fast_entry(G_AFTER) : fast_entry(G_ERR, A_ERR);
+    case G_NM: return c == C_ZERO ? fast_entry(G_NZ) : c == C_DIG19 ? fast_entry(G_NI) : fast_entry(G_ERR, A_ERR);
+    case G_NZ: return c == C_DOT ? fast_entry(G_ND) : exp ? fast_entry(G_NE) : dig ? fast_entry(G_ERR, A_ERR) : fast_after(c);
+    case G_NI: return dig ? fast_entry(G_NI) : c == C_DOT ? fast_entry(G_ND) : exp ? fast_entry(G_NE) : fast_after(c);
+    case G_ND: return dig ? fast_entry(G_NF) : fast_entry(G_ERR, A_ERR);
+    case G_NF: return dig ? fast_entry(G_NF) : exp ? fast_entry(G_NE) : fast_after(c);
+    case G_NE: return dig ? fast_entry(G_NX) : (c == C_PLUS || c == C_MINUS) ? fast_entry(G_NS) : fast_entry(G_ERR, A_ERR);
+    case G_NS: return dig ? fast_entry(G_NX) : fast_entry(G_ERR, A_ERR);
+    case G_NX: return dig ? fast_entry(G_NX) : fast_after(c);
+    default:   return fast_entry(G_ERR, A_ERR);
+  }
+}
+struct FastTablesInit {
+  FastTables t;
+  constexpr FastTablesInit() : t() {
+    for (int b = 0; b < 256; b++) t.cls[b] = (uint8_t)fast_class_of(b);
+    for (uint32_t g = 0; g < G_NSTATES; g++)
+      for (uint32_t c = 0; c < kFastTabStride; c++) t.tab[g * kFastTabStride + c] = c < C_NCLASSES ? fast_transition(g, c) : fast_entry(G_ERR, A_ERR);
+  }
+};
+
+// position of the first byte outside strings at or after `from` (an absolute byte position), or `none`
+ARKS_HD uint32_t next_token(const uint32_t* tb, uint32_t nch, uint32_t from, uint32_t none) {
+  uint32_t w = from >> 5;
+  if (w >= nch) return none;
+  uint32_t m = tb[w] & (0xffffffffu << (from & 31));
+  while (!m) {
+    if (++w >= nch) return none;
+    m = tb[w];
+  }
+  return w * 32 + first_set(m);
+}
+// any backslash among bytes [s, e)?
+ARKS_HD bool any_backslash(const uint32_t* bm, uint32_t s, uint32_t e) {
+  if (e <= s) return false;
+  for (uint32_t w = s >> 5; w <= (e - 1) >> 5; w++) {
+    uint32_t m = bm[w];
+    if (w == (s >> 5)) m &= 0xffffffffu << (s & 31);
+    if (w == ((e - 1) >> 5)) m &= 0xffffffffu >> (31 - ((e - 1) & 31));
+    if (m) return true;
+  }
+  return false;
+}
+// case-folded comparison with a lower-case literal (json-iterator's struct fields), exact comparison (gjson's Map())
+ARKS_HD bool key_is_fold(const uint8_t* doc, uint32_t pos, uint32_t n, const char* lit) {
+  uint32_t d = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t c = doc[pos + i];
+    d |= (((c - 'A') <= 25u) ? c + 32 : c) ^ (uint32_t)(uint8_t)lit[i];
+  }
+  return d == 0;
+}
+ARKS_HD bool key_is(const uint8_t* doc, uint32_t pos, uint32_t n, const char* lit) {
+  uint32_t d = 0;
+  for (uint32_t i = 0; i < n; i++) d |= (uint32_t)doc[pos + i] ^ (uint32_t)(uint8_t)lit[i];
+  return d == 0;
+}
+
+// ---- pass B: walk the bytes outside strings through the grammar; logs the members of the top-level object ----
+// returns the number of members logged, or -1 (not in the subset)
+ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, FastScratch& s, uint32_t nch) {
+  uint32_t g = G_TOP, depth = 0, stack = 0, nmem = 0, kstart = 0, pending = 0, bad = 0;
+  uint32_t w = 0, cur = nch ? s.tb[0] : 0;
+  for (;;) {
+    while (!cur) {
+      if (++w >= nch) goto done;
+      cur = s.tb[w];
+    }
+    {
+      const uint32_t pos = w * 32 + first_set(cur);
+      cur &= cur - 1;
+      const uint32_t e = T.tab[g * kFastTabStride + T.cls[doc[pos]]];
+      const uint32_t act = (e >> 5) & 7u;
+      g = e & 31u;
+      const bool top_obj = depth && ((stack >> (depth - 1)) & 1u);
+      // members of the top-level object: key span and the first byte of the value (depth is still the one BEFORE a push)
+      if ((e & F_KEYSTART) && depth == 1) kstart = pos + 1;
+      if ((e & F_KEYEND) && depth == 1) {
+        if (nmem >= kFastMaxMembers) bad = 1;
+        else { s.mem[3 * nmem] = kstart; s.mem[3 * nmem + 1] = pos - kstart; pending = 1; }
+      }
+      if ((e & F_VALSTART) && pending && depth == 1) { s.mem[3 * nmem + 2] = pos; nmem++; pending = 0; }
+      if (act == A_PUSH_OBJ || act == A_PUSH_ARR) {
+        if (depth >= 32) bad = 1;
+        else { stack = (stack & ~(1u << depth)) | ((act == A_PUSH_OBJ ? 1u : 0u) << depth); depth++; }
+      } else if (act == A_POP_OBJ || act == A_POP_ARR) {
+        if (!depth || top_obj != (act == A_POP_OBJ)) bad = 1;
+        else depth--;
+      } else if (act == A_COMMA) {
+        if (!depth) bad = 1;
+        g = top_obj ? G_KEY : G_VAL;
+      } else if (act == A_ERR) {
+        bad = 1;
+      }
+      if (bad) return -1;
+    }
+  }
+done:
+  // the document is one complete object (numbers cannot be open here: the top-level value is an object)
+  if (g != G_AFTER || depth != 0) return -1;
+  return (int)nmem;
+}
+
+// ---- pass C: the logged members -> what the gateway reads ----
+// the members of the object whose '{' is at `open`, for stream_options (K_REQ) / usage (K_RESP); false: not in the subset
+template <int KIND>
+ARKS_HD bool fast_inner_object(const uint8_t* doc, const FastScratch& s, uint32_t nch, uint32_t open, FastOut& o) {
+  uint32_t rel = 1, in_str = 0, is_key = 0, expect_key = 1, ks = 0, seen = 0, nd = 0;
+  int which = -1;  // the member whose value is being read: 0..2 usage counters, 3 include_usage
+  int64_t acc = 0;
+  uint32_t p = open;
+  for (uint32_t it = 0;; it++) {
+    if (it >= kFastMiniCap) return false;
+    p = next_token(s.tb, nch, p + 1, 0xffffffffu);
+    if (p == 0xffffffffu) return false;
+    const uint8_t b = doc[p];
+    if (in_str) {  // the closing quote
+      in_str = 0;
+      if (is_key) {
+        const uint32_t n = p - ks;
+        if (any_backslash(s.bm, ks, p)) return false;  // may be an escaped spelling of a name that is read
+        which = -1;
+        if (KIND == K_REQ) {
+          if (n == 13 && key_is_fold(doc, ks, n, "include_usage")) which = 3;
+        } else {
+          if (n == 13 && key_is(doc, ks, n, "prompt_tokens")) which = 0;
+          else if (n == 17 && key_is(doc, ks, n, "completion_tokens")) which = 1;
+          else if (n == 12 && key_is(doc, ks, n, "total_tokens")) which = 2;
+        }
+        if (which >= 0) {
+          if (seen & (1u << which)) return false;  // duplicates: exact engine
+          seen |= 1u << which;
+          acc = 0; nd = 0;
+        }
+      }
+      continue;
+    }
+    if (b == '"') {
+      in_str = 1;
+      is_key = rel == 1 && expect_key;
+      ks = p + 1;
+      if (is_key) expect_key = 0;
+      else if (rel == 1 && which >= 0) return false;  // a counter / flag written as a string: exact engine (gjson rules)
+      continue;
+    }
+    if (b == '{' || b == '[') {
+      if (rel == 1 && which >= 0) return false;
+      rel++;
+      continue;
+    }
+    const bool closes = b == '}' || b == ']';
+    if (closes || (b == ',' && rel == 1)) {
+      if (rel == 1 && which >= 0) {  // the value of a member that is read ends here
+        if (which == 3) { if (nd == 0) return false; }
+        else { if (nd == 0 || nd > 18) return false; o.usage[which] = acc; }
+        which = -1;
+      }
+      if (closes) { if (--rel == 0) return true; }
+      else expect_key = 1;
+      continue;
+    }
+    if (rel == 1 && which >= 0 && b != ':' && !(b == ' ' || b == '\t' || b == '\n' || b == '\r')) {
+      if (which == 3) {  // OptionalDecoder{boolCodec}: true / false / null (the grammar pass checked the spelling)
+        if (nd == 0) {
+          if (!(b == 't' || b == 'f' || b == 'n')) return false;
+          o.iu3 = b == 'n' ? 0u : b == 'f' ? 1u : 2u;
+        }
+        nd++;
+      } else {  // a plain non-negative integer; anything else (sign, fraction, exponent, literal): exact engine
+        if ((uint32_t)(b - '0') > 9u) return false;
+        acc = acc * 10 + (int64_t)(b - '0');
+        nd++;
+      }
+    }
+  }
+}
+
+template <int KIND>
+ARKS_HD bool fast_members(const uint8_t* doc, const FastScratch& s, uint32_t nch, int nmem, FastOut& o) {
+  o.m_start = o.m_rawlen = o.m_esc = 0;
+  o.stream3 = o.so_present = o.iu3 = 0;
+  o.usage[0] = o.usage[1] = o.usage[2] = 0;
+  uint32_t seen = 0;  // bit 0 model, 1 stream, 2 stream_options, 3 usage
+  for (int m = 0; m < nmem; m++) {
+    const uint32_t kpos = s.mem[3 * m], klen = s.mem[3 * m + 1], vpos = s.mem[3 * m + 2];
+    // a key with an escape may DECODE to a field name whatever its raw length: exact engine (json-iterator decodes, then hashes)
+    if (any_backslash(s.bm, kpos, kpos + klen)) return false;
+    int what = -1;
+    if (klen == 5 && key_is_fold(doc, kpos, 5, "model")) what = 0;
+    else if (KIND == K_REQ && klen == 6 && key_is_fold(doc, kpos, 6, "stream")) what = 1;
+    else if (KIND == K_REQ && klen == 14 && key_is_fold(doc, kpos, 14, "stream_options")) what = 2;
+    else if (KIND == K_RESP && klen == 5 && key_is_fold(doc, kpos, 5, "usage")) what = 3;
+    if (what < 0) continue;
+    if (seen & (1u << what)) return false;  // duplicated members: exact engine (last-wins / pointer-reuse rules)
+    seen |= 1u << what;
+    const uint8_t vb = doc[vpos];
+    if (what == 0) {  // stringCodec: string or null
+      if (vb == '"') {
+        const uint32_t end = next_token(s.tb, nch, vpos + 1, 0xffffffffu);  // the closing quote
+        if (end == 0xffffffffu) return false;
+        o.m_rawlen = end - vpos - 1;
+        o.m_start = o.m_rawlen ? vpos + 1 : 0;
+        o.m_esc = o.m_rawlen && any_backslash(s.bm, vpos + 1, end) ? 1u : 0u;
+      } else if (vb != 'n') {
+        return false;  // a model of another JSON type is a decode error: the exact engine reports it
+      }
+    } else if (what == 1) {
+      if (!(vb == 't' || vb == 'f' || vb == 'n')) return false;
+      o.stream3 = vb == 'n' ? 0u : vb == 'f' ? 1u : 2u;
+    } else if (what == 2) {
+      if (vb == '{') {
+        o.so_present = 1;
+        if (!fast_inner_object<K_REQ>(doc, s, nch, vpos, o)) return false;
+      } else if (vb != 'n') {
+        return false;
+      }
+    } else {
+      if (vb == '{' && !fast_inner_object<K_RESP>(doc, s, nch, vpos, o)) return false;
+      // null or any other type: the counters stay 0 (apijson decodes objects only)
+    }
+  }
+  return true;
+}
+
+// ---- host reference driver: exactly what one lane does (tests) ----
+#if !defined(__CUDA_ARCH__)
+static const FastTablesInit kFastTablesHost{};
+template <int KIND>
+inline bool fast_scan_host(const uint8_t* doc, uint32_t len, FastOut& out) {
+  if (len == 0 || len > kFastMaxLen) return false;
+  static thread_local FastScratch s;
+  const uint32_t nch = (len + 31) / 32;
+  FastCarry c{0, 0, 0};
+  for (uint32_t j = 0; j < nch; j++) {
+    uint32_t w[8];
+    for (int q = 0; q < 8; q++) {
+      uint32_t v = 0;
+      for (int b = 0; b < 4; b++) {
+        const uint32_t p = 32 * j + 4 * q + b;
+        v |= (uint32_t)(p < len ? doc[p] : (uint8_t)(0xA5 ^ p)) << (8 * b);  // garbage past the end, as on the device
+      }
+      w[q] = v;
+    }
+    fast_chunk(w, len - 32 * j < 32 ? len - 32 * j : 32, doc, len, 32 * j, c, &s.tb[j], &s.bm[j]);
+  }
+  if (c.bad || c.in_str) return false;
+  const int nmem = fast_walk(doc, kFastTablesHost.t, s, nch);
+  if (nmem < 0) return false;
+  return fast_members<KIND>(doc, s, nch, nmem, out);
+}
+#endif
+
+}  // namespace arks

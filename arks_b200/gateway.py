@@ -227,7 +227,7 @@ class Gateway:
 
     @property
     def last_declined(self) -> int:
-        """rows of the last batch the warp-per-document scan left to the exact engine (-1: the batch took the fused kernels)"""
+        """rows of the last batch the fast path left to the exact engine (-1: the batch took the fused kernels)"""
         return int(lib().arks_last_declined(self._h))
 
     @property

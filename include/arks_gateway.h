@@ -248,12 +248,12 @@ int arks_wait_response(arks_ctx* ctx, int slot, arks_response_result* out);
 int arks_select_slot(arks_ctx* ctx, int slot);
 /* per-kernel device timing of the last run_* call: CUDA events around every launch on the library's stream.
  * arks_last_kernel_ms returns the number of intervals timed and fills ms[] (request: scan stage, admit; response: scan stage;
- * large batches add one entry: the warp-per-document kernel of the two-stage scan on its own). */
+ * large batches add one entry: the fast-path kernel of the two-stage scan on its own). */
 int arks_set_profiling(arks_ctx* ctx, int on);
 int arks_last_kernel_ms(arks_ctx* ctx, float* ms, int cap);
 /* CUDA stream handle (cudaStream_t) the kernels are launched on, for event timing by the caller */
 void* arks_stream(arks_ctx* ctx);
-/* Large batches are scanned in two stages: a warp per document for everything plain (arks_b200/csrc/warp_scan.cuh), the
+/* Large batches are scanned in two stages: a warp per document for everything plain (arks_b200/csrc/mask_scan.cuh), the
  * exact engine for the rows that path declines. Rows of the last run_* call left to the exact engine, or -1 if that call
  * used the fused kernels (small or mixed batches). Synchronises the stream: for tests and the bench. */
 int64_t arks_last_declined(arks_ctx* ctx);

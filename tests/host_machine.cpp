@@ -167,22 +167,20 @@ int hm_work_profile(int kind, const uint8_t* body, size_t len, uint32_t* advance
 }
 }
 
-// ---- the warp-per-document fast path (arks_b200/csrc/warp_scan.cuh), host driver: 1 = accepted (fields filled), 0 = the
-// document is left to the exact engine ----
-#include "../arks_b200/csrc/warp_scan.cuh"
+// ---- the fast path (arks_b200/csrc/mask_scan.cuh), host driver = exactly one lane's work: 1 = accepted (fields filled),
+// 0 = the document is left to the exact engine ----
+#include "../arks_b200/csrc/mask_scan.cuh"
 extern "C" {
 int hm_fast_request(const uint8_t* body, size_t len, uint32_t* span /* start, rawlen, esc */, int* stream, int* so_present, int* iu) {
-  static thread_local uint32_t tok[kFastMaxTok + 64];
   FastOut o{};
-  if (len > 0xffffffffu || !fast_scan_host<K_REQ>(body, (uint32_t)len, o, tok)) return 0;
+  if (len > 0xffffffffu || !fast_scan_host<K_REQ>(body, (uint32_t)len, o)) return 0;
   span[0] = o.m_start; span[1] = o.m_rawlen; span[2] = o.m_esc;
   *stream = (int)o.stream3; *so_present = (int)o.so_present; *iu = (int)o.iu3;
   return 1;
 }
 int hm_fast_response(const uint8_t* body, size_t len, uint32_t* span, int64_t* usage) {
-  static thread_local uint32_t tok[kFastMaxTok + 64];
   FastOut o{};
-  if (len > 0xffffffffu || !fast_scan_host<K_RESP>(body, (uint32_t)len, o, tok)) return 0;
+  if (len > 0xffffffffu || !fast_scan_host<K_RESP>(body, (uint32_t)len, o)) return 0;
   span[0] = o.m_start; span[1] = o.m_rawlen; span[2] = o.m_esc;
   usage[0] = o.usage[0]; usage[1] = o.usage[1]; usage[2] = o.usage[2];
   return 1;

@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "host_machine.cpp")
-HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_common.cuh", "json_engine.cuh", "json_tables.h", "warp_scan.cuh")]
+HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_common.cuh", "json_engine.cuh", "json_tables.h", "mask_scan.cuh")]
 OUT = os.path.join(ROOT, "tests", "_build", "libhost_machine.so")
 _lib = None
 
@@ -94,7 +94,7 @@ def _resp(fn, body):
 
 
 def fast_request(body: bytes):
-    """the warp-per-document fast path (host driver of warp_scan.cuh): ((start, rawlen, esc), stream3, so_present, iu3) or
+    """the fast path (host driver of mask_scan.cuh = one lane's work): ((start, rawlen, esc), stream3, so_present, iu3) or
     None when the document is left to the exact engine"""
     return _req(lib().hm_fast_request, body)
 

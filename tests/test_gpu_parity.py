@@ -281,8 +281,8 @@ def test_async_pipelined_submits_match_serial_oracle(gwmod):
 
 
 def test_two_stage_scan_fuzzed_and_plain_documents(gwmod):
-    """Batches of 4 096 rows and more go through the warp-per-document scan first and the exact engine for what it declines
-    (arks_b200/csrc/warp_scan.cuh). Hostile documents, plain ones and bodies longer than the resident window in ONE batch:
+    """Batches of 4 096 rows and more go through the fast path (mask_scan.cuh) first and the exact engine for what it declines
+    (arks_b200/csrc/mask_scan.cuh). Hostile documents, plain ones and bodies longer than the resident window in ONE batch:
     the verdicts must not depend on which path a row took, and both paths must have been taken."""
     w = traffic.Workload(n_tenants=8, seed=1)
     g, o = pair(gwmod, w.tables, 16384, 48 << 20)

@@ -1,5 +1,5 @@
-"""The warp-per-document fast path (arks_b200/csrc/warp_scan.cuh) on CPU: its host driver runs the same per-lane phases
-as the device kernel with the warp collectives written as loops.
+"""The fast path of the scan kernels (arks_b200/csrc/mask_scan.cuh) on CPU: its host driver is exactly what one lane of
+fast_request_kernel / fast_response_kernel does (mask pass, table-driven token pass, member extraction).
 
 Contract: the fast path is a filter. Whenever it ACCEPTS a document its fields equal what the exact engine (and the oracle)
 extract; whenever it declines, nothing is claimed. It must accept the traffic it was built for (every generated chat
@@ -68,7 +68,7 @@ def test_generated_traffic_is_accepted():
 
 def test_structure_corner_cases():
     r = random.Random(3)
-    # documents that straddle lane (32 B) and segment (1 KiB) boundaries at every phase of a token
+    # documents that straddle the 32-byte chunks at every phase of a token
     pad = lambda n: '"p":"' + "x" * n + '",'
     for n in list(range(0, 80)) + list(range(980, 1060)) + [2000, 2010, 2030]:
         b = ('{' + pad(n) + '"model":"qwen-7b","stream":true,"stream_options":{"include_usage":true},"n":[1,2.5e-3,{"a":null}],"t":false}').encode()
@@ -79,11 +79,15 @@ def test_structure_corner_cases():
         b2 = ('{' + pad(n) + '"usage":{"prompt_tokens":12,"completion_tokens":345,"total_tokens":357,"d":{"x":[1]}},"model":"m"}').encode()
         if len(b2) <= 2048:
             assert check_response(b2) == 1, n
-    # backslash runs across lane boundaries
+    # backslash runs across chunk boundaries (and one that fills whole chunks)
     for n in range(20, 45):
         for k in range(1, 9):
             s = "y" * n + "\\\\" * k + ('\\"' if r.random() < 0.5 else "")
             b = ('{"a":"' + s + '","model":"m"}').encode()
+            assert check_request(b) == 1, (n, k)
+    for n in (0, 1, 7, 31, 32, 33):
+        for k in (31, 32, 33, 64, 65, 66):
+            b = ('{"a":"' + "z" * n + "\\" * k + ('' if k % 2 == 0 else 'n') + '","model":"m"}').encode()
             assert check_request(b) == 1, (n, k)
     # things the fast path must decline (the exact engine decides them)
     for b in [b'', b'null', b'[]', b'{"model":"m"} x', b'{"model":"m"}\x00', b'{"model":5}', b'{"model":"a","model":"b"}',
