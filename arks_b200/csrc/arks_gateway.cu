@@ -570,6 +570,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_request_
 __device__ __align__(16) const FastTablesInit g_fast_tables{};
 static_assert(sizeof(FastTables) % 16 == 0, "staged with one bulk copy");
 constexpr int kFastThreads = 128;
+struct FastBlockSmem;
 
 // the grammar tables of mask_scan.cuh into shared memory: ONE 1-D bulk copy (TMA) per block, completion on an mbarrier
 __device__ __forceinline__ void stage_fast_tables(FastTables* dst, uint64_t* bar) {
@@ -583,38 +584,55 @@ __device__ __forceinline__ void stage_fast_tables(FastTables* dst, uint64_t* bar
   mbar_wait(bar, 0);
 }
 
-// passes A-C for the body of one lane; false: declined (or not eligible)
+// Shared memory of a fast-path block: the grammar tables and the per-lane scratch of mask_scan.cuh, lane-interleaved.
+struct __align__(128) FastBlockSmem {
+  FastTables tabs;
+  uint64_t bar;
+  uint32_t tb[kFastChunks * kFastThreads];
+  uint32_t mem[2 * kFastMaxMembers * kFastThreads];
+};
+
+// passes A-C for the body of one lane; false: declined (or not eligible).
+// Pass A streams the body through a 4-deep register queue of 32-byte chunks (the loads of chunks j+1..j+4 are in flight while
+// chunk j is processed): a lane-per-document kernel has one partial wave of warps per SM, so memory latency has to be
+// covered inside the lane, not by other warps. One copy of the chunk code (the instruction cache is small).
 template <int KIND>
-__device__ __forceinline__ bool fast_scan_lane(const uint8_t* body, uint32_t len, const FastTables& tabs, FastScratch& s, FastOut& o) {
+__device__ __forceinline__ bool fast_scan_lane(const uint8_t* body, uint32_t len, FastBlockSmem& sm, FastOut& o) {
   if (len == 0 || len > kFastMaxLen) return false;
+  FastScratch s{sm.tb + threadIdx.x, sm.mem + threadIdx.x, (uint32_t)kFastThreads, 0u, 0u};
   const uint32_t nch = (len + 31) >> 5, plen = (len + 15u) & ~15u;
   FastCarry c{0, 0, 0};
   const uint4* p = reinterpret_cast<const uint4*>(body);
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  auto lo = [&](uint32_t j) { return j < nch ? ld_nc_v4(p + 2 * j) : z; };
+  auto hi = [&](uint32_t j) { return j < nch && 32 * j + 16 < plen ? ld_nc_v4(p + 2 * j + 1) : z; };  // never past the 16-byte padding
+  uint4 a0 = lo(0), b0 = hi(0), a1 = lo(1), b1 = hi(1), a2 = lo(2), b2 = hi(2), a3 = lo(3), b3 = hi(3);
+#pragma unroll 1
   for (uint32_t j = 0; j < nch; j++) {
-    const uint4 a = ld_nc_v4(p + 2 * j);
-    uint4 b = make_uint4(0, 0, 0, 0);
-    if (32 * j + 16 < plen) b = ld_nc_v4(p + 2 * j + 1);  // never read past the body's 16-byte padding
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    fast_chunk(w, min(len - 32 * j, 32u), body, len, 32 * j, c, &s.tb[j], &s.bm[j]);
+    const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+    a0 = a1; b0 = b1; a1 = a2; b1 = b2; a2 = a3; b2 = b3;
+    a3 = lo(j + 4); b3 = hi(j + 4);
+    uint32_t bm;
+    fast_chunk(w, min(len - 32 * j, 32u), body, len, 32 * j, c, &s.tb(j), &bm);
+    if (bm) { if (j < 32) s.bs_lo |= 1u << j; else s.bs_hi |= 1u << (j - 32); }
   }
   if (c.bad || c.in_str) return false;
-  const int nmem = fast_walk(body, tabs, s, nch);
+  const int nmem = fast_walk(body, sm.tabs, s, nch);
   if (nmem < 0) return false;
   return fast_members<KIND>(body, s, nch, nmem, o);
 }
 
 __global__ void __launch_bounds__(kFastThreads) fast_request_kernel(DevTables T, ReqDev B) {
-  __shared__ __align__(128) FastTables tabs;
-  __shared__ uint64_t bar;
-  stage_fast_tables(&tabs, &bar);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  FastBlockSmem& sm = *reinterpret_cast<FastBlockSmem*>(smem);
+  stage_fast_tables(&sm.tabs, &sm.bar);
   const uint32_t lane_id = blockIdx.x * blockDim.x + threadIdx.x;
   if (lane_id >= B.n) return;
   const uint32_t i = B.perm ? B.perm[lane_id] : lane_id;
   const uint8_t* body = B.bodies + B.body_off[i];
   const uint32_t len = B.body_len[i];
-  FastScratch s;
   FastOut o;
-  if (!fast_scan_lane<K_REQ>(body, len, tabs, s, o)) {
+  if (!fast_scan_lane<K_REQ>(body, len, sm, o)) {
     B.slow_list[atomicAdd(B.slow_n, 1u)] = i;
     return;
   }
@@ -942,9 +960,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response
 
 // the fast path for complete response bodies: first stage of the two-stage scan (see fast_request_kernel)
 __global__ void __launch_bounds__(kFastThreads) fast_response_kernel(DevTables T, RespDev B) {
-  __shared__ __align__(128) FastTables tabs;
-  __shared__ uint64_t bar;
-  stage_fast_tables(&tabs, &bar);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  FastBlockSmem& sm = *reinterpret_cast<FastBlockSmem*>(smem);
+  stage_fast_tables(&sm.tabs, &sm.bar);
   const uint32_t lane_id = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = lane_id < B.n;
   const uint32_t i = in ? (B.perm ? B.perm[lane_id] : lane_id) : 0;
@@ -955,9 +973,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_response_kernel(DevTables T
   long long u0 = 0, u1 = 0, u2 = 0;
   bool live = in;
   if (in && !pending && qos >= 0) {
-    FastScratch s;
     FastOut o;
-    if (fast_scan_lane<K_RESP>(B.bodies + B.body_off[i], B.body_len[i], tabs, s, o)) {
+    if (fast_scan_lane<K_RESP>(B.bodies + B.body_off[i], B.body_len[i], sm, o)) {
       if (o.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // handle_response.go:167-181
       else { u0 = o.usage[0]; u1 = o.usage[1]; u2 = o.usage[2]; }
       counted = reason == ARKS_R_OK && u2 != 0;               // :186
@@ -1303,6 +1320,8 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaFuncSetAttribute(scan_sse_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSseSmemPerBlock));
   ARKS_FOR_SCHED(ARKS_SET)
 #undef ARKS_SET
+  CK(cudaFuncSetAttribute(fast_request_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
+  CK(cudaFuncSetAttribute(fast_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
   if (const char* e = getenv("ARKS_FAST")) ctx->fast_scan = e[0] != '0';
   {
     cudaDeviceProp prop;
@@ -1882,7 +1901,7 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
     CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
     r.perm = queue_length_order(ctx, r.body_len, n);
     if (ctx->prof) CK(cudaEventRecord(ctx->ev_fast[0], ctx->stream));
-    fast_request_kernel<<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, 0, ctx->stream>>>(ctx->dt, r);
+    fast_request_kernel<<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, r);
     if (ctx->prof) { CK(cudaEventRecord(ctx->ev_fast[1], ctx->stream)); ctx->ev_fast_set = true; }
     r.perm = nullptr;
     r.bpw = 32;
@@ -2092,7 +2111,7 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
     CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
     rp.perm = queue_length_order(ctx, rp.body_len, rp.n);
     if (ctx->prof) CK(cudaEventRecord(ctx->ev_fast[0], ctx->stream));
-    fast_response_kernel<<<(rp.n + kFastThreads - 1) / kFastThreads, kFastThreads, 0, ctx->stream>>>(ctx->dt, rp);
+    fast_response_kernel<<<(rp.n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, rp);
     if (ctx->prof) { CK(cudaEventRecord(ctx->ev_fast[1], ctx->stream)); ctx->ev_fast_set = true; }
     rp.perm = nullptr;
     rp.bpw = 32;

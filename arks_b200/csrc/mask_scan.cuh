@@ -34,7 +34,7 @@ namespace arks {
 
 constexpr uint32_t kFastMaxLen = 2048;             // longer documents: exact engine
 constexpr uint32_t kFastChunks = kFastMaxLen / 32;
-constexpr uint32_t kFastMaxMembers = 24;           // members of the top-level object that are logged
+constexpr uint32_t kFastMaxMembers = 16;           // members of the top-level object that are logged (more: exact engine)
 constexpr uint32_t kFastMiniCap = 192;             // structure bytes read inside stream_options / usage
 
 struct FastOut {
@@ -43,11 +43,16 @@ struct FastOut {
   int64_t usage[3];                   // K_RESP
 };
 
-// per-lane scratch between the passes (local memory on the device: arrays indexed by the loop counter)
+// Per-lane scratch between the passes, as a strided view: element j of this lane lives at base[j * stride]. On the device
+// the arrays are in shared memory, lane-interleaved (stride = threads per block: every access of a warp is conflict-free
+// when the lanes use the same j, and no lane ever touches local memory); on the host stride is 1.
 struct FastScratch {
-  uint32_t tb[kFastChunks];  // bytes outside strings (quotes included)
-  uint32_t bm[kFastChunks];  // backslashes
-  uint32_t mem[kFastMaxMembers * 3];  // key pos, key len, value pos of the top-level members
+  uint32_t* tb_;    // kFastChunks words: bytes outside strings (quotes included)
+  uint32_t* mem_;   // 2 * kFastMaxMembers words: key pos | key len << 16, value pos
+  uint32_t stride;
+  uint32_t bs_lo, bs_hi;  // chunk j contains a backslash (bit j): lets the key / model checks skip the byte scan
+  ARKS_HD uint32_t& tb(uint32_t j) const { return tb_[j * stride]; }
+  ARKS_HD uint32_t& mem(uint32_t j) const { return mem_[j * stride]; }
 };
 
 // ---- byte-plane SWAR: bit 7 of every byte that is zero, exact ----
@@ -221,26 +226,26 @@ struct FastTablesInit {
 };
 
 // position of the first byte outside strings at or after `from` (an absolute byte position), or `none`
-ARKS_HD uint32_t next_token(const uint32_t* tb, uint32_t nch, uint32_t from, uint32_t none) {
+ARKS_HD uint32_t next_token(const FastScratch& s, uint32_t nch, uint32_t from, uint32_t none) {
   uint32_t w = from >> 5;
   if (w >= nch) return none;
-  uint32_t m = tb[w] & (0xffffffffu << (from & 31));
+  uint32_t m = s.tb(w) & (0xffffffffu << (from & 31));
   while (!m) {
     if (++w >= nch) return none;
-    m = tb[w];
+    m = s.tb(w);
   }
   return w * 32 + first_set(m);
 }
-// any backslash among bytes [s, e)?
-ARKS_HD bool any_backslash(const uint32_t* bm, uint32_t s, uint32_t e) {
-  if (e <= s) return false;
-  for (uint32_t w = s >> 5; w <= (e - 1) >> 5; w++) {
-    uint32_t m = bm[w];
-    if (w == (s >> 5)) m &= 0xffffffffu << (s & 31);
-    if (w == ((e - 1) >> 5)) m &= 0xffffffffu >> (31 - ((e - 1) & 31));
-    if (m) return true;
-  }
-  return false;
+// any backslash among bytes [b, e)? The per-chunk summary answers "no" without touching the document in the usual case.
+ARKS_HD bool any_backslash(const uint8_t* doc, const FastScratch& s, uint32_t b, uint32_t e) {
+  if (e <= b) return false;
+  const uint32_t c0 = b >> 5, c1 = (e - 1) >> 5;
+  uint32_t hit = 0;
+  for (uint32_t c = c0; c <= c1; c++) hit |= c < 32 ? (s.bs_lo >> c) & 1u : (s.bs_hi >> (c - 32)) & 1u;
+  if (!hit) return false;
+  uint32_t d = 0;
+  for (uint32_t i = b; i < e; i++) d |= doc[i] == '\\';
+  return d != 0;
 }
 // case-folded comparison with a lower-case literal (json-iterator's struct fields), exact comparison (gjson's Map())
 ARKS_HD bool key_is_fold(const uint8_t* doc, uint32_t pos, uint32_t n, const char* lit) {
@@ -258,45 +263,76 @@ ARKS_HD bool key_is(const uint8_t* doc, uint32_t pos, uint32_t n, const char* li
 }
 
 // ---- pass B: walk the bytes outside strings through the grammar; logs the members of the top-level object ----
-// returns the number of members logged, or -1 (not in the subset)
-ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, FastScratch& s, uint32_t nch) {
-  uint32_t g = G_TOP, depth = 0, stack = 0, nmem = 0, kstart = 0, pending = 0, bad = 0;
-  uint32_t w = 0, cur = nch ? s.tb[0] : 0;
-  for (;;) {
-    while (!cur) {
-      if (++w >= nch) goto done;
-      cur = s.tb[w];
-    }
-    {
-      const uint32_t pos = w * 32 + first_set(cur);
-      cur &= cur - 1;
-      const uint32_t e = T.tab[g * kFastTabStride + T.cls[doc[pos]]];
-      const uint32_t act = (e >> 5) & 7u;
-      g = e & 31u;
-      const bool top_obj = depth && ((stack >> (depth - 1)) & 1u);
-      // members of the top-level object: key span and the first byte of the value (depth is still the one BEFORE a push)
-      if ((e & F_KEYSTART) && depth == 1) kstart = pos + 1;
-      if ((e & F_KEYEND) && depth == 1) {
-        if (nmem >= kFastMaxMembers) bad = 1;
-        else { s.mem[3 * nmem] = kstart; s.mem[3 * nmem + 1] = pos - kstart; pending = 1; }
-      }
-      if ((e & F_VALSTART) && pending && depth == 1) { s.mem[3 * nmem + 2] = pos; nmem++; pending = 0; }
-      if (act == A_PUSH_OBJ || act == A_PUSH_ARR) {
-        if (depth >= 32) bad = 1;
-        else { stack = (stack & ~(1u << depth)) | ((act == A_PUSH_OBJ ? 1u : 0u) << depth); depth++; }
-      } else if (act == A_POP_OBJ || act == A_POP_ARR) {
-        if (!depth || top_obj != (act == A_POP_OBJ)) bad = 1;
-        else depth--;
-      } else if (act == A_COMMA) {
-        if (!depth) bad = 1;
-        g = top_obj ? G_KEY : G_VAL;
-      } else if (act == A_ERR) {
-        bad = 1;
-      }
-      if (bad) return -1;
-    }
+// Which byte comes next depends only on the bitmap, not on the grammar state, so the bytes are fetched kFastAhead at a time
+// (independent loads: the lane's memory latency is paid once per group, not once per byte) and then stepped in order.
+constexpr int kFastAhead = 8;
+struct TokCursor {  // iterates the set bits of the tb bitmap
+  uint32_t w, cur, nch;
+  ARKS_HD void init(const FastScratch& s, uint32_t nch_, uint32_t from) {
+    nch = nch_;
+    w = from >> 5;
+    cur = w < nch ? (s.tb(w) & (0xffffffffu << (from & 31))) : 0;
   }
-done:
+  ARKS_HD bool next(const FastScratch& s, uint32_t* pos) {
+    while (!cur) {
+      if (w + 1 >= nch) return false;
+      cur = s.tb(++w);
+    }
+    *pos = w * 32 + first_set(cur);
+    cur &= cur - 1;
+    return true;
+  }
+};
+// returns the number of members logged, or -1 (not in the subset)
+ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, const FastScratch& s, uint32_t nch) {
+  uint32_t g = G_TOP, depth = 0, stack = 0, nmem = 0, kstart = 0, pending = 0, bad = 0;
+  TokCursor tc;
+  tc.init(s, nch, 0);
+  for (;;) {
+    uint32_t pos[kFastAhead], by[kFastAhead];
+    int n = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 0; q < kFastAhead; q++) {
+      pos[q] = 0;
+      const bool have = tc.next(s, &pos[q]);
+      by[q] = have ? doc[pos[q]] : 0u;
+      n += have;
+    }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 0; q < kFastAhead; q++) {
+      if (q < n) {
+        const uint32_t e = T.tab[g * kFastTabStride + T.cls[by[q]]];
+        const uint32_t act = (e >> 5) & 7u;
+        g = e & 31u;
+        const bool top_obj = depth && ((stack >> (depth - 1)) & 1u);
+        // members of the top-level object: key span and the first byte of the value (depth is still the one BEFORE a push)
+        if ((e & F_KEYSTART) && depth == 1) kstart = pos[q] + 1;
+        if ((e & F_KEYEND) && depth == 1) {
+          if (nmem >= kFastMaxMembers) bad = 1;
+          else { s.mem(2 * nmem) = kstart | (pos[q] - kstart) << 16; pending = 1; }
+        }
+        if ((e & F_VALSTART) && pending && depth == 1) { s.mem(2 * nmem + 1) = pos[q]; nmem++; pending = 0; }
+        if (act == A_PUSH_OBJ || act == A_PUSH_ARR) {
+          if (depth >= 32) bad = 1;
+          else { stack = (stack & ~(1u << depth)) | ((act == A_PUSH_OBJ ? 1u : 0u) << depth); depth++; }
+        } else if (act == A_POP_OBJ || act == A_POP_ARR) {
+          if (!depth || top_obj != (act == A_POP_OBJ)) bad = 1;
+          else depth--;
+        } else if (act == A_COMMA) {
+          if (!depth) bad = 1;
+          g = top_obj ? G_KEY : G_VAL;
+        } else if (act == A_ERR) {
+          bad = 1;
+        }
+      }
+    }
+    if (bad) return -1;
+    if (n < kFastAhead) break;
+  }
   // the document is one complete object (numbers cannot be open here: the top-level value is an object)
   if (g != G_AFTER || depth != 0) return -1;
   return (int)nmem;
@@ -306,74 +342,98 @@ done:
 // the members of the object whose '{' is at `open`, for stream_options (K_REQ) / usage (K_RESP); false: not in the subset
 template <int KIND>
 ARKS_HD bool fast_inner_object(const uint8_t* doc, const FastScratch& s, uint32_t nch, uint32_t open, FastOut& o) {
-  uint32_t rel = 1, in_str = 0, is_key = 0, expect_key = 1, ks = 0, seen = 0, nd = 0;
+  uint32_t rel = 1, in_str = 0, is_key = 0, expect_key = 1, ks = 0, seen = 0, nd = 0, ok = 1, done = 0;
   int which = -1;  // the member whose value is being read: 0..2 usage counters, 3 include_usage
   int64_t acc = 0;
-  uint32_t p = open;
-  for (uint32_t it = 0;; it++) {
+  TokCursor tc;
+  tc.init(s, nch, open + 1);
+  for (uint32_t it = 0; !done; it += kFastAhead) {
     if (it >= kFastMiniCap) return false;
-    p = next_token(s.tb, nch, p + 1, 0xffffffffu);
-    if (p == 0xffffffffu) return false;
-    const uint8_t b = doc[p];
-    if (in_str) {  // the closing quote
-      in_str = 0;
-      if (is_key) {
-        const uint32_t n = p - ks;
-        if (any_backslash(s.bm, ks, p)) return false;  // may be an escaped spelling of a name that is read
-        which = -1;
-        if (KIND == K_REQ) {
-          if (n == 13 && key_is_fold(doc, ks, n, "include_usage")) which = 3;
-        } else {
-          if (n == 13 && key_is(doc, ks, n, "prompt_tokens")) which = 0;
-          else if (n == 17 && key_is(doc, ks, n, "completion_tokens")) which = 1;
-          else if (n == 12 && key_is(doc, ks, n, "total_tokens")) which = 2;
+    uint32_t pos[kFastAhead], by[kFastAhead];
+    int n = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 0; q < kFastAhead; q++) {
+      pos[q] = 0;
+      const bool have = tc.next(s, &pos[q]);
+      by[q] = have ? doc[pos[q]] : 0u;
+      n += have;
+    }
+    if (n == 0) return false;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 0; q < kFastAhead; q++) {
+      if (q >= n || done || !ok) continue;
+      const uint32_t p = pos[q];
+      const uint8_t b = (uint8_t)by[q];
+      if (in_str) {  // the closing quote
+        in_str = 0;
+        if (is_key) {
+          const uint32_t len = p - ks;
+          if (any_backslash(doc, s, ks, p)) { ok = 0; continue; }  // may be an escaped spelling of a name that is read
+          which = -1;
+          if (KIND == K_REQ) {
+            if (len == 13 && key_is_fold(doc, ks, len, "include_usage")) which = 3;
+          } else {
+            if (len == 13 && key_is(doc, ks, len, "prompt_tokens")) which = 0;
+            else if (len == 17 && key_is(doc, ks, len, "completion_tokens")) which = 1;
+            else if (len == 12 && key_is(doc, ks, len, "total_tokens")) which = 2;
+          }
+          if (which >= 0) {
+            if (seen & (1u << which)) { ok = 0; continue; }  // duplicates: exact engine
+            seen |= 1u << which;
+            acc = 0; nd = 0;
+          }
         }
-        if (which >= 0) {
-          if (seen & (1u << which)) return false;  // duplicates: exact engine
-          seen |= 1u << which;
-          acc = 0; nd = 0;
+        continue;
+      }
+      if (b == '"') {
+        in_str = 1;
+        is_key = rel == 1 && expect_key;
+        ks = p + 1;
+        if (is_key) expect_key = 0;
+        else if (rel == 1 && which >= 0) ok = 0;  // a counter / flag written as a string: exact engine (gjson rules)
+        continue;
+      }
+      if (b == '{' || b == '[') {
+        if (rel == 1 && which >= 0) ok = 0;
+        rel++;
+        continue;
+      }
+      const bool closes = b == '}' || b == ']';
+      if (closes || (b == ',' && rel == 1)) {
+        if (rel == 1 && which >= 0) {  // the value of a member that is read ends here
+          if (which == 3) { if (nd == 0) ok = 0; }
+          else if (nd == 0 || nd > 18) ok = 0;
+          else if (which == 0) o.usage[0] = acc;  // (no dynamic index: the counters stay in registers)
+          else if (which == 1) o.usage[1] = acc;
+          else o.usage[2] = acc;
+          which = -1;
+        }
+        if (closes) { if (--rel == 0) done = 1; }
+        else expect_key = 1;
+        continue;
+      }
+      if (rel == 1 && which >= 0 && b != ':' && !(b == ' ' || b == '\t' || b == '\n' || b == '\r')) {
+        if (which == 3) {  // OptionalDecoder{boolCodec}: true / false / null (the grammar pass checked the spelling)
+          if (nd == 0) {
+            if (!(b == 't' || b == 'f' || b == 'n')) ok = 0;
+            o.iu3 = b == 'n' ? 0u : b == 'f' ? 1u : 2u;
+          }
+          nd++;
+        } else {  // a plain non-negative integer; anything else (sign, fraction, exponent, literal): exact engine
+          if ((uint32_t)(b - '0') > 9u) ok = 0;
+          acc = acc * 10 + (int64_t)(b - '0');
+          nd++;
         }
       }
-      continue;
     }
-    if (b == '"') {
-      in_str = 1;
-      is_key = rel == 1 && expect_key;
-      ks = p + 1;
-      if (is_key) expect_key = 0;
-      else if (rel == 1 && which >= 0) return false;  // a counter / flag written as a string: exact engine (gjson rules)
-      continue;
-    }
-    if (b == '{' || b == '[') {
-      if (rel == 1 && which >= 0) return false;
-      rel++;
-      continue;
-    }
-    const bool closes = b == '}' || b == ']';
-    if (closes || (b == ',' && rel == 1)) {
-      if (rel == 1 && which >= 0) {  // the value of a member that is read ends here
-        if (which == 3) { if (nd == 0) return false; }
-        else { if (nd == 0 || nd > 18) return false; o.usage[which] = acc; }
-        which = -1;
-      }
-      if (closes) { if (--rel == 0) return true; }
-      else expect_key = 1;
-      continue;
-    }
-    if (rel == 1 && which >= 0 && b != ':' && !(b == ' ' || b == '\t' || b == '\n' || b == '\r')) {
-      if (which == 3) {  // OptionalDecoder{boolCodec}: true / false / null (the grammar pass checked the spelling)
-        if (nd == 0) {
-          if (!(b == 't' || b == 'f' || b == 'n')) return false;
-          o.iu3 = b == 'n' ? 0u : b == 'f' ? 1u : 2u;
-        }
-        nd++;
-      } else {  // a plain non-negative integer; anything else (sign, fraction, exponent, literal): exact engine
-        if ((uint32_t)(b - '0') > 9u) return false;
-        acc = acc * 10 + (int64_t)(b - '0');
-        nd++;
-      }
-    }
+    if (!ok) return false;
+    if (n < kFastAhead && !done) return false;
   }
+  return true;
 }
 
 template <int KIND>
@@ -383,9 +443,10 @@ ARKS_HD bool fast_members(const uint8_t* doc, const FastScratch& s, uint32_t nch
   o.usage[0] = o.usage[1] = o.usage[2] = 0;
   uint32_t seen = 0;  // bit 0 model, 1 stream, 2 stream_options, 3 usage
   for (int m = 0; m < nmem; m++) {
-    const uint32_t kpos = s.mem[3 * m], klen = s.mem[3 * m + 1], vpos = s.mem[3 * m + 2];
+    const uint32_t kk = s.mem(2 * m), vpos = s.mem(2 * m + 1);
+    const uint32_t kpos = kk & 0xffffu, klen = kk >> 16;
     // a key with an escape may DECODE to a field name whatever its raw length: exact engine (json-iterator decodes, then hashes)
-    if (any_backslash(s.bm, kpos, kpos + klen)) return false;
+    if (any_backslash(doc, s, kpos, kpos + klen)) return false;
     int what = -1;
     if (klen == 5 && key_is_fold(doc, kpos, 5, "model")) what = 0;
     else if (KIND == K_REQ && klen == 6 && key_is_fold(doc, kpos, 6, "stream")) what = 1;
@@ -397,11 +458,11 @@ ARKS_HD bool fast_members(const uint8_t* doc, const FastScratch& s, uint32_t nch
     const uint8_t vb = doc[vpos];
     if (what == 0) {  // stringCodec: string or null
       if (vb == '"') {
-        const uint32_t end = next_token(s.tb, nch, vpos + 1, 0xffffffffu);  // the closing quote
+        const uint32_t end = next_token(s, nch, vpos + 1, 0xffffffffu);  // the closing quote (the next byte outside strings)
         if (end == 0xffffffffu) return false;
         o.m_rawlen = end - vpos - 1;
         o.m_start = o.m_rawlen ? vpos + 1 : 0;
-        o.m_esc = o.m_rawlen && any_backslash(s.bm, vpos + 1, end) ? 1u : 0u;
+        o.m_esc = o.m_rawlen && any_backslash(doc, s, vpos + 1, end) ? 1u : 0u;
       } else if (vb != 'n') {
         return false;  // a model of another JSON type is a decode error: the exact engine reports it
       }
@@ -429,11 +490,12 @@ static const FastTablesInit kFastTablesHost{};
 template <int KIND>
 inline bool fast_scan_host(const uint8_t* doc, uint32_t len, FastOut& out) {
   if (len == 0 || len > kFastMaxLen) return false;
-  static thread_local FastScratch s;
+  static thread_local uint32_t tb[kFastChunks], mem[2 * kFastMaxMembers];
+  FastScratch s{tb, mem, 1, 0, 0};
   const uint32_t nch = (len + 31) / 32;
   FastCarry c{0, 0, 0};
   for (uint32_t j = 0; j < nch; j++) {
-    uint32_t w[8];
+    uint32_t w[8], bm;
     for (int q = 0; q < 8; q++) {
       uint32_t v = 0;
       for (int b = 0; b < 4; b++) {
@@ -442,7 +504,8 @@ inline bool fast_scan_host(const uint8_t* doc, uint32_t len, FastOut& out) {
       }
       w[q] = v;
     }
-    fast_chunk(w, len - 32 * j < 32 ? len - 32 * j : 32, doc, len, 32 * j, c, &s.tb[j], &s.bm[j]);
+    fast_chunk(w, len - 32 * j < 32 ? len - 32 * j : 32, doc, len, 32 * j, c, &s.tb(j), &bm);
+    if (bm) { if (j < 32) s.bs_lo |= 1u << j; else s.bs_hi |= 1u << (j - 32); }
   }
   if (c.bad || c.in_str) return false;
   const int nmem = fast_walk(doc, kFastTablesHost.t, s, nch);

@@ -10,12 +10,13 @@ N = 65536
 w = traffic.Workload(10000, seed=1)
 g = Gateway(0, N, 120 << 20); g.load_tables(w.tables)
 now = 1_700_000_000
-req = w.request_batch(N, now, seed=5, body_size=1024, n_templates=8192, varied=True)
+NT = int(os.environ.get("PROF_TEMPLATES", "0"))  # 0: every body distinct (the bench workload)
+req = w.request_batch(N, now, seed=5, body_size=1024, n_templates=NT, varied=True)
 for k in range(4):
     req.now_unix = now + 86400 * k
     a = g.handle_request_body(req)
     if k == 0:
-        resp = w.response_batch(a, now + 1, seed=6, body_size=600, varied=True, n_templates=8192)
+        resp = w.response_batch(a, now + 1, seed=6, body_size=600, varied=True, n_templates=NT)
     resp.now_unix = now + 86400 * k + 1
     g.handle_response_body(resp)
 print("done", int((a.reason == 0).sum()))
