@@ -590,6 +590,7 @@ struct __align__(128) FastBlockSmem {
   uint64_t bar;
   uint32_t tb[kFastChunks * kFastThreads];
   uint32_t mem[2 * kFastMaxMembers * kFastThreads];
+  uint32_t ring[16 * kFastThreads];  // the current and the next chunk of every lane (dynamic byte access for escapes)
 };
 
 // passes A-C for the body of one lane; false: declined (or not eligible).
@@ -599,7 +600,8 @@ struct __align__(128) FastBlockSmem {
 template <int KIND>
 __device__ __forceinline__ bool fast_scan_lane(const uint8_t* body, uint32_t len, FastBlockSmem& sm, FastOut& o) {
   if (len == 0 || len > kFastMaxLen) return false;
-  FastScratch s{sm.tb + threadIdx.x, sm.mem + threadIdx.x, (uint32_t)kFastThreads, 0u, 0u};
+  FastScratch s{sm.tb + threadIdx.x, sm.mem + threadIdx.x, (uint32_t)kFastThreads, 0u, 0u, 0u, 0u};
+  const FastRing ring{sm.ring + threadIdx.x, (uint32_t)kFastThreads};
   const uint32_t nch = (len + 31) >> 5, plen = (len + 15u) & ~15u;
   FastCarry c{0, 0, 0};
   const uint4* p = reinterpret_cast<const uint4*>(body);
@@ -607,14 +609,25 @@ __device__ __forceinline__ bool fast_scan_lane(const uint8_t* body, uint32_t len
   auto lo = [&](uint32_t j) { return j < nch ? ld_nc_v4(p + 2 * j) : z; };
   auto hi = [&](uint32_t j) { return j < nch && 32 * j + 16 < plen ? ld_nc_v4(p + 2 * j + 1) : z; };  // never past the 16-byte padding
   uint4 a0 = lo(0), b0 = hi(0), a1 = lo(1), b1 = hi(1), a2 = lo(2), b2 = hi(2), a3 = lo(3), b3 = hi(3);
+  {
+    const uint32_t w0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+    ring.put(0, w0);
+  }
 #pragma unroll 1
   for (uint32_t j = 0; j < nch; j++) {
     const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
     a0 = a1; b0 = b1; a1 = a2; b1 = b2; a2 = a3; b2 = b3;
     a3 = lo(j + 4); b3 = hi(j + 4);
-    uint32_t bm;
-    fast_chunk(w, min(len - 32 * j, 32u), body, len, 32 * j, c, &s.tb(j), &bm);
-    if (bm) { if (j < 32) s.bs_lo |= 1u << j; else s.bs_hi |= 1u << (j - 32); }
+    {
+      const uint32_t wn[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+      ring.put(j + 1, wn);  // the chunk after the current one is at hand too (a \uXXXX may straddle the boundary)
+    }
+    uint32_t bm, tbw;
+    fast_chunk(w, min(len - 32 * j, 32u), ring, len, 32 * j, c, &tbw, &bm);
+    s.tb(j) = tbw;
+    const uint32_t bit = 1u << (j & 31);
+    if (j < 32) { s.bs_lo |= bm ? bit : 0u; s.nz_lo |= tbw ? bit : 0u; }
+    else { s.bs_hi |= bm ? bit : 0u; s.nz_hi |= tbw ? bit : 0u; }
   }
   if (c.bad || c.in_str) return false;
   const int nmem = fast_walk(body, sm.tabs, s, nch);

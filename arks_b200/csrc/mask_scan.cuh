@@ -51,8 +51,24 @@ struct FastScratch {
   uint32_t* mem_;   // 2 * kFastMaxMembers words: key pos | key len << 16, value pos
   uint32_t stride;
   uint32_t bs_lo, bs_hi;  // chunk j contains a backslash (bit j): lets the key / model checks skip the byte scan
+  uint32_t nz_lo, nz_hi;  // chunk j has bytes outside strings (tb(j) != 0): the token cursor jumps over the others
   ARKS_HD uint32_t& tb(uint32_t j) const { return tb_[j * stride]; }
   ARKS_HD uint32_t& mem(uint32_t j) const { return mem_[j * stride]; }
+};
+// the two chunks pass A has at hand (the current one and the next), as words a lane can index dynamically: shared memory
+// on the device (registers cannot be indexed), element k of slot c & 1 at ring[((c & 1) * 8 + k) * stride]
+struct FastRing {
+  uint32_t* ring;
+  uint32_t stride;
+  ARKS_HD void put(uint32_t chunk, const uint32_t w[8]) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < 8; k++) ring[((chunk & 1u) * 8 + k) * stride] = w[k];
+  }
+  ARKS_HD uint8_t byte_at(uint32_t p) const {  // p inside the current or the next chunk
+    return (uint8_t)(ring[((((p >> 5) & 1u) * 8) + ((p >> 2) & 7u)) * stride] >> (8 * (p & 3u)));
+  }
 };
 
 // ---- byte-plane SWAR: bit 7 of every byte that is zero, exact ----
@@ -93,7 +109,7 @@ struct FastCarry {
   uint32_t in_str;  // the next chunk starts inside a string
   uint32_t bad;
 };
-ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const uint8_t* doc, uint32_t len, uint32_t base, FastCarry& c,
+ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const FastRing& ring, uint32_t len, uint32_t base, FastCarry& c,
                         uint32_t* tb_out, uint32_t* bm_out) {
   uint32_t Q = 0, B = 0, anyc = 0;
 #ifdef __CUDA_ARCH__
@@ -103,8 +119,9 @@ ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const uint8_t* doc
     const uint32_t x = w[j];
     Q |= plane_nibble(zero_bytes(x ^ 0x22222222u)) << (4 * j);
     B |= plane_nibble(zero_bytes(x ^ 0x5c5c5c5cu)) << (4 * j);
-    anyc |= zero_bytes(x & 0xe0e0e0e0u);
+    anyc |= (x - 0x20202020u) & ~x;  // bit 7 of a byte < 0x20 (and maybe of a neighbour: only a filter for the exact test)
   }
+  anyc &= 0x80808080u;
   const uint32_t V = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
   Q &= V;
   B &= V;
@@ -128,9 +145,9 @@ ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const uint8_t* doc
   while (e) {  // rare: what follows each backslash must be an escape RFC 8259 knows
     const uint32_t p = base + first_set(e);
     e &= e - 1;
-    const uint8_t ch = doc[p];
+    const uint8_t ch = ring.byte_at(p);
     if (ch == 'u') {
-      if (p + 4 >= len || (hexval(doc[p + 1]) | hexval(doc[p + 2]) | hexval(doc[p + 3]) | hexval(doc[p + 4])) < 0) bad = 1;
+      if (p + 4 >= len || (hexval(ring.byte_at(p + 1)) | hexval(ring.byte_at(p + 2)) | hexval(ring.byte_at(p + 3)) | hexval(ring.byte_at(p + 4))) < 0) bad = 1;
     } else if (!(ch == '"' || ch == '\\' || ch == '/' || ch == 'b' || ch == 'f' || ch == 'n' || ch == 'r' || ch == 't')) {
       bad = 1;
     }
@@ -266,17 +283,22 @@ ARKS_HD bool key_is(const uint8_t* doc, uint32_t pos, uint32_t n, const char* li
 // Which byte comes next depends only on the bitmap, not on the grammar state, so the bytes are fetched kFastAhead at a time
 // (independent loads: the lane's memory latency is paid once per group, not once per byte) and then stepped in order.
 constexpr int kFastAhead = 8;
-struct TokCursor {  // iterates the set bits of the tb bitmap
-  uint32_t w, cur, nch;
-  ARKS_HD void init(const FastScratch& s, uint32_t nch_, uint32_t from) {
-    nch = nch_;
+struct TokCursor {  // iterates the set bits of the tb bitmap, jumping over empty chunks with the nz bitmap
+  uint32_t w, cur, nz_lo, nz_hi;
+  ARKS_HD void init(const FastScratch& s, uint32_t nch, uint32_t from) {
     w = from >> 5;
     cur = w < nch ? (s.tb(w) & (0xffffffffu << (from & 31))) : 0;
+    // chunks after w that are not empty
+    const uint64_t nz = ((uint64_t)s.nz_hi << 32 | s.nz_lo) & (w >= 63 ? 0ull : ~0ull << (w + 1));
+    nz_lo = (uint32_t)nz;
+    nz_hi = (uint32_t)(nz >> 32);
   }
   ARKS_HD bool next(const FastScratch& s, uint32_t* pos) {
-    while (!cur) {
-      if (w + 1 >= nch) return false;
-      cur = s.tb(++w);
+    if (!cur) {
+      if (nz_lo) { w = first_set(nz_lo); nz_lo &= nz_lo - 1; }
+      else if (nz_hi) { w = 32 + first_set(nz_hi); nz_hi &= nz_hi - 1; }
+      else return false;
+      cur = s.tb(w);
     }
     *pos = w * 32 + first_set(cur);
     cur &= cur - 1;
@@ -310,12 +332,14 @@ ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, const FastScratch
         g = e & 31u;
         const bool top_obj = depth && ((stack >> (depth - 1)) & 1u);
         // members of the top-level object: key span and the first byte of the value (depth is still the one BEFORE a push)
-        if ((e & F_KEYSTART) && depth == 1) kstart = pos[q] + 1;
-        if ((e & F_KEYEND) && depth == 1) {
-          if (nmem >= kFastMaxMembers) bad = 1;
-          else { s.mem(2 * nmem) = kstart | (pos[q] - kstart) << 16; pending = 1; }
+        if ((e & (F_KEYSTART | F_KEYEND | F_VALSTART)) && depth == 1) {
+          if (e & F_KEYSTART) kstart = pos[q] + 1;
+          if (e & F_KEYEND) {
+            if (nmem >= kFastMaxMembers) bad = 1;
+            else { s.mem(2 * nmem) = kstart | (pos[q] - kstart) << 16; pending = 1; }
+          }
+          if ((e & F_VALSTART) && pending) { s.mem(2 * nmem + 1) = pos[q]; nmem++; pending = 0; }
         }
-        if ((e & F_VALSTART) && pending && depth == 1) { s.mem(2 * nmem + 1) = pos[q]; nmem++; pending = 0; }
         if (act == A_PUSH_OBJ || act == A_PUSH_ARR) {
           if (depth >= 32) bad = 1;
           else { stack = (stack & ~(1u << depth)) | ((act == A_PUSH_OBJ ? 1u : 0u) << depth); depth++; }
@@ -490,12 +514,12 @@ static const FastTablesInit kFastTablesHost{};
 template <int KIND>
 inline bool fast_scan_host(const uint8_t* doc, uint32_t len, FastOut& out) {
   if (len == 0 || len > kFastMaxLen) return false;
-  static thread_local uint32_t tb[kFastChunks], mem[2 * kFastMaxMembers];
-  FastScratch s{tb, mem, 1, 0, 0};
+  static thread_local uint32_t tb[kFastChunks], mem[2 * kFastMaxMembers], ringw[16];
+  FastScratch s{tb, mem, 1, 0, 0, 0, 0};
+  const FastRing ring{ringw, 1};
   const uint32_t nch = (len + 31) / 32;
   FastCarry c{0, 0, 0};
-  for (uint32_t j = 0; j < nch; j++) {
-    uint32_t w[8], bm;
+  auto words_of = [&](uint32_t j, uint32_t w[8]) {
     for (int q = 0; q < 8; q++) {
       uint32_t v = 0;
       for (int b = 0; b < 4; b++) {
@@ -504,8 +528,18 @@ inline bool fast_scan_host(const uint8_t* doc, uint32_t len, FastOut& out) {
       }
       w[q] = v;
     }
-    fast_chunk(w, len - 32 * j < 32 ? len - 32 * j : 32, doc, len, 32 * j, c, &s.tb(j), &bm);
+  };
+  uint32_t w[8], wn[8];
+  words_of(0, w);
+  ring.put(0, w);
+  for (uint32_t j = 0; j < nch; j++) {
+    uint32_t bm;
+    words_of(j + 1, wn);
+    ring.put(j + 1, wn);  // the chunk after the current one is at hand too (a \uXXXX may straddle the boundary)
+    fast_chunk(w, len - 32 * j < 32 ? len - 32 * j : 32, ring, len, 32 * j, c, &s.tb(j), &bm);
     if (bm) { if (j < 32) s.bs_lo |= 1u << j; else s.bs_hi |= 1u << (j - 32); }
+    if (s.tb(j)) { if (j < 32) s.nz_lo |= 1u << j; else s.nz_hi |= 1u << (j - 32); }
+    for (int q = 0; q < 8; q++) w[q] = wn[q];
   }
   if (c.bad || c.in_str) return false;
   const int nmem = fast_walk(doc, kFastTablesHost.t, s, nch);
