@@ -82,7 +82,7 @@ class ArksResponseBatch(C.Structure):
 
 
 class ArksResponseResult(C.Structure):
-    _fields_ = [("reason", u8p), ("counted", u8p), ("usage", i64p)]
+    _fields_ = [("reason", u8p), ("counted", u8p), ("usage", i64p), ("bpe_count", u32p)]
 
 
 def ptr(a: np.ndarray, ty):
@@ -216,13 +216,15 @@ class ResponseResult:
     reason: np.ndarray
     counted: np.ndarray
     usage: np.ndarray
+    bpe_count: np.ndarray = None
 
     @classmethod
     def empty(cls, n):
-        return cls(np.full(n, 255, np.uint8), np.full(n, 255, np.uint8), np.full((n, 3), -7, np.int64))
+        return cls(np.full(n, 255, np.uint8), np.full(n, 255, np.uint8), np.full((n, 3), -7, np.int64),
+                   np.full(n, 0xEEEEEEEE, np.uint32))
 
     def c_struct(self) -> ArksResponseResult:
-        return ArksResponseResult(ptr(self.reason, u8p), ptr(self.counted, u8p), ptr(self.usage, i64p))
+        return ArksResponseResult(ptr(self.reason, u8p), ptr(self.counted, u8p), ptr(self.usage, i64p), ptr(self.bpe_count, u32p))
 
     def fields(self):
         return {"reason": self.reason, "counted": self.counted, "usage": self.usage}

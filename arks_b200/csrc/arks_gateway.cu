@@ -37,6 +37,7 @@
 #include "../../include/arks_gateway.h"
 #include "json_engine.cuh"
 #include "mask_scan.cuh"
+#include "bpe.cuh"
 
 using namespace arks;
 
@@ -138,6 +139,7 @@ struct RespDev {
   long long* usage;  // 3n
   uint32_t* slow_list;  // two-stage scan: the bodies left to the exact engine
   uint32_t* slow_n;
+  uint32_t* bpe;        // BPE tokens of the completion text (0 without a vocabulary)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1118,6 +1120,60 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, ARKS_SSE_MINBLK) scan_sse
   account_usage(T, B, i, live, qos, acct, reason, counted, u0, u1, u2);
 }
 
+// ------------------------------------------------------------------------------------------------
+// BPE token counting (bpe.cuh): a side output of both phases, two kernels behind the scan stage.
+// ------------------------------------------------------------------------------------------------
+// pass 1: one lane per body. Decoded `content` strings go to `text` (same offsets as the bodies), every pre-token becomes
+// a work-list entry: text offset | (length - 1) << 32 | body << 40. Entries are handed out 32 at a time (one atomic per flush).
+constexpr int kBpeFlush = 32;
+__global__ void __launch_bounds__(128) bpe_scan_kernel(const uint8_t* bodies, const uint32_t* body_off, const uint32_t* body_len, uint32_t n,
+                                                       BpeTablesDev T, uint8_t* text, unsigned long long* list, uint32_t* list_n,
+                                                       uint32_t list_cap, uint32_t* bpe_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t off = body_off[i];
+  unsigned long long buf[kBpeFlush];
+  uint32_t nb = 0, overflow = 0;
+  auto flush = [&]() {
+    if (!nb) return;
+    const uint32_t at = atomicAdd(list_n, nb);
+    if (at + nb > list_cap) overflow = 1;  // (the counter may run past the capacity: the merge kernel clamps it)
+    else
+      for (uint32_t k = 0; k < nb; k++) list[at + k] = buf[k];
+    nb = 0;
+  };
+  const BpeScanOut o = bpe_scan_body(bodies + off, body_len[i], text + off, T, [&](uint32_t s, uint32_t len) {
+    buf[nb++] = (unsigned long long)(off + s) | (unsigned long long)(len - 1) << 32 | (unsigned long long)i << 40;
+    if (nb == kBpeFlush) flush();
+  });
+  flush();
+  bpe_out[i] = (o.bad || overflow) ? kBpeUncounted : 0u;
+}
+// pass 2: one lane per pre-token (grid-stride over the work list). The hot merges come from shared memory, staged by one
+// bulk copy (TMA) per block; the rest of the merge table is read through L2.
+constexpr int kBpeMergeThreads = 256;
+__global__ void __launch_bounds__(kBpeMergeThreads) bpe_merge_kernel(const unsigned long long* list, const uint32_t* list_n, uint32_t list_cap,
+                                                                    BpeTablesDev T, const uint8_t* text, uint32_t* bpe_out) {
+  __shared__ __align__(128) BpeSlot hot[kBpeHotSlots];
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&bar, (uint32_t)sizeof(hot));
+    bulk_g2s(hot, T.hot, (uint32_t)sizeof(hot), &bar);
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  const uint32_t total = min(*list_n, list_cap);
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+    const unsigned long long e = list[k];
+    const uint32_t off = (uint32_t)e, len = ((uint32_t)(e >> 32) & 0xffu) + 1u, body = (uint32_t)(e >> 40);
+    if (bpe_out[body] == kBpeUncounted) continue;  // written by pass 1, never by this kernel
+    const uint32_t ntok = bpe_piece_tokens(text + off, len, hot, T);
+    atomicAdd(&bpe_out[body], ntok);
+  }
+}
+
 // syncQuotaUsage (arks_impl.go:226-296): one lane per ArksQuota, in place on the device copies of the CR status
 __global__ void sync_quota_kernel(const uint32_t* item_off, const uint8_t* item_type, long long* quota, uint32_t n_quotas, int restore,
                                   uint32_t* present, long long* used, uint8_t* action) {
@@ -1192,6 +1248,14 @@ struct arks_ctx {
   long long* d_qexp = nullptr;     // what the last arks_export_quota_delta_dev handed out
   bool qexp_valid = false;
   bool share_quota = false;
+  // BPE side output (arks_load_bpe): tables + per-batch scratch
+  bool bpe_on = false;
+  BpeTablesDev bpe{};
+  std::vector<void*> bpe_allocs;
+  uint8_t* d_bpe_text = nullptr;            // decoded `content` strings, laid out like the bodies
+  unsigned long long* d_bpe_list = nullptr; // work list of pre-tokens
+  uint32_t* d_bpe_n = nullptr;
+  uint32_t bpe_list_cap = 0;
   uint32_t generation = 0;                  // bumped by every successful arks_load_tables
   std::deque<std::vector<int32_t>> remap;   // remap[k]: qos index of generation (generation - remap.size() + k) -> the next one, or -1
   int32_t* d_backend_weight = nullptr;
@@ -1231,6 +1295,10 @@ struct arks_ctx {
   int ev_n = 0;
   cudaEvent_t ev_fast[2] = {nullptr, nullptr};  // around the fast-path kernel alone (roofline of the dominant kernel)
   bool ev_fast_set = false;
+  cudaEvent_t ev_bpe[2] = {nullptr, nullptr};   // around the two BPE kernels
+  bool ev_bpe_set = false;
+  cudaEvent_t ev_admit0 = nullptr;              // start of rank_hot + limit_admit (after the BPE kernels)
+  bool is_req_timing = false;
   bool last_two_stage = false;
   uint8_t* d_inter = nullptr;    // intermediates + group table
   uint32_t* d_perm = nullptr;    // lane -> body permutation of the batch being scanned (length order)
@@ -1324,6 +1392,8 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   ctx->meta_cap = align_up(n * 4, 256) * 4 + align_up(n * 8, 256) + align_up(n, 256) + align_up(n * 256, 256) + kSmallBatchBytes + 256;
   for (int k = 0; k < 4; k++) CK(cudaEventCreate(&ctx->ev[k]));
   for (int k = 0; k < 2; k++) CK(cudaEventCreate(&ctx->ev_fast[k]));
+  for (int k = 0; k < 2; k++) CK(cudaEventCreate(&ctx->ev_bpe[k]));
+  CK(cudaEventCreate(&ctx->ev_admit0));
 #define ARKS_FOR_SCHED(X) X(0) X(1) X(8)
 #define ARKS_SET(S)                                                                                                        \
   CK(cudaFuncSetAttribute(scan_request_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock));     \
@@ -1392,11 +1462,18 @@ void arks_destroy(arks_ctx* ctx) {
   }
   for (int k = 0; k < 4; k++)
     if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
-  for (int k = 0; k < 2; k++)
+  for (int k = 0; k < 2; k++) {
     if (ctx->ev_fast[k]) cudaEventDestroy(ctx->ev_fast[k]);
+    if (ctx->ev_bpe[k]) cudaEventDestroy(ctx->ev_bpe[k]);
+  }
+  if (ctx->ev_admit0) cudaEventDestroy(ctx->ev_admit0);
   cudaFree(ctx->d_inter);
   cudaFree(ctx->d_perm);
   cudaFree(ctx->d_slow);
+  for (void* p : ctx->bpe_allocs) cudaFree(p);
+  cudaFree(ctx->d_bpe_text);
+  cudaFree(ctx->d_bpe_list);
+  cudaFree(ctx->d_bpe_n);
 
   cudaFree(ctx->d_lenhist);
   cudaFree(ctx->d_result);
@@ -1463,6 +1540,58 @@ void* arks_alloc_pinned(size_t bytes) {
 }
 void arks_free_pinned(void* p) {
   if (p) cudaFreeHost(p);
+}
+
+// ---- BPE side output ------------------------------------------------------------------------------
+int arks_load_bpe(arks_ctx* ctx, const arks_bpe_tables* t) {
+  if (!ctx) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (void* p : ctx->bpe_allocs) cudaFree(p);
+  ctx->bpe_allocs.clear();
+  ctx->bpe_on = false;
+  if (!t) return 0;
+  if (!t->byte_id || !t->cp_class || (t->n_merges && (!t->left || !t->right || !t->merged))) return fail(ctx, ARKS_E_INVALID_ARG, "incomplete BPE tables");
+  std::vector<BpeSlot> table, hot;
+  const uint32_t slots = bpe_table_slots(t->n_merges);
+  bpe_fill_table(table, slots, t->left, t->right, t->merged, t->n_merges);
+  bpe_fill_table(hot, kBpeHotSlots, t->left, t->right, t->merged, t->n_merges < kBpeHotMerges ? t->n_merges : kBpeHotMerges);
+  auto up = [&](const void* src, size_t bytes, const void** out) -> int {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes + 64));
+    ctx->bpe_allocs.push_back(p);
+    CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+    *out = p;
+    return 0;
+  };
+  BpeTablesDev d{};
+  int rc;
+  if ((rc = up(t->byte_id, 256 * 4, (const void**)&d.byte_id))) return rc;
+  if ((rc = up(table.data(), table.size() * sizeof(BpeSlot), (const void**)&d.table))) return rc;
+  if ((rc = up(hot.data(), hot.size() * sizeof(BpeSlot), (const void**)&d.hot))) return rc;
+  if ((rc = up(t->cp_class, 0x110000 / 2, (const void**)&d.cp_class))) return rc;
+  d.table_mask = slots - 1;
+  d.flags = t->flags;
+  if (!ctx->d_bpe_text) {
+    // a pre-token is rarely shorter than three bytes on average; bodies whose entries do not fit are reported uncounted
+    ctx->bpe_list_cap = (uint32_t)std::min<uint64_t>(ctx->max_bytes / 3 + 1024, 0xfffffff0ull);
+    CK(cudaMalloc(&ctx->d_bpe_text, ctx->max_bytes + 64));
+    CK(cudaMalloc(&ctx->d_bpe_list, (size_t)ctx->bpe_list_cap * 8));
+    CK(cudaMalloc(&ctx->d_bpe_n, 256));
+  }
+  ctx->bpe = d;
+  ctx->bpe_on = true;
+  return 0;
+}
+// queue the two BPE kernels for `n` bodies on the compute stream; counts land in bpe_out
+static int queue_bpe(arks_ctx* ctx, const uint8_t* bodies, const uint32_t* body_off, const uint32_t* body_len, uint32_t n, uint32_t* bpe_out) {
+  CK(cudaMemsetAsync(ctx->d_bpe_n, 0, 4, ctx->stream));
+  bpe_scan_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(bodies, body_off, body_len, n, ctx->bpe, ctx->d_bpe_text, ctx->d_bpe_list,
+                                                            ctx->d_bpe_n, ctx->bpe_list_cap, bpe_out);
+  bpe_merge_kernel<<<ctx->n_sm * 4, kBpeMergeThreads, 0, ctx->stream>>>(ctx->d_bpe_list, ctx->d_bpe_n, ctx->bpe_list_cap, ctx->bpe,
+                                                                        ctx->d_bpe_text, bpe_out);
+  ctx->launches += 2;
+  return 0;
 }
 
 // ---- config plane -------------------------------------------------------------------------------
@@ -1753,13 +1882,19 @@ int arks_last_kernel_ms(arks_ctx* ctx, float* ms, int cap) {
   if (!ctx || !ms) return ARKS_E_INVALID_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
-  int n = ctx->ev_n > 0 ? ctx->ev_n - 1 : 0;
-  for (int k = 0; k < n && k < cap; k++) CK(cudaEventElapsedTime(&ms[k], ctx->ev[k], ctx->ev[k + 1]));
-  if (ctx->ev_fast_set && n < cap) {  // one more entry: the fast-path kernel of the two-stage scan on its own
-    CK(cudaEventElapsedTime(&ms[n], ctx->ev_fast[0], ctx->ev_fast[1]));
-    n++;
-  }
-  return n;
+  if (ctx->ev_n == 0) return 0;
+  // request: scan stage, rank_hot + limit_admit, fast-path kernel alone (0 if not used), BPE kernels (0 if off)
+  // response: scan stage, fast-path kernel alone, BPE kernels
+  float v[4] = {0, 0, 0, 0};
+  int n = 0;
+  CK(cudaEventElapsedTime(&v[n++], ctx->ev[0], ctx->ev[1]));
+  if (ctx->is_req_timing) CK(cudaEventElapsedTime(&v[n++], ctx->ev_admit0, ctx->ev[2]));
+  if (ctx->ev_fast_set) CK(cudaEventElapsedTime(&v[n], ctx->ev_fast[0], ctx->ev_fast[1]));
+  n++;
+  if (ctx->ev_bpe_set) CK(cudaEventElapsedTime(&v[n], ctx->ev_bpe[0], ctx->ev_bpe[1]));
+  n++;
+  for (int k = 0; k < n && k < cap; k++) ms[k] = v[k];
+  return n < cap ? n : cap;
 }
 
 // ---- request phase ------------------------------------------------------------------------------
@@ -1891,6 +2026,7 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   ctx->fetch_n = n;
   ctx->ev_n = 0;
   ctx->ev_fast_set = false;
+  ctx->ev_bpe_set = false;
   ctx->last_two_stage = false;
   if (n == 0) return 0;
   CK(cudaStreamWaitEvent(ctx->stream, sl.req_copied, 0));
@@ -1935,12 +2071,19 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
     }
   }
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (ctx->bpe_on) {
+    if (ctx->prof) CK(cudaEventRecord(ctx->ev_bpe[0], ctx->stream));
+    rc = queue_bpe(ctx, r.bodies, r.body_off, r.body_len, n, r.bpe);
+    if (rc) return rc;
+    if (ctx->prof) { CK(cudaEventRecord(ctx->ev_bpe[1], ctx->stream)); ctx->ev_bpe_set = true; }
+  }
+  if (ctx->prof) CK(cudaEventRecord(ctx->ev_admit0, ctx->stream));
   if (n > (uint32_t)kHotGroup) {  // a group can only be hot if the batch is larger than the threshold
     rank_hot_groups_kernel<<<296, 256, 0, ctx->stream>>>(r);  // exits at once when scan_request listed no hot group
     ctx->launches += 1;
   }
   limit_admit_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dt, r);
-  if (ctx->prof) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_n = 3; }
+  if (ctx->prof) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_n = 3; ctx->is_req_timing = true; }
   CK(cudaEventRecord(sl.req_ran, ctx->stream));
   ctx->launches += 2;
   CK(cudaGetLastError());
@@ -2088,6 +2231,7 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   r.reason = ctx->d_result;
   r.counted = ctx->d_result + align_up(n, 16);
   r.usage = (long long*)(ctx->d_result + 2 * align_up(n, 16));
+  r.bpe = (uint32_t*)(ctx->d_result + 2 * align_up(n, 16) + (size_t)n * 24);
   return 0;
 }
 
@@ -2102,6 +2246,7 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
   ctx->fetch_n = n;
   ctx->ev_n = 0;
   ctx->ev_fast_set = false;
+  ctx->ev_bpe_set = false;
   ctx->last_two_stage = false;
   if (n == 0) return 0;
   const uint32_t tpb = kWarpsPerBlock * 32;
@@ -2163,7 +2308,15 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
       if (sl.resp_mode == 1) launch_json(sl.rp); else launch_sse(sl.rp);
     }
   }
-  if (ctx->prof) { CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_n = 2; }
+  if (ctx->prof) { CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_n = 2; ctx->is_req_timing = false; }
+  if (ctx->bpe_on) {
+    if (ctx->prof) CK(cudaEventRecord(ctx->ev_bpe[0], ctx->stream));
+    rc = queue_bpe(ctx, sl.rp.bodies, sl.rp.body_off, sl.rp.body_len, n, sl.rp.bpe);
+    if (rc) return rc;
+    if (ctx->prof) { CK(cudaEventRecord(ctx->ev_bpe[1], ctx->stream)); ctx->ev_bpe_set = true; }
+  } else {
+    CK(cudaMemsetAsync(sl.rp.bpe, 0, (size_t)n * 4, ctx->stream));
+  }
   CK(cudaEventRecord(sl.resp_ran, ctx->stream));
   ctx->launches += 1;
   CK(cudaGetLastError());
@@ -2176,7 +2329,7 @@ static int enqueue_response_fetch(arks_ctx* ctx) {
   sl.resp_fetch_n = (uint32_t)n;
   if (n == 0) return 0;
   const size_t o1 = align_up(n, 16);
-  CK(cudaMemcpyAsync(sl.h_resp_result, ctx->d_result, 2 * o1 + n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(sl.h_resp_result, ctx->d_result, 2 * o1 + n * 28, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaEventRecord(sl.resp_done, ctx->stream));
   return 0;
 }
@@ -2190,6 +2343,7 @@ static int finish_response_fetch(arks_ctx* ctx, int slot, arks_response_result* 
   memcpy(out->reason, h, n);
   memcpy(out->counted, h + o1, n);
   memcpy(out->usage, h + 2 * o1, n * 24);
+  if (out->bpe_count) memcpy(out->bpe_count, h + 2 * o1 + n * 24, n * 4);
   return 0;
 }
 int arks_fetch_response_result(arks_ctx* ctx, arks_response_result* out) {

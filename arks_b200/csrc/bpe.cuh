@@ -65,23 +65,21 @@ ARKS_HD bool bpe_lookup(const BpeSlot* hot, const BpeTablesDev& T, uint32_t left
   }
 }
 
-// tokens of one piece of `n` <= kBpeMaxPiece bytes
+// tokens of one piece of `n` <= kBpeMaxPiece bytes. Every round looks all adjacent pairs up again instead of keeping their
+// ranks: the same result, a third of the per-lane scratch (pieces are short: a word, a number, a run of punctuation).
 ARKS_HD uint32_t bpe_piece_tokens(const uint8_t* p, uint32_t n, const BpeSlot* hot, const BpeTablesDev& T) {
-  uint32_t sym[kBpeMaxPiece], rk[kBpeMaxPiece], mg[kBpeMaxPiece];  // rk[i] / mg[i]: rank and result of merging sym[i], sym[i+1]
+  uint32_t sym[kBpeMaxPiece];
   for (uint32_t i = 0; i < n; i++) sym[i] = T.byte_id[p[i]];
-  for (uint32_t i = 0; i + 1 < n; i++)
-    if (!bpe_lookup(hot, T, sym[i], sym[i + 1], &rk[i], &mg[i])) rk[i] = 0xFFFFFFFFu;
   while (n > 1) {
-    uint32_t best = 0xFFFFFFFFu, at = 0;
-    for (uint32_t i = 0; i + 1 < n; i++)
-      if (rk[i] < best) { best = rk[i]; at = i; }  // lowest rank, leftmost
+    uint32_t best = 0xFFFFFFFFu, at = 0, into = 0;
+    for (uint32_t i = 0; i + 1 < n; i++) {
+      uint32_t r, m;
+      if (bpe_lookup(hot, T, sym[i], sym[i + 1], &r, &m) && r < best) { best = r; at = i; into = m; }  // lowest rank, leftmost
+    }
     if (best == 0xFFFFFFFFu) break;
-    sym[at] = mg[at];
-    for (uint32_t i = at + 1; i + 1 < n; i++) { sym[i] = sym[i + 1]; rk[i] = rk[i + 1]; mg[i] = mg[i + 1]; }
+    sym[at] = into;
+    for (uint32_t i = at + 1; i + 1 < n; i++) sym[i] = sym[i + 1];
     n--;
-    if (at > 0 && !bpe_lookup(hot, T, sym[at - 1], sym[at], &rk[at - 1], &mg[at - 1])) rk[at - 1] = 0xFFFFFFFFu;
-    if (at + 1 < n) { if (!bpe_lookup(hot, T, sym[at], sym[at + 1], &rk[at], &mg[at])) rk[at] = 0xFFFFFFFFu; }
-    else rk[at] = 0xFFFFFFFFu;
   }
   return n;
 }
@@ -281,6 +279,31 @@ ARKS_HD BpeScanOut bpe_scan_body(const uint8_t* b, uint32_t len, uint8_t* text, 
     i++;
   }
   return o;
+}
+
+// ---- host: the merge list as the two hash tables the lookups use (also used by the CPU test build) ----
+}  // namespace arks
+#include <vector>
+namespace arks {
+// slots: a power of two; merges [0, n) inserted in rank order (a pair that occurs twice keeps its lowest rank, as in the
+// tokenizer's dictionary)
+inline void bpe_fill_table(std::vector<BpeSlot>& tab, uint32_t slots, const uint32_t* left, const uint32_t* right, const uint32_t* merged,
+                           uint32_t n) {
+  tab.assign(slots, BpeSlot{0, 0, 0xFFFFFFFFu, 0});
+  for (uint32_t r = 0; r < n; r++) {
+    uint32_t s = bpe_hash(left[r], right[r], slots - 1);
+    bool dup = false;
+    while (tab[s].rank != 0xFFFFFFFFu) {
+      if (tab[s].left == left[r] && tab[s].right == right[r]) { dup = true; break; }
+      s = (s + 1) & (slots - 1);
+    }
+    if (!dup) tab[s] = BpeSlot{left[r], right[r], r, merged[r]};
+  }
+}
+inline uint32_t bpe_table_slots(uint32_t n_merges) {
+  uint32_t s = 1024;
+  while (s < 2 * n_merges + 16) s <<= 1;
+  return s;
 }
 
 }  // namespace arks

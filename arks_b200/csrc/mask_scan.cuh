@@ -66,10 +66,25 @@ struct FastRing {
 #endif
     for (int k = 0; k < 8; k++) ring[((chunk & 1u) * 8 + k) * stride] = w[k];
   }
+  ARKS_HD uint32_t word_at(uint32_t p) const { return ring[((((p >> 5) & 1u) * 8) + ((p >> 2) & 7u)) * stride]; }
   ARKS_HD uint8_t byte_at(uint32_t p) const {  // p inside the current or the next chunk
-    return (uint8_t)(ring[((((p >> 5) & 1u) * 8) + ((p >> 2) & 7u)) * stride] >> (8 * (p & 3u)));
+    return (uint8_t)(word_at(p) >> (8 * (p & 3u)));
+  }
+  // the four bytes at p .. p+3 as a little-endian word (p + 3 may reach into the next chunk)
+  ARKS_HD uint32_t four_at(uint32_t p) const {
+    const uint32_t lo = word_at(p), hi = word_at(p + 3), sh = 8 * (p & 3u);
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
   }
 };
+// are the four bytes of x all hexadecimal digits? SWAR, exact (checked over all 2^32 words): bit 7 of every byte is
+// forced on before the subtractions, so no borrow crosses a byte
+ARKS_HD bool four_hex(uint32_t x) {
+  const uint32_t H = 0x80808080u;
+  const uint32_t xs = x | H, ys = x | 0x20202020u | H;
+  const uint32_t dig = (xs - 0x30303030u) & ~(xs - 0x3a3a3a3au);  // bit 7: '0' <= byte < ':'
+  const uint32_t let = (ys - 0x61616161u) & ~(ys - 0x67676767u);  // bit 7: 'a' <= (byte | 0x20) < 'g'
+  return !(x & H) && (((dig | let) & H) == H);
+}
 
 // ---- byte-plane SWAR: bit 7 of every byte that is zero, exact ----
 ARKS_HD uint32_t zero_bytes(uint32_t x) { return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u; }
@@ -147,7 +162,7 @@ ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const FastRing& ri
     e &= e - 1;
     const uint8_t ch = ring.byte_at(p);
     if (ch == 'u') {
-      if (p + 4 >= len || (hexval(ring.byte_at(p + 1)) | hexval(ring.byte_at(p + 2)) | hexval(ring.byte_at(p + 3)) | hexval(ring.byte_at(p + 4))) < 0) bad = 1;
+      if (p + 4 >= len || !four_hex(ring.four_at(p + 1))) bad = 1;
     } else if (!(ch == '"' || ch == '\\' || ch == '/' || ch == 'b' || ch == 'f' || ch == 'n' || ch == 'r' || ch == 't')) {
       bad = 1;
     }

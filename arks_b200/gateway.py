@@ -47,6 +47,7 @@ def lib():
         L.arks_last_error.restype = C.c_char_p
         L.arks_last_error.argtypes = [vp]
         L.arks_load_tables.argtypes = [vp, C.POINTER(ArksTables)]
+        L.arks_load_bpe.argtypes = [vp, vp]
         L.arks_table_generation.restype = C.c_uint32
         L.arks_table_generation.argtypes = [vp]
         L.arks_update_endpoint_weights.argtypes = [vp, C.c_uint32, C.c_uint32, abi.i32p]
@@ -89,7 +90,7 @@ def lib():
 
 
 EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/test_abi.py)
-    "arks_abi_version", "arks_create", "arks_destroy", "arks_last_error", "arks_load_tables", "arks_table_generation",
+    "arks_abi_version", "arks_create", "arks_destroy", "arks_last_error", "arks_load_tables", "arks_table_generation", "arks_load_bpe",
     "arks_update_endpoint_weights", "arks_extract_bearer", "arks_submit_request_batch",
     "arks_submit_response_batch", "arks_stage_request_batch", "arks_run_request_batch",
     "arks_fetch_request_result", "arks_stage_response_batch", "arks_run_response_batch",
@@ -138,6 +139,14 @@ class Gateway:
         ts = tables.c_struct()
         self._ck(lib().arks_load_tables(self._h, C.byref(ts)))
         self.tables = tables
+
+    def load_bpe(self, tables):
+        """switch the bpe_count columns on with a vocabulary (arks_b200.bpe.BpeTables), or off with None"""
+        if tables is None:
+            self._ck(lib().arks_load_bpe(self._h, None))
+            return
+        ts = tables.c_struct()
+        self._ck(lib().arks_load_bpe(self._h, C.byref(ts)))
 
     @property
     def generation(self) -> int:
@@ -215,6 +224,8 @@ class Gateway:
         self._ck(lib().arks_set_profiling(self._h, int(bool(on))))
 
     def last_kernel_ms(self):
+        """request batch: [scan stage, rank + admit, fast-path kernel alone or 0, BPE kernels or 0]; response batch: the
+        same without the admit entry"""
         buf = (C.c_float * 4)()
         n = lib().arks_last_kernel_ms(self._h, buf, 4)
         if n < 0:

@@ -309,12 +309,12 @@ def run_b200(args):
         g.run_request(now)
         ms = g.last_kernel_ms()
         scan_ms.append(ms[0]); admit_ms.append(ms[1])
-        if len(ms) > 2:
+        if ms[2] > 0:
             fast_req_ms.append(ms[2])
         g.run_response(now + 1)
         ms = g.last_kernel_ms()
         resp_ms.append(ms[0])
-        if len(ms) > 1:
+        if ms[1] > 0:
             fast_resp_ms.append(ms[1])
         now += STEP_S
     g.set_profiling(False)

@@ -196,6 +196,7 @@ typedef struct arks_response_result {
   uint8_t* reason;   /* n: ARKS_R_OK / STREAMING / RESPONSE_UNMARSHAL / RESPONSE_UNKNOWN / QUOTA_CONFIG_RESP / PENDING */
   uint8_t* counted;  /* n: 1 iff usage.total_tokens != 0 (counters were incremented, `complete = true`)               */
   int64_t* usage;    /* 3n: prompt_tokens, completion_tokens, total_tokens                                           */
+  uint32_t* bpe_count; /* n or NULL: BPE tokens of the completion text in this body / SSE chunk (see arks_load_bpe)      */
 } arks_response_result;
 
 typedef struct arks_ctx arks_ctx;
@@ -212,6 +213,28 @@ const char* arks_last_error(const arks_ctx* ctx);
 int arks_load_tables(arks_ctx* ctx, const arks_tables* t);
 /* bumped by every arks_load_tables that succeeds: the generation the qos / token indices of request results refer to */
 uint32_t arks_table_generation(const arks_ctx* ctx);
+/* ---- BPE token counting (north star). The reference has NO tokenizer: it reads `usage` from the upstream's response
+ * (pkg/gateway/handle_response.go:90-93,117-123) and counts 0 tokens at request time (check.go:124-126). The count is
+ * therefore a side output with its own oracle (HF `tokenizers`); decisions never depend on it.
+ * What is counted: every JSON string that is the value of a key named "content" in the body (escapes decoded), cut by the
+ * Qwen2 pre-tokenizer pattern and byte-level BPE-merged with the merge list below.  ARKS_BPE_UNCOUNTED is reported instead
+ * of a wrong number when a body is outside what the device handles (invalid UTF-8 / escapes, a lone surrogate, a
+ * pre-token longer than 128 bytes, NFC-unsafe text under ARKS_BPE_NFC, work-list overflow). */
+#define ARKS_BPE_UNCOUNTED 0xFFFFFFFFu
+#define ARKS_BPE_NFC 1u  /* flags: the tokenizer normalises to NFC (Qwen2 does): text NFC could change is not counted */
+typedef struct arks_bpe_tables {
+  const uint32_t* byte_id;  /* 256: token id of every single byte (byte-level alphabet)                           */
+  uint32_t n_merges;
+  const uint32_t* left;     /* n_merges: merge i joins token left[i] and right[i] into merged[i]; rank = i        */
+  const uint32_t* right;
+  const uint32_t* merged;
+  const uint8_t* cp_class;  /* 0x110000 / 2 bytes, a nibble per Unicode code point (low nibble = even code point):
+                             * bits 0-1 class (0 other, 1 \p{L}, 2 \p{N}, 3 \s), bit 2 NFC-unsafe; tools/gen_bpe_unicode.py */
+  uint32_t flags;
+} arks_bpe_tables;
+/* copies the tables to the device and switches the bpe_count columns on (NULL: off) */
+int arks_load_bpe(arks_ctx* ctx, const arks_bpe_tables* t);
+
 /* routing churn (BASELINE config 5): replace the weights of one endpoint's backends in place */
 int arks_update_endpoint_weights(arks_ctx* ctx, uint32_t endpoint, uint32_t n, const int32_t* weights);
 
@@ -247,8 +270,9 @@ int arks_wait_response(arks_ctx* ctx, int slot, arks_response_result* out);
  * timed inputs exceed L2). stage_/run_ calls act on the selected slot (default 0); fetch_ returns the last run. */
 int arks_select_slot(arks_ctx* ctx, int slot);
 /* per-kernel device timing of the last run_* call: CUDA events around every launch on the library's stream.
- * arks_last_kernel_ms returns the number of intervals timed and fills ms[] (request: scan stage, admit; response: scan stage;
- * large batches add one entry: the fast-path kernel of the two-stage scan on its own). */
+ * arks_last_kernel_ms returns the number of intervals and fills ms[]: after a request batch {scan stage, rank_hot +
+ * limit_admit, the fast-path kernel of the two-stage scan alone (0: fused kernel), the BPE kernels (0: no vocabulary)},
+ * after a response batch {scan stage, fast-path kernel alone, BPE kernels}. */
 int arks_set_profiling(arks_ctx* ctx, int on);
 int arks_last_kernel_ms(arks_ctx* ctx, float* ms, int cap);
 /* CUDA stream handle (cudaStream_t) the kernels are launched on, for event timing by the caller */

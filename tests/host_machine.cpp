@@ -209,3 +209,37 @@ int hm_engine_response_span(const uint8_t* body, size_t len, uint32_t* span, int
   return 1;
 }
 }
+
+// ---- the BPE token counter (arks_b200/csrc/bpe.cuh) on the host: the same scanner, pre-tokenizer and merge loop ----
+#include "../arks_b200/csrc/bpe.cuh"
+#include <vector>
+static std::vector<BpeSlot> g_bpe_table, g_bpe_hot;
+static std::vector<uint32_t> g_bpe_byte_id;
+static std::vector<uint8_t> g_bpe_cls;
+static BpeTablesDev g_bpe{};
+extern "C" {
+void hm_bpe_load(const uint32_t* byte_id, uint32_t n, const uint32_t* left, const uint32_t* right, const uint32_t* merged,
+                 const uint8_t* cp_class, uint32_t flags) {
+  g_bpe_byte_id.assign(byte_id, byte_id + 256);
+  g_bpe_cls.assign(cp_class, cp_class + 0x110000 / 2);
+  const uint32_t slots = bpe_table_slots(n);
+  bpe_fill_table(g_bpe_table, slots, left, right, merged, n);
+  bpe_fill_table(g_bpe_hot, kBpeHotSlots, left, right, merged, n < kBpeHotMerges ? n : kBpeHotMerges);
+  g_bpe = BpeTablesDev{g_bpe_byte_id.data(), g_bpe_table.data(), slots - 1, g_bpe_hot.data(), g_bpe_cls.data(), flags};
+}
+// tokens of every `content` string of the body, or 0xFFFFFFFF (uncounted)
+uint32_t hm_bpe_count(const uint8_t* body, size_t len) {
+  std::vector<uint8_t> text(len + 8);
+  uint32_t total = 0;
+  const BpeScanOut o = bpe_scan_body(body, (uint32_t)len, text.data(), g_bpe, [&](uint32_t off, uint32_t n) {
+    total += bpe_piece_tokens(text.data() + off, n, g_bpe.hot, g_bpe);
+  });
+  return o.bad ? kBpeUncounted : total;
+}
+// the pieces of one plain text (UTF-8), as end offsets (test of the pre-tokenizer alone)
+int hm_bpe_pretokenize(const uint8_t* text, size_t len, uint32_t* ends, int cap) {
+  int n = 0;
+  bpe_pretokenize(text, 0, (uint32_t)len, g_bpe.cp_class, [&](uint32_t, uint32_t e) { if (n < cap) ends[n] = e; n++; });
+  return n;
+}
+}

@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "host_machine.cpp")
-HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_common.cuh", "json_engine.cuh", "json_tables.h", "mask_scan.cuh")]
+HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_common.cuh", "json_engine.cuh", "json_tables.h", "mask_scan.cuh", "bpe.cuh")]
 OUT = os.path.join(ROOT, "tests", "_build", "libhost_machine.so")
 _lib = None
 
@@ -31,6 +31,10 @@ def lib():
         L.hm_engine_request_span.argtypes = [C.c_char_p, C.c_size_t, u32p, ip, ip, ip]
         L.hm_fast_response.argtypes = [C.c_char_p, C.c_size_t, u32p, i64p]
         L.hm_engine_response_span.argtypes = [C.c_char_p, C.c_size_t, u32p, i64p]
+        L.hm_bpe_load.argtypes = [u32p, C.c_uint32, u32p, u32p, u32p, C.POINTER(C.c_uint8), C.c_uint32]
+        L.hm_bpe_count.argtypes = [C.c_char_p, C.c_size_t]
+        L.hm_bpe_count.restype = C.c_uint32
+        L.hm_bpe_pretokenize.argtypes = [C.c_char_p, C.c_size_t, u32p, C.c_int]
         L.hm_work_profile.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t]
         _lib = L
     return _lib
@@ -110,3 +114,21 @@ def fast_response(body: bytes):
 
 def engine_response(body: bytes):
     return _resp(lib().hm_engine_response_span, body)
+
+
+def bpe_load(tables):
+    """tables: arks_b200.bpe.BpeTables"""
+    t = tables.c_struct()
+    lib().hm_bpe_load(t.byte_id, t.n_merges, t.left, t.right, t.merged, t.cp_class, t.flags)
+    lib()._bpe_keep = tables
+
+
+def bpe_count(body: bytes) -> int:
+    return int(lib().hm_bpe_count(body, len(body)))
+
+
+def bpe_pretokenize(text: bytes):
+    cap = len(text) + 1
+    ends = (C.c_uint32 * cap)()
+    n = lib().hm_bpe_pretokenize(text, len(text), ends, cap)
+    return list(ends[:n])
