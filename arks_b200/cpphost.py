@@ -30,7 +30,7 @@ class ResponseDecision(C.Structure):
 
 class BatcherStats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("cycles", "request_batches", "response_batches", "requests", "responses",
-                                          "max_request_batch", "max_response_batch")]
+                                          "max_request_batch", "max_response_batch", "ns_submit", "ns_device", "ns_deliver")]
 
 
 REQ_DTYPE = np.dtype(RequestDecision)

@@ -1227,6 +1227,10 @@ struct HostTables {  // what we need to remember for reloads, snapshots and vali
   uint32_t n_tokens = 0, n_qos = 0, n_quotas = 0, n_endpoints = 0, n_backends = 0;
 };
 
+// from this size on requests / complete response bodies go through the two-stage scan (mask_scan.cuh first); below it the
+// exact kernel alone is one launch and spreads the few bodies over more warps (bodies_per_warp). ARKS_FAST_MIN overrides.
+constexpr uint32_t kFastMinBatchDefault = 4096;
+
 struct arks_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;  // kernels, counter memsets, result D2H: the order of this stream IS the linearisation
@@ -1305,6 +1309,7 @@ struct arks_ctx {
   uint32_t* d_lenhist = nullptr; // kLenBuckets counters / offsets
   bool sort_lanes = true;        // ARKS_SORT=0 scans in arrival order (A/B runs)
   bool fast_scan = true;         // ARKS_FAST=0: large batches also take the fused lane-per-document kernels (A/B runs)
+  uint32_t fast_min = kFastMinBatchDefault;  // ARKS_FAST_MIN=n: batches of n rows and more take the two-stage scan
   int n_sm = 148;
   uint32_t* d_slow = nullptr;    // [0] counter, [64..] the rows left to the exact engine by the fast path (mask_scan.cuh)
   uint8_t* d_result = nullptr;   // packed results
@@ -1406,6 +1411,7 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaFuncSetAttribute(fast_request_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
   CK(cudaFuncSetAttribute(fast_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
   if (const char* e = getenv("ARKS_FAST")) ctx->fast_scan = e[0] != '0';
+  if (const char* e = getenv("ARKS_FAST_MIN")) ctx->fast_min = (uint32_t)strtoul(e, nullptr, 10);
   {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -2002,7 +2008,7 @@ static uint32_t scan_grid(uint32_t n, uint32_t bpw) { return ((n + bpw - 1) / bp
 constexpr uint32_t kSortMinBatch = 4096;
 // from this size on requests / complete response bodies go through the two-stage scan (mask_scan.cuh first); below it
 // the exact kernel alone is one launch and spreads the few bodies over more warps (bodies_per_warp)
-constexpr uint32_t kFastMinBatch = 4096;
+
 
 // queue the counting sort by body length; returns the permutation (device pointer) or null when the batch is scanned as is
 static const uint32_t* queue_length_order(arks_ctx* ctx, const uint32_t* d_body_len, uint32_t n) {
@@ -2045,7 +2051,7 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   r.slow_n = ctx->d_slow;
   r.slow_list = ctx->d_slow + 64;
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  if (ctx->fast_scan && n >= kFastMinBatch) {
+  if (ctx->fast_scan && n >= ctx->fast_min) {
     // two-stage scan: the fast path (mask_scan.cuh) decides everything plain, the exact engine what it declines
     CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
     r.perm = queue_length_order(ctx, r.body_len, n);
@@ -2300,7 +2306,7 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
     launch_sse(rs);
     ctx->launches += 1;
   } else {
-    if (sl.resp_mode == 1 && ctx->fast_scan && n >= kFastMinBatch) {
+    if (sl.resp_mode == 1 && ctx->fast_scan && n >= ctx->fast_min) {
       rc = launch_json_two_stage(sl.rp);
       if (rc) return rc;
     } else {

@@ -170,6 +170,7 @@ struct Batcher::Impl {
     last_now = now;
     lk.unlock();
     cv_space.notify_all();
+    const auto t_a = std::chrono::steady_clock::now();
     arks_select_slot(ctx, f.slot);
     if (f.req) {
       Block& b = *f.req;
@@ -191,6 +192,8 @@ struct Batcher::Impl {
       rb.qos = b.qos; rb.flags = b.flags; rb.now_unix = now; rb.gen = b.gen;
       f.rc_resp = arks_submit_response_async(ctx, &rb);
     }
+    const auto t_b = std::chrono::steady_clock::now();
+    t_submit.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_b - t_a).count(), std::memory_order_relaxed);
     if (opt.max_inflight == 1) {  // nothing else can be queued meanwhile: finish the batch here, one thread hand-off less
       deliver(f);
       lk.lock();
@@ -251,9 +254,15 @@ struct Batcher::Impl {
     }
   }
 
+  std::atomic<uint64_t> t_submit{0}, t_device{0}, t_deliver{0};
   // wait for a submitted batch and hand every row its decision (no lock held)
   void deliver(InFlight& f) {
-
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](std::atomic<uint64_t>& acc) {
+      const auto t1 = std::chrono::steady_clock::now();
+      acc.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count(), std::memory_order_relaxed);
+      t0 = t1;
+    };
     if (f.req) {
       Block& b = *f.req;
       int rc = f.rc_req;
@@ -262,6 +271,7 @@ struct Batcher::Impl {
                                b.model_off, b.model_len, b.bpe};
         rc = arks_wait_request(ctx, f.slot, &rr);
       }
+      lap(t_device);
       for (uint32_t i = 0; i < b.n; i++) {
         RequestDecision d{};
         if (rc) d.reason = kReasonHostError;
@@ -274,6 +284,7 @@ struct Batcher::Impl {
         d.cycle = b.cycle; d.index = i; d.now_unix = b.now; d.gen = b.table_gen;
         b.rcb[i](b.user[i], d);
       }
+      lap(t_deliver);
     }
     if (f.resp) {
       Block& b = *f.resp;
@@ -282,6 +293,7 @@ struct Batcher::Impl {
         arks_response_result rr{b.reason, b.counted, b.usage};
         rc = arks_wait_response(ctx, f.slot, &rr);
       }
+      lap(t_device);
       for (uint32_t i = 0; i < b.n; i++) {
         ResponseDecision d{};
         if (rc) d.reason = kReasonHostError;
@@ -292,6 +304,7 @@ struct Batcher::Impl {
         d.cycle = b.cycle; d.index = i; d.now_unix = b.now;
         b.pcb[i](b.user[i], d);
       }
+      lap(t_deliver);
     }
   }
   // stats, block and slot back to the pools (lock held)
@@ -347,7 +360,11 @@ void Batcher::SetClock(int64_t (*clock)(void*), void* arg) {
 }
 BatcherStats Batcher::Stats() const {
   std::lock_guard<std::mutex> g(p_->mu);
-  return p_->st;
+  BatcherStats s = p_->st;
+  s.ns_submit = p_->t_submit.load();
+  s.ns_device = p_->t_device.load();
+  s.ns_deliver = p_->t_deliver.load();
+  return s;
 }
 
 bool Batcher::Impl::submit_request(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user,

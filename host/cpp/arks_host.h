@@ -58,6 +58,9 @@ struct BatcherOptions {
 
 struct BatcherStats {
   uint64_t cycles, request_batches, response_batches, requests, responses, max_request_batch, max_response_batch;
+  // where a cycle's time goes (nanoseconds, summed over cycles): waiting for the rows' copies + staging + queueing the
+  // device work; waiting for the device; handing the decisions to the rows
+  uint64_t ns_submit, ns_device, ns_deliver;
 };
 
 typedef void (*RequestCallback)(void* user, const RequestDecision&);    // run on the batcher's completion thread

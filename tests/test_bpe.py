@@ -145,7 +145,7 @@ def test_gpu_counts_match_tokenizers_on_64k_bodies(gwmod):
     ok.reason[:] = 0
     ok.qos[:] = np.arange(3000) % w.tables.n_qos
     ok.flags[:] = (np.arange(3000) % 3 == 0)
-    resp = w.response_batch(ok, 1_700_000_100, seed=78, varied=True, sse_total=2048)
+    resp = w.response_batch(ok, 1_700_086_500, seed=78, varied=True, sse_total=2048)
     c = g.handle_response_body(resp)
     for i in range(resp.n):
         body = bytes(resp.bodies[resp.body_off[i]:resp.body_off[i] + resp.body_len[i]])
@@ -153,7 +153,7 @@ def test_gpu_counts_match_tokenizers_on_64k_bodies(gwmod):
         assert c.bpe_count[i] == sum(len(tok.encode(s, add_special_tokens=False).ids) for s in strings), body[:200]
     # bodies the device declines are reported as such, not miscounted
     odd = RequestBatch.from_lists([b'{"model":"m","messages":[{"content":"' + b"z" * 300 + b'"}]}', b'{"content":"\\ud800"}',
-                                   b'{"content":"ok then"}'], [w.token_strings[0]] * 3, 1_700_000_200)
+                                   b'{"content":"ok then"}'], [w.token_strings[0]] * 3, 1_700_086_600)
     r = g.handle_request_body(odd)
     assert r.bpe_count[0] == bpe.UNCOUNTED and r.bpe_count[1] == bpe.UNCOUNTED
     assert r.bpe_count[2] == len(tok.encode("ok then", add_special_tokens=False).ids)
