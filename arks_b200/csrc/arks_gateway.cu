@@ -37,6 +37,7 @@
 #include "../../include/arks_gateway.h"
 #include "json_engine.cuh"
 #include "mask_scan.cuh"
+#include "warp_scan.cuh"
 #include "bpe.cuh"
 
 using namespace arks;
@@ -660,6 +661,165 @@ __global__ void __launch_bounds__(kFastThreads) fast_request_kernel(DevTables T,
 }
 
 // ------------------------------------------------------------------------------------------------
+// kernel 1'': the latency path (warp_scan.cuh) — micro-batches. One WARP per body: the body arrives in shared memory by one
+// 1-D bulk copy (TMA), the 32 lanes scan it together, lane 0 decides it (same tail as the other scan kernels). A body the
+// path declines is appended to B.slow_list for scan_*_kernel<.., FROM_LIST>.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWdWarps = 4;  // warps per block
+struct __align__(128) WdWarpSmem {
+  uint8_t doc[wd::kFastMaxLen];  // bulk-copy destination
+  uint32_t tok[wd::kFastMaxTok + 32];
+  uint32_t bmap[wd::kFastMaxLen / 32];
+  uint64_t bar;
+};
+constexpr int kWdSmemPerBlock = kWdWarps * (int)sizeof(WdWarpSmem);
+
+// exclusive prefix of the lanes' stack effects (Hillis-Steele over effect_compose)
+__device__ __forceinline__ wd::FastEffect wd_effect_prefix(const wd::FastEffect& own, uint32_t lane, uint32_t* total_bad) {
+  wd::FastEffect inc = own;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    wd::FastEffect o;
+    o.npop = __shfl_up_sync(0xffffffffu, inc.npop, d);
+    o.npush = __shfl_up_sync(0xffffffffu, inc.npush, d);
+    o.pword = __shfl_up_sync(0xffffffffu, inc.pword, d);
+    o.bad = __shfl_up_sync(0xffffffffu, inc.bad, d);
+    o.ptypes = 0;
+    if (lane >= (uint32_t)d) inc = wd::effect_compose(o, inc);
+  }
+  *total_bad = __shfl_sync(0xffffffffu, inc.bad, 31);
+  wd::FastEffect pre;
+  pre.npop = __shfl_up_sync(0xffffffffu, inc.npop, 1);
+  pre.npush = __shfl_up_sync(0xffffffffu, inc.npush, 1);
+  pre.pword = __shfl_up_sync(0xffffffffu, inc.pword, 1);
+  pre.bad = 0;
+  pre.ptypes = 0;
+  if (lane == 0) pre.npop = pre.npush = pre.pword = 0;
+  return pre;
+}
+
+// one document, whole warp; true = accepted, `out` valid on every lane
+template <int KIND>
+__device__ __forceinline__ bool wd_scan_doc(const uint8_t* doc, uint32_t len, WdWarpSmem& sm, wd::FastOut& out) {
+  using namespace wd;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t ntok = 0, carry_esc = 0, carry_str = 0;
+  bool bad = false;
+  for (uint32_t seg = 0; seg * kFastSeg < len; seg++) {
+    const uint32_t base = seg * kFastSeg + 32u * lane;
+    FastMasks m;
+    {
+      const uint4* p = reinterpret_cast<const uint4*>(doc + base);
+      uint4 a = make_uint4(0, 0, 0, 0), b = a;
+      if (base < len) { a = p[0]; b = p[1]; }
+      m.w[0] = a.x; m.w[1] = a.y; m.w[2] = a.z; m.w[3] = a.w;
+      m.w[4] = b.x; m.w[5] = b.y; m.w[6] = b.z; m.w[7] = b.w;
+    }
+    fast_masks(m, base < len ? min(len - base, 32u) : 0u);
+    const bool allbs = m.B == 0xffffffffu;  // 32 backslashes in a row: exact engine
+    const uint32_t co = odd_tail(m.B);
+    uint32_t prev = __shfl_up_sync(0xffffffffu, co, 1);
+    if (lane == 0) prev = carry_esc;
+    carry_esc = __shfl_sync(0xffffffffu, co, 31);
+    const uint32_t E = wd::find_escaped(m.B, prev);
+    const uint32_t Qu = m.Q & ~E;
+    const uint32_t pm = __ballot_sync(0xffffffffu, __popc(Qu) & 1);
+    const uint32_t inside = ((uint32_t)__popc(pm & ((1u << lane) - 1u)) & 1u) ^ carry_str;
+    carry_str ^= (uint32_t)__popc(pm) & 1u;
+    const uint32_t R = wd::prefix_xor32(Qu) ^ (inside ? 0xffffffffu : 0u);
+    sm.bmap[seg * 32 + lane] = m.B;
+    const bool ok = !allbs && fast_string_checks(doc, len, base, m, E, R);
+    const uint32_t TB = m.V & ~(R & ~Qu);
+    const uint32_t cnt = (uint32_t)__popc(TB);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (uint32_t)d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (__any_sync(0xffffffffu, !ok) || ntok + total > kFastMaxTok) { bad = true; break; }
+    fast_emit(doc, base, TB, Qu, R, sm.tok, ntok + incl - cnt);
+    ntok += total;
+  }
+  __syncwarp();
+  if (bad || carry_str || ntok == 0) return false;
+  const int c = (int)((ntok + 31) / 32);
+  const int k0 = min((int)lane * c, (int)ntok), k1 = min(k0 + c, (int)ntok);
+  FastEffect eff{0, 0, 0, 0, 0};
+  for (int k = k0; k < k1; k++) effect_token(eff, sm.tok[k]);
+  uint32_t total_bad;
+  const FastEffect pre = wd_effect_prefix(eff, lane, &total_bad);
+  FastFound f;
+  f.n_model = f.n_stream = f.n_so = f.n_iu = f.n_usage = f.n_u[0] = f.n_u[1] = f.n_u[2] = f.bad = 0;
+  f.o.m_start = f.o.m_rawlen = f.o.m_esc = f.o.stream3 = f.o.so_present = f.o.iu3 = 0;
+  f.o.usage[0] = f.o.usage[1] = f.o.usage[2] = 0;
+  bool ok = !total_bad;
+  if (ok && k0 < k1) ok = pre.npop == 0 && fast_walk_chunk<KIND>(doc, sm.bmap, sm.tok, k0, k1, (int)ntok, pre.npush, pre.pword, eff, f);
+  ok = ok && f.n_model <= 1 && f.n_stream <= 1 && f.n_so <= 1 && f.n_iu <= 1 && f.n_usage <= 1 && f.n_u[0] <= 1 && f.n_u[1] <= 1 && f.n_u[2] <= 1;
+  if (__any_sync(0xffffffffu, !ok)) return false;
+  // every member at most once in the whole document; its finder hands the value to everybody
+  const uint32_t bm = __ballot_sync(0xffffffffu, f.n_model), bs = __ballot_sync(0xffffffffu, f.n_stream),
+                 bo = __ballot_sync(0xffffffffu, f.n_so), bu = __ballot_sync(0xffffffffu, f.n_usage);
+  if (__popc(bm) > 1 || __popc(bs) > 1 || __popc(bo) > 1 || __popc(bu) > 1) return false;
+  const int lm = bm ? __ffs(bm) - 1 : 0, ls = bs ? __ffs(bs) - 1 : 0, lo = bo ? __ffs(bo) - 1 : 0, lu = bu ? __ffs(bu) - 1 : 0;
+  out.m_start = __shfl_sync(0xffffffffu, f.o.m_start, lm);
+  out.m_rawlen = __shfl_sync(0xffffffffu, f.o.m_rawlen, lm);
+  out.m_esc = __shfl_sync(0xffffffffu, f.o.m_esc, lm);
+  if (KIND == K_REQ) {
+    out.stream3 = __shfl_sync(0xffffffffu, f.o.stream3, ls);
+    out.so_present = __shfl_sync(0xffffffffu, f.o.so_present, lo);
+    out.iu3 = __shfl_sync(0xffffffffu, f.o.iu3, lo);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 3; q++) out.usage[q] = __shfl_sync(0xffffffffu, f.o.usage[q], lu);
+  }
+  return true;
+}
+// the body of this warp into its shared-memory window; false: not eligible (empty or longer than the window)
+__device__ __forceinline__ bool wd_fetch(WdWarpSmem& sm, const uint8_t* src, uint32_t len) {
+  const uint32_t lane = threadIdx.x & 31;
+  const bool elig = len > 0 && len <= wd::kFastMaxLen;
+  if (lane == 0) {
+    mbar_init(&sm.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (elig) {
+      const uint32_t bytes = (len + 15u) & ~15u;
+      mbar_expect_tx(&sm.bar, bytes);
+      bulk_g2s(sm.doc, src, bytes, &sm.bar);
+    }
+  }
+  __syncwarp();
+  if (elig) mbar_wait(&sm.bar, 0);
+  return elig;
+}
+
+__global__ void __launch_bounds__(kWdWarps * 32) warp_request_kernel(DevTables T, ReqDev B) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  WdWarpSmem& sm = reinterpret_cast<WdWarpSmem*>(smem)[threadIdx.x >> 5];
+  const uint32_t i = blockIdx.x * kWdWarps + (threadIdx.x >> 5);
+  if (i >= B.n) return;
+  const uint8_t* body = B.bodies + B.body_off[i];
+  const uint32_t len = B.body_len[i];
+  // GetQosByToken's chain of dependent loads runs in lane 0 while the body is on its way
+  const bool elig = wd_fetch(sm, body, len);
+  int32_t tok = -1;
+  if ((threadIdx.x & 31) == 0) tok = lookup_token(T, B, i);
+  wd::FastOut o;
+  const bool ok = elig && wd_scan_doc<K_REQ>(sm.doc, len, sm, o);
+  if ((threadIdx.x & 31) != 0) return;
+  if (!ok) {
+    B.slow_list[atomicAdd(B.slow_n, 1u)] = i;
+    return;
+  }
+  B.model_off[i] = o.m_rawlen ? o.m_start : 0u;
+  B.model_len[i] = o.m_rawlen ? (o.m_rawlen | (o.m_esc ? 0x80000000u : 0u)) : 0u;
+  B.bpe[i] = 0;
+  const uint8_t pstate = (uint8_t)((o.stream3 == 2 ? PS_STREAM : 0) | (o.so_present && o.iu3 == 2 ? PS_STREAM_OK : 0));
+  resolve_request(T, B, i, body, tok, pstate, o.m_start, o.m_rawlen, o.m_esc);
+}
+
+// ------------------------------------------------------------------------------------------------
 // kernel 2: limit_admit — A6 (checkRateLimit + doRequestRateLimit), A8 (checkTokenQuotaLimit), A12 (pick)
 //
 // Serial semantics being reproduced (oracle/ork_core.c handle_request): requests are applied in index order;
@@ -1004,6 +1164,38 @@ __global__ void __launch_bounds__(kFastThreads) fast_response_kernel(DevTables T
   account_usage(T, B, i, live, qos, acct, reason, counted, u0, u1, u2);  // all 32 lanes: warp-aggregated atomics inside
 }
 
+// the latency path for complete response bodies: one warp per body (see warp_request_kernel)
+__global__ void __launch_bounds__(kWdWarps * 32) warp_response_kernel(DevTables T, RespDev B) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  WdWarpSmem& sm = reinterpret_cast<WdWarpSmem*>(smem)[threadIdx.x >> 5];
+  const uint32_t i = blockIdx.x * kWdWarps + (threadIdx.x >> 5);
+  if (i >= B.n) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const int32_t qos = B.qos[i];
+  const bool pending = !(B.flags[i] & ARKS_RESP_END_OF_STREAM);
+  uint8_t reason = ARKS_R_OK, counted = 0;
+  long long u0 = 0, u1 = 0, u2 = 0;
+  bool live = lane == 0;
+  const uint32_t len = B.body_len[i];
+  const bool scan = !pending && qos >= 0;
+  const bool elig = wd_fetch(sm, B.bodies + B.body_off[i], scan ? len : 0u);
+  const QosAcct acct = load_qos_acct(T, qos, live && qos >= 0);  // behind the bulk copy
+  if (scan) {
+    wd::FastOut o;
+    if (elig && wd_scan_doc<K_RESP>(sm.doc, len, sm, o)) {
+      if (o.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // handle_response.go:167-181
+      else { u0 = o.usage[0]; u1 = o.usage[1]; u2 = o.usage[2]; }
+      counted = reason == ARKS_R_OK && u2 != 0;               // :186
+    } else {
+      if (lane == 0) B.slow_list[atomicAdd(B.slow_n, 1u)] = i;  // the exact engine decides (and accounts) this one
+      live = false;
+    }
+  } else if (pending) {
+    reason = ARKS_R_PENDING;  // :141-149 (a row without a qos entry: account_usage answers ARKS_R_QOS_GONE)
+  }
+  account_usage(T, B, i, live, qos, acct, reason, counted, u0, u1, u2);  // lane 0 carries the row
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel 3b: scan_sse — SSE chunks (BASELINE config 3). Same verdicts as the sequential machine SseT, different
 // work split. A lane that walks a whole chunk sits at an arbitrary phase of the frame structure, so a warp of 32
@@ -1230,6 +1422,9 @@ struct HostTables {  // what we need to remember for reloads, snapshots and vali
 // from this size on requests / complete response bodies go through the two-stage scan (mask_scan.cuh first); below it the
 // exact kernel alone is one launch and spreads the few bodies over more warps (bodies_per_warp). ARKS_FAST_MIN overrides.
 constexpr uint32_t kFastMinBatchDefault = 4096;
+// up to this size a batch takes the latency path (warp_scan.cuh: a warp per body): the GPU is mostly idle and what the
+// streams wait for is the time ONE body takes. ARKS_WARP_MAX overrides (0: off).
+constexpr uint32_t kWarpMaxBatchDefault = 2048;
 
 struct arks_ctx {
   int device = 0;
@@ -1310,6 +1505,7 @@ struct arks_ctx {
   bool sort_lanes = true;        // ARKS_SORT=0 scans in arrival order (A/B runs)
   bool fast_scan = true;         // ARKS_FAST=0: large batches also take the fused lane-per-document kernels (A/B runs)
   uint32_t fast_min = kFastMinBatchDefault;  // ARKS_FAST_MIN=n: batches of n rows and more take the two-stage scan
+  uint32_t warp_max = kWarpMaxBatchDefault;  // ARKS_WARP_MAX=n: batches of up to n rows take the warp-per-document latency path
   int n_sm = 148;
   uint32_t* d_slow = nullptr;    // [0] counter, [64..] the rows left to the exact engine by the fast path (mask_scan.cuh)
   uint8_t* d_result = nullptr;   // packed results
@@ -1408,6 +1604,9 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaFuncSetAttribute(scan_sse_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSseSmemPerBlock));
   ARKS_FOR_SCHED(ARKS_SET)
 #undef ARKS_SET
+  CK(cudaFuncSetAttribute(warp_request_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWdSmemPerBlock));
+  CK(cudaFuncSetAttribute(warp_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWdSmemPerBlock));
+  if (const char* e = getenv("ARKS_WARP_MAX")) ctx->warp_max = (uint32_t)strtoul(e, nullptr, 10);
   CK(cudaFuncSetAttribute(fast_request_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
   CK(cudaFuncSetAttribute(fast_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
   if (const char* e = getenv("ARKS_FAST")) ctx->fast_scan = e[0] != '0';
@@ -2051,7 +2250,20 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   r.slow_n = ctx->d_slow;
   r.slow_list = ctx->d_slow + 64;
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  if (ctx->fast_scan && n >= ctx->fast_min) {
+  if (ctx->fast_scan && n <= ctx->warp_max) {
+    // latency path: a warp per body (warp_scan.cuh), the exact engine for what it declines
+    CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
+    r.perm = nullptr;
+    warp_request_kernel<<<(n + kWdWarps - 1) / kWdWarps, kWdWarps * 32, kWdSmemPerBlock, ctx->stream>>>(ctx->dt, r);
+    r.bpw = 1;
+    switch (ctx->sched[0]) {
+#define ARKS_LAUNCH(S) case S: scan_request_kernel<S, true><<<scan_grid(n, r.bpw), tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, r); break;
+      ARKS_FOR_SCHED(ARKS_LAUNCH)
+#undef ARKS_LAUNCH
+    }
+    ctx->launches += 1;
+    ctx->last_two_stage = true;
+  } else if (ctx->fast_scan && n >= ctx->fast_min) {
     // two-stage scan: the fast path (mask_scan.cuh) decides everything plain, the exact engine what it declines
     CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
     r.perm = queue_length_order(ctx, r.body_len, n);
@@ -2306,7 +2518,23 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
     launch_sse(rs);
     ctx->launches += 1;
   } else {
-    if (sl.resp_mode == 1 && ctx->fast_scan && n >= ctx->fast_min) {
+    if (sl.resp_mode == 1 && ctx->fast_scan && n <= ctx->warp_max) {
+      RespDev rp = sl.rp;
+      rp.slow_n = ctx->d_slow;
+      rp.slow_list = ctx->d_slow + 64;
+      rp.perm = nullptr;
+      CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
+      warp_response_kernel<<<(n + kWdWarps - 1) / kWdWarps, kWdWarps * 32, kWdSmemPerBlock, ctx->stream>>>(ctx->dt, rp);
+      rp.bpw = 1;
+      const dim3 grid(scan_grid(n, rp.bpw));
+      switch (ctx->sched[1]) {
+#define ARKS_LAUNCH(S) case S: scan_response_kernel<S, true><<<grid, tpb, kSmemPerBlock, ctx->stream>>>(ctx->dt, rp); break;
+        ARKS_FOR_SCHED(ARKS_LAUNCH)
+#undef ARKS_LAUNCH
+      }
+      ctx->launches += 1;
+      ctx->last_two_stage = true;
+    } else if (sl.resp_mode == 1 && ctx->fast_scan && n >= ctx->fast_min) {
       rc = launch_json_two_stage(sl.rp);
       if (rc) return rc;
     } else {

@@ -243,3 +243,25 @@ int hm_bpe_pretokenize(const uint8_t* text, size_t len, uint32_t* ends, int cap)
   return n;
 }
 }
+
+// ---- the warp-per-document latency path (arks_b200/csrc/warp_scan.cuh): its host driver runs the per-lane phases with the
+// warp collectives written as loops ----
+#include "../arks_b200/csrc/warp_scan.cuh"
+extern "C" {
+int hm_warp_request(const uint8_t* body, size_t len, uint32_t* span, int* stream, int* so_present, int* iu) {
+  static thread_local uint32_t tok[wd::kFastMaxTok + 64];
+  wd::FastOut o{};
+  if (len > 0xffffffffu || !wd::fast_scan_host<K_REQ>(body, (uint32_t)len, o, tok)) return 0;
+  span[0] = o.m_start; span[1] = o.m_rawlen; span[2] = o.m_esc;
+  *stream = (int)o.stream3; *so_present = (int)o.so_present; *iu = (int)o.iu3;
+  return 1;
+}
+int hm_warp_response(const uint8_t* body, size_t len, uint32_t* span, int64_t* usage) {
+  static thread_local uint32_t tok[wd::kFastMaxTok + 64];
+  wd::FastOut o{};
+  if (len > 0xffffffffu || !wd::fast_scan_host<K_RESP>(body, (uint32_t)len, o, tok)) return 0;
+  span[0] = o.m_start; span[1] = o.m_rawlen; span[2] = o.m_esc;
+  usage[0] = o.usage[0]; usage[1] = o.usage[1]; usage[2] = o.usage[2];
+  return 1;
+}
+}

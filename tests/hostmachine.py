@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "host_machine.cpp")
-HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_common.cuh", "json_engine.cuh", "json_tables.h", "mask_scan.cuh", "bpe.cuh")]
+HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_common.cuh", "json_engine.cuh", "json_tables.h", "mask_scan.cuh", "warp_scan.cuh", "bpe.cuh")]
 OUT = os.path.join(ROOT, "tests", "_build", "libhost_machine.so")
 _lib = None
 
@@ -31,6 +31,8 @@ def lib():
         L.hm_engine_request_span.argtypes = [C.c_char_p, C.c_size_t, u32p, ip, ip, ip]
         L.hm_fast_response.argtypes = [C.c_char_p, C.c_size_t, u32p, i64p]
         L.hm_engine_response_span.argtypes = [C.c_char_p, C.c_size_t, u32p, i64p]
+        L.hm_warp_request.argtypes = [C.c_char_p, C.c_size_t, u32p, ip, ip, ip]
+        L.hm_warp_response.argtypes = [C.c_char_p, C.c_size_t, u32p, i64p]
         L.hm_bpe_load.argtypes = [u32p, C.c_uint32, u32p, u32p, u32p, C.POINTER(C.c_uint8), C.c_uint32]
         L.hm_bpe_count.argtypes = [C.c_char_p, C.c_size_t]
         L.hm_bpe_count.restype = C.c_uint32
@@ -132,3 +134,12 @@ def bpe_pretokenize(text: bytes):
     ends = (C.c_uint32 * cap)()
     n = lib().hm_bpe_pretokenize(text, len(text), ends, cap)
     return list(ends[:n])
+
+
+def warp_request(body: bytes):
+    """the warp-per-document latency path (host driver of warp_scan.cuh), same convention as fast_request"""
+    return _req(lib().hm_warp_request, body)
+
+
+def warp_response(body: bytes):
+    return _resp(lib().hm_warp_response, body)

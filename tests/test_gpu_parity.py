@@ -322,3 +322,36 @@ def test_two_stage_scan_fuzzed_and_plain_documents(gwmod):
     wave = w.request_batch(8192, NOW + 2, seed=5, varied=True)
     same(g.handle_request_body(wave), o.request_batch(wave), "plain wave")
     assert g.last_declined == 0
+
+
+@pytest.mark.parametrize("seed", [95, 96])
+def test_latency_path_warp_per_body_fuzzed(gwmod, seed):
+    """Micro-batches (up to 2 048 rows) take the warp-per-body latency path (arks_b200/csrc/warp_scan.cuh) in front of the exact
+    engine: hostile and plain documents, bodies around the resident window, every batch size from 1 up."""
+    w = traffic.Workload(n_tenants=8, seed=1)
+    g, o = pair(gwmod, w.tables, 4096, 16 << 20)
+    gen = Gen(seed)
+    rng = np.random.default_rng(seed)
+    now = NOW
+    for n in (1, 2, 31, 33, 64, 700, 2048):
+        bodies = [gen.request() if rng.random() < 0.5 else traffic.chat_request_body_varied(rng, 900, stream=bool(rng.random() < 0.3))
+                  for _ in range(n)]
+        if n >= 64:
+            bodies[5] = traffic.chat_request_body(rng, 2047)
+            bodies[6] = traffic.chat_request_body(rng, 2049)
+            bodies[7] = b""
+        req = RequestBatch.from_lists(bodies, [w.token_strings[i % 8] for i in range(n)], now, pick_rand=rng.integers(0, 1 << 63, n, dtype=np.uint64))
+        a = g.handle_request_body(req)
+        assert g.last_declined >= 0  # the batch took the two-stage (latency) path
+        same(a, o.request_batch(req), f"warp path requests n={n}")
+        rb, flags = [], []
+        while len(rb) < n:
+            b = gen.response() if rng.random() < 0.5 else traffic.chat_response_body_varied(rng, 10, 20, 600)
+            if not D2.search(b):
+                rb.append(b)
+                flags.append(abi.RESP_END_OF_STREAM if rng.random() < 0.95 else 0)
+        resp = ResponseBatch.from_lists(rb, [int(i) % 8 if i % 13 else -1 for i in range(n)], flags, now + 1)
+        c = g.handle_response_body(resp)
+        same(c, o.response_batch(resp), f"warp path responses n={n}")
+        state_same(g, o, now + 1)
+        now += 3
