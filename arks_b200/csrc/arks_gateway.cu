@@ -229,6 +229,7 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
 // A micro-batch whose bodies fit here travels as ONE upload (bodies appended to the offsets / tokens block) on the compute
 // stream itself: one copy and one cross-stream event less on the path a lone request takes.
 constexpr size_t kSmallBatchBytes = 256 << 10;
+constexpr size_t kTinyBatchBytes = 16 << 10;  // below this the bodies ride in the meta block's upload
 
 constexpr int kHotGroup = 256;  // above this many arrivals of one qos entry in a batch the member list is not walked
 #ifndef ARKS_KWIN
@@ -1480,6 +1481,7 @@ struct arks_ctx {
     uint32_t resp_n_sse = 0;
     const uint32_t* d_resp_kind = nullptr;  // mixed batch: row indices, complete bodies first then SSE chunks
     bool req_staged = false, resp_staged = false;
+    bool req_zc = false, resp_zc = false;  // this batch's result rows are written into the pinned host block by the kernels
   };
   static constexpr int kSlots = 4;
   Slot slots[kSlots];
@@ -2133,8 +2135,15 @@ int arks_stage_request_batch(arks_ctx* ctx, const arks_request_batch* b) {
   memcpy(h + o_tok, b->tokens, tok_bytes);
   const bool small = b->bodies_bytes <= kSmallBatchBytes;
   if (small) {
-    memcpy(h + total, b->bodies, b->bodies_bytes);
-    CK(cudaMemcpyAsync(sl.d_req_meta, h, total + b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // one upload for a handful of bodies (the extra memcpy is cheaper than a second copy call); above that the bodies go
+    // up from the caller's buffer, as in the large path, but still on the compute stream (no cross-stream event)
+    if (b->bodies_bytes <= kTinyBatchBytes) {
+      memcpy(h + total, b->bodies, b->bodies_bytes);
+      CK(cudaMemcpyAsync(sl.d_req_meta, h, total + b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      CK(cudaMemcpyAsync(sl.d_req_meta, h, total, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(sl.d_req_meta + total, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     CK(cudaEventRecord(sl.req_copied, ctx->stream));
   } else {
     // uploads run on their own stream so that they overlap the kernels of the batches queued before this one
@@ -2162,7 +2171,10 @@ static void result_offsets(size_t n, size_t offs[kReqResultArrays + 1]) {
   offs[6] = offs[5] + a4; offs[7] = offs[6] + a8; offs[8] = offs[7] + a8;
   offs[9] = offs[8] + a4; offs[10] = offs[9] + a4; offs[11] = offs[10] + a4;
 }
-static void carve_request(arks_ctx* ctx, ReqDev& r, size_t batch_n) {
+// Micro-batches write their result rows straight into the slot's pinned host block (zero copy over PCIe: the block is
+// device-addressable under unified addressing): no D2H copy node between the last kernel and the host's wake-up.
+constexpr uint32_t kZeroCopyRows = 2048;
+static void carve_request(arks_ctx* ctx, ReqDev& r, size_t batch_n, uint8_t* result_base) {
   const size_t n = ctx->max_batch;
   uint8_t* p = ctx->d_inter;
   r.st_reason = p; p += align_up(n, 256);
@@ -2180,7 +2192,7 @@ static void carve_request(arks_ctx* ctx, ReqDev& r, size_t batch_n) {
   r.hotrank = (int32_t*)p;
   size_t offs[kReqResultArrays + 1];
   result_offsets(batch_n, offs);
-  uint8_t* q = ctx->d_result;
+  uint8_t* q = result_base;
   r.reason = q + offs[0];
   r.detail = q + offs[1];
   r.flags = q + offs[2];
@@ -2236,7 +2248,8 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   if (n == 0) return 0;
   CK(cudaStreamWaitEvent(ctx->stream, sl.req_copied, 0));
   ReqDev& r = sl.rq;
-  carve_request(ctx, r, n);
+  sl.req_zc = n <= kZeroCopyRows && sl.h_req_result;
+  carve_request(ctx, r, n, sl.req_zc ? sl.h_req_result : ctx->d_result);
   // batch-local group table sized to the batch (2x, power of two); the three arrays are contiguous
   uint32_t g = 64;
   while (g < 2 * n) g <<= 1;
@@ -2316,7 +2329,7 @@ static int enqueue_request_fetch(arks_ctx* ctx) {
   if (n == 0) return 0;
   size_t offs[kReqResultArrays + 1];
   result_offsets(n, offs);
-  CK(cudaMemcpyAsync(sl.h_req_result, ctx->d_result, offs[kReqResultArrays], cudaMemcpyDeviceToHost, ctx->stream));
+  if (!sl.req_zc) CK(cudaMemcpyAsync(sl.h_req_result, ctx->d_result, offs[kReqResultArrays], cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaEventRecord(sl.req_done, ctx->stream));
   return 0;
 }
@@ -2428,9 +2441,14 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   }
   memcpy(h + o_fl, b->flags, n);
   const bool small = b->bodies_bytes <= kSmallBatchBytes;
-  if (small) {  // one upload on the compute stream (see kSmallBatchBytes)
-    memcpy(h + total, b->bodies, b->bodies_bytes);
-    CK(cudaMemcpyAsync(sl.d_resp_meta, h, total + b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (small) {  // uploads on the compute stream (see kSmallBatchBytes / kTinyBatchBytes)
+    if (b->bodies_bytes <= kTinyBatchBytes) {
+      memcpy(h + total, b->bodies, b->bodies_bytes);
+      CK(cudaMemcpyAsync(sl.d_resp_meta, h, total + b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      CK(cudaMemcpyAsync(sl.d_resp_meta, h, total, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(sl.d_resp_meta + total, b->bodies, b->bodies_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     CK(cudaEventRecord(sl.resp_copied, ctx->stream));
   } else {
     CK(cudaStreamWaitEvent(ctx->h2d, sl.resp_ran, 0));
@@ -2446,10 +2464,12 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   r.flags = sl.d_resp_meta + o_fl;
   r.n = n;
   sl.d_resp_kind = reinterpret_cast<const uint32_t*>(sl.d_resp_meta + o_kind);
-  r.reason = ctx->d_result;
-  r.counted = ctx->d_result + align_up(n, 16);
-  r.usage = (long long*)(ctx->d_result + 2 * align_up(n, 16));
-  r.bpe = (uint32_t*)(ctx->d_result + 2 * align_up(n, 16) + (size_t)n * 24);
+  sl.resp_zc = n <= kZeroCopyRows && sl.h_resp_result;
+  uint8_t* rb = sl.resp_zc ? sl.h_resp_result : ctx->d_result;
+  r.reason = rb;
+  r.counted = rb + align_up(n, 16);
+  r.usage = (long long*)(rb + 2 * align_up(n, 16));
+  r.bpe = (uint32_t*)(rb + 2 * align_up(n, 16) + (size_t)n * 24);
   return 0;
 }
 
@@ -2563,7 +2583,7 @@ static int enqueue_response_fetch(arks_ctx* ctx) {
   sl.resp_fetch_n = (uint32_t)n;
   if (n == 0) return 0;
   const size_t o1 = align_up(n, 16);
-  CK(cudaMemcpyAsync(sl.h_resp_result, ctx->d_result, 2 * o1 + n * 28, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!sl.resp_zc) CK(cudaMemcpyAsync(sl.h_resp_result, ctx->d_result, 2 * o1 + n * 28, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaEventRecord(sl.resp_done, ctx->stream));
   return 0;
 }

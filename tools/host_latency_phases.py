@@ -14,6 +14,8 @@ L = cpphost.load(cpphost.build())
 now = 1_700_000_000
 depth = int(os.environ.get("DEPTH", "1"))
 hb = cpphost.Batcher(L, g._h, max_batch=8192, max_bytes=16 << 20, linger_us=0, max_inflight=depth)
+warm = w.request_batch(4000, now, seed=2, body_size=1024, n_templates=64, varied=True)  # module load, first launches, page faults
+hb.set_fixed_clock(now); hb.open_loop_requests(warm, 200_000, producers=8)
 out = {"env": {k: v for k, v in os.environ.items() if k.startswith("ARKS_")}, "depth": depth}
 for rate in (100_000, 500_000, 1_250_000, 2_500_000):
     now += 86400; hb.set_fixed_clock(now)
