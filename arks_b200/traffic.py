@@ -241,6 +241,7 @@ class Workload:
             endpoints.append(simple_endpoint(MODEL, ns, default_weight=5,
                                              routes=[("model-service-%d" % k, int(rng.integers(1, 100)))
                                                      for k in range(n_backends)]))
+        self.objects = (tokens, quotas, endpoints)  # the CRD-shaped objects (merged shards, incremental config tests)
         self.tables = Tables(tokens, quotas, endpoints)
         if zipf_alpha > 0:
             p = 1.0 / np.power(np.arange(1, n_tenants + 1, dtype=np.float64), zipf_alpha)

@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--wave", type=int, default=WAVE)
     ap.add_argument("--tenants", type=int, default=TENANTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-requests", type=int, default=2_000_000,
+                    help="requests per GPU in the 1.25 M/s open-loop latency run (10 M for the metric's full sample)")
     return ap.parse_args()
 
 
@@ -106,6 +108,30 @@ def build_waves(workload, n_waves, wave, rank):
             for k in range(n_waves)]
 
 
+def bind_to_gpu_numa(local: int):
+    """Run this rank's threads (and so, by first touch, its pinned staging buffers) on the NUMA node its GPU hangs off:
+    round 1's 8-GPU end-to-end curve fell to 0.67 because GPUs 4-7 sit on node 1 while every rank's host buffers and
+    batcher threads were wherever the scheduler put them. Returns what was done (for the report)."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        dom, rest = bus.split(":", 1)
+        node = int(open(f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node").read())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA information for this GPU"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "note": "node has no CPU this process may use"}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # no sysfs / nvidia-smi: run unpinned
+        return {"numa_node": None, "note": f"not pinned: {e!r}"}
+
+
 def pin_batch(b):
     """Re-home a batch's arrays in pinned host memory (what the Go batcher's ring buffers would be)."""
     import torch
@@ -126,40 +152,107 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def best_thread_count(o, req, resp, now):
-    """The threaded oracle does not scale to every hardware thread of every box (hyper-threads, cgroup quotas): time one
-    wave at cpu_count, /2, /4, /8 threads and keep the fastest, so that the baseline is the best the host can do."""
-    n = os.cpu_count() or 1
-    best, best_t = n, None
-    for th in sorted({max(1, n), max(1, n // 2), max(1, n // 4), max(1, n // 8)}, reverse=True):
+def physical_cores():
+    """[(socket, cpu)]: one logical CPU per physical core this process may run on, socket by socket (sysfs topology)"""
+    allowed = sorted(os.sched_getaffinity(0))
+    seen, out = set(), []
+    for c in allowed:
+        base = f"/sys/devices/system/cpu/cpu{c}/topology"
+        try:
+            sib = open(f"{base}/thread_siblings_list").read().strip()
+            pkg = int(open(f"{base}/physical_package_id").read())
+        except OSError:
+            sib, pkg = str(c), 0
+        if (pkg, sib) not in seen:
+            seen.add((pkg, sib))
+            out.append((pkg, c))
+    return sorted(out)
+
+
+def choose_threads(o, req, resp, now):
+    """The threaded oracle is memory- and barrier-bound: more threads than physical cores of one socket rarely help and
+    often hurt (round 1: 2.75 M vs 8.45 M req/s on two boxes of the same type because the count was picked from 4 noisy
+    timings). Candidates are sets of PHYSICAL cores, the workers are pinned to them, every candidate gets a warm-up wave and
+    5 timed waves, the median decides; all candidates' rates go into the report."""
+    cores = physical_cores()
+    sock0 = [c for p, c in cores if p == cores[0][0]]
+    allc = [c for _, c in cores]
+    cands = []
+    for cpus in (sock0, sock0[:max(1, len(sock0) // 2)], sock0[:max(1, len(sock0) // 4)], allc, allc[:max(1, len(allc) // 2)]):
+        if cpus and cpus not in cands:
+            cands.append(cpus)
+    everything = set(os.sched_getaffinity(0))
+    rates, best = [], None
+    for cpus in cands:
+        os.sched_setaffinity(0, cpus)  # the oracle's pool is re-created per thread count and inherits this mask
         ts = []
-        for _ in range(4):  # the first call at a new thread count also (re)creates the worker pool
+        for k in range(6):
             req.now_unix, resp.now_unix = now, now + 1
             t0 = time.perf_counter()
-            o.request_batch(req, threads=th)
-            o.response_batch(resp, threads=th)
-            ts.append(time.perf_counter() - t0)
+            o.request_batch(req, threads=len(cpus))
+            o.response_batch(resp, threads=len(cpus))
+            if k:
+                ts.append(time.perf_counter() - t0)
             now += STEP_S
-        if best_t is None or min(ts) < best_t:
-            best, best_t = th, min(ts)
-    return best, now
+        med = float(np.median(ts))
+        rates.append({"threads": len(cpus), "sockets": len({p for p, c in cores if c in cpus}), "req_per_s": round(req.n / med)})
+        if best is None or med < best[0]:
+            best = (med, cpus)
+    os.sched_setaffinity(0, best[1])
+    return best[1], rates, now, everything
 
 
-def cpu_baseline(workload, wave, seconds=12.0, threads=None):
-    """The reference's CPU path as restated by the oracle (kind=port), tenant-sharded over the host's cores, on a
-    bounded sample of the same workload. In-memory counters: it omits the ~9 Redis round trips per request the real
-    Go gateway pays, i.e. it is a generous baseline."""
+def sharded_reference_workload(args, world):
+    """What `world` tenant-sharded GPUs serve per step, for the CPU arm: world x tenants, world x wave requests. The bodies of
+    the world shards are the same 64 Ki generated documents (generating world x 64 Ki distinct ones in Python would take
+    minutes and changes nothing for a parser); every shard has its own tenants, tokens and counters."""
+    from arks_b200 import abi, traffic
+    from arks_b200.tables import Tables
+    shards = [traffic.Workload(n_tenants=args.tenants, seed=0xA2C5 + r) for r in range(world)]
+    if world == 1:
+        w = shards[0]
+        return w, w.request_batch(args.wave, NOW0, seed=1000, body_size=BODY, n_templates=N_TEMPL, varied=True)
+    tokens, quotas, endpoints = [], [], []
+    for r, sh in enumerate(shards):  # namespaces are per shard: prefix them so that the merged config keeps them apart
+        for objs, out in ((sh.objects[0], tokens), (sh.objects[1], quotas), (sh.objects[2], endpoints)):
+            for o in objs:
+                o = json.loads(json.dumps(o))
+                o["metadata"]["namespace"] = f"s{r}-" + o["metadata"]["namespace"]
+                if "token" in o.get("spec", {}):
+                    o["spec"]["token"] = f"s{r}-" + o["spec"]["token"]
+                out.append(o)
+    merged = traffic.Workload.__new__(traffic.Workload)
+    merged.tables = Tables(tokens, quotas, endpoints)
+    merged.n_tenants, merged.seed, merged.popularity = args.tenants * world, 0xA2C5, None
+    merged.token_strings = [f"s{r}-".encode() + t for r, sh in enumerate(shards) for t in sh.token_strings]
+    base = shards[0].request_batch(args.wave, NOW0, seed=1000, body_size=BODY, n_templates=N_TEMPL, varied=True)
+    bodies = [bytes(base.bodies[base.body_off[i]:base.body_off[i] + base.body_len[i]]) for i in range(base.n)]
+    toks = [bytes(base.tokens[base.token_off[i]:base.token_off[i + 1]]) for i in range(base.n)]
+    req = abi.RequestBatch.from_lists(bodies * world, [f"s{r}-".encode() + t for r in range(world) for t in toks], NOW0,
+                                      pick_rand=np.tile(base.pick_rand, world))
+    return merged, req
+
+
+def cpu_arm(args, world, seconds=None, steps=None, warmup=0):
+    """The reference's CPU path as restated by the oracle (kind=port): the C restatement of the Go handlers with in-memory
+    counters — it omits the ~9 Redis round trips per request the real gateway pays, i.e. a generous baseline.
+    Tenant-sharded over pinned physical cores. Either a bounded sample (`seconds`) or exactly `steps` steps."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import orklib
-    threads = threads or (os.cpu_count() or 1)
-    o = orklib.Oracle(workload.tables)
-    req = workload.request_batch(wave, NOW0, seed=4242, body_size=BODY, n_templates=N_TEMPL, varied=True)
-    a = o.request_batch(req, threads=threads)
-    resp = workload.response_batch(a, NOW0 + 1, seed=4243, body_size=RESP_BODY, varied=True, n_templates=N_TEMPL)
-    o.response_batch(resp, threads=threads)
-    threads, now = best_thread_count(o, req, resp, NOW0 + STEP_S)
-    done, t_used, steps = 0, 0.0, 0
-    while t_used < seconds and steps < 400:
+    w, req = sharded_reference_workload(args, world)
+    o = orklib.Oracle(w.tables)
+    a = o.request_batch(req, threads=os.cpu_count() or 1)
+    resp = w.response_batch(a, NOW0 + 1, seed=2000, body_size=RESP_BODY, varied=True, n_templates=N_TEMPL or (0 if world == 1 else 4096))
+    o.response_batch(resp, threads=os.cpu_count() or 1)
+    cpus, rates, now, everything = choose_threads(o, req, resp, NOW0 + STEP_S)
+    threads = len(cpus)
+    for _ in range(warmup):
+        req.now_unix, resp.now_unix = now, now + 1
+        o.request_batch(req, threads=threads)
+        o.response_batch(resp, threads=threads)
+        now += STEP_S
+    done, t_used, n_steps = 0, 0.0, 0
+    while (steps is not None and n_steps < steps) or (steps is None and t_used < seconds and n_steps < 400):
         req.now_unix, resp.now_unix = now, now + 1
         t0 = time.perf_counter()
         o.request_batch(req, threads=threads)
@@ -167,50 +260,27 @@ def cpu_baseline(workload, wave, seconds=12.0, threads=None):
         t_used += time.perf_counter() - t0
         done += req.n
         now += STEP_S
-        steps += 1
-    return {"value": done / t_used, "unit": "req/s", "cores": threads, "kind": "port",
-            "sample": f"{steps} waves of {req.n} requests + {resp.n} responses, oracle/libarks_oracle.so "
-                      f"(C restatement of the Go path, in-memory counters, no Redis), {threads} threads tenant-sharded "
-                      f"(fastest of cpu_count, /2, /4, /8 on this host)"}, o
+        n_steps += 1
+    os.sched_setaffinity(0, everything)
+    sample = (f"{n_steps} steps of {req.n} requests + {resp.n} responses ({world} tenant shard(s) of {args.tenants} tenants); "
+              f"oracle/libarks_oracle.so = C restatement of the Go path, in-memory counters, no Redis; {threads} worker threads "
+              f"pinned to physical cores {cpus[0]}..{cpus[-1]}; candidates (median of 5 waves each): {json.dumps(rates)}")
+    return {"value": done / t_used, "unit": "req/s", "cores": threads, "kind": "port", "sample": sample}, t_used / max(n_steps, 1)
 
 
 def run_reference(args):
     rank, local, world = env_rank()
     if rank != 0:
         return
-    from arks_b200 import traffic
-    w = traffic.Workload(n_tenants=args.tenants, seed=0xA2C5)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orklib
-    threads = os.cpu_count() or 1
-    o = orklib.Oracle(w.tables)
-    req = w.request_batch(args.wave, NOW0, seed=1000, body_size=BODY, n_templates=N_TEMPL, varied=True)
-    a = o.request_batch(req, threads=threads)
-    resp = w.response_batch(a, NOW0 + 1, seed=2000, body_size=RESP_BODY, varied=True, n_templates=N_TEMPL)
-    o.response_batch(resp, threads=threads)
-    threads, now = best_thread_count(o, req, resp, NOW0 + STEP_S)
-    for _ in range(args.warmup):
-        req.now_unix, resp.now_unix = now, now + 1
-        o.request_batch(req, threads=threads)
-        o.response_batch(resp, threads=threads)
-        now += STEP_S
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        req.now_unix, resp.now_unix = now, now + 1
-        o.request_batch(req, threads=threads)
-        o.response_batch(resp, threads=threads)
-        now += STEP_S
-    dt = time.perf_counter() - t0
-    v = args.steps * req.n / dt
-    sample = (f"{args.steps} waves of {req.n} requests + {resp.n} responses per step; the Go gateway cannot be built here "
-              f"(no Go toolchain), so this is oracle/libarks_oracle.so: a C restatement of the Go path with in-memory "
-              f"counters (no Redis round trips), {threads} threads tenant-sharded (fastest of cpu_count, /2, /4, /8 on this host)")
+    world = max(world, args.gpus)
+    cb, s_per_step = cpu_arm(args, world, steps=args.steps, warmup=args.warmup)
+    v = cb["value"]
     print(json.dumps({
         "impl": "reference", "metric": "gateway requests/s (request + response phase)", "value": v, "unit": "req/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": v, "unit": "req/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args, world),
+        "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "req/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -230,6 +300,7 @@ def run_b200(args):
     import torch
     import __graft_entry__ as ge
     rank, local, world = env_rank()
+    numa = bind_to_gpu_numa(local)  # before any pinned allocation and before the library starts its threads
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -365,41 +436,59 @@ def run_b200(args):
                 now += STEP_S
             ts = np.sort(np.array(ts[20:])) * 1e6
             latency[str(bs)] = {"p50_us": float(ts[len(ts) // 2]), "p99_us": float(ts[int(len(ts) * 0.99)])}
-    # ---- the same through the compiled host: N concurrent ext_proc streams, each one blocking HandleRequestBody call at a
-    # time, micro-batched by host/cpp's Batcher (per-call latency seen by a stream thread, C++ clock) --------------------
+    # ---- the compiled host (host/cpp Batcher) at BASELINE's operating point: requests ARRIVE at 1.25 M/s on EVERY GPU at the
+    # same time (10 M req/s over 8 GPUs), open loop (exponential gaps, 8 producer threads per GPU, latency = decision handed
+    # over - scheduled arrival: no coordinated omission), >= args.latency_requests requests per GPU drawn from 4096 distinct
+    # bodies; p50 / p99 / p99.9 per rank, worst rank reported. Little's law puts ~150-250 requests in flight per GPU: the
+    # 64 k concurrent streams of the metric are open connections, of which these are the ones with a message in the gateway.
+    from arks_b200 import cpphost
+    hb = cpphost.Batcher(cpphost.load(cpphost.build()), g._h, max_batch=8192, max_bytes=16 << 20)
+    hb.set_fixed_clock(now)
+    distinct = w.request_batch(4096, now, seed=7100 + rank, body_size=BODY, n_templates=0, varied=True)
+
+    def arrivals(n, seed):
+        """n requests drawn from the 4096 distinct ones: the same body bytes, row offsets repeated"""
+        idx = np.random.default_rng(seed).integers(0, distinct.n, n)
+        tl = np.diff(distinct.token_off)
+        L = int(tl[0])  # every generated bearer token has the same length: gather them as a matrix
+        assert np.all(tl == L)
+        mat = distinct.tokens[:distinct.token_off[-1]].reshape(distinct.n, L)[idx]
+        return abi.RequestBatch(distinct.bodies, distinct.body_off[idx].copy(), distinct.body_len[idx].copy(),
+                                np.ascontiguousarray(mat).reshape(-1), (np.arange(n + 1, dtype=np.uint64) * L).astype(np.uint32), now,
+                                distinct.pick_rand[idx].copy())
+
+    hb.open_loop_requests(arrivals(8000, 1), rate_per_s=400_000, producers=8)  # warm-up: first launches, page faults
     streams_lat, open_lat = {}, {}
-    if rank == 0:
-        from arks_b200 import cpphost
-        hb = cpphost.Batcher(cpphost.load(cpphost.build()), g._h, max_batch=8192, max_bytes=16 << 20)
-        hb.set_fixed_clock(now)
-        for streams in (1, 64):
-            n_calls = {1: 2000, 64: 40000}[streams]
-            load = w.request_batch(n_calls, now, seed=7100 + streams, body_size=BODY, n_templates=256, varied=True)
-            before = hb.stats()
-            _, lat_ns, wall = hb.run_requests(load, threads=streams)
-            after = hb.stats()
-            lat_us = np.sort(lat_ns[n_calls // 10:]) / 1e3
-            nb = after["request_batches"] - before["request_batches"]
-            streams_lat[str(streams)] = {"p50_us": float(lat_us[len(lat_us) // 2]), "p99_us": float(lat_us[int(len(lat_us) * 0.99)]),
-                                         "req_per_s": n_calls / wall, "mean_batch": n_calls / max(nb, 1)}
-            now += STEP_S
-            hb.set_fixed_clock(now)
-        # open loop: requests ARRIVE at a fixed rate through the asynchronous API; 1.25 M/s per GPU is the share of one GPU
-        # in BASELINE's "10 M req/s on 8 GPUs with p99 < 200 us" operating point
-        for rate in (250_000, 1_250_000):
-            n_calls = int(rate * 0.15)
-            load = w.request_batch(n_calls, now, seed=7200 + rate % 97, body_size=BODY, n_templates=256, varied=True)
-            before = hb.stats()
-            dec, lat_ns, wall = hb.open_loop_requests(load, rate_per_s=rate, producers=8)
-            after = hb.stats()
-            lat_us = np.sort(lat_ns[n_calls // 10:]) / 1e3
-            nb = after["request_batches"] - before["request_batches"]
-            open_lat[str(rate)] = {"p50_us": float(lat_us[len(lat_us) // 2]), "p99_us": float(lat_us[int(len(lat_us) * 0.99)]),
-                                   "achieved_req_per_s": n_calls / wall, "mean_batch": n_calls / max(nb, 1),
-                                   "admitted": int((dec["reason"] == 0).sum())}
-            now += STEP_S
-            hb.set_fixed_clock(now)
-        hb.close()
+    for streams in ((1, 64) if rank == 0 else ()):
+        n_calls = {1: 2000, 64: 40000}[streams]
+        now += STEP_S; hb.set_fixed_clock(now)
+        before = hb.stats()
+        _, lat_ns, wall = hb.run_requests(arrivals(n_calls, 7100 + streams), threads=streams)
+        after = hb.stats()
+        lat_us = np.sort(lat_ns[n_calls // 10:]) / 1e3
+        nb = after["request_batches"] - before["request_batches"]
+        streams_lat[str(streams)] = {"p50_us": float(lat_us[len(lat_us) // 2]), "p99_us": float(lat_us[int(len(lat_us) * 0.99)]),
+                                     "req_per_s": n_calls / wall, "mean_batch": n_calls / max(nb, 1)}
+    for rate in (250_000, 1_250_000):
+        n_calls = int(rate * 0.4) if rate < 1_000_000 else args.latency_requests
+        now += STEP_S; hb.set_fixed_clock(now)
+        load = arrivals(n_calls, 7200 + rate % 97 + rank)
+        barrier()  # every GPU's batcher is under load at the same time
+        before = hb.stats()
+        dec, lat_ns, wall = hb.open_loop_requests(load, rate_per_s=rate, producers=8)
+        after = hb.stats()
+        lat_us = np.sort(lat_ns[n_calls // 20:]) / 1e3
+        cyc = max(after["cycles"] - before["cycles"], 1)
+        q = [float(lat_us[len(lat_us) // 2]), float(lat_us[int(len(lat_us) * 0.99)]), float(lat_us[int(len(lat_us) * 0.999)])]
+        if world > 1:
+            t = torch.tensor(q, device=f"cuda:{local}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            q = [float(x) for x in t]
+        open_lat[str(rate)] = {"p50_us": q[0], "p99_us": q[1], "p999_us": q[2], "requests_per_gpu": n_calls, "gpus_loaded_at_once": world,
+                               "achieved_req_per_s_rank0": n_calls / wall, "mean_batch_rank0": n_calls / cyc,
+                               "us_per_cycle_rank0": {k: round((after["ns_" + k] - before["ns_" + k]) / cyc / 1e3, 1) for k in ("submit", "device", "deliver")},
+                               "admitted_rank0": int((dec["reason"] == 0).sum())}
+    hb.close()
 
     # ---- the same step on single-shape traffic (every request / completion the same template, exactly BODY / RESP_BODY
     # bytes): the lanes of a warp then move in lock step. Reported next to the headline because the scan kernels are
@@ -477,7 +566,8 @@ def run_b200(args):
                        "by_batch_size": latency,
                        "by_concurrent_streams": streams_lat,
                        "open_loop_by_arrival_rate": open_lat,
-                       "open_loop_what": "requests arrive at the given rate (exponential gaps, 8 producer threads) through host/cpp Batcher::SubmitRequest; latency = decision callback - scheduled arrival",
+                       "open_loop_what": "requests ARRIVE at the given rate per GPU on every GPU at once (exponential gaps, 8 producer threads per GPU) through host/cpp Batcher::SubmitRequest; latency = decision callback - scheduled arrival; worst rank's percentiles; 1 250 000/s per GPU = BASELINE's 10 M req/s over 8 GPUs, target p99 < 200 us",
+                       "numa": numa,
                        "streams_what": "N stream threads, one blocking HandleRequestBody at a time each, through host/cpp Batcher (C++); per-call latency"},
         "gpu_launches": int(launches),
         "single_shape_traffic": uniform,
@@ -493,7 +583,7 @@ def run_b200(args):
                                   float(np.mean([int(b.body_len.sum()) for b in resps]))) * args.steps * world / (dev_ms / 1e3) / 8e12,
     }
     if not args.no_cpu_baseline:
-        out["cpu_baseline"], _ = cpu_baseline(w, args.wave)
+        out["cpu_baseline"], _ = cpu_arm(args, 1, seconds=12.0)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
