@@ -65,6 +65,11 @@ class ArksTables(C.Structure):
     ]
 
 
+class ArksQosSpec(C.Structure):  # arks_qos_spec: one spec.qos[] entry of arks_upsert_token
+    _fields_ = [("model", C.c_char_p), ("model_len", C.c_uint32), ("quota", C.c_char_p), ("quota_len", C.c_uint32),
+                ("n_rl", C.c_uint32), ("rl_rule", u8p), ("rl_value", i64p)]
+
+
 class ArksRequestBatch(C.Structure):
     _fields_ = [("n", C.c_uint32), ("bodies", u8p), ("body_off", u32p), ("body_len", u32p),
                 ("bodies_bytes", C.c_uint64), ("tokens", u8p), ("token_off", u32p), ("pick_rand", u64p),

@@ -37,7 +37,7 @@ REQ_DTYPE = np.dtype(RequestDecision)
 RESP_DTYPE = np.dtype(ResponseDecision)
 EXPORTED = ["arks_host_create", "arks_host_destroy", "arks_host_set_fixed_clock", "arks_host_request", "arks_host_response",
             "arks_host_stats", "arks_host_run_requests", "arks_host_run_responses", "arks_host_open_loop_requests",
-            "arks_host_stream_transcript", "arks_host_load_tables", "arks_host_set_names", "arks_host_request_error_reply",
+            "arks_host_stream_transcript", "arks_host_load_tables", "arks_host_apply_config", "arks_host_set_names", "arks_host_request_error_reply",
             "arks_host_response_error_reply"]
 
 
@@ -66,6 +66,7 @@ def load(path: str = LIB):
     L.arks_host_request.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint64, C.POINTER(RequestDecision)]
     L.arks_host_response.argtypes = [vp, C.c_int32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint8, C.POINTER(ResponseDecision)]
     L.arks_host_load_tables.argtypes = [vp, vp]
+    L.arks_host_apply_config.argtypes = [vp]
     L.arks_host_set_names.argtypes = [vp, C.c_char_p, C.c_uint32]
     L.arks_host_request_error_reply.argtypes = [vp, C.POINTER(RequestDecision), C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32,
                                                 C.c_char_p, C.c_uint32]
@@ -127,6 +128,15 @@ class Batcher:
         if rc:
             raise RuntimeError(f"arks_host_load_tables: {rc}")
         self.set_names(tables)
+
+    def apply_config(self, tables=None):
+        """publish the arks_upsert_* / arks_delete_* calls made on the context (Batcher::ApplyConfig); `tables`: the same
+        objects as an arks_b200.tables.Tables in (namespace, name) order, for the reply-shaping names"""
+        rc = self.L.arks_host_apply_config(self._h)
+        if rc:
+            raise RuntimeError(f"arks_host_apply_config: {rc}")
+        if tables is not None:
+            self.set_names(tables)
 
     def set_names(self, tables):
         blob = tables.names_blob()

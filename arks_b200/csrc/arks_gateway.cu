@@ -30,6 +30,8 @@
 #include <string.h>
 
 #include <deque>
+#include <mutex>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -39,6 +41,7 @@
 #include "mask_scan.cuh"
 #include "warp_scan.cuh"
 #include "bpe.cuh"
+#include "config_store.h"
 
 using namespace arks;
 
@@ -529,7 +532,7 @@ __global__ void len_scatter_kernel(const uint32_t* body_len, uint32_t n, uint32_
 template <int SCHED, bool FROM_LIST>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_request_kernel(DevTables T, ReqDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t n = FROM_LIST ? *B.slow_n : B.n;
+  const uint32_t n = FROM_LIST ? *B.slow_n + 1u : B.n;  // the counter starts at -1 (it is cleared together with the 0xff tables)
   const uint32_t lane_id = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * B.bpw + (threadIdx.x & 31);
   if (FROM_LIST && ((blockIdx.x * blockDim.x) >> 5) * B.bpw >= n) return;  // nothing left for this block
   const bool live = (threadIdx.x & 31) < B.bpw && lane_id < n;
@@ -650,7 +653,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_request_kernel(DevTables T,
   const uint32_t len = B.body_len[i];
   FastOut o;
   if (!fast_scan_lane<K_REQ>(body, len, sm, o)) {
-    B.slow_list[atomicAdd(B.slow_n, 1u)] = i;
+    B.slow_list[atomicAdd(B.slow_n, 1u) + 1u] = i;
     return;
   }
   B.model_off[i] = o.m_rawlen ? o.m_start : 0u;
@@ -810,7 +813,7 @@ __global__ void __launch_bounds__(kWdWarps * 32) warp_request_kernel(DevTables T
   const bool ok = elig && wd_scan_doc<K_REQ>(sm.doc, len, sm, o);
   if ((threadIdx.x & 31) != 0) return;
   if (!ok) {
-    B.slow_list[atomicAdd(B.slow_n, 1u)] = i;
+    B.slow_list[atomicAdd(B.slow_n, 1u) + 1u] = i;
     return;
   }
   B.model_off[i] = o.m_rawlen ? o.m_start : 0u;
@@ -1096,7 +1099,7 @@ __device__ __forceinline__ void account_usage(const DevTables& T, const RespDev&
 template <int SCHED, bool FROM_LIST>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response_kernel(DevTables T, RespDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t n = FROM_LIST ? *B.slow_n : B.n;
+  const uint32_t n = FROM_LIST ? *B.slow_n + 1u : B.n;  // the counter starts at -1 (it is cleared together with the 0xff tables)
   const uint32_t lane_id = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * B.bpw + (threadIdx.x & 31);
   if (FROM_LIST && ((blockIdx.x * blockDim.x) >> 5) * B.bpw >= n) return;
   const bool live = (threadIdx.x & 31) < B.bpw && lane_id < n;
@@ -1155,7 +1158,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_response_kernel(DevTables T
       else { u0 = o.usage[0]; u1 = o.usage[1]; u2 = o.usage[2]; }
       counted = reason == ARKS_R_OK && u2 != 0;               // :186
     } else {
-      B.slow_list[atomicAdd(B.slow_n, 1u)] = i;  // the exact engine decides (and accounts) this one
+      B.slow_list[atomicAdd(B.slow_n, 1u) + 1u] = i;  // the exact engine decides (and accounts) this one
       live = false;
     }
   } else if (in && pending) {
@@ -1188,7 +1191,7 @@ __global__ void __launch_bounds__(kWdWarps * 32) warp_response_kernel(DevTables 
       else { u0 = o.usage[0]; u1 = o.usage[1]; u2 = o.usage[2]; }
       counted = reason == ARKS_R_OK && u2 != 0;               // :186
     } else {
-      if (lane == 0) B.slow_list[atomicAdd(B.slow_n, 1u)] = i;  // the exact engine decides (and accounts) this one
+      if (lane == 0) B.slow_list[atomicAdd(B.slow_n, 1u) + 1u] = i;  // the exact engine decides (and accounts) this one
       live = false;
     }
   } else if (pending) {
@@ -1431,6 +1434,10 @@ struct arks_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;  // kernels, counter memsets, result D2H: the order of this stream IS the linearisation
   cudaStream_t h2d = nullptr;     // batch uploads (overlap the kernels of earlier batches)
+  cudaStream_t cfg_stream = nullptr;  // config plane: the next generation's tables are uploaded here, off the data path
+  std::mutex cfg_mu;                  // prepare (config thread) vs commit (batch thread)
+  arks::ConfigStore* store = nullptr;  // objects behind arks_upsert_* / arks_delete_*
+  int32_t *d_qos_from = nullptr, *d_quota_from = nullptr;  // row maps of the current generation (kept alive for the carry kernels)
   char err[512] = {0};
   uint32_t max_batch = 0;
   uint64_t max_bytes = 0;
@@ -1501,6 +1508,7 @@ struct arks_ctx {
   cudaEvent_t ev_admit0 = nullptr;              // start of rank_hot + limit_admit (after the BPE kernels)
   bool is_req_timing = false;
   bool last_two_stage = false;
+  const uint32_t* last_slow_n = nullptr;
   uint8_t* d_inter = nullptr;    // intermediates + group table
   uint32_t* d_perm = nullptr;    // lane -> body permutation of the batch being scanned (length order)
   uint32_t* d_lenhist = nullptr; // kLenBuckets counters / offsets
@@ -1590,6 +1598,7 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->cfg_stream, cudaStreamNonBlocking));
   size_t n = max_batch;
   // meta: body_off, body_len, token_off(n+1), pick_rand, qos, flags + token bytes (256 B per request budget)
   ctx->meta_cap = align_up(n * 4, 256) * 4 + align_up(n * 8, 256) + align_up(n, 256) + align_up(n * 256, 256) + kSmallBatchBytes + 256;
@@ -1639,9 +1648,11 @@ static void free_tables(arks_ctx* ctx) {
   ctx->table_allocs.clear();
 }
 
+static void free_store(arks::ConfigStore* s);
 void arks_destroy(arks_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  free_store(ctx->store);
   if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_tables(ctx);
@@ -1686,6 +1697,9 @@ void arks_destroy(arks_ctx* ctx) {
   cudaFree(ctx->d_result);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
+  if (ctx->cfg_stream) cudaStreamDestroy(ctx->cfg_stream);
+  cudaFree(ctx->d_qos_from);
+  cudaFree(ctx->d_quota_from);
   delete ctx;
 }
 
@@ -1696,8 +1710,8 @@ int64_t arks_last_declined(arks_ctx* ctx) {
   if (!ctx || !ctx->last_two_stage) return -1;
   if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
   uint32_t v = 0;
-  if (cudaMemcpy(&v, ctx->d_slow, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  return (int64_t)v;
+  if (!ctx->last_slow_n || cudaMemcpy(&v, ctx->last_slow_n, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)(v + 1u);  // the counter starts at -1
 }
 uint64_t arks_launch_count(const arks_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -1802,9 +1816,50 @@ static int queue_bpe(arks_ctx* ctx, const uint8_t* bodies, const uint32_t* body_
 }
 
 // ---- config plane -------------------------------------------------------------------------------
-int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
-  if (!ctx || !t) return ARKS_E_INVALID_ARG;
+// Counters of the outgoing generation carried into the incoming one ON THE DEVICE, stream-ordered between two batches:
+// row q of the new arrays is row map[q] of the old ones (or zero). No host round trip, no stream synchronisation.
+__global__ void carry_rows_kernel(long long* dst, const long long* src, const int32_t* map, uint32_t n_new, uint32_t cols, uint32_t dst_stride,
+                                  uint32_t src_stride, int col_major) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_new * cols) return;
+  const uint32_t q = col_major ? k % n_new : k / cols, c = col_major ? k / n_new : k % cols;
+  const int32_t o = map[q];
+  // rate counters are [rule][qos] (col_major: the "column" index c selects the rule plane), the others [row][col]
+  const size_t di = col_major ? (size_t)c * dst_stride + q : (size_t)q * cols + c;
+  const size_t si = col_major ? (size_t)c * src_stride + (o < 0 ? 0 : o) : (size_t)(o < 0 ? 0 : o) * cols + c;
+  dst[di] = o < 0 ? 0 : src[si];
+}
+
+// a generation built off the data path (arks_prepare_tables), waiting for arks_commit_tables
+struct arks_prepared {
+  HostTables ht;
+  std::vector<void*> allocs;  // tables; freed when the generation is retired
+  DevTables d{};
+  long long *rate = nullptr, *quota = nullptr, *metrics = nullptr, *qdelta = nullptr, *qtmp = nullptr, *qexp = nullptr;
+  int32_t *d_qos_from = nullptr, *d_quota_from = nullptr;  // new row -> old row, on the device
+  std::vector<int32_t> old_to_new;                          // qos index of the outgoing generation -> this one
+  uint32_t base_generation = 0;
+  uint32_t n_qos = 0, n_quotas = 0;
+};
+
+static void free_prepared(arks_ctx* ctx, arks_prepared* p) {
+  if (!p) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->cfg_stream);
+  for (void* q : p->allocs) cudaFree(q);
+  cudaFree(p->rate); cudaFree(p->quota); cudaFree(p->metrics); cudaFree(p->qdelta); cudaFree(p->qtmp); cudaFree(p->qexp);
+  cudaFree(p->d_qos_from); cudaFree(p->d_quota_from);
+  delete p;
+}
+void arks_discard_prepared(arks_ctx* ctx, arks_prepared* p) {
+  if (ctx) free_prepared(ctx, p);
+}
+
+int arks_prepare_tables(arks_ctx* ctx, const arks_tables* t, arks_prepared** out) {
+  if (!ctx || !t || !out) return ARKS_E_INVALID_ARG;
+  *out = nullptr;
   CK(cudaSetDevice(ctx->device));
+  std::lock_guard<std::mutex> cfg_guard(ctx->cfg_mu);
   auto S = [&](uint32_t id) {
     return std::string((const char*)t->str_bytes + t->str_off[id], t->str_off[id + 1] - t->str_off[id]);
   };
@@ -1873,49 +1928,31 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
   ht.quota_key.resize(t->n_quotas);
   for (uint32_t q = 0; q < t->n_quotas; q++) ht.quota_key[q] = S(t->quota_ns_str[q]) + '\0' + S(t->quota_name_str[q]);
 
-  // carry counters over by key (Redis keys survive a CRD edit)
-  std::vector<long long> new_rate((size_t)4 * t->n_qos + 1, 0), new_quota((size_t)3 * t->n_quotas + 1, 0);
-  std::vector<long long> new_qdelta((size_t)3 * t->n_quotas + 1, 0);  // unfolded increments travel with their quota
-  std::vector<long long> new_metrics((size_t)ARKS_METRIC_COLS * t->n_qos + 1, 0);  // series live as long as the process
+  // counters are carried over by key (Redis keys survive a CRD edit): which old row feeds every new row
+  std::vector<int32_t> qos_from(t->n_qos + 1, -1), quota_from(t->n_quotas + 1, -1);
   std::vector<int32_t> old_to_new(ctx->loaded ? ctx->ht.n_qos : 0, -1);  // qos index of the outgoing generation -> this one
   if (ctx->loaded) {
-    CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<long long> old_rate((size_t)4 * ctx->ht.n_qos + 1), old_quota((size_t)3 * ctx->ht.n_quotas + 1);
-    std::vector<long long> old_qdelta((size_t)3 * ctx->ht.n_quotas + 1, 0);
-    if (ctx->ht.n_qos) CK(cudaMemcpy(old_rate.data(), ctx->d_rate, (size_t)32 * ctx->ht.n_qos, cudaMemcpyDeviceToHost));
-    if (ctx->ht.n_quotas) CK(cudaMemcpy(old_quota.data(), ctx->d_quota, (size_t)24 * ctx->ht.n_quotas, cudaMemcpyDeviceToHost));
-    if (ctx->d_qdelta && ctx->ht.n_quotas)
-      CK(cudaMemcpy(old_qdelta.data(), ctx->d_qdelta, (size_t)24 * ctx->ht.n_quotas, cudaMemcpyDeviceToHost));
-    std::vector<long long> old_metrics((size_t)ARKS_METRIC_COLS * ctx->ht.n_qos + 1, 0);
-    if (ctx->d_metrics && ctx->ht.n_qos)
-      CK(cudaMemcpy(old_metrics.data(), ctx->d_metrics, (size_t)8 * ARKS_METRIC_COLS * ctx->ht.n_qos, cudaMemcpyDeviceToHost));
     std::unordered_map<std::string, uint32_t> oq, ou;
     for (uint32_t q = 0; q < ctx->ht.n_qos; q++) oq.emplace(ctx->ht.qos_key[q], q);
     for (uint32_t q = 0; q < ctx->ht.n_quotas; q++) ou.emplace(ctx->ht.quota_key[q], q);
     for (uint32_t q = 0; q < t->n_qos; q++) {
       auto it = oq.find(ht.qos_key[q]);
       if (it != oq.end()) {
+        qos_from[q] = (int32_t)it->second;
         if (old_to_new[it->second] < 0) old_to_new[it->second] = (int32_t)q;  // first entry with the key, as in the lookup
-        for (int r = 0; r < 4; r++) new_rate[(size_t)r * t->n_qos + q] = old_rate[(size_t)r * ctx->ht.n_qos + it->second];
-        for (int c = 0; c < ARKS_METRIC_COLS; c++)
-          new_metrics[(size_t)ARKS_METRIC_COLS * q + c] = old_metrics[(size_t)ARKS_METRIC_COLS * it->second + c];
       }
     }
     for (uint32_t q = 0; q < t->n_quotas; q++) {
       auto it = ou.find(ht.quota_key[q]);
-      if (it != ou.end())
-        for (int k = 0; k < 3; k++) {
-          new_quota[(size_t)3 * q + k] = old_quota[(size_t)3 * it->second + k];
-          new_qdelta[(size_t)3 * q + k] = old_qdelta[(size_t)3 * it->second + k];
-        }
+      if (it != ou.end()) quota_from[q] = (int32_t)it->second;
     }
   }
 
-  // Build the new generation completely before touching the old one: a failed allocation or upload leaves the context
-  // serving the previous tables and counters.
+  // Build the new generation completely before touching the old one, on the config stream: a failed allocation or upload
+  // leaves the context serving the previous tables and counters, and the data path never waits for any of this.
   std::vector<void*> fresh;
   auto drop_fresh = [&]() {
-    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->cfg_stream);
     for (void* p : fresh) cudaFree(p);
   };
   auto put = [&](const void* src, size_t bytes, void** out, size_t alloc_bytes = 0) -> int {
@@ -1923,7 +1960,8 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
     cudaError_t e = cudaMalloc(&p, (alloc_bytes > bytes ? alloc_bytes : bytes) + 64);
     if (e == cudaSuccess) {
       fresh.push_back(p);
-      if (bytes) e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+      if (bytes && src) e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->cfg_stream);
+      else if (!src) e = cudaMemsetAsync(p, 0, (alloc_bytes > bytes ? alloc_bytes : bytes) + 64, ctx->cfg_stream);
     }
     if (e != cudaSuccess) {
       drop_fresh();
@@ -1970,13 +2008,16 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
   PUT(v_bw, backend_weight);
   const size_t n_table_allocs = fresh.size();
   long long *n_rate = nullptr, *n_quota = nullptr, *n_metrics = nullptr, *n_qdelta = nullptr, *n_qtmp = nullptr, *n_qexp = nullptr;
+  int32_t *n_qos_from = nullptr, *n_quota_from = nullptr;
   {
     int rc;
-    if ((rc = put(new_rate.data(), (size_t)32 * t->n_qos, (void**)&n_rate))) return rc;
-    if ((rc = put(new_quota.data(), (size_t)24 * t->n_quotas, (void**)&n_quota))) return rc;
-    if ((rc = put(new_metrics.data(), (size_t)8 * ARKS_METRIC_COLS * t->n_qos, (void**)&n_metrics))) return rc;
+    if ((rc = put(nullptr, 0, (void**)&n_rate, (size_t)32 * t->n_qos))) return rc;
+    if ((rc = put(nullptr, 0, (void**)&n_quota, (size_t)24 * t->n_quotas))) return rc;
+    if ((rc = put(nullptr, 0, (void**)&n_metrics, (size_t)8 * ARKS_METRIC_COLS * t->n_qos))) return rc;
+    if ((rc = put(qos_from.data(), (size_t)4 * (t->n_qos + 1), (void**)&n_qos_from))) return rc;
+    if ((rc = put(quota_from.data(), (size_t)4 * (t->n_quotas + 1), (void**)&n_quota_from))) return rc;
     if (ctx->share_quota) {
-      if ((rc = put(new_qdelta.data(), (size_t)24 * t->n_quotas, (void**)&n_qdelta))) return rc;
+      if ((rc = put(nullptr, 0, (void**)&n_qdelta, (size_t)24 * t->n_quotas))) return rc;
       // two scratch vectors as long as the delta (host-form apply, export snapshot)
       if ((rc = put(nullptr, 0, (void**)&n_qtmp, (size_t)24 * t->n_quotas))) return rc;
       if ((rc = put(nullptr, 0, (void**)&n_qexp, (size_t)24 * t->n_quotas))) return rc;
@@ -1984,39 +2025,163 @@ int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
   }
 #undef PUT
   {
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->cfg_stream);  // the CONFIG stream: the data path is not involved
     if (e != cudaSuccess) {
       drop_fresh();
-      return fail(ctx, ARKS_E_CUDA, "arks_load_tables: %s (tables unchanged)", cudaGetErrorString(e));
+      return fail(ctx, ARKS_E_CUDA, "arks_prepare_tables: %s (tables unchanged)", cudaGetErrorString(e));
     }
   }
-  // commit: nothing below can fail
-  free_tables(ctx);
-  cudaFree(ctx->d_rate);
-  cudaFree(ctx->d_quota);
-  cudaFree(ctx->d_metrics);
-  cudaFree(ctx->d_qdelta);
-  cudaFree(ctx->d_qtmp);
-  cudaFree(ctx->d_qexp);
-  ctx->table_allocs.assign(fresh.begin(), fresh.begin() + n_table_allocs);
-  ctx->d_rate = n_rate; ctx->d_quota = n_quota; ctx->d_metrics = n_metrics;
-  ctx->d_qdelta = n_qdelta; ctx->d_qtmp = n_qtmp; ctx->d_qexp = n_qexp;
+  arks_prepared* p = new arks_prepared();
+  p->allocs.assign(fresh.begin(), fresh.begin() + n_table_allocs);
+  p->rate = n_rate; p->quota = n_quota; p->metrics = n_metrics; p->qdelta = n_qdelta; p->qtmp = n_qtmp; p->qexp = n_qexp;
+  p->d_qos_from = n_qos_from; p->d_quota_from = n_quota_from;
+  d.n_qos = t->n_qos;
+  p->d = d;
+  p->ht = std::move(ht);
+  p->old_to_new = std::move(old_to_new);
+  p->base_generation = ctx->generation;
+  p->n_qos = t->n_qos;
+  p->n_quotas = t->n_quotas;
+  *out = p;
+  return 0;
+}
+
+// The swap: stream-ordered between the batch queued before this call and the one queued after it. Counters are carried
+// into the new arrays by a few small kernels on the compute stream; the old generation is released once they have run.
+// Call from the thread that submits batches. No host-side wait.
+int arks_commit_tables(arks_ctx* ctx, arks_prepared* p) {
+  if (!ctx || !p) return ARKS_E_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  std::lock_guard<std::mutex> cfg_guard(ctx->cfg_mu);
+  if (p->base_generation != ctx->generation)
+    return fail(ctx, ARKS_E_INVALID_ARG, "prepared against generation %u, the context is at %u: prepare again", p->base_generation, ctx->generation);
+  if (ctx->loaded) {
+    auto carry = [&](long long* dst, const long long* src, const int32_t* map, uint32_t n_new, uint32_t cols, uint32_t ds, uint32_t ss, int cm) {
+      if (!dst || !src || !n_new) return;
+      const uint32_t total = n_new * cols;
+      carry_rows_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(dst, src, map, n_new, cols, ds, ss, cm);
+      ctx->launches += 1;
+    };
+    carry(p->rate, ctx->d_rate, p->d_qos_from, p->n_qos, 4, p->n_qos, ctx->ht.n_qos, 1);
+    carry(p->metrics, ctx->d_metrics, p->d_qos_from, p->n_qos, ARKS_METRIC_COLS, 0, 0, 0);
+    carry(p->quota, ctx->d_quota, p->d_quota_from, p->n_quotas, 3, 0, 0, 0);
+    carry(p->qdelta, ctx->d_qdelta, p->d_quota_from, p->n_quotas, 3, 0, 0, 0);
+    CK(cudaGetLastError());
+  }
+  // retire the outgoing generation: freed stream-ordered, after the carry kernels and everything queued before them
+  for (void* q : ctx->table_allocs) cudaFreeAsync(q, ctx->stream);
+  cudaFreeAsync(ctx->d_rate, ctx->stream); cudaFreeAsync(ctx->d_quota, ctx->stream); cudaFreeAsync(ctx->d_metrics, ctx->stream);
+  cudaFreeAsync(ctx->d_qdelta, ctx->stream); cudaFreeAsync(ctx->d_qtmp, ctx->stream); cudaFreeAsync(ctx->d_qexp, ctx->stream);
+  cudaFreeAsync(ctx->d_qos_from, ctx->stream); cudaFreeAsync(ctx->d_quota_from, ctx->stream);
+  ctx->table_allocs = std::move(p->allocs);
+  ctx->d_rate = p->rate; ctx->d_quota = p->quota; ctx->d_metrics = p->metrics;
+  ctx->d_qdelta = p->qdelta; ctx->d_qtmp = p->qtmp; ctx->d_qexp = p->qexp;
+  ctx->d_qos_from = p->d_qos_from; ctx->d_quota_from = p->d_quota_from;
   ctx->qexp_valid = false;
-  ctx->d_backend_weight = const_cast<int32_t*>(d.backend_weight);
+  ctx->d_backend_weight = const_cast<int32_t*>(p->d.backend_weight);
+  DevTables d = p->d;
   d.rate = ctx->d_rate;
   d.metrics = ctx->metrics_on ? ctx->d_metrics : nullptr;
   d.quota = ctx->d_quota;
   d.qdelta = ctx->d_qdelta;
-  d.n_qos = t->n_qos;
   ctx->dt = d;
   if (ctx->loaded) {
-    ctx->remap.push_back(std::move(old_to_new));
+    ctx->remap.push_back(std::move(p->old_to_new));
     if (ctx->remap.size() > ARKS_GEN_HISTORY) ctx->remap.pop_front();
   }
-  ctx->ht = std::move(ht);
+  ctx->ht = std::move(p->ht);
   ctx->generation++;
   ctx->loaded = true;
+  delete p;
   return 0;
+}
+
+// cold start / blocking form: prepare + commit on the calling thread
+int arks_load_tables(arks_ctx* ctx, const arks_tables* t) {
+  arks_prepared* p = nullptr;
+  int rc = arks_prepare_tables(ctx, t, &p);
+  if (rc) return rc;
+  rc = arks_commit_tables(ctx, p);
+  if (rc) { free_prepared(ctx, p); return rc; }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+
+// ---- object-level config plane: config_store.h keeps the objects, these are the C entry points ----
+static void free_store(ConfigStore* s) { delete s; }
+static ConfigStore& store_of(arks_ctx* ctx) {
+  if (!ctx->store) ctx->store = new ConfigStore();
+  return *ctx->store;
+}
+static bool str_ok(const char* p, uint32_t n) { return p || !n; }
+
+int arks_upsert_token(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len, const char* token,
+                      uint32_t token_len, const arks_qos_spec* qos, uint32_t n_qos) {
+  if (!ctx || !str_ok(ns, ns_len) || !str_ok(name, name_len) || !str_ok(token, token_len) || (n_qos && !qos)) return ARKS_E_INVALID_ARG;
+  for (uint32_t i = 0; i < n_qos; i++)
+    if (!str_ok(qos[i].model, qos[i].model_len) || !str_ok(qos[i].quota, qos[i].quota_len) || (qos[i].n_rl && (!qos[i].rl_rule || !qos[i].rl_value)))
+      return fail(ctx, ARKS_E_INVALID_ARG, "arks_upsert_token: qos %u has a NULL field", i);
+  std::lock_guard<std::mutex> g(ctx->cfg_mu);
+  store_of(ctx).upsert_token(ns, ns_len, name, name_len, token, token_len, qos, n_qos);
+  return 0;
+}
+int arks_upsert_quota(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len, const uint8_t* item_type,
+                      const int64_t* item_value, uint32_t n_items) {
+  if (!ctx || !str_ok(ns, ns_len) || !str_ok(name, name_len) || (n_items && (!item_type || !item_value))) return ARKS_E_INVALID_ARG;
+  std::lock_guard<std::mutex> g(ctx->cfg_mu);
+  store_of(ctx).upsert_quota(ns, ns_len, name, name_len, item_type, item_value, n_items);
+  return 0;
+}
+int arks_upsert_endpoint(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len,
+                         const int32_t* backend_weight, uint32_t n_backends) {
+  if (!ctx || !str_ok(ns, ns_len) || !str_ok(name, name_len) || (n_backends && !backend_weight)) return ARKS_E_INVALID_ARG;
+  std::lock_guard<std::mutex> g(ctx->cfg_mu);
+  store_of(ctx).upsert_endpoint(ns, ns_len, name, name_len, backend_weight, n_backends);
+  return 0;
+}
+static int store_erase(arks_ctx* ctx, int which, const char* what, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len) {
+  if (!ctx || !str_ok(ns, ns_len) || !str_ok(name, name_len)) return ARKS_E_INVALID_ARG;
+  std::lock_guard<std::mutex> g(ctx->cfg_mu);
+  if (!store_of(ctx).erase(which, ns, ns_len, name, name_len))
+    return fail(ctx, ARKS_E_INVALID_ARG, "%s %.*s/%.*s is not in the store", what, (int)ns_len, ns ? ns : "", (int)name_len, name ? name : "");
+  return 0;
+}
+int arks_delete_token(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len) {
+  return store_erase(ctx, 0, "ArksToken", ns, ns_len, name, name_len);
+}
+int arks_delete_quota(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len) {
+  return store_erase(ctx, 1, "ArksQuota", ns, ns_len, name, name_len);
+}
+int arks_delete_endpoint(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len) {
+  return store_erase(ctx, 2, "ArksEndpoint", ns, ns_len, name, name_len);
+}
+// store -> arks_tables (the flat form arks_prepare_tables validates and uploads), objects in (namespace, name) order
+int arks_config_prepare(arks_ctx* ctx, arks_prepared** out) {
+  if (!ctx || !out) return ARKS_E_INVALID_ARG;
+  FlatTables flat;
+  {
+    std::lock_guard<std::mutex> g(ctx->cfg_mu);
+    store_of(ctx).flatten(&flat);
+  }
+  const arks_tables t = flat.view();
+  return arks_prepare_tables(ctx, &t, out);
+}
+
+int32_t arks_find_quota(const arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len) {
+  if (!ctx || !ctx->loaded) return -1;
+  const std::string k = std::string(ns ? ns : "", ns_len) + '\0' + std::string(name ? name : "", name_len);
+  for (uint32_t q = 0; q < ctx->ht.n_quotas; q++)
+    if (ctx->ht.quota_key[q] == k) return (int32_t)q;
+  return -1;
+}
+int32_t arks_find_qos(const arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* user, uint32_t user_len, const char* model,
+                      uint32_t model_len) {
+  if (!ctx || !ctx->loaded) return -1;
+  const std::string k = std::string(ns ? ns : "", ns_len) + '\0' + std::string(user ? user : "", user_len) + '\0' + std::string(model ? model : "", model_len);
+  for (uint32_t q = 0; q < ctx->ht.n_qos; q++)
+    if (ctx->ht.qos_key[q] == k) return (int32_t)q;
+  return -1;
 }
 
 uint32_t arks_table_generation(const arks_ctx* ctx) { return ctx ? ctx->generation : 0; }
@@ -2258,14 +2423,14 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
   r.ghead = r.gkey + g;
   r.gcnt = r.gkey + 2 * (size_t)g;
   r.hot_n = r.gkey + 3 * (size_t)g;  // one more word: the hot-group counter, also starting at -1
-  CK(cudaMemsetAsync(r.gkey, 0xff, (size_t)g * 12 + 4, ctx->stream));
+  CK(cudaMemsetAsync(r.gkey, 0xff, (size_t)g * 12 + 8, ctx->stream));  // + the hot-group and declined-rows counters
   const uint32_t tpb = kWarpsPerBlock * 32;
-  r.slow_n = ctx->d_slow;
+  r.slow_n = reinterpret_cast<uint32_t*>(r.hot_n + 1);  // cleared to -1 by the group table's memset
   r.slow_list = ctx->d_slow + 64;
+  ctx->last_slow_n = r.slow_n;
   if (ctx->prof) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   if (ctx->fast_scan && n <= ctx->warp_max) {
     // latency path: a warp per body (warp_scan.cuh), the exact engine for what it declines
-    CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
     r.perm = nullptr;
     warp_request_kernel<<<(n + kWdWarps - 1) / kWdWarps, kWdWarps * 32, kWdSmemPerBlock, ctx->stream>>>(ctx->dt, r);
     r.bpw = 1;
@@ -2278,7 +2443,6 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
     ctx->last_two_stage = true;
   } else if (ctx->fast_scan && n >= ctx->fast_min) {
     // two-stage scan: the fast path (mask_scan.cuh) decides everything plain, the exact engine what it declines
-    CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
     r.perm = queue_length_order(ctx, r.body_len, n);
     if (ctx->prof) CK(cudaEventRecord(ctx->ev_fast[0], ctx->stream));
     fast_request_kernel<<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, r);
@@ -2333,11 +2497,23 @@ static int enqueue_request_fetch(arks_ctx* ctx) {
   CK(cudaEventRecord(sl.req_done, ctx->stream));
   return 0;
 }
+// Wait for an event by polling it: cudaEventSynchronize from the completion thread would sit inside the driver while the
+// dispatcher thread is trying to queue the next batch (measured: two batches in flight were slower than one).
+static cudaError_t wait_event_polling(cudaEvent_t ev) {
+  for (uint32_t spins = 0;; spins++) {
+    const cudaError_t e = cudaEventQuery(ev);
+    if (e != cudaErrorNotReady) return e;
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if (spins > 200000) return cudaEventSynchronize(ev);  // something is slow (a large batch): stop burning the core
+  }
+}
 static int finish_request_fetch(arks_ctx* ctx, int slot, arks_request_result* out) {
   arks_ctx::Slot& sl = ctx->slots[slot];
   const size_t n = sl.req_fetch_n;
   if (n == 0) return 0;
-  CK(cudaEventSynchronize(sl.req_done));
+  CK(wait_event_polling(sl.req_done));
   const uint8_t* h = sl.h_req_result;
   size_t offs[kReqResultArrays + 1];
   result_offsets(n, offs);
@@ -2504,7 +2680,8 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
   auto launch_json_two_stage = [&](RespDev rp) -> int {
     rp.slow_n = ctx->d_slow;
     rp.slow_list = ctx->d_slow + 64;
-    CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
+    ctx->last_slow_n = rp.slow_n;
+    CK(cudaMemsetAsync(ctx->d_slow, 0xff, 4, ctx->stream));
     rp.perm = queue_length_order(ctx, rp.body_len, rp.n);
     if (ctx->prof) CK(cudaEventRecord(ctx->ev_fast[0], ctx->stream));
     fast_response_kernel<<<(rp.n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, rp);
@@ -2543,7 +2720,8 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
       rp.slow_n = ctx->d_slow;
       rp.slow_list = ctx->d_slow + 64;
       rp.perm = nullptr;
-      CK(cudaMemsetAsync(ctx->d_slow, 0, 4, ctx->stream));
+      ctx->last_slow_n = rp.slow_n;
+      CK(cudaMemsetAsync(ctx->d_slow, 0xff, 4, ctx->stream));
       warp_response_kernel<<<(n + kWdWarps - 1) / kWdWarps, kWdWarps * 32, kWdSmemPerBlock, ctx->stream>>>(ctx->dt, rp);
       rp.bpw = 1;
       const dim3 grid(scan_grid(n, rp.bpw));
@@ -2591,7 +2769,7 @@ static int finish_response_fetch(arks_ctx* ctx, int slot, arks_response_result* 
   arks_ctx::Slot& sl = ctx->slots[slot];
   const size_t n = sl.resp_fetch_n;
   if (n == 0) return 0;
-  CK(cudaEventSynchronize(sl.resp_done));
+  CK(wait_event_polling(sl.resp_done));
   const size_t o1 = align_up(n, 16);
   const uint8_t* h = sl.h_resp_result;
   memcpy(out->reason, h, n);

@@ -48,6 +48,21 @@ def lib():
         L.arks_last_error.argtypes = [vp]
         L.arks_load_tables.argtypes = [vp, C.POINTER(ArksTables)]
         L.arks_load_bpe.argtypes = [vp, vp]
+        L.arks_prepare_tables.argtypes = [vp, C.POINTER(ArksTables), C.POINTER(vp)]
+        L.arks_commit_tables.argtypes = [vp, vp]
+        L.arks_discard_prepared.argtypes = [vp, vp]
+        L.arks_discard_prepared.restype = None
+        cp, u32 = C.c_char_p, C.c_uint32
+        L.arks_upsert_token.argtypes = [vp, cp, u32, cp, u32, cp, u32, C.POINTER(abi.ArksQosSpec), u32]
+        L.arks_upsert_quota.argtypes = [vp, cp, u32, cp, u32, abi.u8p, abi.i64p, u32]
+        L.arks_upsert_endpoint.argtypes = [vp, cp, u32, cp, u32, abi.i32p, u32]
+        for f in (L.arks_delete_token, L.arks_delete_quota, L.arks_delete_endpoint):
+            f.argtypes = [vp, cp, u32, cp, u32]
+        L.arks_config_prepare.argtypes = [vp, C.POINTER(vp)]
+        L.arks_find_quota.argtypes = [vp, cp, u32, cp, u32]
+        L.arks_find_quota.restype = C.c_int32
+        L.arks_find_qos.argtypes = [vp, cp, u32, cp, u32, cp, u32]
+        L.arks_find_qos.restype = C.c_int32
         L.arks_table_generation.restype = C.c_uint32
         L.arks_table_generation.argtypes = [vp]
         L.arks_update_endpoint_weights.argtypes = [vp, C.c_uint32, C.c_uint32, abi.i32p]
@@ -91,6 +106,8 @@ def lib():
 
 EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/test_abi.py)
     "arks_abi_version", "arks_create", "arks_destroy", "arks_last_error", "arks_load_tables", "arks_table_generation", "arks_load_bpe",
+    "arks_prepare_tables", "arks_commit_tables", "arks_discard_prepared", "arks_upsert_token", "arks_delete_token", "arks_upsert_quota",
+    "arks_delete_quota", "arks_upsert_endpoint", "arks_delete_endpoint", "arks_config_prepare", "arks_find_quota", "arks_find_qos",
     "arks_update_endpoint_weights", "arks_extract_bearer", "arks_submit_request_batch",
     "arks_submit_response_batch", "arks_stage_request_batch", "arks_run_request_batch",
     "arks_fetch_request_result", "arks_stage_response_batch", "arks_run_response_batch",
@@ -139,6 +156,67 @@ class Gateway:
         ts = tables.c_struct()
         self._ck(lib().arks_load_tables(self._h, C.byref(ts)))
         self.tables = tables
+
+    def prepare_tables(self, tables):
+        """config thread: build + upload the next generation off the data path -> opaque handle for commit_tables"""
+        ts = tables.c_struct()
+        h = C.c_void_p()
+        self._ck(lib().arks_prepare_tables(self._h, C.byref(ts), C.byref(h)))
+        return (h, tables)
+
+    def commit_tables(self, prepared):
+        """batch thread, between two submissions: stream-ordered swap, counters carried by key on the device, no host wait"""
+        h, tables = prepared
+        self._ck(lib().arks_commit_tables(self._h, h))
+        if tables is not None:
+            self.tables = tables
+
+    def discard_prepared(self, prepared):
+        lib().arks_discard_prepared(self._h, prepared[0])
+
+    # ---- one informer event = one call (qosconfig/arks_impl.go:104-189); config_prepare() + commit_tables() publish them
+    def upsert_token(self, namespace: str, name: str, token: str, qos):
+        """qos: [(model, quota_name or "", [(rule, limit), ...]), ...]"""
+        specs = (abi.ArksQosSpec * max(1, len(qos)))()
+        keep = []
+        for i, (model, quota, rls) in enumerate(qos):
+            m, q = model.encode(), (quota or "").encode()
+            rr = np.array([r for r, _ in rls], np.uint8)
+            rv = np.array([v for _, v in rls], np.int64)
+            keep += [m, q, rr, rv]
+            specs[i] = abi.ArksQosSpec(m, len(m), q, len(q), len(rls), abi.ptr(rr, abi.u8p), abi.ptr(rv, abi.i64p))
+        ns, nm, tk = namespace.encode(), name.encode(), token.encode()
+        self._ck(lib().arks_upsert_token(self._h, ns, len(ns), nm, len(nm), tk, len(tk), specs, len(qos)))
+
+    def upsert_quota(self, namespace: str, name: str, items):
+        """items: [(quota_type, limit), ...]"""
+        t = np.array([a for a, _ in items], np.uint8)
+        v = np.array([b for _, b in items], np.int64)
+        ns, nm = namespace.encode(), name.encode()
+        self._ck(lib().arks_upsert_quota(self._h, ns, len(ns), nm, len(nm), abi.ptr(t, abi.u8p), abi.ptr(v, abi.i64p), len(items)))
+
+    def upsert_endpoint(self, namespace: str, name: str, weights):
+        w = np.ascontiguousarray(weights, np.int32)
+        ns, nm = namespace.encode(), name.encode()
+        self._ck(lib().arks_upsert_endpoint(self._h, ns, len(ns), nm, len(nm), abi.ptr(w, abi.i32p), len(w)))
+
+    def delete_object(self, kind: str, namespace: str, name: str):
+        f = {"token": lib().arks_delete_token, "quota": lib().arks_delete_quota, "endpoint": lib().arks_delete_endpoint}[kind]
+        ns, nm = namespace.encode(), name.encode()
+        self._ck(f(self._h, ns, len(ns), nm, len(nm)))
+
+    def config_prepare(self):
+        h = C.c_void_p()
+        self._ck(lib().arks_config_prepare(self._h, C.byref(h)))
+        return (h, None)
+
+    def find_quota(self, namespace: str, name: str) -> int:
+        ns, nm = namespace.encode(), name.encode()
+        return int(lib().arks_find_quota(self._h, ns, len(ns), nm, len(nm)))
+
+    def find_qos(self, namespace: str, user: str, model: str) -> int:
+        ns, u, m = namespace.encode(), user.encode(), model.encode()
+        return int(lib().arks_find_qos(self._h, ns, len(ns), u, len(u), m, len(m)))
 
     def load_bpe(self, tables):
         """switch the bpe_count columns on with a vocabulary (arks_b200.bpe.BpeTables), or off with None"""

@@ -96,16 +96,8 @@ class Tables:
             ns = md.get("namespace", "default")
             e_ns.append(s(ns))
             e_name.append(s(md["name"]))
-            names = []
-            spec = e.get("spec", {})
-            for rc in spec.get("routeConfigs") or []:
-                names.append(rc["name"])
-                b_w.append(int(rc.get("weight", 1)))  # Gateway API backendRef weight defaults to 1
-            for svc in (ready_backends or {}).get((ns, md["name"]), []):
-                if svc in names:
-                    continue
-                names.append(svc)
-                b_w.append(int(spec.get("defaultWeight", 1)))
+            names, weights = endpoint_backends(e, ready_backends)
+            b_w += weights
             self.endpoint_backends.append(names)
             e_off.append(len(b_w))
 
@@ -156,6 +148,24 @@ class Tables:
             self.n_endpoints, ptr(self.ep_ns_str, u32p), ptr(self.ep_name_str, u32p), ptr(self.ep_backend_off, u32p),
             len(self.backend_weight), ptr(self.backend_weight, i32p),
         )
+
+
+def endpoint_backends(e, ready_backends=None):
+    """(backend names, weights) of one ArksEndpoint in the order the controller emits HTTPRoute backendRefs
+    (internal/controller/arksendpoint_controller.go:283-347): static routeConfigs, then ready Services at defaultWeight"""
+    md = e["metadata"]
+    ns = md.get("namespace", "default")
+    names, weights = [], []
+    spec = e.get("spec", {})
+    for rc in spec.get("routeConfigs") or []:
+        names.append(rc["name"])
+        weights.append(int(rc.get("weight", 1)))  # Gateway API backendRef weight defaults to 1
+    for svc in (ready_backends or {}).get((ns, md["name"]), []):
+        if svc in names:
+            continue
+        names.append(svc)
+        weights.append(int(spec.get("defaultWeight", 1)))
+    return names, weights
 
 
 def simple_token(name, namespace, token, model, limits, quota=""):

@@ -100,6 +100,8 @@ struct Batcher::Impl {
   std::deque<InFlight> inflight;            // submitted, not completed (FIFO == device order)
   bool slot_busy[kSlots] = {false, false, false, false};
   mutable std::mutex mu;
+  std::mutex cfg_mu;  // config calls among themselves
+  int swap_in(arks_prepared* p);
   std::condition_variable cv_work, cv_space, cv_done;
   bool stop = false;
   bool cycling = false;  // a cycle is being run (by the dispatcher thread or by a leading caller): one submitter at a time
@@ -449,20 +451,32 @@ bool Batcher::SubmitResponse(int32_t qos, uint32_t gen, std::string_view body, u
   return p_->submit_response(qos, gen, body, flags, cb, user, false);
 }
 uint32_t Batcher::Generation() const { return arks_table_generation(p_->ctx); }
+// config calls are serialised among themselves; the swap itself happens between two cycles
 int Batcher::LoadTables(const arks_tables* t) {
   Impl& I = *p_;
+  std::lock_guard<std::mutex> one(I.cfg_mu);
+  arks_prepared* p = nullptr;
+  int rc = arks_prepare_tables(I.ctx, t, &p);  // batches keep cycling meanwhile
+  return rc ? rc : I.swap_in(p);
+}
+int Batcher::ApplyConfig() {
+  Impl& I = *p_;
+  std::lock_guard<std::mutex> one(I.cfg_mu);
+  arks_prepared* p = nullptr;
+  int rc = arks_config_prepare(I.ctx, &p);
+  return rc ? rc : I.swap_in(p);
+}
+arks_ctx* Batcher::Context() const { return p_->ctx; }
+int Batcher::Impl::swap_in(arks_prepared* p) {
+  Impl& I = *this;
   std::unique_lock<std::mutex> lk(I.mu);
-  // become the one "cycle" in progress: no submit can start, and wait for what is queued on the device
-  auto idle = [&] {
-    if (I.cycling) return false;
-    for (int k = 0; k < kSlots; k++)
-      if (I.slot_busy[k]) return false;
-    return true;
-  };
-  while (!idle()) I.cv_space.wait_for(lk, std::chrono::microseconds(100));
+  // become the one "cycle" in progress for the length of the commit: no submission interleaves with the pointer swap.
+  // Batches already queued on the device are NOT waited for: the commit is ordered behind them on the stream.
+  while (I.cycling) I.cv_space.wait_for(lk, std::chrono::microseconds(20));
   I.cycling = true;
   lk.unlock();
-  const int rc = arks_load_tables(I.ctx, t);
+  const int rc = arks_commit_tables(I.ctx, p);
+  if (rc) arks_discard_prepared(I.ctx, p);
   lk.lock();
   I.cycling = false;
   lk.unlock();
@@ -882,6 +896,7 @@ int arks_host_response(arks_host_batcher* h, int32_t qos, uint32_t gen, const ui
   return out->reason == 255 ? ARKS_E_INVALID_ARG : 0;
 }
 int arks_host_load_tables(arks_host_batcher* h, const arks_tables* t) { return h->b->LoadTables(t); }
+int arks_host_apply_config(arks_host_batcher* h) { return h->b->ApplyConfig(); }
 int arks_host_set_names(arks_host_batcher* h, const char* text, uint32_t len) {
   return ParseNameTables(std::string_view(text, len), &h->names) ? 0 : ARKS_E_INVALID_ARG;
 }

@@ -84,10 +84,16 @@ class Batcher {
   bool SubmitRequest(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user);
   bool SubmitResponse(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user);
 
-  // Config reload between two cycles (qosconfig informer event -> arks_load_tables): waits for the batches queued on the
-  // device, swaps the tables while no cycle runs, and lets the streams go on. Requests decided before the swap keep
-  // their (gen, qos); the library re-maps them by key when their response chunks arrive.
+  // Config change while streams are in flight (qosconfig informer event): the next generation is built and uploaded on
+  // the CALLING (config) thread with batches still running (arks_prepare_tables), then swapped in between two cycles
+  // (arks_commit_tables: stream-ordered, counters carried by key on the device). Nothing waits for queued batches to
+  // drain; the only exclusion is against the few microseconds in which a cycle submits. Requests decided before the
+  // swap keep their (gen, qos); the library re-maps them by key when their response chunks arrive.
   int LoadTables(const arks_tables* t);
+  // The same for the object-level plane: arks_upsert_* / arks_delete_* on Context() from the config thread, then
+  // ApplyConfig() publishes the store (arks_config_prepare + commit).
+  int ApplyConfig();
+  arks_ctx* Context() const;
   uint32_t Generation() const;  // arks_table_generation of the context
 
   void SetClock(int64_t (*clock)(void*), void* arg);  // default: time(nullptr)
@@ -171,6 +177,7 @@ int arks_host_request(arks_host_batcher* b, const uint8_t* token, uint32_t token
 int arks_host_response(arks_host_batcher* b, int32_t qos, uint32_t gen /* 0xffffffff: the current generation */, const uint8_t* body,
                        uint32_t body_len, uint8_t flags, arks_host::ResponseDecision* out);
 int arks_host_load_tables(arks_host_batcher* b, const arks_tables* t);
+int arks_host_apply_config(arks_host_batcher* b); /* publishes arks_upsert_* / arks_delete_* done on the context */
 // names for the reply shapes of arks_host_stream_transcript / arks_host_error_reply (format: ParseNameTables)
 int arks_host_set_names(arks_host_batcher* b, const char* text, uint32_t len);
 // the reference-exact reply of a failed request / response decision as "status\nheader\nheader value\nmessage"

@@ -211,8 +211,52 @@ const char* arks_last_error(const arks_ctx* ctx);
  * A load between batches swaps the whole snapshot; counters are carried over by key
  * ((namespace,user,model) and (namespace,quotaName)), like Redis keys survive a CRD edit. */
 int arks_load_tables(arks_ctx* ctx, const arks_tables* t);
-/* bumped by every arks_load_tables that succeeds: the generation the qos / token indices of request results refer to */
+/* bumped by every table swap that succeeds: the generation the qos / token indices of request results refer to */
 uint32_t arks_table_generation(const arks_ctx* ctx);
+
+/* ---- the same swap without stalling the data path ---------------------------------------------------------------------
+ * arks_load_tables = prepare + commit + a wait, for cold start. A running gateway splits it:
+ *   arks_prepare_tables  (CONFIG thread, any time)  validates, builds the device image of the next generation in fresh
+ *                        allocations and uploads it on the library's config stream. Batches keep running; nothing they use
+ *                        is touched. Errors leave the context exactly as it was.
+ *   arks_commit_tables   (the thread that submits batches, between two submissions)  queues, on the compute stream, the
+ *                        kernels that carry every counter into the new arrays BY KEY on the device, swaps the pointers and
+ *                        retires the old image stream-ordered. No host wait, no copy through the host: the batch queued
+ *                        before runs on the old generation, the one queued after on the new. Fails (ARKS_E_INVALID_ARG) if
+ *                        another generation was committed since the prepare; discard and prepare again.
+ * This is the informer's OnAdd/OnUpdate/OnDelete (arks_impl.go:104-189) arriving while requests are in flight. */
+typedef struct arks_prepared arks_prepared;
+int arks_prepare_tables(arks_ctx* ctx, const arks_tables* t, arks_prepared** out);
+int arks_commit_tables(arks_ctx* ctx, arks_prepared* p);   /* consumes p on success */
+void arks_discard_prepared(arks_ctx* ctx, arks_prepared* p);
+
+/* ---- object-level config plane: one call per informer event ------------------------------------------------------------
+ * The library keeps the objects (keyed by namespace/name, like the informer cache); each call is O(that object).
+ * arks_config_prepare flattens the store into the next generation (arks_prepare_tables underneath; same commit).
+ * Where several ArksToken objects carry the same spec.token the first in (namespace, name) order wins (the reference
+ * takes Items[0] of an unordered index, arks_impl.go:317). Strings are (pointer, length), not NUL-terminated. */
+typedef struct arks_qos_spec {            /* one spec.qos[] entry, api/v1/arkstoken_types.go:46-52 */
+  const char* model;     uint32_t model_len;  /* arksEndpoint.name                                */
+  const char* quota;     uint32_t quota_len;  /* quota.name; length 0 = no quota                  */
+  uint32_t n_rl;                              /* rateLimits, in spec order                        */
+  const uint8_t* rl_rule;                     /* enum arks_rule                                   */
+  const int64_t* rl_value;
+} arks_qos_spec;
+int arks_upsert_token(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len, const char* token,
+                      uint32_t token_len, const arks_qos_spec* qos, uint32_t n_qos);
+int arks_delete_token(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len);
+int arks_upsert_quota(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len, const uint8_t* item_type,
+                      const int64_t* item_value, uint32_t n_items);
+int arks_delete_quota(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len);
+int arks_upsert_endpoint(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len,
+                         const int32_t* backend_weight, uint32_t n_backends);
+int arks_delete_endpoint(arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len);
+/* delete of an object that is not there: ARKS_E_INVALID_ARG. Nothing reaches the device before: */
+int arks_config_prepare(arks_ctx* ctx, arks_prepared** out);
+/* index lookups in the CURRENT generation (results carry indices): -1 when absent */
+int32_t arks_find_quota(const arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len);
+int32_t arks_find_qos(const arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* user, uint32_t user_len, const char* model,
+                      uint32_t model_len);
 /* ---- BPE token counting (north star). The reference has NO tokenizer: it reads `usage` from the upstream's response
  * (pkg/gateway/handle_response.go:90-93,117-123) and counts 0 tokens at request time (check.go:124-126). The count is
  * therefore a side output with its own oracle (HF `tokenizers`); decisions never depend on it.

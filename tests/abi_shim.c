@@ -39,6 +39,25 @@ int arks_load_tables(arks_ctx* c, const arks_tables* t) {
   if (!rc) c->generation++;
   return rc;
 }
+/* prepare/commit: the shim has no device image to build ahead; the tables pointer must stay valid until the commit (the
+ * host library calls both inside one LoadTables) */
+struct arks_prepared { const arks_tables* t; uint32_t base; };
+int arks_prepare_tables(arks_ctx* c, const arks_tables* t, arks_prepared** out) {
+  arks_prepared* p = (arks_prepared*)malloc(sizeof *p);
+  p->t = t;
+  p->base = c->generation;
+  *out = p;
+  return 0;
+}
+int arks_commit_tables(arks_ctx* c, arks_prepared* p) {
+  if (p->base != c->generation) return ARKS_E_INVALID_ARG;
+  int rc = arks_load_tables(c, p->t);
+  if (!rc) free(p);
+  return rc;
+}
+void arks_discard_prepared(arks_ctx* c, arks_prepared* p) { (void)c; free(p); }
+/* the object store lives in the product library only (its host half is tested through tests/host_machine.cpp) */
+int arks_config_prepare(arks_ctx* c, arks_prepared** out) { (void)c; (void)out; return ARKS_E_INVALID_ARG; }
 void* arks_shim_oracle(arks_ctx* c) { return c->o; } /* for snapshots in tests */
 void arks_shim_destroy(arks_ctx* c) {
   if (!c) return;

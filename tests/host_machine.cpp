@@ -265,3 +265,37 @@ int hm_warp_response(const uint8_t* body, size_t len, uint32_t* span, int64_t* u
   return 1;
 }
 }
+
+// ---- the object store of the config plane (arks_b200/csrc/config_store.h is host-only C++): same calls as the ABI's
+// arks_upsert_* / arks_delete_*, flatten() exposed as an arks_tables view for the oracle ----
+#include "../arks_b200/csrc/config_store.h"
+struct HmStore {
+  arks::ConfigStore st;
+  arks::FlatTables flat;
+  arks_tables view;
+};
+extern "C" {
+void* hm_store_new() { return new HmStore(); }
+void hm_store_free(void* s) { delete static_cast<HmStore*>(s); }
+void hm_store_upsert_token(void* s, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len, const char* token, uint32_t token_len,
+                           const arks_qos_spec* qos, uint32_t n_qos) {
+  static_cast<HmStore*>(s)->st.upsert_token(ns, ns_len, name, name_len, token, token_len, qos, n_qos);
+}
+void hm_store_upsert_quota(void* s, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len, const uint8_t* type,
+                           const int64_t* value, uint32_t n) {
+  static_cast<HmStore*>(s)->st.upsert_quota(ns, ns_len, name, name_len, type, value, n);
+}
+void hm_store_upsert_endpoint(void* s, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len, const int32_t* w, uint32_t n) {
+  static_cast<HmStore*>(s)->st.upsert_endpoint(ns, ns_len, name, name_len, w, n);
+}
+int hm_store_erase(void* s, int which, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len) {
+  return static_cast<HmStore*>(s)->st.erase(which, ns, ns_len, name, name_len) ? 1 : 0;
+}
+const arks_tables* hm_store_flatten(void* s) {
+  HmStore* h = static_cast<HmStore*>(s);
+  h->flat = arks::FlatTables();
+  h->st.flatten(&h->flat);
+  h->view = h->flat.view();
+  return &h->view;
+}
+}

@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "host_machine.cpp")
-HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_common.cuh", "json_engine.cuh", "json_tables.h", "mask_scan.cuh", "warp_scan.cuh", "bpe.cuh")]
+HDRS = [os.path.join(ROOT, "arks_b200", "csrc", f) for f in ("json_common.cuh", "json_engine.cuh", "json_tables.h", "mask_scan.cuh", "warp_scan.cuh", "bpe.cuh", "config_store.h")] + [os.path.join(ROOT, "include", "arks_gateway.h")]
 OUT = os.path.join(ROOT, "tests", "_build", "libhost_machine.so")
 _lib = None
 
@@ -38,6 +38,15 @@ def lib():
         L.hm_bpe_count.restype = C.c_uint32
         L.hm_bpe_pretokenize.argtypes = [C.c_char_p, C.c_size_t, u32p, C.c_int]
         L.hm_work_profile.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t]
+        vp, cp, u32 = C.c_void_p, C.c_char_p, C.c_uint32
+        L.hm_store_new.restype = vp
+        L.hm_store_free.argtypes = [vp]
+        L.hm_store_upsert_token.argtypes = [vp, cp, u32, cp, u32, cp, u32, vp, u32]
+        L.hm_store_upsert_quota.argtypes = [vp, cp, u32, cp, u32, C.POINTER(C.c_uint8), i64p, u32]
+        L.hm_store_upsert_endpoint.argtypes = [vp, cp, u32, cp, u32, C.POINTER(C.c_int32), u32]
+        L.hm_store_erase.argtypes = [vp, C.c_int, cp, u32, cp, u32]
+        L.hm_store_flatten.argtypes = [vp]
+        L.hm_store_flatten.restype = vp
         _lib = L
     return _lib
 
@@ -143,3 +152,63 @@ def warp_request(body: bytes):
 
 def warp_response(body: bytes):
     return _resp(lib().hm_warp_response, body)
+
+
+class ConfigStore:
+    """arks::ConfigStore (csrc/config_store.h) driven with CRD-shaped dicts; flatten() -> an object with c_struct() the oracle takes"""
+
+    def __init__(self):
+        self.h = lib().hm_store_new()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().hm_store_free(self.h)
+            self.h = None
+
+    @staticmethod
+    def _k(obj):
+        md = obj["metadata"]
+        return md.get("namespace", "default").encode(), md["name"].encode()
+
+    def upsert(self, kind, obj):
+        from arks_b200 import abi
+        ns, nm = self._k(obj)
+        if kind == "token":
+            qos = obj["spec"].get("qos") or []
+            specs = (abi.ArksQosSpec * max(1, len(qos)))()
+            keep = []
+            for i, q in enumerate(qos):
+                m = q["arksEndpoint"]["name"].encode()
+                qn = ((q.get("quota") or {}).get("name", "") or "").encode()
+                rls = q.get("rateLimits") or []
+                rr = np.array([abi.RULES[r["type"]] for r in rls], np.uint8)
+                rv = np.array([int(r["value"]) for r in rls], np.int64)
+                keep += [m, qn, rr, rv]
+                specs[i] = abi.ArksQosSpec(m, len(m), qn, len(qn), len(rls), abi.ptr(rr, abi.u8p), abi.ptr(rv, abi.i64p))
+            tk = obj["spec"]["token"].encode()
+            lib().hm_store_upsert_token(self.h, ns, len(ns), nm, len(nm), tk, len(tk), C.cast(specs, C.c_void_p), len(qos))
+        elif kind == "quota":
+            items = obj["spec"]["quotas"]
+            t = np.array([abi.QUOTA_TYPES[i["type"]] for i in items], np.uint8)
+            v = np.array([int(i["value"]) for i in items], np.int64)
+            lib().hm_store_upsert_quota(self.h, ns, len(ns), nm, len(nm), abi.ptr(t, abi.u8p), abi.ptr(v, abi.i64p), len(items))
+        else:
+            w = np.array(obj["weights"], np.int32)
+            lib().hm_store_upsert_endpoint(self.h, ns, len(ns), nm, len(nm), abi.ptr(w, abi.i32p), len(w))
+
+    def erase(self, kind, obj) -> bool:
+        ns, nm = self._k(obj)
+        return bool(lib().hm_store_erase(self.h, {"token": 0, "quota": 1, "endpoint": 2}[kind], ns, len(ns), nm, len(nm)))
+
+    def flatten(self):
+        from arks_b200 import abi
+        p = lib().hm_store_flatten(self.h)
+        ts = C.cast(p, C.POINTER(abi.ArksTables)).contents
+        store = self
+
+        class View:
+            _keep = store
+
+            def c_struct(self):
+                return ts
+        return View()
