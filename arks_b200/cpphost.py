@@ -30,7 +30,9 @@ class ResponseDecision(C.Structure):
 
 class BatcherStats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("cycles", "request_batches", "response_batches", "requests", "responses",
-                                          "max_request_batch", "max_response_batch", "ns_submit", "ns_device", "ns_deliver")]
+                                          "max_request_batch", "max_response_batch", "ns_submit", "ns_device", "ns_deliver",
+                                          "max_ns_submit", "max_ns_device", "max_ns_deliver", "max_ns_gap",
+                                          "slow_submit", "slow_device", "slow_deliver", "slow_gap")]
 
 
 REQ_DTYPE = np.dtype(RequestDecision)
@@ -67,6 +69,9 @@ def load(path: str = LIB):
     L.arks_host_response.argtypes = [vp, C.c_int32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint8, C.POINTER(ResponseDecision)]
     L.arks_host_load_tables.argtypes = [vp, vp]
     L.arks_host_apply_config.argtypes = [vp]
+    L.arks_host_reset_tail.argtypes = [vp]
+    L.arks_host_reset_tail.restype = None
+    L.arks_host_open_loop_lateness.restype = None
     L.arks_host_set_names.argtypes = [vp, C.c_char_p, C.c_uint32]
     L.arks_host_request_error_reply.argtypes = [vp, C.POINTER(RequestDecision), C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32,
                                                 C.c_char_p, C.c_uint32]
@@ -157,6 +162,15 @@ class Batcher:
     def response_error_reply(self, d: ResponseDecision, qos: int, chunk: bytes):
         buf = C.create_string_buffer(len(chunk) + 4096)
         return self._reply(self.L.arks_host_response_error_reply(self._h, C.byref(d), qos, chunk, len(chunk), buf, len(buf)), buf)
+
+    def reset_tail(self):
+        self.L.arks_host_reset_tail(self._h)
+
+    def open_loop_lateness(self) -> dict:
+        """the load generator's own lateness in the last open_loop_requests run (ns)"""
+        a = (C.c_int64 * 3)()
+        self.L.arks_host_open_loop_lateness(a)
+        return {"producer_late_max_us": a[0] / 1e3, "producer_rows_late_100us": int(a[1]), "submit_call_max_us": a[2] / 1e3}
 
     def stats(self) -> dict:
         s = BatcherStats()

@@ -30,6 +30,8 @@
 #include <string.h>
 
 #include <deque>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the entry points are looked up with dlsym at arks_comm_init
 #include <mutex>
 #include <map>
 #include <string>
@@ -1408,6 +1410,21 @@ __global__ void fold_quota_delta_kernel(long long* quota, long long* delta, cons
     delta[i] -= exported[i];
   }
 }
+// the same with only the shared rows on the wire: gather them into the message ...
+__global__ void gather_shared_kernel(long long* msg, const long long* exported, const uint32_t* idx, uint32_t n_shared) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_shared * 3u) msg[k] = exported[(size_t)idx[k / 3] * 3 + k % 3];
+}
+// ... and after the all-reduce: quota[shared] += reduced - exported; every row's delta gives up what was exported
+__global__ void fold_shared_kernel(long long* quota, long long* delta, const long long* msg, const long long* exported, const uint32_t* idx,
+                                   uint32_t n_shared, size_t n_all) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_all) delta[k] -= exported[k];
+  if (k < (size_t)n_shared * 3u) {
+    const size_t q = (size_t)idx[k / 3] * 3 + k % 3;
+    quota[q] += msg[k] - exported[q];
+  }
+}
 __global__ void add_quota_kernel(long long* quota, const long long* add, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) quota[i] += add[i];
@@ -1436,6 +1453,7 @@ struct arks_ctx {
   cudaStream_t h2d = nullptr;     // batch uploads (overlap the kernels of earlier batches)
   cudaStream_t cfg_stream = nullptr;  // config plane: the next generation's tables are uploaded here, off the data path
   std::mutex cfg_mu;                  // prepare (config thread) vs commit (batch thread)
+  struct NcclApi* nccl = nullptr;      // dlopen()ed libnccl + this context's communicator (arks_comm_init)
   arks::ConfigStore* store = nullptr;  // objects behind arks_upsert_* / arks_delete_*
   int32_t *d_qos_from = nullptr, *d_quota_from = nullptr;  // row maps of the current generation (kept alive for the carry kernels)
   char err[512] = {0};
@@ -1653,6 +1671,7 @@ void arks_destroy(arks_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   free_store(ctx->store);
+  arks_comm_destroy(ctx);
   if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_tables(ctx);
@@ -2903,6 +2922,128 @@ int arks_fold_quota_delta_dev(arks_ctx* ctx, const void* reduced_dev, const void
   ctx->launches += 1;
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+// ---- the fold over NCCL, inside the library ----
+struct NcclApi {
+  void* dl = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 0;
+  uint32_t* d_idx = nullptr;   // local indices of the shared quotas
+  long long* d_msg = nullptr;  // what crosses the fabric: n_shared x 3 int64
+  uint32_t n_shared = 0;
+  bool all_rows = true;
+};
+static int nccl_load(arks_ctx* ctx) {
+  if (ctx->nccl) return 0;
+  const char* name = getenv("ARKS_NCCL_LIB");
+  void* dl = dlopen(name && *name ? name : "libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!dl) return fail(ctx, ARKS_E_INVALID_ARG, "dlopen(%s): %s", name && *name ? name : "libnccl.so.2", dlerror());
+  NcclApi* a = new NcclApi();
+  a->dl = dl;
+  a->GetUniqueId = (decltype(a->GetUniqueId))dlsym(dl, "ncclGetUniqueId");
+  a->CommInitRank = (decltype(a->CommInitRank))dlsym(dl, "ncclCommInitRank");
+  a->AllReduce = (decltype(a->AllReduce))dlsym(dl, "ncclAllReduce");
+  a->CommDestroy = (decltype(a->CommDestroy))dlsym(dl, "ncclCommDestroy");
+  a->GetErrorString = (decltype(a->GetErrorString))dlsym(dl, "ncclGetErrorString");
+  if (!a->GetUniqueId || !a->CommInitRank || !a->AllReduce || !a->CommDestroy || !a->GetErrorString) {
+    delete a;
+    return fail(ctx, ARKS_E_INVALID_ARG, "libnccl lacks an entry point this library needs");
+  }
+  ctx->nccl = a;
+  return 0;
+}
+#define NCK(call)                                                                                                \
+  do {                                                                                                           \
+    ncclResult_t r_ = (call);                                                                                    \
+    if (r_ != ncclSuccess) return fail(ctx, ARKS_E_CUDA, "%s: %s", #call, ctx->nccl->GetErrorString(r_));        \
+  } while (0)
+int arks_comm_unique_id(arks_ctx* ctx, void* out) {
+  if (!ctx || !out) return ARKS_E_INVALID_ARG;
+  static_assert(sizeof(ncclUniqueId) == ARKS_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+  int rc = nccl_load(ctx);
+  if (rc) return rc;
+  ncclUniqueId id;
+  NCK(ctx->nccl->GetUniqueId(&id));
+  memcpy(out, &id, sizeof id);
+  return 0;
+}
+int arks_comm_set_shared(arks_ctx* ctx, const uint32_t* shared, uint32_t n_shared) {
+  if (!ctx || !ctx->nccl) return fail(ctx, ARKS_E_INVALID_ARG, "arks_comm_init first");
+  if (!ctx->loaded || !ctx->d_qdelta) return fail(ctx, ARKS_E_INVALID_ARG, "quota sharing is not enabled (or no tables yet)");
+  CK(cudaSetDevice(ctx->device));
+  NcclApi& a = *ctx->nccl;
+  std::vector<uint32_t> idx;
+  a.all_rows = !shared;
+  if (shared) idx.assign(shared, shared + n_shared);
+  else {
+    idx.resize(ctx->ht.n_quotas);
+    for (uint32_t q = 0; q < ctx->ht.n_quotas; q++) idx[q] = q;
+  }
+  for (uint32_t q : idx)
+    if (q >= ctx->ht.n_quotas) return fail(ctx, ARKS_E_INVALID_ARG, "shared quota index %u out of range", q);
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(a.d_idx);
+  cudaFree(a.d_msg);
+  a.d_idx = nullptr; a.d_msg = nullptr;
+  a.n_shared = (uint32_t)idx.size();
+  CK(cudaMalloc(&a.d_idx, idx.size() * 4 + 64));
+  CK(cudaMalloc(&a.d_msg, idx.size() * 24 + 64));
+  CK(cudaMemcpy(a.d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+int arks_comm_init(arks_ctx* ctx, int rank, int world, const void* unique_id, const uint32_t* shared, uint32_t n_shared) {
+  if (!ctx || !unique_id || world < 1 || rank < 0 || rank >= world) return ARKS_E_INVALID_ARG;
+  int rc = nccl_load(ctx);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  NcclApi& a = *ctx->nccl;
+  if (a.comm) { a.CommDestroy(a.comm); a.comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof id);
+  NCK(a.CommInitRank(&a.comm, world, id, rank));
+  a.rank = rank; a.world = world;
+  return arks_comm_set_shared(ctx, shared, n_shared);
+}
+int arks_fold_quota_allreduce(arks_ctx* ctx, int wait) {
+  if (!ctx || !ctx->nccl || !ctx->nccl->comm) return fail(ctx, ARKS_E_INVALID_ARG, "arks_comm_init first");
+  if (!ctx->loaded || !ctx->d_qdelta) return fail(ctx, ARKS_E_INVALID_ARG, "quota sharing is not enabled");
+  NcclApi& a = *ctx->nccl;
+  if (a.all_rows && a.n_shared != ctx->ht.n_quotas) return fail(ctx, ARKS_E_INVALID_ARG, "the tables changed: arks_comm_set_shared again");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n_all = (size_t)3 * ctx->ht.n_quotas;
+  if (!n_all) return 0;
+  // everything below is ordered on the compute stream, between two batches
+  CK(cudaMemcpyAsync(ctx->d_qexp, ctx->d_qdelta, n_all * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (a.n_shared) {
+    gather_shared_kernel<<<(a.n_shared * 3 + 255) / 256, 256, 0, ctx->stream>>>(a.d_msg, ctx->d_qexp, a.d_idx, a.n_shared);
+    NCK(a.AllReduce(a.d_msg, a.d_msg, (size_t)a.n_shared * 3, ncclInt64, ncclSum, a.comm, ctx->stream));
+  }
+  const size_t span = n_all > (size_t)a.n_shared * 3 ? n_all : (size_t)a.n_shared * 3;
+  fold_shared_kernel<<<(unsigned)((span + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_quota, ctx->d_qdelta, a.d_msg, ctx->d_qexp, a.d_idx,
+                                                                              a.n_shared, n_all);
+  ctx->launches += a.n_shared ? 2 : 1;
+  ctx->qexp_valid = false;
+  CK(cudaGetLastError());
+  if (wait) CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+void arks_comm_destroy(arks_ctx* ctx) {
+  if (!ctx || !ctx->nccl) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  NcclApi* a = ctx->nccl;
+  if (a->comm) a->CommDestroy(a->comm);
+  cudaFree(a->d_idx);
+  cudaFree(a->d_msg);
+  // the shared object stays loaded: other contexts (and torch) may be using it
+  delete a;
+  ctx->nccl = nullptr;
 }
 
 }  // extern "C"

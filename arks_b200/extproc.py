@@ -9,8 +9,10 @@ CPU boxes because the product has no CPU path).
 
 No protoc / grpc_tools in this image: the handful of envoy.service.ext_proc.v3 / envoy.config.core.v3 messages used
 on this path are declared programmatically below with the upstream field numbers (envoy API v3 as vendored by
-go-control-plane v1.32.4; written from the published .proto layout — re-check against the .proto files before
-pointing a real Envoy at it).
+go-control-plane v1.32.4). tools/verify_descriptors.py checks the envoy.config.core.v3 / envoy.type.v3 ones against the
+descriptors grpcio's C core embeds (tests/test_descriptors.py); the ext_proc service messages are in no package of this
+image and stay hand-typed from the published .proto layout — re-check those before pointing a real Envoy at it.
+Enum-typed upstream fields (HttpStatus.code, CommonResponse.status) are declared int32 here: same wire encoding.
 """
 from __future__ import annotations
 
@@ -84,6 +86,113 @@ def _build_messages():
 
 PB = _build_messages()
 SERVICE = "envoy.service.ext_proc.v3.ExternalProcessor"
+
+
+def _build_health_messages():
+    """grpc.health.v1 (grpc/health/v1/health.proto): the four messages of Check / List / Watch"""
+    f = descriptor_pb2.FileDescriptorProto()
+    f.name, f.package, f.syntax = "arks_health_subset.proto", "grpc.health.v1", "proto3"
+    m = f.message_type.add()
+    m.name = "HealthCheckRequest"
+    fd = m.field.add()
+    fd.name, fd.number, fd.type, fd.label = "service", 1, _T.TYPE_STRING, _T.LABEL_OPTIONAL
+    m = f.message_type.add()
+    m.name = "HealthCheckResponse"
+    e = m.enum_type.add()
+    e.name = "ServingStatus"
+    for i, n in enumerate(("UNKNOWN", "SERVING", "NOT_SERVING", "SERVICE_UNKNOWN")):
+        v = e.value.add()
+        v.name, v.number = n, i
+    fd = m.field.add()
+    fd.name, fd.number, fd.type, fd.label = "status", 1, _T.TYPE_ENUM, _T.LABEL_OPTIONAL
+    fd.type_name = ".grpc.health.v1.HealthCheckResponse.ServingStatus"
+    f.message_type.add().name = "HealthListRequest"
+    m = f.message_type.add()
+    m.name = "HealthListResponse"
+    ent = m.nested_type.add()  # map<string, HealthCheckResponse> statuses = 1
+    ent.name = "StatusesEntry"
+    ent.options.map_entry = True
+    k = ent.field.add()
+    k.name, k.number, k.type, k.label = "key", 1, _T.TYPE_STRING, _T.LABEL_OPTIONAL
+    v = ent.field.add()
+    v.name, v.number, v.type, v.label, v.type_name = "value", 2, _T.TYPE_MESSAGE, _T.LABEL_OPTIONAL, ".grpc.health.v1.HealthCheckResponse"
+    fd = m.field.add()
+    fd.name, fd.number, fd.type, fd.label = "statuses", 1, _T.TYPE_MESSAGE, _T.LABEL_REPEATED
+    fd.type_name = ".grpc.health.v1.HealthListResponse.StatusesEntry"
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(f)
+    return {n: message_factory.GetMessageClass(pool.FindMessageTypeByName("grpc.health.v1." + n))
+            for n in ("HealthCheckRequest", "HealthCheckResponse", "HealthListRequest", "HealthListResponse")}
+
+
+HEALTH_PB = _build_health_messages()
+HEALTH_SERVICE = "grpc.health.v1.Health"
+SERVING = 1
+
+
+class HealthServer:
+    """HealthServer of the reference (pkg/gateway/gateway.go:261-279): always SERVING, empty List, Watch unimplemented"""
+
+    def Check(self, request, context):
+        return HEALTH_PB["HealthCheckResponse"](status=SERVING)
+
+    def List(self, request, context):
+        return HEALTH_PB["HealthListResponse"]()
+
+    def Watch(self, request, context):
+        import grpc
+        context.abort(grpc.StatusCode.UNIMPLEMENTED, "watch is not implemented")
+
+
+# ---- GET /v1/models (pkg/gateway/http_handler.go:18-60; the plain HTTP listener of gateway.go:140-157) ----------------
+def models_reply(tables, authorization):
+    """-> (status, content type, body) of handleGetModels. GetModelsByToken (qosconfig/arks_impl.go:378-397): the qos
+    entries' endpoint names of the FIRST ArksToken object with that spec.token; an unknown token is a 500, like there.
+    Model objects are openai-go v0.1.0-beta.3's `Model` marshalled by encoding/json (a go.mod dependency that is not
+    vendored: its published struct has id, created, object, owned_by, all emitted); no models -> "data":null (nil slice)."""
+    text = "text/plain; charset=utf-8"
+    if authorization is None or not authorization.startswith("Bearer "):
+        return 401, text, b"Unauthorized\n"
+    token = authorization[len("Bearer "):]
+    if token == "":
+        return 401, text, b"Unauthorized\n"
+    try:
+        t = tables.token_string.index(token)
+    except ValueError:
+        return 500, text, b"error in getting model list\n"
+    lo, hi = int(tables.tok_qos_off[t]), int(tables.tok_qos_off[t + 1])
+    data = [{"id": tables.qos_model_name[q], "created": 0, "object": "model", "owned_by": ""} for q in range(lo, hi)] or None
+    return 200, "application/json", json.dumps({"object": "list", "data": data}, separators=(",", ":"), ensure_ascii=False).encode()
+
+
+def serve_http(get_tables, port: int = 8080):
+    """the /v1/models listener; get_tables() returns the current arks_b200.tables.Tables (it changes with the config plane)"""
+    from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+
+    class H(BaseHTTPRequestHandler):
+        def _any(self):
+            if self.path.split("?", 1)[0] != "/v1/models":  # http.ServeMux: 404 page not found
+                st, ct, body = 404, "text/plain; charset=utf-8", b"404 page not found\n"
+            else:
+                st, ct, body = models_reply(get_tables(), self.headers.get("Authorization"))
+            self.send_response(st)
+            self.send_header("Content-Type", ct)
+            if st != 200:
+                self.send_header("X-Content-Type-Options", "nosniff")  # http.Error
+            self.send_header("Content-Length", str(len(body)))
+            self.end_headers()
+            if self.command != "HEAD":
+                self.wfile.write(body)
+
+        do_GET = do_POST = do_HEAD = do_PUT = do_DELETE = _any  # the mux pattern has no method: every verb is served
+
+        def log_message(self, *a):
+            pass
+
+    httpd = ThreadingHTTPServer(("127.0.0.1", port), H)
+    th = threading.Thread(target=httpd.serve_forever, daemon=True)
+    th.start()
+    return httpd, httpd.server_address[1]
 
 # header names, pkg/gateway/types.go:24-56
 H_WENT_REQ, H_WENT_RESP = "x-went-into-req-headers", "x-went-into-resp-headers"
@@ -363,8 +472,17 @@ def serve(server: ExtProcServer, port: int = 50052, max_workers: int = 64):
         "Process": grpc.stream_stream_rpc_method_handler(
             server.Process, request_deserializer=PB["ProcessingRequest"].FromString,
             response_serializer=PB["ProcessingResponse"].SerializeToString)})
+    hs = HealthServer()  # healthPb.RegisterHealthServer, gateway.go:179
+    HP = HEALTH_PB
+    health = grpc.method_handlers_generic_handler(HEALTH_SERVICE, {
+        "Check": grpc.unary_unary_rpc_method_handler(hs.Check, request_deserializer=HP["HealthCheckRequest"].FromString,
+                                                     response_serializer=HP["HealthCheckResponse"].SerializeToString),
+        "List": grpc.unary_unary_rpc_method_handler(hs.List, request_deserializer=HP["HealthListRequest"].FromString,
+                                                    response_serializer=HP["HealthListResponse"].SerializeToString),
+        "Watch": grpc.unary_stream_rpc_method_handler(hs.Watch, request_deserializer=HP["HealthCheckRequest"].FromString,
+                                                      response_serializer=HP["HealthCheckResponse"].SerializeToString)})
     s = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers))
-    s.add_generic_rpc_handlers((handler,))
+    s.add_generic_rpc_handlers((handler, health))
     bound = s.add_insecure_port(f"127.0.0.1:{port}")
     s.start()
     return s, bound

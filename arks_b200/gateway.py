@@ -99,6 +99,12 @@ def lib():
         L.arks_apply_quota_delta.argtypes = [vp, abi.i64p]
         L.arks_export_quota_delta_dev.argtypes = [vp, vp]
         L.arks_fold_quota_delta_dev.argtypes = [vp, vp, vp]
+        L.arks_comm_unique_id.argtypes = [vp, vp]
+        L.arks_comm_init.argtypes = [vp, C.c_int, C.c_int, vp, abi.u32p, C.c_uint32]
+        L.arks_comm_set_shared.argtypes = [vp, abi.u32p, C.c_uint32]
+        L.arks_fold_quota_allreduce.argtypes = [vp, C.c_int]
+        L.arks_comm_destroy.argtypes = [vp]
+        L.arks_comm_destroy.restype = None
         L.arks_extract_bearer.restype = C.c_size_t
         _lib = L
     return _lib
@@ -115,6 +121,7 @@ EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/t
     "arks_wait_response", "arks_select_slot", "arks_set_profiling", "arks_last_kernel_ms", "arks_stream", "arks_launch_count", "arks_last_declined", "arks_enable_metrics", "arks_snapshot_metrics", "arks_sync_quota_usage", "arks_alloc_pinned", "arks_free_pinned", "arks_snapshot_quota",
     "arks_set_quota_usage", "arks_incr_quota_usage", "arks_snapshot_rate", "arks_take_quota_delta",
     "arks_apply_quota_delta", "arks_quota_delta_dev", "arks_fold_quota_delta_dev", "arks_enable_quota_sharing",
+    "arks_comm_unique_id", "arks_comm_init", "arks_comm_set_shared", "arks_fold_quota_allreduce", "arks_comm_destroy",
     "arks_export_quota_delta_dev",
 ]
 
@@ -379,6 +386,23 @@ class Gateway:
     def fold_quota_delta_dev(self, reduced_ptr: int, own_ptr: int = 0):
         """quota += reduced - own, delta -= own; own defaults to the library's copy of the last export"""
         self._ck(lib().arks_fold_quota_delta_dev(self._h, C.c_void_p(reduced_ptr), C.c_void_p(own_ptr) if own_ptr else None))
+
+    # ---- the fold done by the library over NCCL (arks_comm_*): what a Go / C++ host calls; no torch on this path
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._ck(lib().arks_comm_unique_id(self._h, buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes, shared_local_idx=None):
+        idx = None if shared_local_idx is None else np.ascontiguousarray(shared_local_idx, np.uint32)
+        self._ck(lib().arks_comm_init(self._h, rank, world, unique_id, abi.ptr(idx, abi.u32p), 0 if idx is None else len(idx)))
+
+    def comm_set_shared(self, shared_local_idx=None):
+        idx = None if shared_local_idx is None else np.ascontiguousarray(shared_local_idx, np.uint32)
+        self._ck(lib().arks_comm_set_shared(self._h, abi.ptr(idx, abi.u32p), 0 if idx is None else len(idx)))
+
+    def fold_quota_allreduce(self, wait: bool = True):
+        self._ck(lib().arks_fold_quota_allreduce(self._h, int(wait)))
 
     # ---- reply shaping helpers (what the Go host puts on the wire; handle_request.go:208-247, util.go:40-77)
     def request_headers(self, r: RequestResult, i: int) -> dict:

@@ -44,20 +44,20 @@ class QuotaDeltaExchange:
     def __init__(self, engine, n_quotas: int, shared_local_idx, device=None):
         self.engine, self.n, self.device = engine, n_quotas, device
         self.idx = np.ascontiguousarray(shared_local_idx, np.int64)
+        self._comm = False
 
     def fold(self):
         import torch
         import torch.distributed as dist
         if self.device is not None and dist.get_backend() == "nccl":
-            own = torch.zeros((self.n, 3), dtype=torch.int64, device=self.device)
-            self.engine.export_quota_delta_dev(own.data_ptr())      # D2D: this GPU's unfolded increments
-            idx = torch.from_numpy(self.idx).to(self.device)
-            shared = own.index_select(0, idx).contiguous()
-            dist.all_reduce(shared, op=dist.ReduceOp.SUM)           # NCCL over NVLink: sum over GPUs
-            reduced = own.clone()                                   # non-shared rows: reduced - own == 0
-            reduced.index_copy_(0, idx, shared)
-            torch.cuda.synchronize(self.device)
-            self.engine.fold_quota_delta_dev(reduced.data_ptr())    # quota += reduced - own; own = 0
+            # the library's own fold: gather of the shared rows, ncclAllReduce and the apply, all on its compute stream
+            # (arks_fold_quota_allreduce). torch.distributed only carries the 128-byte communicator id, once.
+            if not self._comm:
+                box = [self.engine.comm_unique_id() if dist.get_rank() == 0 else None]
+                dist.broadcast_object_list(box, src=0)
+                self.engine.comm_init(dist.get_rank(), dist.get_world_size(), box[0], self.idx)
+                self._comm = True
+            self.engine.fold_quota_allreduce(wait=True)
             return
         own = self.engine.take_quota_delta()
         t = torch.from_numpy(own[self.idx].copy())

@@ -51,6 +51,10 @@ def parse_args():
     ap.add_argument("--wave", type=int, default=WAVE)
     ap.add_argument("--tenants", type=int, default=TENANTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shared-quota", type=int, default=0, metavar="K",
+                    help="K quotas per GPU are replicas of quotas shared by all GPUs: every --fold-every steps the library folds "
+                         "their increments with ncclAllReduce (arks_fold_quota_allreduce) INSIDE the timed region")
+    ap.add_argument("--fold-every", type=int, default=8)
     ap.add_argument("--latency-requests", type=int, default=2_000_000,
                     help="requests per GPU in the 1.25 M/s open-loop latency run (10 M for the metric's full sample)")
     return ap.parse_args()
@@ -315,8 +319,15 @@ def run_b200(args):
 
     # every rank owns its own tenant shard (namespaces are the tenant boundary; no key is shared across GPUs)
     w = traffic.Workload(n_tenants=args.tenants, seed=0xA2C5 + rank)
-    g = Gateway(local, max_batch=args.wave, max_batch_bytes=int(args.wave * (BODY + 64) * 1.05))
+    g = Gateway(local, max_batch=args.wave, max_batch_bytes=int(args.wave * (BODY + 64) * 1.05), share_quota=args.shared_quota > 0)
     g.load_tables(w.tables)
+    if args.shared_quota:
+        # the communicator id travels over torch.distributed once (plumbing); the fold itself is the library's
+        box = [g.comm_unique_id() if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        n_shared = min(args.shared_quota, w.tables.n_quotas)
+        g.comm_init(rank, world, box[0], np.arange(n_shared, dtype=np.uint32))
     reqs = [pin_batch(b) for b in build_waves(w, N_WAVES, args.wave, rank)]
     # dry pass to learn which requests are admitted in a fresh window, then build the matching response waves
     resps = []
@@ -347,6 +358,8 @@ def run_b200(args):
         g.select_slot(k)
         g.run_request(now)
         g.run_response(now + 1)
+        if args.shared_quota and i % args.fold_every == args.fold_every - 1:
+            g.fold_quota_allreduce(wait=False)  # stream-ordered behind this step's kernels; nobody waits on the host
 
     for i in range(args.warmup):
         resident_step(i, now)
@@ -371,6 +384,22 @@ def run_b200(args):
     barrier()
     launches = g.launch_count - launches0
     dev_ms = e0.elapsed_time(e1)
+    shared_quota = None
+    if args.shared_quota:
+        # one fold epoch timed alone (gather + all-reduce + apply), every rank in step
+        f0 = [torch.cuda.Event(enable_timing=True) for _ in range(20)]
+        f1 = [torch.cuda.Event(enable_timing=True) for _ in range(20)]
+        barrier()
+        for a_, b_ in zip(f0, f1):
+            a_.record(ext)
+            g.fold_quota_allreduce(wait=False)
+            b_.record(ext)
+        barrier()
+        us = sorted(1e3 * a_.elapsed_time(b_) for a_, b_ in zip(f0, f1))
+        shared_quota = {"rows": int(n_shared), "message_bytes": int(n_shared) * 24, "fold_every_steps": args.fold_every,
+                        "folds_in_timed_region": args.steps // args.fold_every, "fold_us_p50": round(us[len(us) // 2], 1),
+                        "fold_us_max": round(us[-1], 1), "how": "arks_fold_quota_allreduce: ncclAllReduce(int64, sum) issued by the "
+                        "library on its compute stream (libnccl dlopen()ed), CUDA events around one epoch"}
     # per-kernel timing for the roofline (separate pass so event records do not sit inside the timed region)
     g.set_profiling(True)
     scan_ms, admit_ms, resp_ms, fast_req_ms, fast_resp_ms = [], [], [], [], []
@@ -582,6 +611,9 @@ def run_b200(args):
         "body_bytes_over_8TBps": (float(np.mean([int(b.body_len.sum()) for b in reqs])) +
                                   float(np.mean([int(b.body_len.sum()) for b in resps]))) * args.steps * world / (dev_ms / 1e3) / 8e12,
     }
+    if shared_quota:
+        out["shared_quota"] = shared_quota
+        out["config"]["parallelism"] += f" + {shared_quota['rows']} shared quotas folded every {args.fold_every} steps"
     if not args.no_cpu_baseline:
         out["cpu_baseline"], _ = cpu_arm(args, 1, seconds=12.0)
     print(json.dumps(out))

@@ -61,6 +61,10 @@ struct BatcherStats {
   // where a cycle's time goes (nanoseconds, summed over cycles): waiting for the rows' copies + staging + queueing the
   // device work; waiting for the device; handing the decisions to the rows
   uint64_t ns_submit, ns_device, ns_deliver;
+  // the tail: per phase the longest single occurrence and how many took more than 100 us; `gap` is the time between the
+  // end of one cycle and the start of the next while rows were waiting (dispatcher wake-up, lock hand-over)
+  uint64_t max_ns_submit, max_ns_device, max_ns_deliver, max_ns_gap;
+  uint64_t slow_submit, slow_device, slow_deliver, slow_gap;
 };
 
 typedef void (*RequestCallback)(void* user, const RequestDecision&);    // run on the batcher's completion thread
@@ -98,6 +102,7 @@ class Batcher {
 
   void SetClock(int64_t (*clock)(void*), void* arg);  // default: time(nullptr)
   BatcherStats Stats() const;
+  void ResetTailStats();  // the max_* / slow_* fields start over
 
  private:
   struct Impl;
@@ -177,6 +182,8 @@ int arks_host_request(arks_host_batcher* b, const uint8_t* token, uint32_t token
 int arks_host_response(arks_host_batcher* b, int32_t qos, uint32_t gen /* 0xffffffff: the current generation */, const uint8_t* body,
                        uint32_t body_len, uint8_t flags, arks_host::ResponseDecision* out);
 int arks_host_load_tables(arks_host_batcher* b, const arks_tables* t);
+void arks_host_reset_tail(arks_host_batcher* b);
+void arks_host_open_loop_lateness(int64_t out[3]);
 int arks_host_apply_config(arks_host_batcher* b); /* publishes arks_upsert_* / arks_delete_* done on the context */
 // names for the reply shapes of arks_host_stream_transcript / arks_host_error_reply (format: ParseNameTables)
 int arks_host_set_names(arks_host_batcher* b, const char* text, uint32_t len);

@@ -384,6 +384,24 @@ int arks_export_quota_delta_dev(arks_ctx* ctx, void* dst_dev);
  * delta vector for the next epoch. */
 int arks_fold_quota_delta_dev(arks_ctx* ctx, const void* reduced_dev, const void* own_dev);
 
+/* ---- the fold done BY the library over NCCL (NVLink / NVSwitch), so a Go / C++ host needs no torch -------------------
+ * One communicator per context (one context per GPU, one process per GPU or several GPUs in one process). libnccl.so.2
+ * is dlopen()ed at arks_comm_init (ARKS_NCCL_LIB overrides the name); the library does not link against it.
+ *   arks_comm_unique_id   rank 0: 128 opaque bytes (ncclGetUniqueId) to hand to every rank over any channel
+ *   arks_comm_init        every rank: ncclCommInitRank. `shared` lists, in the SAME canonical order on every rank, the LOCAL
+ *                         indices of the quotas that live on every GPU (local numbering may differ per rank); NULL / 0 =
+ *                         every quota, identical numbering everywhere. Call again after a table swap that moves them.
+ *   arks_fold_quota_allreduce   one fold epoch, stream-ordered: snapshot this GPU's unfolded increments, gather the shared
+ *                         rows, ncclAllReduce(sum, int64) in place, quota += reduced - own on the shared rows, delta -= the
+ *                         snapshot. wait != 0 also waits for it (the epoch's duration is then the call's).
+ * Replaces the Redis INCRBY every gateway replica does against the one shared store (quota/redis.go:74-100). */
+#define ARKS_UNIQUE_ID_BYTES 128
+int arks_comm_unique_id(arks_ctx* ctx, void* out /* ARKS_UNIQUE_ID_BYTES */);
+int arks_comm_init(arks_ctx* ctx, int rank, int world, const void* unique_id, const uint32_t* shared, uint32_t n_shared);
+int arks_comm_set_shared(arks_ctx* ctx, const uint32_t* shared, uint32_t n_shared);
+int arks_fold_quota_allreduce(arks_ctx* ctx, int wait);
+void arks_comm_destroy(arks_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -217,3 +217,31 @@ def test_reload_between_request_and_response_bills_the_same_key(gwmod):
     r = g.handle_response_body(ResponseBatch.from_lists(bodies[:4], [-1, 77, 2, 3], [abi.RESP_END_OF_STREAM] * 4, NOW + 3,
                                                         gen=[g.generation, g.generation, g.generation + 5, g.generation]))
     assert r.reason.tolist() == [abi.R_QOS_GONE, abi.R_QOS_GONE, abi.R_QOS_GONE, 0]
+
+
+def test_library_side_nccl_fold_single_rank_communicator(gwmod):
+    """arks_comm_* / arks_fold_quota_allreduce on a one-rank communicator (all a one-GPU lease can hold; two ranks run in
+    tests/test_multi_rank.py on >= 2 GPUs): libnccl is dlopen()ed, the shared rows go through ncclAllReduce in place, and
+    with nobody else to hear from the fold must leave every quota where the oracle has it and hand every delta back."""
+    w = traffic.Workload(2_000, seed=41)
+    g = gwmod.Gateway(0, WAVE, int(WAVE * 1200), share_quota=True)
+    g.load_tables(w.tables)
+    o = orklib.Oracle(w.tables)
+    shared = np.arange(0, w.tables.n_quotas, 7, dtype=np.uint32)  # a subset, like the replicated hot tenants
+    g.comm_init(0, 1, g.comm_unique_id(), shared)
+    for epoch in range(3):
+        req = w.request_batch(16384, NOW + epoch, seed=50 + epoch)
+        a = g.handle_request_body(req)
+        same(a, o.request_batch(req), f"epoch {epoch} requests")
+        resp = w.response_batch(a, NOW + epoch, seed=60 + epoch)
+        same(g.handle_response_body(resp), o.response_batch(resp), f"epoch {epoch} responses")
+        before = g.snapshot_quota()
+        g.fold_quota_allreduce(wait=(epoch != 1))  # epoch 1: stream-ordered only, the next call is behind it
+        assert np.array_equal(g.snapshot_quota(), before)
+        state_same(g, o, NOW + epoch)
+        assert not g.take_quota_delta().any()  # every increment was exported and given up
+    g.comm_set_shared(None)  # every quota, identical numbering: the other calling convention
+    g.fold_quota_allreduce()
+    state_same(g, o, NOW + 2)
+    with pytest.raises(Exception):
+        g.comm_set_shared(np.array([w.tables.n_quotas], np.uint32))  # out of range

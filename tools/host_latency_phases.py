@@ -21,13 +21,15 @@ for rate in (100_000, 500_000, 1_250_000, 2_500_000):
     now += 86400; hb.set_fixed_clock(now)
     n = int(rate * 0.2)
     load = w.request_batch(n, now, seed=4, body_size=1024, n_templates=512, varied=True)
-    b0 = hb.stats(); _, lat, wall = hb.open_loop_requests(load, rate, producers=8); b1 = hb.stats()
+    hb.reset_tail(); b0 = hb.stats(); _, lat, wall = hb.open_loop_requests(load, rate, producers=8); b1 = hb.stats()
     l = np.sort(lat[n // 10:]) / 1e3
     cyc = max(b1["cycles"] - b0["cycles"], 1)
     out[str(rate)] = {"p50": round(float(l[len(l) // 2])), "p99": round(float(l[int(len(l) * .99)])), "p999": round(float(l[int(len(l) * .999)])),
                       "req_s": round(n / wall), "mean_batch": round(n / cyc, 1),
                       "us_submit": round((b1["ns_submit"] - b0["ns_submit"]) / cyc / 1e3, 1),
                       "us_device": round((b1["ns_device"] - b0["ns_device"]) / cyc / 1e3, 1),
-                      "us_deliver": round((b1["ns_deliver"] - b0["ns_deliver"]) / cyc / 1e3, 1)}
+                      "us_deliver": round((b1["ns_deliver"] - b0["ns_deliver"]) / cyc / 1e3, 1),
+                      "tail": {k: (round(v / 1e3) if k.startswith("max") else v) for k, v in b1.items() if k.startswith(("max_ns", "slow_"))},
+                      "harness": hb.open_loop_lateness()}
 print(json.dumps(out), flush=True)
 hb.close()
