@@ -72,6 +72,8 @@ def load(path: str = LIB):
     L.arks_host_reset_tail.argtypes = [vp]
     L.arks_host_reset_tail.restype = None
     L.arks_host_open_loop_lateness.restype = None
+    L.arks_host_open_loop_call_latency.restype = None
+    L.arks_host_open_loop_call_latency.argtypes = [vp]
     L.arks_host_set_names.argtypes = [vp, C.c_char_p, C.c_uint32]
     L.arks_host_request_error_reply.argtypes = [vp, C.POINTER(RequestDecision), C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32,
                                                 C.c_char_p, C.c_uint32]
@@ -192,6 +194,10 @@ class Batcher:
         earlier ones are answered; latency = decision handed over - scheduled arrival (no coordinated omission)."""
         out = np.zeros(batch.n, REQ_DTYPE)
         lat = np.zeros(batch.n, np.int64)
+        # second clock: decision - the moment the generator made the call (a generator thread that the OS kept off its
+        # core for milliseconds is late on its own; `lat` still charges that to the request, this array does not)
+        self.last_call_latency = np.zeros(batch.n, np.int64)
+        self.L.arks_host_open_loop_call_latency(_ptr(self.last_call_latency))
         bodies = np.ascontiguousarray(batch.bodies)
         ns = self.L.arks_host_open_loop_requests(self._h, batch.n, float(rate_per_s), producers, _ptr(bodies), _ptr(batch.body_off),
                                                  _ptr(batch.body_len), _ptr(batch.tokens), _ptr(batch.token_off),

@@ -1674,13 +1674,7 @@ void arks_destroy(arks_ctx* ctx) {
   arks_comm_destroy(ctx);
   if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  free_tables(ctx);
-  cudaFree(ctx->d_rate);
-  cudaFree(ctx->d_metrics);
-  cudaFree(ctx->d_quota);
-  cudaFree(ctx->d_qdelta);
-  cudaFree(ctx->d_qtmp);
-  cudaFree(ctx->d_qexp);
+  free_tables(ctx);  // one arena per generation: tables, counters and row maps are interior pointers
   for (auto& sl : ctx->slots) {
     cudaFree(sl.d_req_bodies);
     cudaFree(sl.d_req_meta);
@@ -1717,8 +1711,6 @@ void arks_destroy(arks_ctx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
   if (ctx->cfg_stream) cudaStreamDestroy(ctx->cfg_stream);
-  cudaFree(ctx->d_qos_from);
-  cudaFree(ctx->d_quota_from);
   delete ctx;
 }
 
@@ -1866,8 +1858,6 @@ static void free_prepared(arks_ctx* ctx, arks_prepared* p) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->cfg_stream);
   for (void* q : p->allocs) cudaFree(q);
-  cudaFree(p->rate); cudaFree(p->quota); cudaFree(p->metrics); cudaFree(p->qdelta); cudaFree(p->qtmp); cudaFree(p->qexp);
-  cudaFree(p->d_qos_from); cudaFree(p->d_quota_from);
   delete p;
 }
 void arks_discard_prepared(arks_ctx* ctx, arks_prepared* p) {
@@ -1969,33 +1959,22 @@ int arks_prepare_tables(arks_ctx* ctx, const arks_tables* t, arks_prepared** out
 
   // Build the new generation completely before touching the old one, on the config stream: a failed allocation or upload
   // leaves the context serving the previous tables and counters, and the data path never waits for any of this.
+  // ONE allocation, ONE upload and ONE memset per generation (a config thread that makes dozens of driver calls competes
+  // with the batch thread for the context lock): arrays are first only laid out, 256-byte aligned, uploads in front and the
+  // zero-initialised counters behind them.
+  struct Piece { const void* src; size_t bytes, span; void** out; size_t off; };
+  std::vector<Piece> pieces;
   std::vector<void*> fresh;
   auto drop_fresh = [&]() {
     cudaStreamSynchronize(ctx->cfg_stream);
     for (void* p : fresh) cudaFree(p);
   };
   auto put = [&](const void* src, size_t bytes, void** out, size_t alloc_bytes = 0) -> int {
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, (alloc_bytes > bytes ? alloc_bytes : bytes) + 64);
-    if (e == cudaSuccess) {
-      fresh.push_back(p);
-      if (bytes && src) e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->cfg_stream);
-      else if (!src) e = cudaMemsetAsync(p, 0, (alloc_bytes > bytes ? alloc_bytes : bytes) + 64, ctx->cfg_stream);
-    }
-    if (e != cudaSuccess) {
-      drop_fresh();
-      return fail(ctx, ARKS_E_CUDA, "arks_load_tables: %s (tables unchanged)", cudaGetErrorString(e));
-    }
-    *out = p;
+    const size_t span = ((alloc_bytes > bytes ? alloc_bytes : bytes) + 64 + 255) & ~(size_t)255;
+    pieces.push_back(Piece{src, src ? bytes : 0, span, out, 0});
     return 0;
   };
-#define PUT(vec, field)                                                                                          \
-  do {                                                                                                           \
-    void* p_ = nullptr;                                                                                          \
-    int rc_ = put((vec).data(), (vec).size() * sizeof((vec)[0]), &p_);                                           \
-    if (rc_) return rc_;                                                                                         \
-    d.field = reinterpret_cast<decltype(d.field)>(p_);                                                           \
-  } while (0)
+#define PUT(vec, field) put((vec).data(), (vec).size() * sizeof((vec)[0]), (void**)&d.field)
   DevTables d{};
   std::vector<uint32_t> v_tok_qos_off(t->tok_qos_off, t->tok_qos_off + t->n_tokens + 1);
   std::vector<int32_t> v_qos_quota(t->qos_quota, t->qos_quota + t->n_qos);
@@ -2025,7 +2004,6 @@ int arks_prepare_tables(arks_ctx* ctx, const arks_tables* t, arks_prepared** out
   PUT(v_qi_val, qitem_value);
   PUT(v_ep_off, ep_backend_off);
   PUT(v_bw, backend_weight);
-  const size_t n_table_allocs = fresh.size();
   long long *n_rate = nullptr, *n_quota = nullptr, *n_metrics = nullptr, *n_qdelta = nullptr, *n_qtmp = nullptr, *n_qexp = nullptr;
   int32_t *n_qos_from = nullptr, *n_quota_from = nullptr;
   {
@@ -2044,14 +2022,31 @@ int arks_prepare_tables(arks_ctx* ctx, const arks_tables* t, arks_prepared** out
   }
 #undef PUT
   {
-    cudaError_t e = cudaStreamSynchronize(ctx->cfg_stream);  // the CONFIG stream: the data path is not involved
+    size_t up = 0, total = 0;
+    for (Piece& pc : pieces)
+      if (pc.src) { pc.off = up; up += pc.span; }
+    total = up;
+    for (Piece& pc : pieces)
+      if (!pc.src) { pc.off = total; total += pc.span; }
+    uint8_t* arena = nullptr;
+    cudaError_t e = cudaMalloc(&arena, total + 256);
+    if (e == cudaSuccess) {
+      fresh.push_back(arena);
+      std::vector<uint8_t> stage(up + 1, 0);
+      for (const Piece& pc : pieces)
+        if (pc.src && pc.bytes) memcpy(stage.data() + pc.off, pc.src, pc.bytes);
+      e = cudaMemcpyAsync(arena, stage.data(), up, cudaMemcpyHostToDevice, ctx->cfg_stream);
+      if (e == cudaSuccess && total > up) e = cudaMemsetAsync(arena + up, 0, total - up, ctx->cfg_stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->cfg_stream);  // the CONFIG stream: the data path is not involved
+    }
     if (e != cudaSuccess) {
       drop_fresh();
       return fail(ctx, ARKS_E_CUDA, "arks_prepare_tables: %s (tables unchanged)", cudaGetErrorString(e));
     }
+    for (const Piece& pc : pieces) *pc.out = arena + pc.off;
   }
   arks_prepared* p = new arks_prepared();
-  p->allocs.assign(fresh.begin(), fresh.begin() + n_table_allocs);
+  p->allocs = fresh;
   p->rate = n_rate; p->quota = n_quota; p->metrics = n_metrics; p->qdelta = n_qdelta; p->qtmp = n_qtmp; p->qexp = n_qexp;
   p->d_qos_from = n_qos_from; p->d_quota_from = n_quota_from;
   d.n_qos = t->n_qos;
@@ -2088,10 +2083,7 @@ int arks_commit_tables(arks_ctx* ctx, arks_prepared* p) {
     CK(cudaGetLastError());
   }
   // retire the outgoing generation: freed stream-ordered, after the carry kernels and everything queued before them
-  for (void* q : ctx->table_allocs) cudaFreeAsync(q, ctx->stream);
-  cudaFreeAsync(ctx->d_rate, ctx->stream); cudaFreeAsync(ctx->d_quota, ctx->stream); cudaFreeAsync(ctx->d_metrics, ctx->stream);
-  cudaFreeAsync(ctx->d_qdelta, ctx->stream); cudaFreeAsync(ctx->d_qtmp, ctx->stream); cudaFreeAsync(ctx->d_qexp, ctx->stream);
-  cudaFreeAsync(ctx->d_qos_from, ctx->stream); cudaFreeAsync(ctx->d_quota_from, ctx->stream);
+  for (void* q : ctx->table_allocs) cudaFreeAsync(q, ctx->stream);  // the one arena of the outgoing generation
   ctx->table_allocs = std::move(p->allocs);
   ctx->d_rate = p->rate; ctx->d_quota = p->quota; ctx->d_metrics = p->metrics;
   ctx->d_qdelta = p->qdelta; ctx->d_qtmp = p->qtmp; ctx->d_qexp = p->qexp;

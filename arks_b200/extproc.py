@@ -372,30 +372,52 @@ class ExtProcServer:
         self.tables = tables
         self.extract_bearer = extract_bearer
         self.batcher = batcher or Batcher(engine, max_wait_s=max_wait_s, clock=clock)
+        from .metrics import HostMetrics
+        self.metrics = HostMetrics()  # the wall-clock series (durations, non-200 statuses); the rest is counted on the device
+        self.monotonic = time.monotonic
 
     # ---- Server.Process, gateway.go:77-138
     def Process(self, request_iterator, context):
         token, qos, stream, status = b"", (-1, None), False, 0
         buffered = bytearray()
+        start, completed, resp_spent = self.monotonic(), False, 0.0
         for req in request_iterator:
             kind = req.WhichOneof("request")
             if kind == "request_headers":
+                start = self.monotonic()  # requestStart, gateway.go:108
                 resp, token = self.handle_request_headers(req)
             elif kind == "request_body":
                 resp, qos, stream = self.handle_request_body(req, token)
             elif kind == "response_headers":
                 resp, status = self.handle_response_headers(req)
                 if status == 500:  # gateway.go:115-121 -> responseErrorProcessing keeps the reply's headers, empty message
+                    self._record_request(qos, start, status)
                     hs = [(o.header.key, o.header.raw_value) for o in resp.response_headers.response.header_mutation.set_headers]
                     resp = passthrough_error(500, hs, "")
             elif kind == "response_body":
                 if status != 200:  # gateway.go:122-126: pass the upstream error through
                     resp = passthrough_error(status, [], req.response_body.body.decode("utf-8", "surrogateescape"))
                 else:
-                    resp = self.handle_response_body(req, qos, stream, buffered)
+                    t0 = self.monotonic()
+                    resp, counted = self.handle_response_body(req, qos, stream, buffered)
+                    resp_spent += self.monotonic() - t0
+                    # handle_response.go:100-106: once per stream, on the end-of-stream message that completed it
+                    if not completed and counted and req.response_body.end_of_stream and qos[0] >= 0:
+                        self.metrics.record_resp_processing(*self._labels(qos[0]), resp_spent)
+                    completed = completed or counted
+                self._record_request(qos, start, status)  # gateway.go:129: every response-body message
             else:
                 resp = PB["ProcessingResponse"]()
             yield resp
+
+    def _labels(self, q):
+        t = self.tables
+        tok = int(t.qos_token[q])
+        return t.token_namespace[tok], t.token_user[tok], t.qos_model_name[q]
+
+    def _record_request(self, qos, start, status):
+        if qos[0] >= 0:  # the reference dereferences a nil qos here when the request phase never resolved one
+            self.metrics.record_request(*self._labels(qos[0]), self.monotonic() - start, status)
 
     # ---- HandleRequestHeaders, handle_request.go:33-81
     def handle_request_headers(self, req):
@@ -455,14 +477,14 @@ class ExtProcServer:
             if not eos:
                 r = PB["ProcessingResponse"]()
                 r.response_body.response.SetInParent()
-                return r
+                return r, False
             out = self.batcher.response(bytes(buffered), qos, abi.RESP_END_OF_STREAM, gen)
         reason = int(out["reason"])
         if reason not in (abi.R_OK, abi.R_PENDING, abi.R_QOS_GONE):
-            return error_response(*replies.response_error_reply(reason, self.tables, qos, body))
+            return error_response(*replies.response_error_reply(reason, self.tables, qos, body)), False
         r = PB["ProcessingResponse"]()
         r.response_body.response.header_mutation.SetInParent()
-        return r
+        return r, bool(out.get("counted", 0))
 
 
 def serve(server: ExtProcServer, port: int = 50052, max_workers: int = 64):

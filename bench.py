@@ -503,10 +503,12 @@ def run_b200(args):
         now += STEP_S; hb.set_fixed_clock(now)
         load = arrivals(n_calls, 7200 + rate % 97 + rank)
         barrier()  # every GPU's batcher is under load at the same time
+        hb.reset_tail()
         before = hb.stats()
         dec, lat_ns, wall = hb.open_loop_requests(load, rate_per_s=rate, producers=8)
         after = hb.stats()
         lat_us = np.sort(lat_ns[n_calls // 20:]) / 1e3
+        call_us = np.sort(hb.last_call_latency[n_calls // 20:]) / 1e3
         cyc = max(after["cycles"] - before["cycles"], 1)
         q = [float(lat_us[len(lat_us) // 2]), float(lat_us[int(len(lat_us) * 0.99)]), float(lat_us[int(len(lat_us) * 0.999)])]
         if world > 1:
@@ -516,7 +518,15 @@ def run_b200(args):
         open_lat[str(rate)] = {"p50_us": q[0], "p99_us": q[1], "p999_us": q[2], "requests_per_gpu": n_calls, "gpus_loaded_at_once": world,
                                "achieved_req_per_s_rank0": n_calls / wall, "mean_batch_rank0": n_calls / cyc,
                                "us_per_cycle_rank0": {k: round((after["ns_" + k] - before["ns_" + k]) / cyc / 1e3, 1) for k in ("submit", "device", "deliver")},
-                               "admitted_rank0": int((dec["reason"] == 0).sum())}
+                               "admitted_rank0": int((dec["reason"] == 0).sum()),
+                               # the same requests on the second clock (decision - the moment the generator made the call) and what
+                               # the generator threads themselves were late by: a tail that is in `p999_us` but not here is the
+                               # load generator being descheduled, not the batcher or the device
+                               "from_call_rank0": {"p50_us": float(call_us[len(call_us) // 2]), "p99_us": float(call_us[int(len(call_us) * 0.99)]),
+                                                   "p999_us": float(call_us[int(len(call_us) * 0.999)])},
+                               "generator_rank0": hb.open_loop_lateness(),
+                               "batcher_tail_rank0": {k: (round(v / 1e3, 1) if k.startswith("max") else v) for k, v in after.items()
+                                                      if k.startswith(("max_ns", "slow_"))}}
     hb.close()
 
     # ---- the same step on single-shape traffic (every request / completion the same template, exactly BODY / RESP_BODY

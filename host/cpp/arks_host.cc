@@ -998,6 +998,8 @@ int64_t arks_host_run_responses(arks_host_batcher* h, uint32_t n, uint32_t threa
 // so a stalled batcher shows up as latency instead of silently slowing the generator down.
 struct OpenRow {
   int64_t sched_ns;
+  int64_t call_ns;        // when the generator actually made the SubmitRequest call
+  int64_t* latency_call;  // optional second clock: decision - call (what the batcher and the device added on their own)
   int64_t* latency;
   arks_host::RequestDecision* out;
   std::atomic<uint32_t>* left;
@@ -1007,7 +1009,9 @@ static inline int64_t mono_ns() {
 }
 static void open_row_done(void* user, const arks_host::RequestDecision& d) {
   OpenRow* r = static_cast<OpenRow*>(user);
-  *r->latency = mono_ns() - r->sched_ns;
+  const int64_t t = mono_ns();
+  *r->latency = t - r->sched_ns;
+  if (r->latency_call) *r->latency_call = t - r->call_ns;
   *r->out = d;
   r->left->fetch_sub(1, std::memory_order_release);
 }
@@ -1015,6 +1019,8 @@ static void open_row_done(void* user, const arks_host::RequestDecision& d) {
 // {max ns, rows more than 100 us late, max ns one SubmitRequest call took}. A late producer shows up in the rows' latency
 // (no coordinated omission) but is the harness's doing, not the batcher's.
 static std::atomic<int64_t> g_late_max{0}, g_late_slow{0}, g_submit_max{0};
+static int64_t* g_call_latency = nullptr;  // n entries for the next run, or null
+void arks_host_open_loop_call_latency(int64_t* buf) { g_call_latency = buf; }
 void arks_host_open_loop_lateness(int64_t out[3]) { out[0] = g_late_max.load(); out[1] = g_late_slow.load(); out[2] = g_submit_max.load(); }
 void arks_host_reset_tail(arks_host_batcher* h) { h->b->ResetTailStats(); }
 int64_t arks_host_open_loop_requests(arks_host_batcher* h, uint32_t n, double rate_per_s, uint32_t producers, const uint8_t* bodies,
@@ -1044,7 +1050,7 @@ int64_t arks_host_open_loop_requests(arks_host_batcher* h, uint32_t n, double ra
         }
         if (now - due > g_late_max.load(std::memory_order_relaxed)) g_late_max.store(now - due, std::memory_order_relaxed);
         if (now - due > 100'000) g_late_slow.fetch_add(1, std::memory_order_relaxed);
-        rows[i] = OpenRow{due, &latency_ns[i], &out[i], &left};
+        rows[i] = OpenRow{due, now, g_call_latency ? &g_call_latency[i] : nullptr, &latency_ns[i], &out[i], &left};
         const bool ok = h->b->SubmitRequest(std::string_view((const char*)tokens + token_off[i], token_off[i + 1] - token_off[i]),
                                             std::string_view((const char*)bodies + body_off[i], body_len[i]),
                                             pick_rand ? pick_rand[i] : 0, open_row_done, &rows[i]);

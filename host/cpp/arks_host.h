@@ -184,6 +184,7 @@ int arks_host_response(arks_host_batcher* b, int32_t qos, uint32_t gen /* 0xffff
 int arks_host_load_tables(arks_host_batcher* b, const arks_tables* t);
 void arks_host_reset_tail(arks_host_batcher* b);
 void arks_host_open_loop_lateness(int64_t out[3]);
+void arks_host_open_loop_call_latency(int64_t* buf); /* n entries filled by the next open-loop run: decision - time of the call */
 int arks_host_apply_config(arks_host_batcher* b); /* publishes arks_upsert_* / arks_delete_* done on the context */
 // names for the reply shapes of arks_host_stream_transcript / arks_host_error_reply (format: ParseNameTables)
 int arks_host_set_names(arks_host_batcher* b, const char* text, uint32_t len);

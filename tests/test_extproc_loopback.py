@@ -68,6 +68,8 @@ def run_loopback(engine, tables, make_batcher=None):
     ge.build()  # arks_extract_bearer lives in the C ABI (pure host function)
     srv = extproc.ExtProcServer(engine, tables, gateway.extract_bearer, clock=lambda: NOW,
                                 batcher=make_batcher(lambda: NOW) if make_batcher else None)
+    tick = iter(range(0, 10**9, 250))  # the server's monotonic clock: every reading 0.25 s after the one before
+    srv.monotonic = lambda: next(tick) / 1000.0
     server, port = extproc.serve(srv, port=0)
     ch, stub = extproc.client_stub(port)
     try:
@@ -89,6 +91,19 @@ def run_loopback(engine, tables, make_batcher=None):
         assert len(replies[4].response_body.response.header_mutation.set_headers) == 0
         assert engine.snapshot_rate(NOW)[0].tolist() == [1, 1, 45, 45]
         assert engine.snapshot_quota()[0].tolist() == [25, 20, 45]
+        # wall-clock series (collector.go:35-38,47-49): RecordRequest on both response-body messages, the processing time once
+        text = srv.metrics.exposition()
+        lab = 'namespace="default",user="example-token",model="qwen-7b"'
+        assert f"gateway_request_duration_seconds_count{{{lab}}} 2" in text
+        assert f'gateway_request_duration_seconds_bucket{{{lab},le="0.5"}} 0' in text
+        assert f"gateway_response_process_duration_milliseconds_count{{{lab}}} 1" in text
+        assert "gateway_requests_total" not in text  # status 200 is counted on the device
+
+        # upstream answers 503: the body is passed through, RecordRequest carries the status label (gateway.go:122-129)
+        r = list(stub(iter([hdrs([("authorization", "Bearer sk-test123456")]), body(FX["request_body"].encode(), "request_body"),
+                            resp_hdrs([(":status", "503")]), body(b"upstream down", "response_body")])))
+        assert r[3].immediate_response.status.code == 503
+        assert f'gateway_requests_total{{{lab},status="503"}} 1' in srv.metrics.exposition()
 
         # no bearer -> 401 x-error-token on the headers message (handle_request.go:48-56)
         r = list(stub(iter([hdrs([("content-type", "application/json")])])))
@@ -96,13 +111,13 @@ def run_loopback(engine, tables, make_batcher=None):
         assert set_headers(r[0].immediate_response.headers)["x-error-token"] == "true"
         assert json.loads(r[0].immediate_response.body)["error"]["code"] == 401
 
-        # rpm 5: requests 2..5 pass, the 6th is 429 x-error-rate-limit with currentUsage 5 / limitMax 5
+        # rpm 5: requests 3..5 pass, the 6th is 429 x-error-rate-limit with currentUsage 5 / limitMax 5
         codes = []
-        for _ in range(5):
+        for _ in range(4):
             r = list(stub(iter([hdrs([("Authorization", "Bearer sk-test123456")]),
                                 body(FX["request_body"].encode(), "request_body")])))
             codes.append(r[1].WhichOneof("response"))
-        assert codes == ["request_body"] * 4 + ["immediate_response"]
+        assert codes == ["request_body"] * 3 + ["immediate_response"]
         assert r[1].immediate_response.status.code == 429
         assert "x-error-rate-limit" in set_headers(r[1].immediate_response.headers)
         detail = json.loads(json.loads(r[1].immediate_response.body)["error"]["message"])

@@ -96,3 +96,25 @@ def test_device_metrics_match_oracle(gwmod):
     after = g.snapshot_metrics()
     assert after[0, abi.METRIC_MESSAGES] - before[0, abi.METRIC_MESSAGES] == 64
     assert after[0, abi.METRIC_USAGE] - before[0, abi.METRIC_USAGE] == 64
+
+
+def test_host_metrics_exposition_buckets_and_truncation():
+    """the wall-clock series kept by the host: bucket bounds of metrics.go:42,52, durations truncated to whole milliseconds"""
+    m = metrics.HostMetrics()
+    m.record_request("ns", "u", "m", 0.0999, 200)   # 99 ms -> 0.099 s -> le 0.1
+    m.record_request("ns", "u", "m", 0.1004, 200)   # 100 ms -> 0.1 s -> le 0.1 (bounds are inclusive)
+    m.record_request("ns", "u", "m", 61.0, 500)     # +Inf only
+    m.record_resp_processing("ns", "u", "m", 0.0019)  # 1 ms
+    m.record_resp_processing("ns", "u", "m", 7.5)     # 7500 ms -> +Inf
+    text = m.exposition()
+    lab = 'namespace="ns",user="u",model="m"'
+    assert f'gateway_requests_total{{{lab},status="500"}} 1' in text and 'status="200"' not in text
+    assert f'gateway_request_duration_seconds_bucket{{{lab},le="0.1"}} 2' in text
+    assert f'gateway_request_duration_seconds_bucket{{{lab},le="60"}} 2' in text
+    assert f'gateway_request_duration_seconds_bucket{{{lab},le="+Inf"}} 3' in text
+    assert f"gateway_request_duration_seconds_sum{{{lab}}} 61.199" in text
+    assert f'gateway_response_process_duration_milliseconds_bucket{{{lab},le="1"}} 1' in text
+    assert f'gateway_response_process_duration_milliseconds_bucket{{{lab},le="5000"}} 1' in text
+    assert f"gateway_response_process_duration_milliseconds_sum{{{lab}}} 7501" in text
+    assert f"gateway_response_process_duration_milliseconds_count{{{lab}}} 2" in text
+    assert metrics.HostMetrics().exposition() == ""
