@@ -32,7 +32,7 @@ class BatcherStats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("cycles", "request_batches", "response_batches", "requests", "responses",
                                           "max_request_batch", "max_response_batch", "ns_submit", "ns_device", "ns_deliver",
                                           "max_ns_submit", "max_ns_device", "max_ns_deliver", "max_ns_gap",
-                                          "slow_submit", "slow_device", "slow_deliver", "slow_gap")]
+                                          "slow_submit", "slow_device", "slow_deliver", "slow_gap", "ns_fill", "max_ns_fill", "slow_fill")]
 
 
 REQ_DTYPE = np.dtype(RequestDecision)
@@ -197,6 +197,10 @@ class Batcher:
         # second clock: decision - the moment the generator made the call (a generator thread that the OS kept off its
         # core for milliseconds is late on its own; `lat` still charges that to the request, this array does not)
         self.last_call_latency = np.zeros(batch.n, np.int64)
+        # np.zeros hands out untouched pages: the first write to each (from the completion path, inside the timed region,
+        # 2 MiB at a time under transparent huge pages) would be charged to the requests that happen to land there
+        for a in (out, lat, self.last_call_latency):
+            a.view(np.uint8)[:] = 0
         self.L.arks_host_open_loop_call_latency(_ptr(self.last_call_latency))
         bodies = np.ascontiguousarray(batch.bodies)
         ns = self.L.arks_host_open_loop_requests(self._h, batch.n, float(rate_per_s), producers, _ptr(bodies), _ptr(batch.body_off),

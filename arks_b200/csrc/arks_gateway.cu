@@ -639,7 +639,7 @@ __device__ __forceinline__ bool fast_scan_lane(const uint8_t* body, uint32_t len
     else { s.bs_hi |= bm ? bit : 0u; s.nz_hi |= tbw ? bit : 0u; }
   }
   if (c.bad || c.in_str) return false;
-  const int nmem = fast_walk(body, sm.tabs, s, nch);
+  const int nmem = fast_walk(body, sm.tabs, s, nch, KIND == K_REQ ? kFastKeyLensReq : kFastKeyLensResp);
   if (nmem < 0) return false;
   return fast_members<KIND>(body, s, nch, nmem, o);
 }
@@ -1638,6 +1638,10 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   if (const char* e = getenv("ARKS_WARP_MAX")) ctx->warp_max = (uint32_t)strtoul(e, nullptr, 10);
   CK(cudaFuncSetAttribute(fast_request_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
   CK(cudaFuncSetAttribute(fast_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
+  // a 64 Ki-document wave is 512 blocks: with four of them resident per SM (4 x ~50 KB) the whole wave runs at once
+  static_assert(sizeof(FastBlockSmem) <= 56 * 1024, "four fast-path blocks per SM");
+  CK(cudaFuncSetAttribute(fast_request_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(fast_response_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (const char* e = getenv("ARKS_FAST")) ctx->fast_scan = e[0] != '0';
   if (const char* e = getenv("ARKS_FAST_MIN")) ctx->fast_min = (uint32_t)strtoul(e, nullptr, 10);
   {

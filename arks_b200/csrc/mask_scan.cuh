@@ -34,7 +34,10 @@ namespace arks {
 
 constexpr uint32_t kFastMaxLen = 2048;             // longer documents: exact engine
 constexpr uint32_t kFastChunks = kFastMaxLen / 32;
-constexpr uint32_t kFastMaxMembers = 16;           // members of the top-level object that are logged (more: exact engine)
+constexpr uint32_t kFastMaxMembers = 8;            // logged members of the top-level object: only keys as long as a name that is
+                                                   // read (more of those than this: exact engine)
+// key lengths pass C looks at, as a bit mask: model, stream, stream_options / model, usage
+constexpr uint32_t kFastKeyLensReq = 1u << 5 | 1u << 6 | 1u << 14, kFastKeyLensResp = 1u << 5;
 constexpr uint32_t kFastMiniCap = 192;             // structure bytes read inside stream_options / usage
 
 struct FastOut {
@@ -321,7 +324,9 @@ struct TokCursor {  // iterates the set bits of the tb bitmap, jumping over empt
   }
 };
 // returns the number of members logged, or -1 (not in the subset)
-ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, const FastScratch& s, uint32_t nch) {
+// key_lens: only members whose raw key length has its bit set are logged (the others cannot spell a name that is read —
+// unless they contain an escape, which sends the document to the exact engine here as it would in pass C)
+ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, const FastScratch& s, uint32_t nch, uint32_t key_lens) {
   uint32_t g = G_TOP, depth = 0, stack = 0, nmem = 0, kstart = 0, pending = 0, bad = 0;
   TokCursor tc;
   tc.init(s, nch, 0);
@@ -350,8 +355,13 @@ ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, const FastScratch
         if ((e & (F_KEYSTART | F_KEYEND | F_VALSTART)) && depth == 1) {
           if (e & F_KEYSTART) kstart = pos[q] + 1;
           if (e & F_KEYEND) {
-            if (nmem >= kFastMaxMembers) bad = 1;
-            else { s.mem(2 * nmem) = kstart | (pos[q] - kstart) << 16; pending = 1; }
+            const uint32_t klen = pos[q] - kstart;
+            pending = 0;
+            if (any_backslash(doc, s, kstart, pos[q])) bad = 1;
+            else if (klen < 32 && (key_lens >> klen & 1u)) {
+              if (nmem >= kFastMaxMembers) bad = 1;
+              else { s.mem(2 * nmem) = kstart | klen << 16; pending = 1; }
+            }
           }
           if ((e & F_VALSTART) && pending) { s.mem(2 * nmem + 1) = pos[q]; nmem++; pending = 0; }
         }
@@ -557,7 +567,7 @@ inline bool fast_scan_host(const uint8_t* doc, uint32_t len, FastOut& out) {
     for (int q = 0; q < 8; q++) w[q] = wn[q];
   }
   if (c.bad || c.in_str) return false;
-  const int nmem = fast_walk(doc, kFastTablesHost.t, s, nch);
+  const int nmem = fast_walk(doc, kFastTablesHost.t, s, nch, KIND == K_REQ ? kFastKeyLensReq : kFastKeyLensResp);
   if (nmem < 0) return false;
   return fast_members<KIND>(doc, s, nch, nmem, out);
 }

@@ -232,7 +232,7 @@ def passthrough_error(status: int, headers, message: str):
 
 
 # --------------------------------------------------------------------------------------------------
-# micro-batcher (the Python twin of host/go/b200/batcher.go)
+# micro-batcher (the Python twin of host/cpp Batcher)
 # --------------------------------------------------------------------------------------------------
 class Batcher:
     """Stream handlers enqueue; one worker thread cuts batches by deadline (max_wait_s) or size and makes one engine

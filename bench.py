@@ -327,7 +327,16 @@ def run_b200(args):
         if world > 1:
             dist.broadcast_object_list(box, src=0)
         n_shared = min(args.shared_quota, w.tables.n_quotas)
-        g.comm_init(rank, world, box[0], np.arange(n_shared, dtype=np.uint32))
+        # libnccl announces its version on stdout when NCCL_DEBUG asks for it; stdout carries exactly one JSON line
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            g.comm_init(rank, world, box[0], np.arange(n_shared, dtype=np.uint32))
+            g.fold_quota_allreduce(wait=True)
+        finally:
+            os.dup2(keep, 1)
+            os.close(keep)
     reqs = [pin_batch(b) for b in build_waves(w, N_WAVES, args.wave, rank)]
     # dry pass to learn which requests are admitted in a fresh window, then build the matching response waves
     resps = []

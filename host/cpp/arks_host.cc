@@ -188,8 +188,11 @@ struct Batcher::Impl {
     return lead;
   }
 
-  static void wait_filled(Block& b) {
+  void wait_filled(Block& b) {
+    if (b.filled.load(std::memory_order_acquire) == b.n) return;
+    const auto t0 = std::chrono::steady_clock::now();
     while (b.filled.load(std::memory_order_acquire) != b.n) std::this_thread::yield();
+    note(t_fill, 4, (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
   }
   int free_slot() const {  // -1 while max_inflight batches are already queued on the device
     int busy = 0, first = -1;
@@ -323,7 +326,8 @@ struct Batcher::Impl {
   }
 
   std::atomic<uint64_t> t_submit{0}, t_device{0}, t_deliver{0}, t_gap{0};
-  std::atomic<uint64_t> t_max[4] = {}, t_slow[4] = {};  // submit, device, deliver, gap
+  std::atomic<uint64_t> t_max[5] = {}, t_slow[5] = {};  // submit, device, deliver, gap, fill
+  std::atomic<uint64_t> t_fill{0};
   std::chrono::steady_clock::time_point last_cycle_end{};
   bool last_had_work = false;
   void note(std::atomic<uint64_t>& acc, int k, uint64_t ns) {
@@ -442,7 +446,7 @@ void Batcher::SetClock(int64_t (*clock)(void*), void* arg) {
   p_->clock_arg = arg;
 }
 void Batcher::ResetTailStats() {
-  for (int k = 0; k < 4; k++) { p_->t_max[k].store(0); p_->t_slow[k].store(0); }
+  for (int k = 0; k < 5; k++) { p_->t_max[k].store(0); p_->t_slow[k].store(0); }
 }
 BatcherStats Batcher::Stats() const {
   std::lock_guard<std::mutex> g(p_->mu);
@@ -452,6 +456,7 @@ BatcherStats Batcher::Stats() const {
   s.ns_deliver = p_->t_deliver.load();
   s.max_ns_submit = p_->t_max[0].load(); s.max_ns_device = p_->t_max[1].load(); s.max_ns_deliver = p_->t_max[2].load(); s.max_ns_gap = p_->t_max[3].load();
   s.slow_submit = p_->t_slow[0].load(); s.slow_device = p_->t_slow[1].load(); s.slow_deliver = p_->t_slow[2].load(); s.slow_gap = p_->t_slow[3].load();
+  s.ns_fill = p_->t_fill.load(); s.max_ns_fill = p_->t_max[4].load(); s.slow_fill = p_->t_slow[4].load();
   return s;
 }
 

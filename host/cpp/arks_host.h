@@ -8,7 +8,7 @@
 //                    while earlier ones are on the GPU); a completion thread waits for the oldest batch and hands
 //                    every row its decision (callback, or futex wake of a blocked caller); with one batch in flight
 //                    (the default) the dispatcher does both, and a blocked caller that finds the batcher idle runs the
-//                    cycle for its own row itself. host/go/b200/batcher.go is the Go twin.
+//                    cycle for its own row itself.
 //   StreamProcessor  Server.Process's per-stream state machine (pkg/gateway/gateway.go:77-138) and the four handlers
 //                    (handle_request.go:33-249, handle_response.go:37-268) over decoded ext_proc messages; the gRPC /
 //                    protobuf transport stays with the embedding server
@@ -65,6 +65,8 @@ struct BatcherStats {
   // end of one cycle and the start of the next while rows were waiting (dispatcher wake-up, lock hand-over)
   uint64_t max_ns_submit, max_ns_device, max_ns_deliver, max_ns_gap;
   uint64_t slow_submit, slow_device, slow_deliver, slow_gap;
+  // the part of `submit` spent waiting for row owners that had reserved a row but not finished copying into it
+  uint64_t ns_fill, max_ns_fill, slow_fill;
 };
 
 typedef void (*RequestCallback)(void* user, const RequestDecision&);    // run on the batcher's completion thread

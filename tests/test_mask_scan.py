@@ -97,6 +97,16 @@ def test_structure_corner_cases():
               b'{"stream_options":{"include_usage":1},"model":"m"}', b'{"stream":"true","model":"m"}',
               b'{"model":"m","d":' + b'[' * 40 + b']' * 40 + b'}']:
         assert hm.fast_request(b) is None, b
+    # the member log only takes keys as long as a name that is read: 40 other members are no reason to decline, an escape
+    # in ANY top-level key is (it may spell a name at another raw length), and so are more than 8 keys of a matching length
+    many = ",".join('"param_%02d":%d' % (i, i) for i in range(40))
+    assert check_request(('{' + many + ',"model":"m","stream":true}').encode()) == 1
+    assert hm.fast_request(('{' + many + ',"model":"m","stream":true}').encode())[1] == 2
+    assert hm.fast_request(b'{"te\\u006dperature":1,"model":"m"}') is None
+    assert check_request(b'{"d":{"te\\u006dperature":1},"model":"m"}') == 1  # deeper keys are nobody's business
+    five = ",".join('"k%04d":1' % i for i in range(9))
+    assert hm.fast_request(('{' + five + ',"model":"m"}').encode()) is None
+    assert check_request(('{' + ",".join('"k%04d":1' % i for i in range(7)) + ',"model":"m"}').encode()) == 1
     # and things it must get right
     assert hm.fast_request(b' {"MODEL" : "M\\u00e9" , "Stream":null, "STREAM_OPTIONS":null} \n')[1:] == (0, 0, 0)
     assert hm.fast_request(b'{"stream_options":{"x":{"include_usage":false},"include_usage":true},"model":"m"}')[1:] == (0, 1, 2)
