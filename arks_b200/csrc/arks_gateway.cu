@@ -593,68 +593,130 @@ __device__ __forceinline__ void stage_fast_tables(FastTables* dst, uint64_t* bar
   mbar_wait(bar, 0);
 }
 
-// Shared memory of a fast-path block: the grammar tables and the per-lane scratch of mask_scan.cuh, lane-interleaved.
+// Shared memory of a fast-path block: the grammar tables and the per-document scratch of mask_scan.cuh, interleaved by slot.
 struct __align__(128) FastBlockSmem {
   FastTables tabs;
   uint64_t bar;
   uint32_t tb[kFastChunks * kFastThreads];
   uint32_t mem[2 * kFastMaxMembers * kFastThreads];
   uint32_t ring[16 * kFastThreads];  // the current and the next chunk of every lane (dynamic byte access for escapes)
+  // hand-over between pass A (thread t scans the document of slot t) and passes B/C (thread t walks slot order[t]):
+  uint32_t hand[5 * kFastThreads];   // bs_lo, bs_hi, nz_lo, nz_hi, tokens + 1 (0: pass A declined)
+  uint32_t hist[64];
+  uint32_t order[kFastThreads];
+  uint32_t slot[kFastThreads];       // which of the block's documents column t holds (pass A takes them in order of length)
 };
 
-// passes A-C for the body of one lane; false: declined (or not eligible).
-// Pass A streams the body through a 4-deep register queue of 32-byte chunks (the loads of chunks j+1..j+4 are in flight while
-// chunk j is processed): a lane-per-document kernel has one partial wave of warps per SM, so memory latency has to be
-// covered inside the lane, not by other warps. One copy of the chunk code (the instruction cache is small).
-template <int KIND>
-__device__ __forceinline__ bool fast_scan_lane(const uint8_t* body, uint32_t len, FastBlockSmem& sm, FastOut& o) {
-  if (len == 0 || len > kFastMaxLen) return false;
-  FastScratch s{sm.tb + threadIdx.x, sm.mem + threadIdx.x, (uint32_t)kFastThreads, 0u, 0u, 0u, 0u};
-  const FastRing ring{sm.ring + threadIdx.x, (uint32_t)kFastThreads};
-  const uint32_t nch = (len + 31) >> 5, plen = (len + 15u) & ~15u;
-  FastCarry c{0, 0, 0};
-  const uint4* p = reinterpret_cast<const uint4*>(body);
-  const uint4 z = make_uint4(0, 0, 0, 0);
-  auto lo = [&](uint32_t j) { return j < nch ? ld_nc_v4(p + 2 * j) : z; };
-  auto hi = [&](uint32_t j) { return j < nch && 32 * j + 16 < plen ? ld_nc_v4(p + 2 * j + 1) : z; };  // never past the 16-byte padding
-  uint4 a0 = lo(0), b0 = hi(0), a1 = lo(1), b1 = hi(1), a2 = lo(2), b2 = hi(2), a3 = lo(3), b3 = hi(3);
-  {
-    const uint32_t w0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
-    ring.put(0, w0);
-  }
-#pragma unroll 1
-  for (uint32_t j = 0; j < nch; j++) {
-    const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
-    a0 = a1; b0 = b1; a1 = a2; b1 = b2; a2 = a3; b2 = b3;
-    a3 = lo(j + 4); b3 = hi(j + 4);
+// Pass A for the body of slot threadIdx.x; its result goes to sm.hand. Streams the body through a 4-deep register queue of
+// 32-byte chunks (the loads of chunks j+1..j+4 are in flight while chunk j is processed): a lane-per-document kernel has one
+// partial wave of warps per SM, so memory latency has to be covered inside the lane, not by other warps. One copy of the
+// chunk code (the instruction cache is small).
+__device__ __forceinline__ void fast_pass_a(const uint8_t* body, uint32_t len, FastBlockSmem& sm) {
+  const uint32_t t = threadIdx.x;
+  uint32_t ntok1 = 0;
+  FastScratch s{sm.tb + t, sm.mem + t, (uint32_t)kFastThreads, 0u, 0u, 0u, 0u};
+  if (len != 0 && len <= kFastMaxLen) {
+    const FastRing ring{sm.ring + t, (uint32_t)kFastThreads};
+    const uint32_t nch = (len + 31) >> 5, plen = (len + 15u) & ~15u;
+    FastCarry c{0, 0, 0};
+    const uint4* p = reinterpret_cast<const uint4*>(body);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    auto lo = [&](uint32_t j) { return j < nch ? ld_nc_v4(p + 2 * j) : z; };
+    auto hi = [&](uint32_t j) { return j < nch && 32 * j + 16 < plen ? ld_nc_v4(p + 2 * j + 1) : z; };  // never past the 16-byte padding
+    uint4 a0 = lo(0), b0 = hi(0), a1 = lo(1), b1 = hi(1), a2 = lo(2), b2 = hi(2), a3 = lo(3), b3 = hi(3);
     {
-      const uint32_t wn[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
-      ring.put(j + 1, wn);  // the chunk after the current one is at hand too (a \uXXXX may straddle the boundary)
+      const uint32_t w0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+      ring.put(0, w0);
     }
-    uint32_t bm, tbw;
-    fast_chunk(w, min(len - 32 * j, 32u), ring, len, 32 * j, c, &tbw, &bm);
-    s.tb(j) = tbw;
-    const uint32_t bit = 1u << (j & 31);
-    if (j < 32) { s.bs_lo |= bm ? bit : 0u; s.nz_lo |= tbw ? bit : 0u; }
-    else { s.bs_hi |= bm ? bit : 0u; s.nz_hi |= tbw ? bit : 0u; }
+    uint32_t ntok = 0;
+#pragma unroll 1
+    for (uint32_t j = 0; j < nch; j++) {
+      const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+      a0 = a1; b0 = b1; a1 = a2; b1 = b2; a2 = a3; b2 = b3;
+      a3 = lo(j + 4); b3 = hi(j + 4);
+      {
+        const uint32_t wn[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+        ring.put(j + 1, wn);  // the chunk after the current one is at hand too (a \uXXXX may straddle the boundary)
+      }
+      uint32_t bm, tbw;
+      fast_chunk(w, min(len - 32 * j, 32u), ring, len, 32 * j, c, &tbw, &bm);
+      s.tb(j) = tbw;
+      ntok += __popc(tbw);
+      const uint32_t bit = 1u << (j & 31);
+      if (j < 32) { s.bs_lo |= bm ? bit : 0u; s.nz_lo |= tbw ? bit : 0u; }
+      else { s.bs_hi |= bm ? bit : 0u; s.nz_hi |= tbw ? bit : 0u; }
+    }
+    if (!(c.bad || c.in_str)) ntok1 = ntok + 1;
   }
-  if (c.bad || c.in_str) return false;
-  const int nmem = fast_walk(body, sm.tabs, s, nch, KIND == K_REQ ? kFastKeyLensReq : kFastKeyLensResp);
+  sm.hand[0 * kFastThreads + t] = s.bs_lo;
+  sm.hand[1 * kFastThreads + t] = s.bs_hi;
+  sm.hand[2 * kFastThreads + t] = s.nz_lo;
+  sm.hand[3 * kFastThreads + t] = s.nz_hi;
+  sm.hand[4 * kFastThreads + t] = ntok1;
+}
+
+// A block's 128 documents are taken in two different orders, both found with a counting sort in shared memory (64 buckets):
+//   pass A in order of LENGTH (chunks): its loop runs as long as the longest document of the warp. The batch itself stays in
+//     arrival order — every block holds the same mix of lengths and all blocks finish together; a globally length-sorted batch
+//     put all the long documents into the last blocks, which then ran on alone (measured: 286 us against 259 us, and the sort
+//     kernels cost another 20 us);
+//   passes B / C in order of the number of bytes outside strings: one table step per such byte, and documents of one length
+//     still differ 2x in structure.
+// Returns the position thread t takes in that order. All threads of the block call it.
+__device__ __forceinline__ uint32_t fast_block_order(FastBlockSmem& sm, uint32_t bucket, bool on) {
+  const uint32_t t = threadIdx.x;
+  if (!on) return t;
+  if (t < 64) sm.hist[t] = 0;
+  __syncthreads();
+  const uint32_t mine = atomicAdd(&sm.hist[bucket], 1u);
+  __syncthreads();
+  uint32_t before = 0;
+  for (uint32_t k = 0; k < bucket; k++) before += sm.hist[k];
+  sm.order[before + mine] = t;
+  __syncthreads();
+  const uint32_t r = sm.order[t];
+  __syncthreads();  // hist / order are reused by the next call
+  return r;
+}
+
+// passes B and C over the scratch in column u; false: declined
+template <int KIND, int WALK>
+__device__ __forceinline__ bool fast_pass_bc(const uint8_t* body, uint32_t len, FastBlockSmem& sm, uint32_t u, FastOut& o) {
+  if (sm.hand[4 * kFastThreads + u] == 0) return false;
+  const FastScratch s{sm.tb + u, sm.mem + u, (uint32_t)kFastThreads, sm.hand[0 * kFastThreads + u], sm.hand[1 * kFastThreads + u],
+                      sm.hand[2 * kFastThreads + u], sm.hand[3 * kFastThreads + u]};
+  const uint32_t nch = (len + 31) >> 5;
+  const int nmem = fast_walk<WALK>(body, sm.tabs, s, nch, KIND == K_REQ ? kFastKeyLensReq : kFastKeyLensResp);
   if (nmem < 0) return false;
   return fast_members<KIND>(body, s, nch, nmem, o);
 }
 
-__global__ void __launch_bounds__(kFastThreads) fast_request_kernel(DevTables T, ReqDev B) {
+template <int WALK>
+__global__ void __launch_bounds__(kFastThreads) fast_request_kernel(DevTables T, ReqDev B, int regroup) {
   extern __shared__ __align__(1024) uint8_t smem[];
   FastBlockSmem& sm = *reinterpret_cast<FastBlockSmem*>(smem);
   stage_fast_tables(&sm.tabs, &sm.bar);
-  const uint32_t lane_id = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t base = blockIdx.x * blockDim.x;
+  {
+    const uint32_t own = base + threadIdx.x;
+    const uint32_t len0 = own < B.n ? B.body_len[B.perm ? B.perm[own] : own] : 0u;
+    const uint32_t a = fast_block_order(sm, min((len0 + 31) >> 5, 63u), regroup != 0);  // the document pass A scans here
+    const bool in = base + a < B.n;
+    const uint32_t i = in ? (B.perm ? B.perm[base + a] : base + a) : 0;
+    fast_pass_a(B.bodies + (in ? B.body_off[i] : 0), in && !(regroup & 512) ? B.body_len[i] : 0u, sm);
+    sm.slot[threadIdx.x] = a;
+    __syncthreads();
+  }
+  if (regroup & 256) return;  // timing experiments only (ARKS_REGROUP=257): pass A alone, no results
+  regroup &= 255;
+  const uint32_t u = fast_block_order(sm, min(sm.hand[4 * kFastThreads + threadIdx.x] >> 2, 63u), regroup > 1);  // column
+  const uint32_t lane_id = base + sm.slot[u];
   if (lane_id >= B.n) return;
   const uint32_t i = B.perm ? B.perm[lane_id] : lane_id;
   const uint8_t* body = B.bodies + B.body_off[i];
   const uint32_t len = B.body_len[i];
   FastOut o;
-  if (!fast_scan_lane<K_REQ>(body, len, sm, o)) {
+  if (!fast_pass_bc<K_REQ, WALK>(body, len, sm, u, o)) {
     B.slow_list[atomicAdd(B.slow_n, 1u) + 1u] = i;
     return;
   }
@@ -1140,11 +1202,31 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kMinBlocks) scan_response
 }
 
 // the fast path for complete response bodies: first stage of the two-stage scan (see fast_request_kernel)
-__global__ void __launch_bounds__(kFastThreads) fast_response_kernel(DevTables T, RespDev B) {
+template <int WALK>
+__global__ void __launch_bounds__(kFastThreads) fast_response_kernel(DevTables T, RespDev B, int regroup) {
   extern __shared__ __align__(1024) uint8_t smem[];
   FastBlockSmem& sm = *reinterpret_cast<FastBlockSmem*>(smem);
   stage_fast_tables(&sm.tabs, &sm.bar);
-  const uint32_t lane_id = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t base = blockIdx.x * blockDim.x;
+  {
+    const uint32_t own = base + threadIdx.x;
+    uint32_t len0 = 0;
+    if (own < B.n) {
+      const uint32_t i0 = B.perm ? B.perm[own] : own;
+      if ((B.flags[i0] & ARKS_RESP_END_OF_STREAM) && B.qos[i0] >= 0) len0 = B.body_len[i0];
+    }
+    const uint32_t a = fast_block_order(sm, min((len0 + 31) >> 5, 63u), regroup != 0);
+    const bool in = base + a < B.n;
+    const uint32_t i = in ? (B.perm ? B.perm[base + a] : base + a) : 0;
+    const bool scan = in && (B.flags[i] & ARKS_RESP_END_OF_STREAM) && B.qos[i] >= 0;
+    fast_pass_a(B.bodies + (scan ? B.body_off[i] : 0), scan ? B.body_len[i] : 0u, sm);
+    sm.slot[threadIdx.x] = a;
+    __syncthreads();
+  }
+  if (regroup & 256) return;  // timing experiments only: pass A alone
+  regroup &= 255;
+  const uint32_t u = fast_block_order(sm, min(sm.hand[4 * kFastThreads + threadIdx.x] >> 2, 63u), regroup > 1);
+  const uint32_t lane_id = base + sm.slot[u];
   const bool in = lane_id < B.n;
   const uint32_t i = in ? (B.perm ? B.perm[lane_id] : lane_id) : 0;
   const int32_t qos = in ? B.qos[i] : 0;
@@ -1155,7 +1237,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_response_kernel(DevTables T
   bool live = in;
   if (in && !pending && qos >= 0) {
     FastOut o;
-    if (fast_scan_lane<K_RESP>(B.bodies + B.body_off[i], B.body_len[i], sm, o)) {
+    if (fast_pass_bc<K_RESP, WALK>(B.bodies + B.body_off[i], B.body_len[i], sm, u, o)) {
       if (o.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // handle_response.go:167-181
       else { u0 = o.usage[0]; u1 = o.usage[1]; u2 = o.usage[2]; }
       counted = reason == ARKS_R_OK && u2 != 0;               // :186
@@ -1453,6 +1535,8 @@ struct arks_ctx {
   cudaStream_t h2d = nullptr;     // batch uploads (overlap the kernels of earlier batches)
   cudaStream_t cfg_stream = nullptr;  // config plane: the next generation's tables are uploaded here, off the data path
   std::mutex cfg_mu;                  // prepare (config thread) vs commit (batch thread)
+  bool walk8 = true;                   // fast path, pass B: the step inlined eight times (true) or one copy in a loop
+  int regroup = 1;                     // fast path: regroup a block's documents by structure between passes A and B
   struct NcclApi* nccl = nullptr;      // dlopen()ed libnccl + this context's communicator (arks_comm_init)
   arks::ConfigStore* store = nullptr;  // objects behind arks_upsert_* / arks_delete_*
   int32_t *d_qos_from = nullptr, *d_quota_from = nullptr;  // row maps of the current generation (kept alive for the carry kernels)
@@ -1531,6 +1615,7 @@ struct arks_ctx {
   uint32_t* d_perm = nullptr;    // lane -> body permutation of the batch being scanned (length order)
   uint32_t* d_lenhist = nullptr; // kLenBuckets counters / offsets
   bool sort_lanes = true;        // ARKS_SORT=0 scans in arrival order (A/B runs)
+  bool sort_fast = false;        // ARKS_SORT=2: global length order in front of the fast path too (A/B runs)
   bool fast_scan = true;         // ARKS_FAST=0: large batches also take the fused lane-per-document kernels (A/B runs)
   uint32_t fast_min = kFastMinBatchDefault;  // ARKS_FAST_MIN=n: batches of n rows and more take the two-stage scan
   uint32_t warp_max = kWarpMaxBatchDefault;  // ARKS_WARP_MAX=n: batches of up to n rows take the warp-per-document latency path
@@ -1601,7 +1686,7 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return ARKS_E_NO_DEVICE;
   arks_ctx* ctx = new arks_ctx();
   ctx->device = device;
-  if (const char* e = getenv("ARKS_SORT")) ctx->sort_lanes = e[0] != '0';
+  if (const char* e = getenv("ARKS_SORT")) { ctx->sort_lanes = e[0] != '0'; ctx->sort_fast = e[0] == '2'; }
   if (const char* e = getenv("ARKS_SCHED")) {
     int a = 8, b = 8, c = 8;
     if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3) {
@@ -1636,12 +1721,25 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaFuncSetAttribute(warp_request_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWdSmemPerBlock));
   CK(cudaFuncSetAttribute(warp_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWdSmemPerBlock));
   if (const char* e = getenv("ARKS_WARP_MAX")) ctx->warp_max = (uint32_t)strtoul(e, nullptr, 10);
-  CK(cudaFuncSetAttribute(fast_request_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
-  CK(cudaFuncSetAttribute(fast_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
+  CK(cudaFuncSetAttribute(fast_request_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
+  CK(cudaFuncSetAttribute(fast_response_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
+  CK(cudaFuncSetAttribute(fast_request_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
+  CK(cudaFuncSetAttribute(fast_response_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
   // a 64 Ki-document wave is 512 blocks: with four of them resident per SM (4 x ~50 KB) the whole wave runs at once
   static_assert(sizeof(FastBlockSmem) <= 56 * 1024, "four fast-path blocks per SM");
-  CK(cudaFuncSetAttribute(fast_request_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(fast_response_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  {
+    const char* cv = getenv("ARKS_CARVEOUT");  // percent of the SM's L1/shared array given to shared memory; default: the driver's choice
+    if (cv && *cv) {
+      CK(cudaFuncSetAttribute(fast_request_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+      CK(cudaFuncSetAttribute(fast_response_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+      CK(cudaFuncSetAttribute(fast_request_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+      CK(cudaFuncSetAttribute(fast_response_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+    }
+    const char* wk = getenv("ARKS_WALK");
+    ctx->walk8 = wk && *wk ? atoi(wk) == 8 : true;
+    const char* rg = getenv("ARKS_REGROUP");
+    ctx->regroup = rg && *rg ? atoi(rg) : 1;
+  }
   if (const char* e = getenv("ARKS_FAST")) ctx->fast_scan = e[0] != '0';
   if (const char* e = getenv("ARKS_FAST_MIN")) ctx->fast_min = (uint32_t)strtoul(e, nullptr, 10);
   {
@@ -2457,10 +2555,15 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
     ctx->launches += 1;
     ctx->last_two_stage = true;
   } else if (ctx->fast_scan && n >= ctx->fast_min) {
-    // two-stage scan: the fast path (mask_scan.cuh) decides everything plain, the exact engine what it declines
-    r.perm = queue_length_order(ctx, r.body_len, n);
+    // two-stage scan: the fast path (mask_scan.cuh) decides everything plain, the exact engine what it declines. The batch
+    // stays in arrival order (every block orders its own 128 documents: fast_block_order) unless ARKS_SORT=2 asks for the
+    // global length order the exact engine uses
+    r.perm = ctx->sort_fast ? queue_length_order(ctx, r.body_len, n) : nullptr;
     if (ctx->prof) CK(cudaEventRecord(ctx->ev_fast[0], ctx->stream));
-    fast_request_kernel<<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, r);
+    if (ctx->walk8)
+      fast_request_kernel<8><<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, r, ctx->regroup);
+    else
+      fast_request_kernel<0><<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, r, ctx->regroup);
     if (ctx->prof) { CK(cudaEventRecord(ctx->ev_fast[1], ctx->stream)); ctx->ev_fast_set = true; }
     r.perm = nullptr;
     r.bpw = 32;
@@ -2697,9 +2800,12 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
     rp.slow_list = ctx->d_slow + 64;
     ctx->last_slow_n = rp.slow_n;
     CK(cudaMemsetAsync(ctx->d_slow, 0xff, 4, ctx->stream));
-    rp.perm = queue_length_order(ctx, rp.body_len, rp.n);
+    rp.perm = ctx->sort_fast ? queue_length_order(ctx, rp.body_len, rp.n) : nullptr;
     if (ctx->prof) CK(cudaEventRecord(ctx->ev_fast[0], ctx->stream));
-    fast_response_kernel<<<(rp.n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, rp);
+    if (ctx->walk8)
+      fast_response_kernel<8><<<(rp.n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, rp, ctx->regroup);
+    else
+      fast_response_kernel<0><<<(rp.n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, rp, ctx->regroup);
     if (ctx->prof) { CK(cudaEventRecord(ctx->ev_fast[1], ctx->stream)); ctx->ev_fast_set = true; }
     rp.perm = nullptr;
     rp.bpw = 32;

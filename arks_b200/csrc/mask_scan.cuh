@@ -272,18 +272,23 @@ ARKS_HD uint32_t next_token(const FastScratch& s, uint32_t nch, uint32_t from, u
   return w * 32 + first_set(m);
 }
 // any backslash among bytes [b, e)? The per-chunk summary answers "no" without touching the document in the usual case.
-ARKS_HD bool any_backslash(const uint8_t* doc, const FastScratch& s, uint32_t b, uint32_t e) {
-  if (e <= b) return false;
-  const uint32_t c0 = b >> 5, c1 = (e - 1) >> 5;
-  uint32_t hit = 0;
-  for (uint32_t c = c0; c <= c1; c++) hit |= c < 32 ? (s.bs_lo >> c) & 1u : (s.bs_hi >> (c - 32)) & 1u;
-  if (!hit) return false;
+// the three helpers below are called from a dozen places with loops inside: inlined they were 3 300 of the request kernel's
+// 9 000 SASS instructions, and a kernel whose warps each sit somewhere else in 144 KB of code waits for the instruction
+// cache more than for anything else (ncu: stall_no_instruction on top). One copy each.
+ARKS_OUTLINE bool any_backslash_bytes(const uint8_t* doc, uint32_t b, uint32_t e) {
   uint32_t d = 0;
   for (uint32_t i = b; i < e; i++) d |= doc[i] == '\\';
   return d != 0;
 }
+ARKS_HD bool any_backslash(const uint8_t* doc, const FastScratch& s, uint32_t b, uint32_t e) {
+  if (e <= b) return false;
+  const uint32_t c0 = b >> 5, c1 = (e - 1) >> 5;  // the chunks the span lies in, tested without a loop
+  const uint64_t m = (~0ull << c0) & (~0ull >> (63 - c1));
+  if (!(((uint64_t)s.bs_hi << 32 | s.bs_lo) & m)) return false;
+  return any_backslash_bytes(doc, b, e);
+}
 // case-folded comparison with a lower-case literal (json-iterator's struct fields), exact comparison (gjson's Map())
-ARKS_HD bool key_is_fold(const uint8_t* doc, uint32_t pos, uint32_t n, const char* lit) {
+ARKS_OUTLINE bool key_is_fold(const uint8_t* doc, uint32_t pos, uint32_t n, const char* lit) {
   uint32_t d = 0;
   for (uint32_t i = 0; i < n; i++) {
     const uint32_t c = doc[pos + i];
@@ -291,7 +296,7 @@ ARKS_HD bool key_is_fold(const uint8_t* doc, uint32_t pos, uint32_t n, const cha
   }
   return d == 0;
 }
-ARKS_HD bool key_is(const uint8_t* doc, uint32_t pos, uint32_t n, const char* lit) {
+ARKS_OUTLINE bool key_is(const uint8_t* doc, uint32_t pos, uint32_t n, const char* lit) {
   uint32_t d = 0;
   for (uint32_t i = 0; i < n; i++) d |= (uint32_t)doc[pos + i] ^ (uint32_t)(uint8_t)lit[i];
   return d == 0;
@@ -323,15 +328,14 @@ struct TokCursor {  // iterates the set bits of the tb bitmap, jumping over empt
     return true;
   }
 };
-// returns the number of members logged, or -1 (not in the subset)
-// key_lens: only members whose raw key length has its bit set are logged (the others cannot spell a name that is read —
-// unless they contain an escape, which sends the document to the exact engine here as it would in pass C)
-ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, const FastScratch& s, uint32_t nch, uint32_t key_lens) {
-  uint32_t g = G_TOP, depth = 0, stack = 0, nmem = 0, kstart = 0, pending = 0, bad = 0;
-  TokCursor tc;
-  tc.init(s, nch, 0);
-  for (;;) {
-    uint32_t pos[kFastAhead], by[kFastAhead];
+// kFastAhead tokens fetched together: the byte loads go out back to back (which byte comes next depends only on the bitmap),
+// then the grammar steps run over them in a loop that exists ONCE — positions and bytes travel packed in four registers,
+// because eight inlined copies of the step were 24 KB of code and the warps of this kernel stall on instruction fetch more
+// than on anything else (they are few and each sits somewhere else in the code).
+struct TokBatch {
+  uint64_t by, p0, p1;  // 8 bytes; 8 positions of 16 bits
+  ARKS_HD int fetch(TokCursor& tc, const FastScratch& s, const uint8_t* doc) {
+    uint32_t pos[kFastAhead], b[kFastAhead];
     int n = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll
@@ -339,51 +343,108 @@ ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, const FastScratch
     for (int q = 0; q < kFastAhead; q++) {
       pos[q] = 0;
       const bool have = tc.next(s, &pos[q]);
-      by[q] = have ? doc[pos[q]] : 0u;
+      b[q] = have ? doc[pos[q]] : 0u;
       n += have;
     }
+    by = (uint64_t)(b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24) | (uint64_t)(b[4] | b[5] << 8 | b[6] << 16 | b[7] << 24) << 32;
+    p0 = (uint64_t)(pos[0] | pos[1] << 16) | (uint64_t)(pos[2] | pos[3] << 16) << 32;
+    p1 = (uint64_t)(pos[4] | pos[5] << 16) | (uint64_t)(pos[6] | pos[7] << 16) << 32;
+    return n;
+  }
+  ARKS_HD uint32_t byte(int q) const { return (uint32_t)(by >> (8 * q)) & 0xffu; }
+  ARKS_HD uint32_t pos(int q) const { return (uint32_t)((q < 4 ? p0 : p1) >> (16 * (q & 3))) & 0xffffu; }
+};
+static_assert(kFastAhead == 8 && kFastMaxLen <= 65536, "TokBatch packs 8 positions of 16 bits");
+// returns the number of members logged, or -1 (not in the subset)
+// key_lens: only members whose raw key length has its bit set are logged (the others cannot spell a name that is read —
+// unless they contain an escape, which sends the document to the exact engine here as it would in pass C)
+// WALK: 8 = the step inlined eight times behind the eight loads (no packing, 24 KB of code); 0 = one copy of the step in a
+// loop over a packed batch (the instruction cache's friend). Same results; which one is faster is a measurement.
+template <int WALK>
+ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, const FastScratch& s, uint32_t nch, uint32_t key_lens) {
+  uint32_t g = G_TOP, depth = 0, stack = 0, nmem = 0, nsus = 0, kstart = 0, pending = 0, bad = 0;
+  const uint64_t bs64 = (uint64_t)s.bs_hi << 32 | s.bs_lo;
+  TokCursor tc;
+  tc.init(s, nch, 0);
+  // (A version of this step without branches — selects and predicated stores only — was measured too: same time for
+  // requests, 5 % slower for completions; the kernel is bound by the latency of each lane's dependent chain, not by the
+  // instructions the diverged branches add. DESIGN.md section 5.)
+  auto step = [&](uint32_t pq, uint32_t byte) {
+    const uint32_t e = T.tab[g * kFastTabStride + T.cls[byte]];
+    const uint32_t act = (e >> 5) & 7u;
+    g = e & 31u;
+    const bool top_obj = depth && ((stack >> (depth - 1)) & 1u);
+    // members of the top-level object: key span and the first byte of the value (depth is still the one BEFORE a push)
+    if ((e & (F_KEYSTART | F_KEYEND | F_VALSTART)) && depth == 1) {
+      if (e & F_KEYSTART) kstart = pq + 1;
+      if (e & F_KEYEND) {
+        const uint32_t klen = pq - kstart;
+        pending = 0;
+        if (klen < 32 && (key_lens >> klen & 1u)) {  // pass C compares it (and checks it for escapes)
+          if (nmem + nsus >= kFastMaxMembers) bad = 1;
+          else { s.mem(2 * nmem) = kstart | klen << 16; pending = 1; }
+        } else if (klen) {
+          // another length: only an escape could make it spell a name that is read. The chunks it lies in are tested
+          // here without a loop; the few keys that share a chunk with a backslash are parked (from the top of the
+          // member log down) and looked at byte by byte after the walk, outside this loop
+          const uint32_t c0 = kstart >> 5, c1 = (pq - 1) >> 5;
+          const uint64_t m = (~0ull << c0) & (~0ull >> (63 - c1));
+          if (bs64 & m) {
+            if (nmem + nsus >= kFastMaxMembers) bad = 1;
+            else { s.mem(2 * (kFastMaxMembers - 1 - nsus)) = kstart | klen << 16; nsus++; }
+          }
+        }
+      }
+      if ((e & F_VALSTART) && pending) { s.mem(2 * nmem + 1) = pq; nmem++; pending = 0; }
+    }
+    if (act == A_PUSH_OBJ || act == A_PUSH_ARR) {
+      if (depth >= 32) bad = 1;
+      else { stack = (stack & ~(1u << depth)) | ((act == A_PUSH_OBJ ? 1u : 0u) << depth); depth++; }
+    } else if (act == A_POP_OBJ || act == A_POP_ARR) {
+      if (!depth || top_obj != (act == A_POP_OBJ)) bad = 1;
+      else depth--;
+    } else if (act == A_COMMA) {
+      if (!depth) bad = 1;
+      g = top_obj ? G_KEY : G_VAL;
+    } else if (act == A_ERR) {
+      bad = 1;
+    }
+  };
+  for (;;) {
+    int n = 0;
+    if (WALK == 8) {
+      uint32_t pos[kFastAhead], by[kFastAhead];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-    for (int q = 0; q < kFastAhead; q++) {
-      if (q < n) {
-        const uint32_t e = T.tab[g * kFastTabStride + T.cls[by[q]]];
-        const uint32_t act = (e >> 5) & 7u;
-        g = e & 31u;
-        const bool top_obj = depth && ((stack >> (depth - 1)) & 1u);
-        // members of the top-level object: key span and the first byte of the value (depth is still the one BEFORE a push)
-        if ((e & (F_KEYSTART | F_KEYEND | F_VALSTART)) && depth == 1) {
-          if (e & F_KEYSTART) kstart = pos[q] + 1;
-          if (e & F_KEYEND) {
-            const uint32_t klen = pos[q] - kstart;
-            pending = 0;
-            if (any_backslash(doc, s, kstart, pos[q])) bad = 1;
-            else if (klen < 32 && (key_lens >> klen & 1u)) {
-              if (nmem >= kFastMaxMembers) bad = 1;
-              else { s.mem(2 * nmem) = kstart | klen << 16; pending = 1; }
-            }
-          }
-          if ((e & F_VALSTART) && pending) { s.mem(2 * nmem + 1) = pos[q]; nmem++; pending = 0; }
-        }
-        if (act == A_PUSH_OBJ || act == A_PUSH_ARR) {
-          if (depth >= 32) bad = 1;
-          else { stack = (stack & ~(1u << depth)) | ((act == A_PUSH_OBJ ? 1u : 0u) << depth); depth++; }
-        } else if (act == A_POP_OBJ || act == A_POP_ARR) {
-          if (!depth || top_obj != (act == A_POP_OBJ)) bad = 1;
-          else depth--;
-        } else if (act == A_COMMA) {
-          if (!depth) bad = 1;
-          g = top_obj ? G_KEY : G_VAL;
-        } else if (act == A_ERR) {
-          bad = 1;
-        }
+      for (int q = 0; q < kFastAhead; q++) {
+        pos[q] = 0;
+        const bool have = tc.next(s, &pos[q]);
+        by[q] = have ? doc[pos[q]] : 0u;
+        n += have;
       }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int q = 0; q < kFastAhead; q++)
+        if (q < n) step(pos[q], by[q]);
+    } else {
+      TokBatch tk;
+      n = tk.fetch(tc, s, doc);
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+      for (int q = 0; q < n; q++) step(tk.pos(q), tk.byte(q));
     }
     if (bad) return -1;
     if (n < kFastAhead) break;
   }
   // the document is one complete object (numbers cannot be open here: the top-level value is an object)
   if (g != G_AFTER || depth != 0) return -1;
+  for (uint32_t k = 0; k < nsus; k++) {  // a top-level key with an escape: the exact engine decodes and compares it
+    const uint32_t kk = s.mem(2 * (kFastMaxMembers - 1 - k));
+    if (any_backslash_bytes(doc, kk & 0xffffu, (kk & 0xffffu) + (kk >> 16))) return -1;
+  }
   return (int)nmem;
 }
 
@@ -398,25 +459,16 @@ ARKS_HD bool fast_inner_object(const uint8_t* doc, const FastScratch& s, uint32_
   tc.init(s, nch, open + 1);
   for (uint32_t it = 0; !done; it += kFastAhead) {
     if (it >= kFastMiniCap) return false;
-    uint32_t pos[kFastAhead], by[kFastAhead];
-    int n = 0;
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int q = 0; q < kFastAhead; q++) {
-      pos[q] = 0;
-      const bool have = tc.next(s, &pos[q]);
-      by[q] = have ? doc[pos[q]] : 0u;
-      n += have;
-    }
+    TokBatch tk;
+    const int n = tk.fetch(tc, s, doc);
     if (n == 0) return false;
 #ifdef __CUDA_ARCH__
-#pragma unroll
+#pragma unroll 1
 #endif
-    for (int q = 0; q < kFastAhead; q++) {
-      if (q >= n || done || !ok) continue;
-      const uint32_t p = pos[q];
-      const uint8_t b = (uint8_t)by[q];
+    for (int q = 0; q < n; q++) {
+      if (done || !ok) continue;
+      const uint32_t p = tk.pos(q);
+      const uint8_t b = (uint8_t)tk.byte(q);
       if (in_str) {  // the closing quote
         in_str = 0;
         if (is_key) {
@@ -567,7 +619,7 @@ inline bool fast_scan_host(const uint8_t* doc, uint32_t len, FastOut& out) {
     for (int q = 0; q < 8; q++) w[q] = wn[q];
   }
   if (c.bad || c.in_str) return false;
-  const int nmem = fast_walk(doc, kFastTablesHost.t, s, nch, KIND == K_REQ ? kFastKeyLensReq : kFastKeyLensResp);
+  const int nmem = fast_walk<0>(doc, kFastTablesHost.t, s, nch, KIND == K_REQ ? kFastKeyLensReq : kFastKeyLensResp);
   if (nmem < 0) return false;
   return fast_members<KIND>(doc, s, nch, nmem, out);
 }

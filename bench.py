@@ -173,6 +173,26 @@ def physical_cores():
     return sorted(out)
 
 
+def cpu_quota():
+    """CPUs this container may use at once: the cgroup's CFS quota (cpu.max, v2; cpu.cfs_quota_us, v1) if there is one. A
+    process that runs more busy threads than this is throttled — the kernel stops the WHOLE group for the rest of each
+    100 ms period — which is what made the CPU arm swing 3.5x between boxes in round 1 (16-CPU quota on a 128-thread host)."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            return max(1, int(int(q) / int(per)))
+    except (OSError, ValueError):
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            return max(1, q // per)
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def choose_threads(o, req, resp, now):
     """The threaded oracle is memory- and barrier-bound: more threads than physical cores of one socket rarely help and
     often hurt (round 1: 2.75 M vs 8.45 M req/s on two boxes of the same type because the count was picked from 4 noisy
@@ -181,8 +201,12 @@ def choose_threads(o, req, resp, now):
     cores = physical_cores()
     sock0 = [c for p, c in cores if p == cores[0][0]]
     allc = [c for _, c in cores]
+    quota = cpu_quota()
+    cap = (lambda cpus: cpus[:quota]) if quota else (lambda cpus: cpus)  # more busy threads than the quota get the group throttled
     cands = []
-    for cpus in (sock0, sock0[:max(1, len(sock0) // 2)], sock0[:max(1, len(sock0) // 4)], allc, allc[:max(1, len(allc) // 2)]):
+    for cpus in (sock0, sock0[:max(1, len(sock0) // 2)], sock0[:max(1, len(sock0) // 4)], allc, allc[:max(1, len(allc) // 2)],
+                 sock0[:max(1, (quota or len(sock0)) // 2)]):
+        cpus = cap(cpus)
         if cpus and cpus not in cands:
             cands.append(cpus)
     everything = set(os.sched_getaffinity(0))
@@ -245,9 +269,10 @@ def cpu_arm(args, world, seconds=None, steps=None, warmup=0):
     import orklib
     w, req = sharded_reference_workload(args, world)
     o = orklib.Oracle(w.tables)
-    a = o.request_batch(req, threads=os.cpu_count() or 1)
+    n_any = min(os.cpu_count() or 1, cpu_quota() or 1 << 30)
+    a = o.request_batch(req, threads=n_any)
     resp = w.response_batch(a, NOW0 + 1, seed=2000, body_size=RESP_BODY, varied=True, n_templates=N_TEMPL or (0 if world == 1 else 4096))
-    o.response_batch(resp, threads=os.cpu_count() or 1)
+    o.response_batch(resp, threads=n_any)
     cpus, rates, now, everything = choose_threads(o, req, resp, NOW0 + STEP_S)
     threads = len(cpus)
     for _ in range(warmup):
@@ -268,7 +293,8 @@ def cpu_arm(args, world, seconds=None, steps=None, warmup=0):
     os.sched_setaffinity(0, everything)
     sample = (f"{n_steps} steps of {req.n} requests + {resp.n} responses ({world} tenant shard(s) of {args.tenants} tenants); "
               f"oracle/libarks_oracle.so = C restatement of the Go path, in-memory counters, no Redis; {threads} worker threads "
-              f"pinned to physical cores {cpus[0]}..{cpus[-1]}; candidates (median of 5 waves each): {json.dumps(rates)}")
+              f"pinned to physical cores {cpus[0]}..{cpus[-1]}; cgroup CPU quota {cpu_quota() or 'none'} (candidates are capped at it: more busy "
+              f"threads get the whole group throttled); candidates (median of 5 waves each): {json.dumps(rates)}")
     return {"value": done / t_used, "unit": "req/s", "cores": threads, "kind": "port", "sample": sample}, t_used / max(n_steps, 1)
 
 
@@ -495,7 +521,11 @@ def run_b200(args):
                                 np.ascontiguousarray(mat).reshape(-1), (np.arange(n + 1, dtype=np.uint64) * L).astype(np.uint32), now,
                                 distinct.pick_rand[idx].copy())
 
-    hb.open_loop_requests(arrivals(8000, 1), rate_per_s=400_000, producers=8)  # warm-up: first launches, page faults
+    # generator threads spin; together with every rank's dispatcher they must fit the container's CPU quota, or the kernel
+    # throttles the whole group for milliseconds at a time and the tail measures that
+    quota = cpu_quota()
+    producers = 8 if not quota else max(2, min(8, quota // world - 2))
+    hb.open_loop_requests(arrivals(8000, 1), rate_per_s=400_000, producers=producers)  # warm-up: first launches, page faults
     streams_lat, open_lat = {}, {}
     for streams in ((1, 64) if rank == 0 else ()):
         n_calls = {1: 2000, 64: 40000}[streams]
@@ -514,7 +544,7 @@ def run_b200(args):
         barrier()  # every GPU's batcher is under load at the same time
         hb.reset_tail()
         before = hb.stats()
-        dec, lat_ns, wall = hb.open_loop_requests(load, rate_per_s=rate, producers=8)
+        dec, lat_ns, wall = hb.open_loop_requests(load, rate_per_s=rate, producers=producers)
         after = hb.stats()
         lat_us = np.sort(lat_ns[n_calls // 20:]) / 1e3
         call_us = np.sort(hb.last_call_latency[n_calls // 20:]) / 1e3
@@ -525,6 +555,7 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             q = [float(x) for x in t]
         open_lat[str(rate)] = {"p50_us": q[0], "p99_us": q[1], "p999_us": q[2], "requests_per_gpu": n_calls, "gpus_loaded_at_once": world,
+                               "generator_threads_per_gpu": producers, "cpu_quota": quota,
                                "achieved_req_per_s_rank0": n_calls / wall, "mean_batch_rank0": n_calls / cyc,
                                "us_per_cycle_rank0": {k: round((after["ns_" + k] - before["ns_" + k]) / cyc / 1e3, 1) for k in ("submit", "device", "deliver")},
                                "admitted_rank0": int((dec["reason"] == 0).sum()),
@@ -536,6 +567,17 @@ def run_b200(args):
                                "generator_rank0": hb.open_loop_lateness(),
                                "batcher_tail_rank0": {k: (round(v / 1e3, 1) if k.startswith("max") else v) for k, v in after.items()
                                                       if k.startswith(("max_ns", "slow_"))}}
+    # what the compiled host itself can carry: the same generator with no pacing (every producer submits as fast as the
+    # batcher takes rows: one compare-and-swap + the copy of the body into the pinned block per request), decisions delivered
+    # by callback. This is the end-to-end rate of the path a gRPC server would use, per-request staging copies included.
+    host_peak = None
+    if rank == 0:
+        now += STEP_S; hb.set_fixed_clock(now)
+        load = arrivals(1_000_000, 7300)
+        dec, _, wall = hb.open_loop_requests(load, rate_per_s=1e9, producers=producers)
+        st = hb.stats()
+        host_peak = {"req_per_s": 1_000_000 / wall, "producer_threads": producers, "mean_batch": 1_000_000 / max(st["cycles"] - after["cycles"], 1),
+                     "what": "host/cpp Batcher::SubmitRequest from unpaced producer threads, 1 M requests of ~1 KiB, one GPU"}
     hb.close()
 
     # ---- the same step on single-shape traffic (every request / completion the same template, exactly BODY / RESP_BODY
@@ -615,6 +657,7 @@ def run_b200(args):
                        "by_concurrent_streams": streams_lat,
                        "open_loop_by_arrival_rate": open_lat,
                        "open_loop_what": "requests ARRIVE at the given rate per GPU on every GPU at once (exponential gaps, 8 producer threads per GPU) through host/cpp Batcher::SubmitRequest; latency = decision callback - scheduled arrival; worst rank's percentiles; 1 250 000/s per GPU = BASELINE's 10 M req/s over 8 GPUs, target p99 < 200 us",
+                       "host_batcher_peak": host_peak,
                        "numa": numa,
                        "streams_what": "N stream threads, one blocking HandleRequestBody at a time each, through host/cpp Batcher (C++); per-call latency"},
         "gpu_launches": int(launches),
