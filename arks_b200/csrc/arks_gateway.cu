@@ -213,6 +213,12 @@ constexpr uint8_t PS_STREAM = 1;     // "stream": true
 constexpr uint8_t PS_STREAM_OK = 2;  // stream_options.include_usage == true
 constexpr uint8_t PS_BAD = 0x40;     // the body does not decode (400 x-error-request-body-processing)
 
+// one 32-byte chunk with ONE 256-bit load (LDG.E.256, new with sm_100): p must be 32-byte aligned
+__device__ __forceinline__ void ld_nc_v8(const uint4* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
 __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -621,9 +627,23 @@ __device__ __forceinline__ void fast_pass_a(const uint8_t* body, uint32_t len, F
     FastCarry c{0, 0, 0};
     const uint4* p = reinterpret_cast<const uint4*>(body);
     const uint4 z = make_uint4(0, 0, 0, 0);
-    auto lo = [&](uint32_t j) { return j < nch ? ld_nc_v4(p + 2 * j) : z; };
-    auto hi = [&](uint32_t j) { return j < nch && 32 * j + 16 < plen ? ld_nc_v4(p + 2 * j + 1) : z; };  // never past the 16-byte padding
-    uint4 a0 = lo(0), b0 = hi(0), a1 = lo(1), b1 = hi(1), a2 = lo(2), b2 = hi(2), a3 = lo(3), b3 = hi(3);
+    // A body that starts on a 32-byte boundary (every packer of this repository does that; the ABI asks for 16) is read a
+    // whole chunk per load; two 16-byte loads of the same sector were two trips to L2 (ncu: L1 keeps nothing of a .nc load
+    // between them: 27 sectors per request, L1 hit rate 2 %). Reading 16 bytes past a body's padded end stays inside the
+    // staging buffer (allocated with slack) and is masked off by the chunk's valid count.
+    const bool a32 = (reinterpret_cast<uintptr_t>(body) & 31u) == 0;
+    auto ld = [&](uint32_t j, uint4& a, uint4& b) {
+      a = z; b = z;
+      if (j < nch) {
+        if (a32) ld_nc_v8(p + 2 * j, a, b);
+        else {
+          a = ld_nc_v4(p + 2 * j);
+          if (32 * j + 16 < plen) b = ld_nc_v4(p + 2 * j + 1);  // never past the 16-byte padding
+        }
+      }
+    };
+    uint4 a0, b0, a1, b1, a2, b2, a3, b3;
+    ld(0, a0, b0); ld(1, a1, b1); ld(2, a2, b2); ld(3, a3, b3);
     {
       const uint32_t w0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
       ring.put(0, w0);
@@ -633,7 +653,7 @@ __device__ __forceinline__ void fast_pass_a(const uint8_t* body, uint32_t len, F
     for (uint32_t j = 0; j < nch; j++) {
       const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
       a0 = a1; b0 = b1; a1 = a2; b1 = b2; a2 = a3; b2 = b3;
-      a3 = lo(j + 4); b3 = hi(j + 4);
+      ld(j + 4, a3, b3);
       {
         const uint32_t wn[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
         ring.put(j + 1, wn);  // the chunk after the current one is at hand too (a \uXXXX may straddle the boundary)
@@ -705,11 +725,16 @@ __global__ void __launch_bounds__(kFastThreads) fast_request_kernel(DevTables T,
     const uint32_t i = in ? (B.perm ? B.perm[base + a] : base + a) : 0;
     fast_pass_a(B.bodies + (in ? B.body_off[i] : 0), in && !(regroup & 512) ? B.body_len[i] : 0u, sm);
     sm.slot[threadIdx.x] = a;
-    __syncthreads();
   }
   if (regroup & 256) return;  // timing experiments only (ARKS_REGROUP=257): pass A alone, no results
   regroup &= 255;
-  const uint32_t u = fast_block_order(sm, min(sm.hand[4 * kFastThreads + threadIdx.x] >> 2, 63u), regroup > 1);  // column
+  // With the length order alone every thread goes on with the document it scanned — no barrier: the warps with the short
+  // documents are in pass B while the long ones still scan. Regrouping by structure (2) needs everybody's pass A first.
+  uint32_t u = threadIdx.x;
+  if (regroup > 1) {
+    __syncthreads();
+    u = fast_block_order(sm, min(sm.hand[4 * kFastThreads + threadIdx.x] >> 2, 63u), true);  // column
+  }
   const uint32_t lane_id = base + sm.slot[u];
   if (lane_id >= B.n) return;
   const uint32_t i = B.perm ? B.perm[lane_id] : lane_id;
@@ -1221,11 +1246,14 @@ __global__ void __launch_bounds__(kFastThreads) fast_response_kernel(DevTables T
     const bool scan = in && (B.flags[i] & ARKS_RESP_END_OF_STREAM) && B.qos[i] >= 0;
     fast_pass_a(B.bodies + (scan ? B.body_off[i] : 0), scan ? B.body_len[i] : 0u, sm);
     sm.slot[threadIdx.x] = a;
-    __syncthreads();
   }
   if (regroup & 256) return;  // timing experiments only: pass A alone
   regroup &= 255;
-  const uint32_t u = fast_block_order(sm, min(sm.hand[4 * kFastThreads + threadIdx.x] >> 2, 63u), regroup > 1);
+  uint32_t u = threadIdx.x;
+  if (regroup > 1) {
+    __syncthreads();
+    u = fast_block_order(sm, min(sm.hand[4 * kFastThreads + threadIdx.x] >> 2, 63u), true);
+  }
   const uint32_t lane_id = base + sm.slot[u];
   const bool in = lane_id < B.n;
   const uint32_t i = in ? (B.perm ? B.perm[lane_id] : lane_id) : 0;
@@ -2331,7 +2359,7 @@ static int roll_windows(arks_ctx* ctx, int64_t now) {
 static int ensure_slot(arks_ctx* ctx, int k, bool want_req, bool want_resp) {
   arks_ctx::Slot& sl = ctx->slots[k];
   if (want_req && !sl.d_req_bodies) {
-    CK(cudaMalloc(&sl.d_req_bodies, ctx->max_bytes));
+    CK(cudaMalloc(&sl.d_req_bodies, ctx->max_bytes + 64));  // + slack: the fast path reads whole 32-byte chunks
     CK(cudaMalloc(&sl.d_req_meta, ctx->meta_cap));
     CK(cudaMallocHost(&sl.h_req_meta, ctx->meta_cap));
     CK(cudaEventCreateWithFlags(&sl.req_copied, cudaEventDisableTiming));
@@ -2340,7 +2368,7 @@ static int ensure_slot(arks_ctx* ctx, int k, bool want_req, bool want_resp) {
     CK(cudaEventCreateWithFlags(&sl.req_ran, cudaEventDisableTiming));
   }
   if (want_resp && !sl.d_resp_bodies) {
-    CK(cudaMalloc(&sl.d_resp_bodies, ctx->max_bytes));
+    CK(cudaMalloc(&sl.d_resp_bodies, ctx->max_bytes + 64));
     CK(cudaMalloc(&sl.d_resp_meta, ctx->meta_cap));
     CK(cudaMallocHost(&sl.h_resp_meta, ctx->meta_cap));
     CK(cudaEventCreateWithFlags(&sl.resp_copied, cudaEventDisableTiming));

@@ -163,10 +163,13 @@ ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const FastRing& ri
   while (e) {  // rare: what follows each backslash must be an escape RFC 8259 knows
     const uint32_t p = base + first_set(e);
     e &= e - 1;
-    const uint8_t ch = ring.byte_at(p);
+    const uint32_t ch = ring.byte_at(p);
+    // " \ / b f n r t as one bit test (bytes 0x20..0x7f: a bit per byte in three words); u needs four hex digits
+    const uint32_t okw = ch < 0x40 ? 0x00008004u : ch < 0x60 ? 0x10000000u : ch < 0x80 ? 0x00144044u : 0u;  // 0x20-0x3f | 0x40-0x5f | 0x60-0x7f
+    const bool simple = ch >= 0x20 && ((okw >> (ch & 31u)) & 1u);
     if (ch == 'u') {
       if (p + 4 >= len || !four_hex(ring.four_at(p + 1))) bad = 1;
-    } else if (!(ch == '"' || ch == '\\' || ch == '/' || ch == 'b' || ch == 'f' || ch == 'n' || ch == 'r' || ch == 't')) {
+    } else if (!simple) {
       bad = 1;
     }
   }

@@ -22,7 +22,8 @@ constexpr uint8_t kReasonHostError = 255;
 constexpr int kSlots = 4;           // staging slots of the library: batches in flight on the device
 constexpr int kBlocks = kSlots + 3; // host staging blocks per kind: in flight + open (two for responses) + one being handed back
 
-inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+// rows start on 32-byte boundaries: the ABI asks for 16, the library reads 32-aligned bodies with 256-bit loads
+inline size_t align16(size_t x) { return (x + 31) & ~size_t(31); }
 
 template <class T>
 T* pinned(size_t n) {  // page-locked so the library's cudaMemcpyAsync is a real DMA; falls back to pageable memory

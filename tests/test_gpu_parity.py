@@ -322,6 +322,13 @@ def test_two_stage_scan_fuzzed_and_plain_documents(gwmod):
     wave = w.request_batch(8192, NOW + 2, seed=5, varied=True)
     same(g.handle_request_body(wave), o.request_batch(wave), "plain wave")
     assert g.last_declined == 0
+    # the same bodies packed on 16-byte boundaries (all the ABI asks for): half of them start in the middle of a 32-byte
+    # sector and are read with two 16-byte loads instead of one 256-bit load
+    bb, bo, bl = abi.pack_blobs(bodies, align=16)
+    assert (bo % 32 == 16).sum() > 1000
+    req16 = RequestBatch(bb, bo, bl, req.tokens, req.token_off, NOW + 3, req.pick_rand)
+    same(g.handle_request_body(req16), o.request_batch(req16), "two-stage requests, 16-byte packing")
+    state_same(g, o, NOW + 3)
 
 
 @pytest.mark.parametrize("seed", [95, 96])
