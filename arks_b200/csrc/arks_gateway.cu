@@ -425,6 +425,38 @@ __device__ __forceinline__ int32_t lookup_token(const DevTables& T, const ReqDev
   }
 }
 
+// The same lookup in two halves for kernels that have other work to put in between (the fast path: hash and first probe before
+// pass A, the string compare after pass C — the two dependent round trips to L2 then run under the scan instead of after it).
+struct TokProbe {
+  unsigned long long h;
+  uint32_t s;
+  TokSlot e;
+};
+__device__ __forceinline__ TokProbe lookup_token_begin(const DevTables& T, const ReqDev& B, uint32_t i) {
+  const uint8_t* tk = B.tokens + B.token_off[i];
+  const uint32_t tkl = B.token_off[i + 1] - B.token_off[i];
+  TokProbe p;
+  p.h = fnv1a64(tk, tkl);
+  p.s = (uint32_t)p.h & T.tok_mask;
+  p.e = T.tok_slots[p.s];
+  return p;
+}
+__device__ __forceinline__ int32_t lookup_token_end(const DevTables& T, const ReqDev& B, uint32_t i, TokProbe p) {
+  const uint8_t* tk = B.tokens + B.token_off[i];
+  const uint32_t tkl = B.token_off[i + 1] - B.token_off[i];
+  for (;;) {
+    if (p.e.tok < 0) return -1;
+    if (p.e.hash == p.h && T.tok_str_len[p.e.tok] == tkl) {
+      const uint8_t* q = T.pool + T.tok_str_off[p.e.tok];
+      uint32_t diff = 0;
+      for (uint32_t k = 0; k < tkl; k++) diff |= (uint32_t)(q[k] ^ tk[k]);
+      if (diff == 0) return p.e.tok;
+    }
+    p.s = (p.s + 1) & T.tok_mask;
+    p.e = T.tok_slots[p.s];
+  }
+}
+
 // Everything HandleRequestBody decides after the body is decoded and before the limiter (handle_request.go:106-171):
 // model present, token known, model in the token's qos list, model an endpoint of the namespace, stream options; then the
 // registration in the batch-local group table. `pstate`: PS_* of the body, (m_start, m_rawlen, m_esc): its model span.
@@ -717,17 +749,21 @@ __global__ void __launch_bounds__(kFastThreads) fast_request_kernel(DevTables T,
   FastBlockSmem& sm = *reinterpret_cast<FastBlockSmem*>(smem);
   stage_fast_tables(&sm.tabs, &sm.bar);
   const uint32_t base = blockIdx.x * blockDim.x;
+  TokProbe probe{};
   {
     const uint32_t own = base + threadIdx.x;
     const uint32_t len0 = own < B.n ? B.body_len[B.perm ? B.perm[own] : own] : 0u;
     const uint32_t a = fast_block_order(sm, min((len0 + 31) >> 5, 63u), regroup != 0);  // the document pass A scans here
     const bool in = base + a < B.n;
     const uint32_t i = in ? (B.perm ? B.perm[base + a] : base + a) : 0;
+    if (in && (regroup & 127) < 2) probe = lookup_token_begin(T, B, i);  // consumed after pass C (same thread, same document)
     fast_pass_a(B.bodies + (in ? B.body_off[i] : 0), in && !(regroup & 512) ? B.body_len[i] : 0u, sm);
     sm.slot[threadIdx.x] = a;
   }
   if (regroup & 256) return;  // timing experiments only (ARKS_REGROUP=257): pass A alone, no results
   regroup &= 255;
+  const int notail = regroup & 128;
+  regroup &= 127;
   // With the length order alone every thread goes on with the document it scanned — no barrier: the warps with the short
   // documents are in pass B while the long ones still scan. Regrouping by structure (2) needs everybody's pass A first.
   uint32_t u = threadIdx.x;
@@ -745,11 +781,13 @@ __global__ void __launch_bounds__(kFastThreads) fast_request_kernel(DevTables T,
     B.slow_list[atomicAdd(B.slow_n, 1u) + 1u] = i;
     return;
   }
+  if (notail) { B.model_off[i] = o.m_start + o.stream3 + o.iu3; return; }  // timing experiments only: no tail
   B.model_off[i] = o.m_rawlen ? o.m_start : 0u;
   B.model_len[i] = o.m_rawlen ? (o.m_rawlen | (o.m_esc ? 0x80000000u : 0u)) : 0u;
   B.bpe[i] = 0;
   const uint8_t pstate = (uint8_t)((o.stream3 == 2 ? PS_STREAM : 0) | (o.so_present && o.iu3 == 2 ? PS_STREAM_OK : 0));
-  const int32_t tok = o.m_rawlen ? lookup_token(T, B, i) : -1;
+  // with regrouping by structure (2) another thread scanned this document: look the token up from scratch
+  const int32_t tok = !o.m_rawlen ? -1 : regroup < 2 ? lookup_token_end(T, B, i, probe) : lookup_token(T, B, i);
   resolve_request(T, B, i, body, tok, pstate, o.m_start, o.m_rawlen, o.m_esc);
 }
 

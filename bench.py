@@ -327,6 +327,11 @@ def workload_config(args, world):
 
 
 def run_b200(args):
+    # stdout carries exactly one JSON line: libraries that announce themselves there (NCCL prints its version on stdout when
+    # NCCL_DEBUG asks for it, from torch's communicator as from the library's own) are sent to stderr for the whole run
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import __graft_entry__ as ge
     rank, local, world = env_rank()
@@ -353,16 +358,8 @@ def run_b200(args):
         if world > 1:
             dist.broadcast_object_list(box, src=0)
         n_shared = min(args.shared_quota, w.tables.n_quotas)
-        # libnccl announces its version on stdout when NCCL_DEBUG asks for it; stdout carries exactly one JSON line
-        sys.stdout.flush()
-        keep = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            g.comm_init(rank, world, box[0], np.arange(n_shared, dtype=np.uint32))
-            g.fold_quota_allreduce(wait=True)
-        finally:
-            os.dup2(keep, 1)
-            os.close(keep)
+        g.comm_init(rank, world, box[0], np.arange(n_shared, dtype=np.uint32))
+        g.fold_quota_allreduce(wait=True)
     reqs = [pin_batch(b) for b in build_waves(w, N_WAVES, args.wave, rank)]
     # dry pass to learn which requests are admitted in a fresh window, then build the matching response waves
     resps = []
@@ -388,12 +385,12 @@ def run_b200(args):
         g.stage_response(resps[k])
     torch.cuda.synchronize()
 
-    def resident_step(i, now):
+    def resident_step(i, now, fold=True):
         k = i % N_WAVES
         g.select_slot(k)
         g.run_request(now)
         g.run_response(now + 1)
-        if args.shared_quota and i % args.fold_every == args.fold_every - 1:
+        if fold and args.shared_quota and i % args.fold_every == args.fold_every - 1:
             g.fold_quota_allreduce(wait=False)  # stream-ordered behind this step's kernels; nobody waits on the host
 
     for i in range(args.warmup):
@@ -405,7 +402,7 @@ def run_b200(args):
     t_spin = time.perf_counter()
     i = 0
     while time.perf_counter() - t_spin < 0.6:
-        resident_step(i, now)
+        resident_step(i, now, fold=False)  # a wall-clock loop: its length differs per rank, a collective inside would not pair up
         now += STEP_S
         i += 1
     barrier()
@@ -527,7 +524,7 @@ def run_b200(args):
     producers = 8 if not quota else max(2, min(8, quota // world - 2))
     hb.open_loop_requests(arrivals(8000, 1), rate_per_s=400_000, producers=producers)  # warm-up: first launches, page faults
     streams_lat, open_lat = {}, {}
-    for streams in ((1, 64) if rank == 0 else ()):
+    for streams in ((1, 64) if rank == 0 and args.latency_requests else ()):
         n_calls = {1: 2000, 64: 40000}[streams]
         now += STEP_S; hb.set_fixed_clock(now)
         before = hb.stats()
@@ -537,7 +534,7 @@ def run_b200(args):
         nb = after["request_batches"] - before["request_batches"]
         streams_lat[str(streams)] = {"p50_us": float(lat_us[len(lat_us) // 2]), "p99_us": float(lat_us[int(len(lat_us) * 0.99)]),
                                      "req_per_s": n_calls / wall, "mean_batch": n_calls / max(nb, 1)}
-    for rate in (250_000, 1_250_000):
+    for rate in ((250_000, 1_250_000) if args.latency_requests else ()):
         n_calls = int(rate * 0.4) if rate < 1_000_000 else args.latency_requests
         now += STEP_S; hb.set_fixed_clock(now)
         load = arrivals(n_calls, 7200 + rate % 97 + rank)
@@ -571,7 +568,7 @@ def run_b200(args):
     # batcher takes rows: one compare-and-swap + the copy of the body into the pinned block per request), decisions delivered
     # by callback. This is the end-to-end rate of the path a gRPC server would use, per-request staging copies included.
     host_peak = None
-    if rank == 0:
+    if rank == 0 and args.latency_requests:
         now += STEP_S; hb.set_fixed_clock(now)
         load = arrivals(1_000_000, 7300)
         dec, _, wall = hb.open_loop_requests(load, rate_per_s=1e9, producers=producers)
@@ -678,7 +675,7 @@ def run_b200(args):
         out["config"]["parallelism"] += f" + {shared_quota['rows']} shared quotas folded every {args.fold_every} steps"
     if not args.no_cpu_baseline:
         out["cpu_baseline"], _ = cpu_arm(args, 1, seconds=12.0)
-    print(json.dumps(out))
+    print(json.dumps(out), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
