@@ -476,8 +476,16 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     now = e2e_steps(args.steps, now)
+    torch.cuda.synchronize()
+    own_e2e_s = time.perf_counter() - t0  # this rank's own finish (the job's time is taken after the barrier)
     barrier()
     e2e_s = time.perf_counter() - t0
+    rank_e2e_s = [own_e2e_s]
+    if world > 1:
+        t = torch.tensor([own_e2e_s], device=f"cuda:{local}", dtype=torch.float64)
+        got = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(got, t)
+        rank_e2e_s = [float(x[0]) for x in got]
     clocks = sampler.stop()  # sampled across both timed regions (kernel-only and end-to-end)
     assert int((req_out[0].reason == 0).sum()) > 0  # the decisions really came back
 
@@ -648,6 +656,9 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "req/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / args.steps,
+                # what every GPU's uploads ran at while all of them were uploading (names the limiter when the curve bends:
+                # ~55 GB/s is one PCIe Gen5 x16 link; less on every rank at once = the host side of the links)
+                "h2d_GBps_per_rank": [round(h2d * args.steps / t_ / 1e9, 1) for t_ in rank_e2e_s],
                 "note": "pinned host buffers; asynchronous submits, two batches in flight; PCIe-bound"},
         "latency_us": {"what": "one synchronous request micro-batch through the C ABI (H2D + 2 kernels + D2H), host wall clock",
                        "by_batch_size": latency,
