@@ -174,7 +174,9 @@ ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const FastRing& ri
     }
   }
   c.bad |= bad;
-  *tb_out = V & ~(R & ~Qu);
+  // bytes outside strings, plus the OPENING quote of every string (R covers a string from its opening quote to the byte
+  // before its closing quote; the closing quote is not a token: whatever follows it is, so "closing quote = next token - 1")
+  *tb_out = V & ~(R & ~Qu) & ~(Qu & ~R);
   *bm_out = B;
 }
 
@@ -214,7 +216,7 @@ constexpr uint16_t fast_after(uint32_t c) {
        : c == C_RBRACK ? fast_entry(G_AFTER, A_POP_ARR) : fast_entry(G_ERR, A_ERR);
 }
 constexpr uint16_t fast_value_start(uint32_t c) {
-  return c == C_QUOTE ? fast_entry(G_STRV, A_NONE, F_VALSTART) : c == C_LBRACE ? fast_entry(G_OBJ0, A_PUSH_OBJ, F_VALSTART)
+  return c == C_QUOTE ? fast_entry(G_AFTER, A_NONE, F_VALSTART) : c == C_LBRACE ? fast_entry(G_OBJ0, A_PUSH_OBJ, F_VALSTART)
        : c == C_LBRACK ? fast_entry(G_ARR0, A_PUSH_ARR, F_VALSTART) : c == C_t ? fast_entry(G_T1, A_NONE, F_VALSTART)
        : c == C_f ? fast_entry(G_F1, A_NONE, F_VALSTART) : c == C_n ? fast_entry(G_N1, A_NONE, F_VALSTART)
        : c == C_MINUS ? fast_entry(G_NM, A_NONE, F_VALSTART) : c == C_ZERO ? fast_entry(G_NZ, A_NONE, F_VALSTART)
@@ -226,13 +228,12 @@ constexpr uint16_t fast_transition(uint32_t g, uint32_t c) {
     case G_TOP:   return c == C_WS ? fast_entry(G_TOP) : c == C_LBRACE ? fast_entry(G_OBJ0, A_PUSH_OBJ) : fast_entry(G_ERR, A_ERR);
     case G_VAL:   return c == C_WS ? fast_entry(G_VAL) : fast_value_start(c);
     case G_ARR0:  return c == C_WS ? fast_entry(G_ARR0) : c == C_RBRACK ? fast_entry(G_AFTER, A_POP_ARR) : fast_value_start(c);
-    case G_OBJ0:  return c == C_WS ? fast_entry(G_OBJ0) : c == C_QUOTE ? fast_entry(G_STRK, A_NONE, F_KEYSTART)
+    case G_OBJ0:  return c == C_WS ? fast_entry(G_OBJ0) : c == C_QUOTE ? fast_entry(G_COLON, A_NONE, F_KEYSTART)
                        : c == C_RBRACE ? fast_entry(G_AFTER, A_POP_OBJ) : fast_entry(G_ERR, A_ERR);
-    case G_KEY:   return c == C_WS ? fast_entry(G_KEY) : c == C_QUOTE ? fast_entry(G_STRK, A_NONE, F_KEYSTART) : fast_entry(G_ERR, A_ERR);
+    case G_KEY:   return c == C_WS ? fast_entry(G_KEY) : c == C_QUOTE ? fast_entry(G_COLON, A_NONE, F_KEYSTART) : fast_entry(G_ERR, A_ERR);
     case G_COLON: return c == C_WS ? fast_entry(G_COLON) : c == C_COLON ? fast_entry(G_VAL) : fast_entry(G_ERR, A_ERR);
     case G_AFTER: return fast_after(c);
-    case G_STRK:  return c == C_QUOTE ? fast_entry(G_COLON, A_NONE, F_KEYEND) : fast_entry(G_ERR, A_ERR);  // only the closing quote
-    case G_STRV:  return c == C_QUOTE ? fast_entry(G_AFTER) : fast_entry(G_ERR, A_ERR);                    // is a token in a string
+    // a string is ONE token, its opening quote (pass A leaves the closing quote out): G_STRK / G_STRV are never entered
     case G_T1: return c == C_r ? fast_entry(G_T2) : fast_entry(G_ERR, A_ERR);
     case G_T2: return c == C_u ? fast_entry(G_T3) : fast_entry(G_ERR, A_ERR);
     case G_T3: return c == C_e ? fast_entry(G_AFTER) : fast_entry(G_ERR, A_ERR);
@@ -365,7 +366,7 @@ static_assert(kFastAhead == 8 && kFastMaxLen <= 65536, "TokBatch packs 8 positio
 // loop over a packed batch (the instruction cache's friend). Same results; which one is faster is a measurement.
 template <int WALK>
 ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, const FastScratch& s, uint32_t nch, uint32_t key_lens) {
-  uint32_t g = G_TOP, depth = 0, stack = 0, nmem = 0, nsus = 0, kstart = 0, pending = 0, bad = 0;
+  uint32_t g = G_TOP, depth = 0, stack = 0, nmem = 0, nsus = 0, kstart = 0, pending = 0, bad = 0, keyopen = 0;
   const uint64_t bs64 = (uint64_t)s.bs_hi << 32 | s.bs_lo;
   TokCursor tc;
   tc.init(s, nch, 0);
@@ -377,27 +378,28 @@ ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, const FastScratch
     const uint32_t act = (e >> 5) & 7u;
     g = e & 31u;
     const bool top_obj = depth && ((stack >> (depth - 1)) & 1u);
-    // members of the top-level object: key span and the first byte of the value (depth is still the one BEFORE a push)
-    if ((e & (F_KEYSTART | F_KEYEND | F_VALSTART)) && depth == 1) {
-      if (e & F_KEYSTART) kstart = pq + 1;
-      if (e & F_KEYEND) {
-        const uint32_t klen = pq - kstart;
-        pending = 0;
-        if (klen < 32 && (key_lens >> klen & 1u)) {  // pass C compares it (and checks it for escapes)
+    // members of the top-level object: key span and the first byte of the value (depth is still the one BEFORE a push).
+    // A key is one token (its opening quote); it ends one byte before whatever token comes next.
+    if (keyopen) {  // this token is the first after a top-level key: the key's closing quote sits right before it
+      keyopen = 0;
+      const uint32_t klen = pq - 1 - kstart;
+      if (klen < 32 && (key_lens >> klen & 1u)) {  // pass C compares it (and checks it for escapes)
+        if (nmem + nsus >= kFastMaxMembers) bad = 1;
+        else { s.mem(2 * nmem) = kstart | klen << 16; pending = 1; }
+      } else if (klen) {
+        // another length: only an escape could make it spell a name that is read. The chunks it lies in are tested
+        // here without a loop; the few keys that share a chunk with a backslash are parked (from the top of the
+        // member log down) and looked at byte by byte after the walk, outside this loop
+        const uint32_t c0 = kstart >> 5, c1 = (pq - 2) >> 5;
+        const uint64_t m = (~0ull << c0) & (~0ull >> (63 - c1));
+        if (bs64 & m) {
           if (nmem + nsus >= kFastMaxMembers) bad = 1;
-          else { s.mem(2 * nmem) = kstart | klen << 16; pending = 1; }
-        } else if (klen) {
-          // another length: only an escape could make it spell a name that is read. The chunks it lies in are tested
-          // here without a loop; the few keys that share a chunk with a backslash are parked (from the top of the
-          // member log down) and looked at byte by byte after the walk, outside this loop
-          const uint32_t c0 = kstart >> 5, c1 = (pq - 1) >> 5;
-          const uint64_t m = (~0ull << c0) & (~0ull >> (63 - c1));
-          if (bs64 & m) {
-            if (nmem + nsus >= kFastMaxMembers) bad = 1;
-            else { s.mem(2 * (kFastMaxMembers - 1 - nsus)) = kstart | klen << 16; nsus++; }
-          }
+          else { s.mem(2 * (kFastMaxMembers - 1 - nsus)) = kstart | klen << 16; nsus++; }
         }
       }
+    }
+    if ((e & (F_KEYSTART | F_VALSTART)) && depth == 1) {
+      if (e & F_KEYSTART) { kstart = pq + 1; keyopen = 1; pending = 0; }
       if ((e & F_VALSTART) && pending) { s.mem(2 * nmem + 1) = pq; nmem++; pending = 0; }
     }
     if (act == A_PUSH_OBJ || act == A_PUSH_ARR) {
@@ -455,7 +457,7 @@ ARKS_HD int fast_walk(const uint8_t* doc, const FastTables& T, const FastScratch
 // the members of the object whose '{' is at `open`, for stream_options (K_REQ) / usage (K_RESP); false: not in the subset
 template <int KIND>
 ARKS_HD bool fast_inner_object(const uint8_t* doc, const FastScratch& s, uint32_t nch, uint32_t open, FastOut& o) {
-  uint32_t rel = 1, in_str = 0, is_key = 0, expect_key = 1, ks = 0, seen = 0, nd = 0, ok = 1, done = 0;
+  uint32_t rel = 1, keyopen = 0, expect_key = 1, ks = 0, seen = 0, nd = 0, ok = 1, done = 0;
   int which = -1;  // the member whose value is being read: 0..2 usage counters, 3 include_usage
   int64_t acc = 0;
   TokCursor tc;
@@ -472,32 +474,26 @@ ARKS_HD bool fast_inner_object(const uint8_t* doc, const FastScratch& s, uint32_
       if (done || !ok) continue;
       const uint32_t p = tk.pos(q);
       const uint8_t b = (uint8_t)tk.byte(q);
-      if (in_str) {  // the closing quote
-        in_str = 0;
-        if (is_key) {
-          const uint32_t len = p - ks;
-          if (any_backslash(doc, s, ks, p)) { ok = 0; continue; }  // may be an escaped spelling of a name that is read
-          which = -1;
-          if (KIND == K_REQ) {
-            if (len == 13 && key_is_fold(doc, ks, len, "include_usage")) which = 3;
-          } else {
-            if (len == 13 && key_is(doc, ks, len, "prompt_tokens")) which = 0;
-            else if (len == 17 && key_is(doc, ks, len, "completion_tokens")) which = 1;
-            else if (len == 12 && key_is(doc, ks, len, "total_tokens")) which = 2;
-          }
-          if (which >= 0) {
-            if (seen & (1u << which)) { ok = 0; continue; }  // duplicates: exact engine
-            seen |= 1u << which;
-            acc = 0; nd = 0;
-          }
+      if (keyopen) {  // the first token after a key of this object: the key ended one byte before its closing quote
+        keyopen = 0;
+        const uint32_t len = p - 1 - ks;
+        if (any_backslash(doc, s, ks, p - 1)) { ok = 0; continue; }  // may be an escaped spelling of a name that is read
+        which = -1;
+        if (KIND == K_REQ) {
+          if (len == 13 && key_is_fold(doc, ks, len, "include_usage")) which = 3;
+        } else {
+          if (len == 13 && key_is(doc, ks, len, "prompt_tokens")) which = 0;
+          else if (len == 17 && key_is(doc, ks, len, "completion_tokens")) which = 1;
+          else if (len == 12 && key_is(doc, ks, len, "total_tokens")) which = 2;
         }
-        continue;
+        if (which >= 0) {
+          if (seen & (1u << which)) { ok = 0; continue; }  // duplicates: exact engine
+          seen |= 1u << which;
+          acc = 0; nd = 0;
+        }
       }
-      if (b == '"') {
-        in_str = 1;
-        is_key = rel == 1 && expect_key;
-        ks = p + 1;
-        if (is_key) expect_key = 0;
+      if (b == '"') {  // a whole string (strings are one token)
+        if (rel == 1 && expect_key) { expect_key = 0; keyopen = 1; ks = p + 1; }
         else if (rel == 1 && which >= 0) ok = 0;  // a counter / flag written as a string: exact engine (gjson rules)
         continue;
       }
@@ -562,8 +558,9 @@ ARKS_HD bool fast_members(const uint8_t* doc, const FastScratch& s, uint32_t nch
     const uint8_t vb = doc[vpos];
     if (what == 0) {  // stringCodec: string or null
       if (vb == '"') {
-        const uint32_t end = next_token(s, nch, vpos + 1, 0xffffffffu);  // the closing quote (the next byte outside strings)
-        if (end == 0xffffffffu) return false;
+        const uint32_t after = next_token(s, nch, vpos + 1, 0xffffffffu);  // the first token behind the string ...
+        if (after == 0xffffffffu) return false;
+        const uint32_t end = after - 1;                                      // ... and its closing quote right before it
         o.m_rawlen = end - vpos - 1;
         o.m_start = o.m_rawlen ? vpos + 1 : 0;
         o.m_esc = o.m_rawlen && any_backslash(doc, s, vpos + 1, end) ? 1u : 0u;
