@@ -383,7 +383,8 @@ __device__ __forceinline__ void feed_tiled(M& m, const uint8_t* body, uint32_t b
 
 __device__ __forceinline__ unsigned long long fnv1a64(const uint8_t* p, uint32_t n) {
   unsigned long long h = 0xcbf29ce484222325ull;
-  for (uint32_t i = 0; i < n; i++) h = (h ^ p[i]) * 0x100000001b3ull;
+#pragma unroll 8
+  for (uint32_t i = 0; i < n; i++) h = (h ^ p[i]) * 0x100000001b3ull;  // the loads of a round go out together
   return h;
 }
 
@@ -449,7 +450,8 @@ __device__ __forceinline__ int32_t lookup_token_end(const DevTables& T, const Re
     if (p.e.hash == p.h && T.tok_str_len[p.e.tok] == tkl) {
       const uint8_t* q = T.pool + T.tok_str_off[p.e.tok];
       uint32_t diff = 0;
-      for (uint32_t k = 0; k < tkl; k++) diff |= (uint32_t)(q[k] ^ tk[k]);
+#pragma unroll 8
+      for (uint32_t k = 0; k < tkl; k++) diff |= (uint32_t)(q[k] ^ tk[k]);  // eight pairs of loads in flight per round
       if (diff == 0) return p.e.tok;
     }
     p.s = (p.s + 1) & T.tok_mask;

@@ -385,13 +385,23 @@ def run_b200(args):
         g.stage_response(resps[k])
     torch.cuda.synchronize()
 
+    fold_events, fold_host_us = [], []
+
     def resident_step(i, now, fold=True):
         k = i % N_WAVES
         g.select_slot(k)
         g.run_request(now)
         g.run_response(now + 1)
         if fold and args.shared_quota and i % args.fold_every == args.fold_every - 1:
-            g.fold_quota_allreduce(wait=False)  # stream-ordered behind this step's kernels; nobody waits on the host
+            # stream-ordered behind this step's kernels; nobody waits on the host. Timed on both sides: the device time includes
+            # waiting for the slowest peer to arrive, the host time is what the enqueue costs the launching thread.
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(ext)
+            t_h = time.perf_counter()
+            g.fold_quota_allreduce(wait=False)
+            fold_host_us.append(1e6 * (time.perf_counter() - t_h))
+            ev[1].record(ext)
+            fold_events.append(ev)
 
     for i in range(args.warmup):
         resident_step(i, now)
@@ -428,9 +438,15 @@ def run_b200(args):
             b_.record(ext)
         barrier()
         us = sorted(1e3 * a_.elapsed_time(b_) for a_, b_ in zip(f0, f1))
+        in_loop = sorted(1e3 * a_.elapsed_time(b_) for a_, b_ in fold_events[-(args.steps // args.fold_every):]) or [0.0]
+        host_us = sorted(fold_host_us[-(args.steps // args.fold_every):]) or [0.0]
         shared_quota = {"rows": int(n_shared), "message_bytes": int(n_shared) * 24, "fold_every_steps": args.fold_every,
                         "folds_in_timed_region": args.steps // args.fold_every, "fold_us_p50": round(us[len(us) // 2], 1),
-                        "fold_us_max": round(us[-1], 1), "how": "arks_fold_quota_allreduce: ncclAllReduce(int64, sum) issued by the "
+                        "fold_us_max": round(us[-1], 1),
+                        "in_timed_region": {"device_us_p50": round(in_loop[len(in_loop) // 2], 1), "device_us_max": round(in_loop[-1], 1),
+                                            "host_enqueue_us_p50": round(host_us[len(host_us) // 2], 1), "host_enqueue_us_max": round(host_us[-1], 1),
+                                            "what": "device: CUDA events around the epoch inside the step loop (includes waiting for the "
+                                                    "slowest rank to arrive); host: time the call holds the launching thread"}, "how": "arks_fold_quota_allreduce: ncclAllReduce(int64, sum) issued by the "
                         "library on its compute stream (libnccl dlopen()ed), CUDA events around one epoch"}
     # per-kernel timing for the roofline (separate pass so event records do not sit inside the timed region)
     g.set_profiling(True)

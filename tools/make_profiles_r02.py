@@ -19,7 +19,7 @@ w("Raw CSV: `profiles/launches_r02.csv`. Per-launch times under ncu are cold-cac
 rows = [r for r in csv.reader(open(launches)) if r and r[0].isdigit()]
 agg = collections.defaultdict(list)
 for r in rows:
-    agg[re.sub(r"<.*", "", r[4].split("(")[0]).strip()].append(float(r[-1]))
+    agg[re.sub(r"<.*", "", r[4].split("(")[0]).replace("void ", "").strip()].append(float(r[-1]))
 tot = sum(sum(v) for v in agg.values())
 w("| kernel | launches | mean us (under ncu) | share of kernel time |\n|---|---|---|---|")
 for k, v in sorted(agg.items(), key=lambda t: -sum(t[1])):
@@ -40,7 +40,7 @@ traffic_path = os.path.join(P, "roofline_traffic.json")
 traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
 w("\n## `ncu --set full --clock-control none --import-source on -k regex:fast_re -c 2 python tools/prof_varied.py` (first launch of each kernel: cold caches)\n")
 for r in rr[2:]:
-    name = re.sub(r"<.*", "", r[hdr.index("Kernel Name")].split("(")[0])
+    name = re.sub(r"<.*", "", r[hdr.index("Kernel Name")].split("(")[0]).replace("void ", "").strip()
     w(f"### `{name}`\n")
     w("| metric | value |\n|---|---|")
     for k in want:
