@@ -32,7 +32,7 @@ class BatcherStats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("cycles", "request_batches", "response_batches", "requests", "responses",
                                           "max_request_batch", "max_response_batch", "ns_submit", "ns_device", "ns_deliver",
                                           "max_ns_submit", "max_ns_device", "max_ns_deliver", "max_ns_gap",
-                                          "slow_submit", "slow_device", "slow_deliver", "slow_gap", "ns_fill", "max_ns_fill", "slow_fill")]
+                                          "slow_submit", "slow_device", "slow_deliver", "slow_gap", "ns_fill", "max_ns_fill", "slow_fill", "late_rows")]
 
 
 REQ_DTYPE = np.dtype(RequestDecision)

@@ -587,7 +587,7 @@ def run_b200(args):
                                                    "p999_us": float(call_us[int(len(call_us) * 0.999)])},
                                "generator_rank0": hb.open_loop_lateness(),
                                "batcher_tail_rank0": {k: (round(v / 1e3, 1) if k.startswith("max") else v) for k, v in after.items()
-                                                      if k.startswith(("max_ns", "slow_"))}}
+                                                      if k.startswith(("max_ns", "slow_", "late_"))}}
     # what the compiled host itself can carry: the same generator with no pacing (every producer submits as fast as the
     # batcher takes rows: one compare-and-swap + the copy of the body into the pinned block per request), decisions delivered
     # by callback. This is the end-to-end rate of the path a gRPC server would use, per-request staging copies included.

@@ -63,20 +63,29 @@ struct Block {
   int32_t *rqos = nullptr, *rtoken = nullptr, *rpick = nullptr;
   int64_t *cur_usage = nullptr, *limit_max = nullptr, *usage = nullptr;
   uint32_t *model_off = nullptr, *model_len = nullptr, *bpe = nullptr;
-  uint32_t table_gen = 0;  // arks_table_generation() when the request batch was submitted
   // bookkeeping
   uint32_t n = 0;
   size_t bytes = 0, tok_bytes = 0;
   std::atomic<uint32_t> filled{0};  // rows whose owner finished copying
-  uint64_t cycle = 0;
-  int64_t now = 0;
+  std::atomic<uint8_t>* ready = nullptr;  // per row: its owner finished copying (what a cut looks at when `filled` lags)
+  uint32_t cut = 0;        // rows below this index have been put into segments (dispatcher only)
+  uint32_t delivered = 0;  // rows whose decision was handed over; the block goes back to the pool at n
+};
+// rows [lo, hi) of a closed block: what one submission carries. A block is normally one segment; when an owner is late with
+// its copy (the OS took its core away between reserving the row and filling it) the rows around it go ahead without it.
+struct Seg {
+  Block* b = nullptr;
+  uint32_t lo = 0, hi = 0;
 };
 
 struct InFlight {
-  Block* req;  // either may be null
-  Block* resp;
+  Seg req;  // either may be empty (b == nullptr)
+  Seg resp;
   int slot;
   int rc_req, rc_resp;
+  uint64_t cycle;
+  int64_t now;
+  uint32_t gen;
 };
 
 // what a blocking call parks on
@@ -100,6 +109,20 @@ void wake_response(void* user, const ResponseDecision& d) {
 
 }  // namespace
 
+// TEST HOOK (ARKS_HOST_TEST_STALL="<row>:<microseconds>:<every>"): the owner of that row of every <every>-th request block
+// sleeps between reserving the row and filling it — what an owner that lost its core looks like to the dispatcher
+static const char* g_test_stall_env = getenv("ARKS_HOST_TEST_STALL");
+static void test_stall(const char* e, uint32_t row) {
+  static std::atomic<uint32_t> seen{0};
+  const uint32_t r = (uint32_t)strtoul(e, nullptr, 10);
+  const char* c = strchr(e, ':');
+  if (row != r || !c) return;
+  const unsigned long us = strtoul(c + 1, nullptr, 10);
+  const char* c2 = strchr(c + 1, ':');
+  const uint32_t every = c2 ? (uint32_t)strtoul(c2 + 1, nullptr, 10) : 1;
+  if (seen.fetch_add(1) % (every ? every : 1) == 0) std::this_thread::sleep_for(std::chrono::microseconds(us));
+}
+
 struct Batcher::Impl {
   arks_ctx* ctx;
   BatcherOptions opt;
@@ -110,6 +133,10 @@ struct Batcher::Impl {
   std::atomic<Block*> open_resp[2] = {nullptr, nullptr};  // complete bodies / SSE chunks: kept apart so that every batch is homogeneous
                                              // (the library has faster kernels for all-JSON and all-SSE batches)
   int resp_turn = 0;
+  // closed blocks that are not fully submitted yet: segments ready to go and rows whose owner is late, per kind
+  // (0 requests, 1 complete response bodies, 2 SSE chunks)
+  std::deque<Seg> pending[3];
+  std::vector<Seg> late[3];  // one-row segments waiting for their owner
   std::deque<InFlight> inflight;            // submitted, not completed (FIFO == device order)
   bool slot_busy[kSlots] = {false, false, false, false};
   mutable std::mutex mu;
@@ -134,6 +161,8 @@ struct Batcher::Impl {
     b.body_off = pinned<uint32_t>(m);
     b.body_len = pinned<uint32_t>(m);
     b.user = new void*[m];
+    b.ready = new std::atomic<uint8_t>[m];
+    for (uint32_t i = 0; i < m; i++) b.ready[i].store(0, std::memory_order_relaxed);
     if (is_req) {
       b.tokens = pinned<uint8_t>(tok_cap);
       b.token_off = pinned<uint32_t>(m + 1);
@@ -189,12 +218,53 @@ struct Batcher::Impl {
     return lead;
   }
 
-  void wait_filled(Block& b) {
-    if (b.filled.load(std::memory_order_acquire) == b.n) return;
+  // How long a closed block waits for its row owners before the rows that ARE filled go ahead without the late ones. A
+  // copy takes well under a microsecond; an owner that is later than this lost its core (preempted, or the whole group
+  // throttled by a CPU quota) and may be gone for milliseconds.
+  static constexpr int64_t kFillGraceNs = 15000;
+  // give the owners of a freshly closed block their grace (no lock held: they never take it)
+  void wait_grace(Block* b) {
+    if (b->filled.load(std::memory_order_acquire) == b->n) return;
     const auto t0 = std::chrono::steady_clock::now();
-    while (b.filled.load(std::memory_order_acquire) != b.n) std::this_thread::yield();
+    for (;;) {
+      if (b->filled.load(std::memory_order_acquire) == b->n) break;
+      const int64_t waited = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+      if (waited > kFillGraceNs) break;
+      std::this_thread::yield();
+    }
     note(t_fill, 4, (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
   }
+  // Cut a closed block into segments of filled rows (pending[k]) and late rows (late[k]). Lock held.
+  void cut_block(Block* b, int k) {
+    if (b->filled.load(std::memory_order_acquire) == b->n) {
+      pending[k].push_back(Seg{b, 0, b->n});
+      b->cut = b->n;
+      return;
+    }
+    uint32_t lo = 0;
+    for (uint32_t i = 0; i <= b->n; i++) {
+      const bool ok = i < b->n && b->ready[i].load(std::memory_order_acquire);
+      if (!ok) {
+        if (i > lo) pending[k].push_back(Seg{b, lo, i});
+        if (i < b->n) { late[k].push_back(Seg{b, i, i + 1}); st_late_rows.fetch_add(1, std::memory_order_relaxed); }
+        lo = i + 1;
+      }
+    }
+    b->cut = b->n;
+  }
+  // late rows whose owner has arrived become one-row segments
+  void collect_late(int k) {
+    for (size_t j = 0; j < late[k].size();) {
+      if (late[k][j].b->ready[late[k][j].lo].load(std::memory_order_acquire)) {
+        pending[k].push_back(late[k][j]);
+        late[k][j] = late[k].back();
+        late[k].pop_back();
+      } else {
+        j++;
+      }
+    }
+  }
+  std::atomic<uint64_t> st_late_rows{0};
   int free_slot() const {  // -1 while max_inflight batches are already queued on the device
     int busy = 0, first = -1;
     for (int k = 0; k < kSlots; k++) {
@@ -205,7 +275,10 @@ struct Batcher::Impl {
   }
 
   static uint32_t rows_of(const std::atomic<Block*>& b) { return st_rows(b.load(std::memory_order_acquire)->state.load(std::memory_order_acquire)); }
-  bool has_work() const { return rows_of(open_req) || rows_of(open_resp[0]) || rows_of(open_resp[1]); }
+  bool waiting(int k) const { return !pending[k].empty() || !late[k].empty(); }
+  bool has_work() const {
+    return rows_of(open_req) || rows_of(open_resp[0]) || rows_of(open_resp[1]) || waiting(0) || waiting(1) || waiting(2);
+  }
   // end the open block: a fresh one is published first (arrivals that lose the race go there), then the closed bit freezes
   // the fill level of the old one. Lock held.
   Block* close_open(std::atomic<Block*>& open, std::vector<Block*>& pool) {
@@ -226,46 +299,69 @@ struct Batcher::Impl {
   // and left with `lk` held and `cycling` set by the caller; the lock is dropped while the device is being talked to.
   // With one batch in flight the cycle also waits for the batch and hands every row its decision.
   void run_cycle(std::unique_lock<std::mutex>& lk) {
-    InFlight f{nullptr, nullptr, free_slot(), 0, 0};
+    InFlight f{Seg{}, Seg{}, free_slot(), 0, 0, 0, 0, 0};
     slot_busy[f.slot] = true;
-    if (rows_of(open_req)) f.req = close_open(open_req, free_req);
+    // what is already cut goes first (order of arrival); otherwise the open block is closed now
+    // (late rows do not hold the open block back: only segments that are ready to go are ahead of it)
+    Block* fresh_req = pending[0].empty() && rows_of(open_req) && !free_req.empty() ? close_open(open_req, free_req) : nullptr;
     // one response batch per cycle (a staging slot holds one): alternate when both kinds are waiting
-    int kind = rows_of(open_resp[0]) && rows_of(open_resp[1]) ? (resp_turn ^= 1) : (rows_of(open_resp[1]) ? 1 : 0);
-    if (rows_of(open_resp[kind])) f.resp = close_open(open_resp[kind], free_resp);
-    const uint64_t cyc = cycle++;
+    const bool has0 = waiting(1) || rows_of(open_resp[0]), has1 = waiting(2) || rows_of(open_resp[1]);
+    const int kind = has0 && has1 ? (resp_turn ^= 1) : (has1 ? 1 : 0);
+    Block* fresh_resp = pending[1 + kind].empty() && rows_of(open_resp[kind]) && !free_resp.empty() ? close_open(open_resp[kind], free_resp) : nullptr;
+    f.cycle = cycle++;
+    const auto prev_end = last_cycle_end;  // (statistics; read under the lock: the completion thread writes them)
+    const bool prev_work = last_had_work;
     int64_t now = clock ? clock(clock_arg) : (int64_t)time(nullptr);
     // a wall clock that steps back (NTP) must not fail the batch (ARKS_E_TIME_WENT_BACK fails every row of it): the
     // limiter's windows only move forward, like Redis keys that already exist
     if (now < last_now) now = last_now;
     last_now = now;
+    f.now = now;
     lk.unlock();
     cv_space.notify_all();
     const auto t_a = std::chrono::steady_clock::now();
+    if (fresh_req) wait_grace(fresh_req);
+    if (fresh_resp) wait_grace(fresh_resp);
+    lk.lock();  // the segment lists are read by has_work() under the lock
+    if (fresh_req) { fresh_req->token_off[fresh_req->n] = (uint32_t)fresh_req->tok_bytes; cut_block(fresh_req, 0); }
+    if (fresh_resp) cut_block(fresh_resp, 1 + kind);
+    collect_late(0);
+    collect_late(1 + kind);
+    if (!pending[0].empty()) { f.req = pending[0].front(); pending[0].pop_front(); }
+    if (!pending[1 + kind].empty()) { f.resp = pending[1 + kind].front(); pending[1 + kind].pop_front(); }
+    if (!f.req.b && !f.resp.b) {  // only late rows are left and their owners are still away
+      slot_busy[f.slot] = false;
+      lk.unlock();
+      std::this_thread::sleep_for(std::chrono::microseconds(5));
+      lk.lock();
+      return;
+    }
+    lk.unlock();
     arks_select_slot(ctx, f.slot);
-    if (f.req) {
-      Block& b = *f.req;
-      wait_filled(b);
-      b.cycle = cyc; b.now = now;
-      b.token_off[b.n] = (uint32_t)b.tok_bytes;
+    f.gen = arks_table_generation(ctx);  // LoadTables only runs between cycles: this is the batch's generation
+    auto span_end = [](const Block& b, uint32_t hi) { return (size_t)b.body_off[hi - 1] + align16(b.body_len[hi - 1]); };
+    if (f.req.b) {
+      Block& b = *f.req.b;
+      const uint32_t lo = f.req.lo, n = f.req.hi - lo;
       arks_request_batch rb{};
-      rb.n = b.n; rb.bodies = b.bodies; rb.body_off = b.body_off; rb.body_len = b.body_len; rb.bodies_bytes = b.bytes;
-      rb.tokens = b.tokens; rb.token_off = b.token_off; rb.pick_rand = b.rnd; rb.now_unix = now;
-      b.table_gen = arks_table_generation(ctx);  // LoadTables only runs between cycles: this is the batch's generation
+      rb.n = n; rb.bodies = b.bodies; rb.body_off = b.body_off + lo; rb.body_len = b.body_len + lo;
+      rb.bodies_bytes = span_end(b, f.req.hi);  // offsets stay relative to the block: rows in front of a segment ride along
+      rb.tokens = b.tokens; rb.token_off = b.token_off + lo; rb.pick_rand = b.rnd + lo; rb.now_unix = now;
       f.rc_req = arks_submit_request_async(ctx, &rb);
     }
-    if (f.resp) {
-      Block& b = *f.resp;
-      wait_filled(b);
-      b.cycle = cyc; b.now = now;
+    if (f.resp.b) {
+      Block& b = *f.resp.b;
+      const uint32_t lo = f.resp.lo, n = f.resp.hi - lo;
       arks_response_batch rb{};
-      rb.n = b.n; rb.bodies = b.bodies; rb.body_off = b.body_off; rb.body_len = b.body_len; rb.bodies_bytes = b.bytes;
-      rb.qos = b.qos; rb.flags = b.flags; rb.now_unix = now; rb.gen = b.gen;
+      rb.n = n; rb.bodies = b.bodies; rb.body_off = b.body_off + lo; rb.body_len = b.body_len + lo;
+      rb.bodies_bytes = span_end(b, f.resp.hi);
+      rb.qos = b.qos + lo; rb.flags = b.flags + lo; rb.now_unix = now; rb.gen = b.gen + lo;
       f.rc_resp = arks_submit_response_async(ctx, &rb);
     }
     const auto t_b = std::chrono::steady_clock::now();
     note(t_submit, 0, (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_b - t_a).count());
-    if (last_cycle_end.time_since_epoch().count() && last_had_work)
-      note(t_gap, 3, (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_a - last_cycle_end).count());
+    if (prev_end.time_since_epoch().count() && prev_work && t_a > prev_end)
+      note(t_gap, 3, (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_a - prev_end).count());
     if (opt.max_inflight == 1) {  // nothing else can be queued meanwhile: finish the batch here, one thread hand-off less
       deliver(f);
       lk.lock();
@@ -344,16 +440,17 @@ struct Batcher::Impl {
       note(acc, &acc == &t_device ? 1 : 2, (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count());
       t0 = t1;
     };
-    if (f.req) {
-      Block& b = *f.req;
+    if (f.req.b) {
+      Block& b = *f.req.b;
+      const uint32_t lo = f.req.lo, hi = f.req.hi;
       int rc = f.rc_req;
       if (rc == 0) {
-        arks_request_result rr{b.reason, b.detail, b.rflags, b.rqos, b.rtoken, b.rpick, b.cur_usage, b.limit_max,
-                               b.model_off, b.model_len, b.bpe};
+        arks_request_result rr{b.reason + lo, b.detail + lo, b.rflags + lo, b.rqos + lo, b.rtoken + lo, b.rpick + lo, b.cur_usage + lo,
+                               b.limit_max + lo, b.model_off + lo, b.model_len + lo, b.bpe + lo};
         rc = arks_wait_request(ctx, f.slot, &rr);
       }
       lap(t_device);
-      for (uint32_t i = 0; i < b.n; i++) {
+      for (uint32_t i = lo; i < hi; i++) {
         RequestDecision d{};
         if (rc) d.reason = kReasonHostError;
         else {
@@ -362,50 +459,59 @@ struct Batcher::Impl {
           d.cur_usage = b.cur_usage[i]; d.limit_max = b.limit_max[i];
           d.model_off = b.model_off[i]; d.model_len = b.model_len[i]; d.bpe_count = b.bpe[i];
         }
-        d.cycle = b.cycle; d.index = i; d.now_unix = b.now; d.gen = b.table_gen;
+        d.cycle = f.cycle; d.index = i - lo; d.now_unix = f.now; d.gen = f.gen;
         b.rcb[i](b.user[i], d);
       }
       lap(t_deliver);
     }
-    if (f.resp) {
-      Block& b = *f.resp;
+    if (f.resp.b) {
+      Block& b = *f.resp.b;
+      const uint32_t lo = f.resp.lo, hi = f.resp.hi;
       int rc = f.rc_resp;
       if (rc == 0) {
-        arks_response_result rr{b.reason, b.counted, b.usage};
+        arks_response_result rr{b.reason + lo, b.counted + lo, b.usage + 3 * (size_t)lo};
         rc = arks_wait_response(ctx, f.slot, &rr);
       }
       lap(t_device);
-      for (uint32_t i = 0; i < b.n; i++) {
+      for (uint32_t i = lo; i < hi; i++) {
         ResponseDecision d{};
         if (rc) d.reason = kReasonHostError;
         else {
           d.reason = b.reason[i]; d.counted = b.counted[i];
           for (int k = 0; k < 3; k++) d.usage[k] = b.usage[3 * (size_t)i + k];
         }
-        d.cycle = b.cycle; d.index = i; d.now_unix = b.now;
+        d.cycle = f.cycle; d.index = i - lo; d.now_unix = f.now;
         b.pcb[i](b.user[i], d);
       }
       lap(t_deliver);
     }
   }
-  // stats, block and slot back to the pools (lock held)
+  // stats, slot and — once every row of a block has its decision — the block back to the pools (lock held)
+  void retire(Seg& g, std::vector<Block*>& pool) {
+    Block* b = g.b;
+    b->delivered += g.hi - g.lo;
+    if (b->delivered != b->n || b->cut != b->n) return;  // other segments / late rows of the block are still on their way
+    for (uint32_t i = 0; i < b->n; i++) b->ready[i].store(0, std::memory_order_relaxed);
+    b->n = 0; b->bytes = 0; b->tok_bytes = 0; b->cut = 0; b->delivered = 0;
+    b->filled.store(0, std::memory_order_relaxed);
+    b->state.store(kClosed, std::memory_order_release);
+    pool.push_back(b);
+  }
   void recycle(InFlight& f) {
     st.cycles++;
     last_cycle_end = std::chrono::steady_clock::now();
     last_had_work = has_work();
-    if (f.req) {
-      st.request_batches++; st.requests += f.req->n;
-      if (f.req->n > st.max_request_batch) st.max_request_batch = f.req->n;
-      f.req->n = 0; f.req->bytes = 0; f.req->tok_bytes = 0; f.req->filled.store(0, std::memory_order_relaxed);
-      f.req->state.store(kClosed, std::memory_order_release);
-      free_req.push_back(f.req);
+    if (f.req.b) {
+      const uint32_t n = f.req.hi - f.req.lo;
+      st.request_batches++; st.requests += n;
+      if (n > st.max_request_batch) st.max_request_batch = n;
+      retire(f.req, free_req);
     }
-    if (f.resp) {
-      st.response_batches++; st.responses += f.resp->n;
-      if (f.resp->n > st.max_response_batch) st.max_response_batch = f.resp->n;
-      f.resp->n = 0; f.resp->bytes = 0; f.resp->filled.store(0, std::memory_order_relaxed);
-      f.resp->state.store(kClosed, std::memory_order_release);
-      free_resp.push_back(f.resp);
+    if (f.resp.b) {
+      const uint32_t n = f.resp.hi - f.resp.lo;
+      st.response_batches++; st.responses += n;
+      if (n > st.max_response_batch) st.max_response_batch = n;
+      retire(f.resp, free_resp);
     }
     slot_busy[f.slot] = false;
     cv_work.notify_one();
@@ -458,6 +564,7 @@ BatcherStats Batcher::Stats() const {
   s.max_ns_submit = p_->t_max[0].load(); s.max_ns_device = p_->t_max[1].load(); s.max_ns_deliver = p_->t_max[2].load(); s.max_ns_gap = p_->t_max[3].load();
   s.slow_submit = p_->t_slow[0].load(); s.slow_device = p_->t_slow[1].load(); s.slow_deliver = p_->t_slow[2].load(); s.slow_gap = p_->t_slow[3].load();
   s.ns_fill = p_->t_fill.load(); s.max_ns_fill = p_->t_max[4].load(); s.slow_fill = p_->t_slow[4].load();
+  s.late_rows = p_->st_late_rows.load();
   return s;
 }
 
@@ -480,6 +587,8 @@ bool Batcher::Impl::submit_request(std::string_view token, std::string_view body
   memcpy(b->bodies + off, body.data(), body.size());
   memset(b->bodies + off + body.size(), 0, need - body.size());
   memcpy(b->tokens + toff, token.data(), token.size());
+  if (const char* e = g_test_stall_env) test_stall(e, row);
+  b->ready[row].store(1, std::memory_order_release);
   b->filled.fetch_add(1, std::memory_order_release);
   if (lead) {
     std::unique_lock<std::mutex> lk(I.mu);
@@ -507,6 +616,7 @@ bool Batcher::Impl::submit_response(int32_t qos, uint32_t gen, std::string_view 
   const bool lead = row == 0 && I.first_row(can_lead);
   memcpy(b->bodies + off, body.data(), body.size());
   memset(b->bodies + off + body.size(), 0, need - body.size());
+  b->ready[row].store(1, std::memory_order_release);
   b->filled.fetch_add(1, std::memory_order_release);
   if (lead) {
     std::unique_lock<std::mutex> lk(I.mu);

@@ -67,6 +67,7 @@ struct BatcherStats {
   uint64_t slow_submit, slow_device, slow_deliver, slow_gap;
   // the part of `submit` spent waiting for row owners that had reserved a row but not finished copying into it
   uint64_t ns_fill, max_ns_fill, slow_fill;
+  uint64_t late_rows;  // rows that were not filled when their block was cut and went in a later cycle on their own
 };
 
 typedef void (*RequestCallback)(void* user, const RequestDecision&);    // run on the batcher's completion thread

@@ -239,3 +239,42 @@ def test_batcher_concurrent_streams_replay_gpu():
 @pytest.mark.gpu
 def test_stream_processor_gpu():
     run_stream_checks(GpuEngine)
+
+
+STRAGGLER = r'''
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.environ["ARKS_ROOT"]); sys.path.insert(0, os.path.join(os.environ["ARKS_ROOT"], "tests"))
+import test_cpp_host as T
+from arks_b200 import traffic
+from arks_b200.abi import RequestBatch
+w = traffic.Workload(n_tenants=40, seed=11)
+eng = T.CpuEngine(w.tables, max_batch=512, max_bytes=2 << 20)
+eng.b.set_fixed_clock(T.NOW)
+req = w.request_batch(3000, T.NOW, seed=5, stream_frac=0.2, noise_frac=0.1)
+dec, lat, wall = eng.b.run_requests(req, threads=24)
+st = eng.b.stats()
+T.replay_requests(w.tables, req, dec)
+late = dec["index"][dec["cycle"].argsort()]  # just to touch the arrays
+print(json.dumps({"late_rows": st["late_rows"], "p50_us": float(np.percentile(lat, 50)) / 1e3, "p99_us": float(np.percentile(lat, 99)) / 1e3,
+                  "max_us": float(lat.max()) / 1e3, "cycles": st["cycles"], "requests": st["requests"]}))
+eng.close()
+'''
+
+
+def test_a_row_owner_that_lost_its_core_does_not_hold_the_batch(tmp_path):
+    """ARKS_HOST_TEST_STALL makes the owner of row 2 of every 40th request block sleep 20 ms between reserving its row and filling
+    it (what a preempted / throttled stream thread looks like to the dispatcher). The rows around it must go ahead without
+    it: the block is cut into segments, the late row follows alone, every decision still replays through the oracle in
+    (cycle, index) order, and only the late rows themselves see the 20 ms."""
+    script = tmp_path / "straggler.py"
+    script.write_text(STRAGGLER)
+    env = dict(os.environ, ARKS_ROOT=ROOT, ARKS_HOST_TEST_STALL="2:20000:40")
+    out = subprocess.run([os.sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["requests"] == 3000
+    assert r["late_rows"] > 0                       # blocks were cut around their late row
+    assert r["max_us"] >= 20000                     # the late rows waited for their owner ...
+    assert r["p99_us"] < 10000, r                   # ... and nobody else did: without the cut every row of those blocks and of
+    #                                                 the blocks queued behind them would have waited the 20 ms too

@@ -54,7 +54,7 @@ for leg in ("quiet", "reloading"):
     if leg == "reloading":
         th.join()
     out[leg] = dict(pct(lat, len(lat)), req_s=round(len(lat) / wall), harness=hb.open_loop_lateness(),
-                    tail={k: (round(v / 1e3) if k.startswith("max") else v) for k, v in hb.stats().items() if k.startswith(("max_ns", "slow_"))})
+                    tail={k: (round(v / 1e3) if k.startswith("max") else v) for k, v in hb.stats().items() if k.startswith(("max_ns", "slow_", "late_"))})
     if leg == "reloading":
         out[leg]["swaps"] = len(swaps)
         out[leg]["load_tables_ms_mean"] = round(1e3 * float(np.mean(swaps)), 2) if swaps else None

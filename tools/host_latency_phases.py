@@ -29,7 +29,7 @@ for rate in (100_000, 500_000, 1_250_000, 2_500_000):
                       "us_submit": round((b1["ns_submit"] - b0["ns_submit"]) / cyc / 1e3, 1),
                       "us_device": round((b1["ns_device"] - b0["ns_device"]) / cyc / 1e3, 1),
                       "us_deliver": round((b1["ns_deliver"] - b0["ns_deliver"]) / cyc / 1e3, 1),
-                      "tail": {k: (round(v / 1e3) if k.startswith("max") else v) for k, v in b1.items() if k.startswith(("max_ns", "slow_"))},
+                      "tail": {k: (round(v / 1e3) if k.startswith("max") else v) for k, v in b1.items() if k.startswith(("max_ns", "slow_", "late_"))},
                       "from_call": {"p50": round(float(np.percentile(hb.last_call_latency[n // 10:], 50)) / 1e3), "p99": round(float(np.percentile(hb.last_call_latency[n // 10:], 99)) / 1e3),
                                     "p999": round(float(np.percentile(hb.last_call_latency[n // 10:], 99.9)) / 1e3)},
                       "harness": hb.open_loop_lateness()}
