@@ -1,6 +1,6 @@
 """Threaded-oracle scaling on the box's host cores (the bench's reference arm): req/s for several thread counts."""
 import os, sys, time
-_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, _R); sys.path.insert(0, os.path.join(_R, "tests"))
 import numpy as np
 import orklib

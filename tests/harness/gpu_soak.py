@@ -1,10 +1,10 @@
 """Randomised parity soak on a GPU box: ROUNDS rounds of mixed traffic (client-application requests, three completion
 dialects, SSE chunks, fuzzed documents, malformed / unauthorised requests, window roll-overs, table reloads) through the
-C ABI, every decision and every counter compared with the oracle. Usage: python tools/gpu_soak.py [rounds] [seed]"""
+C ABI, every decision and every counter compared with the oracle. Usage: python tests/harness/gpu_soak.py [rounds] [seed]"""
 import sys
 import numpy as np
 import os
-_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, _R); sys.path.insert(0, os.path.join(_R, "tests"))
 import __graft_entry__ as ge; ge.build()
 import orklib

@@ -1,7 +1,7 @@
 """A small pass over every kernel (request scan, admit, hot-group ranking, JSON / SSE / mixed response scans, length order,
-quota sync) for compute-sanitizer: `compute-sanitizer --tool memcheck|racecheck python tools/sanitizer_workload.py`."""
+quota sync) for compute-sanitizer: `compute-sanitizer --tool memcheck|racecheck python tests/harness/sanitizer_workload.py`."""
 import os, sys
-_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, _R); sys.path.insert(0, os.path.join(_R, "tests"))
 import numpy as np
 import __graft_entry__ as ge; ge.build()

@@ -3,7 +3,7 @@
 # 12 blocking stream threads, 10 response threads and 3 open-loop producers through it (queue depth 1 and 2).
 # Prints TSAN reports, if any, then "tsan run done". CPU only.
 set -e
-R=$(cd "$(dirname "$0")/.." && pwd)
+R=$(cd "$(dirname "$0")/../.." && pwd)
 T=${TMPDIR:-/tmp}/arks_tsan
 mkdir -p "$T"
 make -C "$R/oracle" -s libarks_oracle.so
