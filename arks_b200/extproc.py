@@ -510,6 +510,58 @@ def serve(server: ExtProcServer, port: int = 50052, max_workers: int = 64):
     return s, bound
 
 
+def serve_metrics(render, port: int = 9110):
+    """the /metrics listener (gateway.go:158-173): `render()` returns the Prometheus text exposition (metrics.exposition of
+    the device rows + HostMetrics.exposition of the wall-clock series)"""
+    from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+
+    class H(BaseHTTPRequestHandler):
+        def do_GET(self):
+            ok = self.path.split("?", 1)[0] == "/metrics"
+            body = render().encode() if ok else b"404 page not found\n"
+            self.send_response(200 if ok else 404)
+            self.send_header("Content-Type", "text/plain; version=0.0.4; charset=utf-8" if ok else "text/plain; charset=utf-8")
+            self.send_header("Content-Length", str(len(body)))
+            self.end_headers()
+            self.wfile.write(body)
+
+        def log_message(self, *a):
+            pass
+
+    httpd = ThreadingHTTPServer(("127.0.0.1", port), H)
+    threading.Thread(target=httpd.serve_forever, daemon=True).start()
+    return httpd, httpd.server_address[1]
+
+
+def gracefully_shutdown(grpc_server=None, http_server=None, metrics_server=None, timeout_s: float = 5.0):
+    """Server.GracefullyShutdown (gateway.go:194-259): the three listeners stop in parallel; the gRPC server stops accepting
+    streams and lets the ones in flight finish, and is cut off when the deadline passes. Returns the list of errors (empty:
+    "All servers shutdown successfully")."""
+    errors, threads = [], []
+
+    def stop_http(srv, what):
+        try:
+            srv.shutdown()
+            srv.server_close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"{what} server shutdown error: {e}")
+
+    for srv, what in ((http_server, "HTTP"), (metrics_server, "Metrics")):
+        if srv is not None:
+            threads.append(threading.Thread(target=stop_http, args=(srv, what)))
+    if grpc_server is not None:
+        def stop_grpc():
+            done = grpc_server.stop(timeout_s)  # GracefulStop with the context's deadline: then Stop()
+            if not done.wait(timeout_s + 1.0):
+                errors.append("gRPC server shutdown timeout")
+        threads.append(threading.Thread(target=stop_grpc))
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    return errors
+
+
 def client_stub(port: int):
     import grpc
     ch = grpc.insecure_channel(f"127.0.0.1:{port}")

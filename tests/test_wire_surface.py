@@ -90,3 +90,49 @@ def test_v1_models_over_http():
         assert get(port, "Bearer sk-alice", path="/v1/models?x=1")[0] == 200
     finally:
         httpd.shutdown()
+
+
+def test_metrics_listener_and_graceful_shutdown():
+    """/metrics over HTTP and Server.GracefullyShutdown (gateway.go:158-173,194-259): an ext_proc stream that is open when the
+    shutdown starts is allowed to finish, new ones are refused, the HTTP listeners close."""
+    import threading
+    import time
+
+    import grpc
+    from arks_b200 import metrics
+    hm = metrics.HostMetrics()
+    hm.record_request("ns", "u", "m", 0.25, 503)
+    httpd_m, port_m = extproc.serve_metrics(lambda: hm.exposition(), port=0)
+    t = tables()
+    httpd, port_h = extproc.serve_http(lambda: t, port=0)
+    st, ct, body = get(port_m, path="/metrics")
+    assert st == 200 and ct.startswith("text/plain; version=0.0.4") and b'gateway_requests_total{namespace="ns",user="u",model="m",status="503"} 1' in body
+    assert get(port_m, path="/other")[0] == 404
+    srv = extproc.ExtProcServer(engine=None, tables=t, extract_bearer=lambda hs: b"tok", batcher=object())
+    server, port = extproc.serve(srv, port=0)
+    ch, stub = extproc.client_stub(port)
+    gate = threading.Event()
+
+    def slow_stream():  # a stream that sends its headers, then stays open for a while
+        m = extproc.PB["ProcessingRequest"]()
+        m.request_headers.end_of_stream = False
+        yield m
+        gate.wait(5)
+
+    replies = []
+    th = threading.Thread(target=lambda: replies.extend(stub(slow_stream())))
+    th.start()
+    time.sleep(0.3)
+    box = {}
+    stopper = threading.Thread(target=lambda: box.update(errors=extproc.gracefully_shutdown(server, httpd, httpd_m, timeout_s=5.0)))
+    stopper.start()
+    time.sleep(0.3)
+    with pytest.raises(grpc.RpcError):  # no new streams once the shutdown has begun
+        list(stub(iter([extproc.PB["ProcessingRequest"]()]), timeout=2))
+    gate.set()  # ... but the open one runs to its end
+    th.join(10)
+    stopper.join(10)
+    assert box["errors"] == [] and len(replies) == 1 and replies[0].WhichOneof("response") == "request_headers"
+    with pytest.raises(Exception):
+        get(port_h)
+    ch.close()
