@@ -2040,7 +2040,6 @@ int arks_prepare_tables(arks_ctx* ctx, const arks_tables* t, arks_prepared** out
   if (!ctx || !t || !out) return ARKS_E_INVALID_ARG;
   *out = nullptr;
   CK(cudaSetDevice(ctx->device));
-  std::lock_guard<std::mutex> cfg_guard(ctx->cfg_mu);
   auto S = [&](uint32_t id) {
     return std::string((const char*)t->str_bytes + t->str_off[id], t->str_off[id + 1] - t->str_off[id]);
   };
@@ -2111,7 +2110,14 @@ int arks_prepare_tables(arks_ctx* ctx, const arks_tables* t, arks_prepared** out
 
   // counters are carried over by key (Redis keys survive a CRD edit): which old row feeds every new row
   std::vector<int32_t> qos_from(t->n_qos + 1, -1), quota_from(t->n_quotas + 1, -1);
-  std::vector<int32_t> old_to_new(ctx->loaded ? ctx->ht.n_qos : 0, -1);  // qos index of the outgoing generation -> this one
+  std::vector<int32_t> old_to_new;  // qos index of the outgoing generation -> this one
+  uint32_t base_generation;
+  {
+    // the only part that looks at the current generation: short, so that a commit on the batch thread never waits for
+    // the tens of milliseconds a prepare on the config thread takes
+    std::lock_guard<std::mutex> cfg_guard(ctx->cfg_mu);
+    base_generation = ctx->generation;
+    old_to_new.assign(ctx->loaded ? ctx->ht.n_qos : 0, -1);
   if (ctx->loaded) {
     std::unordered_map<std::string, uint32_t> oq, ou;
     for (uint32_t q = 0; q < ctx->ht.n_qos; q++) oq.emplace(ctx->ht.qos_key[q], q);
@@ -2127,6 +2133,7 @@ int arks_prepare_tables(arks_ctx* ctx, const arks_tables* t, arks_prepared** out
       auto it = ou.find(ht.quota_key[q]);
       if (it != ou.end()) quota_from[q] = (int32_t)it->second;
     }
+  }
   }
 
   // Build the new generation completely before touching the old one, on the config stream: a failed allocation or upload
@@ -2225,7 +2232,7 @@ int arks_prepare_tables(arks_ctx* ctx, const arks_tables* t, arks_prepared** out
   p->d = d;
   p->ht = std::move(ht);
   p->old_to_new = std::move(old_to_new);
-  p->base_generation = ctx->generation;
+  p->base_generation = base_generation;
   p->n_qos = t->n_qos;
   p->n_quotas = t->n_quotas;
   *out = p;

@@ -202,7 +202,8 @@ def choose_threads(o, req, resp, now):
     sock0 = [c for p, c in cores if p == cores[0][0]]
     allc = [c for _, c in cores]
     quota = cpu_quota()
-    cap = (lambda cpus: cpus[:quota]) if quota else (lambda cpus: cpus)  # more busy threads than the quota get the group throttled
+    # more busy threads than the quota get the group throttled; one CPU of it is left to everything that is not a worker
+    cap = (lambda cpus: cpus[:max(1, quota - 1)]) if quota else (lambda cpus: cpus)
     cands = []
     for cpus in (sock0, sock0[:max(1, len(sock0) // 2)], sock0[:max(1, len(sock0) // 4)], allc, allc[:max(1, len(allc) // 2)],
                  sock0[:max(1, (quota or len(sock0)) // 2)]):
