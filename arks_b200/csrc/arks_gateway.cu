@@ -658,7 +658,7 @@ __device__ __forceinline__ void fast_pass_a(const uint8_t* body, uint32_t len, F
   if (len != 0 && len <= kFastMaxLen) {
     const FastRing ring{sm.ring + t, (uint32_t)kFastThreads};
     const uint32_t nch = (len + 31) >> 5, plen = (len + 15u) & ~15u;
-    FastCarry c{0, 0, 0};
+    FastCarry c{0, 0, 0, 0};
     const uint4* p = reinterpret_cast<const uint4*>(body);
     const uint4 z = make_uint4(0, 0, 0, 0);
     // A body that starts on a 32-byte boundary (every packer of this repository does that; the ABI asks for 16) is read a
@@ -792,6 +792,159 @@ __global__ void __launch_bounds__(kFastThreads) fast_request_kernel(DevTables T,
   const uint8_t pstate = (uint8_t)((o.stream3 == 2 ? PS_STREAM : 0) | (o.so_present && o.iu3 == 2 ? PS_STREAM_OK : 0));
   // with regrouping by structure (2) another thread scanned this document: look the token up from scratch
   const int32_t tok = !o.m_rawlen ? -1 : regroup < 2 ? lookup_token_end(T, B, i, probe) : lookup_token(T, B, i);
+  resolve_request(T, B, i, body, tok, pstate, o.m_start, o.m_rawlen, o.m_esc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1' with TWO lanes per document in pass A (mask_scan.cuh "one document, two lanes"): 64 documents per block of 128
+// threads, 4 096 warps per 64 Ki-document wave instead of 2 048, and each lane's pass-A chain half as long. Lanes 2k / 2k+1
+// share document k of the block; the even lane goes on alone through passes B / C and the tail.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSplitDocs = kFastThreads / 2;
+struct __align__(128) FastSplitSmem {
+  FastTables tabs;
+  uint64_t bar;
+  uint32_t tb[kFastChunks * kSplitDocs];
+  uint32_t mem[2 * kFastMaxMembers * kSplitDocs];
+  uint32_t ring[16 * kFastThreads];  // per LANE: each half validates its own escapes
+  uint32_t hist[64];
+  uint32_t order[kSplitDocs];
+};
+static_assert(sizeof(FastSplitSmem) <= 31 * 1024, "seven blocks per SM: a 64 Ki wave (1 024 blocks) is resident at once");
+
+// which of the block's 64 documents pair `pair` scans: the documents in order of length (counting sort, see fast_block_order)
+__device__ __forceinline__ uint32_t split_block_order(FastSplitSmem& sm, uint32_t len0, bool on) {
+  const uint32_t t = threadIdx.x, pair = t >> 1;
+  if (!on) return pair;
+  if (t < 64) sm.hist[t] = 0;
+  __syncthreads();
+  const uint32_t bucket = min((len0 + 31) >> 5, 63u);
+  uint32_t mine = 0;
+  if (!(t & 1)) mine = atomicAdd(&sm.hist[bucket], 1u);
+  __syncthreads();
+  if (!(t & 1)) {
+    uint32_t before = 0;
+    for (uint32_t k = 0; k < bucket; k++) before += sm.hist[k];
+    sm.order[before + mine] = pair;
+  }
+  __syncthreads();
+  return sm.order[pair];
+}
+
+// pass A of one lane over chunks [j0, j1) of the document in column `col`; everything it learns goes into `acc` and `c`
+__device__ __forceinline__ void split_pass_a(const uint8_t* body, uint32_t len, uint32_t j0, uint32_t j1, FastSplitSmem& sm, uint32_t col,
+                                             FastCarry& c, FastHalf& acc) {
+  const FastScratch s{sm.tb + col, sm.mem + col, (uint32_t)kSplitDocs, 0u, 0u, 0u, 0u};
+  const FastRing ring{sm.ring + threadIdx.x, (uint32_t)kFastThreads};
+  const uint32_t nch = (len + 31) >> 5, plen = (len + 15u) & ~15u;
+  const uint32_t jload = min(j1 + 1, nch);  // one chunk beyond the range: an escape may reach into it
+  const uint4* p = reinterpret_cast<const uint4*>(body);
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  const bool a32 = (reinterpret_cast<uintptr_t>(body) & 31u) == 0;
+  auto ld = [&](uint32_t j, uint4& a, uint4& b) {
+    a = z; b = z;
+    if (j < jload) {
+      if (a32) ld_nc_v8(p + 2 * j, a, b);
+      else {
+        a = ld_nc_v4(p + 2 * j);
+        if (32 * j + 16 < plen) b = ld_nc_v4(p + 2 * j + 1);
+      }
+    }
+  };
+  uint4 a0, b0, a1, b1, a2, b2, a3, b3;
+  ld(j0, a0, b0); ld(j0 + 1, a1, b1); ld(j0 + 2, a2, b2); ld(j0 + 3, a3, b3);
+  {
+    const uint32_t w0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+    ring.put(j0, w0);
+  }
+#pragma unroll 1
+  for (uint32_t j = j0; j < j1; j++) {
+    const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+    a0 = a1; b0 = b1; a1 = a2; b1 = b2; a2 = a3; b2 = b3;
+    ld(j + 4, a3, b3);
+    {
+      const uint32_t wn[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+      ring.put(j + 1, wn);
+    }
+    const uint32_t nv = min(len - 32 * j, 32u);
+    uint32_t bm, tbw;
+    fast_chunk(w, nv, ring, len, 32 * j, c, &tbw, &bm);
+    s.tb(j) = tbw;
+    fast_half_note(acc, j, tbw, bm, nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u));
+  }
+}
+
+// Pass A of the pair's document by both lanes, the hand-over, and the scratch view the even lane walks. Returns false in the
+// odd lane and for documents off this path. All 32 lanes of a warp run this together (shuffles inside).
+__device__ __forceinline__ bool split_scan(const uint8_t* body, uint32_t len, FastSplitSmem& sm, uint32_t col, FastScratch& s, uint32_t* nch_out) {
+  const bool odd = threadIdx.x & 1;
+  const bool elig = len != 0 && len <= kFastMaxLen;
+  const uint32_t nch = elig ? (len + 31) >> 5 : 0, h = fast_split_point(nch);
+  FastCarry c{0, 0, 0, 0};
+  FastHalf acc{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (elig && !odd) {
+    split_pass_a(body, len, 0, h, sm, col, c, acc);
+  } else if (elig && h < nch) {
+    // the escape carry into chunk h is a function of the backslashes at the end of chunk h - 1 alone
+    const uint4* p = reinterpret_cast<const uint4*>(body) + 2 * (h - 1);
+    const uint4 a = ld_nc_v4(p), b = ld_nc_v4(p + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    c.esc = fast_esc_after(fast_backslash_mask(w, 32), &c.bad);
+    c.bad_flip = c.bad;
+    split_pass_a(body, len, h, nch, sm, col, c, acc);
+  }
+  acc.bad0 = c.bad; acc.bad1 = c.bad_flip; acc.parity = c.in_str;
+  // the odd lane's findings to the even lane
+  FastHalf H;
+  H.bs_lo = __shfl_xor_sync(0xffffffffu, acc.bs_lo, 1); H.bs_hi = __shfl_xor_sync(0xffffffffu, acc.bs_hi, 1);
+  H.nz0_lo = __shfl_xor_sync(0xffffffffu, acc.nz0_lo, 1); H.nz0_hi = __shfl_xor_sync(0xffffffffu, acc.nz0_hi, 1);
+  H.nz1_lo = __shfl_xor_sync(0xffffffffu, acc.nz1_lo, 1); H.nz1_hi = __shfl_xor_sync(0xffffffffu, acc.nz1_hi, 1);
+  H.ntok0 = __shfl_xor_sync(0xffffffffu, acc.ntok0, 1); H.ntok1 = __shfl_xor_sync(0xffffffffu, acc.ntok1, 1);
+  H.bad0 = __shfl_xor_sync(0xffffffffu, acc.bad0, 1); H.bad1 = __shfl_xor_sync(0xffffffffu, acc.bad1, 1);
+  H.parity = __shfl_xor_sync(0xffffffffu, acc.parity, 1);
+  __syncwarp();  // the odd lane's words of the bitmap are in shared memory before the even lane reads them
+  if (odd || !elig) return false;
+  s = FastScratch{sm.tb + col, sm.mem + col, (uint32_t)kSplitDocs, acc.bs_lo, acc.bs_hi, acc.nz0_lo, acc.nz0_hi};
+  uint32_t ntok = acc.ntok0;
+  *nch_out = nch;
+  return fast_split_merge(s, len, h, c, H, &ntok);
+}
+
+template <int WALK>
+__global__ void __launch_bounds__(kFastThreads, 7) fast_request_kernel2(DevTables T, ReqDev B, int regroup) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  FastSplitSmem& sm = *reinterpret_cast<FastSplitSmem*>(smem);
+  stage_fast_tables(&sm.tabs, &sm.bar);
+  const uint32_t base = blockIdx.x * kSplitDocs, pair = threadIdx.x >> 1;
+  const uint32_t own = base + pair;
+  const uint32_t len0 = own < B.n ? B.body_len[B.perm ? B.perm[own] : own] : 0u;
+  const uint32_t slot = split_block_order(sm, len0, (regroup & 127) != 0);
+  const bool in = base + slot < B.n;
+  const uint32_t i = in ? (B.perm ? B.perm[base + slot] : base + slot) : 0;
+  const uint8_t* body = B.bodies + (in ? B.body_off[i] : 0);
+  const uint32_t len = in ? B.body_len[i] : 0u;
+  TokProbe probe{};
+  if (in && !(threadIdx.x & 1)) probe = lookup_token_begin(T, B, i);  // consumed after pass C
+  FastScratch s{nullptr, nullptr, 0, 0, 0, 0, 0};
+  uint32_t nch = 0;
+  const bool ok = split_scan(body, len, sm, pair, s, &nch);
+  if ((threadIdx.x & 1) || !in) return;
+  if (regroup & 256) return;  // timing experiments only: pass A alone
+  FastOut o;
+  bool accepted = ok;
+  if (accepted) {
+    const int nmem = fast_walk<WALK>(body, sm.tabs, s, nch, kFastKeyLensReq);
+    accepted = nmem >= 0 && fast_members<K_REQ>(body, s, nch, nmem, o);
+  }
+  if (!accepted) {
+    B.slow_list[atomicAdd(B.slow_n, 1u) + 1u] = i;
+    return;
+  }
+  B.model_off[i] = o.m_rawlen ? o.m_start : 0u;
+  B.model_len[i] = o.m_rawlen ? (o.m_rawlen | (o.m_esc ? 0x80000000u : 0u)) : 0u;
+  B.bpe[i] = 0;
+  const uint8_t pstate = (uint8_t)((o.stream3 == 2 ? PS_STREAM : 0) | (o.so_present && o.iu3 == 2 ? PS_STREAM_OK : 0));
+  const int32_t tok = !o.m_rawlen ? -1 : lookup_token_end(T, B, i, probe);
   resolve_request(T, B, i, body, tok, pstate, o.m_start, o.m_rawlen, o.m_esc);
 }
 
@@ -1322,6 +1475,58 @@ __global__ void __launch_bounds__(kFastThreads) fast_response_kernel(DevTables T
   account_usage(T, B, i, live, qos, acct, reason, counted, u0, u1, u2);  // all 32 lanes: warp-aggregated atomics inside
 }
 
+// two lanes per document in pass A (see fast_request_kernel2)
+template <int WALK>
+__global__ void __launch_bounds__(kFastThreads, 7) fast_response_kernel2(DevTables T, RespDev B, int regroup) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  FastSplitSmem& sm = *reinterpret_cast<FastSplitSmem*>(smem);
+  stage_fast_tables(&sm.tabs, &sm.bar);
+  const uint32_t base = blockIdx.x * kSplitDocs, pair = threadIdx.x >> 1;
+  const uint32_t own = base + pair;
+  uint32_t len0 = 0;
+  if (own < B.n) {
+    const uint32_t i0 = B.perm ? B.perm[own] : own;
+    if ((B.flags[i0] & ARKS_RESP_END_OF_STREAM) && B.qos[i0] >= 0) len0 = B.body_len[i0];
+  }
+  const uint32_t slot = split_block_order(sm, len0, (regroup & 127) != 0);
+  const bool odd = threadIdx.x & 1;
+  const bool in = base + slot < B.n;
+  const uint32_t i = in ? (B.perm ? B.perm[base + slot] : base + slot) : 0;
+  const int32_t qos = in ? B.qos[i] : 0;
+  const uint8_t fl = in ? B.flags[i] : ARKS_RESP_END_OF_STREAM;
+  const bool pending = !(fl & ARKS_RESP_END_OF_STREAM);
+  const bool scan = in && !pending && qos >= 0;
+  const uint8_t* body = B.bodies + (scan ? B.body_off[i] : 0);
+  const uint32_t len = scan ? B.body_len[i] : 0u;
+  FastScratch s{nullptr, nullptr, 0, 0, 0, 0, 0};
+  uint32_t nch = 0;
+  const bool ok = split_scan(body, len, sm, pair, s, &nch);
+  if (regroup & 256) return;  // timing experiments only: pass A alone
+  uint8_t reason = ARKS_R_OK, counted = 0;
+  long long u0 = 0, u1 = 0, u2 = 0;
+  bool live = in && !odd;  // the even lane carries the row; the odd one only keeps the warp-wide calls below complete
+  if (live && scan) {
+    FastOut o;
+    bool accepted = ok;
+    if (accepted) {
+      const int nmem = fast_walk<WALK>(body, sm.tabs, s, nch, kFastKeyLensResp);
+      accepted = nmem >= 0 && fast_members<K_RESP>(body, s, nch, nmem, o);
+    }
+    if (accepted) {
+      if (o.m_rawlen == 0) reason = ARKS_R_RESPONSE_UNKNOWN;  // handle_response.go:167-181
+      else { u0 = o.usage[0]; u1 = o.usage[1]; u2 = o.usage[2]; }
+      counted = reason == ARKS_R_OK && u2 != 0;               // :186
+    } else {
+      B.slow_list[atomicAdd(B.slow_n, 1u) + 1u] = i;  // the exact engine decides (and accounts) this one
+      live = false;
+    }
+  } else if (live && pending) {
+    reason = ARKS_R_PENDING;  // :141-149 (a row without a qos entry: account_usage answers ARKS_R_QOS_GONE)
+  }
+  const QosAcct acct = load_qos_acct(T, qos, live && qos >= 0);
+  account_usage(T, B, i, live, qos, acct, reason, counted, u0, u1, u2);  // all 32 lanes: warp-aggregated atomics inside
+}
+
 // the latency path for complete response bodies: one warp per body (see warp_request_kernel)
 __global__ void __launch_bounds__(kWdWarps * 32) warp_response_kernel(DevTables T, RespDev B) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1605,6 +1810,7 @@ struct arks_ctx {
   cudaStream_t h2d = nullptr;     // batch uploads (overlap the kernels of earlier batches)
   cudaStream_t cfg_stream = nullptr;  // config plane: the next generation's tables are uploaded here, off the data path
   std::mutex cfg_mu;                  // prepare (config thread) vs commit (batch thread)
+  bool split = false;                  // fast path: two lanes per document in pass A (fast_*_kernel2), ARKS_SPLIT=1; measured slower
   bool walk8 = true;                   // fast path, pass B: the step inlined eight times (true) or one copy in a loop
   int regroup = 1;                     // fast path: regroup a block's documents by structure between passes A and B
   struct NcclApi* nccl = nullptr;      // dlopen()ed libnccl + this context's communicator (arks_comm_init)
@@ -1795,6 +2001,9 @@ int arks_create(int device, uint32_t max_batch, uint64_t max_batch_bytes, arks_c
   CK(cudaFuncSetAttribute(fast_response_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
   CK(cudaFuncSetAttribute(fast_request_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
   CK(cudaFuncSetAttribute(fast_response_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastBlockSmem)));
+  CK(cudaFuncSetAttribute(fast_request_kernel2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSplitSmem)));
+  CK(cudaFuncSetAttribute(fast_response_kernel2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSplitSmem)));
+  if (const char* e = getenv("ARKS_SPLIT")) ctx->split = e[0] != '0';
   // a 64 Ki-document wave is 512 blocks: with four of them resident per SM (4 x ~50 KB) the whole wave runs at once
   static_assert(sizeof(FastBlockSmem) <= 56 * 1024, "four fast-path blocks per SM");
   {
@@ -2637,7 +2846,9 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
     // global length order the exact engine uses
     r.perm = ctx->sort_fast ? queue_length_order(ctx, r.body_len, n) : nullptr;
     if (ctx->prof) CK(cudaEventRecord(ctx->ev_fast[0], ctx->stream));
-    if (ctx->walk8)
+    if (ctx->split)
+      fast_request_kernel2<8><<<(n + kSplitDocs - 1) / kSplitDocs, kFastThreads, sizeof(FastSplitSmem), ctx->stream>>>(ctx->dt, r, ctx->regroup);
+    else if (ctx->walk8)
       fast_request_kernel<8><<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, r, ctx->regroup);
     else
       fast_request_kernel<0><<<(n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, r, ctx->regroup);
@@ -2879,7 +3090,9 @@ int arks_run_response_batch(arks_ctx* ctx, int64_t now_unix) {
     CK(cudaMemsetAsync(ctx->d_slow, 0xff, 4, ctx->stream));
     rp.perm = ctx->sort_fast ? queue_length_order(ctx, rp.body_len, rp.n) : nullptr;
     if (ctx->prof) CK(cudaEventRecord(ctx->ev_fast[0], ctx->stream));
-    if (ctx->walk8)
+    if (ctx->split)
+      fast_response_kernel2<8><<<(rp.n + kSplitDocs - 1) / kSplitDocs, kFastThreads, sizeof(FastSplitSmem), ctx->stream>>>(ctx->dt, rp, ctx->regroup);
+    else if (ctx->walk8)
       fast_response_kernel<8><<<(rp.n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, rp, ctx->regroup);
     else
       fast_response_kernel<0><<<(rp.n + kFastThreads - 1) / kFastThreads, kFastThreads, sizeof(FastBlockSmem), ctx->stream>>>(ctx->dt, rp, ctx->regroup);

@@ -55,7 +55,15 @@ struct FastScratch {
   uint32_t stride;
   uint32_t bs_lo, bs_hi;  // chunk j contains a backslash (bit j): lets the key / model checks skip the byte scan
   uint32_t nz_lo, nz_hi;  // chunk j has bytes outside strings (tb(j) != 0): the token cursor jumps over the others
-  ARKS_HD uint32_t& tb(uint32_t j) const { return tb_[j * stride]; }
+  // When two lanes scan one document (the second half is scanned before anybody knows whether it starts inside a string),
+  // the words from `flip_from` on were written under the assumption "outside" and are read complemented if that was wrong:
+  // for every byte — quote or not — "is a token" is exactly the opposite under the other assumption.
+  uint32_t flip_from = 0xffffffffu, last_w = 0, vlast = 0xffffffffu;  // last_w / vlast: last chunk and its valid-byte mask
+  ARKS_HD uint32_t& tb(uint32_t j) const { return tb_[j * stride]; }  // the stored word (pass A writes it)
+  ARKS_HD uint32_t tbv(uint32_t j) const {                            // the word as passes B / C read it
+    const uint32_t raw = tb_[j * stride];
+    return j >= flip_from ? (j == last_w ? vlast : 0xffffffffu) & ~raw : raw;
+  }
   ARKS_HD uint32_t& mem(uint32_t j) const { return mem_[j * stride]; }
 };
 // the two chunks pass A has at hand (the current one and the next), as words a lane can index dynamically: shared memory
@@ -126,6 +134,7 @@ struct FastCarry {
   uint32_t esc;     // the next chunk's first byte is escaped
   uint32_t in_str;  // the next chunk starts inside a string
   uint32_t bad;
+  uint32_t bad_flip;  // the same verdict if the scan had started INSIDE a string instead (second lane of a split document)
 };
 ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const FastRing& ring, uint32_t len, uint32_t base, FastCarry& c,
                         uint32_t* tb_out, uint32_t* bm_out) {
@@ -146,11 +155,15 @@ ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const FastRing& ri
   // a backslash run that fills the whole chunk keeps the carry as it is (32 is even); otherwise the carry out is the
   // parity of the run that touches the chunk's end (its first backslash cannot be escaped: something else precedes it)
   const uint32_t E = find_escaped(B, c.esc);
-  c.esc = B == 0xffffffffu ? c.esc : (clz32(~B) & 1u);
+  // the byte after the chunk is escaped iff the chunk ends in a backslash that is not itself escaped (find_escaped has the
+  // carry in it: this is the parity of the backslash run that touches the chunk's end, without counting it)
+  c.esc = (B >> 31) & ~(E >> 31) & 1u;
   const uint32_t Qu = Q & ~E;
-  const uint32_t R = prefix_xor32(Qu) ^ (c.in_str ? 0xffffffffu : 0u);  // inside a string, opening quote included
-  c.in_str ^= popc32(Qu) & 1u;
+  const uint32_t Rraw = prefix_xor32(Qu);
+  const uint32_t R = Rraw ^ (c.in_str ? 0xffffffffu : 0u);  // inside a string, opening quote included
+  c.in_str ^= Rraw >> 31;                                  // the prefix XOR's top bit is the parity of all quotes
   uint32_t bad = B & ~R;  // a backslash outside a string
+  uint32_t bad_flip = B & R;
   if (anyc) {             // rare: some byte < 0x20 in the chunk; inside a string it takes the document off this path
     uint32_t C = 0;
 #ifdef __CUDA_ARCH__
@@ -158,6 +171,7 @@ ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const FastRing& ri
 #endif
     for (int j = 0; j < 8; j++) C |= plane_nibble(zero_bytes(w[j] & 0xe0e0e0e0u)) << (4 * j);
     bad |= C & V & R;
+    bad_flip |= C & V & ~R;
   }
   uint32_t e = E & V;
   while (e) {  // rare: what follows each backslash must be an escape RFC 8259 knows
@@ -168,16 +182,70 @@ ARKS_HD void fast_chunk(const uint32_t w[8], uint32_t nvalid, const FastRing& ri
     const uint32_t okw = ch < 0x40 ? 0x00008004u : ch < 0x60 ? 0x10000000u : ch < 0x80 ? 0x00144044u : 0u;  // 0x20-0x3f | 0x40-0x5f | 0x60-0x7f
     const bool simple = ch >= 0x20 && ((okw >> (ch & 31u)) & 1u);
     if (ch == 'u') {
-      if (p + 4 >= len || !four_hex(ring.four_at(p + 1))) bad = 1;
+      if (p + 4 >= len || !four_hex(ring.four_at(p + 1))) bad = bad_flip = 1;
     } else if (!simple) {
-      bad = 1;
+      bad = bad_flip = 1;
     }
   }
   c.bad |= bad;
+  c.bad_flip |= bad_flip;
   // bytes outside strings, plus the OPENING quote of every string (R covers a string from its opening quote to the byte
   // before its closing quote; the closing quote is not a token: whatever follows it is, so "closing quote = next token - 1")
   *tb_out = V & ~(R & ~Qu) & ~(Qu & ~R);
   *bm_out = B;
+}
+
+// ---- one document, two lanes (pass A only) ----
+// A lane per document means a 64 Ki-document wave is 2 048 warps, 14 per SM, each a dependent chain: the kernel runs at the
+// speed of that chain. Pass A's chain is cut in two: lane L scans chunks [0, h), lane H chunks [h, nch) AT THE SAME TIME.
+// What H does not know is whether chunk h starts inside a string. It does not need to: it scans as if it started outside,
+//   * the escape carry into chunk h only depends on the backslash run at the end of chunk h-1 (H looks at that one chunk),
+//   * under the other assumption every byte's "is a token" bit is exactly the complement (see FastScratch::tbv), so H keeps
+//     one bitmap and both non-empty-chunk maps, both token counts and both verdicts (FastCarry::bad / bad_flip),
+// and when L arrives with the true parity the right variant is picked. Exact, not speculative.
+struct FastHalf {  // what lane H hands over
+  uint32_t bs_lo, bs_hi;                      // chunks with a backslash
+  uint32_t nz0_lo, nz0_hi, nz1_lo, nz1_hi;    // non-empty chunks under either assumption
+  uint32_t ntok0, ntok1, bad0, bad1, parity;  // parity: quotes seen are odd
+};
+// H's first chunk; nch when the document is too short to be worth splitting
+ARKS_HD uint32_t fast_split_point(uint32_t nch) { return nch >= 4 ? (nch + 1) / 2 : nch; }
+// backslash mask of a chunk (for the escape carry out of chunk h-1)
+ARKS_HD uint32_t fast_backslash_mask(const uint32_t w[8], uint32_t nvalid) {
+  uint32_t B = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 0; j < 8; j++) B |= plane_nibble(zero_bytes(w[j] ^ 0x5c5c5c5cu)) << (4 * j);
+  return B & (nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u));
+}
+// escape carry into the chunk after one whose backslash mask is Bprev; a chunk of 32 backslashes would need the chunk
+// before it as well: such a document is left to the exact engine
+ARKS_HD uint32_t fast_esc_after(uint32_t Bprev, uint32_t* bad) {
+  if (Bprev == 0xffffffffu) { *bad = 1; return 0; }
+  return clz32(~Bprev) & 1u;
+}
+// L's own result is in `s` (bs / nz bits of its chunks) and cL; returns false if the document is off this path
+ARKS_HD bool fast_split_merge(FastScratch& s, uint32_t len, uint32_t h, const FastCarry& cL, const FastHalf& H, uint32_t* ntok) {
+  const uint32_t nch = (len + 31) >> 5, flip = cL.in_str;
+  if (cL.bad || (flip ? H.bad1 : H.bad0) || (cL.in_str ^ H.parity)) return false;  // ... or the document ends inside a string
+  s.bs_lo |= H.bs_lo; s.bs_hi |= H.bs_hi;
+  s.nz_lo |= flip ? H.nz1_lo : H.nz0_lo;
+  s.nz_hi |= flip ? H.nz1_hi : H.nz0_hi;
+  *ntok += flip ? H.ntok1 : H.ntok0;
+  s.flip_from = flip ? h : 0xffffffffu;
+  s.last_w = nch - 1;
+  const uint32_t tail = len - 32 * (nch - 1);
+  s.vlast = tail >= 32 ? 0xffffffffu : ((1u << tail) - 1u);
+  return true;
+}
+// what H accumulates per chunk besides the stored word
+ARKS_HD void fast_half_note(FastHalf& H, uint32_t j, uint32_t tbw, uint32_t bm, uint32_t V) {
+  const uint32_t bit = 1u << (j & 31), alt = V & ~tbw;
+  if (j < 32) { H.bs_lo |= bm ? bit : 0u; H.nz0_lo |= tbw ? bit : 0u; H.nz1_lo |= alt ? bit : 0u; }
+  else { H.bs_hi |= bm ? bit : 0u; H.nz0_hi |= tbw ? bit : 0u; H.nz1_hi |= alt ? bit : 0u; }
+  H.ntok0 += popc32(tbw);
+  H.ntok1 += popc32(alt);
 }
 
 // ---- pass B: the grammar as a table ----
@@ -268,10 +336,10 @@ struct FastTablesInit {
 ARKS_HD uint32_t next_token(const FastScratch& s, uint32_t nch, uint32_t from, uint32_t none) {
   uint32_t w = from >> 5;
   if (w >= nch) return none;
-  uint32_t m = s.tb(w) & (0xffffffffu << (from & 31));
+  uint32_t m = s.tbv(w) & (0xffffffffu << (from & 31));
   while (!m) {
     if (++w >= nch) return none;
-    m = s.tb(w);
+    m = s.tbv(w);
   }
   return w * 32 + first_set(m);
 }
@@ -330,7 +398,7 @@ struct TokCursor {  // iterates the set bits of the tb bitmap, jumping over empt
   uint32_t w, cur, nz_lo, nz_hi;
   ARKS_HD void init(const FastScratch& s, uint32_t nch, uint32_t from) {
     w = from >> 5;
-    cur = w < nch ? (s.tb(w) & (0xffffffffu << (from & 31))) : 0;
+    cur = w < nch ? (s.tbv(w) & (0xffffffffu << (from & 31))) : 0;
     // chunks after w that are not empty
     const uint64_t nz = ((uint64_t)s.nz_hi << 32 | s.nz_lo) & (w >= 63 ? 0ull : ~0ull << (w + 1));
     nz_lo = (uint32_t)nz;
@@ -341,7 +409,7 @@ struct TokCursor {  // iterates the set bits of the tb bitmap, jumping over empt
       if (nz_lo) { w = first_set(nz_lo); nz_lo &= nz_lo - 1; }
       else if (nz_hi) { w = 32 + first_set(nz_hi); nz_hi &= nz_hi - 1; }
       else return false;
-      cur = s.tb(w);
+      cur = s.tbv(w);
     }
     *pos = w * 32 + first_set(cur);
     cur &= cur - 1;
@@ -611,7 +679,7 @@ inline bool fast_scan_host(const uint8_t* doc, uint32_t len, FastOut& out) {
   FastScratch s{tb, mem, 1, 0, 0, 0, 0};
   const FastRing ring{ringw, 1};
   const uint32_t nch = (len + 31) / 32;
-  FastCarry c{0, 0, 0};
+  FastCarry c{0, 0, 0, 0};
   auto words_of = [&](uint32_t j, uint32_t w[8]) {
     for (int q = 0; q < 8; q++) {
       uint32_t v = 0;
@@ -635,6 +703,56 @@ inline bool fast_scan_host(const uint8_t* doc, uint32_t len, FastOut& out) {
     for (int q = 0; q < 8; q++) w[q] = wn[q];
   }
   if (c.bad || c.in_str) return false;
+  const int nmem = fast_walk<0>(doc, kFastTablesHost.t, s, nch, KIND == K_REQ ? kFastKeyLensReq : kFastKeyLensResp);
+  if (nmem < 0) return false;
+  return fast_members<KIND>(doc, s, nch, nmem, out);
+}
+// the same with pass A done the way two lanes do it (first half, second half under the "outside a string" assumption, merge)
+template <int KIND>
+inline bool fast_scan_host_split(const uint8_t* doc, uint32_t len, FastOut& out) {
+  if (len == 0 || len > kFastMaxLen) return false;
+  static thread_local uint32_t tb[kFastChunks], mem[2 * kFastMaxMembers], ringw[16];
+  FastScratch s{tb, mem, 1, 0, 0, 0, 0};
+  const FastRing ring{ringw, 1};
+  const uint32_t nch = (len + 31) / 32, h = fast_split_point(nch);
+  auto words_of = [&](uint32_t j, uint32_t w[8]) {
+    for (int q = 0; q < 8; q++) {
+      uint32_t v = 0;
+      for (int b = 0; b < 4; b++) {
+        const uint32_t p = 32 * j + 4 * q + b;
+        v |= (uint32_t)(p < len ? doc[p] : (uint8_t)(0xA5 ^ p)) << (8 * b);
+      }
+      w[q] = v;
+    }
+  };
+  auto nvalid = [&](uint32_t j) { return len - 32 * j < 32 ? len - 32 * j : 32u; };
+  uint32_t w[8], wn[8], ntok = 0;
+  FastCarry cL{0, 0, 0, 0};
+  for (uint32_t j = 0; j < h; j++) {  // lane L
+    uint32_t bm;
+    words_of(j, w); words_of(j + 1, wn);
+    ring.put(j, w); ring.put(j + 1, wn);
+    fast_chunk(w, nvalid(j), ring, len, 32 * j, cL, &s.tb(j), &bm);
+    if (bm) { if (j < 32) s.bs_lo |= 1u << j; else s.bs_hi |= 1u << (j - 32); }
+    if (s.tb(j)) { if (j < 32) s.nz_lo |= 1u << j; else s.nz_hi |= 1u << (j - 32); }
+    ntok += popc32(s.tb(j));
+  }
+  FastHalf H{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (h < nch) {  // lane H
+    FastCarry cH{0, 0, 0, 0};
+    words_of(h - 1, w);
+    cH.esc = fast_esc_after(fast_backslash_mask(w, 32), &cH.bad);
+    cH.bad_flip = cH.bad;
+    for (uint32_t j = h; j < nch; j++) {
+      uint32_t bm;
+      words_of(j, w); words_of(j + 1, wn);
+      ring.put(j, w); ring.put(j + 1, wn);
+      fast_chunk(w, nvalid(j), ring, len, 32 * j, cH, &s.tb(j), &bm);
+      fast_half_note(H, j, s.tb(j), bm, nvalid(j) >= 32 ? 0xffffffffu : ((1u << nvalid(j)) - 1u));
+    }
+    H.bad0 = cH.bad; H.bad1 = cH.bad_flip; H.parity = cH.in_str;
+  }
+  if (!fast_split_merge(s, len, h, cL, H, &ntok)) return false;
   const int nmem = fast_walk<0>(doc, kFastTablesHost.t, s, nch, KIND == K_REQ ? kFastKeyLensReq : kFastKeyLensResp);
   if (nmem < 0) return false;
   return fast_members<KIND>(doc, s, nch, nmem, out);

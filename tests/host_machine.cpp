@@ -169,18 +169,36 @@ int hm_work_profile(int kind, const uint8_t* body, size_t len, uint32_t* advance
 
 // ---- the fast path (arks_b200/csrc/mask_scan.cuh), host driver = exactly one lane's work: 1 = accepted (fields filled),
 // 0 = the document is left to the exact engine ----
+#include <cstdio>
+#include <cstdlib>
 #include "../arks_b200/csrc/mask_scan.cuh"
 extern "C" {
+// every call also runs the two-lane form of pass A (fast_scan_host_split): same verdict and same output, or the test dies
+static void split_must_agree(bool ok, const FastOut& o, bool ok2, const FastOut& o2, const uint8_t* body, size_t len) {
+  const bool same = ok == ok2 && (!ok || (o.m_start == o2.m_start && o.m_rawlen == o2.m_rawlen && o.m_esc == o2.m_esc && o.stream3 == o2.stream3 &&
+                                          o.so_present == o2.so_present && o.iu3 == o2.iu3 && o.usage[0] == o2.usage[0] &&
+                                          o.usage[1] == o2.usage[1] && o.usage[2] == o2.usage[2]));
+  if (!same) {
+    fprintf(stderr, "split pass A disagrees with the one-lane form (ok %d vs %d) on %zu bytes: %.*s\n", (int)ok, (int)ok2, len, (int)(len < 400 ? len : 400), body);
+    abort();
+  }
+}
 int hm_fast_request(const uint8_t* body, size_t len, uint32_t* span /* start, rawlen, esc */, int* stream, int* so_present, int* iu) {
-  FastOut o{};
-  if (len > 0xffffffffu || !fast_scan_host<K_REQ>(body, (uint32_t)len, o)) return 0;
+  FastOut o{}, o2{};
+  if (len > 0xffffffffu) return 0;
+  const bool ok = fast_scan_host<K_REQ>(body, (uint32_t)len, o), ok2 = fast_scan_host_split<K_REQ>(body, (uint32_t)len, o2);
+  split_must_agree(ok, o, ok2, o2, body, len);
+  if (!ok) return 0;
   span[0] = o.m_start; span[1] = o.m_rawlen; span[2] = o.m_esc;
   *stream = (int)o.stream3; *so_present = (int)o.so_present; *iu = (int)o.iu3;
   return 1;
 }
 int hm_fast_response(const uint8_t* body, size_t len, uint32_t* span, int64_t* usage) {
-  FastOut o{};
-  if (len > 0xffffffffu || !fast_scan_host<K_RESP>(body, (uint32_t)len, o)) return 0;
+  FastOut o{}, o2{};
+  if (len > 0xffffffffu) return 0;
+  const bool ok = fast_scan_host<K_RESP>(body, (uint32_t)len, o), ok2 = fast_scan_host_split<K_RESP>(body, (uint32_t)len, o2);
+  split_must_agree(ok, o, ok2, o2, body, len);
+  if (!ok) return 0;
   span[0] = o.m_start; span[1] = o.m_rawlen; span[2] = o.m_esc;
   usage[0] = o.usage[0]; usage[1] = o.usage[1]; usage[2] = o.usage[2];
   return 1;
