@@ -11,16 +11,25 @@
 //     quota[quota][3]   int64   cumulative usage, never reset (quota/redis_impl.go:38-48)
 //   per batch: bodies (16-byte aligned spans), tokens, a batch-local group table (qos -> arrivals), results.
 //
-// Kernels
-//   scan_request_kernel    one lane per request: JSON machine over the body, token lookup, qos/endpoint match,
-//                          static decision, and registration in the batch-local group table
+// Kernels (which scan kernel takes a batch depends on its size only)
+//   fast_request_kernel /  batches >= 4 096: a lane per document (mask_scan.cuh): SWAR masks over 32-byte chunks read with one
+//   fast_response_kernel   256-bit load each, grammar walk over the tokens outside strings (tables staged by one TMA bulk copy),
+//                          member extraction; then the same tail as the exact engine. Declined documents go on a slow list
+//   warp_request_kernel /  batches <= 2 048 (the latency path, warp_scan.cuh): a warp per document, body by one TMA bulk copy
+//   warp_response_kernel
+//   scan_request_kernel    the exact engine (json_engine.cuh): one lane per request, table-driven JSON machine over the body,
+//                          token lookup, qos / endpoint match, static decision, registration in the batch-local group table.
+//                          <.., FROM_LIST>: over the slow list of the kernels above
 //   limit_admit_kernel     one lane per request: closed-form fixed-window admission in arrival order
-//                          (SURVEY.md §8a A6), quota check, one commit per group, weighted pick (A12)
+//                          (SURVEY.md section 8a A6), quota check, one commit per group, weighted pick (A12)
 //   rank_hot_groups_kernel arrival ranks inside groups with more than 256 arrivals in one batch (a hot tenant)
-//   scan_response_kernel   one lane per complete response body: JSON machine, usage extraction and the unconditional
+//   scan_response_kernel   the exact engine for complete response bodies: usage extraction and the unconditional
 //                          counter increments (check.go:47-72) as warp-aggregated 64-bit atomics
 //   scan_sse_kernel        all-SSE batches: chunks cut into events (one lane per chunk), events parsed one per lane,
 //                          verdicts folded per chunk
+//   bpe_scan_kernel /      the token count of the north star (bpe.cuh): content strings -> pre-tokens -> merge loop per
+//   bpe_merge_kernel       pre-token, hot merges staged into shared memory by TMA
+//   carry_rows_kernel, fold_shared_kernel, gather_shared_kernel   generation swap / shared-quota fold (a few microseconds)
 //
 // Streams: uploads on `h2d`, everything that touches counters on `stream` (its order is the linearisation).
 #include <cuda_runtime.h>

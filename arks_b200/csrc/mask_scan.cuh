@@ -9,15 +9,16 @@
 // document and instead makes every loop body the same for every lane, whatever its document looks like:
 //
 //   pass A  (32 bytes per step, branch-free)  quote / backslash byte masks (SWAR) -> escaped characters (carry in a
-//           register) -> in-string mask (prefix XOR) -> string content checks -> the bitmap of bytes OUTSIDE strings goes to
-//           a per-lane array. Same instructions for prose, escapes, UTF-8, structure.
-//   pass B  one table step per byte outside strings (a few hundred per KiB of chat JSON, not per byte of text):
+//           register) -> in-string mask (prefix XOR) -> string content checks -> the bitmap of TOKENS (the bytes outside
+//           strings plus the opening quote of every string: a string is one token, its closing quote is "next token - 1")
+//           goes to a per-lane array. Same instructions for prose, escapes, UTF-8, structure.
+//   pass B  one table step per token (about fifty per KiB of chat JSON, not per byte of text):
 //           class = CLS[byte]; entry = TAB[state][class] -> next state, push / pop / comma actions on a 32-level bit stack,
 //           and three flags that log the members of the top-level object (key span, first byte of the value).
 //   pass C  the logged members are matched against the names the gateway reads and their values extracted; the
 //           stream_options / usage objects are read by a short token walk.
-//   Lanes only differ in trip counts (document length in A, structure bytes in B, members in C); the batch is ordered by
-//   length so that the lanes of a warp get similar ones.
+//   Lanes only differ in trip counts (document length in A, tokens in B, members in C); every block orders its own 128
+//   documents by length so that the lanes of a warp get similar ones (the batch itself stays in arrival order).
 //
 // This path is a FILTER in front of the exact engine, not a second definition of the decoders: it accepts a document only
 // if it lies in a conservative subset on which json-iterator (and encoding/json) agree with RFC 8259 — no control bytes
@@ -50,7 +51,7 @@ struct FastOut {
 // the arrays are in shared memory, lane-interleaved (stride = threads per block: every access of a warp is conflict-free
 // when the lanes use the same j, and no lane ever touches local memory); on the host stride is 1.
 struct FastScratch {
-  uint32_t* tb_;    // kFastChunks words: bytes outside strings (quotes included)
+  uint32_t* tb_;    // kFastChunks words: the tokens (bytes outside strings + the opening quote of every string)
   uint32_t* mem_;   // 2 * kFastMaxMembers words: key pos | key len << 16, value pos
   uint32_t stride;
   uint32_t bs_lo, bs_hi;  // chunk j contains a backslash (bit j): lets the key / model checks skip the byte scan
