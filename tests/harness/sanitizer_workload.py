@@ -1,5 +1,6 @@
-"""A small pass over every kernel (request scan, admit, hot-group ranking, JSON / SSE / mixed response scans, length order,
-quota sync) for compute-sanitizer: `compute-sanitizer --tool memcheck|racecheck python tests/harness/sanitizer_workload.py`."""
+"""A small pass over every kernel (request scan on all three paths — run with ARKS_FAST_MIN=1024 ARKS_WARP_MAX=512 so that these
+small batches reach the fast and the warp path —, admit, hot-group ranking, JSON / SSE / mixed response scans, generation
+swap, quota sync) for compute-sanitizer: `compute-sanitizer --tool memcheck|racecheck python tests/harness/sanitizer_workload.py`."""
 import os, sys
 _R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, _R); sys.path.insert(0, os.path.join(_R, "tests"))
@@ -27,6 +28,9 @@ for n in (37, 5000):  # one body per warp / length-ordered full warps (and a hot
         c, d = g.handle_response_body(rb), o.response_batch(rb)
         assert all(np.array_equal(v, d.fields()[k]) for k, v in c.fields().items()), name
     now += 61
+    # a generation swap between the batches: the carry kernels move every counter by key (here: the same tables again)
+    g.commit_tables(g.prepare_tables(w.tables)); o.reload(w.tables)
+    assert np.array_equal(g.snapshot_rate(now), o.snapshot_rate(now)) and np.array_equal(g.snapshot_quota(), o.snapshot_quota())
 pres = np.zeros(w.tables.n_quotas, np.uint32); used = np.zeros((w.tables.n_quotas, 3), np.int64)
 g.sync_quota_usage(pres, used)
 assert np.array_equal(g.snapshot_metrics(), o.snapshot_metrics())
