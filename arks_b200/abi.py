@@ -83,7 +83,8 @@ class ArksRequestResult(C.Structure):
 
 class ArksResponseBatch(C.Structure):
     _fields_ = [("n", C.c_uint32), ("bodies", u8p), ("body_off", u32p), ("body_len", u32p),
-                ("bodies_bytes", C.c_uint64), ("qos", i32p), ("flags", u8p), ("now_unix", C.c_int64), ("gen", u32p)]
+                ("bodies_bytes", C.c_uint64), ("qos", i32p), ("flags", u8p), ("now_unix", C.c_int64), ("gen", u32p),
+                ("precharged", u32p)]
 
 
 class ArksResponseResult(C.Structure):
@@ -200,6 +201,7 @@ class ResponseBatch:
     flags: np.ndarray
     now_unix: int
     gen: np.ndarray | None = None  # table generation of each row's request (None: the current one)
+    precharged: np.ndarray | None = None  # N4: what the request phase charged the token-type rules for each row's stream
 
     @property
     def n(self) -> int:
@@ -214,7 +216,7 @@ class ResponseBatch:
     def c_struct(self) -> ArksResponseBatch:
         return ArksResponseBatch(self.n, ptr(self.bodies, u8p), ptr(self.body_off, u32p), ptr(self.body_len, u32p),
                                  int(self.bodies.shape[0]), ptr(self.qos, i32p), ptr(self.flags, u8p), self.now_unix,
-                                 ptr(self.gen, u32p))
+                                 ptr(self.gen, u32p), ptr(self.precharged, u32p))
 
 
 @dataclass

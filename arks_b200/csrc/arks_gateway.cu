@@ -138,6 +138,7 @@ struct ReqDev {  // request batch, device resident
   uint32_t* model_off;  // raw span of the model string inside the body (host-side error shaping)
   uint32_t* model_len;  // bit 31: the span contains a backslash
   uint32_t* bpe;        // BPE tokens of the prompt text (0 without a vocabulary)
+  int precharge;  // N4: admitted requests charge their BPE count to the token-type rules
 };
 
 struct RespDev {
@@ -155,6 +156,7 @@ struct RespDev {
   uint32_t* slow_list;  // two-stage scan: the bodies left to the exact engine
   uint32_t* slow_n;
   uint32_t* bpe;        // BPE tokens of the completion text (0 without a vocabulary)
+  const uint32_t* precharged;  // n or null: what the request phase charged the token-type rules for this stream (N4)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1268,7 +1270,13 @@ __global__ void __launch_bounds__(128) limit_admit_kernel(DevTables T, ReqDev B)
         if (qt == ARKS_QUOTA_MISSING) reason = ARKS_R_QUOTA_CONFIG;
         else { reason = ARKS_R_QUOTA; detail = (uint8_t)quota_fail; cur_out = q_cur; lim_out = q_lim; }
       }
-    } else if (B.pick_rand) {
+    }
+    if (admitted && B.precharge) {  // N4 (opt-in): the estimate is charged when the micro-batch commits; nobody reads T.rate here
+      const uint32_t est = B.bpe[i] == kBpeUncounted ? 0u : B.bpe[i];
+      if (est && cnt[2]) atomicAdd(reinterpret_cast<unsigned long long*>(T.rate + (size_t)2 * T.n_qos + qos), (unsigned long long)est * (unsigned long long)cnt[2]);
+      if (est && cnt[3]) atomicAdd(reinterpret_cast<unsigned long long*>(T.rate + (size_t)3 * T.n_qos + qos), (unsigned long long)est * (unsigned long long)cnt[3]);
+    }
+    if (admitted && B.pick_rand) {
       // Envoy's weighted choice over the HTTPRoute backendRefs order (arksendpoint_controller.go:283-347)
       unsigned long long sum = 0;
       for (uint32_t b = b0; b < b1; b++) sum += (unsigned long long)max(T.backend_weight[b], 0);
@@ -1371,9 +1379,10 @@ __device__ __forceinline__ void account_usage(const DevTables& T, const RespDev&
   }
   // doTokenRateLimit: += total on every token-type entry (check.go:47-59). Warp-aggregated per address.
   const int32_t qt = counted ? acct.qt : ARKS_QUOTA_NONE;
+  const long long pre = B.precharged && live ? (long long)B.precharged[i] : 0;  // N4: the request phase's estimate is reconciled
 #pragma unroll
   for (int r = 0; r < 2; r++)
-    warp_agg_add(T.rate + (size_t)(2 + r) * T.n_qos + qos, u2 * (long long)acct.nt[r], counted && acct.nt[r]);
+    warp_agg_add(T.rate + (size_t)(2 + r) * T.n_qos + qos, (u2 - pre) * (long long)acct.nt[r], counted && acct.nt[r]);
   // doTokenQuotaLimit: QosToQuotaRequests + IncrUsage (check.go:62-72, qosconfig/types.go:45-72)
   long long add[3] = {0, 0, 0};
   if (counted && qt == ARKS_QUOTA_MISSING) reason = ARKS_R_QUOTA_CONFIG_RESP;
@@ -1833,6 +1842,7 @@ struct arks_ctx {
   cudaStream_t h2d = nullptr;     // batch uploads (overlap the kernels of earlier batches)
   cudaStream_t cfg_stream = nullptr;  // config plane: the next generation's tables are uploaded here, off the data path
   std::mutex cfg_mu;                  // prepare (config thread) vs commit (batch thread)
+  bool precharge = false;              // N4 (arks_set_precharge)
   bool split = false;                  // fast path: two lanes per document in pass A (fast_*_kernel2), ARKS_SPLIT=1; measured slower
   bool walk8 = true;                   // fast path, pass B: the step inlined eight times (true) or one copy in a loop
   int regroup = 1;                     // fast path: regroup a block's documents by structure between passes A and B
@@ -2607,6 +2617,11 @@ int32_t arks_find_qos(const arks_ctx* ctx, const char* ns, uint32_t ns_len, cons
 }
 
 uint32_t arks_table_generation(const arks_ctx* ctx) { return ctx ? ctx->generation : 0; }
+int arks_set_precharge(arks_ctx* ctx, int on) {
+  if (!ctx) return ARKS_E_INVALID_ARG;
+  ctx->precharge = on != 0;
+  return 0;
+}
 
 int arks_update_endpoint_weights(arks_ctx* ctx, uint32_t ep, uint32_t n, const int32_t* w) {
   if (!ctx || !ctx->loaded) return ARKS_E_NOT_LOADED;
@@ -2906,6 +2921,7 @@ int arks_run_request_batch(arks_ctx* ctx, int64_t now_unix) {
     rank_hot_groups_kernel<<<296, 256, 0, ctx->stream>>>(r);  // exits at once when scan_request listed no hot group
     ctx->launches += 1;
   }
+  r.precharge = ctx->precharge && ctx->bpe_on ? 1 : 0;
   limit_admit_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dt, r);
   if (ctx->prof) { CK(cudaEventRecord(ctx->ev[2], ctx->stream)); ctx->ev_n = 3; ctx->is_req_timing = true; }
   CK(cudaEventRecord(sl.req_ran, ctx->stream));
@@ -3026,7 +3042,8 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   sl.resp_mode = n_sse == 0 ? 1 : n_sse == n ? 2 : 0;
   sl.resp_n_sse = n_sse;
   size_t o_off = 0, o_len = align_up((size_t)n * 4, 256), o_qos = o_len * 2, o_fl = o_len * 3, o_kind = o_fl + align_up(n, 256),
-         total = o_kind + (sl.resp_mode == 0 ? o_len : 0);
+         o_pre = o_kind + (sl.resp_mode == 0 ? o_len : 0), total = o_pre + (b->precharged ? o_len : 0);
+  if (total + (b->bodies_bytes <= kTinyBatchBytes ? b->bodies_bytes : 0) > ctx->meta_cap) return fail(ctx, ARKS_E_CAPACITY, "response metadata exceeds capacity");
   CK(cudaEventSynchronize(sl.resp_copied));
   uint8_t* h = sl.h_resp_meta;
   if (sl.resp_mode == 0) {  // mixed batch: complete bodies first, SSE chunks after; each kind goes to its own kernel
@@ -3045,6 +3062,7 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
     for (uint32_t i = 0; i < n; i++) hq[i] = resolve_qos(ctx, b->qos[i], b->gen ? b->gen[i] : ctx->generation);
   }
   memcpy(h + o_fl, b->flags, n);
+  if (b->precharged) memcpy(h + o_pre, b->precharged, (size_t)n * 4);
   const bool small = b->bodies_bytes <= kSmallBatchBytes;
   if (small) {  // uploads on the compute stream (see kSmallBatchBytes / kTinyBatchBytes)
     if (b->bodies_bytes <= kTinyBatchBytes) {
@@ -3067,6 +3085,7 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   r.body_len = (const uint32_t*)(sl.d_resp_meta + o_len);
   r.qos = (const int32_t*)(sl.d_resp_meta + o_qos);
   r.flags = sl.d_resp_meta + o_fl;
+  r.precharged = b->precharged ? (const uint32_t*)(sl.d_resp_meta + o_pre) : nullptr;
   r.n = n;
   sl.d_resp_kind = reinterpret_cast<const uint32_t*>(sl.d_resp_meta + o_kind);
   sl.resp_zc = n <= kZeroCopyRows && sl.h_resp_result;

@@ -63,6 +63,7 @@ def lib():
         L.arks_find_quota.restype = C.c_int32
         L.arks_find_qos.argtypes = [vp, cp, u32, cp, u32, cp, u32]
         L.arks_find_qos.restype = C.c_int32
+        L.arks_set_precharge.argtypes = [vp, C.c_int]
         L.arks_table_generation.restype = C.c_uint32
         L.arks_table_generation.argtypes = [vp]
         L.arks_update_endpoint_weights.argtypes = [vp, C.c_uint32, C.c_uint32, abi.i32p]
@@ -111,7 +112,7 @@ def lib():
 
 
 EXPORTED = [  # every symbol include/arks_gateway.h declares (checked by tests/test_abi.py)
-    "arks_abi_version", "arks_create", "arks_destroy", "arks_last_error", "arks_load_tables", "arks_table_generation", "arks_load_bpe",
+    "arks_abi_version", "arks_create", "arks_destroy", "arks_last_error", "arks_load_tables", "arks_table_generation", "arks_load_bpe", "arks_set_precharge",
     "arks_prepare_tables", "arks_commit_tables", "arks_discard_prepared", "arks_upsert_token", "arks_delete_token", "arks_upsert_quota",
     "arks_delete_quota", "arks_upsert_endpoint", "arks_delete_endpoint", "arks_config_prepare", "arks_find_quota", "arks_find_qos",
     "arks_update_endpoint_weights", "arks_extract_bearer", "arks_submit_request_batch",
@@ -232,6 +233,11 @@ class Gateway:
             return
         ts = tables.c_struct()
         self._ck(lib().arks_load_bpe(self._h, C.byref(ts)))
+
+    def set_precharge(self, on: bool):
+        """N4, opt-in: admitted requests charge their prompt's BPE count to tpm / tpd when their batch commits; responses that
+        carry `precharged` reconcile (needs load_bpe; changes admit / deny against the reference)"""
+        self._ck(lib().arks_set_precharge(self._h, int(bool(on))))
 
     @property
     def generation(self) -> int:

@@ -190,6 +190,9 @@ typedef struct arks_response_batch {
                           * positional in the tables of ITS generation; rows of an older generation are re-mapped by their
                           * (namespace,user,model) key (the last ARKS_GEN_HISTORY generations are kept) or answered
                           * ARKS_R_QOS_GONE. NULL: every row belongs to the current generation. */
+  const uint32_t* precharged; /* n or NULL: what arks_set_precharge charged the token-type rules for this stream at request time
+                               * (arks_request_result.bpe_count of its request): the token-type rules are then charged
+                               * total_tokens - precharged, the difference between the upstream's count and the estimate */
 } arks_response_batch;
 #define ARKS_GEN_HISTORY 16
 
@@ -279,6 +282,14 @@ typedef struct arks_bpe_tables {
 } arks_bpe_tables;
 /* copies the tables to the device and switches the bpe_count columns on (NULL: off) */
 int arks_load_bpe(arks_ctx* ctx, const arks_bpe_tables* t);
+/* N4, OPT-IN because it changes admit / deny against the reference, which counts no tokens at request
+ * time ("token is not caculated in request", pkg/gateway/check.go:124-126: a tenant over its TPM is only stopped once the
+ * upstream has answered). With precharge on and a vocabulary loaded, every ADMITTED request adds its prompt's BPE count to
+ * the tpm / tpd counters of its qos entry when its micro-batch commits (checks inside a micro-batch see the counters as of
+ * the batch's start, as they do for token-type rules today), and the response phase reconciles: it adds total_tokens minus
+ * arks_response_batch.precharged. A stream whose response never arrives keeps its estimate charged. Quotas are untouched
+ * (they bill what the upstream reports). Off by default: decisions are the reference's. */
+int arks_set_precharge(arks_ctx* ctx, int on);
 
 /* routing churn (BASELINE config 5): replace the weights of one endpoint's backends in place */
 int arks_update_endpoint_weights(arks_ctx* ctx, uint32_t endpoint, uint32_t n, const int32_t* weights);

@@ -28,6 +28,9 @@ int ork_update_endpoint_weights(ork* o, uint32_t endpoint, uint32_t n, const int
 /* serial batch application: request i is fully applied (check, then increment) before i+1 */
 int ork_request_batch(ork* o, const arks_request_batch* b, arks_request_result* r);
 int ork_response_batch(ork* o, const arks_response_batch* b, arks_response_result* r);
+/* N4 (arks_set_precharge): the mode, and the prompt token counts of the NEXT request batch (the oracle has no tokenizer) */
+void ork_set_precharge(ork* o, int on);
+void ork_set_estimates(ork* o, const uint32_t* est, uint32_t n);
 /* tenant-sharded multi-thread variants (cpu baseline): shard = hash(namespace) % nthreads */
 int ork_request_batch_mt(ork* o, const arks_request_batch* b, arks_request_result* r, int nthreads);
 int ork_response_batch_mt(ork* o, const arks_response_batch* b, arks_response_result* r, int nthreads);

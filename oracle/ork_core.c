@@ -56,6 +56,13 @@ struct ork {
   int64_t* quota_use; /* n_quotas * 3 */
   int64_t* metrics;   /* n_qos * ARKS_METRIC_COLS: the Prometheus series that are functions of the request stream */
   int64_t last_win[4];
+  /* N4 (opt-in precharge, include/arks_gateway.h arks_set_precharge): the estimates of the NEXT request batch (the oracle has
+   * no tokenizer: the test hands it the counts) and what that batch charges when it commits */
+  int precharge;
+  const uint32_t* est;
+  uint32_t est_n;
+  struct { uint32_t q; int rule; int64_t amount; }* pc;
+  uint32_t pc_n, pc_cap;
 };
 
 /* ---------- small helpers ---------- */
@@ -266,6 +273,7 @@ void ork_destroy(ork* o) {
   free(o->rate_val);
   free(o->quota_use);
   free(o->metrics);
+  free(o->pc);
   free(o);
 }
 
@@ -467,6 +475,15 @@ static void handle_request(ork* o, const arks_request_batch* b, arks_request_res
   for (uint32_t j = rl0; j < rl1; j++) {
     int rule = o->rl_rule[j];
     if (RULE_IS_REQUEST[rule]) rate_incr(o, (uint32_t)q, rule, ork_window_start(b->now_unix, rule), 1);
+    else if (o->precharge && o->est && i < o->est_n && o->est[i] && o->est[i] != 0xFFFFFFFFu) {
+      /* N4: the estimate is charged when the batch commits (ork_request_batch): checks inside the batch see the batch's start */
+      if (o->pc_n == o->pc_cap) {
+        o->pc_cap = o->pc_cap ? 2 * o->pc_cap : 1024;
+        o->pc = realloc(o->pc, o->pc_cap * sizeof *o->pc);
+      }
+      o->pc[o->pc_n].q = (uint32_t)q; o->pc[o->pc_n].rule = rule; o->pc[o->pc_n].amount = o->est[i];
+      o->pc_n++;
+    }
   }
   /* 9. BodyResponse{model, namespace, username}; weighted pick is Envoy's (A12) */
   r->flags[out] = stream ? 1 : 0;
@@ -540,7 +557,8 @@ static void handle_response_inner(ork* o, const arks_response_batch* b, arks_res
     /* doTokenRateLimit: INCRBY total per token-type entry              check.go:47-59 */
     for (uint32_t j = o->qos_rl_off[q]; j < o->qos_rl_off[q + 1]; j++) {
       int rule = o->rl_rule[j];
-      if (!RULE_IS_REQUEST[rule]) rate_incr(o, (uint32_t)q, rule, ork_window_start(b->now_unix, rule), usage[2]);
+      if (!RULE_IS_REQUEST[rule]) /* N4: minus what the request phase charged for this stream, if the host says so */
+        rate_incr(o, (uint32_t)q, rule, ork_window_start(b->now_unix, rule), usage[2] - (b->precharged ? (int64_t)b->precharged[i] : 0));
     }
     /* doTokenQuotaLimit: QosToQuotaRequests(conf, countMap) -> IncrUsage   check.go:62-72 */
     int32_t qt = o->qos_quota[q];
@@ -561,8 +579,14 @@ int ork_request_batch(ork* o, const arks_request_batch* b, arks_request_result* 
   int rc = check_time(o, b->now_unix);
   if (rc) return rc;
   for (uint32_t i = 0; i < b->n; i++) handle_request(o, b, r, i, i);
+  for (uint32_t k = 0; k < o->pc_n; k++) rate_incr(o, o->pc[k].q, o->pc[k].rule, ork_window_start(b->now_unix, o->pc[k].rule), o->pc[k].amount);
+  o->pc_n = 0;
+  o->est = NULL; /* estimates belong to one batch */
+  o->est_n = 0;
   return 0;
 }
+void ork_set_precharge(ork* o, int on) { o->precharge = on != 0; }
+void ork_set_estimates(ork* o, const uint32_t* est, uint32_t n) { o->est = est; o->est_n = n; }
 int ork_response_batch(ork* o, const arks_response_batch* b, arks_response_result* r) {
   int rc = check_time(o, b->now_unix);
   if (rc) return rc;

@@ -41,6 +41,10 @@ def lib():
         L.ork_create.argtypes = [C.POINTER(ArksTables)]
         L.ork_destroy.argtypes = [C.c_void_p]
         L.ork_reload.argtypes = [C.c_void_p, C.POINTER(ArksTables)]
+        L.ork_set_precharge.argtypes = [C.c_void_p, C.c_int]
+        L.ork_set_precharge.restype = None
+        L.ork_set_estimates.argtypes = [C.c_void_p, abi.u32p, C.c_uint32]
+        L.ork_set_estimates.restype = None
         L.ork_update_endpoint_weights.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, abi.i32p]
         for f in ("ork_request_batch",):
             getattr(L, f).argtypes = [C.c_void_p, C.POINTER(ArksRequestBatch), C.POINTER(ArksRequestResult)]
@@ -86,6 +90,14 @@ class Oracle:
         if getattr(self, "h", None):
             lib().ork_destroy(self.h)
             self.h = None
+
+    def set_precharge(self, on: bool):
+        lib().ork_set_precharge(self.h, int(bool(on)))
+
+    def set_estimates(self, est):
+        """prompt token counts of the NEXT request batch (N4; the oracle has no tokenizer of its own)"""
+        self._est = np.ascontiguousarray(est, np.uint32)
+        lib().ork_set_estimates(self.h, abi.ptr(self._est, abi.u32p), len(self._est))
 
     def reload(self, tables):
         ts = tables.c_struct()
