@@ -168,7 +168,7 @@ typedef struct arks_request_result {
                          *    of the body                                                                               */
   uint32_t* bpe_count;  /* n: BPE tokens of the prompt text (see arks_load_bpe); 0 when no vocabulary is loaded. A side
                          *    output: the reference counts no tokens at request time (check.go:124-126), so this never
-                         *    feeds admit/deny unless ARKS_OPT_PRECHARGE_TPM is switched on                              */
+                         *    feeds admit/deny unless arks_set_precharge is switched on                              */
 } arks_request_result;
 
 /* ---- response phase (ProcessingRequest_ResponseBody with :status 200, handle_response.go:80-268) ---- */
