@@ -367,7 +367,7 @@ ARKS_HD bool any_backslash(const uint8_t* doc, const FastScratch& s, uint32_t b,
 struct KeyLit {
   uint64_t w[3];
 };
-constexpr KeyLit key_lit(const char* s, int n) {
+ARKS_HD constexpr KeyLit key_lit(const char* s, int n) {
   KeyLit k{{0, 0, 0}};
   for (int i = 0; i < n; i++) k.w[i >> 3] |= (uint64_t)(uint8_t)s[i] << (8 * (i & 7));
   return k;

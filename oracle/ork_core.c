@@ -687,7 +687,7 @@ static void* mt_resp(void* p) {
   for (uint32_t i = 0; i < n; i++) mine += a->shard[i] == a->tid;
   mt_priv* me = &a->priv[a->tid];
   priv_alloc(me, mine, 0);
-  arks_response_result pr = {me->reason, me->counted, me->usage};
+  arks_response_result pr = {me->reason, me->counted, me->usage, NULL};
   uint32_t k = 0;
   for (uint32_t i = 0; i < n; i++)
     if (a->shard[i] == a->tid) {
