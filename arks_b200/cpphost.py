@@ -39,7 +39,7 @@ REQ_DTYPE = np.dtype(RequestDecision)
 RESP_DTYPE = np.dtype(ResponseDecision)
 EXPORTED = ["arks_host_create", "arks_host_destroy", "arks_host_set_fixed_clock", "arks_host_request", "arks_host_response",
             "arks_host_stats", "arks_host_run_requests", "arks_host_run_responses", "arks_host_open_loop_requests",
-            "arks_host_stream_transcript", "arks_host_load_tables", "arks_host_apply_config", "arks_host_set_names", "arks_host_request_error_reply",
+            "arks_host_stream_transcript", "arks_host_load_tables", "arks_host_apply_config", "arks_host_set_precharge", "arks_host_response_pre", "arks_host_set_names", "arks_host_request_error_reply",
             "arks_host_response_error_reply"]
 
 
@@ -69,6 +69,8 @@ def load(path: str = LIB):
     L.arks_host_response.argtypes = [vp, C.c_int32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint8, C.POINTER(ResponseDecision)]
     L.arks_host_load_tables.argtypes = [vp, vp]
     L.arks_host_apply_config.argtypes = [vp]
+    L.arks_host_set_precharge.argtypes = [vp, C.c_int]
+    L.arks_host_response_pre.argtypes = [vp, C.c_int32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint8, C.POINTER(ResponseDecision)]
     L.arks_host_reset_tail.argtypes = [vp]
     L.arks_host_reset_tail.restype = None
     L.arks_host_open_loop_lateness.restype = None
@@ -122,11 +124,16 @@ class Batcher:
         self.L.arks_host_request(self._h, token, len(token), body, len(body), pick_rand, C.byref(d))
         return d
 
-    def response(self, qos: int, body: bytes, flags: int, gen: int = None) -> ResponseDecision:
-        """`gen`: RequestDecision.gen of the stream's request; None = the tables have not changed since"""
+    def response(self, qos: int, body: bytes, flags: int, gen: int = None, precharged: int = 0) -> ResponseDecision:
+        """`gen`: RequestDecision.gen of the stream's request; None = the tables have not changed since. `precharged`: its
+        RequestDecision.bpe_count while set_precharge(True) is in force (N4)"""
         d = ResponseDecision()
-        self.L.arks_host_response(self._h, qos, 0xFFFFFFFF if gen is None else gen, body, len(body), flags, C.byref(d))
+        self.L.arks_host_response_pre(self._h, qos, 0xFFFFFFFF if gen is None else gen, precharged, body, len(body), flags, C.byref(d))
         return d
+
+    def set_precharge(self, on: bool):
+        if self.L.arks_host_set_precharge(self._h, int(bool(on))):
+            raise RuntimeError("arks_host_set_precharge failed")
 
     def load_tables(self, tables):
         """config reload between two cycles (Batcher::LoadTables); also refreshes the reply-shaping names"""

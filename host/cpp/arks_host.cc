@@ -53,6 +53,7 @@ struct Block {
   uint64_t* rnd = nullptr;
   int32_t* qos = nullptr;         // responses
   uint32_t* gen = nullptr;
+  uint32_t* pre = nullptr;        // N4: the request phase's estimate of each row's stream
   uint8_t* flags = nullptr;
   // per-row completion
   RequestCallback* rcb = nullptr;
@@ -141,6 +142,7 @@ struct Batcher::Impl {
   bool slot_busy[kSlots] = {false, false, false, false};
   mutable std::mutex mu;
   std::mutex cfg_mu;  // config calls among themselves
+  std::atomic<bool> precharge{false};  // N4: response batches carry the streams' estimates
   int swap_in(arks_prepared* p);
   std::condition_variable cv_work, cv_space, cv_done;
   bool stop = false;
@@ -152,7 +154,8 @@ struct Batcher::Impl {
   std::thread dispatcher, completer;
 
   bool submit_request(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user, bool can_lead);
-  bool submit_response(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user, bool can_lead);
+  bool submit_response(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user, bool can_lead,
+                       uint32_t precharged);
   int64_t last_now = INT64_MIN;  // batches never carry an earlier clock reading than their predecessor
 
   void alloc(Block& b, bool is_req) {
@@ -175,6 +178,7 @@ struct Batcher::Impl {
     } else {
       b.qos = pinned<int32_t>(m);
       b.gen = pinned<uint32_t>(m);
+      b.pre = pinned<uint32_t>(m);
       b.flags = pinned<uint8_t>(m);
       b.pcb = new ResponseCallback[m];
       b.reason = new uint8_t[m]; b.counted = new uint8_t[m]; b.usage = new int64_t[3 * (size_t)m];
@@ -356,6 +360,7 @@ struct Batcher::Impl {
       rb.n = n; rb.bodies = b.bodies; rb.body_off = b.body_off + lo; rb.body_len = b.body_len + lo;
       rb.bodies_bytes = span_end(b, f.resp.hi);
       rb.qos = b.qos + lo; rb.flags = b.flags + lo; rb.now_unix = now; rb.gen = b.gen + lo;
+      rb.precharged = precharge.load(std::memory_order_relaxed) ? b.pre + lo : nullptr;
       f.rc_resp = arks_submit_response_async(ctx, &rb);
     }
     const auto t_b = std::chrono::steady_clock::now();
@@ -598,7 +603,7 @@ bool Batcher::Impl::submit_request(std::string_view token, std::string_view body
 }
 
 bool Batcher::Impl::submit_response(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user,
-                                    bool can_lead) {
+                                    bool can_lead, uint32_t precharged) {
   Impl& I = *this;
   const size_t need = align16(body.size());
   if (need > I.opt.max_bytes) return false;
@@ -610,6 +615,7 @@ bool Batcher::Impl::submit_response(int32_t qos, uint32_t gen, std::string_view 
   b->body_len[row] = (uint32_t)body.size();
   b->qos[row] = qos;
   b->gen[row] = gen;
+  b->pre[row] = precharged;
   b->flags[row] = flags;
   b->pcb[row] = cb;
   b->user[row] = user;
@@ -628,10 +634,16 @@ bool Batcher::Impl::submit_response(int32_t qos, uint32_t gen, std::string_view 
 bool Batcher::SubmitRequest(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user) {
   return p_->submit_request(token, body, pick_rand, cb, user, false);
 }
-bool Batcher::SubmitResponse(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user) {
-  return p_->submit_response(qos, gen, body, flags, cb, user, false);
+bool Batcher::SubmitResponse(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user, uint32_t precharged) {
+  return p_->submit_response(qos, gen, body, flags, cb, user, false, precharged);
 }
 uint32_t Batcher::Generation() const { return arks_table_generation(p_->ctx); }
+int Batcher::SetPrecharge(bool on) {
+  const int rc = arks_set_precharge(p_->ctx, on ? 1 : 0);
+  if (!rc) p_->precharge.store(on, std::memory_order_relaxed);
+  return rc;
+}
+bool Batcher::Precharge() const { return p_->precharge.load(std::memory_order_relaxed); }
 // config calls are serialised among themselves; the swap itself happens between two cycles
 int Batcher::LoadTables(const arks_tables* t) {
   Impl& I = *p_;
@@ -676,9 +688,9 @@ RequestDecision Batcher::HandleRequestBody(std::string_view token, std::string_v
   p.ready.wait(0, std::memory_order_acquire);  // futex sleep until the completion thread hands the decision over
   return p.rd;
 }
-ResponseDecision Batcher::HandleResponseBody(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags) {
+ResponseDecision Batcher::HandleResponseBody(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, uint32_t precharged) {
   Parked p;
-  if (!p_->submit_response(qos, gen, body, flags, wake_response, &p, true)) {
+  if (!p_->submit_response(qos, gen, body, flags, wake_response, &p, true, precharged)) {
     ResponseDecision d{};
     d.reason = kReasonHostError;
     return d;
@@ -984,7 +996,7 @@ Action StreamProcessor::OnResponseBody(std::string_view body, bool end_of_stream
   // gateway.go:122-126: the upstream's error body is passed on; `resp` is still empty there, so no x-error-* header
   if (status_ != 200) return ErrorResponse(status_, {}, std::string(body));
   if (stream_) {
-    resp_ = b_->HandleResponseBody(qos_, gen_, body, ARKS_RESP_STREAM);
+    resp_ = b_->HandleResponseBody(qos_, gen_, body, ARKS_RESP_STREAM, Estimate());
   } else {
     buffered_.append(body);  // requestBuffers, handle_response.go:134-155
     if (!end_of_stream) {
@@ -992,7 +1004,7 @@ Action StreamProcessor::OnResponseBody(std::string_view body, bool end_of_stream
       a.kind = Action::kContinueResponseBody;
       return a;
     }
-    resp_ = b_->HandleResponseBody(qos_, gen_, buffered_, ARKS_RESP_END_OF_STREAM);
+    resp_ = b_->HandleResponseBody(qos_, gen_, buffered_, ARKS_RESP_END_OF_STREAM, Estimate());
   }
   if (resp_.reason != ARKS_R_OK && resp_.reason != ARKS_R_PENDING && resp_.reason != ARKS_R_QOS_GONE)
     return reply_action(ResponseErrorReply(resp_, *names_, qos_, body));
@@ -1078,6 +1090,12 @@ int arks_host_response(arks_host_batcher* h, int32_t qos, uint32_t gen, const ui
 }
 int arks_host_load_tables(arks_host_batcher* h, const arks_tables* t) { return h->b->LoadTables(t); }
 int arks_host_apply_config(arks_host_batcher* h) { return h->b->ApplyConfig(); }
+int arks_host_set_precharge(arks_host_batcher* h, int on) { return h->b->SetPrecharge(on != 0); }
+int arks_host_response_pre(arks_host_batcher* h, int32_t qos, uint32_t gen, uint32_t precharged, const uint8_t* body, uint32_t body_len,
+                           uint8_t flags, arks_host::ResponseDecision* out) {
+  *out = h->b->HandleResponseBody(qos, gen == 0xffffffffu ? h->b->Generation() : gen, std::string_view((const char*)body, body_len), flags, precharged);
+  return out->reason == 255 ? ARKS_E_INVALID_ARG : 0;
+}
 int arks_host_set_names(arks_host_batcher* h, const char* text, uint32_t len) {
   return ParseNameTables(std::string_view(text, len), &h->names) ? 0 : ARKS_E_INVALID_ARG;
 }

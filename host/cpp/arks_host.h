@@ -84,12 +84,17 @@ class Batcher {
   // A row that can never fit (body larger than max_bytes) is answered with reason 255 without touching the device.
   RequestDecision HandleRequestBody(std::string_view token, std::string_view body, uint64_t pick_rand);
   // `gen`: RequestDecision::gen of the stream's request (the generation its qos index belongs to)
-  ResponseDecision HandleResponseBody(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags);
+  // `precharged`: RequestDecision.bpe_count of the stream's request when SetPrecharge(true) is in force (N4), else 0
+  ResponseDecision HandleResponseBody(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, uint32_t precharged = 0);
   // Asynchronous form for event-driven servers: returns once the row is staged (the body is copied, the caller's buffer
   // is free again); `cb(user, decision)` runs later on the completion thread, rows of a batch in order. false: the row
   // can never fit, cb is not called.
   bool SubmitRequest(std::string_view token, std::string_view body, uint64_t pick_rand, RequestCallback cb, void* user);
-  bool SubmitResponse(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user);
+  bool SubmitResponse(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user, uint32_t precharged = 0);
+  // N4, opt-in (arks_set_precharge): the library charges every admitted request's prompt count to tpm / tpd; from then on the
+  // response batches carry each stream's estimate back so that the accounting adds total_tokens - estimate
+  int SetPrecharge(bool on);
+  bool Precharge() const;
 
   // Config change while streams are in flight (qosconfig informer event): the next generation is built and uploaded on
   // the CALLING (config) thread with batches still running (arks_prepare_tables), then swapped in between two cycles
@@ -155,6 +160,9 @@ class StreamProcessor {
   int status_ = 0;
   RequestDecision req_{};
   ResponseDecision resp_{};
+  // what the request phase charged for this stream (N4), handed back with every response chunk: the library subtracts it
+  // from the one chunk that carries the usage
+  uint32_t Estimate() const { return b_->Precharge() && req_.bpe_count != 0xFFFFFFFFu ? req_.bpe_count : 0u; }
 };
 
 // generateErrorResponse, util.go:40-77: status + headers + Content-Type + {"error":{"message":..,"code":..}}
@@ -188,7 +196,10 @@ int arks_host_load_tables(arks_host_batcher* b, const arks_tables* t);
 void arks_host_reset_tail(arks_host_batcher* b);
 void arks_host_open_loop_lateness(int64_t out[3]);
 void arks_host_open_loop_call_latency(int64_t* buf); /* n entries filled by the next open-loop run: decision - time of the call */
-int arks_host_apply_config(arks_host_batcher* b); /* publishes arks_upsert_* / arks_delete_* done on the context */
+int arks_host_apply_config(arks_host_batcher* b);
+int arks_host_set_precharge(arks_host_batcher* b, int on);
+int arks_host_response_pre(arks_host_batcher* b, int32_t qos, uint32_t gen, uint32_t precharged, const uint8_t* body, uint32_t body_len,
+                           uint8_t flags, arks_host::ResponseDecision* out); /* publishes arks_upsert_* / arks_delete_* done on the context */
 // names for the reply shapes of arks_host_stream_transcript / arks_host_error_reply (format: ParseNameTables)
 int arks_host_set_names(arks_host_batcher* b, const char* text, uint32_t len);
 // the reference-exact reply of a failed request / response decision as "status\nheader\nheader value\nmessage"

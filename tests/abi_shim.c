@@ -21,6 +21,7 @@ struct arks_ctx {
   ork* o;
   int cur;
   uint32_t generation;
+  int precharge;
   struct slot_res rq[SHIM_SLOTS], rs[SHIM_SLOTS];
 };
 
@@ -64,7 +65,22 @@ void arks_shim_destroy(arks_ctx* c) {
   ork_destroy(c->o);
   free(c);
 }
-int arks_submit_request_batch(arks_ctx* c, const arks_request_batch* b, arks_request_result* r) { return ork_request_batch(c->o, b, r); }
+/* N4 through the shim: the oracle has no tokenizer, so the stand-in "prompt count" of a request is body_len / 4 — what matters
+ * to the host tests is that the estimate the request phase reports comes back with the stream's response */
+int arks_set_precharge(arks_ctx* c, int on) { c->precharge = on != 0; ork_set_precharge(c->o, on); return 0; }
+static int shim_request(arks_ctx* c, const arks_request_batch* b, arks_request_result* r) {
+  uint32_t* est = NULL;
+  if (c->precharge && b->n) {
+    est = (uint32_t*)malloc(4 * (size_t)b->n);
+    for (uint32_t i = 0; i < b->n; i++) est[i] = b->body_len[i] / 4;
+    ork_set_estimates(c->o, est, b->n);
+  }
+  int rc = ork_request_batch(c->o, b, r);
+  if (r->bpe_count) for (uint32_t i = 0; i < b->n; i++) r->bpe_count[i] = est ? est[i] : 0;
+  free(est);
+  return rc;
+}
+int arks_submit_request_batch(arks_ctx* c, const arks_request_batch* b, arks_request_result* r) { return shim_request(c, b, r); }
 int arks_submit_response_batch(arks_ctx* c, const arks_response_batch* b, arks_response_result* r) { return ork_response_batch(c->o, b, r); }
 void* arks_alloc_pinned(size_t bytes) { return aligned_alloc(64, (bytes + 127) & ~(size_t)63); }
 void arks_free_pinned(void* p) { free(p); }
@@ -92,7 +108,7 @@ int arks_submit_request_async(arks_ctx* c, const arks_request_batch* b) {
   grow(s, b->n ? b->n : 1);
   s->n = b->n;
   arks_request_result r = {s->reason, s->detail, s->flags, s->qos, s->token, s->pick, s->cur, s->lim, s->moff, s->mlen, s->bpe};
-  s->rc = ork_request_batch(c->o, b, &r);
+  s->rc = shim_request(c, b, &r);
   return s->rc;
 }
 int arks_wait_request(arks_ctx* c, int slot, arks_request_result* out) {

@@ -278,3 +278,40 @@ def test_a_row_owner_that_lost_its_core_does_not_hold_the_batch(tmp_path):
     assert r["max_us"] >= 20000                     # the late rows waited for their owner ...
     assert r["p99_us"] < 10000, r                   # ... and nobody else did: without the cut every row of those blocks and of
     #                                                 the blocks queued behind them would have waited the 20 ms too
+
+
+def test_precharge_estimate_travels_with_the_stream_cpu():
+    """N4 through the compiled host (CPU, oracle-backed shim whose stand-in prompt count is body_len / 4): with SetPrecharge
+    the request's estimate is charged to tpm / tpd when its batch commits, StreamProcessor / HandleResponseBody hand it back
+    with the response, and the accounting ends at the upstream's total; with it off nothing of this happens."""
+    from arks_b200.tables import simple_endpoint, simple_quota, simple_token
+    t = Tables([simple_token("u", "ns", "tk", "m", [("tpm", 10_000), ("rpm", 50)], "q")],
+               [simple_quota("q", "ns", [("total", 10**6)])], [simple_endpoint("m", "ns")])
+    eng = CpuEngine(t, max_batch=64, max_bytes=1 << 20)
+    try:
+        eng.shim.arks_shim_oracle.restype = C.c_void_p
+        eng.shim.arks_shim_oracle.argtypes = [C.c_void_p]
+        o = orklib.Oracle.__new__(orklib.Oracle)
+        o.tables, o.h = t, eng.shim.arks_shim_oracle(eng.ctx)
+        eng.b.set_fixed_clock(NOW)
+        body = b'{"model":"m","messages":[{"role":"user","content":"' + b"word " * 40 + b'"}]}'
+        done = b'{"model":"m","usage":{"prompt_tokens":50,"completion_tokens":7,"total_tokens":57}}'
+        d = eng.b.request(b"tk", body)
+        assert d.reason == 0 and d.bpe_count == 0 and o.snapshot_rate(NOW)[0].tolist() == [1, 0, 0, 0]  # off: the reference's path
+        eng.b.response(d.qos, done, abi.RESP_END_OF_STREAM, d.gen)
+        assert o.snapshot_rate(NOW)[0].tolist() == [1, 0, 57, 0]
+        eng.b.set_precharge(True)
+        d = eng.b.request(b"tk", body)
+        est = len(body) // 4
+        assert d.reason == 0 and d.bpe_count == est
+        assert o.snapshot_rate(NOW)[0].tolist() == [2, 0, 57 + est, 0]        # charged when the batch committed
+        r = eng.b.response(d.qos, done, abi.RESP_END_OF_STREAM, d.gen, precharged=d.bpe_count)
+        assert r.counted == 1
+        assert o.snapshot_rate(NOW)[0].tolist() == [2, 0, 57 + 57, 0]         # += 57 - estimate
+        # the stream state machine carries the estimate by itself
+        eng.b.set_names(t)
+        out = eng.b.stream_transcript([("authorization", "Bearer tk")], body, [(":status", "200")], [done])
+        assert o.snapshot_rate(NOW)[0].tolist() == [3, 0, 57 + 57 + 57, 0]
+        o.h = None  # the shim owns the oracle
+    finally:
+        eng.close()
