@@ -297,7 +297,13 @@ struct Batcher::Impl {
     b->tok_bytes = st_tok(s);
     return b;
   }
-  bool can_cycle() const { return !cycling && has_work() && free_slot() >= 0 && !free_req.empty() && !free_resp.empty(); }
+  // Closing an open block needs a fresh one from the pool; segments and late rows of blocks that are already closed do not —
+  // and they must keep moving when the pool is empty, or the blocks they belong to would never come back to it.
+  bool can_cycle() const {
+    if (cycling || free_slot() < 0) return false;
+    if (waiting(0) || waiting(1) || waiting(2)) return true;
+    return (rows_of(open_req) || rows_of(open_resp[0]) || rows_of(open_resp[1])) && !free_req.empty() && !free_resp.empty();
+  }
 
   // One cycle: close the open blocks and queue them on the device (asynchronous submits, one staging slot). Entered
   // and left with `lk` held and `cycling` set by the caller; the lock is dropped while the device is being talked to.
