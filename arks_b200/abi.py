@@ -15,6 +15,7 @@ RULES = {"rpm": 0, "rpd": 1, "tpm": 2, "tpd": 3}
 RULE_NAMES = ["rpm", "rpd", "tpm", "tpd"]
 QUOTA_TYPES = {"prompt": 0, "response": 1, "total": 2}
 QUOTA_NONE, QUOTA_MISSING = -1, -2
+GEN_HISTORY = 16  # ARKS_GEN_HISTORY: generations a response row can be re-mapped from
 
 # enum arks_reason
 (R_OK, R_NO_TOKEN, R_REQUEST_BODY, R_NO_MODEL, R_TOKEN_NOT_FOUND, R_MODEL_NOT_IN_TOKEN, R_NO_MODEL_BACKENDS,

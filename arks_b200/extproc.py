@@ -266,6 +266,17 @@ class Batcher:
         ev.wait()
         return item["out"]
 
+    def between_batches(self, fn):
+        """run fn() on the worker thread between two engine calls (a table generation swap: arks_commit_tables belongs to the
+        batch thread); what was enqueued before is decided first. Returns fn's result, re-raises its exception."""
+        ev = threading.Event()
+        item = {"kind": "call", "fn": fn, "ev": ev}
+        self.q.put(item)
+        ev.wait()
+        if "error" in item:
+            raise item["error"]
+        return item["out"]
+
     _FAILED = {"reason": 255, "detail": 0, "flags": 0, "qos": -1, "token": -1, "pick": -1, "cur_usage": 0, "limit_max": 0,
                "counted": 0, "usage": [0, 0, 0], "now": 0, "gen": 0, "model_off": 0, "model_len": 0}
 
@@ -274,13 +285,26 @@ class Batcher:
             items = self._collect()
             if not items:
                 continue
-            try:
-                self._decide(items)
-            except Exception as e:  # an engine error must neither kill the worker nor strand the handlers of this cycle
-                for i in items:
-                    if "out" not in i:
-                        i["out"] = dict(self._FAILED, error=repr(e))
-                        i["ev"].set()
+            run = []
+            for it in items + [None]:
+                if it is not None and it["kind"] != "call":
+                    run.append(it)
+                    continue
+                if run:
+                    try:
+                        self._decide(run)
+                    except Exception as e:  # an engine error must neither kill the worker nor strand the handlers of this cycle
+                        for i in run:
+                            if "out" not in i:
+                                i["out"] = dict(self._FAILED, error=repr(e))
+                                i["ev"].set()
+                    run = []
+                if it is not None:
+                    try:
+                        it["out"] = it["fn"]()
+                    except Exception as e:
+                        it["error"] = e
+                    it["ev"].set()
 
     def _collect(self):
         first = self.q.get()
@@ -370,6 +394,7 @@ class ExtProcServer:
         headers); extract_bearer: HandleRequestHeaders' scan (the C ABI's host function); batcher: a CompiledBatcher to
         batch in C++ instead of the Python twin."""
         self.tables = tables
+        self._names = {int(getattr(engine, "generation", 0) or 0): tables}  # generation -> names; a stream keeps its request's
         self.extract_bearer = extract_bearer
         self.batcher = batcher or Batcher(engine, max_wait_s=max_wait_s, clock=clock)
         from .metrics import HostMetrics
@@ -403,21 +428,51 @@ class ExtProcServer:
                     resp_spent += self.monotonic() - t0
                     # handle_response.go:100-106: once per stream, on the end-of-stream message that completed it
                     if not completed and counted and req.response_body.end_of_stream and qos[0] >= 0:
-                        self.metrics.record_resp_processing(*self._labels(qos[0]), resp_spent)
+                        self.metrics.record_resp_processing(*self._labels(qos), resp_spent)
                     completed = completed or counted
                 self._record_request(qos, start, status)  # gateway.go:129: every response-body message
             else:
                 resp = PB["ProcessingResponse"]()
             yield resp
 
-    def _labels(self, q):
-        t = self.tables
+    # ---- live configuration: the names (routing headers, error bodies, metric labels) follow the table generations
+    def names_of(self, gen):
+        """the name tables of the generation a decision was made on (qos / token indices are positional in ITS tables)"""
+        return self._names.get(int(gen), self.tables) if gen is not None else self.tables
+
+    def publish_names(self, gen: int, tables):
+        self._names[int(gen)] = tables
+        self.tables = tables
+        for g in sorted(self._names)[:-abi.GEN_HISTORY]:  # as many as the library re-maps responses for
+            del self._names[g]
+
+    def publisher(self, gateway):
+        """`publish` for arks_b200.provider.ArksProvider: the generation is built on the provider's thread
+        (arks_config_prepare), swapped in on the batch thread between two batches, and the names change with it"""
+        if isinstance(self.batcher, CompiledBatcher):
+            def publish(names):
+                self.batcher.b.apply_config(names)  # Batcher::ApplyConfig: build here, swap between two cycles
+                self.publish_names(gateway.generation, names)
+            return publish
+
+        def publish(names):
+            prepared = gateway.config_prepare()
+
+            def swap():
+                gateway.commit_tables((prepared[0], names))
+                self.publish_names(gateway.generation, names)
+            self.batcher.between_batches(swap)
+        return publish
+
+    def _labels(self, qos):
+        t = self.names_of(qos[1])
+        q = qos[0]
         tok = int(t.qos_token[q])
         return t.token_namespace[tok], t.token_user[tok], t.qos_model_name[q]
 
     def _record_request(self, qos, start, status):
         if qos[0] >= 0:  # the reference dereferences a nil qos here when the request phase never resolved one
-            self.metrics.record_request(*self._labels(qos[0]), self.monotonic() - start, status)
+            self.metrics.record_request(*self._labels(qos), self.monotonic() - start, status)
 
     # ---- HandleRequestHeaders, handle_request.go:33-81
     def handle_request_headers(self, req):
@@ -440,10 +495,10 @@ class ExtProcServer:
             ml = int(out.get("model_len", 0))
             raw = body[int(out.get("model_off", 0)):int(out.get("model_off", 0)) + (ml & 0x7FFFFFFF)]
             st, h, v, m = replies.request_error_reply(reason, int(out["detail"]), int(out["cur_usage"]), int(out["limit_max"]),
-                                                      int(out.get("now", 0)), self.tables, int(out["qos"]), token,
+                                                      int(out.get("now", 0)), self.names_of(out.get("gen")), int(out["qos"]), token,
                                                       replies.decode_model(raw, bool(ml >> 31)))
             return error_response(st, h, v, m), (-1, None), False
-        t = self.tables
+        t = self.names_of(out.get("gen"))
         q, tok = int(out["qos"]), int(out["token"])
         r = PB["ProcessingResponse"]()
         r.request_body.response.header_mutation.CopyFrom(_set_headers([
@@ -481,7 +536,7 @@ class ExtProcServer:
             out = self.batcher.response(bytes(buffered), qos, abi.RESP_END_OF_STREAM, gen)
         reason = int(out["reason"])
         if reason not in (abi.R_OK, abi.R_PENDING, abi.R_QOS_GONE):
-            return error_response(*replies.response_error_reply(reason, self.tables, qos, body)), False
+            return error_response(*replies.response_error_reply(reason, self.names_of(gen), qos, body)), False
         r = PB["ProcessingResponse"]()
         r.response_body.response.header_mutation.SetInParent()
         return r, bool(out.get("counted", 0))

@@ -345,3 +345,95 @@ def test_provider_over_the_library(gwmod):
         ug, uc = pg.sync_quota_status(restore=step == 0), pc.sync_quota_status(restore=step == 0)
         assert ug == uc and len(ug) > 0
     assert (b.reason == abi.R_QUOTA_CONFIG).any()
+
+
+class LiveEngine(StoreGateway):
+    """StoreGateway + the two batch calls + a generation counter, i.e. what the Python ext_proc server needs of a Gateway.
+    Response rows of an older generation are re-mapped by (namespace, user, model) like the library does."""
+
+    def __init__(self):
+        super().__init__()
+        self.generation, self.names = 0, {}
+
+    def commit_tables(self, prepared):
+        super().commit_tables(prepared)
+        self.generation += 1
+        self.names[self.generation] = prepared[1]
+
+    def handle_request_body(self, b):
+        return self.o.request_batch(b)
+
+    def handle_response_body(self, b):
+        cur = self.names[self.generation]
+        key = lambda t, q: (t.token_namespace[int(t.qos_token[q])], t.token_user[int(t.qos_token[q])], t.qos_model_name[q])
+        index = {key(cur, q): q for q in range(cur.n_qos)}
+        for i in range(b.n):
+            if b.gen is not None and int(b.gen[i]) != self.generation and b.qos[i] >= 0:
+                b.qos[i] = index.get(key(self.names[int(b.gen[i])], int(b.qos[i])), -1)
+        return self.o.response_batch(b)
+
+
+def test_ext_proc_server_follows_the_generations():
+    """the names in routing headers and metric labels are those of the generation the request was decided on, while the
+    provider publishes new generations between batches of a running server"""
+    import json
+    import os
+    import __graft_entry__ as ge
+    from arks_b200 import extproc, gateway
+    from test_extproc_loopback import body, hdrs, resp_hdrs, set_headers
+    ge.build()
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "quickstart.json")))
+    eng = LiveEngine()
+    srv = extproc.ExtProcServer(eng, None, gateway.extract_bearer, clock=lambda: NOW)
+    p = ArksProvider(eng, publish=srv.publisher(eng))
+    for kind, key in (("ArksToken", "tokens"), ("ArksQuota", "quotas"), ("ArksEndpoint", "endpoints")):
+        p.replace(kind, [kinded(kind, o) for o in fx[key]])
+    assert p.flush() and eng.generation == 1 and srv.tables.token_user == ["example-token"]
+    server, port = extproc.serve(srv, port=0)
+    ch, stub = extproc.client_stub(port)
+
+    def stream(token, split=None):
+        msgs = [hdrs([("authorization", "Bearer " + token)]), body(fx["request_body"].encode(), "request_body"),
+                resp_hdrs([(":status", "200")]), body(fx["response_body"].encode(), "response_body")]
+        if split is None:
+            return list(stub(iter(msgs)))
+
+        def gen():  # the configuration changes while this stream waits for its upstream
+            yield msgs[0]
+            yield msgs[1]
+            split()
+            yield msgs[2]
+            yield msgs[3]
+        return list(stub(gen()))
+
+    try:
+        r = stream("sk-test123456")
+        assert set_headers(r[1].request_body.response.header_mutation)["username"] == "example-token"
+        # a second user whose name sorts first: every index of the old generation now means somebody else
+        adam = kinded("ArksToken", simple_token("adam", "default", "sk-adam", "qwen-7b", [("rpm", 10)], quota="basic-quota"))
+
+        def add_adam():
+            assert p.apply({"type": "ADDED", "object": adam}) and p.flush()
+        r = stream("sk-test123456", split=add_adam)
+        assert eng.generation == 2 and srv.tables.token_user == ["adam", "example-token"]
+        assert set_headers(r[1].request_body.response.header_mutation)["username"] == "example-token"
+        assert r[3].WhichOneof("response") == "response_body"
+        r = stream("sk-adam")
+        assert set_headers(r[1].request_body.response.header_mutation) == {"model": "qwen-7b", "namespace": "default", "username": "adam"}
+        r = stream("sk-test123456")
+        assert set_headers(r[1].request_body.response.header_mutation)["username"] == "example-token"
+        # usage went to the right rows (three streams of example-token, one of adam; they share the quota)
+        rate = eng.o.snapshot_rate(NOW)
+        assert rate[:, 0].tolist() == [1, 3] and eng.o.snapshot_quota()[0].tolist() == [100, 80, 180]
+        text = srv.metrics.exposition()
+        assert 'gateway_request_duration_seconds_count{namespace="default",user="example-token",model="qwen-7b"} 3' in text
+        assert 'gateway_request_duration_seconds_count{namespace="default",user="adam",model="qwen-7b"} 1' in text
+        # the token is deleted: its next request is refused with the reference's reply
+        assert p.apply({"type": "DELETED", "object": adam}) and p.flush() and eng.generation == 3
+        r = stream("sk-adam")
+        assert r[1].immediate_response.status.code == 500  # "error to get qos by token", handle_request.go:117-125
+        assert "x-error-token" in set_headers(r[1].immediate_response.headers)
+    finally:
+        ch.close()
+        extproc.gracefully_shutdown(server)
+        srv.batcher.close()
