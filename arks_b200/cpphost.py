@@ -40,7 +40,8 @@ RESP_DTYPE = np.dtype(ResponseDecision)
 EXPORTED = ["arks_host_create", "arks_host_destroy", "arks_host_set_fixed_clock", "arks_host_request", "arks_host_response",
             "arks_host_stats", "arks_host_run_requests", "arks_host_run_responses", "arks_host_open_loop_requests",
             "arks_host_stream_transcript", "arks_host_load_tables", "arks_host_apply_config", "arks_host_set_precharge", "arks_host_response_pre", "arks_host_set_names", "arks_host_request_error_reply",
-            "arks_host_response_error_reply"]
+            "arks_host_response_error_reply", "arks_host_load_tables_named", "arks_host_apply_config_named",
+            "arks_host_response_error_reply_gen"]
 
 
 def build(out: str = LIB, against: str = None, force: bool = False) -> str:
@@ -69,6 +70,8 @@ def load(path: str = LIB):
     L.arks_host_response.argtypes = [vp, C.c_int32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint8, C.POINTER(ResponseDecision)]
     L.arks_host_load_tables.argtypes = [vp, vp]
     L.arks_host_apply_config.argtypes = [vp]
+    L.arks_host_load_tables_named.argtypes = [vp, vp, C.c_char_p, C.c_uint32]
+    L.arks_host_apply_config_named.argtypes = [vp, C.c_char_p, C.c_uint32]
     L.arks_host_set_precharge.argtypes = [vp, C.c_int]
     L.arks_host_response_pre.argtypes = [vp, C.c_int32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint8, C.POINTER(ResponseDecision)]
     L.arks_host_reset_tail.argtypes = [vp]
@@ -81,6 +84,8 @@ def load(path: str = LIB):
                                                 C.c_char_p, C.c_uint32]
     L.arks_host_response_error_reply.argtypes = [vp, C.POINTER(ResponseDecision), C.c_int32, C.c_char_p, C.c_uint32, C.c_char_p,
                                                  C.c_uint32]
+    L.arks_host_response_error_reply_gen.argtypes = [vp, C.POINTER(ResponseDecision), C.c_int32, C.c_uint32, C.c_char_p, C.c_uint32,
+                                                     C.c_char_p, C.c_uint32]
     L.arks_host_stats.argtypes = [vp, C.POINTER(BatcherStats)]
     L.arks_host_stats.restype = None
     L.arks_host_run_requests.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -136,21 +141,24 @@ class Batcher:
             raise RuntimeError("arks_host_set_precharge failed")
 
     def load_tables(self, tables):
-        """config reload between two cycles (Batcher::LoadTables); also refreshes the reply-shaping names"""
+        """config reload between two cycles (Batcher::LoadTables); the reply-shaping names of the new generation enter the
+        host's NameBook under its number before the swap (streams decided earlier keep theirs)"""
         ts = tables.c_struct()
-        rc = self.L.arks_host_load_tables(self._h, C.byref(ts))
+        blob = tables.names_blob()
+        rc = self.L.arks_host_load_tables_named(self._h, C.byref(ts), blob, len(blob))
         if rc:
             raise RuntimeError(f"arks_host_load_tables: {rc}")
-        self.set_names(tables)
 
     def apply_config(self, tables=None):
         """publish the arks_upsert_* / arks_delete_* calls made on the context (Batcher::ApplyConfig); `tables`: the same
         objects as an arks_b200.tables.Tables in (namespace, name) order, for the reply-shaping names"""
-        rc = self.L.arks_host_apply_config(self._h)
+        if tables is not None:
+            blob = tables.names_blob()
+            rc = self.L.arks_host_apply_config_named(self._h, blob, len(blob))
+        else:
+            rc = self.L.arks_host_apply_config(self._h)
         if rc:
             raise RuntimeError(f"arks_host_apply_config: {rc}")
-        if tables is not None:
-            self.set_names(tables)
 
     def set_names(self, tables):
         blob = tables.names_blob()
@@ -168,9 +176,12 @@ class Batcher:
         buf = C.create_string_buffer(len(body) + len(token) + 4096)
         return self._reply(self.L.arks_host_request_error_reply(self._h, C.byref(d), token, len(token), body, len(body), buf, len(buf)), buf)
 
-    def response_error_reply(self, d: ResponseDecision, qos: int, chunk: bytes):
+    def response_error_reply(self, d: ResponseDecision, qos: int, chunk: bytes, gen: int = None):
+        """`gen`: RequestDecision.gen of the stream's request (the generation `qos` is an index of); None: the latest"""
         buf = C.create_string_buffer(len(chunk) + 4096)
-        return self._reply(self.L.arks_host_response_error_reply(self._h, C.byref(d), qos, chunk, len(chunk), buf, len(buf)), buf)
+        if gen is None:
+            return self._reply(self.L.arks_host_response_error_reply(self._h, C.byref(d), qos, chunk, len(chunk), buf, len(buf)), buf)
+        return self._reply(self.L.arks_host_response_error_reply_gen(self._h, C.byref(d), qos, gen, chunk, len(chunk), buf, len(buf)), buf)
 
     def reset_tail(self):
         self.L.arks_host_reset_tail(self._h)

@@ -142,8 +142,10 @@ struct Batcher::Impl {
   bool slot_busy[kSlots] = {false, false, false, false};
   mutable std::mutex mu;
   std::mutex cfg_mu;  // config calls among themselves
+  NameBook names;     // generation -> names (published under cfg_mu, read by any stream thread)
   std::atomic<bool> precharge{false};  // N4: response batches carry the streams' estimates
   int swap_in(arks_prepared* p);
+  int publish(arks_prepared* p, const NameTables* nm);
   std::condition_variable cv_work, cv_space, cv_done;
   bool stop = false;
   bool cycling = false;  // a cycle is being run (by the dispatcher thread or by a leading caller): one submitter at a time
@@ -651,19 +653,29 @@ int Batcher::SetPrecharge(bool on) {
 }
 bool Batcher::Precharge() const { return p_->precharge.load(std::memory_order_relaxed); }
 // config calls are serialised among themselves; the swap itself happens between two cycles
-int Batcher::LoadTables(const arks_tables* t) {
+int Batcher::LoadTables(const arks_tables* t, const NameTables* names) {
   Impl& I = *p_;
   std::lock_guard<std::mutex> one(I.cfg_mu);
   arks_prepared* p = nullptr;
   int rc = arks_prepare_tables(I.ctx, t, &p);  // batches keep cycling meanwhile
-  return rc ? rc : I.swap_in(p);
+  return rc ? rc : I.publish(p, names);
 }
-int Batcher::ApplyConfig() {
+int Batcher::ApplyConfig(const NameTables* names) {
   Impl& I = *p_;
   std::lock_guard<std::mutex> one(I.cfg_mu);
   arks_prepared* p = nullptr;
   int rc = arks_config_prepare(I.ctx, &p);
-  return rc ? rc : I.swap_in(p);
+  return rc ? rc : I.publish(p, names);
+}
+NameBook& Batcher::Names() { return p_->names; }
+// under cfg_mu: a commit raises the generation by one, and nobody else commits meanwhile, so the names can be in the book
+// under their number before the first decision of that generation exists
+int Batcher::Impl::publish(arks_prepared* p, const NameTables* nm) {
+  const uint32_t next = arks_table_generation(ctx) + 1;
+  if (nm) names.Publish(next, *nm);
+  const int rc = swap_in(p);
+  if (rc && nm) names.Drop(next);
+  return rc;
 }
 arks_ctx* Batcher::Context() const { return p_->ctx; }
 int Batcher::Impl::swap_in(arks_prepared* p) {
@@ -943,7 +955,36 @@ bool ParseNameTables(std::string_view text, NameTables* out) {
   return true;
 }
 
+// ---- NameBook ---------------------------------------------------------------------------------------------------
+void NameBook::Publish(uint32_t gen, NameTables t) {
+  auto sp = std::make_shared<const NameTables>(std::move(t));
+  std::lock_guard<std::mutex> g(mu_);
+  by_gen_[gen] = std::move(sp);
+  while (by_gen_.size() > ARKS_GEN_HISTORY) by_gen_.erase(by_gen_.begin());
+}
+void NameBook::Drop(uint32_t gen) {
+  std::lock_guard<std::mutex> g(mu_);
+  by_gen_.erase(gen);
+}
+std::shared_ptr<const NameTables> NameBook::Latest() const {
+  static const std::shared_ptr<const NameTables> empty = std::make_shared<const NameTables>();
+  std::lock_guard<std::mutex> g(mu_);
+  return by_gen_.empty() ? empty : by_gen_.rbegin()->second;
+}
+std::shared_ptr<const NameTables> NameBook::Of(uint32_t gen) const {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = by_gen_.find(gen);
+    if (it != by_gen_.end()) return it->second;
+  }
+  return Latest();
+}
+
 // ---- StreamProcessor --------------------------------------------------------------------------------------------
+std::shared_ptr<const NameTables> StreamProcessor::NamesOf(uint32_t gen) const {
+  if (book_) return book_->Of(gen);
+  return std::shared_ptr<const NameTables>(std::shared_ptr<const NameTables>(), names_);  // not owned: the caller's table
+}
 static Action reply_action(const ErrorReply& e) { return ErrorResponse(e.status, {{e.header, e.header_value}}, e.message); }
 
 Action StreamProcessor::OnRequestHeaders(const std::vector<Header>& headers) {
@@ -958,7 +999,7 @@ Action StreamProcessor::OnRequestHeaders(const std::vector<Header>& headers) {
   if (n == 0) {
     RequestDecision d{};
     d.reason = ARKS_R_NO_TOKEN;
-    return reply_action(RequestErrorReply(d, *names_, "", ""));
+    return reply_action(RequestErrorReply(d, *NamesOf(0), "", ""));  // this reply names nothing
   }
   token_.assign((const char*)tok, n);
   Action a;
@@ -969,15 +1010,16 @@ Action StreamProcessor::OnRequestHeaders(const std::vector<Header>& headers) {
 }
 Action StreamProcessor::OnRequestBody(std::string_view body, uint64_t pick_rand) {
   req_ = b_->HandleRequestBody(token_, body, pick_rand);
-  if (req_.reason != ARKS_R_OK) return reply_action(RequestErrorReply(req_, *names_, token_, body));
+  const std::shared_ptr<const NameTables> nm = NamesOf(req_.gen);  // the generation this decision's indices belong to
+  if (req_.reason != ARKS_R_OK) return reply_action(RequestErrorReply(req_, *nm, token_, body));
   qos_ = req_.qos;
   gen_ = req_.gen;
   stream_ = req_.flags & 1;
   Action a;
   a.kind = Action::kContinueRequestBody;
-  a.set_headers.push_back({"model", names_->qos_model[(size_t)req_.qos]});
-  a.set_headers.push_back({"namespace", names_->token_namespace[(size_t)req_.token]});
-  a.set_headers.push_back({"username", names_->token_user[(size_t)req_.token]});
+  a.set_headers.push_back({"model", nm->qos_model[(size_t)req_.qos]});
+  a.set_headers.push_back({"namespace", nm->token_namespace[(size_t)req_.token]});
+  a.set_headers.push_back({"username", nm->token_user[(size_t)req_.token]});
   return a;
 }
 Action StreamProcessor::OnResponseHeaders(const std::vector<Header>& headers) {
@@ -1013,7 +1055,7 @@ Action StreamProcessor::OnResponseBody(std::string_view body, bool end_of_stream
     resp_ = b_->HandleResponseBody(qos_, gen_, buffered_, ARKS_RESP_END_OF_STREAM, Estimate());
   }
   if (resp_.reason != ARKS_R_OK && resp_.reason != ARKS_R_PENDING && resp_.reason != ARKS_R_QOS_GONE)
-    return reply_action(ResponseErrorReply(resp_, *names_, qos_, body));
+    return reply_action(ResponseErrorReply(resp_, *NamesOf(gen_), qos_, body));
   Action a;
   a.kind = Action::kContinueResponseBody;
   return a;
@@ -1027,7 +1069,6 @@ using namespace arks_host;
 struct arks_host_batcher {
   Batcher* b;
   std::atomic<int64_t> fixed_now{0};
-  NameTables names;
 };
 static int put_reply(const ErrorReply& e, char* out, uint32_t out_cap) {
   const std::string o = std::to_string(e.status) + "\n" + e.header + "\n" + e.header_value + "\n" + e.message;
@@ -1096,6 +1137,16 @@ int arks_host_response(arks_host_batcher* h, int32_t qos, uint32_t gen, const ui
 }
 int arks_host_load_tables(arks_host_batcher* h, const arks_tables* t) { return h->b->LoadTables(t); }
 int arks_host_apply_config(arks_host_batcher* h) { return h->b->ApplyConfig(); }
+int arks_host_load_tables_named(arks_host_batcher* h, const arks_tables* t, const char* names, uint32_t names_len) {
+  NameTables nm;
+  if (!ParseNameTables(std::string_view(names, names_len), &nm)) return ARKS_E_INVALID_ARG;
+  return h->b->LoadTables(t, &nm);
+}
+int arks_host_apply_config_named(arks_host_batcher* h, const char* names, uint32_t names_len) {
+  NameTables nm;
+  if (!ParseNameTables(std::string_view(names, names_len), &nm)) return ARKS_E_INVALID_ARG;
+  return h->b->ApplyConfig(&nm);
+}
 int arks_host_set_precharge(arks_host_batcher* h, int on) { return h->b->SetPrecharge(on != 0); }
 int arks_host_response_pre(arks_host_batcher* h, int32_t qos, uint32_t gen, uint32_t precharged, const uint8_t* body, uint32_t body_len,
                            uint8_t flags, arks_host::ResponseDecision* out) {
@@ -1103,16 +1154,23 @@ int arks_host_response_pre(arks_host_batcher* h, int32_t qos, uint32_t gen, uint
   return out->reason == 255 ? ARKS_E_INVALID_ARG : 0;
 }
 int arks_host_set_names(arks_host_batcher* h, const char* text, uint32_t len) {
-  return ParseNameTables(std::string_view(text, len), &h->names) ? 0 : ARKS_E_INVALID_ARG;
+  NameTables nm;  // the names of the generation that is current now
+  if (!ParseNameTables(std::string_view(text, len), &nm)) return ARKS_E_INVALID_ARG;
+  h->b->Names().Publish(h->b->Generation(), std::move(nm));
+  return 0;
 }
 int arks_host_request_error_reply(arks_host_batcher* h, const RequestDecision* d, const uint8_t* token, uint32_t token_len,
                                   const uint8_t* body, uint32_t body_len, char* out, uint32_t out_cap) {
-  return put_reply(RequestErrorReply(*d, h->names, std::string_view((const char*)token, token_len),
+  return put_reply(RequestErrorReply(*d, *h->b->Names().Of(d->gen), std::string_view((const char*)token, token_len),
                                      std::string_view((const char*)body, body_len)), out, out_cap);
 }
 int arks_host_response_error_reply(arks_host_batcher* h, const ResponseDecision* d, int32_t qos, const uint8_t* chunk, uint32_t chunk_len,
                                    char* out, uint32_t out_cap) {
-  return put_reply(ResponseErrorReply(*d, h->names, qos, std::string_view((const char*)chunk, chunk_len)), out, out_cap);
+  return put_reply(ResponseErrorReply(*d, *h->b->Names().Latest(), qos, std::string_view((const char*)chunk, chunk_len)), out, out_cap);
+}
+int arks_host_response_error_reply_gen(arks_host_batcher* h, const ResponseDecision* d, int32_t qos, uint32_t gen, const uint8_t* chunk,
+                                       uint32_t chunk_len, char* out, uint32_t out_cap) {
+  return put_reply(ResponseErrorReply(*d, *h->b->Names().Of(gen), qos, std::string_view((const char*)chunk, chunk_len)), out, out_cap);
 }
 void arks_host_stats(arks_host_batcher* h, BatcherStats* out) { *out = h->b->Stats(); }
 
@@ -1214,7 +1272,7 @@ int arks_host_stream_transcript(arks_host_batcher* h, const char* const* req_hdr
                                 const char* const* resp_hdr_keys, const char* const* resp_hdr_vals, uint32_t n_resp_hdr,
                                 const uint8_t* const* resp_chunks, const uint32_t* resp_chunk_len, uint32_t n_resp_chunks,
                                 uint64_t pick_rand, char* out, uint32_t out_cap) {
-  StreamProcessor sp(h->b, &h->names);
+  StreamProcessor sp(h->b, &h->b->Names());
   std::string o;
   std::vector<Header> rh, ph;
   for (uint32_t i = 0; i < n_req_hdr; i++) rh.push_back({req_hdr_keys[i], req_hdr_vals[i]});

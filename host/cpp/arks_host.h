@@ -18,6 +18,10 @@
 #pragma once
 #include <stdint.h>
 
+#include <map>
+#include <memory>
+#include <mutex>
+
 #include <string>
 #include <string_view>
 #include <vector>
@@ -70,6 +74,30 @@ struct BatcherStats {
   uint64_t late_rows;  // rows that were not filled when their block was cut and went in a later cycle on their own
 };
 
+// names the routing headers and the error replies are built from (arks_impl.go: qos -> model, token -> namespace / user)
+struct NameTables {
+  std::vector<std::string> qos_model, token_namespace, token_user;
+  std::vector<int32_t> qos_token;                               // owning ArksToken of each qos entry
+  std::vector<std::vector<std::string>> qos_rule_names;         // RateLimit.Type of qos.RateLimits, in order ("rpm", ...)
+  std::vector<std::string> qos_quota_name;                      // qos.Quota.Name, "" when none
+  std::vector<std::vector<std::string>> qos_quota_item_types;   // QuotaItem.Type of the referenced ArksQuota, in order
+};
+// generation -> names. The qos / token indices of a decision are positional in the tables of the generation it was made
+// on (RequestDecision::gen); while the config plane publishes new generations, a stream's headers and error replies are
+// built from ITS generation's names. The last ARKS_GEN_HISTORY generations are kept (as many as the library re-maps
+// response rows for).
+class NameBook {
+ public:
+  void Publish(uint32_t gen, NameTables t);
+  void Drop(uint32_t gen);                                    // a generation that was announced but not committed
+  std::shared_ptr<const NameTables> Of(uint32_t gen) const;   // that generation's; the latest when it is not kept; never null
+  std::shared_ptr<const NameTables> Latest() const;
+
+ private:
+  mutable std::mutex mu_;
+  std::map<uint32_t, std::shared_ptr<const NameTables>> by_gen_;
+};
+
 typedef void (*RequestCallback)(void* user, const RequestDecision&);    // run on the batcher's completion thread
 typedef void (*ResponseCallback)(void* user, const ResponseDecision&);
 
@@ -101,10 +129,13 @@ class Batcher {
   // (arks_commit_tables: stream-ordered, counters carried by key on the device). Nothing waits for queued batches to
   // drain; the only exclusion is against the few microseconds in which a cycle submits. Requests decided before the
   // swap keep their (gen, qos); the library re-maps them by key when their response chunks arrive.
-  int LoadTables(const arks_tables* t);
+  // `names` (optional): the name tables of the generation being published; they enter Names() under the new generation's
+  // number BEFORE the swap, so a decision of that generation never meets the previous generation's names.
+  int LoadTables(const arks_tables* t, const NameTables* names = nullptr);
   // The same for the object-level plane: arks_upsert_* / arks_delete_* on Context() from the config thread, then
   // ApplyConfig() publishes the store (arks_config_prepare + commit).
-  int ApplyConfig();
+  int ApplyConfig(const NameTables* names = nullptr);
+  NameBook& Names();
   arks_ctx* Context() const;
   uint32_t Generation() const;  // arks_table_generation of the context
 
@@ -121,14 +152,6 @@ class Batcher {
 struct Header {
   std::string key, value;
 };
-// names the routing headers and the error replies are built from (arks_impl.go: qos -> model, token -> namespace / user)
-struct NameTables {
-  std::vector<std::string> qos_model, token_namespace, token_user;
-  std::vector<int32_t> qos_token;                               // owning ArksToken of each qos entry
-  std::vector<std::vector<std::string>> qos_rule_names;         // RateLimit.Type of qos.RateLimits, in order ("rpm", ...)
-  std::vector<std::string> qos_quota_name;                      // qos.Quota.Name, "" when none
-  std::vector<std::vector<std::string>> qos_quota_item_types;   // QuotaItem.Type of the referenced ArksQuota, in order
-};
 // one table line per object: "T\t<namespace>\t<user>" / "Q\t<token index>\t<model>\t<quota name>\t<rule,rule,..>\t<type,type,..>"
 bool ParseNameTables(std::string_view text, NameTables* out);
 struct Action {
@@ -142,7 +165,8 @@ struct Action {
 
 class StreamProcessor {
  public:
-  StreamProcessor(Batcher* batcher, const NameTables* names) : b_(batcher), names_(names) {}
+  StreamProcessor(Batcher* batcher, const NameTables* names) : b_(batcher), names_(names) {}  // one fixed configuration
+  StreamProcessor(Batcher* batcher, const NameBook* book) : b_(batcher), book_(book) {}       // names follow the generations
   Action OnRequestHeaders(const std::vector<Header>& headers);              // handle_request.go:33-81
   Action OnRequestBody(std::string_view body, uint64_t pick_rand);          // handle_request.go:83-249
   Action OnResponseHeaders(const std::vector<Header>& headers);             // handle_response.go:37-78
@@ -152,7 +176,9 @@ class StreamProcessor {
 
  private:
   Batcher* b_;
-  const NameTables* names_;
+  const NameTables* names_ = nullptr;
+  const NameBook* book_ = nullptr;
+  std::shared_ptr<const NameTables> NamesOf(uint32_t gen) const;
   std::string token_, buffered_;
   int32_t qos_ = -1;
   uint32_t gen_ = 0;
@@ -193,6 +219,9 @@ int arks_host_request(arks_host_batcher* b, const uint8_t* token, uint32_t token
 int arks_host_response(arks_host_batcher* b, int32_t qos, uint32_t gen /* 0xffffffff: the current generation */, const uint8_t* body,
                        uint32_t body_len, uint8_t flags, arks_host::ResponseDecision* out);
 int arks_host_load_tables(arks_host_batcher* b, const arks_tables* t);
+/* the same with the generation's name tables (format: ParseNameTables), published under the new generation's number */
+int arks_host_load_tables_named(arks_host_batcher* b, const arks_tables* t, const char* names, uint32_t names_len);
+int arks_host_apply_config_named(arks_host_batcher* b, const char* names, uint32_t names_len);
 void arks_host_reset_tail(arks_host_batcher* b);
 void arks_host_open_loop_lateness(int64_t out[3]);
 void arks_host_open_loop_call_latency(int64_t* buf); /* n entries filled by the next open-loop run: decision - time of the call */
@@ -200,13 +229,17 @@ int arks_host_apply_config(arks_host_batcher* b);
 int arks_host_set_precharge(arks_host_batcher* b, int on);
 int arks_host_response_pre(arks_host_batcher* b, int32_t qos, uint32_t gen, uint32_t precharged, const uint8_t* body, uint32_t body_len,
                            uint8_t flags, arks_host::ResponseDecision* out); /* publishes arks_upsert_* / arks_delete_* done on the context */
-// names for the reply shapes of arks_host_stream_transcript / arks_host_error_reply (format: ParseNameTables)
+// names of the CURRENT generation for the reply shapes of arks_host_stream_transcript / arks_host_*_error_reply (format:
+// ParseNameTables); arks_host_load_tables_named / arks_host_apply_config_named publish them together with a generation
 int arks_host_set_names(arks_host_batcher* b, const char* text, uint32_t len);
 // the reference-exact reply of a failed request / response decision as "status\nheader\nheader value\nmessage"
 int arks_host_request_error_reply(arks_host_batcher* b, const arks_host::RequestDecision* d, const uint8_t* token, uint32_t token_len,
                                   const uint8_t* body, uint32_t body_len, char* out, uint32_t out_cap);
 int arks_host_response_error_reply(arks_host_batcher* b, const arks_host::ResponseDecision* d, int32_t qos, const uint8_t* chunk,
                                    uint32_t chunk_len, char* out, uint32_t out_cap);
+/* `gen`: the generation `qos` belongs to (RequestDecision.gen of the stream's request) */
+int arks_host_response_error_reply_gen(arks_host_batcher* b, const arks_host::ResponseDecision* d, int32_t qos, uint32_t gen,
+                                       const uint8_t* chunk, uint32_t chunk_len, char* out, uint32_t out_cap);
 void arks_host_stats(arks_host_batcher* b, arks_host::BatcherStats* out);
 // n requests issued by `threads` stream threads (thread t owns rows t, t+threads, ...; each row is one blocking
 // HandleRequestBody). Decisions and per-call latencies (ns) come back in row order; returns wall nanoseconds.

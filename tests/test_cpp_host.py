@@ -315,3 +315,38 @@ def test_precharge_estimate_travels_with_the_stream_cpu():
         o.h = None  # the shim owns the oracle
     finally:
         eng.close()
+
+
+def test_names_follow_the_generations():
+    """A reload shifts every index (a user whose name sorts first appears): replies for decisions of the old generation are
+    still built from the old generation's names (NameBook), new streams get the new ones"""
+    from arks_b200.tables import Tables, simple_endpoint, simple_token
+    ep = [simple_endpoint("m", "default", 1, [("b0", 1)])]
+    alice = simple_token("alice", "default", "sk-alice", "m", [("rpm", 1)])
+    adam = simple_token("adam", "default", "sk-adam", "m", [("tpd", 5), ("rpd", 7)])
+    t1, t2 = Tables([alice], [], ep), Tables([adam, alice], [], ep)
+    eng = CpuEngine(t1, max_batch=64, max_bytes=1 << 20)
+    try:
+        eng.b.set_fixed_clock(NOW)
+        eng.b.set_names(t1)
+        body = b'{"model":"m","messages":[]}'
+        d1 = eng.b.request(b"sk-alice", body)
+        d2 = eng.b.request(b"sk-alice", body)
+        assert (d1.reason, d2.reason, d2.qos) == (abi.R_OK, abi.R_RATE_LIMIT, 0)
+        old = eng.b.request_error_reply(d2, b"sk-alice", body)
+        assert old[0] == 429 and "rpm" in old[3] + old[2]
+        eng.b.load_tables(t2)
+        d3 = eng.b.request(b"sk-alice", body)
+        assert (d3.reason, d3.qos, d3.gen) == (abi.R_RATE_LIMIT, 1, d2.gen + 1)
+        assert eng.b.request_error_reply(d2, b"sk-alice", body) == old          # qos 0 of the old generation is still alice
+        assert eng.b.request_error_reply(d3, b"sk-alice", body) == old          # and qos 1 of the new one
+        t = eng.b.stream_transcript([("authorization", "Bearer sk-adam")], body, [(":status", "200")],
+                                    [b'{"model":"m","usage":{"prompt_tokens":1,"completion_tokens":1,"total_tokens":2}}'])
+        assert "username: adam" in t
+        # more reloads than the book keeps: old generations fall back to the latest names, nothing dangles
+        for _ in range(abi.GEN_HISTORY + 3):
+            eng.b.load_tables(t2)
+        assert eng.b.request_error_reply(d3, b"sk-alice", body)[0] == 429
+        assert eng.b.request_error_reply(d2, b"sk-alice", body)[0] == 429
+    finally:
+        eng.close()
