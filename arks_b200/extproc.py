@@ -165,7 +165,7 @@ def models_reply(tables, authorization):
     return 200, "application/json", json.dumps({"object": "list", "data": data}, separators=(",", ":"), ensure_ascii=False).encode()
 
 
-def serve_http(get_tables, port: int = 8080):
+def serve_http(get_tables, port: int = 8080, host: str = "127.0.0.1"):
     """the /v1/models listener; get_tables() returns the current arks_b200.tables.Tables (it changes with the config plane)"""
     from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 
@@ -189,7 +189,7 @@ def serve_http(get_tables, port: int = 8080):
         def log_message(self, *a):
             pass
 
-    httpd = ThreadingHTTPServer(("127.0.0.1", port), H)
+    httpd = ThreadingHTTPServer((host, port), H)
     th = threading.Thread(target=httpd.serve_forever, daemon=True)
     th.start()
     return httpd, httpd.server_address[1]
@@ -542,7 +542,7 @@ class ExtProcServer:
         return r, bool(out.get("counted", 0))
 
 
-def serve(server: ExtProcServer, port: int = 50052, max_workers: int = 64):
+def serve(server: ExtProcServer, port: int = 50052, max_workers: int = 64, host: str = "127.0.0.1"):
     """grpc.NewServer() + RegisterExternalProcessorServer (gateway.go:175-192); plaintext, default options."""
     import grpc
     handler = grpc.method_handlers_generic_handler(SERVICE, {
@@ -560,12 +560,12 @@ def serve(server: ExtProcServer, port: int = 50052, max_workers: int = 64):
                                                       response_serializer=HP["HealthCheckResponse"].SerializeToString)})
     s = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers))
     s.add_generic_rpc_handlers((handler, health))
-    bound = s.add_insecure_port(f"127.0.0.1:{port}")
+    bound = s.add_insecure_port(f"{host}:{port}")
     s.start()
     return s, bound
 
 
-def serve_metrics(render, port: int = 9110):
+def serve_metrics(render, port: int = 9110, host: str = "127.0.0.1"):
     """the /metrics listener (gateway.go:158-173): `render()` returns the Prometheus text exposition (metrics.exposition of
     the device rows + HostMetrics.exposition of the wall-clock series)"""
     from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
@@ -583,7 +583,7 @@ def serve_metrics(render, port: int = 9110):
         def log_message(self, *a):
             pass
 
-    httpd = ThreadingHTTPServer(("127.0.0.1", port), H)
+    httpd = ThreadingHTTPServer((host, port), H)
     threading.Thread(target=httpd.serve_forever, daemon=True).start()
     return httpd, httpd.server_address[1]
 
