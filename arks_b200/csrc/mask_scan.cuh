@@ -610,7 +610,7 @@ ARKS_HD bool fast_inner_object(const uint8_t* doc, const FastScratch& s, uint32_
           nd++;
         } else {  // a plain non-negative integer; anything else (sign, fraction, exponent, literal): exact engine
           if ((uint32_t)(b - '0') > 9u) ok = 0;
-          acc = acc * 10 + (int64_t)(b - '0');
+          acc = (int64_t)((uint64_t)acc * 10u + (uint64_t)(b - '0'));  // wraps past 18 digits; such a value is declined below
           nd++;
         }
       }
