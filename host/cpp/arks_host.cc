@@ -482,7 +482,7 @@ struct Batcher::Impl {
       const uint32_t lo = f.resp.lo, hi = f.resp.hi;
       int rc = f.rc_resp;
       if (rc == 0) {
-        arks_response_result rr{b.reason + lo, b.counted + lo, b.usage + 3 * (size_t)lo};
+        arks_response_result rr{b.reason + lo, b.counted + lo, b.usage + 3 * (size_t)lo, nullptr};  // no completion BPE count wanted
         rc = arks_wait_response(ctx, f.slot, &rr);
       }
       lap(t_device);
