@@ -437,3 +437,68 @@ def test_ext_proc_server_follows_the_generations():
         ch.close()
         extproc.gracefully_shutdown(server)
         srv.batcher.close()
+
+
+def test_generations_published_under_load_never_mix_names():
+    """client streams keep running while the provider publishes a generation every few milliseconds (a user that sorts first
+    comes and goes, so every index flips each time): each stream's routing headers name the user its token belongs to"""
+    import json
+    import os
+    import threading
+    import time
+    import __graft_entry__ as ge
+    from arks_b200 import extproc, gateway
+    from test_extproc_loopback import body, hdrs, resp_hdrs, set_headers
+    ge.build()
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "quickstart.json")))
+    eng = LiveEngine()
+    srv = extproc.ExtProcServer(eng, None, gateway.extract_bearer, clock=lambda: NOW)
+    p = ArksProvider(eng, publish=srv.publisher(eng))
+    tok = kinded("ArksToken", fx["tokens"][0])
+    tok["spec"]["qos"][0]["rateLimits"] = []  # nothing to run into: every stream is admitted
+    tok["spec"]["qos"][0]["quota"] = {"name": ""}
+    users = [dict(copy.deepcopy(tok), metadata={"name": f"user-{i}", "namespace": "default"}) for i in range(4)]
+    for i, u in enumerate(users):
+        u["spec"]["token"] = f"sk-{i}"
+    p.replace("ArksToken", users)
+    p.replace("ArksEndpoint", [kinded("ArksEndpoint", o) for o in fx["endpoints"]])
+    assert p.flush()
+    server, port = extproc.serve(srv, port=0)
+    stop, bad, done = threading.Event(), [], [0]
+
+    def client(i):
+        ch, stub = extproc.client_stub(port)
+        try:
+            while not stop.is_set():
+                r = list(stub(iter([hdrs([("authorization", f"Bearer sk-{i}")]), body(fx["request_body"].encode(), "request_body"),
+                                    resp_hdrs([(":status", "200")]), body(fx["response_body"].encode(), "response_body")])))
+                h = set_headers(r[1].request_body.response.header_mutation) if r[1].WhichOneof("response") == "request_body" else r[1]
+                if h != {"model": "qwen-7b", "namespace": "default", "username": f"user-{i}"} or len(r) != 4:
+                    bad.append((i, h))
+                done[0] += 1
+        except Exception as e:  # noqa: BLE001
+            bad.append((i, repr(e)))
+        finally:
+            ch.close()
+
+    threads = [threading.Thread(target=client, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    first = dict(copy.deepcopy(users[0]), metadata={"name": "aaa-first", "namespace": "default"})
+    first["spec"]["token"] = "sk-first"
+    end, flips = time.monotonic() + 1.5, 0
+    try:
+        while time.monotonic() < end:
+            assert p.apply({"type": "ADDED" if flips % 2 == 0 else "DELETED", "object": first}) and p.flush()
+            flips += 1
+            time.sleep(0.003)
+    finally:
+        stop.set()
+        for t in threads:
+            t.join()
+        extproc.gracefully_shutdown(server)
+        srv.batcher.close()
+    assert not bad, bad[:3]
+    assert flips > 20 and done[0] > 20 and eng.generation == flips + 1
+    rate = eng.o.snapshot_rate(NOW)
+    assert rate.shape[0] == eng.tables.n_qos
