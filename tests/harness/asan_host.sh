@@ -29,6 +29,23 @@ for depth in (1, 2):
     resp = w.response_batch(adm, 1_700_000_001, seed=6)
     b.run_responses(resp, threads=10)
     b.open_loop_requests(req, 100000, producers=3)
+    # a config thread republishes the tables (and their names, NameBook) while streams run and replies are shaped
+    import threading
+    stop = threading.Event()
+    def config():
+        while not stop.is_set():
+            b.load_tables(w.tables)
+    def shaper():
+        k = 0
+        while not stop.is_set():
+            dd = cpphost.RequestDecision(); dd.reason, dd.qos, dd.gen = 8, 0, k % 40
+            b.request_error_reply(dd, b"sk", b"{}"); k += 1
+    ths = [threading.Thread(target=config), threading.Thread(target=shaper)]
+    for t in ths: t.start()
+    d2, _, _ = b.run_requests(req, threads=12)
+    stop.set()
+    for t in ths: t.join()
+    assert (d2["reason"] != 255).all()
     print("depth", depth, b.stats())
     b.close()
 print("asan run done")
