@@ -272,7 +272,9 @@ class Batcher:
         ev = threading.Event()
         item = {"kind": "call", "fn": fn, "ev": ev}
         self.q.put(item)
-        ev.wait()
+        while not ev.wait(0.1):
+            if self._stop and not self.t.is_alive():  # closed before the call's turn came
+                raise RuntimeError("the batcher is closed")
         if "error" in item:
             raise item["error"]
         return item["out"]
