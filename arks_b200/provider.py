@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import datetime
 import queue
+import sys
 import threading
 import time
 
@@ -224,6 +225,7 @@ class ProviderLoop:
         self.first_dirty = self.last_event = None
         self.next_sync = None
         self.stop = threading.Event()
+        self.errors = []  # what run() survived
 
     def offer(self, event):
         """any thread (the watch connections)"""
@@ -260,5 +262,10 @@ class ProviderLoop:
         """until stop is set; 1 ms granularity while events are pending, asleep otherwise"""
         while not self.stop.is_set():
             now = time.monotonic()
-            wake = self.step(now)
+            try:
+                wake = self.step(now)
+            except Exception as e:  # a refused generation or a failed status pass must not end the loop: retried in a second
+                self.errors.append(repr(e))
+                print(f"arks provider: {e!r}", file=sys.stderr)
+                wake = now + 1.0
             self.stop.wait(max(0.001, min(wake - time.monotonic(), 0.05)))

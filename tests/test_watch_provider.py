@@ -502,3 +502,33 @@ def test_generations_published_under_load_never_mix_names():
     assert flips > 20 and done[0] > 20 and eng.generation == flips + 1
     rate = eng.o.snapshot_rate(NOW)
     assert rate.shape[0] == eng.tables.n_qos
+
+
+def test_loop_survives_a_refused_generation_and_retries():
+    from arks_b200.provider import ProviderLoop
+    import threading
+    import time
+    g = StoreGateway()
+    fail = [2]
+    real = g.commit_tables
+
+    def flaky(prepared):
+        if fail[0]:
+            fail[0] -= 1
+            raise RuntimeError("commit refused")
+        real(prepared)
+    g.commit_tables = flaky
+    p = ArksProvider(g, publish=lambda names: g.commit_tables((g.config_prepare()[0], names)))
+    loop = ProviderLoop(p, debounce_s=0.01)
+    loop.offer({"type": "ADDED", "object": kinded("ArksToken", simple_token("alice", "default", "sk-a", "m", [("rpm", 2)]))})
+    with pytest.raises(RuntimeError):
+        loop.step(1.0) and loop.step(1.02)
+    assert p.dirty and g.commits == 0  # nothing was lost
+    th = threading.Thread(target=loop.run)
+    th.start()
+    end = time.monotonic() + 10
+    while g.commits == 0 and time.monotonic() < end:
+        time.sleep(0.05)
+    loop.stop.set()
+    th.join()
+    assert g.commits == 1 and len(loop.errors) == 1 and g.tables.token_user == ["alice"]
