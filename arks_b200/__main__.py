@@ -85,7 +85,7 @@ class Assembly:
             try:
                 if os.path.getmtime(self.args.objects) != self._objects_mtime and self.relist():
                     self.provider.flush()
-            except (OSError, ValueError) as e:  # a half-written file: keep the configuration, try again
+            except Exception as e:  # noqa: BLE001  a half-written or malformed file: keep the configuration, try again
                 print(f"provider.objects: {e!r}", file=sys.stderr)
 
     def _read_events(self, f):
