@@ -112,7 +112,8 @@ class Assembly:
         if snap is not None and self.engine.tables is not None:
             between = getattr(self.srv.batcher, "between_batches", None)
             grab = lambda: (self.engine.tables, snap())  # noqa: E731  (rows and names of the same generation)
-            tables, rows = between(grab) if between else grab()
+            with self.provider.no_publish():  # the snapshot must not meet a table swap
+                tables, rows = between(grab) if between else grab()
             if len(rows) == tables.n_qos:
                 text = metrics.exposition(tables, rows)
         return text + self.srv.metrics.exposition()

@@ -139,6 +139,11 @@ class ArksProvider:
         self.dirty = True
         return True
 
+    def no_publish(self):
+        """context manager: no generation is published while it is held (for readers of the CURRENT generation's rows that
+        are not on the batch thread, e.g. a metrics scrape: the library's snapshot calls must not meet a table swap)"""
+        return self._mu
+
     # ---- publishing ------------------------------------------------------------------------------------------------
     def tables(self) -> Tables:
         """the host-side names of the pending configuration, in the library's order ((namespace, name) per kind)"""
