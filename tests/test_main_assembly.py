@@ -82,6 +82,7 @@ def test_the_assembled_process(tmp_path):
         assert st == 200 and json.loads(text)["data"][0]["id"] == "qwen-7b"
         st, ct, text = get(asm.metrics_port, path="/metrics")
         assert st == 200 and b'gateway_request_duration_seconds_count{namespace="default",user="adam",model="qwen-7b"} 1' in text
+        assert b'gateway_requests_total{namespace="default",user="adam",model="qwen-7b",status="200"}' in text  # the engine's rows
         # the status loop: first pass in restore mode, one line per ArksQuota whose status moved
         wait_for(lambda: "basic-quota" in status.getvalue(), "no status update was written")
         line = json.loads(status.getvalue().splitlines()[-1])

@@ -363,6 +363,9 @@ class LiveEngine(StoreGateway):
     def handle_request_body(self, b):
         return self.o.request_batch(b)
 
+    def snapshot_metrics(self):
+        return self.o.snapshot_metrics()
+
     def handle_response_body(self, b):
         cur = self.names[self.generation]
         key = lambda t, q: (t.token_namespace[int(t.qos_token[q])], t.token_user[int(t.qos_token[q])], t.qos_model_name[q])
