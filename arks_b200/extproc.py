@@ -203,7 +203,7 @@ def _set_headers(pairs):
     for k, v in pairs:
         o = mut.set_headers.add()
         o.header.key = k
-        o.header.raw_value = v if isinstance(v, bytes) else str(v).encode()
+        o.header.raw_value = v if isinstance(v, bytes) else str(v).encode("utf-8", "surrogateescape")  # Go strings are bytes
     return mut
 
 

@@ -29,12 +29,60 @@ def _go_str(s: str) -> str:
     return json.dumps(s, ensure_ascii=False)
 
 
+def _utf8(r: int) -> bytes:
+    if r > 0x10FFFF or 0xD800 <= r <= 0xDFFF:
+        r = 0xFFFD
+    return chr(r).encode("utf-8")
+
+
+_SIMPLE = {ord("b"): b"\b", ord("f"): b"\f", ord("n"): b"\n", ord("r"): b"\r", ord("t"): b"\t"}
+
+
 def decode_model(raw: bytes, escaped: bool) -> str:
-    """the model name out of its raw span (arks_request_result.model_off / model_len)"""
+    """the model name out of its raw span (arks_request_result.model_off / model_len): jsoniter's ReadString on bytes the
+    parser already accepted -- escapes are decoded (a lone surrogate becomes U+FFFD, a pair one code point), every other
+    byte is copied as it is, valid UTF-8 or not. Bytes that are not UTF-8 travel as surrogate escapes in the str and come
+    out as the same bytes on the wire (Go strings are byte strings: `RawValue: []byte(...)`, util.go:40-77)."""
     if not escaped:
-        return raw.decode("utf-8", "replace")
-    s = json.loads(b'"' + raw + b'"')
-    return "".join("�" if 0xD800 <= ord(c) <= 0xDFFF else c for c in s)
+        return raw.decode("utf-8", "surrogateescape")
+
+    def hex4(i):
+        v = 0
+        for c in raw[i:i + 4]:
+            v = v * 16 + (c - 48 if c <= 57 else (c | 0x20) - 97 + 10)
+        return v
+    o, i, n = bytearray(), 0, len(raw)
+    while i < n:
+        c = raw[i]
+        i += 1
+        if c != 0x5C or i >= n:
+            o.append(c)
+            continue
+        e = raw[i]
+        i += 1
+        while True:
+            if e != 0x75:  # not \u
+                o += _SIMPLE.get(e, bytes([e]))
+                break
+            r = hex4(i)
+            i += 4
+            if r < 0xD800 or r > 0xDFFF or i >= n or raw[i] != 0x5C:
+                o += _utf8(r)
+                break
+            i += 1
+            e = raw[i] if i < n else 0x5C
+            i += 1 if i < n else 0
+            if e != 0x75:  # the next escape is decoded on its own
+                o += _utf8(r)
+                continue
+            r2 = hex4(i)
+            i += 4
+            if r < 0xDC00 and 0xDC00 <= r2 < 0xE000:
+                o += _utf8((((r - 0xD800) << 10) | (r2 - 0xDC00)) + 0x10000)
+            else:
+                o += _utf8(r) + _utf8(r2)
+            break
+    return bytes(o).decode("utf-8", "surrogateescape")
 
 
 def request_error_reply(reason: int, detail: int, cur_usage: int, limit_max: int, now_unix: int, tables, qos: int,
@@ -49,7 +97,7 @@ def request_error_reply(reason: int, detail: int, cur_usage: int, limit_max: int
     elif reason == abi.R_NO_MODEL:
         value, msg = "", "no model in request body"
     elif reason == abi.R_TOKEN_NOT_FOUND:
-        value, msg = "token not found: " + token.decode("utf-8", "replace"), "error to get qos by token"
+        value, msg = "token not found: " + token.decode("utf-8", "surrogateescape"), "error to get qos by token"
     elif reason == abi.R_MODEL_NOT_IN_TOKEN:
         value, msg = "model not found: " + model, "error to get qos by token"
     elif reason == abi.R_NO_MODEL_BACKENDS:
