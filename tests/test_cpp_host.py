@@ -350,3 +350,99 @@ def test_names_follow_the_generations():
         assert eng.b.request_error_reply(d2, b"sk-alice", body)[0] == 429
     finally:
         eng.close()
+
+
+def _py_transcript(srv, req_h, body, resp_h, chunks):
+    """the Python ext_proc server's replies to one stream in the format of arks_host_stream_transcript (the exchange ends at
+    the first ImmediateResponse, as it does on Envoy's side)"""
+    from test_extproc_loopback import body as body_msg, hdrs, resp_hdrs
+    msgs = [hdrs(req_h), body_msg(body, "request_body"), resp_hdrs(resp_h)]
+    msgs[0].request_headers.SetInParent()  # an empty header list is still a headers message
+    msgs[2].response_headers.SetInParent()
+    msgs += [body_msg(c, "response_body", eos=i + 1 == len(chunks)) for i, c in enumerate(chunks)]
+    out = ""
+
+    def feed():  # stop sending once the exchange is over
+        for m in msgs:
+            if "\n4 " in "\n" + out:
+                return
+            yield m
+    kinds = {"request_headers": 0, "request_body": 1, "response_headers": 2, "response_body": 3}
+    for r in srv.Process(feed(), None):
+        which = r.WhichOneof("response")
+        if which == "immediate_response":
+            im = r.immediate_response
+            hs, text, head = im.headers.set_headers, im.body.decode("utf-8", "surrogateescape"), f"4 {im.status.code} 0\n"
+        else:
+            common = getattr(r, which).response
+            hs, text, head = common.header_mutation.set_headers, "", f"{kinds[which]} 0 {1 if common.clear_route_cache else 0}\n"
+        out += head + "".join(f"{o.header.key}: {(o.header.raw_value or o.header.value.encode()).decode('utf-8', 'surrogateescape')}\n"
+                              for o in hs) + "\n" + text + "\n--\n"
+    return out
+
+
+def test_python_and_compiled_state_machines_agree_on_random_streams():
+    """A1 twice: host/cpp StreamProcessor (over the oracle shim) and the Python ExtProcServer (over the oracle) answer the same
+    random streams -- odd bearer headers, broken and unusual bodies, every upstream status branch, JSON and SSE responses cut at
+    random, limits being crossed on the way -- with the same replies, byte for byte"""
+    import random
+    from arks_b200 import extproc, gateway
+    from arks_b200.tables import simple_endpoint, simple_quota, simple_token
+    from test_extproc_loopback import OracleEngine
+    import __graft_entry__ as ge
+    ge.build()
+    toks = FX["tokens"] + [simple_token("bob", "team-b", "sk-bob", "qwen-7b", [("rpd", 9), ("tpm", 300)], quota="small"),
+                           simple_token("eve", "team-b", "sk-eve", "other-model", [("rpm", 3)])]
+    quotas = FX["quotas"] + [simple_quota("small", "team-b", [("total", 150), ("prompt", 100000)])]
+    eps = FX["endpoints"] + [simple_endpoint("qwen-7b", "team-b", 1, [("b0", 1)])]
+    key = lambda o: (o["metadata"].get("namespace", "default"), o["metadata"]["name"])  # noqa: E731
+    t = Tables(sorted(toks, key=key), sorted(quotas, key=key), sorted(eps, key=key))
+    eng = CpuEngine(t, max_batch=64, max_bytes=1 << 20)
+    srv = extproc.ExtProcServer(OracleEngine(t), t, gateway.extract_bearer, clock=lambda: NOW)
+    sse = json.load(open(os.path.join(HERE, "golden", "sse_stream.json")))["chunks"]
+    r = random.Random(23)
+    auth = [[("authorization", "Bearer sk-test123456")], [("Authorization", "Bearer sk-bob")], [("AUTHORIZATION", "Bearer sk-eve")],
+            [("authorization", "bearer sk-bob")], [("x-other", "1")], [("authorization", "Bearer ")], [("authorization", "Bearer nobody")],
+            [("authorization", "Basic abc"), ("authorization", "Bearer sk-bob")], [("authorization", "Bearer  sk-bob")], []]
+    plain = FX["request_body"].encode()
+    bodies = [plain, plain, plain,
+              b'{"model":"qwen-7b","stream":true,"stream_options":{"include_usage":true},"messages":[]}',
+              b'{"model":"qwen-7b","stream":true,"messages":[]}', b'{"model":"qwen-7b","stream":true,"stream_options":{"include_usage":false}}',
+              b'{"model":"qwen-7b","stream":null,"stream_options":null}', b'{"messages":[]}', b'{"model":""}', b'{"model":"other-model"}',
+              b'{"model":"qw\\u0065n-7b"}', b'{"model":"a\\"b\\\\c"}', b'{"model":"qwen-7b"', b"", b"[1,2]", b'{"model":7}', b'{"MODEL":"qwen-7b"}']
+    statuses = [[(":status", "200")]] * 6 + [[(":status", "500"), ("x-up", "a")], [(":status", "404")], [(":status", "abc")], [],
+                                             [(":status", "200"), ("content-type", "text/event-stream")], [(":status", "429")]]
+    full = FX["response_body"].encode()
+    try:
+        eng.b.set_fixed_clock(NOW)
+        eng.b.set_names(t)
+        seen = set()
+        for k in range(600):
+            req_h = [(":method", "POST")] + r.choice(auth) if r.random() < 0.5 else r.choice(auth)
+            body = r.choice(bodies)
+            resp_h = r.choice(statuses)
+            kind = r.random()
+            if kind < 0.35:
+                cut = sorted(r.sample(range(1, len(full)), r.randrange(0, 3)))
+                chunks = [full[a:b] for a, b in zip([0] + cut, cut + [len(full)])]
+            elif kind < 0.7:
+                chunks = [c.encode() for c in sse]
+                if r.random() < 0.3:
+                    chunks = chunks[:r.randrange(1, len(chunks))]
+            elif kind < 0.8:
+                chunks = [b'{"model":"qwen-7b","usage":{"prompt_tokens":0,"completion_tokens":0,"total_tokens":0}}']
+            elif kind < 0.9:
+                chunks = [b"not json at all", b'data: {"error":"x"}\n\n']
+            else:
+                chunks = [b'{"model":"","usage":{"prompt_tokens":3,"completion_tokens":4,"total_tokens":7}}']
+            if k == 300:  # the next minute: rpm has room again, the day's limits stay
+                eng.b.set_fixed_clock(NOW + 60)
+                srv.batcher.clock = lambda: NOW + 60
+            got = eng.b.stream_transcript(req_h, body, resp_h, chunks)
+            want = _py_transcript(srv, req_h, body, resp_h, chunks)
+            assert got == want, (k, req_h, body, resp_h, chunks, got, want)
+            seen.update(line.split(" ")[1] for line in got.split("\n") if line.startswith("4 "))
+        assert {"400", "401", "404", "429", "500"} <= seen, seen  # the walk met every family of refusals
+    finally:
+        eng.close()
+        srv.batcher.close()
