@@ -55,8 +55,8 @@ def parse_args():
                     help="K quotas per GPU are replicas of quotas shared by all GPUs: every --fold-every steps the library folds "
                          "their increments with ncclAllReduce (arks_fold_quota_allreduce) INSIDE the timed region")
     ap.add_argument("--fold-every", type=int, default=8)
-    ap.add_argument("--latency-requests", type=int, default=2_000_000,
-                    help="requests per GPU in the 1.25 M/s open-loop latency run (10 M for the metric's full sample)")
+    ap.add_argument("--latency-requests", type=int, default=10_000_000,
+                    help="requests per GPU in the 1.25 M/s open-loop latency run (SURVEY.md section 8d: >= 10 M; 8 s of arrivals)")
     return ap.parse_args()
 
 
