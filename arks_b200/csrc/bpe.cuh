@@ -43,6 +43,11 @@ struct BpeTablesDev {
   uint32_t flags;
 };
 
+// host test build only (tests/host_machine.cpp): counts the table slots a lookup reads, so that the bench can state the
+// merge-table traffic of a workload next to its text bytes. Nothing on the device.
+#ifndef ARKS_BPE_PROBE
+#define ARKS_BPE_PROBE(kind)
+#endif
 ARKS_HD uint32_t bpe_hash(uint32_t left, uint32_t right, uint32_t mask) {
   const uint64_t k = ((uint64_t)right << 32 | left) * 0x9E3779B97F4A7C15ull;
   return (uint32_t)(k >> 40) & mask;
@@ -51,6 +56,7 @@ ARKS_HD uint32_t bpe_hash(uint32_t left, uint32_t right, uint32_t mask) {
 ARKS_HD bool bpe_lookup(const BpeSlot* hot, const BpeTablesDev& T, uint32_t left, uint32_t right, uint32_t* rank, uint32_t* merged) {
   uint32_t s = bpe_hash(left, right, kBpeHotSlots - 1);
   for (;;) {
+    ARKS_BPE_PROBE(0);
     const BpeSlot e = hot[s];
     if (e.rank == 0xFFFFFFFFu) break;
     if (e.left == left && e.right == right) { *rank = e.rank; *merged = e.merged; return true; }
@@ -58,6 +64,7 @@ ARKS_HD bool bpe_lookup(const BpeSlot* hot, const BpeTablesDev& T, uint32_t left
   }
   s = bpe_hash(left, right, T.table_mask);
   for (;;) {
+    ARKS_BPE_PROBE(1);
     const BpeSlot e = T.table[s];
     if (e.rank == 0xFFFFFFFFu) return false;
     if (e.left == left && e.right == right) { *rank = e.rank; *merged = e.merged; return true; }

@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--wave", type=int, default=WAVE)
     ap.add_argument("--tenants", type=int, default=TENANTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bpe", action="store_true", help="skip the BPE count section (builds a 151 k-merge stand-in vocabulary: ~30 s)")
     ap.add_argument("--shared-quota", type=int, default=0, metavar="K",
                     help="K quotas per GPU are replicas of quotas shared by all GPUs: every --fold-every steps the library folds "
                          "their increments with ncclAllReduce (arks_fold_quota_allreduce) INSIDE the timed region")
@@ -110,6 +111,76 @@ def build_waves(workload, n_waves, wave, rank):
     first pass admits, so they are produced after a dry request pass on the device (see run_b200)."""
     return [workload.request_batch(wave, NOW0, seed=1000 + 17 * rank + k, body_size=BODY, n_templates=N_TEMPL, varied=True)
             for k in range(n_waves)]
+
+
+def bpe_section(g, w, reqs, now, peak, sample=2048):
+    """Request waves with a vocabulary loaded: device time of the two BPE kernels per 65 536-body wave, their algorithmic
+    bytes (body read once + decoded text written and read + one 8-byte work-list entry per piece written and read + the count),
+    and SEPARATELY the merge-table slots they read (probes are not body bytes) - counted on the host build of
+    the same code (tests/host_machine.cpp) over a sample and scaled by body bytes. Every sampled count is compared with HF
+    `tokenizers` (the external oracle of this column). The Qwen2.5 vocabulary is not on disk: a seeded stand-in of the same
+    size (151 k merges) trained with `tokenizers` on synthetic text, same pre-tokenizer and algorithm."""
+    from arks_b200 import bpe
+    t0 = time.perf_counter()
+    tok, text = bpe.standin_tokenizer(151_643, cache_dir=os.path.join(ROOT, "tests", "_build"))
+    tables = bpe.load_tokenizer(text)
+    vocab_s = time.perf_counter() - t0
+    g.load_bpe(tables)
+    try:
+        for k in range(N_WAVES):
+            g.select_slot(k)
+            g.stage_request(reqs[k])
+        g.set_profiling(True)
+        ms = []
+        for i in range(3 + 12):
+            g.select_slot(i % N_WAVES)
+            g.run_request(now)
+            now += STEP_S
+            t = g.last_kernel_ms()
+            if i >= 3:
+                ms.append(t[3])
+        g.set_profiling(False)
+        g.select_slot(0)
+        reqs[0].now_unix = now
+        counts = g.handle_request_body(reqs[0]).bpe_count.copy()
+    finally:
+        g.set_profiling(False)
+        g.load_bpe(None)
+    # the sample: first `sample` rows of wave 0 against `tokenizers`, and through the host build for the table probes
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hostmachine as hm
+    hm.bpe_load(tables)
+    hm.bpe_probes()
+    rb = reqs[0]
+    n = min(sample, rb.n)
+    wrong = uncounted = 0
+    sample_body_bytes = 0
+    for i in range(n):
+        body = bytes(rb.bodies[rb.body_off[i]:rb.body_off[i] + rb.body_len[i]])
+        sample_body_bytes += len(body)
+        hm.bpe_count(body)
+        if counts[i] == bpe.UNCOUNTED:
+            uncounted += 1
+            continue
+        wrong += int(counts[i]) != sum(len(tok.encode(x, add_special_tokens=False).ids) for x in bpe.content_strings(body))
+    hot, full, pieces, text_bytes = hm.bpe_probes()
+    body_bytes = float(np.mean([int(b.body_len.sum()) for b in reqs]))
+    scale = body_bytes / sample_body_bytes
+    alg = body_bytes + scale * (2 * text_bytes + 16 * pieces) + 4 * rb.n
+    t_s = float(np.mean(ms)) / 1e3
+    counted = counts[counts != bpe.UNCOUNTED]
+    return {"kernels": "bpe_scan_kernel + bpe_merge_kernel", "ms_per_wave": t_s * 1e3, "bodies_per_wave": int(rb.n),
+            "tokens_per_wave_0": int(counted.sum()), "tokens_per_s": float(counted.sum()) / t_s, "uncounted_rows_wave_0": int((counts == bpe.UNCOUNTED).sum()),
+            "roofline": {"bound": "hbm", "achieved": alg / t_s / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t_s / 1e9 / peak,
+                         "algorithmic_bytes_per_launch": alg,
+                         "what": "body bytes read once + decoded text written and read + 8 B work-list entry per pre-token written and read + 4 B count"},
+            "table_probes": {"full_table_slots_per_wave": scale * full, "full_table_bytes_per_wave": scale * full * 16,
+                             "hot_table_slots_per_wave": scale * hot, "pretokens_per_wave": scale * pieces,
+                             "what": "16-byte merge-table slots read, NOT counted as body bytes: full table = open-addressing hash in HBM (8 MB, L2-resident), "
+                                     "hot table = the 1 400 lowest-rank merges staged into shared memory by one bulk copy (TMA) per block; counted on the host "
+                                     f"build of bpe.cuh over the first {n} bodies of wave 0 and scaled by body bytes"},
+            "checked_against_tokenizers": {"rows": n, "uncounted": uncounted, "different": wrong},
+            "vocabulary": f"stand-in byte-level BPE, {len(tables.left)} merges, Qwen2 pre-tokenizer, NFC flag {tables.flags} (the Qwen2.5 files are not on disk); built in {vocab_s:.1f} s"}
 
 
 def bind_to_gpu_numa(local: int):
@@ -698,6 +769,14 @@ def run_b200(args):
         "body_bytes_over_8TBps": (float(np.mean([int(b.body_len.sum()) for b in reqs])) +
                                   float(np.mean([int(b.body_len.sum()) for b in resps]))) * args.steps * world / (dev_ms / 1e3) / 8e12,
     }
+    # ---- the BPE count kernels (north star side output) on the same waves, timed by the library's own events
+    # around bpe_scan_kernel + bpe_merge_kernel. Last GPU work of the run and self-contained: a failure here is reported
+    # in the key and costs nothing else.
+    if not args.no_bpe:
+        try:
+            out["bpe"] = bpe_section(g, w, reqs, now, peak)
+        except Exception as e:  # noqa: BLE001
+            out["bpe"] = {"error": f"{type(e).__name__}: {e}"[:400]}
     if shared_quota:
         out["shared_quota"] = shared_quota
         out["config"]["parallelism"] += f" + {shared_quota['rows']} shared quotas folded every {args.fold_every} steps"

@@ -229,6 +229,9 @@ int hm_engine_response_span(const uint8_t* body, size_t len, uint32_t* span, int
 }
 
 // ---- the BPE token counter (arks_b200/csrc/bpe.cuh) on the host: the same scanner, pre-tokenizer and merge loop ----
+static unsigned long long g_bpe_probes[2];  // slots read in the shared-memory table / in the full table
+static unsigned long long g_bpe_pieces, g_bpe_text_bytes;
+#define ARKS_BPE_PROBE(kind) (g_bpe_probes[kind]++)
 #include "../arks_b200/csrc/bpe.cuh"
 #include <vector>
 static std::vector<BpeSlot> g_bpe_table, g_bpe_hot;
@@ -251,8 +254,15 @@ uint32_t hm_bpe_count(const uint8_t* body, size_t len) {
   uint32_t total = 0;
   const BpeScanOut o = bpe_scan_body(body, (uint32_t)len, text.data(), g_bpe, [&](uint32_t off, uint32_t n) {
     total += bpe_piece_tokens(text.data() + off, n, g_bpe.hot, g_bpe);
+    g_bpe_pieces++;
+    g_bpe_text_bytes += n;
   });
   return o.bad ? kBpeUncounted : total;
+}
+// table slots read since the last call: [0] hot (shared-memory) table, [1] full table; [2] pieces, [3] decoded text bytes
+void hm_bpe_probes(unsigned long long* out) {
+  out[0] = g_bpe_probes[0]; out[1] = g_bpe_probes[1]; out[2] = g_bpe_pieces; out[3] = g_bpe_text_bytes;
+  g_bpe_probes[0] = g_bpe_probes[1] = g_bpe_pieces = g_bpe_text_bytes = 0;
 }
 // the pieces of one plain text (UTF-8), as end offsets (test of the pre-tokenizer alone)
 int hm_bpe_pretokenize(const uint8_t* text, size_t len, uint32_t* ends, int cap) {

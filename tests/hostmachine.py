@@ -134,6 +134,13 @@ def bpe_load(tables):
     lib()._bpe_keep = tables
 
 
+def bpe_probes():
+    """since the last call: slots read in the hot (shared-memory) table, in the full table, pieces, decoded text bytes"""
+    out = (C.c_ulonglong * 4)()
+    lib().hm_bpe_probes(out)
+    return [int(x) for x in out]
+
+
 def bpe_count(body: bytes) -> int:
     return int(lib().hm_bpe_count(body, len(body)))
 
