@@ -772,7 +772,7 @@ def run_b200(args):
     # ---- the BPE count kernels (north star side output) on the same waves, timed by the library's own events
     # around bpe_scan_kernel + bpe_merge_kernel. Last GPU work of the run and self-contained: a failure here is reported
     # in the key and costs nothing else.
-    if not args.no_bpe:
+    if not args.no_bpe and world == 1:  # a one-GPU measurement: the scaling runs do not repeat it
         try:
             out["bpe"] = bpe_section(g, w, reqs, now, peak)
         except Exception as e:  # noqa: BLE001
