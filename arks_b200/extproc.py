@@ -252,19 +252,21 @@ class Batcher:
         self.q.put(None)
         self.t.join(timeout=5)
 
-    def request(self, body: bytes, token: bytes):
-        ev = threading.Event()
-        item = {"kind": "req", "body": body, "token": token, "ev": ev}
+    def _answer(self, item):
+        """enqueue and wait for the worker; a row that arrives after close() (or that the worker left behind when it stopped)
+        is answered like an engine failure instead of holding its stream forever"""
+        ev = item["ev"] = threading.Event()
         self.q.put(item)
-        ev.wait()
+        while not ev.wait(0.1):
+            if self._stop and not self.t.is_alive():
+                return dict(self._FAILED, error="the batcher is closed")
         return item["out"]
 
+    def request(self, body: bytes, token: bytes):
+        return self._answer({"kind": "req", "body": body, "token": token})
+
     def response(self, body: bytes, qos: int, flags: int, gen: int = None):
-        ev = threading.Event()
-        item = {"kind": "resp", "body": body, "qos": qos, "flags": flags, "gen": gen, "ev": ev}
-        self.q.put(item)
-        ev.wait()
-        return item["out"]
+        return self._answer({"kind": "resp", "body": body, "qos": qos, "flags": flags, "gen": gen})
 
     def between_batches(self, fn):
         """run fn() on the worker thread between two engine calls (a table generation swap: arks_commit_tables belongs to the

@@ -193,3 +193,17 @@ def test_loopback_gpu_engine():
     g = gateway.Gateway(0, 4096, 8 << 20)
     g.load_tables(t)
     run_loopback(g, t)
+
+
+def test_rows_and_calls_that_arrive_after_close_are_answered_not_held():
+    """a stream whose message reaches the Python batcher after close() gets the engine-failure row (-> 500, like an INCRBY
+    error in the reference, handle_request.go:199-205) instead of waiting forever; a table swap asked for then raises"""
+    tables = Tables(FX["tokens"], FX["quotas"], FX["endpoints"])
+    b = extproc.Batcher(OracleEngine(tables), clock=lambda: NOW)
+    assert int(b.request(FX["request_body"].encode(), b"sk-test123456")["reason"]) == abi.R_OK
+    b.close()
+    out = b.request(b"{}", b"t")
+    assert int(out["reason"]) == 255 and "closed" in out["error"]
+    assert int(b.response(b"{}", 0, abi.RESP_END_OF_STREAM)["reason"]) == 255
+    with pytest.raises(RuntimeError):
+        b.between_batches(lambda: 1)
