@@ -124,6 +124,14 @@ class Assembly:
         if a.objects:
             self.relist()
             self.provider.flush()  # "wait cache sync" (arks_impl.go:167-170): the first generation precedes the listeners
+            if a.restore and self.engine.tables is not None:
+                # the restore pass belongs BEFORE the first request, not one ticker period after it: a gateway that restarts
+                # must not hand every tenant a fresh quota for ten seconds (the reference's first pass comes with the ticker,
+                # arks_impl.go:217-225, and zeroes instead of restoring)
+                updates = self.provider.sync_quota_status(restore=True)
+                self.loop.restore_next = False
+                if updates:
+                    self._write_status(updates)
             self.threads.append(threading.Thread(target=self._watch_objects, daemon=True))
         self.threads.append(threading.Thread(target=self.loop.run, daemon=True))
         if a.events:

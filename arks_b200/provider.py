@@ -108,7 +108,7 @@ class ArksProvider:
         try:
             spec = _spec_of(kind, obj, self.ready_backends)
         except (KeyError, TypeError, ValueError) as e:  # a rule / quota type this gateway does not know, a missing field
-            self.rejected.append((kind, k, repr(e)))
+            self._reject(kind, k, e)
             return False
         if self._spec[kind].get(k) == spec:
             self.objects[kind][k] = obj  # status and metadata stay current even when the spec did not move
@@ -122,12 +122,16 @@ class ArksProvider:
             else:
                 self.g.upsert_endpoint(k[0], k[1], spec[1])
         except Exception as e:  # the library keeps the previous version of the object
-            self.rejected.append((kind, k, repr(e)))
+            self._reject(kind, k, e)
             return False
         self.objects[kind][k] = obj
         self._spec[kind][k] = spec
         self.dirty = True
         return True
+
+    def _reject(self, kind, k, e):
+        self.rejected.append((kind, k, repr(e)))
+        del self.rejected[:-256]  # a diagnostic, not a log: an object that is re-sent broken for days must not grow the process
 
     def _delete(self, kind, obj) -> bool:
         k = object_key(obj)
@@ -271,6 +275,7 @@ class ProviderLoop:
                 wake = self.step(now)
             except Exception as e:  # a refused generation or a failed status pass must not end the loop: retried in a second
                 self.errors.append(repr(e))
+                del self.errors[:-256]
                 print(f"arks provider: {e!r}", file=sys.stderr)
                 wake = now + 1.0
             self.stop.wait(max(0.001, min(wake - time.monotonic(), 0.05)))

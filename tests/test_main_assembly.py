@@ -83,8 +83,10 @@ def test_the_assembled_process(tmp_path):
         st, ct, text = get(asm.metrics_port, path="/metrics")
         assert st == 200 and b'gateway_request_duration_seconds_count{namespace="default",user="adam",model="qwen-7b"} 1' in text
         assert b'gateway_requests_total{namespace="default",user="adam",model="qwen-7b",status="200"}' in text  # the engine's rows
-        # the status loop: first pass in restore mode, one line per ArksQuota whose status moved
-        wait_for(lambda: "basic-quota" in status.getvalue(), "no status update was written")
+        # the status loop: the restore pass ran before the listeners opened (it entered the quota's types into the status, all
+        # zero); the ticker then writes one line per ArksQuota whose status moved
+        assert not asm.loop.restore_next and '"used":0' in status.getvalue().splitlines()[0]
+        wait_for(lambda: '"used":45' in status.getvalue(), "no status update was written")
         line = json.loads(status.getvalue().splitlines()[-1])
         assert (line["kind"], line["metadata"]) == ("ArksQuota", {"namespace": "default", "name": "basic-quota"})
         assert {s["type"]: s["used"] for s in line["status"]["quotaStatus"]} == {"prompt": 25, "response": 20, "total": 45}
@@ -106,3 +108,28 @@ def test_main_refuses_without_a_cuda_device():
     p = subprocess.run([sys.executable, "-m", "arks_b200", "--server.grpc-port", "0"], capture_output=True, text=True, timeout=300,
                        cwd=os.path.dirname(HERE))
     assert p.returncode != 0 and "no CPU fallback" in p.stderr
+
+
+def test_a_restart_restores_the_quota_counters_before_the_first_request(tmp_path):
+    """ArksQuota.status carries what the previous process billed; with --provider.restore-on-start (default) the counters are
+    raised to it before the listeners open, so the very first request already meets the quota (the reference's first pass comes
+    ten seconds later and zeroes the store instead, arks_impl.go:217-225,286-288)"""
+    objs = crds()
+    for o in objs:
+        if o["kind"] == "ArksQuota":
+            limits = {i["type"]: int(i["value"]) for i in o["spec"]["quotas"]}
+            o["status"] = {"quotaStatus": [{"type": t, "used": v + 1, "lastUpdateTime": "2025-01-01T00:00:00Z"} for t, v in limits.items()]}
+    objects = tmp_path / "objects.yaml"
+    objects.write_text(yaml.safe_dump_all(objs))
+    args = parse_args(["--server.grpc-port", "0", "--server.http-port", "0", "--metrics.port", "0", "--server.bind", "127.0.0.1",
+                       "--provider.objects", str(objects), "--batcher", "python"])
+    asm = Assembly(LiveEngine(), args, status_out=io.StringIO()).start()
+    try:
+        assert not asm.loop.restore_next
+        ch, stub = extproc.client_stub(asm.grpc_port)
+        r = list(stub(iter([hdrs([("authorization", "Bearer sk-test123456")]), body(FX["request_body"].encode(), "request_body")])))
+        im = r[1].immediate_response
+        assert im.status.code == 429 and "x-error-quota" in set_headers(im.headers)
+        ch.close()
+    finally:
+        assert asm.shutdown() == []
