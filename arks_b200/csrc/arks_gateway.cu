@@ -2281,6 +2281,7 @@ void arks_discard_prepared(arks_ctx* ctx, arks_prepared* p) {
 int arks_prepare_tables(arks_ctx* ctx, const arks_tables* t, arks_prepared** out) {
   if (!ctx || !t || !out) return ARKS_E_INVALID_ARG;
   *out = nullptr;
+  if (const char* why = tables_shape_error(t)) return fail(ctx, ARKS_E_BAD_TABLE, "arks_tables: %s", why);
   CK(cudaSetDevice(ctx->device));
   auto S = [&](uint32_t id) {
     return std::string((const char*)t->str_bytes + t->str_off[id], t->str_off[id + 1] - t->str_off[id]);
@@ -2600,8 +2601,12 @@ int arks_config_prepare(arks_ctx* ctx, arks_prepared** out) {
   return arks_prepare_tables(ctx, &t, out);
 }
 
+// the host tables of the current generation are replaced by arks_commit_tables (batch thread) under cfg_mu: readers on the
+// config thread take it too
 int32_t arks_find_quota(const arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len) {
-  if (!ctx || !ctx->loaded) return -1;
+  if (!ctx) return -1;
+  std::lock_guard<std::mutex> g(const_cast<arks_ctx*>(ctx)->cfg_mu);
+  if (!ctx->loaded) return -1;
   const std::string k = std::string(ns ? ns : "", ns_len) + '\0' + std::string(name ? name : "", name_len);
   for (uint32_t q = 0; q < ctx->ht.n_quotas; q++)
     if (ctx->ht.quota_key[q] == k) return (int32_t)q;
@@ -2609,7 +2614,9 @@ int32_t arks_find_quota(const arks_ctx* ctx, const char* ns, uint32_t ns_len, co
 }
 int32_t arks_find_qos(const arks_ctx* ctx, const char* ns, uint32_t ns_len, const char* user, uint32_t user_len, const char* model,
                       uint32_t model_len) {
-  if (!ctx || !ctx->loaded) return -1;
+  if (!ctx) return -1;
+  std::lock_guard<std::mutex> g(const_cast<arks_ctx*>(ctx)->cfg_mu);
+  if (!ctx->loaded) return -1;
   const std::string k = std::string(ns ? ns : "", ns_len) + '\0' + std::string(user ? user : "", user_len) + '\0' + std::string(model ? model : "", model_len);
   for (uint32_t q = 0; q < ctx->ht.n_qos; q++)
     if (ctx->ht.qos_key[q] == k) return (int32_t)q;
@@ -2627,6 +2634,10 @@ int arks_update_endpoint_weights(arks_ctx* ctx, uint32_t ep, uint32_t n, const i
   if (!ctx || !ctx->loaded) return ARKS_E_NOT_LOADED;
   if (ep >= ctx->ht.n_endpoints || ctx->ht.ep_backend_off[ep + 1] - ctx->ht.ep_backend_off[ep] != n)
     return fail(ctx, ARKS_E_INVALID_ARG, "endpoint %u has a different backend count", ep);
+  if (n == 0) return 0;
+  if (!w) return ARKS_E_INVALID_ARG;
+  for (uint32_t i = 0; i < n; i++)
+    if (w[i] < 0) return fail(ctx, ARKS_E_INVALID_ARG, "endpoint %u: negative backend weight", ep);
   CK(cudaSetDevice(ctx->device));
   // stream-ordered: lands between the previous and the next batch
   CK(cudaMemcpyAsync(ctx->d_backend_weight + ctx->ht.ep_backend_off[ep], w, n * 4, cudaMemcpyHostToDevice, ctx->stream));

@@ -70,6 +70,45 @@ struct FlatTables {
   }
 };
 
+// Shape check of a caller-built snapshot (arks_prepare_tables / arks_load_tables): every index the host code and the kernels
+// will follow must stay inside its array. The reference gets its objects from the API server, validated by the CRD schemas
+// (api/v1/*_types.go kubebuilder markers); a C caller has no such guard, and a bad offset here would be an out-of-bounds read
+// on the device. Returns NULL when the snapshot is well formed, else what is wrong (static text).
+inline const char* tables_shape_error(const arks_tables* t) {
+  if (!t) return "null tables";
+  auto csr = [](const uint32_t* off, uint32_t n, uint32_t total) {
+    if (!off || off[0] != 0 || off[n] != total) return false;
+    for (uint32_t i = 0; i < n; i++)
+      if (off[i] > off[i + 1]) return false;
+    return true;
+  };
+  auto ids = [&](const uint32_t* id, uint32_t n) {
+    if (n && !id) return false;
+    for (uint32_t i = 0; i < n; i++)
+      if (id[i] >= t->n_str) return false;
+    return true;
+  };
+  if (!t->str_off || (t->n_str && t->str_off[t->n_str] && !t->str_bytes)) return "string pool: null pointer";
+  for (uint32_t i = 0; i < t->n_str; i++)
+    if (t->str_off[i] > t->str_off[i + 1]) return "string pool: offsets decrease";
+  if (!ids(t->tok_token_str, t->n_tokens) || !ids(t->tok_ns_str, t->n_tokens) || !ids(t->tok_name_str, t->n_tokens))
+    return "ArksToken: string id out of range";
+  if (!csr(t->tok_qos_off, t->n_tokens, t->n_qos)) return "tok_qos_off is not a CSR over the qos entries";
+  if (!ids(t->qos_model_str, t->n_qos)) return "qos: model string id out of range";
+  if (t->n_qos && !t->qos_quota) return "qos_quota: null pointer";
+  if (!csr(t->qos_rl_off, t->n_qos, t->n_rl)) return "qos_rl_off is not a CSR over the rate limits";
+  if (t->n_rl && (!t->rl_rule || !t->rl_value)) return "rate limits: null pointer";
+  if (!ids(t->quota_ns_str, t->n_quotas) || !ids(t->quota_name_str, t->n_quotas)) return "ArksQuota: string id out of range";
+  if (!csr(t->quota_item_off, t->n_quotas, t->n_qitems)) return "quota_item_off is not a CSR over the quota items";
+  if (t->n_qitems && (!t->qitem_type || !t->qitem_value)) return "quota items: null pointer";
+  if (!ids(t->ep_ns_str, t->n_endpoints) || !ids(t->ep_name_str, t->n_endpoints)) return "ArksEndpoint: string id out of range";
+  if (!csr(t->ep_backend_off, t->n_endpoints, t->n_backends)) return "ep_backend_off is not a CSR over the backends";
+  if (t->n_backends && !t->backend_weight) return "backend_weight: null pointer";
+  for (uint32_t i = 0; i < t->n_backends; i++)
+    if (t->backend_weight[i] < 0) return "negative backend weight";
+  return nullptr;
+}
+
 struct ConfigStore {
   using Key = std::pair<std::string, std::string>;  // (namespace, name)
   struct Qos {

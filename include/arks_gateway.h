@@ -50,7 +50,8 @@ enum arks_status {
   ARKS_E_CUDA = -3,
   ARKS_E_TIME_WENT_BACK = -4, /* now_unix fell into an earlier window than a previous batch */
   ARKS_E_BAD_TABLE = -5,      /* unknown rate-limit rule / quota type (reference: 500 / panic,
-                                 pkg/gateway/check.go:112-121, ratelimiter/types.go:46) */
+                                 pkg/gateway/check.go:112-121, ratelimiter/types.go:46); or a snapshot whose
+                                 offsets / string ids / weights are out of range (checked before anything follows them) */
   ARKS_E_CAPACITY = -6,
   ARKS_E_NOT_LOADED = -7,
 };

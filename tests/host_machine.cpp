@@ -319,6 +319,8 @@ void hm_store_upsert_endpoint(void* s, const char* ns, uint32_t ns_len, const ch
 int hm_store_erase(void* s, int which, const char* ns, uint32_t ns_len, const char* name, uint32_t name_len) {
   return static_cast<HmStore*>(s)->st.erase(which, ns, ns_len, name, name_len) ? 1 : 0;
 }
+// the snapshot shape check arks_prepare_tables applies (config_store.h): NULL = well formed
+const char* hm_tables_shape_error(const arks_tables* t) { return arks::tables_shape_error(t); }
 const arks_tables* hm_store_flatten(void* s) {
   HmStore* h = static_cast<HmStore*>(s);
   h->flat = arks::FlatTables();

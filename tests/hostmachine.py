@@ -47,6 +47,8 @@ def lib():
         L.hm_store_erase.argtypes = [vp, C.c_int, cp, u32, cp, u32]
         L.hm_store_flatten.argtypes = [vp]
         L.hm_store_flatten.restype = vp
+        L.hm_tables_shape_error.argtypes = [vp]
+        L.hm_tables_shape_error.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -132,6 +134,12 @@ def bpe_load(tables):
     t = tables.c_struct()
     lib().hm_bpe_load(t.byte_id, t.n_merges, t.left, t.right, t.merged, t.cp_class, t.flags)
     lib()._bpe_keep = tables
+
+
+def tables_shape_error(c_tables):
+    """c_tables: a ctypes arks_tables (arks_b200.tables.Tables.c_struct()); None when well formed, else the complaint"""
+    e = lib().hm_tables_shape_error(C.cast(C.pointer(c_tables), C.c_void_p))
+    return e.decode() if e else None
 
 
 def bpe_probes():

@@ -5,6 +5,7 @@ import random
 
 import numpy as np
 import orklib
+import hostmachine as hm
 from hostmachine import ConfigStore
 
 from arks_b200 import traffic
@@ -76,3 +77,42 @@ def test_empty_store_and_empty_objects_flatten():
     ts = st.flatten().c_struct()
     assert (ts.n_tokens, ts.n_qos, ts.n_quotas, ts.n_endpoints, ts.n_backends) == (1, 0, 1, 1, 0)
     assert orklib.Oracle(st.flatten()) is not None
+
+
+def test_snapshot_shape_check_accepts_every_producer_and_names_what_is_wrong():
+    """arks_prepare_tables / arks_load_tables check a caller-built snapshot before anything follows its indices
+    (config_store.h: tables_shape_error; the reference's objects come validated from the API server). Every producer in this
+    repository must pass; a snapshot with one index out of place is refused with the array named."""
+    import copy
+    import json
+    import os
+    import numpy as np
+    from arks_b200 import traffic
+    from arks_b200.tables import Tables
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "quickstart.json")))
+    good = [Tables(fx["tokens"], fx["quotas"], fx["endpoints"]), Tables([], [], []),
+            traffic.Workload(n_tenants=300, seed=9).tables, traffic.Workload(50, seed=3, n_backends=16).tables]
+    for t in good:
+        assert hm.tables_shape_error(t.c_struct()) is None
+    # the library's own flatten (object-level config plane), full and empty
+    w = traffic.Workload(n_tenants=40, seed=2)
+    st = ConfigStore()
+    assert hm.tables_shape_error(st.flatten().c_struct()) is None
+    for kind, objs in zip(("token", "quota", "endpoint"), w.objects):
+        for o in objs:
+            st.upsert(kind, as_endpoint(o) if kind == "endpoint" else o)
+    assert hm.tables_shape_error(st.flatten().c_struct()) is None
+
+    def broken(field, edit):
+        t = copy.deepcopy(good[2])
+        edit(getattr(t, field))
+        return hm.tables_shape_error(t.c_struct())
+    assert "tok_qos_off" in broken("tok_qos_off", lambda a: a.__setitem__(3, a[3] + 1000))
+    assert "tok_qos_off" in broken("tok_qos_off", lambda a: a.__setitem__(0, 1))
+    assert "qos_rl_off" in broken("qos_rl_off", lambda a: a.__setitem__(-1, a[-1] + 1))
+    assert "quota_item_off" in broken("quota_item_off", lambda a: a.__setitem__(5, 0))
+    assert "ep_backend_off" in broken("ep_backend_off", lambda a: a.__setitem__(-1, a[-1] - 1))
+    assert "string id" in broken("tok_ns_str", lambda a: a.__setitem__(7, 1 << 30))
+    assert "string id" in broken("qos_model_str", lambda a: a.__setitem__(0, 0xFFFFFFFF))
+    assert "string pool" in broken("str_off", lambda a: a.__setitem__(4, a[5] + 1))
+    assert "negative" in broken("backend_weight", lambda a: a.__setitem__(1, -1))
