@@ -2728,12 +2728,16 @@ int arks_stage_request_batch(arks_ctx* ctx, const arks_request_batch* b) {
   int rc = ensure_slot(ctx, ctx->cur, true, false);
   if (rc) return rc;
   arks_ctx::Slot& sl = ctx->slots[ctx->cur];
+  sl.req_staged = false;  // a batch that is refused below leaves nothing to run in this slot
   sl.req_n = n;
-  sl.req_staged = true;
-  if (n == 0) return 0;
-  for (uint32_t i = 0; i < n; i++)
+  if (n == 0) { sl.req_staged = true; return 0; }
+  if (!b->body_off || !b->body_len || !b->token_off || (b->bodies_bytes && !b->bodies) || (b->token_off[n] && !b->tokens))
+    return fail(ctx, ARKS_E_INVALID_ARG, "request batch: null array");
+  for (uint32_t i = 0; i < n; i++) {
     if ((b->body_off[i] & 15u) || (uint64_t)b->body_off[i] + b->body_len[i] > b->bodies_bytes)
       return fail(ctx, ARKS_E_INVALID_ARG, "body %u: offset not 16-byte aligned or out of range", i);
+    if (b->token_off[i] > b->token_off[i + 1]) return fail(ctx, ARKS_E_INVALID_ARG, "token %u: offsets decrease", i);
+  }
   const size_t tok_bytes = b->token_off[n];
   size_t o_off = 0, o_len = o_off + align_up((size_t)n * 4, 256), o_toff = o_len + align_up((size_t)n * 4, 256),
          o_rand = o_toff + align_up((size_t)(n + 1) * 4, 256), o_tok = o_rand + align_up((size_t)n * 8, 256),
@@ -2745,8 +2749,9 @@ int arks_stage_request_batch(arks_ctx* ctx, const arks_request_batch* b) {
   memcpy(h + o_len, b->body_len, (size_t)n * 4);
   memcpy(h + o_toff, b->token_off, (size_t)(n + 1) * 4);
   if (b->pick_rand) memcpy(h + o_rand, b->pick_rand, (size_t)n * 8);
-  memcpy(h + o_tok, b->tokens, tok_bytes);
-  const bool small = b->bodies_bytes <= kSmallBatchBytes;
+  if (tok_bytes) memcpy(h + o_tok, b->tokens, tok_bytes);
+  // (a micro-batch whose tokens leave no room for its bodies behind the metadata takes the large path: separate buffer)
+  const bool small = b->bodies_bytes <= kSmallBatchBytes && total + b->bodies_bytes <= ctx->meta_cap;
   if (small) {
     // one upload for a handful of bodies (the extra memcpy is cheaper than a second copy call); above that the bodies go
     // up from the caller's buffer, as in the large path, but still on the compute stream (no cross-stream event)
@@ -2773,6 +2778,7 @@ int arks_stage_request_batch(arks_ctx* ctx, const arks_request_batch* b) {
   r.pick_rand = b->pick_rand ? (const unsigned long long*)(sl.d_req_meta + o_rand) : nullptr;
   r.tokens = sl.d_req_meta + o_tok;
   r.n = n;
+  sl.req_staged = true;
   return 0;
 }
 
@@ -3041,9 +3047,10 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   int rc = ensure_slot(ctx, ctx->cur, false, true);
   if (rc) return rc;
   arks_ctx::Slot& sl = ctx->slots[ctx->cur];
+  sl.resp_staged = false;  // a batch that is refused below leaves nothing to run in this slot
   sl.resp_n = n;
-  sl.resp_staged = true;
-  if (n == 0) return 0;
+  if (n == 0) { sl.resp_staged = true; return 0; }
+  if (!b->body_off || !b->body_len || !b->qos || !b->flags || (b->bodies_bytes && !b->bodies)) return fail(ctx, ARKS_E_INVALID_ARG, "response batch: null array");
   uint32_t n_sse = 0;
   for (uint32_t i = 0; i < n; i++) {
     n_sse += (b->flags[i] & ARKS_RESP_STREAM) != 0;
@@ -3105,6 +3112,7 @@ int arks_stage_response_batch(arks_ctx* ctx, const arks_response_batch* b) {
   r.counted = rb + align_up(n, 16);
   r.usage = (long long*)(rb + 2 * align_up(n, 16));
   r.bpe = (uint32_t*)(rb + 2 * align_up(n, 16) + (size_t)n * 24);
+  sl.resp_staged = true;
   return 0;
 }
 

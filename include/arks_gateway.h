@@ -152,7 +152,8 @@ typedef struct arks_request_batch {
   const uint32_t* body_len;   /* n: exact length                                                */
   uint64_t bodies_bytes;      /* total size of `bodies` (last body padded up to 16)             */
   const uint8_t* tokens;      /* concatenated bearer tokens (output of arks_extract_bearer)     */
-  const uint32_t* token_off;  /* n + 1                                                          */
+  const uint32_t* token_off;  /* n + 1, non-decreasing (a batch that breaks this or the body     *
+                               * bounds is refused as a whole: ARKS_E_INVALID_ARG, nothing staged) */
   const uint64_t* pick_rand;  /* n or NULL: per-request random for the weighted pick (A12)      */
   int64_t now_unix;
 } arks_request_batch;
