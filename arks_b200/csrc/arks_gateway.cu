@@ -3391,6 +3391,7 @@ struct NcclApi {
   long long* d_msg = nullptr;  // what crosses the fabric: n_shared x 3 int64
   uint32_t n_shared = 0;
   bool all_rows = true;
+  uint32_t generation = 0;     // the table generation the indices in d_idx belong to
 };
 static int nccl_load(arks_ctx* ctx) {
   if (ctx->nccl) return 0;
@@ -3445,6 +3446,7 @@ int arks_comm_set_shared(arks_ctx* ctx, const uint32_t* shared, uint32_t n_share
   cudaFree(a.d_msg);
   a.d_idx = nullptr; a.d_msg = nullptr;
   a.n_shared = (uint32_t)idx.size();
+  a.generation = ctx->generation;
   CK(cudaMalloc(&a.d_idx, idx.size() * 4 + 64));
   CK(cudaMalloc(&a.d_msg, idx.size() * 24 + 64));
   CK(cudaMemcpy(a.d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice));
@@ -3467,7 +3469,10 @@ int arks_fold_quota_allreduce(arks_ctx* ctx, int wait) {
   if (!ctx || !ctx->nccl || !ctx->nccl->comm) return fail(ctx, ARKS_E_INVALID_ARG, "arks_comm_init first");
   if (!ctx->loaded || !ctx->d_qdelta) return fail(ctx, ARKS_E_INVALID_ARG, "quota sharing is not enabled");
   NcclApi& a = *ctx->nccl;
-  if (a.all_rows && a.n_shared != ctx->ht.n_quotas) return fail(ctx, ARKS_E_INVALID_ARG, "the tables changed: arks_comm_set_shared again");
+  // local quota indices are positional in the generation they were given for: a swap since then may have moved or removed them
+  if (a.generation != ctx->generation || (a.all_rows && a.n_shared != ctx->ht.n_quotas))
+    return fail(ctx, ARKS_E_INVALID_ARG, "the tables changed since arks_comm_set_shared (generation %u, now %u): call it again", a.generation,
+                ctx->generation);
   CK(cudaSetDevice(ctx->device));
   const size_t n_all = (size_t)3 * ctx->ht.n_quotas;
   if (!n_all) return 0;

@@ -409,7 +409,9 @@ int arks_fold_quota_delta_dev(arks_ctx* ctx, const void* reduced_dev, const void
  *   arks_comm_unique_id   rank 0: 128 opaque bytes (ncclGetUniqueId) to hand to every rank over any channel
  *   arks_comm_init        every rank: ncclCommInitRank. `shared` lists, in the SAME canonical order on every rank, the LOCAL
  *                         indices of the quotas that live on every GPU (local numbering may differ per rank); NULL / 0 =
- *                         every quota, identical numbering everywhere. Call again after a table swap that moves them.
+ *                         every quota, identical numbering everywhere. Call arks_comm_set_shared again after every table
+ *                         swap: the indices belong to the generation they were given for, and a fold against another
+ *                         generation is refused (ARKS_E_INVALID_ARG) instead of touching rows that moved.
  *   arks_fold_quota_allreduce   one fold epoch, stream-ordered: snapshot this GPU's unfolded increments, gather the shared
  *                         rows, ncclAllReduce(sum, int64) in place, quota += reduced - own on the shared rows, delta -= the
  *                         snapshot. wait != 0 also waits for it (the epoch's duration is then the call's).
