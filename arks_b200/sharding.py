@@ -46,6 +46,14 @@ class QuotaDeltaExchange:
         self.idx = np.ascontiguousarray(shared_local_idx, np.int64)
         self._comm = False
 
+    def set_shared(self, n_quotas: int, shared_local_idx):
+        """after a table swap: the shared quotas' local indices in the NEW generation (the library refuses a fold whose
+        indices belong to another generation, arks_comm_set_shared)"""
+        self.n = n_quotas
+        self.idx = np.ascontiguousarray(shared_local_idx, np.int64)
+        if self._comm:
+            self.engine.comm_set_shared(self.idx)
+
     def fold(self):
         import torch
         import torch.distributed as dist
