@@ -186,7 +186,7 @@ def sse_split(chunk: bytes):
         return None
     if b"\r" in chunk.replace(b"\r\n", b"\n"):
         return None
-    pending = False
+    has_data, event_name = False, b""  # what openai-python holds when a blank line arrives
     lines = chunk.replace(b"\r\n", b"\n").split(b"\n")
     for li, line in enumerate(lines):
         if len(line) >= 65000:
@@ -197,16 +197,17 @@ def sse_split(chunk: bytes):
         if not line:
             # openai-go dispatches an event on EVERY blank line (an event without data then fails to unmarshal);
             # openai-python swallows a blank line when nothing is pending. Chunks with such a line are outside the subset.
-            if not pending and li < len(lines) - 1:
+            if not (has_data or event_name) and li < len(lines) - 1:
                 return None
-            pending = False
+            has_data, event_name = False, b""
         elif name == b"data":
-            pending = True
+            has_data = True
         elif name == b"event":
             value = line.split(b":", 1)[1] if b":" in line else b""
             if value[:1] == b" ":
                 value = value[1:]
-            pending = pending or bool(value)  # openai-python tests the event NAME for truthiness
+            event_name = value  # openai-python tests the event NAME for truthiness, and a later `event` line REPLACES it
+                                # (`event: message` then a bare `event` leaves nothing pending there; openai-go dispatches)
     # Go's bufio.Scanner delivers an unterminated last line as a token; openai-python's chunker does too
     return [(e.event or "", e.data) for e in SSEDecoder().iter_bytes(iter([chunk]))]
 

@@ -182,3 +182,14 @@ def test_device_engine_host_build_matches_golden_vectors(vec):
             assert rc == e["err"], (e["doc"], rc)
             if not rc:
                 assert list(usage) == list(e["usage"]), e["doc"]
+
+
+def test_a_bare_event_line_replaces_the_event_name():
+    """found by a long run of the pin above (seed 1000): `event: message` followed by a bare `event` line leaves openai-python
+    with nothing pending, so it swallows the blank line, while openai-go (the reference's decoder) dispatches an event on
+    EVERY blank line. The chunk is outside the subset on which the two agree; the oracle follows openai-go."""
+    doc = b'data:  NULL\n\ndata:{"choices":[ ]}\n\nevent: message\nevent\n\r\n'
+    assert pymodel.sse_split(doc) is None
+    n, got = orklib.sse_events(doc)
+    assert n == 3 and [(t, d) for t, d, _ in got][2] == (b"", b"")
+    assert pymodel.sse_split(b'event: message\nevent: x\ndata: 1\n\n') == [("x", "1")]
