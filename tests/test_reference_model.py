@@ -182,8 +182,8 @@ def test_oracle_against_the_go_shaped_model(seed):
     for step in range(40):
         now += r.choice([0, 1, 7, 30, 61, 3600, 90000])  # same window, next minute, next day
         reqs = [random_request(r, tokens) for _ in range(r.randint(1, 60))]
-        got = o.request_batch(RequestBatch.from_lists([b for _, b in reqs], [t for t, _ in reqs], now,
-                                                      pick_rand=np.array([r.getrandbits(63) for _ in reqs], np.uint64)))
+        rand = [r.getrandbits(63) for _ in reqs]
+        got = o.request_batch(RequestBatch.from_lists([b for _, b in reqs], [t for t, _ in reqs], now, pick_rand=np.array(rand, np.uint64)))
         admitted = []
         for i, (tok, body) in enumerate(reqs):
             f = {"err": 1} if body.endswith(b"]") else pymodel.request_fields(body)
@@ -196,6 +196,17 @@ def test_oracle_against_the_go_shaped_model(seed):
                 q = key_of[(qos["namespace"], qos["user"], qos["model"])]
                 assert int(got.qos[i]) == q and bool(got.flags[i] & 1) == stream
                 assert (tables.token_namespace[int(got.token[i])], tables.token_user[int(got.token[i])]) == (qos["namespace"], qos["user"])
+                # A12: the backend Envoy's weighted-cluster walk lands on for this request's random (r mod sum of weights over
+                # the cumulative weights, in backendRef order: static routeConfigs; no discovered Services in this cluster)
+                ep = next(e for e in endpoints if (e["metadata"]["namespace"], e["metadata"]["name"]) == (qos["namespace"], qos["model"]))
+                weights = [int(rc["weight"]) for rc in ep["spec"]["routeConfigs"]]
+                want, x = -1, rand[i] % sum(weights) if sum(weights) else 0
+                for k, wgt in enumerate(weights):
+                    if sum(weights) and x < wgt:
+                        want = k
+                        break
+                    x -= wgt
+                assert int(got.pick[i]) == want, (seed, step, weights, rand[i])
                 admitted.append((q, qos))
         # the upstream answers some of the admitted requests (complete bodies; SSE has its own pins)
         resp = []
