@@ -171,10 +171,18 @@ def random_request(r: random.Random, tokens):
 
 @pytest.mark.parametrize("seed", range(40))
 def test_oracle_against_the_go_shaped_model(seed):
+    run_scenario(orklib.Oracle, seed)
+
+
+def run_scenario(make_engine, seed):
+    """make_engine(tables) -> anything with handle-or-oracle batch calls (the oracle here; the CUDA library in
+    tests/test_z_gpu_reference_model.py)"""
     r = random.Random(1000 + seed)
     tokens, quotas, endpoints = random_objects(r)
     tables = Tables(tokens, quotas, endpoints)
-    o, go = orklib.Oracle(tables), GoGateway(tokens, quotas, endpoints)
+    o, go = make_engine(tables), GoGateway(tokens, quotas, endpoints)
+    request_batch = getattr(o, "request_batch", None) or o.handle_request_body
+    response_batch = getattr(o, "response_batch", None) or o.handle_response_body
     key_of = {(tables.token_namespace[int(tables.qos_token[q])], tables.token_user[int(tables.qos_token[q])], tables.qos_model_name[q]): q
               for q in reversed(range(tables.n_qos))}  # first entry with the key
     now = 1_700_000_000 + r.randint(0, 86400)
@@ -183,7 +191,7 @@ def test_oracle_against_the_go_shaped_model(seed):
         now += r.choice([0, 1, 7, 30, 61, 3600, 90000])  # same window, next minute, next day
         reqs = [random_request(r, tokens) for _ in range(r.randint(1, 60))]
         rand = [r.getrandbits(63) for _ in reqs]
-        got = o.request_batch(RequestBatch.from_lists([b for _, b in reqs], [t for t, _ in reqs], now, pick_rand=np.array(rand, np.uint64)))
+        got = request_batch(RequestBatch.from_lists([b for _, b in reqs], [t for t, _ in reqs], now, pick_rand=np.array(rand, np.uint64)))
         admitted = []
         for i, (tok, body) in enumerate(reqs):
             f = {"err": 1} if body.endswith(b"]") else pymodel.request_fields(body)
@@ -217,7 +225,7 @@ def test_oracle_against_the_go_shaped_model(seed):
                 d = r.choice([{"model": "x", "usage": u}, {"model": "x", "usage": u, "choices": []}, {"usage": u}, {"model": "x"}, {"model": 5}])
                 resp.append((q, qos, json.dumps(d).encode()))
         if resp:
-            rgot = o.response_batch(ResponseBatch.from_lists([b for _, _, b in resp], [q for q, _, _ in resp],
+            rgot = response_batch(ResponseBatch.from_lists([b for _, _, b in resp], [q for q, _, _ in resp],
                                                              [abi.RESP_END_OF_STREAM] * len(resp), now + 1))
             for i, (q, qos, body) in enumerate(resp):
                 reason, counted, usage = go.handle_response_body(pymodel.response_fields(body), qos, now + 1)
@@ -237,6 +245,8 @@ def test_oracle_against_the_go_shaped_model(seed):
         now += 1  # the library's clock contract: a batch never falls into an earlier window than the one before it
     for k, v in enumerate(seen):
         COVERED[k] += v
+    if hasattr(o, "close"):
+        o.close()
 
 
 COVERED = [0] * 17
