@@ -148,7 +148,9 @@ def random_objects(r: random.Random):
         for u in range(r.randint(1, 4)):
             qos = []
             for m in r.sample(models + ["other"], r.randint(1, len(models) + 1)):
-                lim = [{"type": t, "value": r.choice([0, 1, 3, 8, 60, 2000])} for t in r.sample(list(RULES), r.randint(0, 4))]
+                # 0-4 limits in any order; one entry in four repeats a rule (every entry is checked and INCRBY'd on its own)
+                rules = r.sample(list(RULES), r.randint(0, 4)) if r.random() < 0.75 else [r.choice(list(RULES)) for _ in range(r.randint(1, 4))]
+                lim = [{"type": t, "value": r.choice([0, 1, 3, 8, 60, 2000])} for t in rules]
                 quota = r.choice(qnames + ["", "", "missing"]) if qnames or r.random() < 0.5 else ""
                 qos.append({"arksEndpoint": {"name": m}, "rateLimits": lim, "quota": {"name": quota}})
             tokens.append({"metadata": {"name": "u%d" % u, "namespace": ns}, "spec": {"token": "sk-%s-%d" % (ns, u), "qos": qos}})
