@@ -113,7 +113,7 @@ def build_waves(workload, n_waves, wave, rank):
             for k in range(n_waves)]
 
 
-def bpe_section(g, w, reqs, now, peak, sample=2048):
+def bpe_section(g, w, reqs, resps, now, peak, ext, sample=2048):
     """Request waves with a vocabulary loaded: device time of the two BPE kernels per 65 536-body wave, their algorithmic
     bytes (body read once + decoded text written and read + one 8-byte work-list entry per piece written and read + the count),
     and SEPARATELY the merge-table slots they read (probes are not body bytes) - counted on the host build of
@@ -125,21 +125,40 @@ def bpe_section(g, w, reqs, now, peak, sample=2048):
     tok, text = bpe.standin_tokenizer(151_643, cache_dir=os.path.join(ROOT, "tests", "_build"))
     tables = bpe.load_tokenizer(text)
     vocab_s = time.perf_counter() - t0
+    import torch
     g.load_bpe(tables)
     try:
         for k in range(N_WAVES):
             g.select_slot(k)
             g.stage_request(reqs[k])
+            g.stage_response(resps[k])
         g.set_profiling(True)
-        ms = []
+        ms, ms_resp = [], []
         for i in range(3 + 12):
             g.select_slot(i % N_WAVES)
             g.run_request(now)
-            now += STEP_S
             t = g.last_kernel_ms()
+            g.run_response(now + 1)
+            t2 = g.last_kernel_ms()
+            now += STEP_S
             if i >= 3:
                 ms.append(t[3])
+                ms_resp.append(t2[2])
         g.set_profiling(False)
+        # the whole step (request stage + admit + response stage) with both count columns on: BASELINE config 2 names the
+        # vocabulary, the reference itself counts nothing, so the line's `value` is the step without the side
+        # output and this is the same step with it
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(ext)
+        for i in range(12):
+            g.select_slot(i % N_WAVES)
+            g.run_request(now)
+            g.run_response(now + 1)
+            now += STEP_S
+        e1.record(ext)
+        torch.cuda.synchronize()
+        step_ms = e0.elapsed_time(e1) / 12
         g.select_slot(0)
         reqs[0].now_unix = now
         counts = g.handle_request_body(reqs[0]).bpe_count.copy()
@@ -170,6 +189,10 @@ def bpe_section(g, w, reqs, now, peak, sample=2048):
     t_s = float(np.mean(ms)) / 1e3
     counted = counts[counts != bpe.UNCOUNTED]
     return {"kernels": "bpe_scan_kernel + bpe_merge_kernel", "ms_per_wave": t_s * 1e3, "bodies_per_wave": int(rb.n),
+            "ms_per_response_wave": float(np.mean(ms_resp)), "response_bodies_per_wave": int(resps[0].n),
+            "step_with_counts": {"ms_per_step": step_ms, "value": rb.n / (step_ms / 1e3), "unit": "req/s per GPU",
+                                 "what": "request stage + limit_admit + response stage with the prompt and completion BPE counts on (12 steps, CUDA events, "
+                                         "waves rotating through the staging slots as in the timed region of `value`)"},
             "tokens_per_wave_0": int(counted.sum()), "tokens_per_s": float(counted.sum()) / t_s, "uncounted_rows_wave_0": int((counts == bpe.UNCOUNTED).sum()),
             "roofline": {"bound": "hbm", "achieved": alg / t_s / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t_s / 1e9 / peak,
                          "algorithmic_bytes_per_launch": alg,
@@ -394,6 +417,9 @@ def workload_config(args, world):
                         f"UTF-8 in the text: 0.3-1.7 KiB), {args.tenants} tenants "
                         f"(ArksToken+ArksQuota+ArksEndpoint each, rpm/tpm/rpd/tpd + 3-item quota), ~{RESP_BODY} B completion JSON with "
                         f"usage in three server dialects; request phase + response phase per step",
+            "token_counts": "the work the reference does per request: it counts no tokens itself (usage comes from the upstream's response, "
+                            "pkg/gateway/check.go:124-126); the on-device BPE count is a side output, off in `value` / `e2e` and on in "
+                            "`bpe.step_with_counts` (same step, both count columns, 151 k-merge vocabulary)",
             "tenants_per_gpu": args.tenants, "requests_per_wave_per_gpu": args.wave, "parallelism": f"tenant-sharded x{world}",
             "l2": f"inputs larger than L2: {N_WAVES} distinct waves rotate through staging slots (~{N_WAVES * (args.wave * (BODY + RESP_BODY)) >> 20} MiB)"}
 
@@ -774,7 +800,7 @@ def run_b200(args):
     # in the key and costs nothing else.
     if not args.no_bpe and world == 1:  # a one-GPU measurement: the scaling runs do not repeat it
         try:
-            out["bpe"] = bpe_section(g, w, reqs, now, peak)
+            out["bpe"] = bpe_section(g, w, reqs, resps, now, peak, ext)
         except Exception as e:  # noqa: BLE001
             out["bpe"] = {"error": f"{type(e).__name__}: {e}"[:400]}
     if shared_quota:
