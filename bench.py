@@ -200,7 +200,7 @@ def bpe_section(g, w, reqs, resps, now, peak, ext, sample=2048):
             "table_probes": {"full_table_slots_per_wave": scale * full, "full_table_bytes_per_wave": scale * full * 16,
                              "hot_table_slots_per_wave": scale * hot, "pretokens_per_wave": scale * pieces,
                              "what": "16-byte merge-table slots read, NOT counted as body bytes: full table = open-addressing hash in HBM (8 MB, L2-resident), "
-                                     "hot table = the 1 400 lowest-rank merges staged into shared memory by one bulk copy (TMA) per block; counted on the host "
+                                     "hot table = the 768 lowest-rank merges staged into shared memory by one bulk copy (TMA) per block; counted on the host "
                                      f"build of bpe.cuh over the first {n} bodies of wave 0 and scaled by body bytes"},
             "checked_against_tokenizers": {"rows": n, "uncounted": uncounted, "different": wrong},
             "vocabulary": f"stand-in byte-level BPE, {len(tables.left)} merges, Qwen2 pre-tokenizer, NFC flag {tables.flags} (the Qwen2.5 files are not on disk); built in {vocab_s:.1f} s"}
