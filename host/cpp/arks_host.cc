@@ -49,7 +49,8 @@ struct Block {
   uint8_t* bodies = nullptr;
   uint32_t *body_off = nullptr, *body_len = nullptr;
   uint8_t* tokens = nullptr;      // requests
-  uint32_t* token_off = nullptr;  // n + 1
+  uint32_t* token_off = nullptr;  // n + 1: entry r is written by the OWNER of row r (entry n by the dispatcher)
+  uint8_t* tok_len = nullptr;     // n: length of row r's token (<= 255), written by its owner
   uint64_t* rnd = nullptr;
   int32_t* qos = nullptr;         // responses
   uint32_t* gen = nullptr;
@@ -159,6 +160,7 @@ struct Batcher::Impl {
   bool submit_response(int32_t qos, uint32_t gen, std::string_view body, uint8_t flags, ResponseCallback cb, void* user, bool can_lead,
                        uint32_t precharged);
   int64_t last_now = INT64_MIN;  // batches never carry an earlier clock reading than their predecessor
+  std::vector<uint32_t> seg_token_off;  // dispatcher only: the token CSR of a segment (see the request submit)
 
   void alloc(Block& b, bool is_req) {
     const uint32_t m = opt.max_batch;
@@ -171,6 +173,7 @@ struct Batcher::Impl {
     if (is_req) {
       b.tokens = pinned<uint8_t>(tok_cap);
       b.token_off = pinned<uint32_t>(m + 1);
+      b.tok_len = new uint8_t[m];
       b.rnd = pinned<uint64_t>(m);
       b.rcb = new RequestCallback[m];
       b.reason = new uint8_t[m]; b.detail = new uint8_t[m]; b.rflags = new uint8_t[m];
@@ -358,7 +361,17 @@ struct Batcher::Impl {
       arks_request_batch rb{};
       rb.n = n; rb.bodies = b.bodies; rb.body_off = b.body_off + lo; rb.body_len = b.body_len + lo;
       rb.bodies_bytes = span_end(b, f.req.hi);  // offsets stay relative to the block: rows in front of a segment ride along
-      rb.tokens = b.tokens; rb.token_off = b.token_off + lo; rb.pick_rand = b.rnd + lo; rb.now_unix = now;
+      rb.tokens = b.tokens; rb.pick_rand = b.rnd + lo; rb.now_unix = now;
+      if (lo == 0 && f.req.hi == b.n) {
+        rb.token_off = b.token_off;  // the whole block: every entry is written (the last one by the dispatcher when it closed it)
+      } else {
+        // A segment: entry `hi` of the block's CSR belongs to the row BEHIND the segment, whose owner may have reserved it and
+        // not written a byte yet (that is why the block was cut). The end of the segment's last token is its own start + length.
+        seg_token_off.resize((size_t)n + 1);
+        memcpy(seg_token_off.data(), b.token_off + lo, (size_t)n * 4);
+        seg_token_off[n] = b.token_off[f.req.hi - 1] + b.tok_len[f.req.hi - 1];
+        rb.token_off = seg_token_off.data();  // copied by the library before arks_submit_request_async returns
+      }
       f.rc_req = arks_submit_request_async(ctx, &rb);
     }
     if (f.resp.b) {
@@ -590,9 +603,11 @@ bool Batcher::Impl::submit_request(std::string_view token, std::string_view body
   uint32_t row;
   size_t off, toff;
   if (!I.reserve(I.open_req, need, token.size(), &b, &row, &off, &toff)) return false;
+  if (const char* e = g_test_stall_env) test_stall(e, row);  // the worst moment to lose the core: the row is reserved, nothing of it is written
   b->body_off[row] = (uint32_t)off;
   b->body_len[row] = (uint32_t)body.size();
   b->token_off[row] = (uint32_t)toff;
+  b->tok_len[row] = (uint8_t)token.size();
   b->rnd[row] = pick_rand;
   b->rcb[row] = cb;
   b->user[row] = user;
@@ -600,7 +615,6 @@ bool Batcher::Impl::submit_request(std::string_view token, std::string_view body
   memcpy(b->bodies + off, body.data(), body.size());
   memset(b->bodies + off + body.size(), 0, need - body.size());
   memcpy(b->tokens + toff, token.data(), token.size());
-  if (const char* e = g_test_stall_env) test_stall(e, row);
   b->ready[row].store(1, std::memory_order_release);
   b->filled.fetch_add(1, std::memory_order_release);
   if (lead) {

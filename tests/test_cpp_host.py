@@ -249,7 +249,9 @@ import test_cpp_host as T
 from arks_b200 import traffic
 from arks_b200.abi import RequestBatch
 w = traffic.Workload(n_tenants=40, seed=11)
-eng = T.CpuEngine(w.tables, max_batch=512, max_bytes=2 << 20)
+# linger: the leader of a cycle gives the other streams 200 us to join it. Without it the CPU stand-in of the device is so fast
+# that on an idle box every request can end up as its own one-row cycle, and there is no row 2 to be late
+eng = T.CpuEngine(w.tables, max_batch=512, max_bytes=2 << 20, linger_us=200)
 eng.b.set_fixed_clock(T.NOW)
 req = w.request_batch(3000, T.NOW, seed=5, stream_frac=0.2, noise_frac=0.1)
 dec, lat, wall = eng.b.run_requests(req, threads=24)
@@ -278,6 +280,43 @@ def test_a_row_owner_that_lost_its_core_does_not_hold_the_batch(tmp_path):
     assert r["max_us"] >= 20000                     # the late rows waited for their owner ...
     assert r["p99_us"] < 10000, r                   # ... and nobody else did: without the cut every row of those blocks and of
     #                                                 the blocks queued behind them would have waited the 20 ms too
+
+
+STRAGGLER_TOKENS = r'''
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.environ["ARKS_ROOT"]); sys.path.insert(0, os.path.join(os.environ["ARKS_ROOT"], "tests"))
+import test_cpp_host as T
+from arks_b200.abi import RequestBatch
+from arks_b200.tables import Tables, simple_endpoint, simple_token
+rng = np.random.default_rng(3)
+names = ["sk-" + "x" * int(rng.integers(1, 60)) + str(i) for i in range(30)]   # bearer tokens of 5 .. 65 bytes
+t = Tables([simple_token("u%d" % i, "ns", names[i], "m", [("rpm", 10**6)]) for i in range(30)], [], [simple_endpoint("m", "ns")])
+eng = T.CpuEngine(t, max_batch=64, max_bytes=1 << 20, linger_us=200)  # (see STRAGGLER)
+eng.b.set_fixed_clock(T.NOW)
+who = rng.integers(0, 30, 4000)
+req = RequestBatch.from_lists([b'{"model":"m","messages":[]}'] * 4000, [names[k].encode() for k in who], T.NOW)
+dec, lat, wall = eng.b.run_requests(req, threads=16)
+st = eng.b.stats()
+assert (dec["reason"] == 0).all(), np.unique(dec["reason"], return_counts=True)   # every row was decided on ITS token
+assert (dec["token"] == who).all()
+T.replay_requests(t, req, dec)
+print(json.dumps({"late_rows": st["late_rows"], "requests": st["requests"]}))
+eng.close()
+'''
+
+
+def test_the_rows_next_to_a_late_row_keep_their_own_tokens(tmp_path):
+    """Bearer tokens travel as one CSR (token_off): the end of a row's token is the START of the next row's. When that next row's
+    owner is late - it has reserved the row and written nothing yet - the segment in front of it must not read the neighbour's
+    unwritten entry: tokens of different lengths, an owner stalled right after its reservation in every 7th block."""
+    script = tmp_path / "straggler_tokens.py"
+    script.write_text(STRAGGLER_TOKENS)
+    env = dict(os.environ, ARKS_ROOT=ROOT, ARKS_HOST_TEST_STALL="3:3000:7")
+    out = subprocess.run([os.sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["requests"] == 4000 and r["late_rows"] > 0
 
 
 def test_precharge_estimate_travels_with_the_stream_cpu():
