@@ -265,21 +265,22 @@ eng.close()
 
 
 def test_a_row_owner_that_lost_its_core_does_not_hold_the_batch(tmp_path):
-    """ARKS_HOST_TEST_STALL makes the owner of row 2 of every 40th request block sleep 20 ms between reserving its row and filling
+    """ARKS_HOST_TEST_STALL makes the owner of row 2 of every 40th request block sleep 100 ms between reserving its row and filling
     it (what a preempted / throttled stream thread looks like to the dispatcher). The rows around it must go ahead without
     it: the block is cut into segments, the late row follows alone, every decision still replays through the oracle in
-    (cycle, index) order, and only the late rows themselves see the 20 ms."""
+    (cycle, index) order, and only the late rows themselves see the 100 ms (long against what a loaded test box adds to
+    everybody: with eight busy loops next to it the p99 of this run was 16 ms)."""
     script = tmp_path / "straggler.py"
     script.write_text(STRAGGLER)
-    env = dict(os.environ, ARKS_ROOT=ROOT, ARKS_HOST_TEST_STALL="2:20000:40")
+    env = dict(os.environ, ARKS_ROOT=ROOT, ARKS_HOST_TEST_STALL="2:100000:40")
     out = subprocess.run([os.sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["requests"] == 3000
     assert r["late_rows"] > 0                       # blocks were cut around their late row
-    assert r["max_us"] >= 20000                     # the late rows waited for their owner ...
-    assert r["p99_us"] < 10000, r                   # ... and nobody else did: without the cut every row of those blocks and of
-    #                                                 the blocks queued behind them would have waited the 20 ms too
+    assert r["max_us"] >= 100000                    # the late rows waited for their owner ...
+    assert r["p99_us"] < 50000, r                   # ... and nobody else did: without the cut every row of those blocks and of
+    #                                                 the blocks queued behind them would have waited the 100 ms too
 
 
 STRAGGLER_TOKENS = r'''
