@@ -25,8 +25,9 @@
  *   - return value: 0 ok, negative `arks_status`. Per-request outcomes only via the result arrays.
  *   - there is no CPU fallback: without a CUDA device `arks_create` fails with ARKS_E_NO_DEVICE.
  *   - threads: a context has ONE batch thread (submit / stage / run / select, arks_commit_tables, arks_update_endpoint_weights)
- *     and may have one config thread (arks_upsert_*, arks_delete_*, arks_config_prepare, arks_prepare_tables, arks_find_*:
- *     they never touch the generation the batch thread reads). The snapshot / sync calls (arks_snapshot_*,
+ *     and may have one config thread (arks_upsert_*, arks_delete_*, arks_config_prepare, arks_prepare_tables: they never
+ *     touch the generation the batch thread reads; arks_find_*: they read the current generation's keys under the lock a
+ *     commit holds while it swaps them). The snapshot / sync calls (arks_snapshot_*,
  *     arks_sync_quota_usage, arks_set / incr_quota_usage) are ordered on the compute stream and may come from a third thread,
  *     but not while arks_commit_tables runs (host/cpp's Batcher and arks_b200/provider.py arrange exactly that).
  */
