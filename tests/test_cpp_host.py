@@ -104,7 +104,11 @@ def replay_responses(o, batch: ResponseBatch, dec):
 
 def run_batcher_checks(make_engine):
     w = traffic.Workload(n_tenants=40, seed=11)  # few tenants, many requests: limits are crossed inside cycles
-    eng = make_engine(w.tables, max_batch=512, max_bytes=2 << 20)
+    # over the CPU stand-in a cycle takes a microsecond or two: on an idle box 48 streams can each find the batcher idle and run
+    # their own one-row cycle for the whole test. The leader's linger (a product option) makes them share cycles there; on the
+    # GPU a cycle is ~50 us of device time and they share without it
+    extra = {"linger_us": 100} if make_engine is CpuEngine else {}
+    eng = make_engine(w.tables, max_batch=512, max_bytes=2 << 20, **extra)
     try:
         eng.b.set_fixed_clock(NOW)
         req = w.request_batch(6000, NOW, seed=5, stream_frac=0.2, noise_frac=0.1)
